@@ -1119,4 +1119,21 @@ void orc_mie_rigid_sphere(double k, double radius, int num_terms, const double* 
     }
 }
 
+// sphere_rcs_3d(): solutions_3d.rs:264-275
+double orc_sphere_rcs(double k, double radius, int num_terms) {
+    const double ka = k * radius;
+    double rcs = 0.0;
+    for (int nn = 0; nn < num_terms; ++nn) {
+        double nf = (double)nn;
+        double jn = sph_j(nn, ka), yn = sph_y(nn, ka);
+        double jm1 = nn > 0 ? sph_j(nn - 1, ka) : std::cos(ka) / ka;
+        double jp = jm1 - (nf + 1.0) / ka * jn;
+        double ym1 = nn > 0 ? sph_y(nn - 1, ka) : -std::sin(ka) / ka;
+        double yp = ym1 - (nf + 1.0) / ka * yn;
+        cplx a = C(jp, 0.0) / C(jp, yp);
+        rcs += (double)(2 * nn + 1) * norm_sqr(a);
+    }
+    return 4.0 * PI * rcs / (k * k);
+}
+
 }  // extern "C"

@@ -54,7 +54,7 @@ def lib():
         _lib.orc_dg_dn_sign.restype = C.c_double
         _lib.orc_count_dofs.restype = C.c_uint64
         _lib.orc_row_sum_correction.restype = C.c_double
-        for f in ("orc_spherical_bessel_j", "orc_spherical_bessel_y", "orc_legendre_p"):
+        for f in ("orc_spherical_bessel_j", "orc_spherical_bessel_y", "orc_legendre_p", "orc_sphere_rcs"):
             getattr(_lib, f).restype = C.c_double
     return _lib
 
@@ -286,6 +286,10 @@ def spherical_bessel_y(n, x):
 
 def legendre_p(n, x):
     return float(lib().orc_legendre_p(C.c_int(n), C.c_double(x)))
+
+
+def sphere_rcs(k, radius, num_terms):
+    return float(lib().orc_sphere_rcs(C.c_double(k), C.c_double(radius), C.c_int(num_terms)))
 
 
 def l2_relative(analytical, bem) -> float:
