@@ -1,0 +1,164 @@
+/* bemb200.h -- C ABI of libbemb200: B200 (sm_100a) backend for the dense Helmholtz BEM
+ * assemble + GMRES path of math-bem / math-solvers.
+ *
+ * Every entry point below is what a Rust `extern "C"` block (or cgo / ctypes) binds;
+ * each one names the reference interface it replaces (paths relative to the
+ * reference repository).  Conventions:
+ *   - plain pointers and sizes only; complex numbers are interleaved (re, im) doubles,
+ *     layout-identical to num_complex::Complex64 and cuDoubleComplex;
+ *   - inputs are COPIED during the call, no pointer is retained after return;
+ *   - every function returns 0 on success or a negative BEMB200_E* code and never
+ *     throws/aborts; bemb200_last_error() gives the message of the last failure;
+ *   - handles are opaque and owned by the library; free them with the matching call;
+ *   - there is no CPU fallback: without a CUDA device every compute call fails with
+ *     BEMB200_ENODEVICE.
+ */
+#ifndef BEMB200_H
+#define BEMB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BEMB200_OK 0
+#define BEMB200_EINVAL (-1)     /* bad argument / shape mismatch (the reference panics) */
+#define BEMB200_ENODEVICE (-2)  /* no usable CUDA device */
+#define BEMB200_ECUDA (-3)      /* CUDA runtime error, see bemb200_last_error */
+#define BEMB200_ENOMEM (-4)     /* device or host allocation failed */
+#define BEMB200_ENCCL (-5)      /* NCCL error / NCCL not loadable */
+#define BEMB200_EUNSUPPORTED (-6)
+
+typedef struct bemb200_ctx bemb200_ctx;
+typedef struct bemb200_staged_mesh bemb200_staged_mesh;
+typedef struct bemb200_matrix bemb200_matrix;
+
+/* SoA view of `&[Element]` + `nodes: Array2<f64>` (math-bem/src/core/types.rs:329-351,
+ * 371-373).  One DOF per non-evaluation element (types.rs:359-363). */
+typedef struct bemb200_mesh {
+    uint64_t n_nodes;
+    uint64_t n_elem;
+    const double* nodes;      /* [n_nodes*3]  Mesh.nodes, row-major                         */
+    const uint32_t* conn;     /* [n_elem*4]   Element.connectivity, Tri3 padded 0xFFFFFFFF  */
+    const uint8_t* etype;     /* [n_elem]     3 = Tri3, 4 = Quad4 (Element.element_type)     */
+    const double* center;     /* [n_elem*3]   Element.center  (collocation point)           */
+    const double* normal;     /* [n_elem*3]   Element.normal  (n_x; may be flipped outward) */
+    const double* area;       /* [n_elem]     Element.area    (drives the subdivision test) */
+    const int32_t* bc_type;   /* [n_elem]     get_bc_type_and_value(): 0 velocity, 1 pressure, 2 transfer (tbem.rs:234-244) */
+    const uint8_t* bc_len;    /* [n_elem]     number of per-node BC values supplied (1..4)  */
+    const double* bc_val;     /* [n_elem*4*2] per-node complex BC values                     */
+    const uint32_t* dof;      /* [n_elem]     Element.dof_addresses[0]                       */
+    const uint8_t* is_eval;   /* [n_elem]     ElementProperty::Evaluation (skipped)          */
+} bemb200_mesh;
+
+/* PhysicsParams (types.rs:16-58, 216-218) -- the four fields the path reads. */
+typedef struct bemb200_physics {
+    double wave_number;
+    double harmonic_factor; /* +1 => exp(+ikr) */
+    double tau;             /* +1 exterior, -1 interior */
+    double gamma;           /* 1.0 */
+} bemb200_physics;
+
+/* GmresSolution minus x (math-solvers/src/iterative/gmres.rs:74-85). */
+typedef struct bemb200_gmres_info {
+    uint64_t iterations; /* Arnoldi matvecs (gmres.rs:178) */
+    uint64_t restarts;
+    double residual;     /* relative to ||b|| */
+    int32_t converged;
+} bemb200_gmres_info;
+
+typedef struct bemb200_assembly_stats {
+    uint64_t near_pairs;    /* pairs re-integrated with adaptive subdivision */
+    uint64_t special_pairs; /* pairs through the generic path (pressure BC, non-zero BC, warped Quad4) */
+    uint64_t far_kernel_launches;
+    uint64_t total_launches;
+    double far_ms;   /* device time of the far-field kernel(s), CUDA events */
+    double total_ms; /* device time of the whole assembly */
+} bemb200_assembly_stats;
+
+/* ---- context -------------------------------------------------------------------- */
+int bemb200_device_count(void);
+/* single-GPU context on `device` */
+int bemb200_ctx_create(int device, bemb200_ctx** out);
+/* one rank of a row-sharded job: one process per GPU; `nccl_id` is the 128-byte
+ * ncclUniqueId produced by bemb200_nccl_unique_id() on rank 0 and distributed by the
+ * host program (MPI, torch.distributed, a file ...). */
+int bemb200_nccl_unique_id(uint8_t out[128]);
+int bemb200_ctx_create_dist(int device, int rank, int nranks, const uint8_t nccl_id[128], bemb200_ctx** out);
+void bemb200_ctx_destroy(bemb200_ctx* ctx);
+const char* bemb200_last_error(const bemb200_ctx* ctx); /* ctx may be NULL: last global error */
+/* canonical row partition used by the distributed solver: rank r owns
+ * [r*ceil(n/nranks), min(n,(r+1)*ceil(n/nranks))) */
+void bemb200_partition(uint64_t n, int nranks, int rank, uint64_t* row_begin, uint64_t* row_end);
+
+/* ---- assembly: replaces build_tbem_system_with_beta (assembly/tbem.rs:96-222) ------ */
+/* Frequency-independent staging (gather to DOF order, quadrature points, ratio-test
+ * data); reuse across a frequency sweep. */
+int bemb200_mesh_stage(bemb200_ctx* ctx, const bemb200_mesh* mesh, bemb200_staged_mesh** out);
+void bemb200_staged_mesh_free(bemb200_staged_mesh* sm);
+uint64_t bemb200_staged_num_dofs(const bemb200_staged_mesh* sm);
+/* Assemble matrix rows [row_begin,row_end) (all columns) and the matching rhs entries.
+ * If *inout is NULL a matrix is allocated, otherwise the handle is reused (same shape
+ * required). */
+int bemb200_assemble_staged(bemb200_ctx* ctx, const bemb200_staged_mesh* sm, const bemb200_physics* phys, double beta_re,
+                            double beta_im, uint64_t row_begin, uint64_t row_end, bemb200_matrix** inout);
+/* stage + assemble in one call (the drop-in for one build_tbem_system_with_beta call) */
+int bemb200_assemble(bemb200_ctx* ctx, const bemb200_mesh* mesh, const bemb200_physics* phys, double beta_re,
+                     double beta_im, uint64_t row_begin, uint64_t row_end, bemb200_matrix** out);
+int bemb200_assembly_stats_get(const bemb200_matrix* m, bemb200_assembly_stats* out);
+/* dg_dn_sign heuristic of tbem.rs:108-123 for this mesh and wave number */
+double bemb200_dg_dn_sign(const bemb200_staged_mesh* sm, double wave_number);
+
+/* ---- matrix handle: TbemSystem (tbem.rs:13-31) / DenseOperator (solver/fmm_interface.rs:25-52) */
+/* wrap an existing host matrix: DenseOperator::new(Array2) -- rows [row_begin,row_end) of an n x n_cols matrix */
+int bemb200_matrix_from_host(bemb200_ctx* ctx, const double* a_rows, uint64_t n_rows_global, uint64_t n_cols,
+                             uint64_t row_begin, uint64_t row_end, bemb200_matrix** out);
+void bemb200_matrix_free(bemb200_matrix* m);
+uint64_t bemb200_num_rows(const bemb200_matrix* m);   /* LinearOperator::num_rows (global) */
+uint64_t bemb200_num_cols(const bemb200_matrix* m);   /* LinearOperator::num_cols */
+uint64_t bemb200_local_row_begin(const bemb200_matrix* m);
+uint64_t bemb200_local_row_end(const bemb200_matrix* m);
+/* copy local rows [row_begin,row_end) (must lie inside the local slab) to the host */
+int bemb200_matrix_download(const bemb200_matrix* m, uint64_t row_begin, uint64_t row_end, double* out);
+/* rhs entries of the local rows (TbemSystem.rhs) */
+int bemb200_rhs_download(const bemb200_matrix* m, double* out);
+/* apply_row_sum_correction (tbem.rs:500-520); returns |sum of all row sums| / n in *avg */
+int bemb200_row_sum_correction(bemb200_matrix* m, double* avg);
+
+/* LinearOperator::apply / apply_transpose (math-solvers/src/traits.rs:316-364):
+ * x has num_cols entries, y has num_rows entries (all ranks receive the full y). */
+int bemb200_apply(const bemb200_matrix* m, const double* x, double* y);
+int bemb200_apply_transpose(const bemb200_matrix* m, const double* x, double* y);
+/* same with DEVICE pointers (x: num_cols, y: num_rows complex128), asynchronous on the
+ * context stream followed by a stream synchronise */
+int bemb200_apply_device(const bemb200_matrix* m, const double* x_dev, double* y_dev);
+
+/* gmres / gmres_with_guess (math-solvers/src/iterative/gmres.rs:96-277): restarted
+ * GMRES(m), modified Gram-Schmidt, complex Givens; `max_iterations` counts restart
+ * cycles, info->iterations counts Arnoldi matvecs; residual is relative to ||b||;
+ * ||b|| < 1e-15 returns x0 at once; breakdown threshold 1e-14.  b, x0 (may be NULL),
+ * x_out: num_rows complex128 on the HOST. */
+int bemb200_gmres(const bemb200_matrix* m, const double* b, const double* x0, uint32_t max_iterations, uint32_t restart,
+                  double tolerance, double* x_out, bemb200_gmres_info* info);
+/* same with DEVICE pointers (b_dev, x0_dev or NULL, x_dev) */
+int bemb200_gmres_device(const bemb200_matrix* m, const double* b_dev, const double* x0_dev, uint32_t max_iterations,
+                         uint32_t restart, double tolerance, double* x_dev, bemb200_gmres_info* info);
+/* number of kernels launched and device milliseconds spent inside the zgemv kernel by
+ * the last bemb200_gmres* / bemb200_apply* call on this matrix */
+int bemb200_solver_stats(const bemb200_matrix* m, uint64_t* kernel_launches, double* matvec_ms, uint64_t* matvecs);
+
+/* ---- measurement helpers ----------------------------------------------------------- */
+/* register-resident DFMA peak of this device in TFLOP/s (2 flop per DFMA) */
+int bemb200_measure_fp64_peak(bemb200_ctx* ctx, double* tflops);
+/* max abs error of the far kernel's sincos / rsqrt against the CUDA math library over
+ * `n` sample arguments in [0, xmax] */
+int bemb200_selftest_math(bemb200_ctx* ctx, uint64_t n, double xmax, double* sincos_err, double* rsqrt_relerr);
+/* device pointer of the local matrix slab / device stream, for callers that own a CUDA
+ * context in the same process (bench harness) */
+void* bemb200_matrix_device_ptr(const bemb200_matrix* m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BEMB200_H */

@@ -1,0 +1,327 @@
+"""Host-side mirror of the reference's operator interface for the assemble + GMRES path,
+over the C ABI of libbemb200 (no torch types, no CPU fallback).
+
+Reference interface (same names, argument meaning, error behaviour):
+
+* ``build_tbem_system{,_with_beta,_scaled,_bounded}`` -> ``TbemSystem``   math-bem/src/core/assembly/tbem.rs:13-101
+* ``apply_row_sum_correction`` / ``build_tbem_system_corrected``          tbem.rs:500-534
+* ``DenseOperator`` (``LinearOperator``: num_rows/num_cols/apply/apply_transpose/apply_hermitian)
+                                                                          math-bem/src/core/solver/fmm_interface.rs:25-52,
+                                                                          math-solvers/src/traits.rs:316-364
+* ``GmresConfig`` / ``GmresSolution`` / ``gmres`` / ``gmres_with_guess`` / ``solve_gmres``
+                                                                          math-solvers/src/iterative/gmres.rs:16-36,74-105,
+                                                                          fmm_interface.rs:378-384
+
+Differences forced by the device: ``TbemSystem.matrix`` stays on the GPU behind an opaque
+handle (a 120k x 120k complex128 matrix is 237 GB, it can never be an ``Array2``); rows can be
+fetched with ``matrix_rows``.  Shape mismatches raise (the reference panics).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import _capi
+from .mesh import Mesh
+from .types import PhysicsParams
+
+
+class Context:
+    """One GPU (optionally one rank of a row-sharded job: one process per GPU)."""
+
+    def __init__(self, device: int = 0, rank: int = 0, nranks: int = 1, nccl_id: Optional[bytes] = None):
+        self._lib = _capi.lib()
+        self._h = C.c_void_p()
+        if nranks > 1:
+            assert nccl_id is not None and len(nccl_id) == 128
+            buf = (C.c_uint8 * 128).from_buffer_copy(nccl_id)
+            _capi.check(self._lib.bemb200_ctx_create_dist(device, rank, nranks, C.cast(buf, C.c_void_p), C.byref(self._h)))
+        else:
+            _capi.check(self._lib.bemb200_ctx_create(device, C.byref(self._h)))
+        self.device, self.rank, self.nranks = device, rank, nranks
+
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        _capi.check(_capi.lib().bemb200_nccl_unique_id(C.cast(buf, C.c_void_p)))
+        return bytes(buf)
+
+    def partition(self, n: int):
+        b, e = C.c_uint64(), C.c_uint64()
+        self._lib.bemb200_partition(n, self.nranks, self.rank, C.byref(b), C.byref(e))
+        return int(b.value), int(e.value)
+
+    def measure_fp64_peak(self) -> float:
+        t = C.c_double()
+        _capi.check(self._lib.bemb200_measure_fp64_peak(self._h, C.byref(t)), self._h)
+        return float(t.value)
+
+    def selftest_math(self, n: int = 1 << 22, xmax: float = 200.0):
+        a, b = C.c_double(), C.c_double()
+        _capi.check(self._lib.bemb200_selftest_math(self._h, n, xmax, C.byref(a), C.byref(b)), self._h)
+        return float(a.value), float(b.value)
+
+    def close(self):
+        if self._h:
+            self._lib.bemb200_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx: Optional[Context] = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+class StagedMesh:
+    """Frequency-independent device copy of a mesh (reused across a sweep)."""
+
+    def __init__(self, mesh: Mesh, ctx: Optional[Context] = None):
+        self.ctx = ctx or default_context()
+        self._lib = _capi.lib()
+        self._h = C.c_void_p()
+        cm = _capi.cmesh(mesh)
+        _capi.check(self._lib.bemb200_mesh_stage(self.ctx._h, C.byref(cm), C.byref(self._h)), self.ctx._h)
+        self.num_dofs = int(self._lib.bemb200_staged_num_dofs(self._h))
+        self.nbytes_host = _capi.mesh_nbytes(mesh)
+
+    def dg_dn_sign(self, wave_number: float) -> float:
+        return float(self._lib.bemb200_dg_dn_sign(self._h, wave_number))
+
+    def close(self):
+        if self._h:
+            self._lib.bemb200_staged_mesh_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _cphys(physics: PhysicsParams) -> _capi.CPhysics:
+    return _capi.CPhysics(physics.wave_number, physics.harmonic_factor, physics.tau, physics.gamma())
+
+
+class DeviceMatrix:
+    """Opaque handle of the local row slab of a dense complex128 operator on the GPU."""
+
+    def __init__(self, ctx: Context, handle: C.c_void_p):
+        self.ctx = ctx
+        self._lib = _capi.lib()
+        self._h = handle
+
+    @property
+    def shape(self):
+        return int(self._lib.bemb200_num_rows(self._h)), int(self._lib.bemb200_num_cols(self._h))
+
+    @property
+    def local_rows(self):
+        return int(self._lib.bemb200_local_row_begin(self._h)), int(self._lib.bemb200_local_row_end(self._h))
+
+    def rows(self, row_begin: Optional[int] = None, row_end: Optional[int] = None) -> np.ndarray:
+        lb, le = self.local_rows
+        row_begin = lb if row_begin is None else row_begin
+        row_end = le if row_end is None else row_end
+        out = np.empty((row_end - row_begin, self.shape[1]), dtype=np.complex128)
+        _capi.check(self._lib.bemb200_matrix_download(self._h, row_begin, row_end, _capi.ptr(out)), self.ctx._h)
+        return out
+
+    def rhs(self) -> np.ndarray:
+        lb, le = self.local_rows
+        out = np.empty(le - lb, dtype=np.complex128)
+        _capi.check(self._lib.bemb200_rhs_download(self._h, _capi.ptr(out)), self.ctx._h)
+        return out
+
+    def assembly_stats(self) -> dict:
+        st = _capi.CAssemblyStats()
+        _capi.check(self._lib.bemb200_assembly_stats_get(self._h, C.byref(st)), self.ctx._h)
+        return {k: getattr(st, k) for k, _ in st._fields_}
+
+    def solver_stats(self) -> dict:
+        a, b, c = C.c_uint64(), C.c_double(), C.c_uint64()
+        _capi.check(self._lib.bemb200_solver_stats(self._h, C.byref(a), C.byref(b), C.byref(c)), self.ctx._h)
+        return dict(kernel_launches=int(a.value), matvec_ms=float(b.value), matvecs=int(c.value))
+
+    def device_ptr(self) -> int:
+        return int(self._lib.bemb200_matrix_device_ptr(self._h) or 0)
+
+    def close(self):
+        if self._h:
+            self._lib.bemb200_matrix_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+@dataclass
+class TbemSystem:
+    """tbem.rs:13-20.  ``matrix`` is device resident; ``rhs`` holds the local rows' entries."""
+
+    matrix: DeviceMatrix
+    rhs: np.ndarray
+    num_dofs: int
+
+
+def build_tbem_system_with_beta(elements: Mesh | StagedMesh, physics: PhysicsParams, beta: complex,
+                                ctx: Optional[Context] = None, rows=None, reuse: Optional[TbemSystem] = None) -> TbemSystem:
+    """tbem.rs:96-222.  ``elements`` carries nodes + elements (SoA).  ``rows=(r0, r1)`` assembles
+    one row block (default: this rank's canonical block, i.e. everything on one GPU)."""
+    lib = _capi.lib()
+    staged = elements if isinstance(elements, StagedMesh) else StagedMesh(elements, ctx)
+    ctx = staged.ctx
+    n = staged.num_dofs
+    r0, r1 = rows if rows is not None else ctx.partition(n)
+    h = reuse.matrix._h if reuse is not None else C.c_void_p()
+    ph = _cphys(physics)
+    beta = complex(beta)
+    _capi.check(lib.bemb200_assemble_staged(ctx._h, staged._h, C.byref(ph), beta.real, beta.imag, r0, r1, C.byref(h)), ctx._h)
+    mat = reuse.matrix if reuse is not None else DeviceMatrix(ctx, h)
+    return TbemSystem(matrix=mat, rhs=mat.rhs(), num_dofs=n)
+
+
+def build_tbem_system(elements, physics: PhysicsParams, **kw) -> TbemSystem:  # tbem.rs:45-51
+    return build_tbem_system_with_beta(elements, physics, physics.burton_miller_beta(), **kw)
+
+
+def build_tbem_system_scaled(elements, physics: PhysicsParams, scale: float, **kw) -> TbemSystem:  # tbem.rs:85-93
+    return build_tbem_system_with_beta(elements, physics, physics.burton_miller_beta_scaled(scale), **kw)
+
+
+def build_tbem_system_bounded(elements, physics: PhysicsParams, avg_element_size: float, **kw) -> TbemSystem:  # tbem.rs:64-72
+    return build_tbem_system_with_beta(elements, physics, physics.burton_miller_beta_optimal(avg_element_size), **kw)
+
+
+def apply_row_sum_correction(system: TbemSystem) -> float:  # tbem.rs:500-520
+    avg = C.c_double()
+    _capi.check(_capi.lib().bemb200_row_sum_correction(system.matrix._h, C.byref(avg)), system.matrix.ctx._h)
+    return float(avg.value)
+
+
+def build_tbem_system_corrected(elements, physics: PhysicsParams, **kw):  # tbem.rs:526-534
+    system = build_tbem_system(elements, physics, **kw)
+    return system, apply_row_sum_correction(system)
+
+
+class DenseOperator:
+    """fmm_interface.rs:25-52: ``DenseOperator::new(matrix)`` + the ``LinearOperator`` trait."""
+
+    def __init__(self, matrix, ctx: Optional[Context] = None):
+        if isinstance(matrix, TbemSystem):
+            matrix = matrix.matrix
+        if isinstance(matrix, DeviceMatrix):
+            self.matrix = matrix
+        else:
+            a = np.ascontiguousarray(matrix, dtype=np.complex128)
+            if a.ndim != 2:
+                raise ValueError("DenseOperator needs a 2-D matrix")
+            ctx = ctx or default_context()
+            r0, r1 = ctx.partition(a.shape[0])
+            h = C.c_void_p()
+            loc = np.ascontiguousarray(a[r0:r1])
+            _capi.check(_capi.lib().bemb200_matrix_from_host(ctx._h, _capi.ptr(loc), a.shape[0], a.shape[1], r0, r1, C.byref(h)), ctx._h)
+            self.matrix = DeviceMatrix(ctx, h)
+        self._lib = _capi.lib()
+
+    def num_rows(self) -> int:
+        return self.matrix.shape[0]
+
+    def num_cols(self) -> int:
+        return self.matrix.shape[1]
+
+    def is_square(self) -> bool:
+        return self.num_rows() == self.num_cols()
+
+    def apply(self, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.complex128)
+        if x.shape != (self.num_cols(),):
+            raise ValueError(f"apply: x has shape {x.shape}, operator has {self.num_cols()} columns")
+        y = np.empty(self.num_rows(), dtype=np.complex128)
+        _capi.check(self._lib.bemb200_apply(self.matrix._h, _capi.ptr(x), _capi.ptr(y)), self.matrix.ctx._h)
+        return y
+
+    def apply_transpose(self, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.complex128)
+        if x.shape != (self.num_rows(),):
+            raise ValueError(f"apply_transpose: x has shape {x.shape}, operator has {self.num_rows()} rows")
+        y = np.empty(self.num_cols(), dtype=np.complex128)
+        _capi.check(self._lib.bemb200_apply_transpose(self.matrix._h, _capi.ptr(x), _capi.ptr(y)), self.matrix.ctx._h)
+        return y
+
+    def apply_hermitian(self, x: np.ndarray) -> np.ndarray:  # traits.rs:331-358 default: conj(A^T conj(x))
+        return np.conj(self.apply_transpose(np.conj(x)))
+
+
+@dataclass
+class GmresConfig:
+    """gmres.rs:16-36 (defaults of ``GmresConfig<f64>``)."""
+
+    max_iterations: int = 100  # restart CYCLES
+    restart: int = 30
+    tolerance: float = 1e-6
+    print_interval: int = 0
+
+    @staticmethod
+    def for_small_problems() -> "GmresConfig":  # gmres.rs:52-59
+        return GmresConfig(max_iterations=50, restart=50, tolerance=1e-8)
+
+    @staticmethod
+    def with_restart(restart: int) -> "GmresConfig":  # gmres.rs:62-70
+        return GmresConfig(restart=restart)
+
+
+@dataclass
+class GmresSolution:
+    """gmres.rs:74-85."""
+
+    x: np.ndarray
+    iterations: int
+    restarts: int
+    residual: float
+    converged: bool
+
+
+def gmres_with_guess(operator: DenseOperator, b: np.ndarray, x0: Optional[np.ndarray], config: GmresConfig) -> GmresSolution:
+    """gmres.rs:105-277 on the device."""
+    b = np.ascontiguousarray(b, dtype=np.complex128)
+    n = operator.num_rows()
+    if b.shape != (n,):
+        raise ValueError(f"gmres: b has shape {b.shape}, operator has {n} rows")
+    x0a = None
+    if x0 is not None:
+        x0a = np.ascontiguousarray(x0, dtype=np.complex128)
+        if x0a.shape != (n,):
+            raise ValueError("gmres: x0 has the wrong length")
+    x = np.empty(n, dtype=np.complex128)
+    info = _capi.CGmresInfo()
+    _capi.check(_capi.lib().bemb200_gmres(operator.matrix._h, _capi.ptr(b), _capi.ptr(x0a) if x0a is not None else None,
+                                          config.max_iterations, config.restart, config.tolerance, _capi.ptr(x), C.byref(info)),
+                operator.matrix.ctx._h)
+    return GmresSolution(x=x, iterations=int(info.iterations), restarts=int(info.restarts), residual=float(info.residual),
+                         converged=bool(info.converged))
+
+
+def gmres(operator: DenseOperator, b: np.ndarray, config: GmresConfig) -> GmresSolution:  # gmres.rs:96-102
+    return gmres_with_guess(operator, b, None, config)
+
+
+def solve_gmres(operator: DenseOperator, b: np.ndarray, config: GmresConfig) -> GmresSolution:  # fmm_interface.rs:378-384
+    return gmres(operator, b, config)

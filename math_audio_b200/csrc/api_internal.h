@@ -1,0 +1,55 @@
+// Handle definitions behind the opaque C types of include/bemb200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/bemb200.h"
+#include "internal.h"
+
+struct bemb200_ctx {
+    int device = 0;
+    int rank = 0, nranks = 1;
+    cudaStream_t stream = nullptr;
+    void* nccl_comm = nullptr;  // ncclComm_t when nranks > 1
+    std::string err;
+    std::mutex mu;  // LinearOperator is Send + Sync: serialise stream submission per context
+};
+
+struct bemb200_staged_mesh {
+    bemb200_ctx* ctx = nullptr;
+    bemb::DeviceMesh dm;
+    std::vector<void*> allocs;
+};
+
+struct GmresWorkspace;  // gmres.cu
+
+struct bemb200_matrix {
+    bemb200_ctx* ctx = nullptr;
+    uint64_t n_rows = 0, n_cols = 0;  // global shape
+    uint64_t r0 = 0, r1 = 0;          // local rows
+    bemb::cplx* A = nullptr;          // (r1-r0) x n_cols, row-major
+    bemb::cplx* rhs = nullptr;        // r1-r0
+    uint2* near_list = nullptr;
+    unsigned int near_cap = 0;
+    unsigned int* near_count = nullptr;
+    bemb200_assembly_stats stats{};
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    GmresWorkspace* ws = nullptr;
+    // solver statistics of the last call
+    uint64_t last_launches = 0, last_matvecs = 0;
+    double last_matvec_ms = 0.0;
+};
+
+namespace bemb {
+int set_error(bemb200_ctx* ctx, int code, const std::string& msg);
+int cuda_fail(bemb200_ctx* ctx, cudaError_t e, const char* what);
+void free_workspace(bemb200_matrix* m);
+}  // namespace bemb
+
+#define BEMB_CUDA(ctx, call)                                          \
+    do {                                                              \
+        cudaError_t _e = (call);                                      \
+        if (_e != cudaSuccess) return bemb::cuda_fail(ctx, _e, #call); \
+    } while (0)

@@ -1,0 +1,480 @@
+// gmres.cu -- operator application and restarted GMRES on a device-resident, row-sharded
+// matrix.  Host control flow restates math-solvers/src/iterative/gmres.rs:105-277 (restart
+// semantics, iteration counting, Givens with conj(c), conj(s), relative residual vs ||b||,
+// breakdown 1e-14, zero-RHS early return); all O(N) and O(N^2) work runs in the kernels of
+// linalg.cu.
+//
+// Multi-GPU layout ("sharded matvec, replicated Arnoldi"): rank p owns rows
+// [p*chunk,(p+1)*chunk) of A; after the local GEMV the slices of y are all-gathered (NCCL,
+// 16*N bytes) and EVERY rank runs the same deterministic cluster MGS kernel on the full
+// vectors, so all ranks hold bit-identical Krylov bases and Hessenberg columns and take the
+// same convergence decisions without any all-reduce.
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "api_internal.h"
+#include "linalg.h"
+
+using namespace bemb;
+
+namespace bemb {
+int nccl_allgather_bytes(bemb200_ctx* ctx, const void* send, void* recv, size_t count_bytes);
+}
+
+struct GmresWorkspace {
+    uint64_t n = 0, npad = 0, chunk = 0;
+    uint32_t restart = 0;
+    cplx* V = nullptr;      // (restart+1) x npad
+    cplx* w = nullptr;      // npad  (matvec output / Arnoldi work vector)
+    cplx* r = nullptr;      // npad
+    cplx* xin = nullptr;    // npad  staging for host-pointer calls
+    cplx* bin = nullptr;    // npad
+    cplx* xout = nullptr;   // npad
+    cplx* hcol_d = nullptr; // restart+2
+    cplx* ycoef_d = nullptr;
+    double* scal_d = nullptr;
+    cplx* hcol_h = nullptr;   // pinned
+    double* scal_h = nullptr; // pinned
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace bemb {
+void free_workspace(bemb200_matrix* m) {
+    GmresWorkspace* ws = m->ws;
+    if (!ws) return;
+    cudaFree(ws->V); cudaFree(ws->w); cudaFree(ws->r); cudaFree(ws->xin); cudaFree(ws->bin); cudaFree(ws->xout);
+    cudaFree(ws->hcol_d); cudaFree(ws->ycoef_d); cudaFree(ws->scal_d);
+    if (ws->hcol_h) cudaFreeHost(ws->hcol_h);
+    if (ws->scal_h) cudaFreeHost(ws->scal_h);
+    if (ws->ev0) cudaEventDestroy(ws->ev0);
+    if (ws->ev1) cudaEventDestroy(ws->ev1);
+    delete ws;
+    m->ws = nullptr;
+}
+}  // namespace bemb
+
+static int ensure_workspace(bemb200_matrix* m, uint32_t restart) {
+    bemb200_ctx* ctx = m->ctx;
+    if (m->ws && m->ws->restart >= restart) return BEMB200_OK;
+    free_workspace(m);
+    GmresWorkspace* ws = new GmresWorkspace();
+    m->ws = ws;
+    ws->n = m->n_rows;
+    ws->chunk = (m->n_rows + ctx->nranks - 1) / ctx->nranks;
+    ws->npad = ws->chunk * ctx->nranks;
+    if (m->n_cols > ws->npad) ws->npad = m->n_cols;
+    ws->restart = restart;
+    const size_t vb = ws->npad * sizeof(cplx);
+    BEMB_CUDA(ctx, cudaMalloc((void**)&ws->V, (size_t)(restart + 1) * vb));
+    BEMB_CUDA(ctx, cudaMalloc((void**)&ws->w, vb));
+    BEMB_CUDA(ctx, cudaMalloc((void**)&ws->r, vb));
+    BEMB_CUDA(ctx, cudaMalloc((void**)&ws->xin, vb));
+    BEMB_CUDA(ctx, cudaMalloc((void**)&ws->bin, vb));
+    BEMB_CUDA(ctx, cudaMalloc((void**)&ws->xout, vb));
+    BEMB_CUDA(ctx, cudaMalloc((void**)&ws->hcol_d, (restart + 2) * sizeof(cplx)));
+    BEMB_CUDA(ctx, cudaMalloc((void**)&ws->ycoef_d, (restart + 2) * sizeof(cplx)));
+    BEMB_CUDA(ctx, cudaMalloc((void**)&ws->scal_d, 4 * sizeof(double)));
+    BEMB_CUDA(ctx, cudaMallocHost((void**)&ws->hcol_h, (restart + 2) * sizeof(cplx)));
+    BEMB_CUDA(ctx, cudaMallocHost((void**)&ws->scal_h, 4 * sizeof(double)));
+    BEMB_CUDA(ctx, cudaEventCreate(&ws->ev0));
+    BEMB_CUDA(ctx, cudaEventCreate(&ws->ev1));
+    BEMB_CUDA(ctx, cudaMemsetAsync(ws->w, 0, vb, ctx->stream));
+    return BEMB200_OK;
+}
+
+// y_full = A x  (x: n_cols on device, y_full: npad on device, valid in [0, n_rows))
+static int matvec(bemb200_matrix* m, const cplx* x, cplx* y_full, bool timed) {
+    bemb200_ctx* ctx = m->ctx;
+    GmresWorkspace* ws = m->ws;
+    const uint64_t nloc = m->r1 - m->r0;
+    cplx* yloc = y_full + (ctx->nranks > 1 ? (uint64_t)ctx->rank * ws->chunk : m->r0);
+    if (timed) BEMB_CUDA(ctx, cudaEventRecord(ws->ev0, ctx->stream));
+    BEMB_CUDA(ctx, launch_zgemv(m->A, m->n_cols, nloc, m->n_cols, x, yloc, ctx->stream));
+    if (timed) BEMB_CUDA(ctx, cudaEventRecord(ws->ev1, ctx->stream));
+    m->last_launches += 1;
+    m->last_matvecs += 1;
+    if (ctx->nranks > 1) {
+        int rc = nccl_allgather_bytes(ctx, yloc, y_full, ws->chunk * sizeof(cplx));
+        if (rc != BEMB200_OK) return rc;
+    }
+    return BEMB200_OK;
+}
+
+static void accumulate_matvec_time(bemb200_matrix* m) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, m->ws->ev0, m->ws->ev1) == cudaSuccess) m->last_matvec_ms += ms;
+    else cudaGetLastError();
+}
+
+// ---- host-side pieces of gmres.rs ----------------------------------------------------------
+static inline double tnorm(cplx a) { return std::sqrt(norm_sqr(a)); }  // ComplexField::norm (traits.rs:93-95)
+static void givens_rotation(cplx a, cplx b, cplx* c, cplx* s) {        // gmres.rs:589-603
+    const double tol = 1e-30;
+    if (tnorm(b) < tol) { *c = C(1, 0); *s = C(0, 0); return; }
+    if (tnorm(a) < tol) { *c = C(0, 0); *s = C(1, 0); return; }
+    double r = std::sqrt(norm_sqr(a) + norm_sqr(b));
+    *c = a * C(1.0 / r, 0.0);
+    *s = b * C(1.0 / r, 0.0);
+}
+static void solve_upper_triangular(const std::vector<cplx>& h, int ldh, const std::vector<cplx>& g, int k,
+                                   std::vector<cplx>& y) {  // gmres.rs:606-621
+    y.assign(k, C(0, 0));
+    for (int i = k - 1; i >= 0; --i) {
+        cplx sum = g[i];
+        for (int j = i + 1; j < k; ++j) sum -= h[i * ldh + j] * y[j];
+        cplx d = h[i * ldh + i];
+        if (tnorm(d) > 1e-30) {
+            double ns = norm_sqr(d);
+            y[i] = sum * C(d.re / ns, -d.im / ns);
+        }
+    }
+}
+
+static int norm_of(bemb200_matrix* m, const cplx* b, const cplx* ax, cplx* r, double* out) {
+    bemb200_ctx* ctx = m->ctx;
+    GmresWorkspace* ws = m->ws;
+    BEMB_CUDA(ctx, launch_residual(b, ax, r, m->n_rows, ws->scal_d, ctx->stream));
+    m->last_launches += 1;
+    BEMB_CUDA(ctx, cudaMemcpyAsync(ws->scal_h, ws->scal_d, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    BEMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = std::sqrt(ws->scal_h[0]);
+    return BEMB200_OK;
+}
+
+static int update_x(bemb200_matrix* m, cplx* x, const std::vector<cplx>& y) {
+    bemb200_ctx* ctx = m->ctx;
+    GmresWorkspace* ws = m->ws;
+    if (y.empty()) return BEMB200_OK;
+    BEMB_CUDA(ctx, cudaMemcpyAsync(ws->ycoef_d, y.data(), y.size() * sizeof(cplx), cudaMemcpyHostToDevice, ctx->stream));
+    BEMB_CUDA(ctx, launch_update_x(x, ws->V, ws->npad, ws->ycoef_d, (int)y.size(), m->n_rows, ctx->stream));
+    m->last_launches += 1;
+    BEMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // y lives on the host stack
+    return BEMB200_OK;
+}
+
+// gmres_with_guess (gmres.rs:105-277) with device vectors b, x (x holds x0 on entry)
+static int gmres_core(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t max_iterations, uint32_t restart, double tol,
+                      bemb200_gmres_info* info) {
+    bemb200_ctx* ctx = m->ctx;
+    GmresWorkspace* ws = m->ws;
+    const uint64_t n = m->n_rows;
+    const int mm = (int)restart;
+    cudaStream_t s = ctx->stream;
+    double b_norm = 0.0;
+    int rc = norm_of(m, b, nullptr, nullptr, &b_norm);
+    if (rc != BEMB200_OK) return rc;
+    if (b_norm < 1e-15) {
+        *info = bemb200_gmres_info{0, 0, 0.0, 1};
+        return BEMB200_OK;
+    }
+    uint64_t total_iterations = 0, restarts = 0;
+    const int ldh = mm;
+    std::vector<cplx> h, cs, sn, g, y;
+    for (uint32_t outer = 0; outer < max_iterations; ++outer) {
+        rc = matvec(m, x, ws->w, true);
+        if (rc != BEMB200_OK) return rc;
+        double beta = 0.0;
+        rc = norm_of(m, b, ws->w, ws->r, &beta);
+        if (rc != BEMB200_OK) return rc;
+        accumulate_matvec_time(m);
+        double rel = beta / b_norm;
+        if (rel < tol) {
+            *info = bemb200_gmres_info{total_iterations, restarts, rel, 1};
+            return BEMB200_OK;
+        }
+        BEMB_CUDA(ctx, launch_scale(ws->r, 1.0 / beta, ws->V, n, s));
+        m->last_launches += 1;
+        h.assign((size_t)(mm + 1) * mm, C(0, 0));
+        cs.clear(); sn.clear();
+        g.assign(mm + 1, C(0, 0));
+        g[0] = C(beta, 0.0);
+        bool inner_converged = false;
+        for (int j = 0; j < mm; ++j) {
+            total_iterations += 1;
+            rc = matvec(m, ws->V + (uint64_t)j * ws->npad, ws->w, true);
+            if (rc != BEMB200_OK) return rc;
+            BEMB_CUDA(ctx, launch_mgs(ws->V, ws->npad, ws->w, j, n, ws->hcol_d, ws->V + (uint64_t)(j + 1) * ws->npad, s));
+            m->last_launches += 1;
+            BEMB_CUDA(ctx, cudaMemcpyAsync(ws->hcol_h, ws->hcol_d, (j + 2) * sizeof(cplx), cudaMemcpyDeviceToHost, s));
+            BEMB_CUDA(ctx, cudaStreamSynchronize(s));
+            accumulate_matvec_time(m);
+            for (int i = 0; i <= j; ++i) h[i * ldh + j] = ws->hcol_h[i];
+            const double w_norm = ws->hcol_h[j + 1].re;
+            h[(j + 1) * ldh + j] = C(w_norm, 0.0);
+            if (w_norm < 1e-14) inner_converged = true;  // breakdown: v_{j+1} not formed (gmres.rs:194-202)
+            for (int i = 0; i < j; ++i) {
+                cplx temp = conj(cs[i]) * h[i * ldh + j] + conj(sn[i]) * h[(i + 1) * ldh + j];
+                h[(i + 1) * ldh + j] = C(0, 0) - sn[i] * h[i * ldh + j] + cs[i] * h[(i + 1) * ldh + j];
+                h[i * ldh + j] = temp;
+            }
+            cplx c, sgiv;
+            givens_rotation(h[j * ldh + j], h[(j + 1) * ldh + j], &c, &sgiv);
+            cs.push_back(c); sn.push_back(sgiv);
+            h[j * ldh + j] = conj(c) * h[j * ldh + j] + conj(sgiv) * h[(j + 1) * ldh + j];
+            h[(j + 1) * ldh + j] = C(0, 0);
+            cplx temp = conj(c) * g[j] + conj(sgiv) * g[j + 1];
+            g[j + 1] = C(0, 0) - sgiv * g[j] + c * g[j + 1];
+            g[j] = temp;
+            const double rel_res = tnorm(g[j + 1]) / b_norm;
+            if (rel_res < tol || inner_converged) {
+                solve_upper_triangular(h, ldh, g, j + 1, y);
+                rc = update_x(m, x, y);
+                if (rc != BEMB200_OK) return rc;
+                *info = bemb200_gmres_info{total_iterations, restarts, rel_res, 1};
+                return BEMB200_OK;
+            }
+        }
+        solve_upper_triangular(h, ldh, g, mm, y);
+        rc = update_x(m, x, y);
+        if (rc != BEMB200_OK) return rc;
+        restarts += 1;
+    }
+    rc = matvec(m, x, ws->w, true);
+    if (rc != BEMB200_OK) return rc;
+    double rn = 0.0;
+    rc = norm_of(m, b, ws->w, ws->r, &rn);
+    if (rc != BEMB200_OK) return rc;
+    accumulate_matvec_time(m);
+    *info = bemb200_gmres_info{total_iterations, restarts, rn / b_norm, 0};
+    return BEMB200_OK;
+}
+
+// the solver needs the whole operator: every row owned by exactly one rank, canonical split
+static int check_partition(bemb200_matrix* m) {
+    bemb200_ctx* ctx = m->ctx;
+    uint64_t b = 0, e = 0;
+    bemb200_partition(m->n_rows, ctx->nranks, ctx->rank, &b, &e);
+    if (m->r0 != b || m->r1 != e)
+        return set_error(ctx, BEMB200_EINVAL,
+                         "matrix slab is not this rank's canonical row block (see bemb200_partition); apply/gmres need the whole operator");
+    return BEMB200_OK;
+}
+
+static void reset_stats(bemb200_matrix* m) {
+    m->last_launches = 0;
+    m->last_matvecs = 0;
+    m->last_matvec_ms = 0.0;
+}
+
+extern "C" {
+
+int bemb200_gmres_device(const bemb200_matrix* cm, const double* b_dev, const double* x0_dev, uint32_t max_iterations,
+                         uint32_t restart, double tolerance, double* x_dev, bemb200_gmres_info* info) {
+    bemb200_matrix* m = const_cast<bemb200_matrix*>(cm);
+    if (!m || !b_dev || !x_dev || !info) return set_error(nullptr, BEMB200_EINVAL, "NULL argument");
+    bemb200_ctx* ctx = m->ctx;
+    if (m->n_rows != m->n_cols) return set_error(ctx, BEMB200_EINVAL, "gmres needs a square operator");
+    if (restart == 0) return set_error(ctx, BEMB200_EINVAL, "restart must be >= 1");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    BEMB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = check_partition(m);
+    if (rc != BEMB200_OK) return rc;
+    rc = ensure_workspace(m, restart);
+    if (rc != BEMB200_OK) return rc;
+    reset_stats(m);
+    const size_t nb = m->n_rows * sizeof(cplx);
+    if (x0_dev) {
+        if ((const void*)x0_dev != (const void*)x_dev)
+            BEMB_CUDA(ctx, cudaMemcpyAsync(x_dev, x0_dev, nb, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+        BEMB_CUDA(ctx, cudaMemsetAsync(x_dev, 0, nb, ctx->stream));
+    }
+    rc = gmres_core(m, (const cplx*)b_dev, (cplx*)x_dev, max_iterations, restart, tolerance, info);
+    cudaStreamSynchronize(ctx->stream);
+    return rc;
+}
+
+int bemb200_gmres(const bemb200_matrix* cm, const double* b, const double* x0, uint32_t max_iterations, uint32_t restart,
+                  double tolerance, double* x_out, bemb200_gmres_info* info) {
+    bemb200_matrix* m = const_cast<bemb200_matrix*>(cm);
+    if (!m || !b || !x_out || !info) return set_error(nullptr, BEMB200_EINVAL, "NULL argument");
+    bemb200_ctx* ctx = m->ctx;
+    if (m->n_rows != m->n_cols) return set_error(ctx, BEMB200_EINVAL, "gmres needs a square operator");
+    if (restart == 0) return set_error(ctx, BEMB200_EINVAL, "restart must be >= 1");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    BEMB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = check_partition(m);
+    if (rc != BEMB200_OK) return rc;
+    rc = ensure_workspace(m, restart);
+    if (rc != BEMB200_OK) return rc;
+    reset_stats(m);
+    GmresWorkspace* ws = m->ws;
+    const size_t nb = m->n_rows * sizeof(cplx);
+    BEMB_CUDA(ctx, cudaMemcpyAsync(ws->bin, b, nb, cudaMemcpyHostToDevice, ctx->stream));
+    if (x0) BEMB_CUDA(ctx, cudaMemcpyAsync(ws->xout, x0, nb, cudaMemcpyHostToDevice, ctx->stream));
+    else BEMB_CUDA(ctx, cudaMemsetAsync(ws->xout, 0, nb, ctx->stream));
+    rc = gmres_core(m, ws->bin, ws->xout, max_iterations, restart, tolerance, info);
+    if (rc != BEMB200_OK) return rc;
+    BEMB_CUDA(ctx, cudaMemcpyAsync(x_out, ws->xout, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    BEMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BEMB200_OK;
+}
+
+int bemb200_apply_device(const bemb200_matrix* cm, const double* x_dev, double* y_dev) {
+    bemb200_matrix* m = const_cast<bemb200_matrix*>(cm);
+    if (!m || !x_dev || !y_dev) return set_error(nullptr, BEMB200_EINVAL, "NULL argument");
+    bemb200_ctx* ctx = m->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    BEMB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = check_partition(m);
+    if (rc != BEMB200_OK) return rc;
+    rc = ensure_workspace(m, 1);
+    if (rc != BEMB200_OK) return rc;
+    reset_stats(m);
+    GmresWorkspace* ws = m->ws;
+    if (ctx->nranks == 1) {
+        // write straight into the caller's vector
+        BEMB_CUDA(ctx, cudaEventRecord(ws->ev0, ctx->stream));
+        BEMB_CUDA(ctx, launch_zgemv(m->A, m->n_cols, m->r1 - m->r0, m->n_cols, (const cplx*)x_dev, (cplx*)y_dev + m->r0, ctx->stream));
+        BEMB_CUDA(ctx, cudaEventRecord(ws->ev1, ctx->stream));
+        m->last_launches = 1;
+        m->last_matvecs = 1;
+    } else {
+        rc = matvec(m, (const cplx*)x_dev, ws->w, true);
+        if (rc != BEMB200_OK) return rc;
+        BEMB_CUDA(ctx, cudaMemcpyAsync(y_dev, ws->w, m->n_rows * sizeof(cplx), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    BEMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    accumulate_matvec_time(m);
+    return BEMB200_OK;
+}
+
+int bemb200_apply(const bemb200_matrix* cm, const double* x, double* y) {
+    bemb200_matrix* m = const_cast<bemb200_matrix*>(cm);
+    if (!m || !x || !y) return set_error(nullptr, BEMB200_EINVAL, "NULL argument");
+    bemb200_ctx* ctx = m->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    BEMB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = check_partition(m);
+    if (rc != BEMB200_OK) return rc;
+    rc = ensure_workspace(m, 1);
+    if (rc != BEMB200_OK) return rc;
+    reset_stats(m);
+    GmresWorkspace* ws = m->ws;
+    BEMB_CUDA(ctx, cudaMemcpyAsync(ws->xin, x, m->n_cols * sizeof(cplx), cudaMemcpyHostToDevice, ctx->stream));
+    rc = matvec(m, ws->xin, ws->w, true);
+    if (rc != BEMB200_OK) return rc;
+    BEMB_CUDA(ctx, cudaMemcpyAsync(y, ws->w, m->n_rows * sizeof(cplx), cudaMemcpyDeviceToHost, ctx->stream));
+    BEMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    accumulate_matvec_time(m);
+    return BEMB200_OK;
+}
+
+int bemb200_apply_transpose(const bemb200_matrix* cm, const double* x, double* y) {
+    bemb200_matrix* m = const_cast<bemb200_matrix*>(cm);
+    if (!m || !x || !y) return set_error(nullptr, BEMB200_EINVAL, "NULL argument");
+    bemb200_ctx* ctx = m->ctx;
+    if (ctx->nranks > 1) return set_error(ctx, BEMB200_EUNSUPPORTED, "apply_transpose on a row-sharded matrix is not implemented");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    BEMB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = check_partition(m);
+    if (rc != BEMB200_OK) return rc;
+    rc = ensure_workspace(m, 1);
+    if (rc != BEMB200_OK) return rc;
+    reset_stats(m);
+    GmresWorkspace* ws = m->ws;
+    // y = A^T x : x has num_rows entries, y has num_cols entries
+    BEMB_CUDA(ctx, cudaMemcpyAsync(ws->xin, x, m->n_rows * sizeof(cplx), cudaMemcpyHostToDevice, ctx->stream));
+    BEMB_CUDA(ctx, launch_zgemv_t(m->A, m->n_cols, m->r1 - m->r0, m->n_cols, ws->xin + m->r0, ws->w, ctx->stream));
+    m->last_launches = 1;
+    BEMB_CUDA(ctx, cudaMemcpyAsync(y, ws->w, m->n_cols * sizeof(cplx), cudaMemcpyDeviceToHost, ctx->stream));
+    BEMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BEMB200_OK;
+}
+
+int bemb200_row_sum_correction(bemb200_matrix* m, double* avg) {
+    if (!m) return set_error(nullptr, BEMB200_EINVAL, "NULL argument");
+    bemb200_ctx* ctx = m->ctx;
+    if (m->n_rows != m->n_cols) return set_error(ctx, BEMB200_EINVAL, "row-sum correction needs a square matrix");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    BEMB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t nloc = m->r1 - m->r0;
+    cplx* d_sums = nullptr;
+    BEMB_CUDA(ctx, cudaMalloc((void**)&d_sums, (nloc + 1) * sizeof(cplx)));
+    cudaError_t e = launch_row_sum(m->A, m->n_cols, nloc, m->n_cols, m->r0, d_sums, ctx->stream);
+    std::vector<cplx> sums(nloc);
+    if (e == cudaSuccess && nloc) e = cudaMemcpyAsync(sums.data(), d_sums, nloc * sizeof(cplx), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_sums);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "row_sum_correction");
+    cplx total = C(0, 0);
+    for (uint64_t i = 0; i < nloc; ++i) total += sums[i];
+    if (ctx->nranks > 1) {
+        // gather the per-rank partial totals (16 bytes each) and add them in rank order
+        cplx* d_part = nullptr;
+        BEMB_CUDA(ctx, cudaMalloc((void**)&d_part, ctx->nranks * sizeof(cplx)));
+        BEMB_CUDA(ctx, cudaMemcpyAsync(d_part + ctx->rank, &total, sizeof(cplx), cudaMemcpyHostToDevice, ctx->stream));
+        int rc = nccl_allgather_bytes(ctx, d_part + ctx->rank, d_part, sizeof(cplx));
+        std::vector<cplx> parts(ctx->nranks);
+        if (rc == BEMB200_OK) {
+            e = cudaMemcpyAsync(parts.data(), d_part, ctx->nranks * sizeof(cplx), cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        }
+        cudaFree(d_part);
+        if (rc != BEMB200_OK) return rc;
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "row_sum_correction gather");
+        total = C(0, 0);
+        for (int p = 0; p < ctx->nranks; ++p) total += parts[p];
+    }
+    if (avg) *avg = std::hypot(total.re, total.im) / (double)m->n_rows;
+    return BEMB200_OK;
+}
+
+int bemb200_solver_stats(const bemb200_matrix* m, uint64_t* kernel_launches, double* matvec_ms, uint64_t* matvecs) {
+    if (!m) return set_error(nullptr, BEMB200_EINVAL, "NULL argument");
+    if (kernel_launches) *kernel_launches = m->last_launches;
+    if (matvec_ms) *matvec_ms = m->last_matvec_ms;
+    if (matvecs) *matvecs = m->last_matvecs;
+    return BEMB200_OK;
+}
+
+int bemb200_measure_fp64_peak(bemb200_ctx* ctx, double* tflops) {
+    if (!ctx || !tflops) return set_error(ctx, BEMB200_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    BEMB_CUDA(ctx, cudaSetDevice(ctx->device));
+    double* d = nullptr;
+    BEMB_CUDA(ctx, cudaMalloc((void**)&d, sizeof(double)));
+    cudaEvent_t a, b;
+    BEMB_CUDA(ctx, cudaEventCreate(&a));
+    BEMB_CUDA(ctx, cudaEventCreate(&b));
+    const int iters = 4096;
+    double best = 0.0;
+    cudaError_t e = launch_dfma_peak(d, 256, ctx->stream);  // warm-up
+    for (int rep = 0; rep < 5 && e == cudaSuccess; ++rep) {
+        cudaEventRecord(a, ctx->stream);
+        e = launch_dfma_peak(d, iters, ctx->stream);
+        cudaEventRecord(b, ctx->stream);
+        if (e == cudaSuccess) e = cudaEventSynchronize(b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        const double flops = 2.0 * 64.0 * (double)iters * 256.0 * 148.0 * 8.0;  // 8 chains x 8 unrolled FMAs per iteration
+        if (ms > 0.f && flops / (ms * 1e-3) > best) best = flops / (ms * 1e-3);
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "dfma peak kernel");
+    *tflops = best * 1e-12;
+    return BEMB200_OK;
+}
+
+int bemb200_selftest_math(bemb200_ctx* ctx, uint64_t n, double xmax, double* sincos_err, double* rsqrt_relerr) {
+    if (!ctx) return set_error(ctx, BEMB200_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    BEMB_CUDA(ctx, cudaSetDevice(ctx->device));
+    double* d = nullptr;
+    BEMB_CUDA(ctx, cudaMalloc((void**)&d, 2 * sizeof(double)));
+    cudaError_t e = cudaMemsetAsync(d, 0, 2 * sizeof(double), ctx->stream);
+    if (e == cudaSuccess) e = launch_math_selftest(n, xmax, d, ctx->stream);
+    double h[2] = {0, 0};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "math selftest");
+    if (sincos_err) *sincos_err = h[0];
+    if (rsqrt_relerr) *rsqrt_relerr = h[1];
+    return BEMB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,416 @@
+// linalg.cu -- device kernels of the solve phase.
+//
+//   zgemv_kernel        K5: y = A x, streaming complex128 GEMV (HBM-bound), replaces
+//                       DenseOperator::apply = Array2::dot -> cblas zgemv
+//                       (math-bem/src/core/solver/fmm_interface.rs:45-47)
+//   zgemv_t_kernel      apply_transpose (fmm_interface.rs:49-51)
+//   mgs_cluster_kernel  K7: one Arnoldi step of gmres.rs:184-202 -- modified Gram-Schmidt
+//                       of w against v_0..v_j, ||w||, v_{j+1} -- in ONE launch: a thread-block
+//                       cluster keeps w in (distributed) shared memory, and the j+1 DEPENDENT
+//                       dot products are reduced across the CTAs through DSMEM + cluster
+//                       barriers instead of j+1 kernel launches / host round trips.
+//   residual / scale / update kernels for gmres.rs:143-172,238-262
+#include <cooperative_groups.h>
+
+#include "linalg.h"
+
+namespace cg = cooperative_groups;
+
+namespace bemb {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// ZGEMV: block = 256 threads = 8 warps walks RB rows at once; lane-contiguous 128-bit loads
+// (each warp load instruction covers 512 contiguous bytes of one row), x re-used across the
+// RB rows from registers, 2x unrolled => RB*2 independent 16-byte loads in flight per thread.
+// ------------------------------------------------------------------------------------------
+constexpr int GEMV_THREADS = 256;
+constexpr int GEMV_RB = 4;
+
+__device__ __forceinline__ double2 ld_stream(const cplx* p) { return __ldcs(reinterpret_cast<const double2*>(p)); }
+__device__ __forceinline__ double2 ld_ro(const cplx* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
+
+__device__ __forceinline__ void cfma(double& are, double& aim, double2 a, double2 x) {
+    are = fma(a.x, x.x, are);
+    are = fma(-a.y, x.y, are);
+    aim = fma(a.x, x.y, aim);
+    aim = fma(a.y, x.x, aim);
+}
+
+__global__ void __launch_bounds__(GEMV_THREADS)
+zgemv_kernel(const cplx* __restrict__ A, uint64_t lda, uint64_t nrows, uint64_t ncols, const cplx* __restrict__ x,
+             cplx* __restrict__ y) {
+    __shared__ double red[GEMV_RB][2][GEMV_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint64_t rb = (uint64_t)blockIdx.x * GEMV_RB; rb < nrows; rb += (uint64_t)gridDim.x * GEMV_RB) {
+        double are[GEMV_RB], aim[GEMV_RB];
+        const cplx* rowp[GEMV_RB];
+#pragma unroll
+        for (int r = 0; r < GEMV_RB; ++r) {
+            are[r] = 0.0; aim[r] = 0.0;
+            uint64_t row = rb + r < nrows ? rb + r : nrows - 1;  // clamp: tail rows recompute the last row
+            rowp[r] = A + row * lda;
+        }
+        uint64_t c = tid;
+        for (; c + GEMV_THREADS < ncols; c += 2 * GEMV_THREADS) {
+            double2 a0[GEMV_RB], a1[GEMV_RB];
+#pragma unroll
+            for (int r = 0; r < GEMV_RB; ++r) {
+                a0[r] = ld_stream(rowp[r] + c);
+                a1[r] = ld_stream(rowp[r] + c + GEMV_THREADS);
+            }
+            const double2 x0 = ld_ro(x + c), x1 = ld_ro(x + c + GEMV_THREADS);
+#pragma unroll
+            for (int r = 0; r < GEMV_RB; ++r) {
+                cfma(are[r], aim[r], a0[r], x0);
+                cfma(are[r], aim[r], a1[r], x1);
+            }
+        }
+        if (c < ncols) {
+            const double2 x0 = ld_ro(x + c);
+#pragma unroll
+            for (int r = 0; r < GEMV_RB; ++r) cfma(are[r], aim[r], ld_stream(rowp[r] + c), x0);
+        }
+#pragma unroll
+        for (int r = 0; r < GEMV_RB; ++r) {
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) {
+                are[r] += __shfl_xor_sync(0xffffffffu, are[r], m);
+                aim[r] += __shfl_xor_sync(0xffffffffu, aim[r], m);
+            }
+            if (lane == 0) { red[r][0][warp] = are[r]; red[r][1][warp] = aim[r]; }
+        }
+        __syncthreads();
+        if (tid < GEMV_RB && rb + tid < nrows) {
+            double sr = 0.0, si = 0.0;
+#pragma unroll
+            for (int w = 0; w < GEMV_THREADS / 32; ++w) { sr += red[tid][0][w]; si += red[tid][1][w]; }
+            y[rb + tid] = C(sr, si);
+        }
+        __syncthreads();
+    }
+}
+
+// y[j] += sum_i A[i,j] x[i] over a chunk of rows (y pre-zeroed)
+constexpr int GEMVT_ROWS = 64;
+__global__ void __launch_bounds__(256)
+zgemv_t_kernel(const cplx* __restrict__ A, uint64_t lda, uint64_t nrows, uint64_t ncols, const cplx* __restrict__ x,
+               cplx* __restrict__ y) {
+    const uint64_t col = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    const uint64_t r0 = (uint64_t)blockIdx.y * GEMVT_ROWS;
+    const uint64_t r1 = r0 + GEMVT_ROWS < nrows ? r0 + GEMVT_ROWS : nrows;
+    if (col >= ncols) return;
+    double sr = 0.0, si = 0.0;
+    for (uint64_t r = r0; r < r1; ++r) cfma(sr, si, ld_stream(A + r * lda + col), ld_ro(x + r));
+    atomicAdd(&y[col].re, sr);
+    atomicAdd(&y[col].im, si);
+}
+
+// ------------------------------------------------------------------------------------------
+// cluster helpers
+// ------------------------------------------------------------------------------------------
+constexpr int VEC_THREADS = 512;
+constexpr int MAX_CLUSTER = 16;
+
+struct ClusterShared {
+    cplx part[2][MAX_CLUSTER];
+    double red[2][VEC_THREADS / 32];
+};
+
+__device__ __forceinline__ cplx block_reduce(cplx v, ClusterShared& sh) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        v.re += __shfl_xor_sync(0xffffffffu, v.re, m);
+        v.im += __shfl_xor_sync(0xffffffffu, v.im, m);
+    }
+    __syncthreads();  // protects sh.red against the previous use
+    if (lane == 0) { sh.red[0][warp] = v.re; sh.red[1][warp] = v.im; }
+    __syncthreads();
+    cplx t = C(0, 0);
+    const int nw = blockDim.x >> 5;
+    for (int w = 0; w < nw; ++w) { t.re += sh.red[0][w]; t.im += sh.red[1][w]; }
+    return t;  // every thread holds the block total
+}
+
+// all-CTA sum of one complex value; `parity` alternates between consecutive calls
+__device__ __forceinline__ cplx cluster_allreduce(cplx block_total, ClusterShared& sh, int parity) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned nb = cluster.num_blocks(), me = cluster.block_rank();
+    if (threadIdx.x < nb) {
+        ClusterShared* remote = cluster.map_shared_rank(&sh, threadIdx.x);
+        remote->part[parity][me] = block_total;
+    }
+    cluster.sync();
+    cplx t = C(0, 0);
+    for (unsigned d = 0; d < nb; ++d) { t.re += sh.part[parity][d].re; t.im += sh.part[parity][d].im; }
+    return t;  // bit-identical in every CTA (fixed summation order)
+}
+
+// One Arnoldi orthogonalisation step (gmres.rs:184-202).  One cluster; CTA c owns the slice
+// [c*S, (c+1)*S) of every vector.  w lives in shared memory when it fits, else in global.
+__global__ void __launch_bounds__(VEC_THREADS)
+mgs_cluster_kernel(const cplx* __restrict__ V, uint64_t ldv, cplx* __restrict__ w, int j, uint64_t n, uint64_t S,
+                   int w_in_smem, cplx* __restrict__ hcol, cplx* __restrict__ vnext, double breakdown_tol) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    __shared__ ClusterShared sh;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned me = cluster.block_rank();
+    const uint64_t begin = (uint64_t)me * S;
+    const uint64_t end = begin + S < n ? begin + S : n;
+    const uint64_t len = end > begin ? end - begin : 0;
+    cplx* ws = w_in_smem ? reinterpret_cast<cplx*>(dyn) : (w + begin);
+    if (w_in_smem)
+        for (uint64_t k = threadIdx.x; k < len; k += blockDim.x) ws[k] = w[begin + k];
+    // (each thread only ever touches its own k's of ws: no barrier needed for ws itself)
+    int parity = 0;
+    for (int i = 0; i <= j; ++i) {
+        const cplx* vi = V + (uint64_t)i * ldv + begin;
+        cplx acc = C(0, 0);
+        for (uint64_t k = threadIdx.x; k < len; k += blockDim.x) {
+            const cplx a = vi[k], b = ws[k];  // conj(a) * b  (inner_product: blas_helpers.rs:21-33)
+            acc.re = fma(a.re, b.re, fma(a.im, b.im, acc.re));
+            acc.im = fma(a.re, b.im, fma(-a.im, b.re, acc.im));
+        }
+        const cplx h = cluster_allreduce(block_reduce(acc, sh), sh, parity);
+        parity ^= 1;
+        if (me == 0 && threadIdx.x == 0) hcol[i] = h;
+        for (uint64_t k = threadIdx.x; k < len; k += blockDim.x) {  // axpy(-h, v_i, w)
+            const cplx a = vi[k];
+            cplx b = ws[k];
+            b.re = fma(-h.re, a.re, fma(h.im, a.im, b.re));
+            b.im = fma(-h.re, a.im, fma(-h.im, a.re, b.im));
+            ws[k] = b;
+        }
+    }
+    cplx acc = C(0, 0);
+    for (uint64_t k = threadIdx.x; k < len; k += blockDim.x) acc.re = fma(ws[k].re, ws[k].re, fma(ws[k].im, ws[k].im, acc.re));
+    const cplx nn = cluster_allreduce(block_reduce(acc, sh), sh, parity);
+    const double nrm = sqrt(nn.re);
+    if (me == 0 && threadIdx.x == 0) hcol[j + 1] = C(nrm, 0.0);
+    if (!(nrm < breakdown_tol)) {
+        // new_v = w; axpy(1/||w|| - 1, w, new_v)   (gmres.rs:198-201)
+        const double s = 1.0 / nrm - 1.0;
+        for (uint64_t k = threadIdx.x; k < len; k += blockDim.x) {
+            const cplx b = ws[k];
+            vnext[begin + k] = C(b.re + b.re * s, b.im + b.im * s);
+        }
+    }
+    cluster.sync();  // no CTA may exit while a peer could still address its shared memory
+}
+
+// r = b - ax ; out[0] = sum |r|^2  (one cluster)
+__global__ void __launch_bounds__(VEC_THREADS)
+residual_cluster_kernel(const cplx* __restrict__ b, const cplx* __restrict__ ax, cplx* __restrict__ r, uint64_t n, uint64_t S,
+                        double* __restrict__ out) {
+    __shared__ ClusterShared sh;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned me = cluster.block_rank();
+    const uint64_t begin = (uint64_t)me * S;
+    const uint64_t end = begin + S < n ? begin + S : n;
+    cplx acc = C(0, 0);
+    for (uint64_t k = begin + threadIdx.x; k < end; k += blockDim.x) {
+        cplx v = b[k];
+        if (ax) { v.re -= ax[k].re; v.im -= ax[k].im; }
+        if (r) r[k] = v;
+        acc.re = fma(v.re, v.re, fma(v.im, v.im, acc.re));
+    }
+    const cplx t = cluster_allreduce(block_reduce(acc, sh), sh, 0);
+    if (me == 0 && threadIdx.x == 0) out[0] = t.re;
+    cluster.sync();
+}
+
+__global__ void scale_kernel(const cplx* __restrict__ r, double s, cplx* __restrict__ v, uint64_t n) {
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x)
+        v[k] = C(r[k].re * s, r[k].im * s);
+}
+
+// x += sum_i y_i V_i, applied in the reference's order i = 0..cnt-1 (gmres.rs:241-243)
+__global__ void update_x_kernel(cplx* __restrict__ x, const cplx* __restrict__ V, uint64_t ldv, const cplx* __restrict__ ycoef,
+                                int cnt, uint64_t n) {
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
+        cplx v = x[k];
+        for (int i = 0; i < cnt; ++i) {
+            const cplx a = ycoef[i], b = V[(uint64_t)i * ldv + k];
+            v.re += a.re * b.re - a.im * b.im;
+            v.im += a.re * b.im + a.im * b.re;
+        }
+        x[k] = v;
+    }
+}
+
+// apply_row_sum_correction (tbem.rs:500-520): one warp per local row
+__global__ void row_sum_kernel(cplx* __restrict__ A, uint64_t lda, uint64_t nloc, uint64_t ncols, uint64_t r0,
+                               cplx* __restrict__ rowsums) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t row = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= nloc) return;
+    cplx acc = C(0, 0);
+    for (uint64_t c = lane; c < ncols; c += 32) { acc.re += A[row * lda + c].re; acc.im += A[row * lda + c].im; }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        acc.re += __shfl_xor_sync(0xffffffffu, acc.re, m);
+        acc.im += __shfl_xor_sync(0xffffffffu, acc.im, m);
+    }
+    if (lane == 0) {
+        rowsums[row] = acc;
+        A[row * lda + r0 + row].re -= acc.re;
+        A[row * lda + r0 + row].im -= acc.im;
+    }
+}
+
+// ---- measurement kernels ---------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dfma_peak_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 123.456) out[0] = s;
+}
+
+__device__ __forceinline__ void atomic_max_pos(double* addr, double v) {
+    atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
+}
+__global__ void math_selftest_kernel(uint64_t n, double xmax, double* err) {
+    double e_sc = 0.0, e_rs = 0.0;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
+        // low-discrepancy sample of [0, xmax]
+        double u = (double)k * 0.6180339887498949;
+        u -= floor(u);
+        double x = u * xmax;
+        double s, c, fs, fc;
+        sincos(x, &s, &c);
+        fast_sincos(x, fs, fc);
+        e_sc = fmax(e_sc, fmax(fabs(fs - s), fabs(fc - c)));
+        double a = x * x + 1e-12;
+        double ref = 1.0 / sqrt(a);
+        e_rs = fmax(e_rs, fabs(fast_rsqrt(a) - ref) / ref);
+    }
+    atomic_max_pos(&err[0], e_sc);
+    atomic_max_pos(&err[1], e_rs);
+}
+
+template <class Kern, class... Args>
+cudaError_t launch_cluster(Kern kern, int cluster, int threads, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cluster, 1, 1);
+    cfg.blockDim = dim3(threads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
+}  // namespace
+
+cudaError_t launch_zgemv(const cplx* A, uint64_t lda, uint64_t nrows, uint64_t ncols, const cplx* x, cplx* y, cudaStream_t s) {
+    if (nrows == 0) return cudaSuccess;
+    uint64_t blocks = (nrows + GEMV_RB - 1) / GEMV_RB;
+    const uint64_t maxb = 148ull * 8ull * 8ull;
+    if (blocks > maxb) blocks = maxb;
+    zgemv_kernel<<<(unsigned)blocks, GEMV_THREADS, 0, s>>>(A, lda, nrows, ncols, x, y);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_zgemv_t(const cplx* A, uint64_t lda, uint64_t nrows, uint64_t ncols, const cplx* x, cplx* y, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(y, 0, ncols * sizeof(cplx), s);
+    if (e != cudaSuccess || nrows == 0) return e;
+    dim3 grid((unsigned)((ncols + 255) / 256), (unsigned)((nrows + GEMVT_ROWS - 1) / GEMVT_ROWS));
+    zgemv_t_kernel<<<grid, 256, 0, s>>>(A, lda, nrows, ncols, x, y);
+    return cudaGetLastError();
+}
+
+// cluster size / slice / where w lives.  `level` 0: preferred (w in shared memory, 16 CTAs if a
+// slice would not fit in 8), level 1: conservative fallback (8 CTAs, w in global/L2).
+static int pick_cluster(uint64_t n, int level, bool* w_in_smem, size_t* smem_bytes, uint64_t* slice) {
+    int cl = n >= 4096 ? 8 : 1;
+    uint64_t S = (n + cl - 1) / cl;
+    const size_t cap = 200 * 1024;
+    if (level == 0 && S * sizeof(cplx) > cap && cl == 8) {
+        cl = 16;
+        S = (n + cl - 1) / cl;
+    }
+    bool fits = level == 0 && S * sizeof(cplx) <= cap;
+    *w_in_smem = fits;
+    *smem_bytes = fits ? S * sizeof(cplx) : 0;
+    *slice = S;
+    return cl;
+}
+
+static int g_cluster_level = 0;
+
+cudaError_t launch_mgs(const cplx* V, uint64_t ldv, cplx* w, int j, uint64_t n, cplx* hcol, cplx* vnext, cudaStream_t s) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(mgs_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(mgs_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    for (;;) {
+        bool in_smem;
+        size_t smem;
+        uint64_t S;
+        int cl = pick_cluster(n, g_cluster_level, &in_smem, &smem, &S);
+        cudaError_t e = launch_cluster(mgs_cluster_kernel, cl, VEC_THREADS, smem, s, V, ldv, w, j, n, S, (int)in_smem, hcol,
+                                       vnext, 1e-14);
+        if (e == cudaSuccess || g_cluster_level == 1) return e;
+        cudaGetLastError();  // e.g. a 16-CTA / 200 KB cluster that this GPC layout cannot place
+        g_cluster_level = 1;
+    }
+}
+
+cudaError_t launch_residual(const cplx* b, const cplx* ax, cplx* r, uint64_t n, double* out, cudaStream_t s) {
+    bool in_smem;
+    size_t smem;
+    uint64_t S;
+    int cl = pick_cluster(n, 1, &in_smem, &smem, &S);  // no shared-memory slice needed: 8 CTAs always place
+    return launch_cluster(residual_cluster_kernel, cl, VEC_THREADS, 0, s, b, ax, r, n, S, out);
+}
+
+cudaError_t launch_scale(const cplx* r, double sc, cplx* v, uint64_t n, cudaStream_t s) {
+    unsigned blocks = (unsigned)((n + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    scale_kernel<<<blocks, 256, 0, s>>>(r, sc, v, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_update_x(cplx* x, const cplx* V, uint64_t ldv, const cplx* ycoef, int cnt, uint64_t n, cudaStream_t s) {
+    unsigned blocks = (unsigned)((n + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    update_x_kernel<<<blocks, 256, 0, s>>>(x, V, ldv, ycoef, cnt, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_row_sum(cplx* A, uint64_t lda, uint64_t nloc, uint64_t ncols, uint64_t r0, cplx* rowsums, cudaStream_t s) {
+    if (nloc == 0) return cudaSuccess;
+    unsigned blocks = (unsigned)((nloc * 32 + 255) / 256);
+    row_sum_kernel<<<blocks, 256, 0, s>>>(A, lda, nloc, ncols, r0, rowsums);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dfma_peak(double* out, int iters, cudaStream_t s) {
+    dfma_peak_kernel<<<148 * 8, 256, 0, s>>>(out, iters, 1.0000001, 1e-9);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_math_selftest(uint64_t n, double xmax, double* err, cudaStream_t s) {
+    math_selftest_kernel<<<148 * 4, 256, 0, s>>>(n, xmax, err);
+    return cudaGetLastError();
+}
+
+}  // namespace bemb

@@ -1,0 +1,15 @@
+// Launchers of the solve-phase kernels (linalg.cu).
+#pragma once
+#include "internal.h"
+
+namespace bemb {
+cudaError_t launch_zgemv(const cplx* A, uint64_t lda, uint64_t nrows, uint64_t ncols, const cplx* x, cplx* y, cudaStream_t s);
+cudaError_t launch_zgemv_t(const cplx* A, uint64_t lda, uint64_t nrows, uint64_t ncols, const cplx* x, cplx* y, cudaStream_t s);
+cudaError_t launch_mgs(const cplx* V, uint64_t ldv, cplx* w, int j, uint64_t n, cplx* hcol, cplx* vnext, cudaStream_t s);
+cudaError_t launch_residual(const cplx* b, const cplx* ax, cplx* r, uint64_t n, double* out, cudaStream_t s);
+cudaError_t launch_scale(const cplx* r, double sc, cplx* v, uint64_t n, cudaStream_t s);
+cudaError_t launch_update_x(cplx* x, const cplx* V, uint64_t ldv, const cplx* ycoef, int cnt, uint64_t n, cudaStream_t s);
+cudaError_t launch_row_sum(cplx* A, uint64_t lda, uint64_t nloc, uint64_t ncols, uint64_t r0, cplx* rowsums, cudaStream_t s);
+cudaError_t launch_dfma_peak(double* out, int iters, cudaStream_t s);
+cudaError_t launch_math_selftest(uint64_t n, double xmax, double* err, cudaStream_t s);
+}  // namespace bemb
