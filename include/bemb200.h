@@ -86,6 +86,10 @@ int bemb200_ctx_create(int device, bemb200_ctx** out);
  * host program (MPI, torch.distributed, a file ...). */
 int bemb200_nccl_unique_id(uint8_t out[128]);
 int bemb200_ctx_create_dist(int device, int rank, int nranks, const uint8_t nccl_id[128], bemb200_ctx** out);
+/* general form: `cuda_stream` (a cudaStream_t, may be NULL) makes the library submit all its
+ * work to a stream owned by the caller, so that the caller's CUDA events bracket it;
+ * nranks == 1 ignores nccl_id. */
+int bemb200_ctx_create_ex(int device, int rank, int nranks, const uint8_t* nccl_id, void* cuda_stream, bemb200_ctx** out);
 void bemb200_ctx_destroy(bemb200_ctx* ctx);
 const char* bemb200_last_error(const bemb200_ctx* ctx); /* ctx may be NULL: last global error */
 /* canonical row partition used by the distributed solver: rank r owns
@@ -123,6 +127,8 @@ uint64_t bemb200_local_row_end(const bemb200_matrix* m);
 int bemb200_matrix_download(const bemb200_matrix* m, uint64_t row_begin, uint64_t row_end, double* out);
 /* rhs entries of the local rows (TbemSystem.rhs) */
 int bemb200_rhs_download(const bemb200_matrix* m, double* out);
+/* the full rhs vector (num_rows entries) on every rank: local slices all-gathered */
+int bemb200_rhs_download_full(const bemb200_matrix* m, double* out);
 /* apply_row_sum_correction (tbem.rs:500-520); returns |sum of all row sums| / n in *avg */
 int bemb200_row_sum_correction(bemb200_matrix* m, double* avg);
 

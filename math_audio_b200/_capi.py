@@ -54,6 +54,7 @@ SYMBOLS = {
     "bemb200_ctx_create": (C.c_int, [C.c_int, _PP]),
     "bemb200_nccl_unique_id": (C.c_int, [_VP]),
     "bemb200_ctx_create_dist": (C.c_int, [C.c_int, C.c_int, C.c_int, _VP, _PP]),
+    "bemb200_ctx_create_ex": (C.c_int, [C.c_int, C.c_int, C.c_int, _VP, _VP, _PP]),
     "bemb200_ctx_destroy": (None, [_VP]),
     "bemb200_last_error": (C.c_char_p, [_VP]),
     "bemb200_partition": (None, [C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
@@ -72,6 +73,7 @@ SYMBOLS = {
     "bemb200_local_row_end": (C.c_uint64, [_VP]),
     "bemb200_matrix_download": (C.c_int, [_VP, C.c_uint64, C.c_uint64, _VP]),
     "bemb200_rhs_download": (C.c_int, [_VP, _VP]),
+    "bemb200_rhs_download_full": (C.c_int, [_VP, _VP]),
     "bemb200_row_sum_correction": (C.c_int, [_VP, C.POINTER(C.c_double)]),
     "bemb200_apply": (C.c_int, [_VP, _VP, _VP]),
     "bemb200_apply_transpose": (C.c_int, [_VP, _VP, _VP]),

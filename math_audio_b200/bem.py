@@ -32,15 +32,18 @@ from .types import PhysicsParams
 class Context:
     """One GPU (optionally one rank of a row-sharded job: one process per GPU)."""
 
-    def __init__(self, device: int = 0, rank: int = 0, nranks: int = 1, nccl_id: Optional[bytes] = None):
+    def __init__(self, device: int = 0, rank: int = 0, nranks: int = 1, nccl_id: Optional[bytes] = None,
+                 cuda_stream: int = 0):
+        """``cuda_stream``: raw cudaStream_t (e.g. ``torch.cuda.current_stream().cuda_stream``) to submit
+        all work to, so that the caller's CUDA events bracket it; 0 = library-owned stream."""
         self._lib = _capi.lib()
         self._h = C.c_void_p()
+        idp = None
         if nranks > 1:
             assert nccl_id is not None and len(nccl_id) == 128
-            buf = (C.c_uint8 * 128).from_buffer_copy(nccl_id)
-            _capi.check(self._lib.bemb200_ctx_create_dist(device, rank, nranks, C.cast(buf, C.c_void_p), C.byref(self._h)))
-        else:
-            _capi.check(self._lib.bemb200_ctx_create(device, C.byref(self._h)))
+            self._idbuf = (C.c_uint8 * 128).from_buffer_copy(nccl_id)
+            idp = C.cast(self._idbuf, C.c_void_p)
+        _capi.check(self._lib.bemb200_ctx_create_ex(device, rank, nranks, idp, C.c_void_p(cuda_stream or None), C.byref(self._h)))
         self.device, self.rank, self.nranks = device, rank, nranks
 
     @staticmethod
@@ -177,14 +180,22 @@ class TbemSystem:
     """tbem.rs:13-20.  ``matrix`` is device resident; ``rhs`` holds the local rows' entries."""
 
     matrix: DeviceMatrix
-    rhs: np.ndarray
+    rhs: Optional[np.ndarray]
     num_dofs: int
+
+    def rhs_full(self, n: Optional[int] = None) -> np.ndarray:
+        """TbemSystem.rhs for ALL rows (on a row-sharded system the slices are all-gathered)."""
+        out = np.empty(self.num_dofs, dtype=np.complex128)
+        _capi.check(_capi.lib().bemb200_rhs_download_full(self.matrix._h, _capi.ptr(out)), self.matrix.ctx._h)
+        return out
 
 
 def build_tbem_system_with_beta(elements: Mesh | StagedMesh, physics: PhysicsParams, beta: complex,
-                                ctx: Optional[Context] = None, rows=None, reuse: Optional[TbemSystem] = None) -> TbemSystem:
+                                ctx: Optional[Context] = None, rows=None, reuse: Optional[TbemSystem] = None,
+                                fetch_rhs: bool = True) -> TbemSystem:
     """tbem.rs:96-222.  ``elements`` carries nodes + elements (SoA).  ``rows=(r0, r1)`` assembles
-    one row block (default: this rank's canonical block, i.e. everything on one GPU)."""
+    one row block (default: this rank's canonical block, i.e. everything on one GPU).
+    ``fetch_rhs=False`` leaves TbemSystem.rhs on the device (``rhs`` is None)."""
     lib = _capi.lib()
     staged = elements if isinstance(elements, StagedMesh) else StagedMesh(elements, ctx)
     ctx = staged.ctx
@@ -195,7 +206,7 @@ def build_tbem_system_with_beta(elements: Mesh | StagedMesh, physics: PhysicsPar
     beta = complex(beta)
     _capi.check(lib.bemb200_assemble_staged(ctx._h, staged._h, C.byref(ph), beta.real, beta.imag, r0, r1, C.byref(h)), ctx._h)
     mat = reuse.matrix if reuse is not None else DeviceMatrix(ctx, h)
-    return TbemSystem(matrix=mat, rhs=mat.rhs(), num_dofs=n)
+    return TbemSystem(matrix=mat, rhs=mat.rhs() if fetch_rhs else None, num_dofs=n)
 
 
 def build_tbem_system(elements, physics: PhysicsParams, **kw) -> TbemSystem:  # tbem.rs:45-51
@@ -317,6 +328,21 @@ def gmres_with_guess(operator: DenseOperator, b: np.ndarray, x0: Optional[np.nda
                 operator.matrix.ctx._h)
     return GmresSolution(x=x, iterations=int(info.iterations), restarts=int(info.restarts), residual=float(info.residual),
                          converged=bool(info.converged))
+
+
+def gmres_device(operator: DenseOperator, b_dev: int, x_dev: int, config: GmresConfig, x0_dev: int = 0) -> GmresSolution:
+    """Same solve with DEVICE pointers (complex128 vectors of num_rows entries); ``x`` of the
+    returned solution is None, the result is in ``x_dev``."""
+    info = _capi.CGmresInfo()
+    _capi.check(_capi.lib().bemb200_gmres_device(operator.matrix._h, C.c_void_p(b_dev), C.c_void_p(x0_dev or None),
+                                                 config.max_iterations, config.restart, config.tolerance, C.c_void_p(x_dev),
+                                                 C.byref(info)), operator.matrix.ctx._h)
+    return GmresSolution(x=None, iterations=int(info.iterations), restarts=int(info.restarts), residual=float(info.residual),
+                         converged=bool(info.converged))
+
+
+def apply_device(operator: DenseOperator, x_dev: int, y_dev: int) -> None:
+    _capi.check(_capi.lib().bemb200_apply_device(operator.matrix._h, C.c_void_p(x_dev), C.c_void_p(y_dev)), operator.matrix.ctx._h)
 
 
 def gmres(operator: DenseOperator, b: np.ndarray, config: GmresConfig) -> GmresSolution:  # gmres.rs:96-102

@@ -108,7 +108,7 @@ int bemb200_device_count(void) {
     return n;
 }
 
-static int ctx_create_common(int device, bemb200_ctx** out) {
+static int ctx_create_common(int device, void* ext_stream, bemb200_ctx** out) {
     if (!out) return set_error(nullptr, BEMB200_EINVAL, "out is NULL");
     *out = nullptr;
     int n = bemb200_device_count();
@@ -124,12 +124,17 @@ static int ctx_create_common(int device, bemb200_ctx** out) {
         delete c;
         return set_error(nullptr, BEMB200_EUNSUPPORTED, msg);
     }
-    BEMB_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    if (ext_stream) {
+        c->stream = (cudaStream_t)ext_stream;
+        c->own_stream = false;
+    } else {
+        BEMB_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    }
     *out = c;
     return BEMB200_OK;
 }
 
-int bemb200_ctx_create(int device, bemb200_ctx** out) { return ctx_create_common(device, out); }
+int bemb200_ctx_create(int device, bemb200_ctx** out) { return ctx_create_common(device, nullptr, out); }
 
 int bemb200_nccl_unique_id(uint8_t out[128]) {
     std::string why;
@@ -142,8 +147,13 @@ int bemb200_nccl_unique_id(uint8_t out[128]) {
 }
 
 int bemb200_ctx_create_dist(int device, int rank, int nranks, const uint8_t nccl_id[128], bemb200_ctx** out) {
+    return bemb200_ctx_create_ex(device, rank, nranks, nccl_id, nullptr, out);
+}
+
+int bemb200_ctx_create_ex(int device, int rank, int nranks, const uint8_t* nccl_id, void* cuda_stream, bemb200_ctx** out) {
     if (nranks < 1 || rank < 0 || rank >= nranks) return set_error(nullptr, BEMB200_EINVAL, "bad rank/nranks");
-    int rc = ctx_create_common(device, out);
+    if (nranks > 1 && !nccl_id) return set_error(nullptr, BEMB200_EINVAL, "nccl_id is NULL");
+    int rc = ctx_create_common(device, cuda_stream, out);
     if (rc != BEMB200_OK) return rc;
     bemb200_ctx* c = *out;
     c->rank = rank;
@@ -171,7 +181,7 @@ void bemb200_ctx_destroy(bemb200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->nccl_comm && ncclshim::CommDestroy) ncclshim::CommDestroy(ctx->nccl_comm);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 

@@ -12,6 +12,7 @@ struct bemb200_ctx {
     int device = 0;
     int rank = 0, nranks = 1;
     cudaStream_t stream = nullptr;
+    bool own_stream = true;
     void* nccl_comm = nullptr;  // ncclComm_t when nranks > 1
     std::string err;
     std::mutex mu;  // LinearOperator is Send + Sync: serialise stream submission per context

@@ -421,6 +421,26 @@ int bemb200_row_sum_correction(bemb200_matrix* m, double* avg) {
     return BEMB200_OK;
 }
 
+int bemb200_rhs_download_full(const bemb200_matrix* cm, double* out) {
+    bemb200_matrix* m = const_cast<bemb200_matrix*>(cm);
+    if (!m || !out) return set_error(nullptr, BEMB200_EINVAL, "NULL argument");
+    bemb200_ctx* ctx = m->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    BEMB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = check_partition(m);
+    if (rc != BEMB200_OK) return rc;
+    rc = ensure_workspace(m, 1);
+    if (rc != BEMB200_OK) return rc;
+    GmresWorkspace* ws = m->ws;
+    cplx* loc = ws->r + (ctx->nranks > 1 ? (uint64_t)ctx->rank * ws->chunk : m->r0);
+    BEMB_CUDA(ctx, cudaMemcpyAsync(loc, m->rhs, (m->r1 - m->r0) * sizeof(cplx), cudaMemcpyDeviceToDevice, ctx->stream));
+    rc = nccl_allgather_bytes(ctx, loc, ws->r, ws->chunk * sizeof(cplx));
+    if (rc != BEMB200_OK) return rc;
+    BEMB_CUDA(ctx, cudaMemcpyAsync(out, ws->r, m->n_rows * sizeof(cplx), cudaMemcpyDeviceToHost, ctx->stream));
+    BEMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BEMB200_OK;
+}
+
 int bemb200_solver_stats(const bemb200_matrix* m, uint64_t* kernel_launches, double* matvec_ms, uint64_t* matvecs) {
     if (!m) return set_error(nullptr, BEMB200_EINVAL, "NULL argument");
     if (kernel_launches) *kernel_launches = m->last_launches;

@@ -299,3 +299,26 @@ def l2_relative(analytical, bem) -> float:
     num = np.sqrt((np.abs(a - b) ** 2).sum())
     den = np.sqrt((np.abs(a) ** 2).sum())
     return float(num / den) if den > 1e-15 else float(num)
+
+
+_APPLY_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p)
+
+
+def gmres_op(apply, n, b, x0=None, max_iterations=100, restart=30, tolerance=1e-6):
+    """gmres_with_guess (gmres.rs:105-277) over an arbitrary Python operator ``apply(x) -> y``
+    (used to model the row-sharded operator of the multi-GPU path on CPU)."""
+    b = np.ascontiguousarray(b, dtype=np.complex128)
+    x = np.zeros(n, dtype=np.complex128)
+    x0a = np.ascontiguousarray(x0, dtype=np.complex128) if x0 is not None else None
+
+    def _cb(_user, xp, yp):
+        xv = np.ctypeslib.as_array(C.cast(xp, C.POINTER(C.c_double)), shape=(2 * n,)).view(np.complex128)
+        yv = np.ctypeslib.as_array(C.cast(yp, C.POINTER(C.c_double)), shape=(2 * n,)).view(np.complex128)
+        yv[:] = apply(xv.copy())
+
+    cb = _APPLY_FN(_cb)
+    info = GmresInfo()
+    lib().orc_gmres_op(cb, None, C.c_uint64(n), _p(b), _p(x0a) if x0a is not None else None, C.c_uint32(max_iterations),
+                       C.c_uint32(restart), C.c_double(tolerance), _p(x), C.byref(info))
+    return x, dict(iterations=int(info.iterations), restarts=int(info.restarts), residual=float(info.residual),
+                   converged=bool(info.converged))

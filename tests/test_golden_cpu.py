@@ -1,0 +1,167 @@
+"""CPU suite: the oracle against the committed golden fixtures, the host-side logic, and the
+C-ABI library surface (load + exported symbols; no compute without a GPU)."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from math_audio_b200.mesh import (fibonacci_directions, generate_box_mesh_quad, generate_geodesic_sphere_mesh,
+                                  generate_icosphere_mesh, generate_sphere_mesh)
+from math_audio_b200.types import PhysicsParams
+
+ROOT = Path(__file__).resolve().parent.parent
+GOLD = ROOT / "tests" / "golden"
+
+
+def box_piston_mesh():
+    mesh = generate_box_mesh_quad(0.32, 0.44, 0.64, 4, 6, 8)
+    front = (np.abs(mesh.center[:, 1] + 0.22) < 1e-9) & (np.hypot(mesh.center[:, 0], mesh.center[:, 2]) < 0.12)
+    v = np.zeros((mesh.n_elem, 4), dtype=np.complex128)
+    v[front] = 1.0
+    mesh.set_velocity_bc(v)
+    mesh.bc_len[~front] = 1
+    return mesh, front
+
+
+# ---- oracle vs frozen fixtures -------------------------------------------------------
+@pytest.mark.parametrize("name", ["ico1_ka0p5", "ico2_ka0p2", "ico2_ka6"])
+def test_oracle_matches_golden_sphere(orc, name):
+    g = np.load(GOLD / f"{name}.npz")
+    mesh = generate_icosphere_mesh(float(g["a"]), int(g["sub"]))
+    A, rhs0, nq = orc.assemble(mesh, float(g["k"]), complex(g["beta"]))
+    # same compiler flags, same libm => bit-identical; allow 1e-13 for a different libm
+    assert np.max(np.abs(A - g["A"]) / np.abs(g["A"])) < 1e-13
+    assert nq == int(g["nqp"])
+    x, info = orc.gmres(g["A"], g["b"], max_iterations=1000, restart=50, tolerance=1e-10)
+    assert info["iterations"] == int(g["iterations"]) and info["restarts"] == int(g["restarts"])
+    assert np.linalg.norm(x - g["x"]) / np.linalg.norm(g["x"]) < 1e-12
+    # independent check of the frozen solution (LAPACK)
+    xl = np.linalg.solve(g["A"], g["b"])
+    assert np.linalg.norm(g["x"] - xl) / np.linalg.norm(xl) < 1e-8
+
+
+def test_oracle_matches_golden_box(orc):
+    g = np.load(GOLD / "box_4x6x8_piston.npz")
+    mesh, front = box_piston_mesh()
+    assert (front == g["front"]).all() and front.sum() == 4
+    A, rhs, nq = orc.assemble(mesh, float(g["k"]), complex(g["beta"]))
+    assert np.max(np.abs(A - g["A"])) / np.max(np.abs(g["A"])) < 1e-13
+    assert np.max(np.abs(rhs - g["rhs"])) / np.max(np.abs(g["rhs"])) < 1e-13
+    assert np.abs(g["rhs"]).min() > 0  # every row sees the piston (tbem.rs:164,342-344)
+
+
+def test_oracle_row_blocks_equal_full(orc):
+    mesh = generate_icosphere_mesh(0.1, 1)
+    ph = PhysicsParams.from_wave_number(5.0)
+    beta = ph.burton_miller_beta_scaled(4.0)
+    A, rhs, _ = orc.assemble(mesh, ph.wave_number, beta)
+    A1, r1, _ = orc.assemble(mesh, ph.wave_number, beta, row_begin=0, row_end=33)
+    A2, r2, _ = orc.assemble(mesh, ph.wave_number, beta, row_begin=33, row_end=80)
+    assert (np.vstack([A1, A2]) == A).all() and (np.concatenate([r1, r2]) == rhs).all()
+    # thread count must not change a single bit (rows are independent)
+    A3, _, _ = orc.assemble(mesh, ph.wave_number, beta, nthreads=1)
+    assert (A3 == A).all()
+
+
+def test_oracle_eval_elements_and_dof_permutation(orc):
+    mesh = generate_icosphere_mesh(0.1, 1)
+    ph = PhysicsParams.from_wave_number(5.0)
+    beta = ph.burton_miller_beta()
+    A, _, _ = orc.assemble(mesh, ph.wave_number, beta)
+    perm = np.random.default_rng(7).permutation(mesh.n_elem).astype(np.uint32)
+    mesh.dof[:] = perm
+    Ap, _, _ = orc.assemble(mesh, ph.wave_number, beta)
+    # A[dof_i, dof_j] = entry of (element i, element j)
+    assert (Ap[np.ix_(perm, perm)] == A).all()
+    # evaluation elements are skipped as sources and as field elements (tbem.rs:128-131,152-155)
+    mesh = generate_icosphere_mesh(0.1, 1)
+    mesh.is_eval[-5:] = 1
+    assert mesh.num_dofs == 75
+    Ae, _, _ = orc.assemble(mesh, ph.wave_number, beta)
+    assert Ae.shape == (75, 75)
+    # NB the dg_dn_sign heuristic still reads the first 100 elements, evaluation or not
+    assert np.max(np.abs(Ae - A[:75, :75])) == 0.0
+
+
+# ---- host logic --------------------------------------------------------------------------
+def test_physics_params_beta_variants():
+    ph = PhysicsParams.new(1000.0, 343.0, 1.21, False)  # types.rs:745-751
+    assert abs(ph.wave_number - 2 * np.pi * 1000 / 343) < 1e-10 and abs(ph.wave_length - 0.343) < 1e-10 and ph.tau == 1.0
+    k = ph.wave_number
+    assert ph.burton_miller_beta() == complex(0, 1 / k)
+    assert ph.burton_miller_beta_scaled(4.0) == complex(0, 4 / k)
+    assert ph.burton_miller_beta_optimal(0.01) == complex(0, 1 / (k + 100.0))
+    a = 0.1
+    for ka, scale in [(0.49, 1.0), (0.5, 4.0), (1.19, 4.0), (1.2, 8.0), (1.79, 8.0), (1.8, 16.0), (8.0, 16.0)]:
+        p = PhysicsParams.from_wave_number(ka / a)
+        b, s = p.burton_miller_beta_adaptive(a)
+        assert s == scale and abs(b - complex(0, scale / p.wave_number)) < 1e-15
+    pin = PhysicsParams.new(100.0, 343.0, 1.21, True)
+    assert pin.tau == -1.0 and pin.burton_miller_beta() == 0 and pin.burton_miller_beta_adaptive(1.0) == (0j, 1.0)
+
+
+def test_mesh_generators_counts():
+    assert generate_sphere_mesh(0.1, 32, 32).n_elem == 1984  # config 1
+    m = generate_icosphere_mesh(0.1, 3)
+    assert m.n_elem == 1280 and m.n_nodes == 642
+    g = generate_geodesic_sphere_mesh(1.0, 6)
+    assert g.n_elem == 20 * 36 and g.n_nodes == 10 * 36 + 2
+    assert np.abs(np.linalg.norm(g.nodes, axis=1) - 1).max() < 1e-12 and g.meta["n_flipped"] == 0
+    # class-I geodesic with nu = 2^s has the icosphere's element count
+    assert generate_geodesic_sphere_mesh(1.0, 4).n_elem == generate_icosphere_mesh(1.0, 2).n_elem
+    b = generate_box_mesh_quad(0.32, 0.44, 0.64, 4, 6, 8)
+    assert b.n_elem == 2 * (4 * 6 + 4 * 8 + 6 * 8) and (b.etype == 4).all()
+    assert b.meta["n_flipped"] == 0 and ((b.normal * b.center).sum(1) > 0).all()  # outward winding
+    assert abs(b.area.sum() - 2 * (0.32 * 0.44 + 0.32 * 0.64 + 0.44 * 0.64)) < 1e-12
+    d = fibonacci_directions(32)
+    assert d.shape == (32, 3) and np.abs(np.linalg.norm(d, axis=1) - 1).max() < 1e-12
+    for mm in (m, g, b):
+        mm.validate()
+
+
+def test_incident_rhs_matches_oracle(orc):
+    from math_audio_b200.incident import IncidentField
+
+    mesh = generate_icosphere_mesh(0.1, 2)
+    ph = PhysicsParams.from_wave_number(12.0)
+    beta = ph.burton_miller_beta_scaled(4.0)
+    for kind, vec in [(0, [0, 0, 1.0]), (0, [0.6, 0.0, 0.8]), (1, [0.3, 0.1, -0.4])]:
+        inc = IncidentField.plane_wave(vec) if kind == 0 else IncidentField.point_source(vec)
+        got = inc.compute_rhs_with_beta(mesh.center, mesh.normal, ph, beta)
+        ref, pinc = orc.incident_rhs(kind, vec, 1.0, mesh.center, mesh.normal, ph.wave_number, beta)
+        assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < 1e-13
+        assert np.max(np.abs(inc.evaluate_pressure(mesh.center, ph) - pinc)) < 1e-13
+
+
+# ---- the C-ABI library: loads, exports everything the header declares, fails loudly --------
+def test_capi_exports_every_declared_symbol():
+    from math_audio_b200 import _capi
+
+    header = (ROOT / "include" / "bemb200.h").read_text()
+    declared = set(re.findall(r"\b(bemb200_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 30
+    assert declared == set(_capi.SYMBOLS), declared ^ set(_capi.SYMBOLS)
+    lib = C.CDLL(str(_capi.LIB_PATH))
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_capi_partition_and_loud_failure_without_gpu():
+    from math_audio_b200 import _capi, bem
+
+    lib = _capi.lib()
+    for n, p in [(20480, 8), (121680, 8), (10, 3), (5, 8)]:
+        covered = []
+        for r in range(p):
+            b, e = C.c_uint64(), C.c_uint64()
+            lib.bemb200_partition(n, p, r, C.byref(b), C.byref(e))
+            covered += list(range(b.value, e.value)) if n < 100 else []
+            assert b.value <= e.value <= n
+        if n < 100:
+            assert covered == list(range(n))
+    if lib.bemb200_device_count() == 0:
+        with pytest.raises(_capi.Bemb200Error) as ei:
+            bem.Context(0)
+        assert ei.value.code == -2 and "no CPU fallback" in str(ei.value)

@@ -1,0 +1,358 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI
+(math_audio_b200.bem -> ctypes -> libbemb200.so), against the CPU oracle and the committed
+golden fixtures.
+
+Tolerances (BASELINE.json north_star): matrix entries relative 1e-10 in FP64; surface
+pressure after GMRES relative 1e-8 (GMRES tol 1e-10 on both sides).
+"""
+import math
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from math_audio_b200.mesh import (BC_PRESSURE, BC_TRANSFER, generate_box_mesh_quad, generate_icosphere_mesh,
+                                  generate_sphere_mesh, mesh_from_data)
+from math_audio_b200.types import PhysicsParams
+
+pytestmark = pytest.mark.gpu
+
+ENTRY_TOL = 1e-10
+X_TOL = 1e-8
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+@pytest.fixture(scope="module")
+def bem():
+    from math_audio_b200 import bem as b
+
+    b.default_context()  # raises loudly if the extension or the GPU is missing
+    return b
+
+
+def entry_err(A, Aref):
+    """max |dA_ij|/|A_ij| where the reference entry is not (numerically) zero, plus the
+    row-normwise error everywhere (SURVEY 8d 'Tolerances & metrics')."""
+    scale = np.max(np.abs(Aref), axis=1, keepdims=True)
+    rownorm = np.max(np.abs(A - Aref) / scale)
+    big = np.abs(Aref) > 1e-9 * scale
+    rel = np.max(np.abs(A - Aref)[big] / np.abs(Aref)[big])
+    return rel, rownorm
+
+
+def box_piston_mesh(nx=4, ny=6, nz=8):
+    mesh = generate_box_mesh_quad(0.32, 0.44, 0.64, nx, ny, nz)
+    front = (np.abs(mesh.center[:, 1] + 0.22) < 1e-9) & (np.hypot(mesh.center[:, 0], mesh.center[:, 2]) < 0.12)
+    v = np.zeros((mesh.n_elem, 4), dtype=np.complex128)
+    v[front] = 1.0
+    mesh.set_velocity_bc(v)
+    mesh.bc_len[~front] = 1
+    return mesh, front
+
+
+def test_far_kernel_math(bem):
+    ctx = bem.default_context()
+    for xmax in (50.0, 200.0, 5000.0):
+        sc, rs = ctx.selftest_math(1 << 21, xmax)
+        assert sc < 5e-16 * max(1.0, xmax / 200.0), (xmax, sc)  # abs error of sin/cos
+        assert rs < 5e-16, rs                                    # rel error of 1/sqrt
+
+
+@pytest.mark.parametrize("name", ["ico1_ka0p5", "ico2_ka0p2", "ico2_ka6"])
+def test_golden_sphere(bem, name):
+    g = np.load(GOLD / f"{name}.npz")
+    a, k, beta = float(g["a"]), float(g["k"]), complex(g["beta"])
+    mesh = generate_icosphere_mesh(a, int(g["sub"]))
+    ph = PhysicsParams.from_wave_number(k)
+    assert ph.wave_number == pytest.approx(k, rel=1e-15)
+    ph.wave_number = k
+    system = bem.build_tbem_system_with_beta(mesh, ph, beta)
+    rel, rown = entry_err(system.matrix.rows(), g["A"])
+    assert rel < ENTRY_TOL and rown < ENTRY_TOL, (rel, rown)
+    op = bem.DenseOperator(system)
+    sol = bem.gmres(op, g["b"], bem.GmresConfig(max_iterations=1000, restart=50, tolerance=1e-10))
+    assert sol.converged and sol.iterations == int(g["iterations"]) and sol.restarts == int(g["restarts"])
+    assert np.linalg.norm(sol.x - g["x"]) / np.linalg.norm(g["x"]) < X_TOL
+
+
+def test_golden_box_piston_rhs(bem):
+    g = np.load(GOLD / "box_4x6x8_piston.npz")
+    mesh, front = box_piston_mesh()
+    ph = PhysicsParams.new(500.0, 343.0, 1.21, False)
+    system = bem.build_tbem_system_with_beta(mesh, ph, complex(g["beta"]))
+    rel, rown = entry_err(system.matrix.rows(), g["A"])
+    assert rown < ENTRY_TOL and rel < 1e-9, (rel, rown)  # coplanar pairs: H ~ 1e-17 noise vs exact 0
+    assert np.max(np.abs(system.rhs - g["rhs"])) / np.max(np.abs(g["rhs"])) < ENTRY_TOL
+    st = system.matrix.assembly_stats()
+    assert st["special_pairs"] == int(front.sum()) * mesh.n_elem  # piston columns take the generic path
+
+
+@pytest.mark.parametrize("sub,ka", [(3, 0.2), (3, 1.0), (3, 3.0), (3, 8.0), (3, 16.0)])
+def test_full_matrix_parity_icosphere(bem, orc, sub, ka):
+    """All N^2 entries.  ka=8/16 on icosphere(3) reach k*h_e >= 1 and >= 2: the nsec2 = 3 / 4
+    duplicate-sub-triangle quirk of the singular integration (singular.rs:268-278)."""
+    a = 0.1
+    ph = PhysicsParams.from_wave_number(ka / a)
+    mesh = generate_icosphere_mesh(a, sub)
+    beta, _ = ph.burton_miller_beta_adaptive(a)
+    system = bem.build_tbem_system_with_beta(mesh, ph, beta)
+    Ao, rhso, _ = orc.assemble(mesh, ph.wave_number, beta)
+    rel, rown = entry_err(system.matrix.rows(), Ao)
+    assert rel < ENTRY_TOL and rown < ENTRY_TOL, (rel, rown)
+    assert np.abs(system.rhs).max() == 0.0 and np.abs(rhso).max() == 0.0  # rigid: v = 0
+    assert system.matrix.ctx and bem.StagedMesh(mesh).dg_dn_sign(ph.wave_number) == orc.dg_dn_sign(mesh, ph.wave_number)
+
+
+def test_config1_uv_sphere_solve_and_mie(bem, orc):
+    """BASELINE.json configs[0]: rigid UV sphere (32x32 -> 1984 Tri3), ka = 1, plane wave +z,
+    beta = adaptive (4i/k); GMRES(50) tol 1e-10; L2 vs the 50-term Mie series must EQUAL the
+    oracle's (the reference's own accuracy here is ~27 %, qa_suite.rs:175-179)."""
+    from math_audio_b200.incident import IncidentField
+
+    a = 0.1
+    ph = PhysicsParams.from_wave_number(1.0 / a)
+    mesh = generate_sphere_mesh(a, 32, 32)
+    assert mesh.n_elem == 1984
+    beta, scale = ph.burton_miller_beta_adaptive(a)
+    assert scale == 4.0
+    system = bem.build_tbem_system_with_beta(mesh, ph, beta)
+    Ao, rhso, _ = orc.assemble(mesh, ph.wave_number, beta)
+    rel, rown = entry_err(system.matrix.rows(), Ao)
+    assert rel < ENTRY_TOL and rown < ENTRY_TOL, (rel, rown)
+    b = system.rhs + IncidentField.plane_wave_z().compute_rhs_with_beta(mesh.center, mesh.normal, ph, beta)
+    bo = rhso + orc.incident_rhs(0, [0, 0, 1.0], 1.0, mesh.center, mesh.normal, ph.wave_number, beta)[0]
+    assert np.max(np.abs(b - bo)) < 1e-13
+    cfg = bem.GmresConfig(max_iterations=1000, restart=50, tolerance=1e-10)
+    sol = bem.solve_gmres(bem.DenseOperator(system), b, cfg)
+    xo, io = orc.gmres(Ao, bo, max_iterations=1000, restart=50, tolerance=1e-10)
+    assert sol.converged and abs(sol.iterations - io["iterations"]) <= 1
+    assert np.linalg.norm(sol.x - xo) / np.linalg.norm(xo) < X_TOL
+    xl = np.linalg.solve(Ao, bo)
+    assert np.linalg.norm(sol.x - xl) / np.linalg.norm(xl) < X_TOL
+    r = np.linalg.norm(mesh.center, axis=1)
+    mie = orc.mie_rigid_sphere(ph.wave_number, a, 50, r, np.arccos(mesh.center[:, 2] / r))
+    e_gpu, e_orc = orc.l2_relative(mie, sol.x), orc.l2_relative(mie, xo)
+    assert abs(e_gpu - e_orc) < 1e-8 and e_gpu < 0.30
+    # far field: 72 points on r = 10a in the xz-plane through the oracle's field evaluation
+    th = np.linspace(0, 2 * math.pi, 72, endpoint=False)
+    pts = np.stack([10 * a * np.sin(th), np.zeros_like(th), 10 * a * np.cos(th)], axis=1)
+    fg = orc.scattered_field(mesh, pts, sol.x, ph.wave_number)
+    fo = orc.scattered_field(mesh, pts, xo, ph.wave_number)
+    assert np.linalg.norm(fg - fo) / np.linalg.norm(fo) < X_TOL
+
+
+def test_mixed_bc_and_element_types(bem, orc):
+    """Pressure / transfer BCs, 1-entry non-zero velocity (the N0-weighted quirk of
+    regular.rs:159-164), Tri3 + Quad4 in one mesh, a warped (non-planar) Quad4."""
+    box = generate_box_mesh_quad(0.3, 0.4, 0.5, 3, 4, 5)
+    nodes = box.nodes.copy()
+    quads = box.conn[:, :4].copy()
+    # split every quad of the z = -0.25 wall into two triangles, keep the others as quads
+    conn = []
+    for q in quads:
+        if abs(nodes[q, 2].mean() + 0.25) < 1e-12:
+            conn.append([q[0], q[1], q[2]])
+            conn.append([q[0], q[2], q[3]])
+        else:
+            conn.append(list(q))
+    # warp one wall out of plane so that some quads are not flat
+    warped = np.abs(nodes[:, 0] - 0.15) < 1e-12
+    nodes[warped, 0] += 0.01 * np.sin(17.0 * nodes[warped, 1]) * np.cos(11.0 * nodes[warped, 2])
+    mesh = mesh_from_data(nodes, conn)
+    n = mesh.n_elem
+    rng = np.random.default_rng(5)
+    pick = rng.permutation(n)
+    mesh.bc_type[pick[:9]] = BC_PRESSURE
+    mesh.bc_val[pick[:5], 0] = 0.7 - 0.2j          # pressure, 1 value
+    mesh.bc_type[pick[9:12]] = BC_TRANSFER
+    mesh.bc_val[pick[12:20], 0] = 1.0 + 0.5j        # velocity, single entry -> v * N0
+    full = pick[20:26]
+    mesh.bc_len[full] = mesh.etype[full]
+    mesh.bc_val[full] = 0.0
+    for e in full:
+        mesh.bc_val[e, : mesh.etype[e]] = rng.standard_normal(mesh.etype[e]) + 1j * rng.standard_normal(mesh.etype[e])
+    assert set(np.unique(mesh.etype)) == {3, 4}
+    for freq in (200.0, 2500.0):
+        ph = PhysicsParams.new(freq, 343.0, 1.21, False)
+        beta = ph.burton_miller_beta_scaled(2.0)
+        system = bem.build_tbem_system_with_beta(mesh, ph, beta)
+        Ao, rhso, _ = orc.assemble(mesh, ph.wave_number, beta)
+        A = system.matrix.rows()
+        rel, rown = entry_err(A, Ao)
+        assert rown < ENTRY_TOL, (freq, rel, rown)
+        assert np.abs(A[:, mesh.dof[pick[9:12]]]).max() == 0.0  # transfer columns contribute 0
+        assert np.max(np.abs(system.rhs - rhso)) / np.max(np.abs(rhso)) < ENTRY_TOL
+        assert system.matrix.assembly_stats()["special_pairs"] > 0
+
+
+def test_row_blocks_eval_elements_and_dof_permutation(bem, orc):
+    mesh = generate_icosphere_mesh(0.1, 2)
+    ph = PhysicsParams.from_wave_number(15.0)
+    beta = ph.burton_miller_beta_scaled(4.0)
+    full = bem.build_tbem_system_with_beta(mesh, ph, beta).matrix.rows()
+    st = bem.StagedMesh(mesh)
+    parts = [bem.build_tbem_system_with_beta(st, ph, beta, rows=(r0, r1)).matrix.rows() for r0, r1 in [(0, 1), (1, 130), (130, 320)]]
+    assert (np.vstack(parts) == full).all()  # row sharding changes no bit
+    empty = bem.build_tbem_system_with_beta(st, ph, beta, rows=(7, 7))
+    assert empty.matrix.rows().shape == (0, 320) and empty.rhs.shape == (0,)
+    perm = np.random.default_rng(3).permutation(mesh.n_elem).astype(np.uint32)
+    mesh.dof[:] = perm
+    Ap = bem.build_tbem_system_with_beta(mesh, ph, beta).matrix.rows()
+    Ao, _, _ = orc.assemble(mesh, ph.wave_number, beta)
+    assert entry_err(Ap, Ao)[0] < ENTRY_TOL
+    mesh = generate_icosphere_mesh(0.1, 2)
+    mesh.is_eval[::7] = 1
+    mesh.dof[mesh.is_eval == 0] = np.arange(mesh.num_dofs, dtype=np.uint32)
+    Ae = bem.build_tbem_system_with_beta(mesh, ph, beta).matrix.rows()
+    Ao, _, _ = orc.assemble(mesh, ph.wave_number, beta)
+    assert Ae.shape == (mesh.num_dofs, mesh.num_dofs) and entry_err(Ae, Ao)[0] < ENTRY_TOL
+
+
+def test_row_sum_correction(bem, orc):
+    mesh = generate_icosphere_mesh(0.1, 2)
+    ph = PhysicsParams.from_wave_number(2.0)
+    system, avg = bem.build_tbem_system_corrected(mesh, ph)
+    Ao, _, _ = orc.assemble(mesh, ph.wave_number, ph.burton_miller_beta())
+    avg_o = orc.row_sum_correction(Ao)
+    assert abs(avg - avg_o) < 1e-12
+    assert entry_err(system.matrix.rows(), Ao)[1] < ENTRY_TOL
+    assert np.abs(system.matrix.rows().sum(axis=1)).max() < 1e-11
+
+
+def test_invalid_inputs_fail_loudly(bem):
+    from math_audio_b200._capi import Bemb200Error
+
+    mesh = generate_icosphere_mesh(0.1, 1)
+    ph = PhysicsParams.from_wave_number(5.0)
+    mesh.dof[3] = mesh.dof[4]
+    with pytest.raises(Bemb200Error) as ei:
+        bem.build_tbem_system(mesh, ph)
+    assert ei.value.code == -1 and "permutation" in str(ei.value)
+    mesh = generate_icosphere_mesh(0.1, 1)
+    mesh.conn[0, 0] = 10_000
+    with pytest.raises(Bemb200Error):
+        bem.build_tbem_system(mesh, ph)
+    mesh = generate_icosphere_mesh(0.1, 1)
+    with pytest.raises(Bemb200Error):
+        bem.build_tbem_system_with_beta(mesh, ph, 1j, rows=(10, 200))
+    op = bem.DenseOperator(np.eye(4, dtype=np.complex128))
+    with pytest.raises(ValueError):
+        op.apply(np.zeros(5, dtype=np.complex128))  # the reference panics on shape mismatch
+    with pytest.raises(ValueError):
+        bem.gmres(op, np.zeros(3, dtype=np.complex128), bem.GmresConfig())
+    with pytest.raises(Bemb200Error):  # gmres needs a square operator
+        bem.gmres(bem.DenseOperator(np.ones((3, 5), dtype=np.complex128)), np.ones(3, dtype=np.complex128), bem.GmresConfig())
+
+
+# ---- operator + GMRES: the reference's own tests through the GPU operator ----------------------
+def tridiag(n, d, lo, up):
+    A = np.zeros((n, n), dtype=np.complex128)
+    for i in range(n):
+        A[i, i] = d
+        if i > 0:
+            A[i, i - 1] = lo
+        if i < n - 1:
+            A[i, i + 1] = up
+    return A
+
+
+def test_dense_operator_apply(bem):
+    rng = np.random.default_rng(1234)
+    for shape in [(1, 1), (3, 5), (257, 300), (1000, 513), (2048, 2048)]:
+        A = rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+        op = bem.DenseOperator(A)
+        assert (op.num_rows(), op.num_cols()) == shape and op.is_square() == (shape[0] == shape[1])
+        x = rng.standard_normal(shape[1]) + 1j * rng.standard_normal(shape[1])
+        xt = rng.standard_normal(shape[0]) + 1j * rng.standard_normal(shape[0])
+        for got, ref in [(op.apply(x), A @ x), (op.apply_transpose(xt), A.T @ xt), (op.apply_hermitian(xt), A.conj().T @ xt)]:
+            assert np.linalg.norm(got - ref) <= 1e-13 * np.linalg.norm(ref) + 1e-300
+        # linearity and determinism
+        assert (op.apply(x) == op.apply(x)).all()
+        assert np.linalg.norm(op.apply(2.5 * x) - 2.5 * op.apply(x)) <= 1e-13 * np.linalg.norm(A @ x) + 1e-300
+
+
+def test_gmres_reference_kats(bem, orc):
+    A = np.array([[4.0, 1.0], [1.0, 3.0]], dtype=np.complex128)        # gmres.rs:631-655
+    b = np.array([1.0, 2.0], dtype=np.complex128)
+    sol = bem.gmres(bem.DenseOperator(A), b, bem.GmresConfig(100, 10, 1e-10))
+    assert sol.converged and np.linalg.norm(A @ sol.x - b) < 1e-8
+    n = 5                                                               # gmres.rs:657-680
+    b = np.arange(1, n + 1, dtype=np.complex128)
+    sol = bem.gmres(bem.DenseOperator(np.eye(n, dtype=np.complex128)), b, bem.GmresConfig(10, 10, 1e-12))
+    assert sol.converged and sol.iterations <= 2 and np.linalg.norm(sol.x - b) < 1e-10
+    sol = bem.gmres(bem.DenseOperator(np.eye(3, dtype=np.complex128)), np.zeros(3, dtype=np.complex128), bem.GmresConfig())
+    assert (sol.iterations, sol.restarts, sol.residual, sol.converged) == (0, 0, 0.0, True) and (sol.x == 0).all()
+    n = 20                                                              # test_fmm_validation.rs:537-585
+    A = tridiag(n, 10.0, complex(-1.0, 0.1), complex(-1.0, -0.1))
+    b = np.array([math.sin(i * 0.3) for i in range(n)], dtype=np.complex128)
+    sol = bem.solve_gmres(bem.DenseOperator(A), b, bem.GmresConfig(50, 15, 1e-10))
+    xo, io = orc.gmres(A, b, max_iterations=50, restart=15, tolerance=1e-10)
+    assert sol.converged and (sol.iterations, sol.restarts) == (io["iterations"], io["restarts"])
+    assert np.linalg.norm(A @ sol.x - b) / np.linalg.norm(b) < 1e-8 and np.linalg.norm(sol.x - xo) < 1e-12
+    n = 50                                                              # test_fmm_validation.rs:640-700
+    A = tridiag(n, 4.0, -1.0, -1.0)
+    b = np.ones(n, dtype=np.complex128)
+    small = bem.gmres(bem.DenseOperator(A), b, bem.GmresConfig(100, 5, 1e-10))
+    large = bem.gmres(bem.DenseOperator(A), b, bem.GmresConfig(100, 50, 1e-10))
+    xs, osm = orc.gmres(A, b, max_iterations=100, restart=5, tolerance=1e-10)
+    assert small.converged and large.converged and large.restarts <= small.restarts
+    assert (small.iterations, small.restarts) == (osm["iterations"], osm["restarts"])
+    assert np.linalg.norm(small.x - xs) / np.linalg.norm(xs) < 1e-10
+    # budget exhausted: converged = false and the TRUE residual is reported (gmres.rs:264-276)
+    sol = bem.gmres(bem.DenseOperator(A), b, bem.GmresConfig(1, 3, 1e-14))
+    assert (not sol.converged) and sol.restarts == 1 and sol.iterations == 3
+    assert abs(sol.residual - np.linalg.norm(b - A @ sol.x) / np.linalg.norm(b)) < 1e-12
+    # initial guess (gmres_with_guess): starting from the solution converges in 0 iterations
+    xl = np.linalg.solve(A, b)
+    sol = bem.gmres_with_guess(bem.DenseOperator(A), b, xl, bem.GmresConfig(10, 10, 1e-10))
+    assert sol.converged and sol.iterations == 0
+
+
+# ---- full benchmark size: size-independent properties ---------------------------------------------
+@pytest.fixture(scope="module")
+def big(bem):
+    a = 0.1
+    mesh = generate_icosphere_mesh(a, 5)  # 20 480 elements: BASELINE.json configs[1]
+    st = bem.StagedMesh(mesh)
+    return a, mesh, st
+
+
+@pytest.mark.parametrize("ka", [0.25, 2.0, 8.0])
+def test_config2_sampled_rows_and_solve(bem, orc, big, ka):
+    from math_audio_b200.incident import IncidentField
+
+    a, mesh, st = big
+    n = mesh.n_elem
+    ph = PhysicsParams.from_wave_number(ka / a)
+    beta, _ = ph.burton_miller_beta_adaptive(a)
+    system = bem.build_tbem_system_with_beta(st, ph, beta)
+    # >= 64 sampled rows incl. the first/last, icosahedron-vertex neighbourhoods and random rows
+    rng = np.random.default_rng(99)
+    rows = sorted(set([0, 1, 2, 3, 4, n - 1, n - 2] + list(rng.integers(0, n, 57))))
+    assert len(rows) >= 60
+    worst = 0.0
+    for r in rows:
+        Ar = system.matrix.rows(r, r + 1)
+        Ao, _, _ = orc.assemble(mesh, ph.wave_number, beta, row_begin=r, row_end=r + 1)
+        worst = max(worst, *entry_err(Ar, Ao))
+    assert worst < ENTRY_TOL, worst
+    st_a = system.matrix.assembly_stats()
+    assert 20 * n < st_a["near_pairs"] < 40 * n  # ~28 near pairs per row
+    op = bem.DenseOperator(system)
+    b = system.rhs + IncidentField.plane_wave_z().compute_rhs_with_beta(mesh.center, mesh.normal, ph, beta)
+    sol = bem.gmres(op, b, bem.GmresConfig(max_iterations=1000, restart=50, tolerance=1e-10))
+    assert sol.converged and sol.residual < 1e-10
+    # independent residual through the operator boundary + linearity of the operator
+    res = np.linalg.norm(b - op.apply(sol.x)) / np.linalg.norm(b)
+    assert res < 2e-10
+    x2 = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    y1, y2 = op.apply(sol.x), op.apply(x2)
+    assert np.linalg.norm(op.apply(sol.x + 3.0 * x2) - (y1 + 3.0 * y2)) < 1e-12 * np.linalg.norm(y1 + 3.0 * y2)
+    # sampled-row matvec parity against the oracle rows
+    for r in rows[:8]:
+        Ao, _, _ = orc.assemble(mesh, ph.wave_number, beta, row_begin=r, row_end=r + 1)
+        assert abs(y2[r] - (Ao @ x2)[0]) < 1e-12 * np.linalg.norm(Ao) * np.linalg.norm(x2)
+    if ka < 0.5:
+        # +K' branch: closed-surface row sums ~ -1 (tbem.rs:487-493)
+        ones = op.apply(np.ones(n, dtype=np.complex128))
+        assert np.abs(ones + 1.0).max() < 0.05
