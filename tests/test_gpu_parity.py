@@ -353,6 +353,7 @@ def test_config2_sampled_rows_and_solve(bem, orc, big, ka):
         Ao, _, _ = orc.assemble(mesh, ph.wave_number, beta, row_begin=r, row_end=r + 1)
         assert abs(y2[r] - (Ao @ x2)[0]) < 1e-12 * np.linalg.norm(Ao) * np.linalg.norm(x2)
     if ka < 0.5:
-        # +K' branch: closed-surface row sums ~ -1 (tbem.rs:487-493)
+        # +K' branch: closed-surface row sums = -1/2 + K'[1] + beta E[1] ~ -1 (tbem.rs:487-493); the
+        # beta E[1] quadrature residue is O(0.1) here, exactly as in the oracle
         ones = op.apply(np.ones(n, dtype=np.complex128))
-        assert np.abs(ones + 1.0).max() < 0.05
+        assert np.abs(ones.real + 1.0).max() < 0.05 and np.abs(ones + 1.0).max() < 0.2
