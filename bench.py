@@ -96,8 +96,12 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                        "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+            t0 = time.time()  # nvidia-smi needs a moment before its first sample
+            while time.time() - t0 < 3.0 and os.path.getsize(self.f.name) == 0:
+                time.sleep(0.05)
+            self.skip = len(open(self.f.name).read().splitlines())  # samples taken before the timed region
         except Exception:
             self.p = None
 
@@ -113,7 +117,7 @@ class ClockSampler:
         self.f.flush()
         self.f.seek(0)
         sm, mx, reasons = [], [], set()
-        for line in self.f.read().splitlines():
+        for line in self.f.read().splitlines()[getattr(self, "skip", 0):]:
             c = [x.strip() for x in line.split(",")]
             if len(c) < 9:
                 continue
@@ -238,6 +242,8 @@ def run_native(args):
         raise SystemExit("for --gpus N > 1 launch with torchrun (one process per GPU)")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libbemb200 has no CPU fallback (use --impl reference for the CPU arm)")
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: ONE JSON line only
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -276,7 +282,15 @@ def run_native(args):
         state["system"] = bem.build_tbem_system_with_beta(staged, ph, beta, reuse=state["system"], fetch_rhs=False)
         if state["op"] is None:
             state["op"] = bem.DenseOperator(state["system"])
+        tq = time.perf_counter()
         sol = bem.gmres_device(state["op"], b_dev[s].data_ptr(), x_dev.data_ptr(), cfg)
+        if os.environ.get("BENCH_DEBUG"):
+            import ctypes
+            from math_audio_b200 import _capi
+            la, wa = ctypes.c_double(), ctypes.c_double()
+            _capi.lib().bemb200_debug_times(ctypes.byref(la), ctypes.byref(wa))
+            ss = state["system"].matrix.solver_stats()
+            print(f"[value rank {rank}] step {s}: gmres wall {(time.perf_counter() - tq) * 1e3:.2f} ms it {sol.iterations} launch {la.value / 1e3:.2f} ms wait {wa.value / 1e3:.2f} ms matvec {ss['matvec_ms']:.2f} ms", file=sys.stderr)
         if record:
             a_st = state["system"].matrix.assembly_stats()
             s_st = state["system"].matrix.solver_stats()
@@ -292,8 +306,10 @@ def run_native(args):
 
     for s in range(args.warmup):
         step_device(s, False)
-    barrier()
+    # start the clock sampler BEFORE the barrier: nvidia-smi's start-up stalls CUDA calls for
+    # ~100 ms and must not leak into any rank's timed region
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
         ev0.record(stream)
@@ -311,15 +327,26 @@ def run_native(args):
     e2e_steps = max(1, min(args.steps, 4))
     sys_e2e = state["system"]
     x_pinned = torch.empty(n, dtype=torch.complex128).pin_memory().numpy()
+    # one untimed warm-up pass of the host-buffer path (first-use costs of the staging copies)
+    _, ph_w, beta_w = physics_for(wl, 0)
+    sys_e2e = bem.build_tbem_system_with_beta(mesh, ph_w, beta_w, ctx=ctx, reuse=sys_e2e)
+    bem.gmres(bem.DenseOperator(sys_e2e), b_host[0], bem.GmresConfig(max_iterations=1, restart=2, tolerance=1e-10))
     barrier()
     t0 = time.perf_counter()
     h2d = d2h = 0
+    dbg = os.environ.get("BENCH_DEBUG")
     for s in range(args.warmup, args.warmup + e2e_steps):
         ka, ph, beta = physics_for(wl, s)
+        ta = time.perf_counter()
         sys_e2e = bem.build_tbem_system_with_beta(mesh, ph, beta, ctx=ctx, reuse=sys_e2e)   # stages the host mesh (H2D), rhs D2H
+        tb = time.perf_counter()
         b = sys_e2e.rhs_full(n) + inc.compute_rhs_with_beta(mesh.center, mesh.normal, ph, beta)
+        tc = time.perf_counter()
         sol = bem.gmres(bem.DenseOperator(sys_e2e), b, cfg)                                   # b H2D, x D2H
+        td = time.perf_counter()
         x_pinned[:] = sol.x
+        if dbg:
+            print(f"[e2e rank {rank}] step {s}: assemble {tb - ta:.4f} rhs {tc - tb:.4f} gmres {td - tc:.4f} it {sol.iterations}", file=sys.stderr)
         h2d += staged.nbytes_host + b.nbytes
         d2h += nloc * 16 + sol.x.nbytes
     barrier()

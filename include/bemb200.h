@@ -160,6 +160,10 @@ int bemb200_measure_fp64_peak(bemb200_ctx* ctx, double* tflops);
 /* max abs error of the far kernel's sincos / rsqrt against the CUDA math library over
  * `n` sample arguments in [0, xmax] */
 int bemb200_selftest_math(bemb200_ctx* ctx, uint64_t n, double xmax, double* sincos_err, double* rsqrt_relerr);
+/* latency probe of the in-stream all-gather used by the distributed solver: microseconds per
+ * call for `iters` all-gathers of `bytes_per_rank` bytes, stream-ordered (sync_each = 0) or
+ * with a host synchronisation after each one (sync_each = 1) */
+int bemb200_measure_allgather(bemb200_ctx* ctx, uint64_t bytes_per_rank, int iters, int sync_each, double* usec_per_call);
 /* device pointer of the local matrix slab / device stream, for callers that own a CUDA
  * context in the same process (bench harness) */
 void* bemb200_matrix_device_ptr(const bemb200_matrix* m);

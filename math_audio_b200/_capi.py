@@ -83,6 +83,7 @@ SYMBOLS = {
     "bemb200_solver_stats": (C.c_int, [_VP, C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "bemb200_measure_fp64_peak": (C.c_int, [_VP, C.POINTER(C.c_double)]),
     "bemb200_selftest_math": (C.c_int, [_VP, C.c_uint64, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "bemb200_measure_allgather": (C.c_int, [_VP, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "bemb200_matrix_device_ptr": (_VP, [_VP]),
 }
 

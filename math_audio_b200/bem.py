@@ -67,6 +67,11 @@ class Context:
         _capi.check(self._lib.bemb200_selftest_math(self._h, n, xmax, C.byref(a), C.byref(b)), self._h)
         return float(a.value), float(b.value)
 
+    def measure_allgather(self, bytes_per_rank: int, iters: int = 200, sync_each: bool = False) -> float:
+        t = C.c_double()
+        _capi.check(self._lib.bemb200_measure_allgather(self._h, bytes_per_rank, iters, 1 if sync_each else 0, C.byref(t)), self._h)
+        return float(t.value)
+
     def close(self):
         if self._h:
             self._lib.bemb200_ctx_destroy(self._h)

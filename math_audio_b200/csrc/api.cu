@@ -85,14 +85,14 @@ template <class T>
 static int dev_alloc_copy(bemb200_staged_mesh* sm, T** dst, const std::vector<T>& src) {
     size_t bytes = src.size() * sizeof(T);
     if (bytes == 0) bytes = sizeof(T);
-    BEMB_CUDA(sm->ctx, cudaMalloc((void**)dst, bytes));
+    BEMB_CUDA(sm->ctx, cudaMallocAsync((void**)dst, bytes, sm->ctx->stream));
     sm->allocs.push_back(*dst);
     if (!src.empty()) BEMB_CUDA(sm->ctx, cudaMemcpyAsync(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, sm->ctx->stream));
     return BEMB200_OK;
 }
 template <class T>
 static int dev_alloc(bemb200_staged_mesh* sm, T** dst, size_t count) {
-    BEMB_CUDA(sm->ctx, cudaMalloc((void**)dst, (count ? count : 1) * sizeof(T)));
+    BEMB_CUDA(sm->ctx, cudaMallocAsync((void**)dst, (count ? count : 1) * sizeof(T), sm->ctx->stream));
     sm->allocs.push_back(*dst);
     return BEMB200_OK;
 }
@@ -123,6 +123,15 @@ static int ctx_create_common(int device, void* ext_stream, bemb200_ctx** out) {
         std::string msg = std::string("device '") + prop.name + "' is not sm_100 (libbemb200 ships sm_100a code only)";
         delete c;
         return set_error(nullptr, BEMB200_EUNSUPPORTED, msg);
+    }
+    {
+        // keep stream-ordered (cudaMallocAsync) staging memory cached between calls
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        cudaGetLastError();
     }
     if (ext_stream) {
         c->stream = (cudaStream_t)ext_stream;
@@ -202,7 +211,8 @@ void bemb200_partition(uint64_t n, int nranks, int rank, uint64_t* row_begin, ui
 void bemb200_staged_mesh_free(bemb200_staged_mesh* sm) {
     if (!sm) return;
     cudaSetDevice(sm->ctx->device);
-    for (void* p : sm->allocs) cudaFree(p);
+    // stream-ordered frees (no device-wide synchronisation, unlike cudaFree)
+    for (void* p : sm->allocs) cudaFreeAsync(p, sm->ctx->stream);
     delete sm;
 }
 
@@ -297,7 +307,7 @@ int bemb200_mesh_stage(bemb200_ctx* ctx, const bemb200_mesh* mesh, bemb200_stage
     STAGE_TRY(dev_alloc_copy(sm, &dm.bc_val, bcval));
     STAGE_TRY(dev_alloc_copy(sm, &dm.nonzero_bc, nz));
     STAGE_TRY(dev_alloc(sm, &dm.esize, ndof));
-    STAGE_TRY(dev_alloc(sm, &dm.far_y, (size_t)dm.ntiles * NQ_MAX * 3 * TILE));
+    STAGE_TRY(dev_alloc(sm, &dm.far_k, (size_t)dm.ntiles * NQ_MAX * TILE));
     STAGE_TRY(dev_alloc(sm, &dm.far_c, (size_t)dm.ntiles * FAR_NCONST * TILE));
     STAGE_TRY(dev_alloc(sm, &dm.col_class, (size_t)dm.ntiles * TILE));
     cudaError_t e = launch_prep(dm, ctx->stream);

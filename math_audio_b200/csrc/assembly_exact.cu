@@ -254,6 +254,19 @@ __device__ Acc regular_integration_warp(WarpScratch& ws, const double* src, cons
     const int NQ = (et == 3) ? NQ_TRI : NQ_QUAD;
     Acc a = acc_zero();
     const int total = nsub * NQ;
+    // The DECISIONS above are bit-faithful; the integrals below only have to agree with the
+    // reference to ~1e-15, so they use the far kernel's arithmetic (explicit fma(), MUFU-seeded
+    // rsqrt, Cody-Waite sincos) instead of IEEE divisions and the libm sincos.
+    // Tri3: position/normal/Jacobian are affine -> hoisted out of the point loop.
+    double e1[3], e2[3], nyc[3] = {0, 0, 0}, jac_c = 0.0;
+    if (et == 3) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { e1[d] = c[3 + d] - c[d]; e2[d] = c[6 + d] - c[d]; }
+        double nv[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+        double n2 = dot3(nv, nv);
+        jac_c = sqrt(n2);
+        if (jac_c > 1e-15) { nyc[0] = nv[0] / jac_c; nyc[1] = nv[1] / jac_c; nyc[2] = nv[2] / jac_c; }
+    }
     for (int p = lane; p < total; p += 32) {
         const int is = p / NQ, q = p - is * NQ;
         const double* se = ws.subs[is];
@@ -274,33 +287,65 @@ __device__ Acc regular_integration_warp(WarpScratch& ws, const double* src, cons
         } else {
             xio = se[0] + csi * fase; eto = se[1] + eta * fase; weih2 = wei * (fase * fase);
         }
-        Params pr = compute_parameters(c, et, xio, eto);
-        double wga = weih2 * pr.jac;
-        double diff[3] = {pr.pos[0] - src[0], pr.pos[1] - src[1], pr.pos[2] - src[2]};
-        double dis = sqrt(dot3(diff, diff));
-        if (!(dis > 1e-15)) continue;  // normalize() returns len 0 -> `dis_fsp < 1e-15` skip (regular.rs:120)
-        double u[3] = {diff[0] / dis, diff[1] / dis, diff[2] / dis};
-        double re1 = ph.wavruim * dis;
-        double re2 = wga / (4.0 * PI * dis);
+        double pos[3], ny[3], jac, shp[4];
+        if (et == 3) {
+            shp[0] = 1.0 - xio - eto; shp[1] = xio; shp[2] = eto; shp[3] = 0.0;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                pos[d] = fma(eto, e2[d], fma(xio, e1[d], c[d]));
+                ny[d] = nyc[d];
+            }
+            jac = jac_c;
+        } else {
+            const double s1 = 0.25 * (xio + 1.0), s2 = 0.25 * (xio - 1.0), t1 = eto + 1.0, t2 = eto - 1.0;
+            shp[0] = s1 * t1; shp[1] = -s2 * t1; shp[2] = s2 * t2; shp[3] = -s1 * t2;
+            const double ds[4] = {0.25 * t1, -0.25 * t1, 0.25 * t2, -0.25 * t2};
+            const double dt[4] = {s1, -s2, s2, -s1};
+            double xs[3], xt[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                pos[d] = fma(shp[3], c[9 + d], fma(shp[2], c[6 + d], fma(shp[1], c[3 + d], shp[0] * c[d])));
+                xs[d] = fma(ds[3], c[9 + d], fma(ds[2], c[6 + d], fma(ds[1], c[3 + d], ds[0] * c[d])));
+                xt[d] = fma(dt[3], c[9 + d], fma(dt[2], c[6 + d], fma(dt[1], c[3 + d], dt[0] * c[d])));
+            }
+            double nv[3] = {fma(xs[1], xt[2], -(xs[2] * xt[1])), fma(xs[2], xt[0], -(xs[0] * xt[2])),
+                            fma(xs[0], xt[1], -(xs[1] * xt[0]))};
+            const double n2 = fma(nv[2], nv[2], fma(nv[1], nv[1], nv[0] * nv[0]));
+            if (n2 > 1e-30) {
+                const double rn = fast_rsqrt(n2);
+                jac = n2 * rn;
+                ny[0] = nv[0] * rn; ny[1] = nv[1] * rn; ny[2] = nv[2] * rn;
+            } else {
+                jac = sqrt(n2);
+                ny[0] = ny[1] = ny[2] = 0.0;
+            }
+        }
+        const double dx = pos[0] - src[0], dy = pos[1] - src[1], dz = pos[2] - src[2];
+        const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+        if (!(r2 > 1e-30)) continue;  // `dis_fsp < 1e-15` skip (regular.rs:120)
+        const double rho = fast_rsqrt(r2);
+        const double dis = r2 * rho;
         double sn, cs;
-        sincos(re1, &sn, &cs);
-        cplx zg = C(cs * re2, sn * re2);
-        cplx z1 = C(-1.0 / dis, ph.wavruim);
-        cplx zb = zg * z1;
-        double re1_h = dot3(u, pr.nrm);
-        cplx zhh = zb * re1_h;
-        double re2_h = -dot3(u, nx);
-        cplx zht = zb * re2_h;
-        double rq = re1_h * re2_h;
-        double nxny = dot3(nx, pr.nrm);
-        double dq = dis * dis;
-        cplx zef = C((3.0 / dq - ph.k2) * rq + nxny / dq, -ph.wavruim / dis * (3.0 * rq + nxny));
-        cplx ze = zg * zef;
+        fast_sincos(ph.wavruim * dis, sn, cs);
+        const double g = (weih2 * jac) * (INV_4PI * rho);
+        const cplx zg = C(g * cs, g * sn);
+        const cplx zb = C(fma(-zg.re, rho, -(zg.im * ph.wavruim)), fma(zg.re, ph.wavruim, -(zg.im * rho)));  // zg*(-1/r + ik)
+        const double re1_h = fma(dz, ny[2], fma(dy, ny[1], dx * ny[0])) * rho;
+        const double re2_h = -(fma(dz, nx[2], fma(dy, nx[1], dx * nx[0])) * rho);
+        const cplx zhh = C(zb.re * re1_h, zb.im * re1_h);
+        const cplx zht = C(zb.re * re2_h, zb.im * re2_h);
+        const double rq = re1_h * re2_h;
+        const double nxny = fma(nx[2], ny[2], fma(nx[1], ny[1], nx[0] * ny[0]));
+        const double rho2 = rho * rho;
+        const double t3 = fma(3.0, rq, nxny);
+        const double fre = fma(rho2, t3, -(ph.k2 * rq));
+        const double fim = -(ph.wavruim * rho) * t3;
+        const cplx ze = C(fma(zg.re, fre, -(zg.im * fim)), fma(zg.re, fim, zg.im * fre));
         a.g += zg; a.h += zhh; a.ht += zht; a.e += ze;
         if (compute_rhs) {
             cplx zbg = C(0, 0);
             for (int i = 0; i < et; ++i)
-                if (i < bc_len) zbg += bc[i] * pr.shape[i];
+                if (i < bc_len) zbg += bc[i] * shp[i];
             if (bc_type == 0) a.rhs += (zg * ph.gamma * ph.tau + zht * ph.beta_unscaled) * zbg;
             else if (bc_type == 1) a.rhs -= (zhh * ph.gamma * ph.tau + ze * ph.beta_unscaled) * zbg;
         }
@@ -550,17 +595,33 @@ self_kernel(DeviceMesh m, Phys ph, uint64_t row_begin, uint64_t row_end, cplx* A
 }
 
 // ---- prep: per-column far-field records -------------------------------------------
+// For a flat element (Tri3, parallelogram Quad4) y_q = y_0 + a_q e1 + b_q e2 with
+// e1 = dx/ds, e2 = dx/dt constant, so the far kernel only needs y_0, e1, e2, n_y, J and
+// kappa_q = |y_q - y_0|^2 (see assembly_far.cu).
+__device__ __forceinline__ void tangents(const double* c, int et, double s, double t, double* e1, double* e2) {
+    double ds[4], dt[4];
+    if (et == 3) {
+        ds[0] = -1.0; ds[1] = 1.0; ds[2] = 0.0; ds[3] = 0.0;
+        dt[0] = -1.0; dt[1] = 0.0; dt[2] = 1.0; dt[3] = 0.0;
+    } else {
+        ds[0] = 0.25 * (t + 1.0); ds[1] = -0.25 * (t + 1.0); ds[2] = 0.25 * (t - 1.0); ds[3] = -0.25 * (t - 1.0);
+        dt[0] = 0.25 * (s + 1.0); dt[1] = 0.25 * (1.0 - s); dt[2] = 0.25 * (s - 1.0); dt[3] = -0.25 * (s + 1.0);
+    }
+    for (int d = 0; d < 3; ++d) { e1[d] = 0.0; e2[d] = 0.0; }
+    for (int i = 0; i < et; ++i)
+        for (int d = 0; d < 3; ++d) { e1[d] += ds[i] * c[3 * i + d]; e2[d] += dt[i] * c[3 * i + d]; }
+}
+
 __global__ void prep_kernel(DeviceMesh m) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= m.ntiles * TILE) return;
     const uint32_t tile = j / TILE, t = j % TILE;
-    double* fy = m.far_y + (uint64_t)tile * NQ_MAX * 3 * TILE;
+    double* fk = m.far_k + (uint64_t)tile * NQ_MAX * TILE;
     double* fc = m.far_c + (uint64_t)tile * FAR_NCONST * TILE;
     if (j >= m.n) {  // padding columns of the last tile
-        for (int q = 0; q < NQ_MAX; ++q)
-            for (int d = 0; d < 3; ++d) fy[(q * 3 + d) * TILE + t] = 1.0e30;
+        for (int q = 0; q < NQ_MAX; ++q) fk[q * TILE + t] = 0.0;
         for (int s = 0; s < FAR_NCONST; ++s) fc[s * TILE + t] = 0.0;
-        fc[FC_CX * TILE + t] = 1.0e30;
+        fc[FC_Y0X * TILE + t] = 1.0e30;
         m.col_class[j] = COL_NONE;
         return;
     }
@@ -568,54 +629,68 @@ __global__ void prep_kernel(DeviceMesh m) {
     for (int i = 0; i < 12; ++i) c[i] = m.coords[12ull * j + i];
     const int et = m.etype[j];
     const int NQ = (et == 3) ? NQ_TRI : NQ_QUAD;
-    double n0[3] = {0, 0, 0}, j0 = 0.0, y0[3] = {0, 0, 0}, dev = 0.0;
+    double n0[3] = {0, 0, 0}, j0 = 0.0, y0[3] = {0, 0, 0}, dev = 0.0, devp = 0.0, e1[3], e2[3];
+    double xi0 = 0.0, eta0 = 0.0;
     for (int q = 0; q < NQ_MAX; ++q) {
+        double kap = 0.0;
         if (q < NQ) {
             double xi, eta, w;
             quad_point(et, q, xi, eta, w);
             Params p = compute_parameters(c, et, xi, eta);
-            for (int d = 0; d < 3; ++d) fy[(q * 3 + d) * TILE + t] = p.pos[d];
             if (q == 0) {
                 for (int d = 0; d < 3; ++d) { n0[d] = p.nrm[d]; y0[d] = p.pos[d]; }
                 j0 = p.jac;
+                xi0 = xi; eta0 = eta;
+                tangents(c, et, xi, eta, e1, e2);
             } else {
                 for (int d = 0; d < 3; ++d) dev = fmax(dev, fabs(p.nrm[d] * p.jac - n0[d] * j0));
+                // the affine model must reproduce the true quadrature point
+                double aq = xi - xi0, bq = eta - eta0;
+                for (int d = 0; d < 3; ++d) devp = fmax(devp, fabs(y0[d] + aq * e1[d] + bq * e2[d] - p.pos[d]));
+                double dl[3] = {p.pos[0] - y0[0], p.pos[1] - y0[1], p.pos[2] - y0[2]};
+                kap = dot3(dl, dl);
             }
-        } else {
-            for (int d = 0; d < 3; ++d) fy[(q * 3 + d) * TILE + t] = 0.0;
         }
+        fk[q * TILE + t] = kap;
     }
-    // centroid used by the level-0 ratio test: local_to_global at the mean of the
-    // vertex local coordinates (singular.rs:541-548)
-    double sc = 0.0, tc = 0.0;
-    for (int v = 0; v < et; ++v) sc += (et == 3) ? d_CSI6[v] : d_CSI8[v];
-    sc = sc / (double)et;
-    for (int v = 0; v < et; ++v) tc += (et == 3) ? d_ETA6[v] : d_ETA8[v];
-    tc = tc / (double)et;
-    double cen[3];
-    local_to_global(c, et, sc, tc, cen);
     fc[FC_NX * TILE + t] = n0[0]; fc[FC_NY * TILE + t] = n0[1]; fc[FC_NZ * TILE + t] = n0[2];
     fc[FC_J4PI * TILE + t] = j0 * INV_4PI;
-    fc[FC_CX * TILE + t] = cen[0]; fc[FC_CY * TILE + t] = cen[1]; fc[FC_CZ * TILE + t] = cen[2];
-    // dist^2 < 9*area  <=>  ratdis < 3 up to rounding; the 1e-9 guard band sends every
-    // borderline pair to the exact near kernel, which re-takes the decision bit-faithfully
+    fc[FC_Y0X * TILE + t] = y0[0]; fc[FC_Y0Y * TILE + t] = y0[1]; fc[FC_Y0Z * TILE + t] = y0[2];
+    // |y_0 - x|^2 < 9*area  <=>  ratdis < 3 up to rounding (y_0 is the table centroid, 3e-16 away
+    // from the 1/3-centroid of singular.rs:541-548); the 1e-9 guard band sends every borderline
+    // pair to the exact near kernel, which re-takes the decision bit-faithfully
     fc[FC_THR * TILE + t] = 9.0 * m.area[j] * (1.0 + 1e-9);
-    fc[FC_P * TILE + t] = dot3(y0, n0);
-    fc[FC_SPARE * TILE + t] = 0.0;
+    fc[FC_E1X * TILE + t] = e1[0]; fc[FC_E1Y * TILE + t] = e1[1]; fc[FC_E1Z * TILE + t] = e1[2];
+    fc[FC_E2X * TILE + t] = e2[0]; fc[FC_E2Y * TILE + t] = e2[1]; fc[FC_E2Z * TILE + t] = e2[2];
+    // kappa of the ratio-test centre relative to y_0: the centre is y_0 for TR13 (q = 0 is the
+    // centroid) but (s,t) = (0,0) for the 4x4 Gauss rule, i.e. y_0 - s_0 e1 - t_0 e2
+    {
+        double kc = 0.0;
+        if (et == 4) {
+            double dl[3];
+            for (int d = 0; d < 3; ++d) dl[d] = -xi0 * e1[d] - eta0 * e2[d];
+            kc = dot3(dl, dl);
+        }
+        fc[FC_KC * TILE + t] = kc;
+    }
+    fc[FC_SPARE1 * TILE + t] = 0.0;
     // estimate_element_size(): singular.rs:730-745
     double total = 0.0;
     for (int i = 0; i < et; ++i) {
         int jn = (i + 1) % et;
-        double e2 = 0.0;
+        double e2s = 0.0;
         for (int k = 0; k < 3; ++k) {
             double d = c[3 * jn + k] - c[3 * i + k];
-            e2 += d * d;
+            e2s += d * d;
         }
-        total += sqrt(e2);
+        total += sqrt(e2s);
     }
     m.esize[j] = total / (double)et;
-    bool special = (m.bc_type[j] != 0) || (m.nonzero_bc[j] != 0) || !(j0 > 1e-15) || (et == 4 && dev > 1e-13 * j0) ||
-                   !(m.area[j] > 0.0);
+    // flat <=> n_y*J constant over the rule (1e-13 relative) and the affine model reproduces the
+    // quadrature points to 1e-12 of the element size
+    const double len = sqrt(dot3(e1, e1)) + sqrt(dot3(e2, e2));
+    bool special = (m.bc_type[j] != 0) || (m.nonzero_bc[j] != 0) || !(j0 > 1e-15) || (dev > 1e-13 * j0) ||
+                   (devp > 1e-12 * len) || !(m.area[j] > 0.0);
     m.col_class[j] = special ? COL_SPECIAL : (et == 3 ? COL_FLAT_TRI : COL_FLAT_QUAD);
 }
 

@@ -1,70 +1,95 @@
 // assembly_far.cu -- the FP64 compute-bound far-field assembly kernel (K1).
 //
-// Replaces, for every (collocation row i, field element j) pair whose level-0
-// ratio test passes (dist/sqrt(area) >= 3, singular.rs:553-556), the un-subdivided
-// branch of regular_integration (regular.rs:67-154) followed by assemble_tbem for a
-// velocity-BC field element (tbem.rs:323-331):
+// Replaces, for every (collocation row i, field element j) pair whose level-0 ratio test
+// passes (dist/sqrt(area) >= 3, singular.rs:553-556), the un-subdivided branch of
+// regular_integration (regular.rs:67-154) followed by assemble_tbem for a velocity-BC field
+// element (tbem.rs:323-331):
 //     A[i,j] = sign*gamma*tau * sum_q H_q  +  beta * sum_q E_q
 // with the 13-point triangle rule (Tri3) or the 4x4 Gauss rule (flat Quad4).
 //
-// Mapping (B200): block = 128 threads <-> one tile of 128 consecutive matrix
-// columns; the tile's quadrature points y_q (SoA, 40-48 KB) are brought into
-// shared memory by one TMA bulk copy (cp.async.bulk + mbarrier), per-column
-// constants (n_y, J/4pi, ratio-test centroid, 9*area, y.n_y) live in registers,
-// and the block then walks a chunk of collocation rows: every warp computes 32
-// adjacent entries of the same row, so the complex128 stores are 512 contiguous
-// bytes per warp.  Source point/normal are block-uniform loads.  Per quadrature
-// point the thread spends ~60 DP-pipe instructions (one MUFU-seeded rsqrt, one
-// Cody-Waite + minimax sincos, the rest FMAs); nothing else touches HBM.
-// Pairs that fail the (guard-banded) ratio test are appended to a compact list
-// for the exact near-field kernel.
+// Mapping (B200): block = 128 threads <-> one tile of 128 consecutive matrix columns.  Per
+// column the thread keeps the element's frame in registers -- first quadrature point y_0,
+// tangents e1 = dx/ds, e2 = dx/dt, unit normal n_y, J/(4 pi) -- and the tile's table
+// kappa_q = |y_q - y_0|^2 (13-16 values per element, SoA) is brought into shared memory by one
+// TMA bulk copy (cp.async.bulk + mbarrier).  The block then walks a chunk of collocation rows:
+// every warp computes 32 adjacent entries of one row, so the complex128 stores are 512
+// contiguous bytes per warp; the source point/normal are block-uniform loads.
+//
+// Arithmetic per pair (x = source, d0 = y_0 - x):  on a flat element y_q = y_0 + a_q e1 + b_q e2
+// (a_q, b_q compile-time constants of the rule), hence
+//     r_q^2        = |d0|^2 + a_q (2 d0.e1) + b_q (2 d0.e2) + kappa_q            3 DP ops
+//     (y_q-x).n_x  = d0.n_x + a_q (e1.n_x) + b_q (e2.n_x)                       2 DP ops
+//     (y_q-x).n_y  = d0.n_y                                   (constant over the element)
+// then one MUFU-seeded rsqrt (5), one Cody-Waite + minimax sincos (20) and the kernel algebra
+// with H and E folded into ONE complex accumulator:
+//     A_ij = sum_q zg_q * [ cH h rho (-rho + ik) + beta (P_q - i Q_q) ],
+//     P = rho^2 t - k^2 rq,  Q = k rho t,  t = 3 rq + n_x.n_y,  rq = (h rho)(-m rho)
+// ~50 DP-pipe instructions per quadrature point (purely imaginary beta, the reference's
+// beta = i*scale/k).  Nothing but the 16-byte result touches HBM.
+// Pairs that fail the (guard-banded) ratio test are appended to a compact list for the exact
+// near-field kernel, which re-takes the decision bit-faithfully and overwrites the entry.
+#include <cstdlib>
+
 #include "internal.h"
 
 namespace bemb {
 
 namespace {
 
-__device__ __constant__ double d_wq_tri[NQ_TRI];    // 0.5 * TR13 weights
-__device__ __constant__ double d_wq_quad[NQ_QUAD];  // w_i * w_j of the 4x4 rule
+struct RuleConst {
+    double w[NQ_MAX];   // weights (0.5*TR13 weight | w_i*w_j)
+    double a[NQ_MAX];   // xi_q  - xi_0
+    double b[NQ_MAX];   // eta_q - eta_0
+    double a2[NQ_MAX];  // 2 a_q
+    double b2[NQ_MAX];  // 2 b_q
+    double ac, bc;      // ratio-test centre relative to (xi_0, eta_0)
+    double ac2, bc2;
+};
+__device__ __constant__ RuleConst d_rule_tri;
+__device__ __constant__ RuleConst d_rule_quad;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <int NQ>
-__global__ void __launch_bounds__(TILE, 4)
-far_kernel(const double* __restrict__ far_y, const double* __restrict__ far_c, const uint8_t* __restrict__ col_class,
+template <int NQ, bool BIMAG, int MINB>
+__global__ void __launch_bounds__(TILE, MINB)
+far_kernel(const double* __restrict__ far_k, const double* __restrict__ far_c, const uint8_t* __restrict__ col_class,
            const double* __restrict__ srcdat, uint32_t n, uint64_t row_begin, uint64_t row_end, uint32_t rows_per_block,
            double wavruim, double k2, double cH, double beta_re, double beta_im, cplx* __restrict__ A, uint64_t lda,
            uint2* __restrict__ near_list, unsigned int near_cap, unsigned int* __restrict__ near_count) {
-    extern __shared__ __align__(128) double sm_y[];  // [NQ][3][TILE]
+    __shared__ __align__(128) double sm_k[NQ * TILE];  // kappa_q, [q][column]
     __shared__ __align__(8) unsigned long long mbar;
 
     const uint32_t tile = blockIdx.x;
     const uint32_t t = threadIdx.x;
     const uint32_t col = tile * TILE + t;
-    constexpr uint32_t BYTES = NQ * 3 * TILE * sizeof(double);
-    const uint8_t want = (NQ == NQ_TRI) ? COL_FLAT_TRI : COL_FLAT_QUAD;
+    constexpr uint32_t BYTES = NQ * TILE * sizeof(double);
+    constexpr bool QUAD = (NQ == NQ_QUAD);
+    const uint8_t want = QUAD ? COL_FLAT_QUAD : COL_FLAT_TRI;
+    const RuleConst& rc = QUAD ? d_rule_quad : d_rule_tri;
 
-    // ---- stage the tile's quadrature points with one TMA bulk copy ------------------
+    // ---- stage the tile's kappa table with one TMA bulk copy -------------------------------
     if (t == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     if (t == 0) {
-        const double* gsrc = far_y + (uint64_t)tile * NQ_MAX * 3 * TILE;
+        const double* gsrc = far_k + (uint64_t)tile * NQ_MAX * TILE;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(BYTES) : "memory");
         asm volatile(
-            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sm_y)),
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sm_k)),
             "l"(gsrc), "r"(BYTES), "r"(smem_u32(&mbar))
             : "memory");
     }
-    // per-column constants -> registers (coalesced, overlaps the bulk copy)
+    // per-column frame -> registers (coalesced, overlaps the bulk copy)
     const double* fc = far_c + (uint64_t)tile * FAR_NCONST * TILE + t;
     const double nyx = fc[FC_NX * TILE], nyy = fc[FC_NY * TILE], nyz = fc[FC_NZ * TILE];
     const double j4pi = fc[FC_J4PI * TILE];
-    const double ccx = fc[FC_CX * TILE], ccy = fc[FC_CY * TILE], ccz = fc[FC_CZ * TILE];
+    const double y0x = fc[FC_Y0X * TILE], y0y = fc[FC_Y0Y * TILE], y0z = fc[FC_Y0Z * TILE];
     const double thr = fc[FC_THR * TILE];
-    const double pj = fc[FC_P * TILE];
+    const double e1x = fc[FC_E1X * TILE], e1y = fc[FC_E1Y * TILE], e1z = fc[FC_E1Z * TILE];
+    const double e2x = fc[FC_E2X * TILE], e2y = fc[FC_E2Y * TILE], e2z = fc[FC_E2Z * TILE];
+    const double kc = fc[FC_KC * TILE];
     const bool active = (col < n) && (col_class[col] == want);
     {
         uint32_t done = 0;
@@ -77,18 +102,23 @@ far_kernel(const double* __restrict__ far_y, const double* __restrict__ far_c, c
         }
     }
 
+    const double bk = beta_im * wavruim, bk2 = beta_im * k2;
     const uint64_t r0 = row_begin + (uint64_t)blockIdx.y * rows_per_block;
     const uint64_t r1 = (r0 + rows_per_block < row_end) ? r0 + rows_per_block : row_end;
-    const double* wq = (NQ == NQ_TRI) ? d_wq_tri : d_wq_quad;
-    const double* yq = sm_y + t;
+    const double* kq = sm_k + t;
 
     for (uint64_t row = r0; row < r1; ++row) {
         const double* sp = srcdat + 8ull * row;  // block-uniform
         const double sx = __ldg(sp + 0), sy = __ldg(sp + 1), sz = __ldg(sp + 2);
         const double nxx = __ldg(sp + 3), nxy = __ldg(sp + 4), nxz = __ldg(sp + 5);
-        // level-0 ratio test, guard-banded (exact decision is re-taken by the near kernel)
-        const double dcx = ccx - sx, dcy = ccy - sy, dcz = ccz - sz;
-        const double d2c = fma(dcz, dcz, fma(dcy, dcy, dcx * dcx));
+        const double dx = y0x - sx, dy = y0y - sy, dz = y0z - sz;
+        const double D = fma(dz, dz, fma(dy, dy, dx * dx));
+        const double p1 = fma(dz, e1z, fma(dy, e1y, dx * e1x));  // d0.e1  (the factor 2 lives in a2/b2)
+        const double p2 = fma(dz, e2z, fma(dy, e2y, dx * e2x));
+        // level-0 ratio test against the element centre, guard-banded (the exact decision is
+        // re-taken by the near kernel)
+        double d2c = D;
+        if (QUAD) d2c = fma(rc.ac2, p1, fma(rc.bc2, p2, D + kc));
         const bool is_near = active && (d2c < thr);
         if (__any_sync(0xffffffffu, is_near)) {
             const unsigned mask = __ballot_sync(0xffffffffu, is_near && (uint64_t)col != row);
@@ -103,43 +133,50 @@ far_kernel(const double* __restrict__ far_y, const double* __restrict__ far_c, c
                 }
             }
         }
-        // h = (y_q - x).n_y is the same for every point of a flat element
-        const double h = pj - fma(sz, nyz, fma(sy, nyy, sx * nyx));
+        const double h = fma(dz, nyz, fma(dy, nyy, dx * nyx));   // (y_q - x).n_y, same for all q
         const double nn = fma(nxz, nyz, fma(nxy, nyy, nxx * nyx));
-        double hre = 0.0, him = 0.0, ere = 0.0, eim = 0.0;
+        const double M0 = fma(dz, nxz, fma(dy, nxy, dx * nxx));  // d0.n_x
+        const double E1 = fma(e1z, nxz, fma(e1y, nxy, e1x * nxx));
+        const double E2 = fma(e2z, nxz, fma(e2y, nxy, e2x * nxx));
+        // per-pair constants of the folded kernel (see header): with rho = 1/r, m = (y_q-x).n_x
+        //   rq = (u.n_y)(-(u.n_x)) = (-h m) rho^2          t = 3 rq + n_x.n_y
+        //   H factor  cH (h rho)(-rho + ik)             = (-cH h) rho^2 + i (cH h k) rho
+        //   E factor  (rho^2 t - k^2 rq) - i (k rho) t
+        const double nh = -h;
+        const double nhc = -cH * h;          // A1 = nhc * rho^2
+        const double hck = (cH * h) * wavruim;  // A2 = hck * rho
+        double are = 0.0, aim = 0.0;
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
-            const double dx = yq[(q * 3 + 0) * TILE] - sx;
-            const double dy = yq[(q * 3 + 1) * TILE] - sy;
-            const double dz = yq[(q * 3 + 2) * TILE] - sz;
-            const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+            const double r2 = (q == 0) ? D : fma(rc.a2[q], p1, fma(rc.b2[q], p2, D + kq[q * TILE]));
             const double rho = fast_rsqrt(r2);  // 1/r
             const double r = r2 * rho;
             double sn, cs;
             fast_sincos(wavruim * r, sn, cs);
-            const double g = (j4pi * rho) * wq[q];  // w J /(4 pi r)
+            const double g = rho * rc.w[q];  // w / r   (J/(4 pi) is applied once per pair)
             const double zgr = g * cs, zgi = g * sn;
-            const double m = fma(dz, nxz, fma(dy, nxy, dx * nxx));  // (y-x).n_x
-            const double re1h = h * rho;                             // u.n_y
-            const double re2h = -m * rho;                            // -(u.n_x)
-            // zhh_base = zg * (-1/r + i k)
-            const double bre = fma(-zgr, rho, -(zgi * wavruim));
-            const double bim = fma(zgr, wavruim, -(zgi * rho));
-            hre = fma(bre, re1h, hre);
-            him = fma(bim, re1h, him);
-            const double rq = re1h * re2h;
+            const double m = (q == 0) ? M0 : fma(rc.a[q], E1, fma(rc.b[q], E2, M0));  // (y_q - x).n_x
             const double rho2 = rho * rho;
-            const double fre = fma(nn, rho2, fma(3.0, rho2, -k2) * rq);
-            const double fim = -(wavruim * rho) * fma(3.0, rq, nn);
-            ere = fma(zgr, fre, fma(-zgi, fim, ere));
-            eim = fma(zgr, fim, fma(zgi, fre, eim));
+            const double rq = (nh * m) * rho2;
+            const double t3 = fma(3.0, rq, nn);
+            const double A1 = nhc * rho2;
+            const double A2 = hck * rho;
+            double fre, fim;
+            if (BIMAG) {
+                // beta = i b:  beta (P - iQ) = b Q + i b P,  Q = k rho t,  P = rho^2 t - k^2 rq
+                fre = fma(bk * rho, t3, A1);
+                fim = fma(beta_im * rho2, t3, fma(-bk2, rq, A2));
+            } else {
+                const double P = fma(rho2, t3, -(k2 * rq));
+                const double Q = (wavruim * rho) * t3;
+                fre = fma(beta_re, P, fma(beta_im, Q, A1));
+                fim = fma(beta_im, P, fma(-beta_re, Q, A2));
+            }
+            are = fma(zgr, fre, fma(-zgi, fim, are));
+            aim = fma(zgr, fim, fma(zgi, fre, aim));
         }
         if (active) {
-            // coeff = H*sign*gamma*tau + E*beta   (tbem.rs:203,329)
-            cplx out;
-            out.re = fma(cH, hre, fma(beta_re, ere, -(beta_im * eim)));
-            out.im = fma(cH, him, fma(beta_re, eim, beta_im * ere));
-            double2 v = make_double2(out.re, out.im);
+            double2 v = make_double2(are * j4pi, aim * j4pi);
             __stcs(reinterpret_cast<double2*>(A + (row - row_begin) * lda + col), v);
         }
     }
@@ -152,39 +189,68 @@ cudaError_t upload_tables() {
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (dev < 64 && g_tables_uploaded[dev]) return cudaSuccess;
-    double wt[NQ_TRI], wqd[NQ_QUAD];
-    for (int q = 0; q < NQ_TRI; ++q) wt[q] = hosttab::BEMQ_TR13[q][2] * 0.5;  // gauss.rs:67-89
+    RuleConst tri = {}, quad = {};
+    for (int q = 0; q < NQ_TRI; ++q) {  // gauss.rs:67-89
+        tri.w[q] = hosttab::BEMQ_TR13[q][2] * 0.5;
+        tri.a[q] = hosttab::BEMQ_TR13[q][0] - hosttab::BEMQ_TR13[0][0];
+        tri.b[q] = hosttab::BEMQ_TR13[q][1] - hosttab::BEMQ_TR13[0][1];
+    }
+    tri.ac = 0.0; tri.bc = 0.0;  // q = 0 of TR13 is the centroid
     for (int i = 0; i < 4; ++i)
-        for (int j = 0; j < 4; ++j) wqd[i * 4 + j] = hosttab::BEMQ_GL4_W[i] * hosttab::BEMQ_GL4_W[j];  // gauss.rs:94-105
-    e = cudaMemcpyToSymbol(d_wq_tri, wt, sizeof wt);
+        for (int j = 0; j < 4; ++j) {  // gauss.rs:94-105, i outer
+            const int q = i * 4 + j;
+            quad.w[q] = hosttab::BEMQ_GL4_W[i] * hosttab::BEMQ_GL4_W[j];
+            quad.a[q] = hosttab::BEMQ_GL4_X[i] - hosttab::BEMQ_GL4_X[0];
+            quad.b[q] = hosttab::BEMQ_GL4_X[j] - hosttab::BEMQ_GL4_X[0];
+        }
+    quad.ac = -hosttab::BEMQ_GL4_X[0]; quad.bc = -hosttab::BEMQ_GL4_X[0];  // centre (0,0) relative to q = 0
+    for (RuleConst* r : {&tri, &quad}) {
+        for (int q = 0; q < NQ_MAX; ++q) { r->a2[q] = 2.0 * r->a[q]; r->b2[q] = 2.0 * r->b[q]; }
+        r->ac2 = 2.0 * r->ac; r->bc2 = 2.0 * r->bc;
+    }
+    e = cudaMemcpyToSymbol(d_rule_tri, &tri, sizeof tri);
     if (e != cudaSuccess) return e;
-    e = cudaMemcpyToSymbol(d_wq_quad, wqd, sizeof wqd);
+    e = cudaMemcpyToSymbol(d_rule_quad, &quad, sizeof quad);
     if (e != cudaSuccess) return e;
     if (dev < 64) g_tables_uploaded[dev] = true;
     return cudaSuccess;
 }
 
+int env_int(const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    return v ? std::atoi(v) : dflt;
+}
+
+template <int NQ, bool BIMAG, int MINB>
+cudaError_t launch_far_v(const DeviceMesh& m, const Phys& ph, uint64_t row_begin, uint64_t row_end, cplx* A, uint64_t lda,
+                         uint2* near_list, unsigned int near_cap, unsigned int* near_count, cudaStream_t s) {
+    const uint64_t nrows = row_end - row_begin;
+    // enough blocks to fill 148 SMs x MINB resident blocks several times over, but row chunks
+    // long enough to amortise the per-block set-up
+    uint32_t rpb = 128;
+    while (rpb > 8 && (uint64_t)m.ntiles * ((nrows + rpb - 1) / rpb) < 148ull * MINB * 4ull) rpb >>= 1;
+    dim3 grid(m.ntiles, (unsigned)((nrows + rpb - 1) / rpb));
+    const double cH = ph.sign * ph.gamma * ph.tau;
+    far_kernel<NQ, BIMAG, MINB><<<grid, TILE, 0, s>>>(m.far_k, m.far_c, m.col_class, m.src, m.n, row_begin, row_end, rpb,
+                                                      ph.wavruim, ph.k2, cH, ph.beta.re, ph.beta.im, A, lda, near_list,
+                                                      near_cap, near_count);
+    return cudaGetLastError();
+}
+
 template <int NQ>
 cudaError_t launch_far_t(const DeviceMesh& m, const Phys& ph, uint64_t row_begin, uint64_t row_end, cplx* A, uint64_t lda,
                          uint2* near_list, unsigned int near_cap, unsigned int* near_count, cudaStream_t s) {
-    const uint64_t nrows = row_end - row_begin;
-    // enough blocks to fill 148 SMs x 4 resident blocks several times over, but rows
-    // chunks long enough to amortise the tile load
-    uint32_t rpb = 128;
-    while (rpb > 8 && (uint64_t)m.ntiles * ((nrows + rpb - 1) / rpb) < 148ull * 4ull * 4ull) rpb >>= 1;
-    dim3 grid(m.ntiles, (unsigned)((nrows + rpb - 1) / rpb));
-    const size_t smem = (size_t)NQ * 3 * TILE * sizeof(double);
-    static bool attr_set[2] = {false, false};
-    const int ai = (NQ == NQ_TRI) ? 0 : 1;
-    if (!attr_set[ai]) {
-        cudaError_t e = cudaFuncSetAttribute(far_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_set[ai] = true;
+    const bool bimag = (ph.beta.re == 0.0);
+    const int minb = env_int("BEMB200_FAR_MINB", 4);
+#define FAR_DISPATCH(B, M) \
+    return launch_far_v<NQ, B, M>(m, ph, row_begin, row_end, A, lda, near_list, near_cap, near_count, s)
+    if (bimag) {
+        if (minb == 5) FAR_DISPATCH(true, 5);
+        if (minb == 6) FAR_DISPATCH(true, 6);
+        FAR_DISPATCH(true, 4);
     }
-    const double cH = ph.sign * ph.gamma * ph.tau;
-    far_kernel<NQ><<<grid, TILE, smem, s>>>(m.far_y, m.far_c, m.col_class, m.src, m.n, row_begin, row_end, rpb, ph.wavruim,
-                                            ph.k2, cH, ph.beta.re, ph.beta.im, A, lda, near_list, near_cap, near_count);
-    return cudaGetLastError();
+    FAR_DISPATCH(false, 4);
+#undef FAR_DISPATCH
 }
 
 }  // namespace

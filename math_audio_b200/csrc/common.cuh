@@ -26,10 +26,15 @@ constexpr int TILE = 128;      // field elements (matrix columns) per far-field 
 constexpr int NQ_TRI = 13;     // TR13 rule  (gauss.rs:84-87; order is always GAU_MIN=4)
 constexpr int NQ_QUAD = 16;    // 4x4 Gauss-Legendre (gauss.rs:94-105)
 constexpr int NQ_MAX = 16;
-constexpr int FAR_NCONST = 10; // per-column constants, see FarConst
+constexpr int FAR_NCONST = 16; // per-column constants, see FarConst
 
-// per-column constant slots in far_c[tile][slot][TILE]
-enum FarConst { FC_NX = 0, FC_NY = 1, FC_NZ = 2, FC_J4PI = 3, FC_CX = 4, FC_CY = 5, FC_CZ = 6, FC_THR = 7, FC_P = 8, FC_SPARE = 9 };
+// per-column constant slots in far_c[tile][slot][TILE]:
+//   n_y (unit normal), J/(4 pi), y_0 (first quadrature point), 9*area*(1+1e-9),
+//   e1 = dx/ds, e2 = dx/dt  (y_q = y_0 + a_q e1 + b_q e2 on a flat element)
+enum FarConst {
+    FC_NX = 0, FC_NY = 1, FC_NZ = 2, FC_J4PI = 3, FC_Y0X = 4, FC_Y0Y = 5, FC_Y0Z = 6, FC_THR = 7,
+    FC_E1X = 8, FC_E1Y = 9, FC_E1Z = 10, FC_E2X = 11, FC_E2Y = 12, FC_E2Z = 13, FC_KC = 14, FC_SPARE1 = 15
+};
 
 struct cplx {
     double re, im;

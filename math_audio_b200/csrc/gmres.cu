@@ -9,6 +9,7 @@
 // 16*N bytes) and EVERY rank runs the same deterministic cluster MGS kernel on the full
 // vectors, so all ranks hold bit-identical Krylov bases and Hessenberg columns and take the
 // same convergence decisions without any all-reduce.
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -107,6 +108,8 @@ static void accumulate_matvec_time(bemb200_matrix* m) {
     else cudaGetLastError();
 }
 
+static double g_dbg_launch_us = 0.0, g_dbg_wait_us = 0.0;  // host-side phase timers (diagnostics)
+
 // ---- host-side pieces of gmres.rs ----------------------------------------------------------
 static inline double tnorm(cplx a) { return std::sqrt(norm_sqr(a)); }  // ComplexField::norm (traits.rs:93-95)
 static void givens_rotation(cplx a, cplx b, cplx* c, cplx* s) {        // gmres.rs:589-603
@@ -192,13 +195,18 @@ static int gmres_core(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t max_it
         bool inner_converged = false;
         for (int j = 0; j < mm; ++j) {
             total_iterations += 1;
+            auto tp0 = std::chrono::steady_clock::now();
             rc = matvec(m, ws->V + (uint64_t)j * ws->npad, ws->w, true);
             if (rc != BEMB200_OK) return rc;
             BEMB_CUDA(ctx, launch_mgs(ws->V, ws->npad, ws->w, j, n, ws->hcol_d, ws->V + (uint64_t)(j + 1) * ws->npad, s));
             m->last_launches += 1;
             BEMB_CUDA(ctx, cudaMemcpyAsync(ws->hcol_h, ws->hcol_d, (j + 2) * sizeof(cplx), cudaMemcpyDeviceToHost, s));
+            auto tp1 = std::chrono::steady_clock::now();
             BEMB_CUDA(ctx, cudaStreamSynchronize(s));
+            auto tp2 = std::chrono::steady_clock::now();
             accumulate_matvec_time(m);
+            g_dbg_launch_us += std::chrono::duration<double, std::micro>(tp1 - tp0).count();
+            g_dbg_wait_us += std::chrono::duration<double, std::micro>(tp2 - tp1).count();
             for (int i = 0; i <= j; ++i) h[i * ldh + j] = ws->hcol_h[i];
             const double w_norm = ws->hcol_h[j + 1].re;
             h[(j + 1) * ldh + j] = C(w_norm, 0.0);
@@ -249,6 +257,12 @@ static int check_partition(bemb200_matrix* m) {
         return set_error(ctx, BEMB200_EINVAL,
                          "matrix slab is not this rank's canonical row block (see bemb200_partition); apply/gmres need the whole operator");
     return BEMB200_OK;
+}
+
+extern "C" void bemb200_debug_times(double* launch_us, double* wait_us) {
+    *launch_us = g_dbg_launch_us;
+    *wait_us = g_dbg_wait_us;
+    g_dbg_launch_us = g_dbg_wait_us = 0.0;
 }
 
 static void reset_stats(bemb200_matrix* m) {
@@ -476,6 +490,29 @@ int bemb200_measure_fp64_peak(bemb200_ctx* ctx, double* tflops) {
     cudaFree(d);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "dfma peak kernel");
     *tflops = best * 1e-12;
+    return BEMB200_OK;
+}
+
+int bemb200_measure_allgather(bemb200_ctx* ctx, uint64_t bytes_per_rank, int iters, int sync_each, double* usec_per_call) {
+    if (!ctx || !usec_per_call || iters < 1) return set_error(ctx, BEMB200_EINVAL, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    BEMB_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned char* buf = nullptr;
+    BEMB_CUDA(ctx, cudaMalloc((void**)&buf, bytes_per_rank * ctx->nranks + 16));
+    BEMB_CUDA(ctx, cudaMemsetAsync(buf, 0, bytes_per_rank * ctx->nranks, ctx->stream));
+    int rc = BEMB200_OK;
+    for (int i = 0; i < 5 && rc == BEMB200_OK; ++i) rc = nccl_allgather_bytes(ctx, buf + bytes_per_rank * ctx->rank, buf, bytes_per_rank);
+    cudaStreamSynchronize(ctx->stream);
+    auto t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < iters && rc == BEMB200_OK; ++i) {
+        rc = nccl_allgather_bytes(ctx, buf + bytes_per_rank * ctx->rank, buf, bytes_per_rank);
+        if (sync_each) cudaStreamSynchronize(ctx->stream);
+    }
+    cudaStreamSynchronize(ctx->stream);
+    auto t1 = std::chrono::steady_clock::now();
+    cudaFree(buf);
+    if (rc != BEMB200_OK) return rc;
+    *usec_per_call = std::chrono::duration<double, std::micro>(t1 - t0).count() / iters;
     return BEMB200_OK;
 }
 

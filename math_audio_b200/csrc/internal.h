@@ -23,7 +23,7 @@ struct DeviceMesh {
     cplx* bc_val = nullptr;      // [n][4]
     uint8_t* nonzero_bc = nullptr;  // [n]   has_nonzero_bc (tbem.rs:247)
     double* esize = nullptr;     // [n]      estimate_element_size (singular.rs:730-745)
-    double* far_y = nullptr;     // [ntiles][NQ_MAX][3][TILE]  quadrature points y_q
+    double* far_k = nullptr;     // [ntiles][NQ_MAX][TILE]     kappa_q = |y_q - y_0|^2
     double* far_c = nullptr;     // [ntiles][FAR_NCONST][TILE] per-column constants
     uint8_t* col_class = nullptr;   // [ntiles*TILE]
     uint32_t* special_cols = nullptr;  // [n_special]

@@ -110,46 +110,117 @@ zgemv_t_kernel(const cplx* __restrict__ A, uint64_t lda, uint64_t nrows, uint64_
 // ------------------------------------------------------------------------------------------
 // cluster helpers
 // ------------------------------------------------------------------------------------------
-constexpr int VEC_THREADS = 512;
 constexpr int MAX_CLUSTER = 16;
+constexpr int MAX_WARPS = 32;
 
 struct ClusterShared {
-    cplx part[2][MAX_CLUSTER];
-    double red[2][VEC_THREADS / 32];
+    cplx part[2][MAX_CLUSTER * MAX_WARPS];  // [parity][cta * nwarps + warp]
 };
 
-__device__ __forceinline__ cplx block_reduce(cplx v, ClusterShared& sh) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// Sum of one complex value over every thread of every CTA of the cluster with ONE cluster
+// barrier and no block barrier: warp shuffle -> each warp posts its partial into the slot table
+// of every CTA through DSMEM -> barrier.cluster -> every warp adds the nb*nw slots in the same
+// fixed order (bit-identical result in all warps of all CTAs).  `parity` must alternate between
+// consecutive calls (double-buffered slot table).
+__device__ __forceinline__ cplx cluster_allreduce(cplx v, ClusterShared& sh, int parity) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned nb = cluster.num_blocks(), me = cluster.block_rank();
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) {
         v.re += __shfl_xor_sync(0xffffffffu, v.re, m);
         v.im += __shfl_xor_sync(0xffffffffu, v.im, m);
     }
-    __syncthreads();  // protects sh.red against the previous use
-    if (lane == 0) { sh.red[0][warp] = v.re; sh.red[1][warp] = v.im; }
-    __syncthreads();
-    cplx t = C(0, 0);
-    const int nw = blockDim.x >> 5;
-    for (int w = 0; w < nw; ++w) { t.re += sh.red[0][w]; t.im += sh.red[1][w]; }
-    return t;  // every thread holds the block total
-}
-
-// all-CTA sum of one complex value; `parity` alternates between consecutive calls
-__device__ __forceinline__ cplx cluster_allreduce(cplx block_total, ClusterShared& sh, int parity) {
-    cg::cluster_group cluster = cg::this_cluster();
-    const unsigned nb = cluster.num_blocks(), me = cluster.block_rank();
-    if (threadIdx.x < nb) {
-        ClusterShared* remote = cluster.map_shared_rank(&sh, threadIdx.x);
-        remote->part[parity][me] = block_total;
+    if (lane < nb) {
+        ClusterShared* remote = cluster.map_shared_rank(&sh, lane);
+        remote->part[parity][me * nw + warp] = v;
     }
     cluster.sync();
     cplx t = C(0, 0);
-    for (unsigned d = 0; d < nb; ++d) { t.re += sh.part[parity][d].re; t.im += sh.part[parity][d].im; }
-    return t;  // bit-identical in every CTA (fixed summation order)
+    const unsigned total = nb * nw;
+    for (unsigned sidx = lane; sidx < total; sidx += 32) {
+        t.re += sh.part[parity][sidx].re;
+        t.im += sh.part[parity][sidx].im;
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        t.re += __shfl_xor_sync(0xffffffffu, t.re, m);
+        t.im += __shfl_xor_sync(0xffffffffu, t.im, m);
+    }
+    return t;
 }
 
-// One Arnoldi orthogonalisation step (gmres.rs:184-202).  One cluster; CTA c owns the slice
-// [c*S, (c+1)*S) of every vector.  w lives in shared memory when it fits, else in global.
+__device__ __forceinline__ cplx ldg_c(const cplx* p) {
+    double2 v = __ldg(reinterpret_cast<const double2*>(p));
+    return C(v.x, v.y);
+}
+
+// One Arnoldi orthogonalisation step (gmres.rs:184-202), register-resident variant: CTA c owns
+// the slice [c*S, (c+1)*S) and thread t its elements t, t+T, ... (EPT per thread) of w in
+// registers; v_{i+1} is prefetched while step i's dot product crosses the cluster.
+template <int EPT>
+__global__ void __launch_bounds__(256)
+mgs_cluster_reg_kernel(const cplx* __restrict__ V, uint64_t ldv, const cplx* __restrict__ w, int j, uint64_t n, uint64_t S,
+                       cplx* __restrict__ hcol, cplx* __restrict__ vnext, double breakdown_tol) {
+    __shared__ ClusterShared sh;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned me = cluster.block_rank();
+    const uint64_t begin = (uint64_t)me * S;
+    const uint64_t end = begin + S < n ? begin + S : n;
+    const uint64_t len = end > begin ? end - begin : 0;
+    cplx wr[EPT], vc[EPT], vn[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+        const uint64_t k = threadIdx.x + (uint64_t)e * blockDim.x;
+        wr[e] = k < len ? w[begin + k] : C(0, 0);
+        vc[e] = k < len ? ldg_c(V + begin + k) : C(0, 0);
+    }
+    int parity = 0;
+    for (int i = 0; i <= j; ++i) {
+        if (i < j) {
+            const cplx* vi1 = V + (uint64_t)(i + 1) * ldv + begin;
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+                const uint64_t k = threadIdx.x + (uint64_t)e * blockDim.x;
+                vn[e] = k < len ? ldg_c(vi1 + k) : C(0, 0);
+            }
+        }
+        cplx acc = C(0, 0);
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {  // conj(v) * w  (inner_product: blas_helpers.rs:21-33)
+            acc.re = fma(vc[e].re, wr[e].re, fma(vc[e].im, wr[e].im, acc.re));
+            acc.im = fma(vc[e].re, wr[e].im, fma(-vc[e].im, wr[e].re, acc.im));
+        }
+        const cplx h = cluster_allreduce(acc, sh, parity);
+        parity ^= 1;
+        if (me == 0 && threadIdx.x == 0) hcol[i] = h;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {  // axpy(-h, v_i, w)
+            wr[e].re = fma(-h.re, vc[e].re, fma(h.im, vc[e].im, wr[e].re));
+            wr[e].im = fma(-h.re, vc[e].im, fma(-h.im, vc[e].re, wr[e].im));
+            vc[e] = vn[e];
+        }
+    }
+    cplx acc = C(0, 0);
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) acc.re = fma(wr[e].re, wr[e].re, fma(wr[e].im, wr[e].im, acc.re));
+    const cplx nn = cluster_allreduce(acc, sh, parity);
+    const double nrm = sqrt(nn.re);
+    if (me == 0 && threadIdx.x == 0) hcol[j + 1] = C(nrm, 0.0);
+    if (!(nrm < breakdown_tol)) {
+        const double sc = 1.0 / nrm - 1.0;  // new_v = w; axpy(1/||w|| - 1, w, new_v)   (gmres.rs:198-201)
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            const uint64_t k = threadIdx.x + (uint64_t)e * blockDim.x;
+            if (k < len) vnext[begin + k] = C(wr[e].re + wr[e].re * sc, wr[e].im + wr[e].im * sc);
+        }
+    }
+    cluster.sync();  // no CTA may exit while a peer could still address its shared memory
+}
+
+// Same step for long vectors: w slice in shared memory (or global/L2 if even that does not
+// fit), v_i streamed from L2.
+constexpr int VEC_THREADS = 512;
 __global__ void __launch_bounds__(VEC_THREADS)
 mgs_cluster_kernel(const cplx* __restrict__ V, uint64_t ldv, cplx* __restrict__ w, int j, uint64_t n, uint64_t S,
                    int w_in_smem, cplx* __restrict__ hcol, cplx* __restrict__ vnext, double breakdown_tol) {
@@ -169,15 +240,15 @@ mgs_cluster_kernel(const cplx* __restrict__ V, uint64_t ldv, cplx* __restrict__ 
         const cplx* vi = V + (uint64_t)i * ldv + begin;
         cplx acc = C(0, 0);
         for (uint64_t k = threadIdx.x; k < len; k += blockDim.x) {
-            const cplx a = vi[k], b = ws[k];  // conj(a) * b  (inner_product: blas_helpers.rs:21-33)
+            const cplx a = ldg_c(vi + k), b = ws[k];
             acc.re = fma(a.re, b.re, fma(a.im, b.im, acc.re));
             acc.im = fma(a.re, b.im, fma(-a.im, b.re, acc.im));
         }
-        const cplx h = cluster_allreduce(block_reduce(acc, sh), sh, parity);
+        const cplx h = cluster_allreduce(acc, sh, parity);
         parity ^= 1;
         if (me == 0 && threadIdx.x == 0) hcol[i] = h;
-        for (uint64_t k = threadIdx.x; k < len; k += blockDim.x) {  // axpy(-h, v_i, w)
-            const cplx a = vi[k];
+        for (uint64_t k = threadIdx.x; k < len; k += blockDim.x) {
+            const cplx a = ldg_c(vi + k);
             cplx b = ws[k];
             b.re = fma(-h.re, a.re, fma(h.im, a.im, b.re));
             b.im = fma(-h.re, a.im, fma(-h.im, a.re, b.im));
@@ -186,18 +257,17 @@ mgs_cluster_kernel(const cplx* __restrict__ V, uint64_t ldv, cplx* __restrict__ 
     }
     cplx acc = C(0, 0);
     for (uint64_t k = threadIdx.x; k < len; k += blockDim.x) acc.re = fma(ws[k].re, ws[k].re, fma(ws[k].im, ws[k].im, acc.re));
-    const cplx nn = cluster_allreduce(block_reduce(acc, sh), sh, parity);
+    const cplx nn = cluster_allreduce(acc, sh, parity);
     const double nrm = sqrt(nn.re);
     if (me == 0 && threadIdx.x == 0) hcol[j + 1] = C(nrm, 0.0);
     if (!(nrm < breakdown_tol)) {
-        // new_v = w; axpy(1/||w|| - 1, w, new_v)   (gmres.rs:198-201)
-        const double s = 1.0 / nrm - 1.0;
+        const double sc = 1.0 / nrm - 1.0;
         for (uint64_t k = threadIdx.x; k < len; k += blockDim.x) {
             const cplx b = ws[k];
-            vnext[begin + k] = C(b.re + b.re * s, b.im + b.im * s);
+            vnext[begin + k] = C(b.re + b.re * sc, b.im + b.im * sc);
         }
     }
-    cluster.sync();  // no CTA may exit while a peer could still address its shared memory
+    cluster.sync();
 }
 
 // r = b - ax ; out[0] = sum |r|^2  (one cluster)
@@ -216,7 +286,7 @@ residual_cluster_kernel(const cplx* __restrict__ b, const cplx* __restrict__ ax,
         if (r) r[k] = v;
         acc.re = fma(v.re, v.re, fma(v.im, v.im, acc.re));
     }
-    const cplx t = cluster_allreduce(block_reduce(acc, sh), sh, 0);
+    const cplx t = cluster_allreduce(acc, sh, 0);
     if (me == 0 && threadIdx.x == 0) out[0] = t.re;
     cluster.sync();
 }
@@ -352,7 +422,35 @@ static int pick_cluster(uint64_t n, int level, bool* w_in_smem, size_t* smem_byt
 
 static int g_cluster_level = 0;
 
+template <int EPT>
+static cudaError_t launch_mgs_reg(int cl, const cplx* V, uint64_t ldv, const cplx* w, int j, uint64_t n, uint64_t S, cplx* hcol,
+                                  cplx* vnext, cudaStream_t s) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(mgs_cluster_reg_kernel<EPT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    return launch_cluster(mgs_cluster_reg_kernel<EPT>, cl, 256, 0, s, V, ldv, w, j, n, S, hcol, vnext, 1e-14);
+}
+
+static int g_mgs_mode = 0;  // 0: register kernel on a 16-CTA cluster when the slice fits, 1: generic kernel only
+
 cudaError_t launch_mgs(const cplx* V, uint64_t ldv, cplx* w, int j, uint64_t n, cplx* hcol, cplx* vnext, cudaStream_t s) {
+    if (g_mgs_mode == 0 && n <= 16ull * 256ull * 8ull) {
+        // register-resident w: 16 CTAs (non-portable cluster size) x 256 threads x <= 8 elements
+        const int cl = n >= 2048 ? 16 : (n >= 512 ? 4 : 1);
+        const uint64_t S = (n + cl - 1) / cl;
+        const uint64_t ept = (S + 255) / 256;
+        cudaError_t e;
+        if (ept <= 1) e = launch_mgs_reg<1>(cl, V, ldv, w, j, n, S, hcol, vnext, s);
+        else if (ept <= 2) e = launch_mgs_reg<2>(cl, V, ldv, w, j, n, S, hcol, vnext, s);
+        else if (ept <= 4) e = launch_mgs_reg<4>(cl, V, ldv, w, j, n, S, hcol, vnext, s);
+        else e = launch_mgs_reg<8>(cl, V, ldv, w, j, n, S, hcol, vnext, s);
+        if (e == cudaSuccess) return e;
+        cudaGetLastError();  // a 16-CTA cluster this device cannot place: fall back for good
+        g_mgs_mode = 1;
+    }
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(mgs_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
