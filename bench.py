@@ -80,6 +80,15 @@ def physics_for(wl, step):
     return ka, ph, beta
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def load_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -220,7 +229,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -418,13 +427,19 @@ def run_native(args):
             "sample": (f"oracle port: {cs['rows']} of {n} rows assembled ({cs['asm_s']:.1f} s/frequency extrapolated) + zgemv on that slab "
                        f"({cs['matvec_s'] * 1e3:.1f} ms/matvec extrapolated) x {cs['matvecs']} matvecs at ka={cs['ka']:.3f}; {cs['src']}"),
             "assembly_gflops": cs["asm_gflops"], "matvec_gbs": cs["matvec_gbs"]}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
 def main():
+    # ONE JSON line on stdout: everything else any library prints (NCCL banner, warnings) is sent
+    # to stderr by pointing fd 1 at fd 2 and keeping a private handle on the real stdout.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)

@@ -147,9 +147,32 @@ int bemb200_apply_device(const bemb200_matrix* m, const double* x_dev, double* y
  * x_out: num_rows complex128 on the HOST. */
 int bemb200_gmres(const bemb200_matrix* m, const double* b, const double* x0, uint32_t max_iterations, uint32_t restart,
                   double tolerance, double* x_out, bemb200_gmres_info* info);
+/* gmres_preconditioned / gmres_preconditioned_with_guess (gmres.rs:282-585): LEFT preconditioning,
+ * residual relative to ||M^-1 b||.  The preconditioners of the reference that make sense for a
+ * dense operator at scale are built in: inv_diag == NULL is IdentityPreconditioner
+ * (traits.rs:377-385); otherwise inv_diag (num_rows complex128, host) is the inverse diagonal of
+ * DiagonalPreconditioner (math-solvers/src/preconditioners/diagonal.rs:20-58). */
+int bemb200_gmres_preconditioned(const bemb200_matrix* m, const double* inv_diag, const double* b, const double* x0,
+                                 uint32_t max_iterations, uint32_t restart, double tolerance, double* x_out,
+                                 bemb200_gmres_info* info);
+/* diagonal of the (square) matrix, all ranks receive all num_rows entries */
+int bemb200_matrix_diagonal(const bemb200_matrix* m, double* out);
 /* same with DEVICE pointers (b_dev, x0_dev or NULL, x_dev) */
 int bemb200_gmres_device(const bemb200_matrix* m, const double* b_dev, const double* x0_dev, uint32_t max_iterations,
                          uint32_t restart, double tolerance, double* x_dev, bemb200_gmres_info* info);
+/* Multi-RHS solve (BASELINE config 5): `nrhs` (<= 32) independent gmres() solves -- the reference
+ * would loop `gmres(operator, b_s, config)` over the right-hand sides -- advanced in lockstep so
+ * that they share ONE FP64 tensor-core block matvec per iteration (A is streamed once for all
+ * right-hand sides).  Per-RHS semantics (iterations, restarts, residual, converged) are exactly
+ * those of the single-RHS call.  b_all / x_all: nrhs vectors of num_rows complex128, each
+ * contiguous; infos[nrhs].  block_matvec_ms / block_matvecs (may be NULL): device time and count
+ * of the block matvec kernel. */
+int bemb200_gmres_batched(const bemb200_matrix* m, const double* b_all, uint32_t nrhs, uint32_t max_iterations,
+                          uint32_t restart, double tolerance, double* x_all, bemb200_gmres_info* infos,
+                          double* block_matvec_ms, uint64_t* block_matvecs);
+/* Y = A X for nrhs (<= 32) vectors at once with the tensor-core block kernel; kernel_ms (may be
+ * NULL) receives the device time of one block matvec */
+int bemb200_apply_block(const bemb200_matrix* m, const double* x_all, uint32_t nrhs, double* y_all, double* kernel_ms);
 /* number of kernels launched and device milliseconds spent inside the zgemv kernel by
  * the last bemb200_gmres* / bemb200_apply* call on this matrix */
 int bemb200_solver_stats(const bemb200_matrix* m, uint64_t* kernel_launches, double* matvec_ms, uint64_t* matvecs);

@@ -79,7 +79,12 @@ SYMBOLS = {
     "bemb200_apply_transpose": (C.c_int, [_VP, _VP, _VP]),
     "bemb200_apply_device": (C.c_int, [_VP, _VP, _VP]),
     "bemb200_gmres": (C.c_int, [_VP, _VP, _VP, C.c_uint32, C.c_uint32, C.c_double, _VP, C.POINTER(CGmresInfo)]),
+    "bemb200_gmres_preconditioned": (C.c_int, [_VP, _VP, _VP, _VP, C.c_uint32, C.c_uint32, C.c_double, _VP, C.POINTER(CGmresInfo)]),
+    "bemb200_matrix_diagonal": (C.c_int, [_VP, _VP]),
     "bemb200_gmres_device": (C.c_int, [_VP, _VP, _VP, C.c_uint32, C.c_uint32, C.c_double, _VP, C.POINTER(CGmresInfo)]),
+    "bemb200_gmres_batched": (C.c_int, [_VP, _VP, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, _VP, C.POINTER(CGmresInfo),
+                                        C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "bemb200_apply_block": (C.c_int, [_VP, _VP, C.c_uint32, _VP, C.POINTER(C.c_double)]),
     "bemb200_solver_stats": (C.c_int, [_VP, C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "bemb200_measure_fp64_peak": (C.c_int, [_VP, C.POINTER(C.c_double)]),
     "bemb200_selftest_math": (C.c_int, [_VP, C.c_uint64, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]),

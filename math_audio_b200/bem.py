@@ -350,8 +350,109 @@ def apply_device(operator: DenseOperator, x_dev: int, y_dev: int) -> None:
     _capi.check(_capi.lib().bemb200_apply_device(operator.matrix._h, C.c_void_p(x_dev), C.c_void_p(y_dev)), operator.matrix.ctx._h)
 
 
+class IdentityPreconditioner:
+    """traits.rs:377-385."""
+
+    inv_diag = None
+
+    def apply(self, r: np.ndarray) -> np.ndarray:
+        return np.array(r, copy=True)
+
+
+class DiagonalPreconditioner:
+    """math-solvers/src/preconditioners/diagonal.rs:20-80 (Jacobi): M^-1 r = r_i / A_ii."""
+
+    def __init__(self, inv_diag: np.ndarray):
+        self.inv_diag = np.ascontiguousarray(inv_diag, dtype=np.complex128)
+
+    @staticmethod
+    def from_diagonal(diag: np.ndarray) -> "DiagonalPreconditioner":  # diagonal.rs:40-50
+        d = np.asarray(diag, dtype=np.complex128)
+        out = np.ones_like(d)
+        ok = np.sqrt(d.real ** 2 + d.imag ** 2) > 1e-30
+        ns = d.real[ok] ** 2 + d.imag[ok] ** 2
+        out[ok] = d.real[ok] / ns - 1j * (d.imag[ok] / ns)  # ComplexField::inv (traits.rs:150-153)
+        return DiagonalPreconditioner(out)
+
+    @staticmethod
+    def from_inverse_diagonal(inv_diag: np.ndarray) -> "DiagonalPreconditioner":  # diagonal.rs:53-55
+        return DiagonalPreconditioner(inv_diag)
+
+    @staticmethod
+    def from_operator(operator: "DenseOperator") -> "DiagonalPreconditioner":
+        """Jacobi preconditioner of a device-resident operator (diagonal fetched from the GPU)."""
+        n = operator.num_rows()
+        d = np.empty(n, dtype=np.complex128)
+        _capi.check(_capi.lib().bemb200_matrix_diagonal(operator.matrix._h, _capi.ptr(d)), operator.matrix.ctx._h)
+        return DiagonalPreconditioner.from_diagonal(d)
+
+    def apply(self, r: np.ndarray) -> np.ndarray:
+        return r * self.inv_diag
+
+
+def gmres_preconditioned_with_guess(operator: DenseOperator, precond, b: np.ndarray, x0: Optional[np.ndarray],
+                                    config: GmresConfig) -> GmresSolution:
+    """gmres.rs:434-585: left-preconditioned restarted GMRES on the device.  ``precond`` is an
+    IdentityPreconditioner or a DiagonalPreconditioner (the two preconditioners of the reference that
+    apply to a dense operator without an O(N^3) factorisation)."""
+    if not isinstance(precond, (IdentityPreconditioner, DiagonalPreconditioner)):
+        raise TypeError("the device solver supports IdentityPreconditioner and DiagonalPreconditioner")
+    b = np.ascontiguousarray(b, dtype=np.complex128)
+    n = operator.num_rows()
+    if b.shape != (n,):
+        raise ValueError(f"gmres: b has shape {b.shape}, operator has {n} rows")
+    x0a = np.ascontiguousarray(x0, dtype=np.complex128) if x0 is not None else None
+    idg = precond.inv_diag
+    if idg is not None and idg.shape != (n,):
+        raise ValueError("preconditioner has the wrong length")
+    x = np.empty(n, dtype=np.complex128)
+    info = _capi.CGmresInfo()
+    _capi.check(_capi.lib().bemb200_gmres_preconditioned(operator.matrix._h, _capi.ptr(idg) if idg is not None else None,
+                                                         _capi.ptr(b), _capi.ptr(x0a) if x0a is not None else None,
+                                                         config.max_iterations, config.restart, config.tolerance, _capi.ptr(x),
+                                                         C.byref(info)), operator.matrix.ctx._h)
+    return GmresSolution(x=x, iterations=int(info.iterations), restarts=int(info.restarts), residual=float(info.residual),
+                         converged=bool(info.converged))
+
+
+def gmres_preconditioned(operator: DenseOperator, precond, b: np.ndarray, config: GmresConfig) -> GmresSolution:  # gmres.rs:282
+    return gmres_preconditioned_with_guess(operator, precond, b, None, config)
+
+
 def gmres(operator: DenseOperator, b: np.ndarray, config: GmresConfig) -> GmresSolution:  # gmres.rs:96-102
     return gmres_with_guess(operator, b, None, config)
+
+
+def gmres_batched(operator: DenseOperator, b_all: np.ndarray, config: GmresConfig):
+    """``[gmres(operator, b, config) for b in b_all]`` (the reference's way to solve several
+    right-hand sides) executed in lockstep on the device with one tensor-core block matvec per
+    iteration.  ``b_all``: (nrhs, n).  Returns (list of GmresSolution, stats dict)."""
+    b_all = np.ascontiguousarray(b_all, dtype=np.complex128)
+    n = operator.num_rows()
+    if b_all.ndim != 2 or b_all.shape[1] != n:
+        raise ValueError(f"gmres_batched: b_all has shape {b_all.shape}, expected (nrhs, {n})")
+    nrhs = b_all.shape[0]
+    x_all = np.empty_like(b_all)
+    infos = (_capi.CGmresInfo * nrhs)()
+    ms, cnt = C.c_double(), C.c_uint64()
+    _capi.check(_capi.lib().bemb200_gmres_batched(operator.matrix._h, _capi.ptr(b_all), nrhs, config.max_iterations, config.restart,
+                                                  config.tolerance, _capi.ptr(x_all), infos, C.byref(ms), C.byref(cnt)),
+                operator.matrix.ctx._h)
+    sols = [GmresSolution(x=x_all[i], iterations=int(infos[i].iterations), restarts=int(infos[i].restarts),
+                          residual=float(infos[i].residual), converged=bool(infos[i].converged)) for i in range(nrhs)]
+    return sols, dict(block_matvec_ms=float(ms.value), block_matvecs=int(cnt.value))
+
+
+def apply_block(operator: DenseOperator, x_all: np.ndarray):
+    """A @ x for nrhs vectors at once (tensor-core block matvec) -> (y_all, kernel_ms)."""
+    x_all = np.ascontiguousarray(x_all, dtype=np.complex128)
+    if x_all.ndim != 2 or x_all.shape[1] != operator.num_cols():
+        raise ValueError("apply_block: x_all must be (nrhs, num_cols)")
+    y_all = np.empty((x_all.shape[0], operator.num_rows()), dtype=np.complex128)
+    ms = C.c_double()
+    _capi.check(_capi.lib().bemb200_apply_block(operator.matrix._h, _capi.ptr(x_all), x_all.shape[0], _capi.ptr(y_all), C.byref(ms)),
+                operator.matrix.ctx._h)
+    return y_all, float(ms.value)
 
 
 def solve_gmres(operator: DenseOperator, b: np.ndarray, config: GmresConfig) -> GmresSolution:  # fmm_interface.rs:378-384

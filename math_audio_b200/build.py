@@ -28,6 +28,7 @@ UNITS = {
     "assembly_far.cu": [],
     "linalg.cu": [],
     "gmres.cu": [],
+    "block_gmres.cu": [],
     "api.cu": [],
 }
 

@@ -10,6 +10,7 @@
 // vectors, so all ranks hold bit-identical Krylov bases and Hessenberg columns and take the
 // same convergence decisions without any all-reduce.
 #include <chrono>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -32,12 +33,16 @@ struct GmresWorkspace {
     cplx* xin = nullptr;    // npad  staging for host-pointer calls
     cplx* bin = nullptr;    // npad
     cplx* xout = nullptr;   // npad
-    cplx* hcol_d = nullptr; // restart+2
+    cplx* hcol_d = nullptr; // (restart+1) slots x (restart+2): one Hessenberg column per in-flight iteration
     cplx* ycoef_d = nullptr;
     double* scal_d = nullptr;
-    cplx* hcol_h = nullptr;   // pinned
+    cplx* hcol_h = nullptr;   // pinned, same shape as hcol_d
     double* scal_h = nullptr; // pinned
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // per-iteration events: matvec start/stop and "column j is on the host"
+    std::vector<cudaEvent_t> it_ev0, it_ev1, it_done;
+    std::vector<char> launched;
+    uint32_t ldh_slot = 0;
 };
 
 namespace bemb {
@@ -50,6 +55,8 @@ void free_workspace(bemb200_matrix* m) {
     if (ws->scal_h) cudaFreeHost(ws->scal_h);
     if (ws->ev0) cudaEventDestroy(ws->ev0);
     if (ws->ev1) cudaEventDestroy(ws->ev1);
+    for (auto& v : {ws->it_ev0, ws->it_ev1, ws->it_done})
+        for (cudaEvent_t e : v) cudaEventDestroy(e);
     delete ws;
     m->ws = nullptr;
 }
@@ -73,10 +80,18 @@ static int ensure_workspace(bemb200_matrix* m, uint32_t restart) {
     BEMB_CUDA(ctx, cudaMalloc((void**)&ws->xin, vb));
     BEMB_CUDA(ctx, cudaMalloc((void**)&ws->bin, vb));
     BEMB_CUDA(ctx, cudaMalloc((void**)&ws->xout, vb));
-    BEMB_CUDA(ctx, cudaMalloc((void**)&ws->hcol_d, (restart + 2) * sizeof(cplx)));
+    ws->ldh_slot = restart + 2;
+    BEMB_CUDA(ctx, cudaMalloc((void**)&ws->hcol_d, (size_t)(restart + 1) * ws->ldh_slot * sizeof(cplx)));
     BEMB_CUDA(ctx, cudaMalloc((void**)&ws->ycoef_d, (restart + 2) * sizeof(cplx)));
     BEMB_CUDA(ctx, cudaMalloc((void**)&ws->scal_d, 4 * sizeof(double)));
-    BEMB_CUDA(ctx, cudaMallocHost((void**)&ws->hcol_h, (restart + 2) * sizeof(cplx)));
+    BEMB_CUDA(ctx, cudaMallocHost((void**)&ws->hcol_h, (size_t)(restart + 1) * ws->ldh_slot * sizeof(cplx)));
+    ws->it_ev0.resize(restart + 1); ws->it_ev1.resize(restart + 1); ws->it_done.resize(restart + 1);
+    ws->launched.assign(restart + 1, 0);
+    for (uint32_t i = 0; i <= restart; ++i) {
+        BEMB_CUDA(ctx, cudaEventCreate(&ws->it_ev0[i]));
+        BEMB_CUDA(ctx, cudaEventCreate(&ws->it_ev1[i]));
+        BEMB_CUDA(ctx, cudaEventCreateWithFlags(&ws->it_done[i], cudaEventDisableTiming));
+    }
     BEMB_CUDA(ctx, cudaMallocHost((void**)&ws->scal_h, 4 * sizeof(double)));
     BEMB_CUDA(ctx, cudaEventCreate(&ws->ev0));
     BEMB_CUDA(ctx, cudaEventCreate(&ws->ev1));
@@ -109,6 +124,10 @@ static void accumulate_matvec_time(bemb200_matrix* m) {
 }
 
 static double g_dbg_launch_us = 0.0, g_dbg_wait_us = 0.0;  // host-side phase timers (diagnostics)
+static const bool g_speculate = []() {
+    const char* v = std::getenv("BEMB200_GMRES_SPECULATE");
+    return v ? (std::atoi(v) != 0) : true;
+}();
 
 // ---- host-side pieces of gmres.rs ----------------------------------------------------------
 static inline double tnorm(cplx a) { return std::sqrt(norm_sqr(a)); }  // ComplexField::norm (traits.rs:93-95)
@@ -134,10 +153,10 @@ static void solve_upper_triangular(const std::vector<cplx>& h, int ldh, const st
     }
 }
 
-static int norm_of(bemb200_matrix* m, const cplx* b, const cplx* ax, cplx* r, double* out) {
+static int norm_of(bemb200_matrix* m, const cplx* b, const cplx* ax, cplx* r, double* out, const cplx* pinv = nullptr) {
     bemb200_ctx* ctx = m->ctx;
     GmresWorkspace* ws = m->ws;
-    BEMB_CUDA(ctx, launch_residual(b, ax, r, m->n_rows, ws->scal_d, ctx->stream));
+    BEMB_CUDA(ctx, launch_residual(b, ax, r, m->n_rows, ws->scal_d, pinv, ctx->stream));
     m->last_launches += 1;
     BEMB_CUDA(ctx, cudaMemcpyAsync(ws->scal_h, ws->scal_d, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     BEMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -156,17 +175,21 @@ static int update_x(bemb200_matrix* m, cplx* x, const std::vector<cplx>& y) {
     return BEMB200_OK;
 }
 
-// gmres_with_guess (gmres.rs:105-277) with device vectors b, x (x holds x0 on entry)
+// gmres_with_guess (gmres.rs:105-277) with device vectors b, x (x holds x0 on entry).
+// `precond` selects the left-preconditioned variant gmres_preconditioned_with_guess
+// (gmres.rs:434-585): pinv = inverse diagonal on the device (DiagonalPreconditioner) or nullptr
+// with precond = true (IdentityPreconditioner).
 static int gmres_core(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t max_iterations, uint32_t restart, double tol,
-                      bemb200_gmres_info* info) {
+                      bemb200_gmres_info* info, bool precond = false, const cplx* pinv = nullptr) {
     bemb200_ctx* ctx = m->ctx;
     GmresWorkspace* ws = m->ws;
     const uint64_t n = m->n_rows;
     const int mm = (int)restart;
     cudaStream_t s = ctx->stream;
     double b_norm = 0.0;
-    int rc = norm_of(m, b, nullptr, nullptr, &b_norm);
+    int rc = norm_of(m, b, nullptr, nullptr, &b_norm, pinv);  // ||b|| resp. ||M^-1 b|| (gmres.rs:455-457)
     if (rc != BEMB200_OK) return rc;
+    const int direct_scale = precond ? 1 : 0;
     if (b_norm < 1e-15) {
         *info = bemb200_gmres_info{0, 0, 0.0, 1};
         return BEMB200_OK;
@@ -178,7 +201,7 @@ static int gmres_core(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t max_it
         rc = matvec(m, x, ws->w, true);
         if (rc != BEMB200_OK) return rc;
         double beta = 0.0;
-        rc = norm_of(m, b, ws->w, ws->r, &beta);
+        rc = norm_of(m, b, ws->w, ws->r, &beta, pinv);
         if (rc != BEMB200_OK) return rc;
         accumulate_matvec_time(m);
         double rel = beta / b_norm;
@@ -193,22 +216,55 @@ static int gmres_core(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t max_it
         g.assign(mm + 1, C(0, 0));
         g[0] = C(beta, 0.0);
         bool inner_converged = false;
+        // One Arnoldi iteration = ZGEMV (+ all-gather) + ONE cluster MGS kernel + a (j+2)-number
+        // D2H copy.  Iteration j+1 is enqueued BEFORE the host waits for column j, so the GPU never
+        // idles on the host round trip; if column j turns out to converge, the speculative
+        // iteration j+1 is simply ignored (it only touches V[j+2], w and its own column slot).
+        for (int j = 0; j < mm; ++j) ws->launched[j] = 0;
+        auto enqueue_iteration = [&](int j) -> int {
+            BEMB_CUDA(ctx, cudaEventRecord(ws->it_ev0[j], s));
+            const uint64_t nloc = m->r1 - m->r0;
+            cplx* yloc = ws->w + (ctx->nranks > 1 ? (uint64_t)ctx->rank * ws->chunk : m->r0);
+            BEMB_CUDA(ctx, launch_zgemv(m->A, m->n_cols, nloc, m->n_cols, ws->V + (uint64_t)j * ws->npad, yloc, s));
+            BEMB_CUDA(ctx, cudaEventRecord(ws->it_ev1[j], s));
+            if (ctx->nranks > 1) {
+                int rc2 = nccl_allgather_bytes(ctx, yloc, ws->w, ws->chunk * sizeof(cplx));
+                if (rc2 != BEMB200_OK) return rc2;
+            }
+            cplx* hd = ws->hcol_d + (size_t)j * ws->ldh_slot;
+            BEMB_CUDA(ctx, launch_mgs(ws->V, ws->npad, ws->w, j, n, hd, ws->V + (uint64_t)(j + 1) * ws->npad, pinv, direct_scale, s));
+            BEMB_CUDA(ctx, cudaMemcpyAsync(ws->hcol_h + (size_t)j * ws->ldh_slot, hd, (j + 2) * sizeof(cplx),
+                                           cudaMemcpyDeviceToHost, s));
+            BEMB_CUDA(ctx, cudaEventRecord(ws->it_done[j], s));
+            ws->launched[j] = 1;
+            m->last_launches += 2;  // every launch counts, also a speculative iteration that ends up unused
+            return BEMB200_OK;
+        };
         for (int j = 0; j < mm; ++j) {
             total_iterations += 1;
             auto tp0 = std::chrono::steady_clock::now();
-            rc = matvec(m, ws->V + (uint64_t)j * ws->npad, ws->w, true);
-            if (rc != BEMB200_OK) return rc;
-            BEMB_CUDA(ctx, launch_mgs(ws->V, ws->npad, ws->w, j, n, ws->hcol_d, ws->V + (uint64_t)(j + 1) * ws->npad, s));
-            m->last_launches += 1;
-            BEMB_CUDA(ctx, cudaMemcpyAsync(ws->hcol_h, ws->hcol_d, (j + 2) * sizeof(cplx), cudaMemcpyDeviceToHost, s));
+            if (!ws->launched[j]) {
+                rc = enqueue_iteration(j);
+                if (rc != BEMB200_OK) return rc;
+            }
+            if (g_speculate && j + 1 < mm && !ws->launched[j + 1]) {
+                rc = enqueue_iteration(j + 1);
+                if (rc != BEMB200_OK) return rc;
+            }
             auto tp1 = std::chrono::steady_clock::now();
-            BEMB_CUDA(ctx, cudaStreamSynchronize(s));
+            BEMB_CUDA(ctx, cudaEventSynchronize(ws->it_done[j]));
             auto tp2 = std::chrono::steady_clock::now();
-            accumulate_matvec_time(m);
+            {
+                float ms = 0.f;
+                if (cudaEventElapsedTime(&ms, ws->it_ev0[j], ws->it_ev1[j]) == cudaSuccess) m->last_matvec_ms += ms;
+                else cudaGetLastError();
+                m->last_matvecs += 1;  // matvecs whose duration is in last_matvec_ms
+            }
             g_dbg_launch_us += std::chrono::duration<double, std::micro>(tp1 - tp0).count();
             g_dbg_wait_us += std::chrono::duration<double, std::micro>(tp2 - tp1).count();
-            for (int i = 0; i <= j; ++i) h[i * ldh + j] = ws->hcol_h[i];
-            const double w_norm = ws->hcol_h[j + 1].re;
+            const cplx* hcol = ws->hcol_h + (size_t)j * ws->ldh_slot;
+            for (int i = 0; i <= j; ++i) h[i * ldh + j] = hcol[i];
+            const double w_norm = hcol[j + 1].re;
             h[(j + 1) * ldh + j] = C(w_norm, 0.0);
             if (w_norm < 1e-14) inner_converged = true;  // breakdown: v_{j+1} not formed (gmres.rs:194-202)
             for (int i = 0; i < j; ++i) {
@@ -241,7 +297,7 @@ static int gmres_core(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t max_it
     rc = matvec(m, x, ws->w, true);
     if (rc != BEMB200_OK) return rc;
     double rn = 0.0;
-    rc = norm_of(m, b, ws->w, ws->r, &rn);
+    rc = norm_of(m, b, ws->w, ws->r, &rn, pinv);
     if (rc != BEMB200_OK) return rc;
     accumulate_matvec_time(m);
     *info = bemb200_gmres_info{total_iterations, restarts, rn / b_norm, 0};
@@ -321,6 +377,63 @@ int bemb200_gmres(const bemb200_matrix* cm, const double* b, const double* x0, u
     rc = gmres_core(m, ws->bin, ws->xout, max_iterations, restart, tolerance, info);
     if (rc != BEMB200_OK) return rc;
     BEMB_CUDA(ctx, cudaMemcpyAsync(x_out, ws->xout, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    BEMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BEMB200_OK;
+}
+
+int bemb200_gmres_preconditioned(const bemb200_matrix* cm, const double* inv_diag, const double* b, const double* x0,
+                                 uint32_t max_iterations, uint32_t restart, double tolerance, double* x_out,
+                                 bemb200_gmres_info* info) {
+    bemb200_matrix* m = const_cast<bemb200_matrix*>(cm);
+    if (!m || !b || !x_out || !info) return set_error(nullptr, BEMB200_EINVAL, "NULL argument");
+    bemb200_ctx* ctx = m->ctx;
+    if (m->n_rows != m->n_cols) return set_error(ctx, BEMB200_EINVAL, "gmres needs a square operator");
+    if (restart == 0) return set_error(ctx, BEMB200_EINVAL, "restart must be >= 1");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    BEMB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = check_partition(m);
+    if (rc != BEMB200_OK) return rc;
+    rc = ensure_workspace(m, restart);
+    if (rc != BEMB200_OK) return rc;
+    reset_stats(m);
+    GmresWorkspace* ws = m->ws;
+    const size_t nb = m->n_rows * sizeof(cplx);
+    BEMB_CUDA(ctx, cudaMemcpyAsync(ws->bin, b, nb, cudaMemcpyHostToDevice, ctx->stream));
+    if (x0) BEMB_CUDA(ctx, cudaMemcpyAsync(ws->xout, x0, nb, cudaMemcpyHostToDevice, ctx->stream));
+    else BEMB_CUDA(ctx, cudaMemsetAsync(ws->xout, 0, nb, ctx->stream));
+    const cplx* pinv = nullptr;
+    if (inv_diag) {
+        BEMB_CUDA(ctx, cudaMemcpyAsync(ws->xin, inv_diag, nb, cudaMemcpyHostToDevice, ctx->stream));
+        pinv = ws->xin;
+    }
+    rc = gmres_core(m, ws->bin, ws->xout, max_iterations, restart, tolerance, info, true, pinv);
+    if (rc != BEMB200_OK) return rc;
+    BEMB_CUDA(ctx, cudaMemcpyAsync(x_out, ws->xout, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    BEMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BEMB200_OK;
+}
+
+int bemb200_matrix_diagonal(const bemb200_matrix* cm, double* out) {
+    bemb200_matrix* m = const_cast<bemb200_matrix*>(cm);
+    if (!m || !out) return set_error(nullptr, BEMB200_EINVAL, "NULL argument");
+    bemb200_ctx* ctx = m->ctx;
+    if (m->n_rows != m->n_cols) return set_error(ctx, BEMB200_EINVAL, "diagonal needs a square matrix");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    BEMB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = check_partition(m);
+    if (rc != BEMB200_OK) return rc;
+    rc = ensure_workspace(m, 1);
+    if (rc != BEMB200_OK) return rc;
+    GmresWorkspace* ws = m->ws;
+    const uint64_t nloc = m->r1 - m->r0;
+    cplx* loc = ws->r + (ctx->nranks > 1 ? (uint64_t)ctx->rank * ws->chunk : m->r0);
+    // strided gather of A[i, r0 + i]
+    if (nloc)
+        BEMB_CUDA(ctx, cudaMemcpy2DAsync(loc, sizeof(cplx), m->A + m->r0, (m->n_cols + 1) * sizeof(cplx), sizeof(cplx), nloc,
+                                         cudaMemcpyDeviceToDevice, ctx->stream));
+    rc = nccl_allgather_bytes(ctx, loc, ws->r, ws->chunk * sizeof(cplx));
+    if (rc != BEMB200_OK) return rc;
+    BEMB_CUDA(ctx, cudaMemcpyAsync(out, ws->r, m->n_rows * sizeof(cplx), cudaMemcpyDeviceToHost, ctx->stream));
     BEMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return BEMB200_OK;
 }

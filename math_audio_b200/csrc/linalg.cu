@@ -161,7 +161,8 @@ __device__ __forceinline__ cplx ldg_c(const cplx* p) {
 template <int EPT>
 __global__ void __launch_bounds__(256)
 mgs_cluster_reg_kernel(const cplx* __restrict__ V, uint64_t ldv, const cplx* __restrict__ w, int j, uint64_t n, uint64_t S,
-                       cplx* __restrict__ hcol, cplx* __restrict__ vnext, double breakdown_tol) {
+                       cplx* __restrict__ hcol, cplx* __restrict__ vnext, double breakdown_tol,
+                       const cplx* __restrict__ pinv, int direct_scale) {
     __shared__ ClusterShared sh;
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned me = cluster.block_rank();
@@ -173,6 +174,7 @@ mgs_cluster_reg_kernel(const cplx* __restrict__ V, uint64_t ldv, const cplx* __r
     for (int e = 0; e < EPT; ++e) {
         const uint64_t k = threadIdx.x + (uint64_t)e * blockDim.x;
         wr[e] = k < len ? w[begin + k] : C(0, 0);
+        if (pinv && k < len) wr[e] = wr[e] * ldg_c(pinv + begin + k);  // w = M^-1 (A v_j)  (gmres.rs:345-347)
         vc[e] = k < len ? ldg_c(V + begin + k) : C(0, 0);
     }
     int parity = 0;
@@ -208,11 +210,14 @@ mgs_cluster_reg_kernel(const cplx* __restrict__ V, uint64_t ldv, const cplx* __r
     const double nrm = sqrt(nn.re);
     if (me == 0 && threadIdx.x == 0) hcol[j + 1] = C(nrm, 0.0);
     if (!(nrm < breakdown_tol)) {
-        const double sc = 1.0 / nrm - 1.0;  // new_v = w; axpy(1/||w|| - 1, w, new_v)   (gmres.rs:198-201)
+        const double inv = 1.0 / nrm;
+        const double sc = inv - 1.0;  // new_v = w; axpy(1/||w|| - 1, w, new_v)   (gmres.rs:198-201)
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
             const uint64_t k = threadIdx.x + (uint64_t)e * blockDim.x;
-            if (k < len) vnext[begin + k] = C(wr[e].re + wr[e].re * sc, wr[e].im + wr[e].im * sc);
+            if (k < len)
+                vnext[begin + k] = direct_scale ? C(wr[e].re * inv, wr[e].im * inv)  // w.mapv(|wi| wi * (1/||w||)) (gmres.rs:362)
+                                                : C(wr[e].re + wr[e].re * sc, wr[e].im + wr[e].im * sc);
         }
     }
     cluster.sync();  // no CTA may exit while a peer could still address its shared memory
@@ -223,7 +228,8 @@ mgs_cluster_reg_kernel(const cplx* __restrict__ V, uint64_t ldv, const cplx* __r
 constexpr int VEC_THREADS = 512;
 __global__ void __launch_bounds__(VEC_THREADS)
 mgs_cluster_kernel(const cplx* __restrict__ V, uint64_t ldv, cplx* __restrict__ w, int j, uint64_t n, uint64_t S,
-                   int w_in_smem, cplx* __restrict__ hcol, cplx* __restrict__ vnext, double breakdown_tol) {
+                   int w_in_smem, cplx* __restrict__ hcol, cplx* __restrict__ vnext, double breakdown_tol,
+                   const cplx* __restrict__ pinv, int direct_scale) {
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ ClusterShared sh;
     cg::cluster_group cluster = cg::this_cluster();
@@ -232,8 +238,12 @@ mgs_cluster_kernel(const cplx* __restrict__ V, uint64_t ldv, cplx* __restrict__ 
     const uint64_t end = begin + S < n ? begin + S : n;
     const uint64_t len = end > begin ? end - begin : 0;
     cplx* ws = w_in_smem ? reinterpret_cast<cplx*>(dyn) : (w + begin);
-    if (w_in_smem)
-        for (uint64_t k = threadIdx.x; k < len; k += blockDim.x) ws[k] = w[begin + k];
+    if (w_in_smem || pinv)
+        for (uint64_t k = threadIdx.x; k < len; k += blockDim.x) {
+            cplx v = w[begin + k];
+            if (pinv) v = v * ldg_c(pinv + begin + k);
+            ws[k] = v;
+        }
     // (each thread only ever touches its own k's of ws: no barrier needed for ws itself)
     int parity = 0;
     for (int i = 0; i <= j; ++i) {
@@ -261,10 +271,11 @@ mgs_cluster_kernel(const cplx* __restrict__ V, uint64_t ldv, cplx* __restrict__ 
     const double nrm = sqrt(nn.re);
     if (me == 0 && threadIdx.x == 0) hcol[j + 1] = C(nrm, 0.0);
     if (!(nrm < breakdown_tol)) {
-        const double sc = 1.0 / nrm - 1.0;
+        const double inv = 1.0 / nrm;
+        const double sc = inv - 1.0;
         for (uint64_t k = threadIdx.x; k < len; k += blockDim.x) {
             const cplx b = ws[k];
-            vnext[begin + k] = C(b.re + b.re * sc, b.im + b.im * sc);
+            vnext[begin + k] = direct_scale ? C(b.re * inv, b.im * inv) : C(b.re + b.re * sc, b.im + b.im * sc);
         }
     }
     cluster.sync();
@@ -273,7 +284,7 @@ mgs_cluster_kernel(const cplx* __restrict__ V, uint64_t ldv, cplx* __restrict__ 
 // r = b - ax ; out[0] = sum |r|^2  (one cluster)
 __global__ void __launch_bounds__(VEC_THREADS)
 residual_cluster_kernel(const cplx* __restrict__ b, const cplx* __restrict__ ax, cplx* __restrict__ r, uint64_t n, uint64_t S,
-                        double* __restrict__ out) {
+                        double* __restrict__ out, const cplx* __restrict__ pinv) {
     __shared__ ClusterShared sh;
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned me = cluster.block_rank();
@@ -283,12 +294,246 @@ residual_cluster_kernel(const cplx* __restrict__ b, const cplx* __restrict__ ax,
     for (uint64_t k = begin + threadIdx.x; k < end; k += blockDim.x) {
         cplx v = b[k];
         if (ax) { v.re -= ax[k].re; v.im -= ax[k].im; }
+        if (pinv) v = v * pinv[k];  // r = M^-1 (b - A x)
         if (r) r[k] = v;
         acc.re = fma(v.re, v.re, fma(v.im, v.im, acc.re));
     }
     const cplx t = cluster_allreduce(acc, sh, 0);
     if (me == 0 && threadIdx.x == 0) out[0] = t.re;
     cluster.sync();
+}
+
+// ------------------------------------------------------------------------------------------
+// K6: block matvec Y = A X for S = 8*NT right-hand sides (multi-RHS scattering, BASELINE config 5).
+// A is read ONCE for all S columns, so the op is a genuine dense contraction (8 N^2 S flops on
+// 16 N^2 bytes): FP64 tensor cores, mma.sync.m8n8k4.f64 (tcgen05 has no f64 kind).  Complex
+// product = 4 real MMAs per (k-step, n-tile).  X is [ncols][S] (RHS-interleaved), Y is [nrows][S].
+// Block = 8 warps x 8 rows; the A fragment layout (lane -> row lane/4, k lane%4) is loaded
+// straight from global (each 128-byte line is consumed by two consecutive k-steps), the X chunk
+// of 32 k's is staged in shared memory with cp.async, double buffered.
+// ------------------------------------------------------------------------------------------
+constexpr int BM_WARPS = 8;
+constexpr int BM_ROWS = BM_WARPS * 8;
+constexpr int BM_KC = 32;
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+template <int NT>
+__global__ void __launch_bounds__(BM_WARPS * 32)
+zgemm_block_kernel(const cplx* __restrict__ A, uint64_t lda, uint64_t nrows, uint64_t ncols, const cplx* __restrict__ X,
+                   cplx* __restrict__ Y) {
+    constexpr int S = 8 * NT;
+    constexpr int XLD = S + 1;  // padded row stride (in complex) against bank conflicts
+    __shared__ __align__(16) cplx Xs[2][BM_KC * XLD];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, kq = lane & 3;
+    const uint64_t r_out = (uint64_t)blockIdx.x * BM_ROWS + warp * 8 + g;
+    const uint64_t r = r_out < nrows ? r_out : nrows - 1;
+    const cplx* arow = A + r * lda;
+    const uint64_t nchunks = (ncols + BM_KC - 1) / BM_KC;
+
+    double acc_re[NT][2], acc_im[NT][2];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) { acc_re[t][0] = acc_re[t][1] = acc_im[t][0] = acc_im[t][1] = 0.0; }
+
+    auto load_a = [&](uint64_t c, double2* dst) {
+#pragma unroll
+        for (int i = 0; i < BM_KC / 4; ++i) {
+            const uint64_t col = c * BM_KC + 4 * i + kq;
+            dst[i] = col < ncols ? __ldg(reinterpret_cast<const double2*>(arow + col)) : make_double2(0.0, 0.0);
+        }
+    };
+    auto stage_x = [&](uint64_t c, int buf) {
+        // BM_KC x S complex values, coalesced 16-byte cp.async
+        for (int e = tid; e < BM_KC * S; e += BM_WARPS * 32) {
+            const int kk = e / S, n = e - kk * S;
+            const uint64_t k = c * BM_KC + kk;
+            cplx* dst = &Xs[buf][kk * XLD + n];
+            if (k < ncols) {
+                const uint32_t sa = (uint32_t)__cvta_generic_to_shared(dst);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(X + k * S + n) : "memory");
+            } else {
+                *dst = C(0, 0);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    double2 a_cur[BM_KC / 4], a_nxt[BM_KC / 4];
+    load_a(0, a_cur);
+    stage_x(0, 0);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    for (uint64_t c = 0; c < nchunks; ++c) {
+        const int buf = (int)(c & 1);
+        if (c + 1 < nchunks) {
+            load_a(c + 1, a_nxt);
+            stage_x(c + 1, buf ^ 1);
+        }
+#pragma unroll
+        for (int i = 0; i < BM_KC / 4; ++i) {
+            const double are = a_cur[i].x, aim = a_cur[i].y, naim = -aim;
+            const cplx* xb = &Xs[buf][(4 * i + kq) * XLD + g];
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                const cplx b = xb[t * 8];
+                dmma884(acc_re[t][0], acc_re[t][1], are, b.re);
+                dmma884(acc_re[t][0], acc_re[t][1], naim, b.im);
+                dmma884(acc_im[t][0], acc_im[t][1], are, b.im);
+                dmma884(acc_im[t][0], acc_im[t][1], aim, b.re);
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < BM_KC / 4; ++i) a_cur[i] = a_nxt[i];
+    }
+    if (r_out < nrows) {
+        cplx* yrow = Y + r_out * S;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            // D fragment: row g, columns 2*kq, 2*kq+1 of n-tile t
+            double4 v = make_double4(acc_re[t][0], acc_im[t][0], acc_re[t][1], acc_im[t][1]);
+            *reinterpret_cast<double4*>(yrow + t * 8 + 2 * kq) = v;
+        }
+    }
+}
+
+// ---- batched (one cluster per right-hand side) MGS step; same algebra as
+// mgs_cluster_reg_kernel.  RHS index = blockIdx.y.  w is read from the block-matvec output
+// Yblk[k][S]; v_{j+1} is written both to the RHS's own contiguous Krylov basis and to the
+// interleaved block Xblk[k][S] that feeds the next block matvec.
+template <int EPT>
+__global__ void __launch_bounds__(256)
+mgs_batched_kernel(const cplx* __restrict__ Vall, uint64_t ldv, uint64_t vstride, const cplx* __restrict__ Yblk, int S_rhs,
+                   int j, uint64_t n, uint64_t S, cplx* __restrict__ hcol_all, uint64_t hstride, cplx* __restrict__ Xblk,
+                   double breakdown_tol, const unsigned char* __restrict__ active) {
+    __shared__ ClusterShared sh;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned me = cluster.block_rank();
+    const int rhs = blockIdx.y;
+    if (active && !active[rhs]) return;  // whole cluster leaves together: no barrier is left waiting
+    const cplx* V = Vall + (uint64_t)rhs * vstride;
+    cplx* hcol = hcol_all + (uint64_t)rhs * hstride;
+    const uint64_t begin = (uint64_t)me * S;
+    const uint64_t end = begin + S < n ? begin + S : n;
+    const uint64_t len = end > begin ? end - begin : 0;
+    cplx wr[EPT], vc[EPT], vn[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+        const uint64_t k = threadIdx.x + (uint64_t)e * blockDim.x;
+        wr[e] = k < len ? ldg_c(Yblk + (begin + k) * S_rhs + rhs) : C(0, 0);
+        vc[e] = k < len ? ldg_c(V + begin + k) : C(0, 0);
+    }
+    int parity = 0;
+    for (int i = 0; i <= j; ++i) {
+        if (i < j) {
+            const cplx* vi1 = V + (uint64_t)(i + 1) * ldv + begin;
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+                const uint64_t k = threadIdx.x + (uint64_t)e * blockDim.x;
+                vn[e] = k < len ? ldg_c(vi1 + k) : C(0, 0);
+            }
+        }
+        cplx acc = C(0, 0);
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            acc.re = fma(vc[e].re, wr[e].re, fma(vc[e].im, wr[e].im, acc.re));
+            acc.im = fma(vc[e].re, wr[e].im, fma(-vc[e].im, wr[e].re, acc.im));
+        }
+        const cplx h = cluster_allreduce(acc, sh, parity);
+        parity ^= 1;
+        if (me == 0 && threadIdx.x == 0) hcol[i] = h;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            wr[e].re = fma(-h.re, vc[e].re, fma(h.im, vc[e].im, wr[e].re));
+            wr[e].im = fma(-h.re, vc[e].im, fma(-h.im, vc[e].re, wr[e].im));
+            vc[e] = vn[e];
+        }
+    }
+    cplx acc = C(0, 0);
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) acc.re = fma(wr[e].re, wr[e].re, fma(wr[e].im, wr[e].im, acc.re));
+    const cplx nn = cluster_allreduce(acc, sh, parity);
+    const double nrm = sqrt(nn.re);
+    if (me == 0 && threadIdx.x == 0) hcol[j + 1] = C(nrm, 0.0);
+    if (!(nrm < breakdown_tol)) {
+        const double sc = 1.0 / nrm - 1.0;
+        cplx* vnext = const_cast<cplx*>(V) + (uint64_t)(j + 1) * ldv;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            const uint64_t k = threadIdx.x + (uint64_t)e * blockDim.x;
+            if (k < len) {
+                const cplx v = C(wr[e].re + wr[e].re * sc, wr[e].im + wr[e].im * sc);
+                vnext[begin + k] = v;
+                Xblk[(begin + k) * S_rhs + rhs] = v;
+            }
+        }
+    }
+    cluster.sync();
+}
+
+// per-RHS residual of a block: R[:, s] = B[:, s] - AX[:, s] (interleaved [n][S]); out[s] = sum |R[:, s]|^2.
+// One block per RHS (deterministic block reduction).
+__global__ void __launch_bounds__(1024)
+block_residual_kernel(const cplx* __restrict__ B, const cplx* __restrict__ AX, cplx* __restrict__ R, uint64_t n, int S_rhs,
+                      double* __restrict__ out) {
+    __shared__ double red[32];
+    const int rhs = blockIdx.x;
+    double acc = 0.0;
+    for (uint64_t k = threadIdx.x; k < n; k += blockDim.x) {
+        cplx v = B[k * S_rhs + rhs];
+        if (AX) { v.re -= AX[k * S_rhs + rhs].re; v.im -= AX[k * S_rhs + rhs].im; }
+        if (R) R[k * S_rhs + rhs] = v;
+        acc = fma(v.re, v.re, fma(v.im, v.im, acc));
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+        out[rhs] = t;
+    }
+}
+
+// v0[:, s] = R[:, s] * scale[s]: written to the RHS's contiguous basis slot 0 and to the interleaved block
+__global__ void block_scale_kernel(const cplx* __restrict__ R, const double* __restrict__ scale, cplx* __restrict__ Vall,
+                                   uint64_t vstride, cplx* __restrict__ Xblk, uint64_t n, int S_rhs) {
+    const uint64_t total = n * (uint64_t)S_rhs;
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = e / S_rhs;
+        const int s = (int)(e - k * S_rhs);
+        const double sc = scale[s];
+        const cplx v = C(R[e].re * sc, R[e].im * sc);
+        Xblk[e] = v;
+        Vall[(uint64_t)s * vstride + k] = v;
+    }
+}
+
+// X[:, s] += sum_i y[s][i] V_s[i]  for the right-hand sides with cnt[s] > 0 (interleaved X)
+__global__ void block_update_x_kernel(cplx* __restrict__ Xsol, const cplx* __restrict__ Vall, uint64_t ldv, uint64_t vstride,
+                                      const cplx* __restrict__ ycoef, int ldy, const int* __restrict__ cnt, uint64_t n, int S_rhs) {
+    const uint64_t total = n * (uint64_t)S_rhs;
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = e / S_rhs;
+        const int s = (int)(e - k * S_rhs);
+        const int c = cnt[s];
+        if (c <= 0) continue;
+        cplx v = Xsol[e];
+        const cplx* V = Vall + (uint64_t)s * vstride;
+        for (int i = 0; i < c; ++i) {
+            const cplx a = ycoef[s * ldy + i], b = V[(uint64_t)i * ldv + k];
+            v.re += a.re * b.re - a.im * b.im;
+            v.im += a.re * b.im + a.im * b.re;
+        }
+        Xsol[e] = v;
+    }
 }
 
 __global__ void scale_kernel(const cplx* __restrict__ r, double s, cplx* __restrict__ v, uint64_t n) {
@@ -424,29 +669,30 @@ static int g_cluster_level = 0;
 
 template <int EPT>
 static cudaError_t launch_mgs_reg(int cl, const cplx* V, uint64_t ldv, const cplx* w, int j, uint64_t n, uint64_t S, cplx* hcol,
-                                  cplx* vnext, cudaStream_t s) {
+                                  cplx* vnext, const cplx* pinv, int direct_scale, cudaStream_t s) {
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(mgs_cluster_reg_kernel<EPT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    return launch_cluster(mgs_cluster_reg_kernel<EPT>, cl, 256, 0, s, V, ldv, w, j, n, S, hcol, vnext, 1e-14);
+    return launch_cluster(mgs_cluster_reg_kernel<EPT>, cl, 256, 0, s, V, ldv, w, j, n, S, hcol, vnext, 1e-14, pinv, direct_scale);
 }
 
 static int g_mgs_mode = 0;  // 0: register kernel on a 16-CTA cluster when the slice fits, 1: generic kernel only
 
-cudaError_t launch_mgs(const cplx* V, uint64_t ldv, cplx* w, int j, uint64_t n, cplx* hcol, cplx* vnext, cudaStream_t s) {
+cudaError_t launch_mgs(const cplx* V, uint64_t ldv, cplx* w, int j, uint64_t n, cplx* hcol, cplx* vnext, const cplx* pinv,
+                       int direct_scale, cudaStream_t s) {
     if (g_mgs_mode == 0 && n <= 16ull * 256ull * 8ull) {
         // register-resident w: 16 CTAs (non-portable cluster size) x 256 threads x <= 8 elements
         const int cl = n >= 2048 ? 16 : (n >= 512 ? 4 : 1);
         const uint64_t S = (n + cl - 1) / cl;
         const uint64_t ept = (S + 255) / 256;
         cudaError_t e;
-        if (ept <= 1) e = launch_mgs_reg<1>(cl, V, ldv, w, j, n, S, hcol, vnext, s);
-        else if (ept <= 2) e = launch_mgs_reg<2>(cl, V, ldv, w, j, n, S, hcol, vnext, s);
-        else if (ept <= 4) e = launch_mgs_reg<4>(cl, V, ldv, w, j, n, S, hcol, vnext, s);
-        else e = launch_mgs_reg<8>(cl, V, ldv, w, j, n, S, hcol, vnext, s);
+        if (ept <= 1) e = launch_mgs_reg<1>(cl, V, ldv, w, j, n, S, hcol, vnext, pinv, direct_scale, s);
+        else if (ept <= 2) e = launch_mgs_reg<2>(cl, V, ldv, w, j, n, S, hcol, vnext, pinv, direct_scale, s);
+        else if (ept <= 4) e = launch_mgs_reg<4>(cl, V, ldv, w, j, n, S, hcol, vnext, pinv, direct_scale, s);
+        else e = launch_mgs_reg<8>(cl, V, ldv, w, j, n, S, hcol, vnext, pinv, direct_scale, s);
         if (e == cudaSuccess) return e;
         cudaGetLastError();  // a 16-CTA cluster this device cannot place: fall back for good
         g_mgs_mode = 1;
@@ -465,19 +711,104 @@ cudaError_t launch_mgs(const cplx* V, uint64_t ldv, cplx* w, int j, uint64_t n, 
         uint64_t S;
         int cl = pick_cluster(n, g_cluster_level, &in_smem, &smem, &S);
         cudaError_t e = launch_cluster(mgs_cluster_kernel, cl, VEC_THREADS, smem, s, V, ldv, w, j, n, S, (int)in_smem, hcol,
-                                       vnext, 1e-14);
+                                       vnext, 1e-14, pinv, direct_scale);
         if (e == cudaSuccess || g_cluster_level == 1) return e;
         cudaGetLastError();  // e.g. a 16-CTA / 200 KB cluster that this GPC layout cannot place
         g_cluster_level = 1;
     }
 }
 
-cudaError_t launch_residual(const cplx* b, const cplx* ax, cplx* r, uint64_t n, double* out, cudaStream_t s) {
+cudaError_t launch_residual(const cplx* b, const cplx* ax, cplx* r, uint64_t n, double* out, const cplx* pinv, cudaStream_t s) {
     bool in_smem;
     size_t smem;
     uint64_t S;
     int cl = pick_cluster(n, 1, &in_smem, &smem, &S);  // no shared-memory slice needed: 8 CTAs always place
-    return launch_cluster(residual_cluster_kernel, cl, VEC_THREADS, 0, s, b, ax, r, n, S, out);
+    return launch_cluster(residual_cluster_kernel, cl, VEC_THREADS, 0, s, b, ax, r, n, S, out, pinv);
+}
+
+cudaError_t launch_zgemm_block(const cplx* A, uint64_t lda, uint64_t nrows, uint64_t ncols, const cplx* X, cplx* Y, int nrhs,
+                               cudaStream_t s) {
+    if (nrows == 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)((nrows + BM_ROWS - 1) / BM_ROWS);
+    switch (nrhs) {
+        case 8: zgemm_block_kernel<1><<<blocks, BM_WARPS * 32, 0, s>>>(A, lda, nrows, ncols, X, Y); break;
+        case 16: zgemm_block_kernel<2><<<blocks, BM_WARPS * 32, 0, s>>>(A, lda, nrows, ncols, X, Y); break;
+        case 24: zgemm_block_kernel<3><<<blocks, BM_WARPS * 32, 0, s>>>(A, lda, nrows, ncols, X, Y); break;
+        case 32: zgemm_block_kernel<4><<<blocks, BM_WARPS * 32, 0, s>>>(A, lda, nrows, ncols, X, Y); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+template <int EPT>
+static cudaError_t launch_mgs_batched_t(int cl, int nrhs, const cplx* Vall, uint64_t ldv, uint64_t vstride, const cplx* Yblk,
+                                        int j, uint64_t n, uint64_t S, cplx* hcol_all, uint64_t hstride, cplx* Xblk,
+                                        const unsigned char* active, cudaStream_t s) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(mgs_batched_kernel<EPT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cl, nrhs, 1);
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, mgs_batched_kernel<EPT>, Vall, ldv, vstride, Yblk, nrhs, j, n, S, hcol_all, hstride, Xblk,
+                              1e-14, active);
+}
+
+cudaError_t launch_mgs_batched(int nrhs, const cplx* Vall, uint64_t ldv, uint64_t vstride, const cplx* Yblk, int j, uint64_t n,
+                               cplx* hcol_all, uint64_t hstride, cplx* Xblk, const unsigned char* active, cudaStream_t s) {
+    if (n > 16ull * 256ull * 8ull) return cudaErrorInvalidValue;  // register-resident variant only (n <= 32768)
+    const int cl = n >= 2048 ? 16 : (n >= 512 ? 4 : 1);
+    const uint64_t S = (n + cl - 1) / cl;
+    const uint64_t ept = (S + 255) / 256;
+    if (ept <= 1) return launch_mgs_batched_t<1>(cl, nrhs, Vall, ldv, vstride, Yblk, j, n, S, hcol_all, hstride, Xblk, active, s);
+    if (ept <= 2) return launch_mgs_batched_t<2>(cl, nrhs, Vall, ldv, vstride, Yblk, j, n, S, hcol_all, hstride, Xblk, active, s);
+    if (ept <= 4) return launch_mgs_batched_t<4>(cl, nrhs, Vall, ldv, vstride, Yblk, j, n, S, hcol_all, hstride, Xblk, active, s);
+    return launch_mgs_batched_t<8>(cl, nrhs, Vall, ldv, vstride, Yblk, j, n, S, hcol_all, hstride, Xblk, active, s);
+}
+
+__global__ void interleave_kernel(const cplx* __restrict__ src, cplx* __restrict__ dst, uint64_t n, int nsrc, int S_rhs, int to_block) {
+    // to_block: src [nsrc][n] -> dst [n][S_rhs] (columns >= nsrc zero);  else: src [n][S_rhs] -> dst [nsrc][n]
+    const uint64_t total = n * (uint64_t)S_rhs;
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = e / S_rhs;
+        const int s2 = (int)(e - k * S_rhs);
+        if (to_block) dst[e] = s2 < nsrc ? src[(uint64_t)s2 * n + k] : C(0, 0);
+        else if (s2 < nsrc) dst[(uint64_t)s2 * n + k] = src[e];
+    }
+}
+
+cudaError_t launch_interleave(const cplx* src, cplx* dst, uint64_t n, int nsrc, int nrhs, int to_block, cudaStream_t s) {
+    interleave_kernel<<<148 * 4, 256, 0, s>>>(src, dst, n, nsrc, nrhs, to_block);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_block_residual(const cplx* B, const cplx* AX, cplx* R, uint64_t n, int nrhs, double* out, cudaStream_t s) {
+    block_residual_kernel<<<nrhs, 1024, 0, s>>>(B, AX, R, n, nrhs, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_block_scale(const cplx* R, const double* scale, cplx* Vall, uint64_t vstride, cplx* Xblk, uint64_t n, int nrhs,
+                               cudaStream_t s) {
+    block_scale_kernel<<<148 * 4, 256, 0, s>>>(R, scale, Vall, vstride, Xblk, n, nrhs);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_block_update_x(cplx* Xsol, const cplx* Vall, uint64_t ldv, uint64_t vstride, const cplx* ycoef, int ldy,
+                                  const int* cnt, uint64_t n, int nrhs, cudaStream_t s) {
+    block_update_x_kernel<<<148 * 4, 256, 0, s>>>(Xsol, Vall, ldv, vstride, ycoef, ldy, cnt, n, nrhs);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_scale(const cplx* r, double sc, cplx* v, uint64_t n, cudaStream_t s) {

@@ -5,8 +5,19 @@
 namespace bemb {
 cudaError_t launch_zgemv(const cplx* A, uint64_t lda, uint64_t nrows, uint64_t ncols, const cplx* x, cplx* y, cudaStream_t s);
 cudaError_t launch_zgemv_t(const cplx* A, uint64_t lda, uint64_t nrows, uint64_t ncols, const cplx* x, cplx* y, cudaStream_t s);
-cudaError_t launch_mgs(const cplx* V, uint64_t ldv, cplx* w, int j, uint64_t n, cplx* hcol, cplx* vnext, cudaStream_t s);
-cudaError_t launch_residual(const cplx* b, const cplx* ax, cplx* r, uint64_t n, double* out, cudaStream_t s);
+cudaError_t launch_mgs(const cplx* V, uint64_t ldv, cplx* w, int j, uint64_t n, cplx* hcol, cplx* vnext, const cplx* pinv,
+                       int direct_scale, cudaStream_t s);
+cudaError_t launch_residual(const cplx* b, const cplx* ax, cplx* r, uint64_t n, double* out, const cplx* pinv, cudaStream_t s);
+cudaError_t launch_zgemm_block(const cplx* A, uint64_t lda, uint64_t nrows, uint64_t ncols, const cplx* X, cplx* Y, int nrhs,
+                               cudaStream_t s);
+cudaError_t launch_mgs_batched(int nrhs, const cplx* Vall, uint64_t ldv, uint64_t vstride, const cplx* Yblk, int j, uint64_t n,
+                               cplx* hcol_all, uint64_t hstride, cplx* Xblk, const unsigned char* active, cudaStream_t s);
+cudaError_t launch_block_residual(const cplx* B, const cplx* AX, cplx* R, uint64_t n, int nrhs, double* out, cudaStream_t s);
+cudaError_t launch_block_scale(const cplx* R, const double* scale, cplx* Vall, uint64_t vstride, cplx* Xblk, uint64_t n, int nrhs,
+                               cudaStream_t s);
+cudaError_t launch_block_update_x(cplx* Xsol, const cplx* Vall, uint64_t ldv, uint64_t vstride, const cplx* ycoef, int ldy,
+                                  const int* cnt, uint64_t n, int nrhs, cudaStream_t s);
+cudaError_t launch_interleave(const cplx* src, cplx* dst, uint64_t n, int nsrc, int nrhs, int to_block, cudaStream_t s);
 cudaError_t launch_scale(const cplx* r, double sc, cplx* v, uint64_t n, cudaStream_t s);
 cudaError_t launch_update_x(cplx* x, const cplx* V, uint64_t ldv, const cplx* ycoef, int cnt, uint64_t n, cudaStream_t s);
 cudaError_t launch_row_sum(cplx* A, uint64_t lda, uint64_t nloc, uint64_t ncols, uint64_t r0, cplx* rowsums, cudaStream_t s);

@@ -939,11 +939,116 @@ void orc_gmres_op(orc_apply_fn apply, void* user, uint64_t n, const double* b_in
     *info = {total_iterations, restarts, rel, 0};
 }
 
+// gmres_preconditioned_with_guess(): gmres.rs:434-585 (left preconditioning).  The preconditioner
+// is IdentityPreconditioner (inv_diag == NULL, traits.rs:377-385: r.clone()) or
+// DiagonalPreconditioner (preconditioners/diagonal.rs:60-80: r_i * inv_diag_i).
+static void precond_apply(const double* inv_diag, const cplx* r, cplx* out, uint64_t n) {
+    const cplx* d = (const cplx*)inv_diag;
+    for (uint64_t i = 0; i < n; ++i) out[i] = d ? r[i] * d[i] : r[i];
+}
+void orc_gmres_preconditioned_op(orc_apply_fn apply, void* user, uint64_t n, const double* inv_diag, const double* b_in,
+                                 const double* x0_in, uint32_t max_iterations, uint32_t restart, double tolerance,
+                                 double* x_out, orc_gmres_info* info) {
+    const cplx* b = (const cplx*)b_in;
+    cplx* x = (cplx*)x_out;
+    const int m = (int)restart;
+    if (x0_in) std::memcpy(x, x0_in, sizeof(cplx) * n);
+    else for (uint64_t i = 0; i < n; ++i) x[i] = C(0, 0);
+    std::vector<cplx> pb(n), ax(n), residual(n), r(n), av(n), w(n);
+    precond_apply(inv_diag, b, pb.data(), n);
+    double b_norm = vector_norm(pb.data(), n);
+    if (b_norm < 1e-15) { *info = {0, 0, 0.0, 1}; return; }
+    uint64_t total_iterations = 0, restarts = 0;
+    std::vector<std::vector<cplx>> v;
+    const int ldh = m;
+    for (uint32_t outer = 0; outer < max_iterations; ++outer) {
+        apply(user, (const double*)x, (double*)ax.data());
+        for (uint64_t i = 0; i < n; ++i) residual[i] = b[i] - ax[i];
+        precond_apply(inv_diag, residual.data(), r.data(), n);
+        double beta = vector_norm(r.data(), n);
+        double rel = beta / b_norm;
+        if (rel < tolerance) { *info = {total_iterations, restarts, rel, 1}; return; }
+        v.clear();
+        v.emplace_back(n);
+        {
+            cplx sc = C(1.0 / beta, 0.0);
+            for (uint64_t i = 0; i < n; ++i) v[0][i] = r[i] * sc;
+        }
+        std::vector<cplx> h((size_t)(m + 1) * m, C(0, 0));
+        std::vector<cplx> cs, sn;
+        std::vector<cplx> g(m + 1, C(0, 0));
+        g[0] = C(beta, 0.0);
+        bool inner_converged = false;
+        for (int j = 0; j < m; ++j) {
+            total_iterations += 1;
+            apply(user, (const double*)v[j].data(), (double*)av.data());
+            precond_apply(inv_diag, av.data(), w.data(), n);
+            for (int i = 0; i <= j; ++i) {
+                h[i * ldh + j] = inner_product(v[i].data(), w.data(), n);
+                cplx hij = h[i * ldh + j];
+                for (uint64_t k = 0; k < n; ++k) w[k] = w[k] - v[i][k] * hij;  // w = &w - &v[i].mapv(|vi| vi * h_ij)
+            }
+            double w_norm = vector_norm(w.data(), n);
+            h[(j + 1) * ldh + j] = C(w_norm, 0.0);
+            if (w_norm < 1e-14) {
+                inner_converged = true;
+            } else {
+                cplx inv = C(1.0 / w_norm, 0.0);
+                std::vector<cplx> nv(n);
+                for (uint64_t k = 0; k < n; ++k) nv[k] = w[k] * inv;  // w.mapv(|wi| wi * (1/w_norm))
+                v.push_back(std::move(nv));
+            }
+            for (int i = 0; i < j; ++i) {
+                cplx temp = conj(cs[i]) * h[i * ldh + j] + conj(sn[i]) * h[(i + 1) * ldh + j];
+                h[(i + 1) * ldh + j] = C(0, 0) - sn[i] * h[i * ldh + j] + cs[i] * h[(i + 1) * ldh + j];
+                h[i * ldh + j] = temp;
+            }
+            cplx c, s;
+            givens_rotation(h[j * ldh + j], h[(j + 1) * ldh + j], &c, &s);
+            cs.push_back(c); sn.push_back(s);
+            h[j * ldh + j] = conj(c) * h[j * ldh + j] + conj(s) * h[(j + 1) * ldh + j];
+            h[(j + 1) * ldh + j] = C(0, 0);
+            cplx temp = conj(c) * g[j] + conj(s) * g[j + 1];
+            g[j + 1] = C(0, 0) - s * g[j] + c * g[j + 1];
+            g[j] = temp;
+            double rel_res = tnorm(g[j + 1]) / b_norm;
+            if (rel_res < tolerance || inner_converged) {
+                std::vector<cplx> y;
+                solve_upper_triangular(h, ldh, g, j + 1, y);
+                for (int i = 0; i < (int)y.size(); ++i)
+                    for (uint64_t k = 0; k < n; ++k) x[k] = x[k] + v[i][k] * y[i];
+                *info = {total_iterations, restarts, rel_res, 1};
+                return;
+            }
+        }
+        std::vector<cplx> y;
+        solve_upper_triangular(h, ldh, g, m, y);
+        for (int i = 0; i < (int)y.size(); ++i)
+            for (uint64_t k = 0; k < n; ++k) x[k] = x[k] + v[i][k] * y[i];
+        restarts += 1;
+    }
+    apply(user, (const double*)x, (double*)ax.data());
+    for (uint64_t i = 0; i < n; ++i) residual[i] = b[i] - ax[i];
+    precond_apply(inv_diag, residual.data(), r.data(), n);
+    double rel = vector_norm(r.data(), n) / b_norm;
+    *info = {total_iterations, restarts, rel, 0};
+}
+void orc_gmres_preconditioned(const double* A, uint64_t n, const double* inv_diag, const double* b, const double* x0,
+                              uint32_t max_iterations, uint32_t restart, double tolerance, double* x_out,
+                              orc_gmres_info* info, int nthreads);
+
 // gmres on a dense n x n row-major matrix (DenseOperator, fmm_interface.rs:25-52)
 void orc_gmres(const double* A, uint64_t n, const double* b, const double* x0, uint32_t max_iterations,
                uint32_t restart, double tolerance, double* x_out, orc_gmres_info* info, int nthreads) {
     DenseCtx ctx{A, n, nthreads};
     orc_gmres_op(dense_apply, &ctx, n, b, x0, max_iterations, restart, tolerance, x_out, info);
+}
+
+void orc_gmres_preconditioned(const double* A, uint64_t n, const double* inv_diag, const double* b, const double* x0,
+                              uint32_t max_iterations, uint32_t restart, double tolerance, double* x_out,
+                              orc_gmres_info* info, int nthreads) {
+    DenseCtx ctx{A, n, nthreads};
+    orc_gmres_preconditioned_op(dense_apply, &ctx, n, inv_diag, b, x0, max_iterations, restart, tolerance, x_out, info);
 }
 
 // ---- incident field: incident.rs:93-166 (pressure), 177-280 (dp/dn), 317-342 ---

@@ -239,6 +239,33 @@ def gmres(A, b, x0=None, max_iterations=100, restart=30, tolerance=1e-6, nthread
                    converged=bool(info.converged))
 
 
+def inverse_diagonal(diag) -> np.ndarray:
+    """DiagonalPreconditioner::from_diagonal (preconditioners/diagonal.rs:40-50): 1/d, or 1 when |d| <= 1e-30."""
+    d = np.asarray(diag, dtype=np.complex128)
+    out = np.ones_like(d)
+    ok = np.sqrt(d.real ** 2 + d.imag ** 2) > 1e-30
+    ns = d.real[ok] ** 2 + d.imag[ok] ** 2
+    out[ok] = d.real[ok] / ns - 1j * (d.imag[ok] / ns)
+    return out
+
+
+def gmres_preconditioned(A, b, inv_diag=None, x0=None, max_iterations=100, restart=30, tolerance=1e-6, nthreads=0):
+    """gmres_preconditioned_with_guess (gmres.rs:434-585) with the identity (inv_diag None) or the
+    diagonal preconditioner -> (x, info dict)."""
+    A = np.ascontiguousarray(A, dtype=np.complex128)
+    b = np.ascontiguousarray(b, dtype=np.complex128)
+    n = b.shape[0]
+    x = np.zeros(n, dtype=np.complex128)
+    x0a = np.ascontiguousarray(x0, dtype=np.complex128) if x0 is not None else None
+    ida = np.ascontiguousarray(inv_diag, dtype=np.complex128) if inv_diag is not None else None
+    info = GmresInfo()
+    lib().orc_gmres_preconditioned(_p(A), C.c_uint64(n), _p(ida) if ida is not None else None, _p(b),
+                                   _p(x0a) if x0a is not None else None, C.c_uint32(max_iterations), C.c_uint32(restart),
+                                   C.c_double(tolerance), _p(x), C.byref(info), C.c_int(nthreads))
+    return x, dict(iterations=int(info.iterations), restarts=int(info.restarts), residual=float(info.residual),
+                   converged=bool(info.converged))
+
+
 def incident_rhs(kind, vec, amplitude, centers, normals, k, beta, tau=1.0):
     """compute_rhs_with_beta for one plane wave (kind=0) or point source (kind=1) -> (rhs, p_inc)."""
     centers = np.ascontiguousarray(centers, dtype=np.float64)

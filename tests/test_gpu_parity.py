@@ -308,6 +308,89 @@ def test_gmres_reference_kats(bem, orc):
     assert sol.converged and sol.iterations == 0
 
 
+def test_gmres_preconditioned(bem, orc):
+    """gmres_preconditioned (gmres.rs:282-585) with the identity and the Jacobi preconditioner on an
+    assembled BEM matrix and on the reference's tridiagonal KAT."""
+    from math_audio_b200.incident import IncidentField
+
+    a = 0.1
+    mesh = generate_icosphere_mesh(a, 3)
+    ph = PhysicsParams.from_wave_number(3.0 / a)
+    beta, _ = ph.burton_miller_beta_adaptive(a)
+    system = bem.build_tbem_system_with_beta(mesh, ph, beta)
+    A = system.matrix.rows()
+    b = system.rhs + IncidentField.plane_wave_z().compute_rhs_with_beta(mesh.center, mesh.normal, ph, beta)
+    op = bem.DenseOperator(system)
+    cfg = bem.GmresConfig(max_iterations=100, restart=20, tolerance=1e-10)
+    jac = bem.DiagonalPreconditioner.from_operator(op)
+    assert np.max(np.abs(jac.inv_diag - orc.inverse_diagonal(np.diag(A)))) < 1e-13 * np.abs(jac.inv_diag).max()
+    for pre, idg in [(bem.IdentityPreconditioner(), None), (jac, jac.inv_diag)]:
+        sol = bem.gmres_preconditioned(op, pre, b, cfg)
+        xo, io = orc.gmres_preconditioned(A, b, inv_diag=idg, max_iterations=100, restart=20, tolerance=1e-10)
+        assert sol.converged and (sol.iterations, sol.restarts) == (io["iterations"], io["restarts"])
+        assert abs(sol.residual - io["residual"]) < 1e-3 * io["residual"] + 1e-14
+        assert np.linalg.norm(sol.x - xo) / np.linalg.norm(xo) < X_TOL
+        assert np.linalg.norm(b - A @ sol.x) / np.linalg.norm(b) < 1e-8
+    # initial guess + budget exhaustion report the PRECONDITIONED true residual
+    sol = bem.gmres_preconditioned_with_guess(op, jac, b, np.ones_like(b), bem.GmresConfig(1, 4, 1e-14))
+    xo, io = orc.gmres_preconditioned(A, b, inv_diag=jac.inv_diag, x0=np.ones_like(b), max_iterations=1, restart=4, tolerance=1e-14)
+    assert not sol.converged and sol.iterations == io["iterations"] == 4
+    assert abs(sol.residual - io["residual"]) < 1e-9 * io["residual"]
+    n = 30  # test_fmm_validation.rs:587-637 matrix with Jacobi instead of ILU
+    T = tridiag(n, complex(5.0, 0.5), complex(-2.0, 0.2), complex(-2.0, -0.2))
+    for i in range(n - 3):
+        T[i, i + 3] = 0.5
+    bb = np.array([math.sin(i * 0.2) + 0.5 + 0.1j for i in range(n)], dtype=np.complex128)
+    opT = bem.DenseOperator(T)
+    sol = bem.gmres_preconditioned(opT, bem.DiagonalPreconditioner.from_operator(opT), bb, bem.GmresConfig(100, 20, 1e-8))
+    assert sol.converged and np.linalg.norm(T @ sol.x - bb) / np.linalg.norm(bb) < 1e-5
+
+
+def test_block_matvec_and_batched_gmres(bem, orc):
+    """BASELINE config 5 at test size: several incident directions, reference semantics = one
+    independent gmres() per right-hand side; the device runs them in lockstep on the FP64
+    tensor-core block matvec."""
+    from math_audio_b200.incident import IncidentField
+    from math_audio_b200.mesh import fibonacci_directions
+
+    rng = np.random.default_rng(11)
+    for shape, nrhs in [((300, 257), 5), ((1024, 1024), 32), ((77, 1000), 16)]:
+        A = rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+        X = rng.standard_normal((nrhs, shape[1])) + 1j * rng.standard_normal((nrhs, shape[1]))
+        Y, ms = bem.apply_block(bem.DenseOperator(A), X)
+        ref = X @ A.T
+        assert np.linalg.norm(Y - ref) < 1e-13 * np.linalg.norm(ref) and ms > 0
+    a = 0.1
+    mesh = generate_icosphere_mesh(a, 3)
+    ph = PhysicsParams.from_wave_number(2.0 / a)
+    beta, _ = ph.burton_miller_beta_adaptive(a)
+    system = bem.build_tbem_system_with_beta(mesh, ph, beta)
+    A = system.matrix.rows()
+    op = bem.DenseOperator(system)
+    cfg = bem.GmresConfig(max_iterations=1000, restart=20, tolerance=1e-10)
+    for nrhs in (11, 32):
+        dirs = fibonacci_directions(nrhs)
+        B = np.stack([system.rhs + IncidentField.plane_wave(d).compute_rhs_with_beta(mesh.center, mesh.normal, ph, beta) for d in dirs])
+        if nrhs == 11:
+            B[3] = 0.0  # a zero right-hand side returns at once (gmres.rs:125-135)
+        sols, st = bem.gmres_batched(op, B, cfg)
+        assert st["block_matvecs"] > 0 and len(sols) == nrhs
+        for i, sol in enumerate(sols):
+            xo, io = orc.gmres(A, B[i], max_iterations=1000, restart=20, tolerance=1e-10)
+            assert sol.converged == io["converged"]
+            assert (sol.iterations, sol.restarts) == (io["iterations"], io["restarts"]), (i, sol.iterations, io)
+            if np.abs(B[i]).max() == 0:
+                assert sol.iterations == 0 and (sol.x == 0).all()
+                continue
+            assert np.linalg.norm(sol.x - xo) / np.linalg.norm(xo) < X_TOL
+            assert np.linalg.norm(B[i] - A @ sol.x) / np.linalg.norm(B[i]) < 2e-10
+    # budget exhaustion: converged = false, true residual (per right-hand side)
+    sols, _ = bem.gmres_batched(op, B[:8], bem.GmresConfig(max_iterations=1, restart=5, tolerance=1e-14))
+    for i, sol in enumerate(sols):
+        assert (not sol.converged) and sol.iterations == 5 and sol.restarts == 1
+        assert abs(sol.residual - np.linalg.norm(B[i] - A @ sol.x) / np.linalg.norm(B[i])) < 1e-10
+
+
 # ---- full benchmark size: size-independent properties ---------------------------------------------
 @pytest.fixture(scope="module")
 def big(bem):

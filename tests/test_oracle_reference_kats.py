@@ -257,6 +257,22 @@ def test_gmres_not_converged_reports_true_residual(orc):
     assert abs(info["residual"] - np.linalg.norm(b - A @ x) / np.linalg.norm(b)) < 1e-12
 
 
+def test_gmres_preconditioned_identity_equals_plain(orc):
+    # left preconditioning with M = I is the same Krylov process (gmres.rs:282-428 vs :105-277)
+    n = 50
+    A = tridiag(n, 4.0, complex(-1.0, 0.3), -1.0)
+    b = np.arange(1, n + 1, dtype=np.complex128)
+    x0, i0 = orc.gmres(A, b, max_iterations=100, restart=7, tolerance=1e-10)
+    x1, i1 = orc.gmres_preconditioned(A, b, inv_diag=None, max_iterations=100, restart=7, tolerance=1e-10)
+    assert (i0["iterations"], i0["restarts"]) == (i1["iterations"], i1["restarts"])
+    assert np.linalg.norm(x0 - x1) / np.linalg.norm(x0) < 1e-12
+    # Jacobi: residual is measured in the preconditioned norm
+    idg = orc.inverse_diagonal(np.diag(A))
+    x2, i2 = orc.gmres_preconditioned(A, b, inv_diag=idg, max_iterations=100, restart=7, tolerance=1e-10)
+    assert i2["converged"] and np.linalg.norm(A @ x2 - b) / np.linalg.norm(b) < 1e-8
+    assert orc.inverse_diagonal(np.array([0.0, 2.0, 1e-31]))[0] == 1.0  # |d| <= 1e-30 -> 1 (diagonal.rs:29-35)
+
+
 # ---- math-wave/src/analytical/solutions_3d.rs:385-525 -----------------------------
 def test_spherical_bessel_and_legendre(orc):
     assert abs(orc.spherical_bessel_j(0, 1.0) - math.sin(1.0)) < 1e-10
