@@ -260,12 +260,19 @@ def run_native(args):
     nccl_id = None
     if world > 1:
         nccl_id = bdist.broadcast_bytes(bem.Context.nccl_unique_id() if rank == 0 else None, 128, 0, device=dev)
-    stream = torch.cuda.Stream(device=dev)
-    ctx = bem.Context(local_rank, rank, world, nccl_id, cuda_stream=stream.cuda_stream)
+    from math_audio_b200.sweep import SweepDriver
 
+    # two streams: the solve (HBM-bound ZGEMV + Arnoldi) gets the higher priority, the assembly of
+    # the NEXT frequency (FP64-bound) runs underneath it on the second stream
+    s_solve = torch.cuda.Stream(device=dev, priority=-1)
+    s_asm = torch.cuda.Stream(device=dev, priority=0)
     wl = workload(args.workload)
     mesh = wl["mesh"]
     n = mesh.num_dofs
+    overlap = not args.no_overlap
+    driver = SweepDriver(mesh, local_rank, rank, world, nccl_id, solve_stream=s_solve.cuda_stream,
+                         assembly_stream=s_asm.cuda_stream, overlap=overlap, background_blocks_per_sm=args.background)
+    ctx = driver.ctx_solve
     nsteps = args.warmup + args.steps
     inc = IncidentField.plane_wave_z()
     cfg = bem.GmresConfig(max_iterations=GMRES_MAX_CYCLES, restart=GMRES_RESTART, tolerance=GMRES_TOL)
@@ -273,95 +280,95 @@ def run_native(args):
     nloc = r1 - r0
 
     # ---- device-resident inputs ------------------------------------------------------------
-    staged = bem.StagedMesh(mesh, ctx)
-    b_host, b_dev = [], []
+    b_host, b_dev, cases = [], [], []
     for s in range(nsteps):
         ka, ph, beta = physics_for(wl, s)
         b = inc.compute_rhs_with_beta(mesh.center, mesh.normal, ph, beta)  # rigid: TbemSystem.rhs == 0
         b_host.append(b)
         b_dev.append(torch.from_numpy(b).to(dev))
+        cases.append((ph, beta))
     x_dev = torch.zeros(n, dtype=torch.complex128, device=dev)
     torch.cuda.synchronize(dev)
+    dbg = os.environ.get("BENCH_DEBUG")
 
-    state = {"system": None, "op": None}
-    stats = []
-
-    def step_device(s, record):
-        ka, ph, beta = physics_for(wl, s)
-        state["system"] = bem.build_tbem_system_with_beta(staged, ph, beta, reuse=state["system"], fetch_rhs=False)
-        if state["op"] is None:
-            state["op"] = bem.DenseOperator(state["system"])
-        tq = time.perf_counter()
-        sol = bem.gmres_device(state["op"], b_dev[s].data_ptr(), x_dev.data_ptr(), cfg)
-        if os.environ.get("BENCH_DEBUG"):
-            import ctypes
-            from math_audio_b200 import _capi
-            la, wa = ctypes.c_double(), ctypes.c_double()
-            _capi.lib().bemb200_debug_times(ctypes.byref(la), ctypes.byref(wa))
-            ss = state["system"].matrix.solver_stats()
-            print(f"[value rank {rank}] step {s}: gmres wall {(time.perf_counter() - tq) * 1e3:.2f} ms it {sol.iterations} launch {la.value / 1e3:.2f} ms wait {wa.value / 1e3:.2f} ms matvec {ss['matvec_ms']:.2f} ms", file=sys.stderr)
-        if record:
-            a_st = state["system"].matrix.assembly_stats()
-            s_st = state["system"].matrix.solver_stats()
-            stats.append(dict(ka=ka, fi=freq_index(s, len(wl["ka"])), iterations=sol.iterations, restarts=sol.restarts,
-                              residual=sol.residual, converged=sol.converged, **{f"asm_{k}": v for k, v in a_st.items()},
-                              **{f"sol_{k}": v for k, v in s_st.items()}))
-        return sol
+    def make_solve_device(offset):
+        def solve_device(i, system, op):
+            s = offset + i
+            tq = time.perf_counter()
+            sol = bem.gmres_device(op, b_dev[s].data_ptr(), x_dev.data_ptr(), cfg)
+            if dbg:
+                print(f"[value rank {rank}] step {s}: gmres wall {(time.perf_counter() - tq) * 1e3:.2f} ms it {sol.iterations}", file=sys.stderr)
+            return dict(ka=float(wl["ka"][freq_index(s, len(wl["ka"]))]), fi=freq_index(s, len(wl["ka"])), iterations=sol.iterations,
+                        restarts=sol.restarts, residual=sol.residual, converged=sol.converged)
+        return solve_device
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for s in range(args.warmup):
-        step_device(s, False)
+    driver.run(cases[: args.warmup], cfg, make_solve_device(0))
+    driver.asm_stats.clear()
+    driver.sol_stats.clear()
     # start the clock sampler BEFORE the barrier: nvidia-smi's start-up stalls CUDA calls for
     # ~100 ms and must not leak into any rank's timed region
     sampler = ClockSampler(local_rank) if rank == 0 else None
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(stream):
-        ev0.record(stream)
-        for s in range(args.warmup, nsteps):
-            step_device(s, True)
-        ev1.record(stream)
+    ev0.record(s_asm)     # the first timed kernel is an assembly kernel on the assembly stream
+    sols = driver.run(cases[args.warmup:], cfg, make_solve_device(args.warmup))
+    ev1.record(s_solve)   # the last one is the solution update on the solve stream
     barrier()
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
     clocks = sampler.stop() if sampler else None
+    stats = []
+    for i, sd in enumerate(sols):
+        stats.append(dict(sd, **{f"asm_{k}": v for k, v in driver.asm_stats[i].items()},
+                          **{f"sol_{k}": v for k, v in driver.sol_stats[i].items()}))
 
     # ---- end-to-end through the host-buffer API -----------------------------------------------
+    # the drop-in calls a user of the reference makes, once per frequency, with HOST buffers:
+    # build_tbem_system_with_beta(host mesh) [stage H2D, rhs D2H] + gmres(host b) [b H2D, x D2H]
     e2e_steps = max(1, args.steps)
-    sys_e2e = state["system"]
     x_pinned = torch.empty(n, dtype=torch.complex128).pin_memory().numpy()
-    # one untimed warm-up pass of the host-buffer path (first-use costs of the staging copies)
+    sys_e2e = None
     _, ph_w, beta_w = physics_for(wl, 0)
-    sys_e2e = bem.build_tbem_system_with_beta(mesh, ph_w, beta_w, ctx=ctx, reuse=sys_e2e)
-    bem.gmres(bem.DenseOperator(sys_e2e), b_host[0], bem.GmresConfig(max_iterations=1, restart=2, tolerance=1e-10))
+    sys_e2e = bem.build_tbem_system_with_beta(mesh, ph_w, beta_w, ctx=ctx, reuse=sys_e2e)  # untimed warm-up of the host path
+    bem.gmres(bem.DenseOperator(sys_e2e), b_host[0], bem.GmresConfig(max_iterations=1, restart=2, tolerance=GMRES_TOL))
+    h2d = d2h = 0
     barrier()
     t0 = time.perf_counter()
-    h2d = d2h = 0
-    dbg = os.environ.get("BENCH_DEBUG")
     for s in range(args.warmup, args.warmup + e2e_steps):
-        ka, ph, beta = physics_for(wl, s)
-        ta = time.perf_counter()
-        sys_e2e = bem.build_tbem_system_with_beta(mesh, ph, beta, ctx=ctx, reuse=sys_e2e)   # stages the host mesh (H2D), rhs D2H
-        tb = time.perf_counter()
-        b = sys_e2e.rhs_full(n) + inc.compute_rhs_with_beta(mesh.center, mesh.normal, ph, beta)
-        tc = time.perf_counter()
-        sol = bem.gmres(bem.DenseOperator(sys_e2e), b, cfg)                                   # b H2D, x D2H
-        td = time.perf_counter()
+        ph, beta = cases[s]
+        sys_e2e = bem.build_tbem_system_with_beta(mesh, ph, beta, ctx=ctx, reuse=sys_e2e)
+        b = sys_e2e.rhs_full() + inc.compute_rhs_with_beta(mesh.center, mesh.normal, ph, beta)
+        sol = bem.gmres(bem.DenseOperator(sys_e2e), b, cfg)
         x_pinned[:] = sol.x
-        if dbg:
-            print(f"[e2e rank {rank}] step {s}: assemble {tb - ta:.4f} rhs {tc - tb:.4f} gmres {td - tc:.4f} it {sol.iterations}", file=sys.stderr)
-        h2d += staged.nbytes_host + b.nbytes
-        d2h += nloc * 16 + sol.x.nbytes
+        h2d += driver.staged.nbytes_host + b.nbytes
+        d2h += nloc * 16 + n * 16 + sol.x.nbytes
     barrier()
     e2e_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+
+    # ---- the ZGEMV alone (nothing else on the GPU): 20 launches through the operator boundary
+    iso_ms = None
+    try:
+        op_iso = bem.DenseOperator(sys_e2e)
+        y_dev = torch.zeros(n, dtype=torch.complex128, device=dev)
+        tot, cnt = 0.0, 0
+        for it in range(23):
+            bem.apply_device(op_iso, b_dev[0].data_ptr(), y_dev.data_ptr())
+            if it >= 3:
+                st_iso = sys_e2e.matrix.solver_stats()
+                tot += st_iso["matvec_ms"]
+                cnt += st_iso["matvecs"]
+        iso_ms = tot / max(1, cnt)
+    except Exception as e:  # diagnostics only
+        print(f"isolated zgemv measurement failed: {e}", file=sys.stderr)
 
     if rank != 0:
         if world > 1:
@@ -398,11 +405,16 @@ def run_native(args):
                    "matrix_bytes_per_gpu": int(16 * nloc * n), "gmres": f"restart {GMRES_RESTART}, tol {GMRES_TOL}, MGS",
                    "beta": "burton_miller_beta_adaptive", "parallelism": f"row-block x{world}",
                    "l2": "inputs larger than L2: the matrix slab is re-streamed from HBM by every matvec",
+                   "schedule": ("sweep pipeline: assembly of frequency f+1 on a second stream/buffer overlaps the solve of f"
+                                if overlap else "sequential: assemble then solve"),
                    "frequencies_timed": [st["fi"] for st in stats]},
         "roofline": {"kernel": "zgemv_kernel", "bound": "hbm", "achieved": mv_gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": mv_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                      "launches": int(mv_cnt), "avg_launch_ms": mv_ms / max(1, mv_cnt), "share_of_step": mv_ms / total_ms,
-                     "frac_of_nominal_8TBs": mv_gbs / 8000.0},
+                     "frac_of_nominal_8TBs": mv_gbs / 8000.0,
+                     "isolated": (None if not iso_ms else {"avg_launch_ms": iso_ms, "achieved": mv_bytes / (iso_ms * 1e-3) / 1e9,
+                                                           "frac": mv_bytes / (iso_ms * 1e-3) / 1e9 / hbm_peak,
+                                                           "note": "same kernel with nothing else running (no overlapped assembly)"})},
         "roofline_assembly": {"kernel": "far_kernel<13>", "bound": "fp64", "achieved": far_tf, "peak": fp64_nominal,
                               "unit": "TFLOP/s", "frac": far_tf / fp64_nominal, "peak_measured_dfma": fp64_meas,
                               "frac_of_measured": far_tf / fp64_meas if fp64_meas > 0 else None,
@@ -414,10 +426,12 @@ def run_native(args):
         "gpu_launches": launches,
         "clocks": clocks,
         "gmres": {"matvecs_per_step": mv_cnt / K, "iterations": [st["iterations"] for st in stats],
+                  "matvecs": [st["sol_matvecs"] for st in stats],
                   "all_converged": all(st["converged"] for st in stats),
                   "max_residual": max(st["residual"] for st in stats)},
         "breakdown_ms_per_step": {"assembly": asm_ms / K, "far_kernel": far_ms / K, "matvec": mv_ms / K,
-                                  "gmres_other": (total_ms - asm_ms - mv_ms) / K},
+                                  "wall": total_ms / K,
+                                  "note": "kernel times are per-kernel CUDA-event durations; with the sweep pipeline assembly overlaps the solve, so they do not add up to wall"},
     }
     if world == 1 and not args.no_cpu_baseline:
         hint = {st["fi"]: st["sol_matvecs"] for st in stats}
@@ -447,6 +461,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="sphere20k_sweep64")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--background", type=int, default=1, help="blocks/SM of the background assembly kernel in the sweep pipeline")
+    ap.add_argument("--no-overlap", action="store_true", help="do not overlap assembly(f+1) with solve(f)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3  # timing rule: W >= 3

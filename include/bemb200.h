@@ -88,9 +88,18 @@ int bemb200_nccl_unique_id(uint8_t out[128]);
 int bemb200_ctx_create_dist(int device, int rank, int nranks, const uint8_t nccl_id[128], bemb200_ctx** out);
 /* general form: `cuda_stream` (a cudaStream_t, may be NULL) makes the library submit all its
  * work to a stream owned by the caller, so that the caller's CUDA events bracket it;
- * nranks == 1 ignores nccl_id. */
+ * nranks == 1 ignores nccl_id; nranks > 1 with nccl_id == NULL creates a context WITHOUT a
+ * communicator (assembly only: row-block assembly needs no communication). */
 int bemb200_ctx_create_ex(int device, int rank, int nranks, const uint8_t* nccl_id, void* cuda_stream, bemb200_ctx** out);
 void bemb200_ctx_destroy(bemb200_ctx* ctx);
+/* blocks_per_sm > 0 turns the FP64 assembly kernel of this context into a "background" kernel: a
+ * persistent grid of 148*blocks_per_sm blocks that leaves registers/shared memory to kernels of
+ * other streams (assembly of frequency f+1 underneath the solve of frequency f); 0 = normal. */
+int bemb200_ctx_set_background(bemb200_ctx* ctx, int blocks_per_sm);
+/* Hand a matrix to another context of the SAME device (e.g. a solve context with its own stream
+ * while an assembly context fills the next matrix of a frequency sweep).  The caller orders the
+ * use of one matrix by the two contexts. */
+int bemb200_matrix_set_context(bemb200_matrix* m, bemb200_ctx* ctx);
 const char* bemb200_last_error(const bemb200_ctx* ctx); /* ctx may be NULL: last global error */
 /* canonical row partition used by the distributed solver: rank r owns
  * [r*ceil(n/nranks), min(n,(r+1)*ceil(n/nranks))) */

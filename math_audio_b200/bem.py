@@ -39,8 +39,8 @@ class Context:
         self._lib = _capi.lib()
         self._h = C.c_void_p()
         idp = None
-        if nranks > 1:
-            assert nccl_id is not None and len(nccl_id) == 128
+        if nranks > 1 and nccl_id is not None:  # nccl_id None: context without communicator (assembly only)
+            assert len(nccl_id) == 128
             self._idbuf = (C.c_uint8 * 128).from_buffer_copy(nccl_id)
             idp = C.cast(self._idbuf, C.c_void_p)
         _capi.check(self._lib.bemb200_ctx_create_ex(device, rank, nranks, idp, C.c_void_p(cuda_stream or None), C.byref(self._h)))
@@ -66,6 +66,9 @@ class Context:
         a, b = C.c_double(), C.c_double()
         _capi.check(self._lib.bemb200_selftest_math(self._h, n, xmax, C.byref(a), C.byref(b)), self._h)
         return float(a.value), float(b.value)
+
+    def set_background(self, blocks_per_sm: int) -> None:
+        _capi.check(self._lib.bemb200_ctx_set_background(self._h, blocks_per_sm), self._h)
 
     def measure_allgather(self, bytes_per_rank: int, iters: int = 200, sync_each: bool = False) -> float:
         t = C.c_double()
@@ -167,6 +170,11 @@ class DeviceMatrix:
 
     def device_ptr(self) -> int:
         return int(self._lib.bemb200_matrix_device_ptr(self._h) or 0)
+
+    def set_context(self, ctx: "Context") -> None:
+        """Hand the matrix to another context of the same device (frequency-sweep pipelining)."""
+        _capi.check(self._lib.bemb200_matrix_set_context(self._h, ctx._h), ctx._h)
+        self.ctx = ctx
 
     def close(self):
         if self._h:

@@ -72,6 +72,7 @@ namespace bemb {
 // all-gather `count_bytes` bytes per rank (in-stream); used by gmres.cu
 int nccl_allgather_bytes(bemb200_ctx* ctx, const void* send, void* recv, size_t count_bytes) {
     if (ctx->nranks == 1) return BEMB200_OK;
+    if (!ctx->nccl_comm) return set_error(ctx, BEMB200_ENCCL, "this context was created without a communicator (assembly only)");
     int rc = ncclshim::AllGather(send, recv, count_bytes, /*ncclInt8=*/0, ctx->nccl_comm, ctx->stream);
     if (rc != 0)
         return set_error(ctx, BEMB200_ENCCL, std::string("ncclAllGather failed: ") +
@@ -161,13 +162,12 @@ int bemb200_ctx_create_dist(int device, int rank, int nranks, const uint8_t nccl
 
 int bemb200_ctx_create_ex(int device, int rank, int nranks, const uint8_t* nccl_id, void* cuda_stream, bemb200_ctx** out) {
     if (nranks < 1 || rank < 0 || rank >= nranks) return set_error(nullptr, BEMB200_EINVAL, "bad rank/nranks");
-    if (nranks > 1 && !nccl_id) return set_error(nullptr, BEMB200_EINVAL, "nccl_id is NULL");
     int rc = ctx_create_common(device, cuda_stream, out);
     if (rc != BEMB200_OK) return rc;
     bemb200_ctx* c = *out;
     c->rank = rank;
     c->nranks = nranks;
-    if (nranks > 1) {
+    if (nranks > 1 && nccl_id) {
         std::string why;
         if (!ncclshim::load(why)) {
             bemb200_ctx_destroy(c);
@@ -431,7 +431,8 @@ int bemb200_assemble_staged(bemb200_ctx* ctx, const bemb200_staged_mesh* sm, con
     for (int attempt = 0; attempt < 2; ++attempt) {
         ASM_CUDA(cudaMemsetAsync(m->near_count, 0, sizeof(unsigned int), s));
         ASM_CUDA(cudaEventRecord(m->ev[1], s));
-        ASM_CUDA(launch_far(dm, ph, row_begin, row_end, m->A, dm.n, m->near_list, m->near_cap, m->near_count, s));
+        ASM_CUDA(launch_far(dm, ph, row_begin, row_end, m->A, dm.n, m->near_list, m->near_cap, m->near_count,
+                            ctx->background_blocks_per_sm.load(), s));
         ASM_CUDA(cudaEventRecord(m->ev[2], s));
         ASM_CUDA(cudaMemcpyAsync(&count, m->near_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
         ASM_CUDA(cudaStreamSynchronize(s));
@@ -496,6 +497,26 @@ int bemb200_matrix_from_host(bemb200_ctx* ctx, const double* a_rows, uint64_t n_
         return cuda_fail(ctx, e, "matrix upload");
     }
     *out = m;
+    return BEMB200_OK;
+}
+
+int bemb200_ctx_set_background(bemb200_ctx* ctx, int blocks_per_sm) {
+    if (!ctx || blocks_per_sm < 0 || blocks_per_sm > 8) return set_error(ctx, BEMB200_EINVAL, "blocks_per_sm must be 0..8");
+    // lock-free on purpose: may be flipped by another thread WHILE an assembly call of this context
+    // is in flight (the call re-reads it between row slabs)
+    ctx->background_blocks_per_sm.store(blocks_per_sm);
+    return BEMB200_OK;
+}
+
+int bemb200_matrix_set_context(bemb200_matrix* m, bemb200_ctx* ctx) {
+    if (!m || !ctx) return set_error(ctx, BEMB200_EINVAL, "NULL argument");
+    if (ctx->device != m->ctx->device || ctx->nranks != m->ctx->nranks || ctx->rank != m->ctx->rank)
+        return set_error(ctx, BEMB200_EINVAL, "contexts must share device, rank and nranks");
+    std::lock_guard<std::mutex> lk(m->ctx->mu);
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(m->ctx->stream);
+    free_workspace(m);  // the solver workspace is re-created lazily on the new context's stream
+    m->ctx = ctx;
     return BEMB200_OK;
 }
 

@@ -1,6 +1,7 @@
 // Handle definitions behind the opaque C types of include/bemb200.h.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -13,6 +14,7 @@ struct bemb200_ctx {
     int rank = 0, nranks = 1;
     cudaStream_t stream = nullptr;
     bool own_stream = true;
+    std::atomic<int> background_blocks_per_sm{0};  // > 0: assembly kernels use a small persistent grid (sweep pipelining)
     void* nccl_comm = nullptr;  // ncclComm_t when nranks > 1
     std::string err;
     std::mutex mu;  // LinearOperator is Send + Sync: serialise stream submission per context

@@ -54,58 +54,79 @@ template <int NQ, bool BIMAG, int MINB>
 __global__ void __launch_bounds__(TILE, MINB)
 far_kernel(const double* __restrict__ far_k, const double* __restrict__ far_c, const uint8_t* __restrict__ col_class,
            const double* __restrict__ srcdat, uint32_t n, uint64_t row_begin, uint64_t row_end, uint32_t rows_per_block,
+           uint32_t nchunks, uint32_t total_items, uint32_t items_per_block,
            double wavruim, double k2, double cH, double beta_re, double beta_im, cplx* __restrict__ A, uint64_t lda,
            uint2* __restrict__ near_list, unsigned int near_cap, unsigned int* __restrict__ near_count) {
     __shared__ __align__(128) double sm_k[NQ * TILE];  // kappa_q, [q][column]
     __shared__ __align__(8) unsigned long long mbar;
 
-    const uint32_t tile = blockIdx.x;
     const uint32_t t = threadIdx.x;
-    const uint32_t col = tile * TILE + t;
     constexpr uint32_t BYTES = NQ * TILE * sizeof(double);
     constexpr bool QUAD = (NQ == NQ_QUAD);
     const uint8_t want = QUAD ? COL_FLAT_QUAD : COL_FLAT_TRI;
     const RuleConst& rc = QUAD ? d_rule_quad : d_rule_tri;
+    const double bk = beta_im * wavruim, bk2 = beta_im * k2;
 
-    // ---- stage the tile's kappa table with one TMA bulk copy -------------------------------
     if (t == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (t == 0) {
-        const double* gsrc = far_k + (uint64_t)tile * NQ_MAX * TILE;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(BYTES) : "memory");
-        asm volatile(
-            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sm_k)),
-            "l"(gsrc), "r"(BYTES), "r"(smem_u32(&mbar))
-            : "memory");
-    }
-    // per-column frame -> registers (coalesced, overlaps the bulk copy)
-    const double* fc = far_c + (uint64_t)tile * FAR_NCONST * TILE + t;
-    const double nyx = fc[FC_NX * TILE], nyy = fc[FC_NY * TILE], nyz = fc[FC_NZ * TILE];
-    const double j4pi = fc[FC_J4PI * TILE];
-    const double y0x = fc[FC_Y0X * TILE], y0y = fc[FC_Y0Y * TILE], y0z = fc[FC_Y0Z * TILE];
-    const double thr = fc[FC_THR * TILE];
-    const double e1x = fc[FC_E1X * TILE], e1y = fc[FC_E1Y * TILE], e1z = fc[FC_E1Z * TILE];
-    const double e2x = fc[FC_E2X * TILE], e2y = fc[FC_E2Y * TILE], e2z = fc[FC_E2Z * TILE];
-    const double kc = fc[FC_KC * TILE];
-    const bool active = (col < n) && (col_class[col] == want);
-    {
-        uint32_t done = 0;
-        while (!done) {
+
+    // Work item = (column tile, row chunk); a block owns a contiguous range of items, ordered so
+    // that consecutive items share the tile (one item per block in the normal launch; a
+    // "background" launch -- assembly of the next frequency underneath a running solve -- uses a
+    // small persistent grid so that it leaves registers and shared memory to the solver's kernels).
+    const uint32_t item_first = blockIdx.x * items_per_block;
+    const uint32_t item_last = (item_first + items_per_block < total_items) ? item_first + items_per_block : total_items;
+    uint32_t cur_tile = 0xffffffffu, loads = 0;
+    double nyx = 0, nyy = 0, nyz = 0, j4pi = 0, y0x = 0, y0y = 0, y0z = 0, thr = 0, e1x = 0, e1y = 0, e1z = 0, e2x = 0, e2y = 0,
+           e2z = 0, kc = 0;
+    bool active = false;
+    uint32_t col = 0;
+    const double* kq = sm_k + t;
+
+    for (uint32_t item = item_first; item < item_last; ++item) {
+    const uint32_t tile = item / nchunks, chunk = item - tile * nchunks;
+    if (tile != cur_tile) {
+        cur_tile = tile;
+        col = tile * TILE + t;
+        __syncthreads();  // everybody is done with the previous tile's kappa table
+        // ---- stage the tile's kappa table with one TMA bulk copy ----------------------------
+        if (t == 0) {
+            const double* gsrc = far_k + (uint64_t)tile * NQ_MAX * TILE;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(BYTES) : "memory");
             asm volatile(
-                "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
-                : "=r"(done)
-                : "r"(smem_u32(&mbar)), "r"(0u)
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sm_k)),
+                "l"(gsrc), "r"(BYTES), "r"(smem_u32(&mbar))
                 : "memory");
+        }
+        // per-column frame -> registers (coalesced, overlaps the bulk copy)
+        const double* fc = far_c + (uint64_t)tile * FAR_NCONST * TILE + t;
+        nyx = fc[FC_NX * TILE]; nyy = fc[FC_NY * TILE]; nyz = fc[FC_NZ * TILE];
+        j4pi = fc[FC_J4PI * TILE];
+        y0x = fc[FC_Y0X * TILE]; y0y = fc[FC_Y0Y * TILE]; y0z = fc[FC_Y0Z * TILE];
+        thr = fc[FC_THR * TILE];
+        e1x = fc[FC_E1X * TILE]; e1y = fc[FC_E1Y * TILE]; e1z = fc[FC_E1Z * TILE];
+        e2x = fc[FC_E2X * TILE]; e2y = fc[FC_E2Y * TILE]; e2z = fc[FC_E2Z * TILE];
+        kc = fc[FC_KC * TILE];
+        active = (col < n) && (col_class[col] == want);
+        {
+            const uint32_t parity = loads & 1u;
+            uint32_t done = 0;
+            while (!done) {
+                asm volatile(
+                    "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                    : "=r"(done)
+                    : "r"(smem_u32(&mbar)), "r"(parity)
+                    : "memory");
+            }
+            ++loads;
         }
     }
 
-    const double bk = beta_im * wavruim, bk2 = beta_im * k2;
-    const uint64_t r0 = row_begin + (uint64_t)blockIdx.y * rows_per_block;
+    const uint64_t r0 = row_begin + (uint64_t)chunk * rows_per_block;
     const uint64_t r1 = (r0 + rows_per_block < row_end) ? r0 + rows_per_block : row_end;
-    const double* kq = sm_k + t;
 
     for (uint64_t row = r0; row < r1; ++row) {
         const double* sp = srcdat + 8ull * row;  // block-uniform
@@ -180,6 +201,7 @@ far_kernel(const double* __restrict__ far_k, const double* __restrict__ far_c, c
             __stcs(reinterpret_cast<double2*>(A + (row - row_begin) * lda + col), v);
         }
     }
+    }  // work items
 }
 
 bool g_tables_uploaded[64] = {false};
@@ -223,27 +245,35 @@ int env_int(const char* name, int dflt) {
 
 template <int NQ, bool BIMAG, int MINB>
 cudaError_t launch_far_v(const DeviceMesh& m, const Phys& ph, uint64_t row_begin, uint64_t row_end, cplx* A, uint64_t lda,
-                         uint2* near_list, unsigned int near_cap, unsigned int* near_count, cudaStream_t s) {
+                         uint2* near_list, unsigned int near_cap, unsigned int* near_count, int background_blocks_per_sm,
+                         cudaStream_t s) {
     const uint64_t nrows = row_end - row_begin;
-    // enough blocks to fill 148 SMs x MINB resident blocks several times over, but row chunks
+    // enough work items to fill 148 SMs x MINB resident blocks several times over, but row chunks
     // long enough to amortise the per-block set-up
     uint32_t rpb = 128;
     while (rpb > 8 && (uint64_t)m.ntiles * ((nrows + rpb - 1) / rpb) < 148ull * MINB * 4ull) rpb >>= 1;
-    dim3 grid(m.ntiles, (unsigned)((nrows + rpb - 1) / rpb));
+    const uint32_t nchunks = (uint32_t)((nrows + rpb - 1) / rpb);
+    const uint32_t total = m.ntiles * nchunks;
+    uint32_t grid = total, ipb = 1;
+    if (background_blocks_per_sm > 0 && total > 148u * (uint32_t)background_blocks_per_sm) {
+        grid = 148u * (uint32_t)background_blocks_per_sm;  // persistent, polite grid
+        ipb = (total + grid - 1) / grid;
+        grid = (total + ipb - 1) / ipb;
+    }
     const double cH = ph.sign * ph.gamma * ph.tau;
-    far_kernel<NQ, BIMAG, MINB><<<grid, TILE, 0, s>>>(m.far_k, m.far_c, m.col_class, m.src, m.n, row_begin, row_end, rpb,
-                                                      ph.wavruim, ph.k2, cH, ph.beta.re, ph.beta.im, A, lda, near_list,
-                                                      near_cap, near_count);
+    far_kernel<NQ, BIMAG, MINB><<<grid, TILE, 0, s>>>(m.far_k, m.far_c, m.col_class, m.src, m.n, row_begin, row_end, rpb, nchunks,
+                                                      total, ipb, ph.wavruim, ph.k2, cH, ph.beta.re, ph.beta.im, A, lda,
+                                                      near_list, near_cap, near_count);
     return cudaGetLastError();
 }
 
 template <int NQ>
 cudaError_t launch_far_t(const DeviceMesh& m, const Phys& ph, uint64_t row_begin, uint64_t row_end, cplx* A, uint64_t lda,
-                         uint2* near_list, unsigned int near_cap, unsigned int* near_count, cudaStream_t s) {
+                         uint2* near_list, unsigned int near_cap, unsigned int* near_count, int bg, cudaStream_t s) {
     const bool bimag = (ph.beta.re == 0.0);
     const int minb = env_int("BEMB200_FAR_MINB", 4);
 #define FAR_DISPATCH(B, M) \
-    return launch_far_v<NQ, B, M>(m, ph, row_begin, row_end, A, lda, near_list, near_cap, near_count, s)
+    return launch_far_v<NQ, B, M>(m, ph, row_begin, row_end, A, lda, near_list, near_cap, near_count, bg, s)
     if (bimag) {
         if (minb == 5) FAR_DISPATCH(true, 5);
         if (minb == 6) FAR_DISPATCH(true, 6);
@@ -258,16 +288,17 @@ cudaError_t launch_far_t(const DeviceMesh& m, const Phys& ph, uint64_t row_begin
 int far_kernel_launch_count(const DeviceMesh& m) { return (m.n_flat_tri ? 1 : 0) + (m.n_flat_quad ? 1 : 0); }
 
 cudaError_t launch_far(const DeviceMesh& m, const Phys& ph, uint64_t row_begin, uint64_t row_end, cplx* A, uint64_t lda,
-                       uint2* near_list, unsigned int near_cap, unsigned int* near_count, cudaStream_t s) {
+                       uint2* near_list, unsigned int near_cap, unsigned int* near_count, int background_blocks_per_sm,
+                       cudaStream_t s) {
     if (row_end <= row_begin) return cudaSuccess;
     cudaError_t e = upload_tables();
     if (e != cudaSuccess) return e;
     if (m.n_flat_tri) {
-        e = launch_far_t<NQ_TRI>(m, ph, row_begin, row_end, A, lda, near_list, near_cap, near_count, s);
+        e = launch_far_t<NQ_TRI>(m, ph, row_begin, row_end, A, lda, near_list, near_cap, near_count, background_blocks_per_sm, s);
         if (e != cudaSuccess) return e;
     }
     if (m.n_flat_quad) {
-        e = launch_far_t<NQ_QUAD>(m, ph, row_begin, row_end, A, lda, near_list, near_cap, near_count, s);
+        e = launch_far_t<NQ_QUAD>(m, ph, row_begin, row_end, A, lda, near_list, near_cap, near_count, background_blocks_per_sm, s);
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;

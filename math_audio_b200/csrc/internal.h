@@ -52,7 +52,8 @@ struct AssemblyStats {
 // launchers (assembly_exact.cu / assembly_far.cu)
 cudaError_t launch_prep(const DeviceMesh& m, cudaStream_t s);
 cudaError_t launch_far(const DeviceMesh& m, const Phys& ph, uint64_t row_begin, uint64_t row_end, cplx* A, uint64_t lda,
-                       uint2* near_list, unsigned int near_cap, unsigned int* near_count, cudaStream_t s);
+                       uint2* near_list, unsigned int near_cap, unsigned int* near_count, int background_blocks_per_sm,
+                       cudaStream_t s);
 cudaError_t launch_near_list(const DeviceMesh& m, const Phys& ph, uint64_t row_begin, cplx* A, uint64_t lda, cplx* rhs,
                              const uint2* near_list, unsigned int count, cudaStream_t s);
 cudaError_t launch_special(const DeviceMesh& m, const Phys& ph, uint64_t row_begin, uint64_t row_end, cplx* A,

@@ -1,0 +1,81 @@
+"""Frequency-sweep driver: the mesh stays staged on the device and the assembly of frequency
+f+1 (FP64-bound) overlaps the GMRES solve of frequency f (HBM-bound) on a second stream with a
+second matrix buffer.  SURVEY.md section 8f rank 2; the reference re-runs everything per
+frequency (`bem_solver.rs:273-322`, examples/audio_frequency_sweep.rs).
+
+Every frequency still goes through exactly `build_tbem_system_with_beta` + `gmres`; only the
+schedule changes.
+"""
+from __future__ import annotations
+
+import threading
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import bem
+from .mesh import Mesh
+from .types import PhysicsParams
+
+
+class SweepDriver:
+    def __init__(self, mesh: Mesh, device: int = 0, rank: int = 0, nranks: int = 1, nccl_id: Optional[bytes] = None,
+                 solve_stream: int = 0, assembly_stream: int = 0, overlap: bool = True, background_blocks_per_sm: int = 1):
+        # the solve context owns the communicator; the assembly context needs none
+        self.ctx_solve = bem.Context(device, rank, nranks, nccl_id, cuda_stream=solve_stream)
+        self.ctx_asm = bem.Context(device, rank, nranks, None, cuda_stream=assembly_stream) if overlap else self.ctx_solve
+        self.overlap = overlap
+        self.background_blocks_per_sm = background_blocks_per_sm if overlap else 0
+        self.mesh = mesh
+        self.staged = bem.StagedMesh(mesh, self.ctx_asm)
+        self.n = self.staged.num_dofs
+        self.rows = self.ctx_solve.partition(self.n)
+        self.buffers: List[Optional[bem.TbemSystem]] = [None, None]
+        self.asm_stats: List[dict] = []
+        self.sol_stats: List[dict] = []
+
+    def _assemble(self, slot: int, physics: PhysicsParams, beta: complex, mesh_for_stage: Optional[Mesh], err: list):
+        try:
+            staged = self.staged if mesh_for_stage is None else bem.StagedMesh(mesh_for_stage, self.ctx_asm)
+            first = self.buffers[slot] is None
+            self.buffers[slot] = bem.build_tbem_system_with_beta(staged, physics, beta, ctx=self.ctx_asm, rows=self.rows,
+                                                                reuse=self.buffers[slot], fetch_rhs=False)
+            if first and self.overlap:
+                self.buffers[slot].matrix.set_context(self.ctx_solve)
+        except Exception as e:  # surfaced in the caller thread
+            err.append(e)
+
+    def run(self, cases: Sequence[Tuple[PhysicsParams, complex]], config: bem.GmresConfig,
+            solve: Callable[[int, bem.TbemSystem, bem.DenseOperator], object], restage_host_mesh: bool = False) -> list:
+        """For every (physics, beta) in `cases`: assemble, then call ``solve(i, system, operator)``
+        (which builds its right-hand side and calls gmres / gmres_device) -- assembly of case i+1
+        runs while case i is being solved.  ``restage_host_mesh``: re-upload the host mesh for every
+        frequency (what a caller without a staged mesh pays; used by the end-to-end benchmark)."""
+        out = []
+        err: list = []
+        mesh_arg = self.mesh if restage_host_mesh else None
+        if not cases:
+            return out
+        self.ctx_asm.set_background(0)  # nothing to hide behind yet: full-speed assembly
+        self._assemble(0, cases[0][0], cases[0][1], mesh_arg, err)
+        if err:
+            raise err[0]
+        self.ctx_asm.set_background(self.background_blocks_per_sm)
+        for i in range(len(cases)):
+            t = None
+            if i + 1 < len(cases):
+                if self.overlap:
+                    t = threading.Thread(target=self._assemble, args=((i + 1) % 2, cases[i + 1][0], cases[i + 1][1], mesh_arg, err))
+                    t.start()
+            system = self.buffers[i % 2]
+            self.asm_stats.append(system.matrix.assembly_stats())
+            op = bem.DenseOperator(system)
+            out.append(solve(i, system, op))
+            self.sol_stats.append(system.matrix.solver_stats())
+            if t is not None:
+                t.join()
+            elif i + 1 < len(cases):
+                self._assemble((i + 1) % 2, cases[i + 1][0], cases[i + 1][1], mesh_arg, err)
+            if err:
+                raise err[0]
+        return out
