@@ -35,6 +35,7 @@ struct GmresWorkspace {
     cplx* xout = nullptr;   // npad
     cplx* hcol_d = nullptr; // (restart+1) slots x (restart+2): one Hessenberg column per in-flight iteration
     cplx* ycoef_d = nullptr;
+    cplx* lmat_d = nullptr;  // (restart+1)^2 Gram triangle of the current cycle (low-sync MGS kernel)
     double* scal_d = nullptr;
     cplx* hcol_h = nullptr;   // pinned, same shape as hcol_d
     double* scal_h = nullptr; // pinned
@@ -50,7 +51,7 @@ void free_workspace(bemb200_matrix* m) {
     GmresWorkspace* ws = m->ws;
     if (!ws) return;
     cudaFree(ws->V); cudaFree(ws->w); cudaFree(ws->r); cudaFree(ws->xin); cudaFree(ws->bin); cudaFree(ws->xout);
-    cudaFree(ws->hcol_d); cudaFree(ws->ycoef_d); cudaFree(ws->scal_d);
+    cudaFree(ws->hcol_d); cudaFree(ws->ycoef_d); cudaFree(ws->scal_d); cudaFree(ws->lmat_d);
     if (ws->hcol_h) cudaFreeHost(ws->hcol_h);
     if (ws->scal_h) cudaFreeHost(ws->scal_h);
     if (ws->ev0) cudaEventDestroy(ws->ev0);
@@ -83,6 +84,7 @@ static int ensure_workspace(bemb200_matrix* m, uint32_t restart) {
     ws->ldh_slot = restart + 2;
     BEMB_CUDA(ctx, cudaMalloc((void**)&ws->hcol_d, (size_t)(restart + 1) * ws->ldh_slot * sizeof(cplx)));
     BEMB_CUDA(ctx, cudaMalloc((void**)&ws->ycoef_d, (restart + 2) * sizeof(cplx)));
+    BEMB_CUDA(ctx, cudaMalloc((void**)&ws->lmat_d, (size_t)(restart + 1) * (restart + 1) * sizeof(cplx)));
     BEMB_CUDA(ctx, cudaMalloc((void**)&ws->scal_d, 4 * sizeof(double)));
     BEMB_CUDA(ctx, cudaMallocHost((void**)&ws->hcol_h, (size_t)(restart + 1) * ws->ldh_slot * sizeof(cplx)));
     ws->it_ev0.resize(restart + 1); ws->it_ev1.resize(restart + 1); ws->it_done.resize(restart + 1);
@@ -90,7 +92,7 @@ static int ensure_workspace(bemb200_matrix* m, uint32_t restart) {
     for (uint32_t i = 0; i <= restart; ++i) {
         BEMB_CUDA(ctx, cudaEventCreate(&ws->it_ev0[i]));
         BEMB_CUDA(ctx, cudaEventCreate(&ws->it_ev1[i]));
-        BEMB_CUDA(ctx, cudaEventCreateWithFlags(&ws->it_done[i], cudaEventDisableTiming));
+        BEMB_CUDA(ctx, cudaEventCreate(&ws->it_done[i]));
     }
     BEMB_CUDA(ctx, cudaMallocHost((void**)&ws->scal_h, 4 * sizeof(double)));
     BEMB_CUDA(ctx, cudaEventCreate(&ws->ev0));
@@ -124,6 +126,9 @@ static void accumulate_matvec_time(bemb200_matrix* m) {
 }
 
 static double g_dbg_launch_us = 0.0, g_dbg_wait_us = 0.0;  // host-side phase timers (diagnostics)
+static double g_dbg_post_ms = 0.0, g_dbg_gap_ms = 0.0;     // device: zgemv-end -> column-on-host, and iteration-to-iteration gap
+static double g_dbg_mgs_ms = 0.0;
+static const bool g_dbg_split = std::getenv("BEMB200_DEBUG_SPLIT") != nullptr;
 static const bool g_speculate = []() {
     const char* v = std::getenv("BEMB200_GMRES_SPECULATE");
     return v ? (std::atoi(v) != 0) : true;
@@ -232,7 +237,9 @@ static int gmres_core(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t max_it
                 if (rc2 != BEMB200_OK) return rc2;
             }
             cplx* hd = ws->hcol_d + (size_t)j * ws->ldh_slot;
-            BEMB_CUDA(ctx, launch_mgs(ws->V, ws->npad, ws->w, j, n, hd, ws->V + (uint64_t)(j + 1) * ws->npad, pinv, direct_scale, s));
+            BEMB_CUDA(ctx, launch_mgs(ws->V, ws->npad, ws->w, j, n, hd, ws->V + (uint64_t)(j + 1) * ws->npad, pinv, direct_scale,
+                                      ws->lmat_d, (int)ws->restart + 1, s));
+            if (g_dbg_split) BEMB_CUDA(ctx, cudaEventRecord(ws->ev0, s));
             BEMB_CUDA(ctx, cudaMemcpyAsync(ws->hcol_h + (size_t)j * ws->ldh_slot, hd, (j + 2) * sizeof(cplx),
                                            cudaMemcpyDeviceToHost, s));
             BEMB_CUDA(ctx, cudaEventRecord(ws->it_done[j], s));
@@ -259,6 +266,16 @@ static int gmres_core(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t max_it
                 if (cudaEventElapsedTime(&ms, ws->it_ev0[j], ws->it_ev1[j]) == cudaSuccess) m->last_matvec_ms += ms;
                 else cudaGetLastError();
                 m->last_matvecs += 1;  // matvecs whose duration is in last_matvec_ms
+                if (cudaEventElapsedTime(&ms, ws->it_ev1[j], ws->it_done[j]) == cudaSuccess) g_dbg_post_ms += ms;
+                else cudaGetLastError();
+                if (g_dbg_split && !g_speculate) {
+                    if (cudaEventElapsedTime(&ms, ws->it_ev1[j], ws->ev0) == cudaSuccess) g_dbg_mgs_ms += ms;
+                    else cudaGetLastError();
+                }
+                if (j > 0 && ws->launched[j - 1]) {
+                    if (cudaEventElapsedTime(&ms, ws->it_done[j - 1], ws->it_ev0[j]) == cudaSuccess) g_dbg_gap_ms += ms;
+                    else cudaGetLastError();
+                }
             }
             g_dbg_launch_us += std::chrono::duration<double, std::micro>(tp1 - tp0).count();
             g_dbg_wait_us += std::chrono::duration<double, std::micro>(tp2 - tp1).count();
@@ -319,6 +336,11 @@ extern "C" void bemb200_debug_times(double* launch_us, double* wait_us) {
     *launch_us = g_dbg_launch_us;
     *wait_us = g_dbg_wait_us;
     g_dbg_launch_us = g_dbg_wait_us = 0.0;
+}
+extern "C" void bemb200_debug_times2(double* post_ms, double* gap_ms) {
+    *post_ms = g_dbg_post_ms;
+    *gap_ms = g_dbg_mgs_ms > 0.0 ? g_dbg_mgs_ms : g_dbg_gap_ms;
+    g_dbg_post_ms = g_dbg_gap_ms = g_dbg_mgs_ms = 0.0;
 }
 
 static void reset_stats(bemb200_matrix* m) {

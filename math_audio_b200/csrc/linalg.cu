@@ -11,6 +11,7 @@
 //                       barriers instead of j+1 kernel launches / host round trips.
 //   residual / scale / update kernels for gmres.rs:143-172,238-262
 #include <cooperative_groups.h>
+#include <cstdlib>
 
 #include "linalg.h"
 
@@ -221,6 +222,170 @@ mgs_cluster_reg_kernel(const cplx* __restrict__ V, uint64_t ldv, const cplx* __r
         }
     }
     cluster.sync();  // no CTA may exit while a peer could still address its shared memory
+}
+
+// ------------------------------------------------------------------------------------------
+// Low-synchronisation form of the same modified Gram-Schmidt sweep.  With L the strictly lower
+// triangle of the Gram matrix of the stored basis, L_kl = v_k^H v_l (k > l; rounding-level numbers,
+// the loss of orthogonality of V), the MGS coefficients h_k = v_k^H (w - sum_{l<k} h_l v_l) satisfy
+//       (I + L) h = V^H w ,
+// so ALL j+1 inner products can be taken in one pass over V and cross the cluster in ONE barrier;
+// a (j+1)x(j+1) forward substitution then yields exactly the h of gmres.rs:184-188 (same algebra,
+// different rounding), and a second pass applies w -= V h.  Row j of L (v_j^H v_l, l < j) is
+// computed in the same first pass, kept in global memory for the later iterations of the cycle.
+// 2 cluster barriers per iteration instead of j+2.
+// ------------------------------------------------------------------------------------------
+constexpr int LS_THREADS = 256;
+constexpr int LS_WARPS = LS_THREADS / 32;
+constexpr int LS_MAXV = 64;  // max j+1 handled here (restart <= 63), else the one-vector kernels
+
+template <int EPT>
+__global__ void __launch_bounds__(LS_THREADS)
+mgs_lowsync_kernel(const cplx* __restrict__ V, uint64_t ldv, const cplx* __restrict__ w, int j, uint64_t n, uint64_t S,
+                   cplx* __restrict__ Lmat, int ldl, cplx* __restrict__ hcol, cplx* __restrict__ vnext, double breakdown_tol,
+                   const cplx* __restrict__ pinv, int direct_scale) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    __shared__ ClusterShared sh1;  // single-value all-reduce (norm)
+    // dynamic layout: warp_part[LS_WARPS][2*LS_MAXV] | slots[MAX_CLUSTER][2*LS_MAXV] | a[LS_MAXV] | Ls[(j+1)*(j+1)]
+    cplx* warp_part = reinterpret_cast<cplx*>(dyn);
+    cplx* slots = warp_part + LS_WARPS * 2 * LS_MAXV;
+    cplx* avec = slots + MAX_CLUSTER * 2 * LS_MAXV;
+    cplx* Ls = avec + LS_MAXV;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned nb = cluster.num_blocks(), me = cluster.block_rank();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nv = j + 1;
+    const uint64_t begin = (uint64_t)me * S;
+    const uint64_t end = begin + S < n ? begin + S : n;
+    const uint64_t len = end > begin ? end - begin : 0;
+
+    cplx wr[EPT], vj[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+        const uint64_t k = tid + (uint64_t)e * LS_THREADS;
+        wr[e] = k < len ? w[begin + k] : C(0, 0);
+        if (pinv && k < len) wr[e] = wr[e] * ldg_c(pinv + begin + k);
+        vj[e] = (k < len) ? ldg_c(V + (uint64_t)j * ldv + begin + k) : C(0, 0);
+    }
+    // previous rows of L (rows 1..j-1) -> shared memory
+    for (int idx = tid; idx < nv * nv; idx += LS_THREADS) {
+        const int k = idx / nv, l = idx - k * nv;
+        Ls[idx] = (l < k && k < j) ? Lmat[k * ldl + l] : C(0, 0);
+    }
+
+    // ---- pass 1: a_l = v_l^H w (l <= j) and g_l = v_j^H v_l (l < j), 8 vectors at a time -------
+    for (int l0 = 0; l0 < nv; l0 += 8) {
+        cplx aa[8], gg[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { aa[q] = C(0, 0); gg[q] = C(0, 0); }
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            const uint64_t k = tid + (uint64_t)e * LS_THREADS;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int l = l0 + q;
+                const cplx v = (l < nv && k < len) ? ldg_c(V + (uint64_t)l * ldv + begin + k) : C(0, 0);
+                aa[q].re = fma(v.re, wr[e].re, fma(v.im, wr[e].im, aa[q].re));    // conj(v_l) * w
+                aa[q].im = fma(v.re, wr[e].im, fma(-v.im, wr[e].re, aa[q].im));
+                gg[q].re = fma(vj[e].re, v.re, fma(vj[e].im, v.im, gg[q].re));    // conj(v_j) * v_l
+                gg[q].im = fma(vj[e].re, v.im, fma(-vj[e].im, v.re, gg[q].im));
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) {
+                aa[q].re += __shfl_xor_sync(0xffffffffu, aa[q].re, m);
+                aa[q].im += __shfl_xor_sync(0xffffffffu, aa[q].im, m);
+                gg[q].re += __shfl_xor_sync(0xffffffffu, gg[q].re, m);
+                gg[q].im += __shfl_xor_sync(0xffffffffu, gg[q].im, m);
+            }
+            if (lane == 0 && l0 + q < nv) {
+                warp_part[warp * 2 * LS_MAXV + l0 + q] = aa[q];
+                warp_part[warp * 2 * LS_MAXV + LS_MAXV + l0 + q] = gg[q];
+            }
+        }
+    }
+    __syncthreads();
+    // block partials -> slot `me` of every CTA of the cluster (DSMEM)
+    if (tid < 2 * nv) {
+        const int idx = tid < nv ? tid : LS_MAXV + (tid - nv);
+        cplx t = C(0, 0);
+#pragma unroll
+        for (int wq = 0; wq < LS_WARPS; ++wq) { t.re += warp_part[wq * 2 * LS_MAXV + idx].re; t.im += warp_part[wq * 2 * LS_MAXV + idx].im; }
+        for (unsigned d = 0; d < nb; ++d) {
+            cplx* remote = cluster.map_shared_rank(slots, d);
+            remote[me * 2 * LS_MAXV + idx] = t;
+        }
+    }
+    cluster.sync();
+    // every CTA: totals in fixed CTA order, forward substitution (I + L) h = a
+    if (tid < 2 * nv) {
+        const int idx = tid < nv ? tid : LS_MAXV + (tid - nv);
+        cplx t = C(0, 0);
+        for (unsigned d = 0; d < nb; ++d) { t.re += slots[d * 2 * LS_MAXV + idx].re; t.im += slots[d * 2 * LS_MAXV + idx].im; }
+        if (tid < nv) {
+            avec[tid] = t;
+        } else {
+            const int l = tid - nv;
+            if (l < j) {
+                Ls[j * nv + l] = t;                                   // new row j of L
+                if (me == 0) Lmat[j * ldl + l] = t;
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        for (int l = 0; l < nv; ++l) {
+            const cplx hl = avec[l];
+            for (int k = l + 1 + lane; k < nv; k += 32) {
+                const cplx lk = Ls[k * nv + l];
+                cplx ak = avec[k];
+                ak.re -= lk.re * hl.re - lk.im * hl.im;
+                ak.im -= lk.re * hl.im + lk.im * hl.re;
+                avec[k] = ak;
+            }
+            __syncwarp();
+        }
+        if (me == 0)
+            for (int l = lane; l < nv; l += 32) hcol[l] = avec[l];
+    }
+    __syncthreads();
+    // ---- pass 2: w -= sum_l h_l v_l ----------------------------------------------------------------
+    for (int l0 = 0; l0 < nv; l0 += 8) {
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            const uint64_t k = tid + (uint64_t)e * LS_THREADS;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int l = l0 + q;
+                if (l < nv && k < len) {
+                    const cplx v = ldg_c(V + (uint64_t)l * ldv + begin + k);
+                    const cplx h = avec[l];
+                    wr[e].re = fma(-h.re, v.re, fma(h.im, v.im, wr[e].re));
+                    wr[e].im = fma(-h.re, v.im, fma(-h.im, v.re, wr[e].im));
+                }
+            }
+        }
+    }
+    cplx acc = C(0, 0);
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) acc.re = fma(wr[e].re, wr[e].re, fma(wr[e].im, wr[e].im, acc.re));
+    const cplx nn = cluster_allreduce(acc, sh1, 0);
+    const double nrm = sqrt(nn.re);
+    if (me == 0 && tid == 0) hcol[j + 1] = C(nrm, 0.0);
+    if (!(nrm < breakdown_tol)) {
+        const double inv = 1.0 / nrm;
+        const double sc = inv - 1.0;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            const uint64_t k = tid + (uint64_t)e * LS_THREADS;
+            if (k < len)
+                vnext[begin + k] = direct_scale ? C(wr[e].re * inv, wr[e].im * inv)
+                                                : C(wr[e].re + wr[e].re * sc, wr[e].im + wr[e].im * sc);
+        }
+    }
+    cluster.sync();
 }
 
 // Same step for long vectors: w slice in shared memory (or global/L2 if even that does not
@@ -679,11 +844,45 @@ static cudaError_t launch_mgs_reg(int cl, const cplx* V, uint64_t ldv, const cpl
     return launch_cluster(mgs_cluster_reg_kernel<EPT>, cl, 256, 0, s, V, ldv, w, j, n, S, hcol, vnext, 1e-14, pinv, direct_scale);
 }
 
-static int g_mgs_mode = 0;  // 0: register kernel on a 16-CTA cluster when the slice fits, 1: generic kernel only
+template <int EPT>
+static cudaError_t launch_mgs_lowsync(int cl, const cplx* V, uint64_t ldv, const cplx* w, int j, uint64_t n, uint64_t S, cplx* Lmat,
+                                      int ldl, cplx* hcol, cplx* vnext, const cplx* pinv, int direct_scale, cudaStream_t s) {
+    static bool attr_done = false;
+    const size_t fixed = (size_t)(LS_WARPS * 2 * LS_MAXV + MAX_CLUSTER * 2 * LS_MAXV + LS_MAXV) * sizeof(cplx);
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(mgs_lowsync_kernel<EPT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(mgs_lowsync_kernel<EPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(fixed + (size_t)LS_MAXV * LS_MAXV * sizeof(cplx)));
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    const size_t smem = fixed + (size_t)(j + 1) * (j + 1) * sizeof(cplx);
+    return launch_cluster(mgs_lowsync_kernel<EPT>, cl, LS_THREADS, smem, s, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, 1e-14, pinv,
+                          direct_scale);
+}
+
+static int g_mgs_mode = []() {
+    const char* v = std::getenv("BEMB200_MGS_MODE");
+    return v ? std::atoi(v) : 0;
+}();  // 0: low-sync register kernel (16-CTA cluster) when the slice fits, 2: one-vector register kernel, 1: generic kernel only
 
 cudaError_t launch_mgs(const cplx* V, uint64_t ldv, cplx* w, int j, uint64_t n, cplx* hcol, cplx* vnext, const cplx* pinv,
-                       int direct_scale, cudaStream_t s) {
-    if (g_mgs_mode == 0 && n <= 16ull * 256ull * 8ull) {
+                       int direct_scale, cplx* Lmat, int ldl, cudaStream_t s) {
+    if (g_mgs_mode == 0 && Lmat && j + 1 <= LS_MAXV && n <= 16ull * LS_THREADS * 8ull) {
+        const int cl = n >= 2048 ? 16 : (n >= 512 ? 4 : 1);
+        const uint64_t S = (n + cl - 1) / cl;
+        const uint64_t ept = (S + LS_THREADS - 1) / LS_THREADS;
+        cudaError_t e;
+        if (ept <= 1) e = launch_mgs_lowsync<1>(cl, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, s);
+        else if (ept <= 2) e = launch_mgs_lowsync<2>(cl, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, s);
+        else if (ept <= 4) e = launch_mgs_lowsync<4>(cl, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, s);
+        else e = launch_mgs_lowsync<8>(cl, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, s);
+        if (e == cudaSuccess) return e;
+        cudaGetLastError();
+        g_mgs_mode = 2;
+    }
+    if ((g_mgs_mode == 0 || g_mgs_mode == 2) && n <= 16ull * 256ull * 8ull) {
         // register-resident w: 16 CTAs (non-portable cluster size) x 256 threads x <= 8 elements
         const int cl = n >= 2048 ? 16 : (n >= 512 ? 4 : 1);
         const uint64_t S = (n + cl - 1) / cl;
