@@ -186,6 +186,21 @@ int bemb200_apply_block(const bemb200_matrix* m, const double* x_all, uint32_t n
  * the last bemb200_gmres* / bemb200_apply* call on this matrix */
 int bemb200_solver_stats(const bemb200_matrix* m, uint64_t* kernel_launches, double* matvec_ms, uint64_t* matvecs);
 
+/* ---- neighbours of the hot path (device-resident sweep): incident RHS and field evaluation ---- */
+/* IncidentField::compute_rhs_with_beta (math-bem/src/core/incident.rs:317-342) at the collocation
+ * points / normals of the staged mesh, in DOF order: rhs_i = -(gamma p_inc + beta tau dp_inc/dn),
+ * summed over n_sources sources (MultiplePlaneWaves / MultiplePointSources, incident.rs:136-165).
+ * kinds[s]: 0 plane wave (vecs[3s..] = unit direction), 1 point source (vecs = position);
+ * amps[2s..] complex amplitude / strength.  Result to rhs_host and/or rhs_dev (either may be NULL). */
+int bemb200_incident_rhs(const bemb200_staged_mesh* sm, const bemb200_physics* phys, double beta_re, double beta_im,
+                         uint32_t n_sources, const int32_t* kinds, const double* vecs, const double* amps, double* rhs_host,
+                         double* rhs_dev);
+/* compute_scattered_field (math-bem/src/core/postprocess/pressure.rs:81-259): 7-point rule per
+ * element (Quad4 = its first triangle, as the reference).  eval_pts [n_eval*3]; surface_pressure /
+ * surface_velocity (may be NULL): num_dofs complex128 in DOF order; out [n_eval] complex128. */
+int bemb200_scattered_field(const bemb200_staged_mesh* sm, const bemb200_physics* phys, uint64_t n_eval, const double* eval_pts,
+                            const double* surface_pressure, const double* surface_velocity, double* out);
+
 /* ---- measurement helpers ----------------------------------------------------------- */
 /* register-resident DFMA peak of this device in TFLOP/s (2 flop per DFMA) */
 int bemb200_measure_fp64_peak(bemb200_ctx* ctx, double* tflops);

@@ -358,6 +358,47 @@ def apply_device(operator: DenseOperator, x_dev: int, y_dev: int) -> None:
     _capi.check(_capi.lib().bemb200_apply_device(operator.matrix._h, C.c_void_p(x_dev), C.c_void_p(y_dev)), operator.matrix.ctx._h)
 
 
+def incident_rhs_device(staged: StagedMesh, physics: PhysicsParams, beta: complex, incident, rhs_dev: int = 0,
+                        fetch: bool = True) -> Optional[np.ndarray]:
+    """IncidentField::compute_rhs_with_beta (incident.rs:317-342) on the device, at the staged
+    mesh's collocation points (DOF order).  ``incident`` is a math_audio_b200.incident.IncidentField;
+    ``rhs_dev``: optional device pointer receiving the vector (sweeps that never leave the GPU)."""
+    kinds, vecs, amps = [], [], []
+    for d, a in incident.plane_waves:
+        kinds.append(0); vecs.append(np.asarray(d, dtype=np.float64)); amps.append(complex(a))
+    for p, a in incident.point_sources:
+        kinds.append(1); vecs.append(np.asarray(p, dtype=np.float64)); amps.append(complex(a))
+    kinds_a = np.ascontiguousarray(kinds, dtype=np.int32)
+    vecs_a = np.ascontiguousarray(np.stack(vecs), dtype=np.float64)
+    amps_a = np.ascontiguousarray(amps, dtype=np.complex128)
+    out = np.empty(staged.num_dofs, dtype=np.complex128) if fetch else None
+    ph = _cphys(physics)
+    beta = complex(beta)
+    _capi.check(_capi.lib().bemb200_incident_rhs(staged._h, C.byref(ph), beta.real, beta.imag, len(kinds), _capi.ptr(kinds_a),
+                                                 _capi.ptr(vecs_a), _capi.ptr(amps_a), _capi.ptr(out) if fetch else None,
+                                                 C.c_void_p(rhs_dev or None)), staged.ctx._h)
+    return out
+
+
+def compute_scattered_field(eval_points: np.ndarray, staged: StagedMesh, surface_pressure: np.ndarray,
+                            surface_velocity: Optional[np.ndarray], physics: PhysicsParams) -> np.ndarray:
+    """postprocess/pressure.rs:81-137 on the device (surface values in DOF order)."""
+    pts = np.ascontiguousarray(eval_points, dtype=np.float64).reshape(-1, 3)
+    ps = np.ascontiguousarray(surface_pressure, dtype=np.complex128)
+    if ps.shape != (staged.num_dofs,):
+        raise ValueError("surface_pressure must have num_dofs entries")
+    vs = None
+    if surface_velocity is not None:
+        vs = np.ascontiguousarray(surface_velocity, dtype=np.complex128)
+        if vs.shape != (staged.num_dofs,):
+            raise ValueError("surface_velocity must have num_dofs entries")
+    out = np.empty(pts.shape[0], dtype=np.complex128)
+    ph = _cphys(physics)
+    _capi.check(_capi.lib().bemb200_scattered_field(staged._h, C.byref(ph), pts.shape[0], _capi.ptr(pts), _capi.ptr(ps),
+                                                    _capi.ptr(vs) if vs is not None else None, _capi.ptr(out)), staged.ctx._h)
+    return out
+
+
 class IdentityPreconditioner:
     """traits.rs:377-385."""
 

@@ -29,6 +29,7 @@ UNITS = {
     "linalg.cu": [],
     "gmres.cu": [],
     "block_gmres.cu": [],
+    "postprocess.cu": ["-fmad=false"],
     "api.cu": [],
 }
 

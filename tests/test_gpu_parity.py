@@ -308,6 +308,37 @@ def test_gmres_reference_kats(bem, orc):
     assert sol.converged and sol.iterations == 0
 
 
+def test_incident_rhs_and_field_evaluation_on_device(bem, orc):
+    """SURVEY 8f ranks 1-2: IncidentField::compute_rhs_with_beta and compute_scattered_field."""
+    from math_audio_b200.incident import IncidentField
+    from math_audio_b200.mesh import fibonacci_directions
+
+    a = 0.1
+    ph = PhysicsParams.from_wave_number(25.0)
+    beta = ph.burton_miller_beta_scaled(4.0)
+    for mesh in (generate_icosphere_mesh(a, 3), generate_box_mesh_quad(0.3, 0.4, 0.5, 6, 8, 10)):
+        st = bem.StagedMesh(mesh)
+        n = mesh.n_elem
+        for inc, kind, vec in [(IncidentField.plane_wave_z(), 0, [0, 0, 1.0]), (IncidentField.plane_wave([0.6, 0.0, 0.8]), 0, [0.6, 0.0, 0.8]),
+                               (IncidentField.point_source([0.7, -0.2, 0.4]), 1, [0.7, -0.2, 0.4])]:
+            got = bem.incident_rhs_device(st, ph, beta, inc)
+            ref, _ = orc.incident_rhs(kind, vec, 1.0, mesh.center, mesh.normal, ph.wave_number, beta)
+            assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < 1e-13
+        multi = IncidentField(plane_waves=[(d, 0.5 + 0.1j) for d in fibonacci_directions(5)])
+        ref = sum(orc.incident_rhs(0, d, 0.5 + 0.1j, mesh.center, mesh.normal, ph.wave_number, beta)[0] for d in fibonacci_directions(5))
+        assert np.max(np.abs(bem.incident_rhs_device(st, ph, beta, multi) - ref)) / np.max(np.abs(ref)) < 1e-13
+        rng = np.random.default_rng(8)
+        p = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        v = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        v[::3] = 0.0
+        pts = rng.standard_normal((97, 3))
+        pts *= (3.0 * a / np.linalg.norm(pts, axis=1))[:, None] * (1.0 + rng.random(97))[:, None]
+        for vel in (None, v):
+            got = bem.compute_scattered_field(pts, st, p, vel, ph)
+            ref = orc.scattered_field(mesh, pts, p, ph.wave_number, surface_velocity=vel)
+            assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-12
+
+
 def test_gmres_preconditioned(bem, orc):
     """gmres_preconditioned (gmres.rs:282-585) with the identity and the Jacobi preconditioner on an
     assembled BEM matrix and on the reference's tridiagonal KAT."""
