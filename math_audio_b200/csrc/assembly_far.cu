@@ -275,6 +275,8 @@ cudaError_t launch_far_t(const DeviceMesh& m, const Phys& ph, uint64_t row_begin
 #define FAR_DISPATCH(B, M) \
     return launch_far_v<NQ, B, M>(m, ph, row_begin, row_end, A, lda, near_list, near_cap, near_count, bg, s)
     if (bimag) {
+        if (minb == 2) FAR_DISPATCH(true, 2);
+        if (minb == 3) FAR_DISPATCH(true, 3);
         if (minb == 5) FAR_DISPATCH(true, 5);
         if (minb == 6) FAR_DISPATCH(true, 6);
         FAR_DISPATCH(true, 4);
