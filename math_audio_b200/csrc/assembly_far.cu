@@ -20,14 +20,16 @@
 //     r_q^2        = |d0|^2 + a_q (2 d0.e1) + b_q (2 d0.e2) + kappa_q            3 DP ops
 //     (y_q-x).n_x  = d0.n_x + a_q (e1.n_x) + b_q (e2.n_x)                       2 DP ops
 //     (y_q-x).n_y  = d0.n_y                                   (constant over the element)
-// then one MUFU-seeded rsqrt (5), one Cody-Waite + minimax sincos (20) and the kernel algebra
+// then one MUFU-seeded rsqrt (5), one table-based sincos (pi/64 reduction, 128-entry (cos,sin) table in
+// shared memory, degree-6/7 kernels, one rotation: 16) and the kernel algebra
 // with H and E folded into ONE complex accumulator:
 //     A_ij = sum_q zg_q * [ cH h rho (-rho + ik) + beta (P_q - i Q_q) ],
 //     P = rho^2 t - k^2 rq,  Q = k rho t,  t = 3 rq + n_x.n_y,  rq = (h rho)(-m rho)
-// ~50 DP-pipe instructions per quadrature point (purely imaginary beta, the reference's
+// ~46 DP-pipe instructions per quadrature point (purely imaginary beta, the reference's
 // beta = i*scale/k).  Nothing but the 16-byte result touches HBM.
 // Pairs that fail the (guard-banded) ratio test are appended to a compact list for the exact
 // near-field kernel, which re-takes the decision bit-faithfully and overwrites the entry.
+#include <cmath>
 #include <cstdlib>
 
 #include "internal.h"
@@ -47,6 +49,7 @@ struct RuleConst {
 };
 __device__ __constant__ RuleConst d_rule_tri;
 __device__ __constant__ RuleConst d_rule_quad;
+__device__ double2 d_sincos_tab[SINCOS_TAB];  // (cos, sin)(i*pi/64), filled by upload_tables()
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -58,6 +61,7 @@ far_kernel(const double* __restrict__ far_k, const double* __restrict__ far_c, c
            double wavruim, double k2, double cH, double beta_re, double beta_im, cplx* __restrict__ A, uint64_t lda,
            uint2* __restrict__ near_list, unsigned int near_cap, unsigned int* __restrict__ near_count) {
     __shared__ __align__(128) double sm_k[NQ * TILE];  // kappa_q, [q][column]
+    __shared__ __align__(16) double2 sm_tab[SINCOS_TAB];
     __shared__ __align__(8) unsigned long long mbar;
 
     const uint32_t t = threadIdx.x;
@@ -71,6 +75,7 @@ far_kernel(const double* __restrict__ far_k, const double* __restrict__ far_c, c
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (t < SINCOS_TAB) sm_tab[t] = d_sincos_tab[t];
     __syncthreads();
 
     // Work item = (column tile, row chunk); a block owns a contiguous range of items, ordered so
@@ -173,7 +178,7 @@ far_kernel(const double* __restrict__ far_k, const double* __restrict__ far_c, c
             const double rho = fast_rsqrt(r2);  // 1/r
             const double r = r2 * rho;
             double sn, cs;
-            fast_sincos(wavruim * r, sn, cs);
+            fast_sincos_tab(wavruim * r, sm_tab, sn, cs);
             const double g = rho * rc.w[q];  // w / r   (J/(4 pi) is applied once per pair)
             const double zgr = g * cs, zgi = g * sn;
             const double m = (q == 0) ? M0 : fma(rc.a[q], E1, fma(rc.b[q], E2, M0));  // (y_q - x).n_x
@@ -229,6 +234,16 @@ cudaError_t upload_tables() {
     for (RuleConst* r : {&tri, &quad}) {
         for (int q = 0; q < NQ_MAX; ++q) { r->a2[q] = 2.0 * r->a[q]; r->b2[q] = 2.0 * r->b[q]; }
         r->ac2 = 2.0 * r->ac; r->bc2 = 2.0 * r->bc;
+    }
+    {
+        double2 tab[SINCOS_TAB];
+        for (int i = 0; i < SINCOS_TAB; ++i) {
+            const double ang = (double)i * (PI / 64.0);
+            tab[i] = make_double2(std::cos(ang), std::sin(ang));
+        }
+        tab[0] = make_double2(1.0, 0.0); tab[32] = make_double2(0.0, 1.0); tab[64] = make_double2(-1.0, 0.0); tab[96] = make_double2(0.0, -1.0);
+        e = cudaMemcpyToSymbol(d_sincos_tab, tab, sizeof tab);
+        if (e != cudaSuccess) return e;
     }
     e = cudaMemcpyToSymbol(d_rule_tri, &tri, sizeof tri);
     if (e != cudaSuccess) return e;

@@ -89,6 +89,29 @@ __device__ __forceinline__ void fast_sincos(double x, double& s_out, double& c_o
     c_out = cc;
 }
 
+// Table variant for the far kernel: reduction by pi/64 against a 128-entry (cos, sin) table held in
+// shared memory, degree-6/7 Taylor kernels on |t| <= pi/128 (truncation < 1e-17) and one complex
+// rotation: 16 DP-pipe instructions, no quadrant selects.  tab[i] = (cos(i*pi/64), sin(i*pi/64)).
+constexpr int SINCOS_TAB = 128;
+__device__ __forceinline__ void fast_sincos_tab(double x, const double2* __restrict__ tab, double& s_out, double& c_out) {
+    const double MAGIC = 6755399441055744.0;
+    double tq = fma(x, 20.371832715762604, MAGIC);  // 64/pi
+    const int idx = __double2loint(tq) & (SINCOS_TAB - 1);
+    const double q = tq - MAGIC;
+    double t = fma(-q, 0.04908738521234052, x);     // pi/64 hi
+    t = fma(-q, 1.9135106236677394e-18, t);         // pi/64 lo
+    const double z = t * t;
+    double ps = fma(z, -1.9841269841269841e-04, 8.3333333333333332e-03);  // -1/5040, 1/120
+    double pc = fma(z, -1.3888888888888889e-03, 4.1666666666666664e-02);  // -1/720, 1/24
+    ps = fma(z, ps, -1.6666666666666666e-01);
+    pc = fma(z, pc, -0.5);
+    const double sn = fma(t * z, ps, t);
+    const double cs = fma(z, pc, 1.0);
+    const double2 CS = tab[idx];
+    c_out = fma(CS.x, cs, -(CS.y * sn));
+    s_out = fma(CS.y, cs, CS.x * sn);
+}
+
 // 1/sqrt(a) to ~1 ulp: MUFU.RSQ64H seed + one cubically convergent step (5 DP ops)
 __device__ __forceinline__ double fast_rsqrt(double a) {
     double y;

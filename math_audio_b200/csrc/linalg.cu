@@ -759,6 +759,13 @@ __device__ __forceinline__ void atomic_max_pos(double* addr, double v) {
     atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
 }
 __global__ void math_selftest_kernel(uint64_t n, double xmax, double* err) {
+    __shared__ double2 tab[SINCOS_TAB];
+    for (int i = threadIdx.x; i < SINCOS_TAB; i += blockDim.x) {
+        double sv, cv;
+        sincospi((double)i / 64.0, &sv, &cv);
+        tab[i] = make_double2(cv, sv);
+    }
+    __syncthreads();
     double e_sc = 0.0, e_rs = 0.0;
     for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
         // low-discrepancy sample of [0, xmax]
@@ -769,6 +776,10 @@ __global__ void math_selftest_kernel(uint64_t n, double xmax, double* err) {
         sincos(x, &s, &c);
         fast_sincos(x, fs, fc);
         e_sc = fmax(e_sc, fmax(fabs(fs - s), fabs(fc - c)));
+        fast_sincos_tab(x, tab, fs, fc);   // the far kernel's variant
+        e_sc = fmax(e_sc, fmax(fabs(fs - s), fabs(fc - c)));
+        fast_sincos_tab(-x, tab, fs, fc);  // harmonic_factor = -1
+        e_sc = fmax(e_sc, fmax(fabs(fs + s), fabs(fc - c)));
         double a = x * x + 1e-12;
         double ref = 1.0 / sqrt(a);
         e_rs = fmax(e_rs, fabs(fast_rsqrt(a) - ref) / ref);
