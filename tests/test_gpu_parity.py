@@ -339,6 +339,39 @@ def test_incident_rhs_and_field_evaluation_on_device(bem, orc):
             assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-12
 
 
+def test_sweep_driver_equals_sequential(bem):
+    """The pipelined frequency sweep (assembly of f+1 on a second stream underneath the solve of f,
+    persistent 'background' far kernel) must give the results of the plain sequential calls."""
+    from math_audio_b200.incident import IncidentField
+    from math_audio_b200.sweep import SweepDriver
+
+    a = 0.1
+    mesh = generate_icosphere_mesh(a, 3)
+    inc = IncidentField.plane_wave_z()
+    cfg = bem.GmresConfig(max_iterations=1000, restart=50, tolerance=1e-10)
+    cases = []
+    for ka in (0.3, 1.0, 2.5, 6.0, 0.7):
+        ph = PhysicsParams.from_wave_number(ka / a)
+        cases.append((ph, ph.burton_miller_beta_adaptive(a)[0]))
+    ref = []
+    for ph, beta in cases:
+        system = bem.build_tbem_system_with_beta(mesh, ph, beta)
+        b = system.rhs + inc.compute_rhs_with_beta(mesh.center, mesh.normal, ph, beta)
+        ref.append((system.matrix.rows(), bem.gmres(bem.DenseOperator(system), b, cfg)))
+    for overlap in (True, False):
+        driver = SweepDriver(mesh, overlap=overlap, background_blocks_per_sm=1)
+
+        def solve(i, system, op):
+            ph, beta = cases[i]
+            b = system.rhs_full() + inc.compute_rhs_with_beta(mesh.center, mesh.normal, ph, beta)
+            return system.matrix.rows(), bem.gmres(op, b, cfg)
+
+        out = driver.run(cases, cfg, solve)
+        for (A0, s0), (A1, s1) in zip(ref, out):
+            assert (A0 == A1).all()  # same kernels, same bits (the background grid only changes the schedule)
+            assert (s0.iterations, s0.restarts) == (s1.iterations, s1.restarts) and (s0.x == s1.x).all()
+
+
 def test_gmres_preconditioned(bem, orc):
     """gmres_preconditioned (gmres.rs:282-585) with the identity and the Jacobi preconditioner on an
     assembled BEM matrix and on the reference's tridiagonal KAT."""
