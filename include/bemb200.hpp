@@ -1,0 +1,322 @@
+// bemb200.hpp -- C++17 host-side mirror of the reference's operator interface for the dense
+// TBEM assemble + GMRES path, over the C ABI of bemb200.h (header only, no CUDA/torch types).
+//
+// The reference is Rust; where its toolchain is absent this header plays the role of the Rust
+// shim (rust/bem-b200-sys): same names, argument meaning and error behaviour as
+//   math-bem/src/core/types.rs:16-351            PhysicsParams, ElementType, BoundaryCondition, Element
+//   math-bem/src/core/assembly/tbem.rs:13-101    TbemSystem, build_tbem_system{,_with_beta,_scaled,_bounded}
+//   math-bem/src/core/assembly/tbem.rs:500-534   apply_row_sum_correction
+//   math-bem/src/core/solver/fmm_interface.rs:25-52,378-384  DenseOperator, solve_gmres
+//   math-solvers/src/traits.rs:316-385           LinearOperator, IdentityPreconditioner
+//   math-solvers/src/preconditioners/diagonal.rs DiagonalPreconditioner
+//   math-solvers/src/iterative/gmres.rs:16-585   GmresConfig, GmresSolution, gmres, gmres_with_guess,
+//                                                gmres_preconditioned{,_with_guess}
+// Shape mismatches throw std::invalid_argument (the reference panics); library failures throw
+// bemb200::Error carrying the BEMB200_E* code and bemb200_last_error().
+#pragma once
+#include <cmath>
+#include <complex>
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "bemb200.h"
+
+namespace bemb200 {
+
+using Complex64 = std::complex<double>;
+static_assert(sizeof(Complex64) == 2 * sizeof(double), "std::complex<double> must be two doubles");
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error("libbemb200 error " + std::to_string(c) + ": " + m), code(c) {}
+};
+inline void check(int rc, const bemb200_ctx* ctx = nullptr) {
+    if (rc != BEMB200_OK) {
+        const char* m = bemb200_last_error(ctx);
+        if ((!m || !*m) && ctx) m = bemb200_last_error(nullptr);
+        throw Error(rc, m ? m : "");
+    }
+}
+
+// ---- types.rs -------------------------------------------------------------------------------
+struct PhysicsParams {  // types.rs:16-58
+    double speed_of_sound, density, frequency, wave_number, omega, wave_length, harmonic_factor, pressure_factor, tau;
+    PhysicsParams(double frequency_, double speed_of_sound_, double density_, bool is_internal)
+        : speed_of_sound(speed_of_sound_), density(density_), frequency(frequency_) {
+        const double PI = 3.14159265358979323846264338327950288;
+        omega = 2.0 * PI * frequency;
+        wave_number = omega / speed_of_sound;
+        wave_length = speed_of_sound / frequency;
+        harmonic_factor = 1.0;
+        pressure_factor = density * omega * harmonic_factor;
+        tau = is_internal ? -1.0 : 1.0;
+    }
+    double gamma() const { return 1.0; }  // types.rs:216-218
+    Complex64 burton_miller_beta() const { return tau > 0.0 ? Complex64(0.0, harmonic_factor / wave_number) : Complex64(0.0, 0.0); }
+    Complex64 burton_miller_beta_scaled(double scale) const {
+        return tau > 0.0 ? Complex64(0.0, harmonic_factor * scale / wave_number) : Complex64(0.0, 0.0);
+    }
+    Complex64 burton_miller_beta_optimal(double element_size) const {
+        return tau > 0.0 ? Complex64(0.0, harmonic_factor / (wave_number + 1.0 / element_size)) : Complex64(0.0, 0.0);
+    }
+    std::pair<Complex64, double> burton_miller_beta_adaptive(double radius) const {  // types.rs:173-195
+        if (tau <= 0.0) return {Complex64(0.0, 0.0), 1.0};
+        const double ka = wave_number * radius;
+        const double scale = ka < 0.5 ? 1.0 : (ka < 1.2 ? 4.0 : (ka < 1.8 ? 8.0 : 16.0));
+        return {Complex64(0.0, harmonic_factor * scale / wave_number), scale};
+    }
+};
+
+enum class ElementType { Tri3, Quad4 };
+enum class ElementProperty { Surface = 0, MidFace = 1, Evaluation = 2 };
+
+struct BoundaryCondition {  // types.rs:267-292 (the variants the assembly distinguishes, tbem.rs:234-244)
+    enum Kind { Velocity, Pressure, VelocityWithAdmittance, TransferAdmittance, TransferWithSurfaceAdmittance } kind = Velocity;
+    std::vector<Complex64> values{Complex64(0.0, 0.0)};
+    static BoundaryCondition velocity(std::vector<Complex64> v) { return {Velocity, std::move(v)}; }
+    static BoundaryCondition pressure(std::vector<Complex64> p) { return {Pressure, std::move(p)}; }
+};
+
+struct Element {  // types.rs:329-351
+    std::vector<std::size_t> connectivity;
+    ElementType element_type = ElementType::Tri3;
+    ElementProperty property = ElementProperty::Surface;
+    double normal[3] = {0, 0, 0};
+    double center[3] = {0, 0, 0};
+    double area = 0.0;
+    BoundaryCondition boundary_condition;
+    std::size_t group = 0;
+    std::vector<std::size_t> dof_addresses;
+};
+
+// ---- device context -----------------------------------------------------------------------------
+class Context {
+public:
+    explicit Context(int device = 0) { check(bemb200_ctx_create(device, &h_)); }
+    Context(int device, int rank, int nranks, const uint8_t* nccl_id, void* cuda_stream = nullptr) {
+        check(bemb200_ctx_create_ex(device, rank, nranks, nccl_id, cuda_stream, &h_));
+    }
+    ~Context() { bemb200_ctx_destroy(h_); }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    bemb200_ctx* handle() const { return h_; }
+
+private:
+    bemb200_ctx* h_ = nullptr;
+};
+
+// ---- LinearOperator / DenseOperator -----------------------------------------------------------------
+struct LinearOperator {  // math-solvers/src/traits.rs:316-364
+    virtual ~LinearOperator() = default;
+    virtual std::size_t num_rows() const = 0;
+    virtual std::size_t num_cols() const = 0;
+    virtual std::vector<Complex64> apply(const std::vector<Complex64>& x) const = 0;
+    virtual std::vector<Complex64> apply_transpose(const std::vector<Complex64>& x) const = 0;
+    virtual std::vector<Complex64> apply_hermitian(const std::vector<Complex64>& x) const {  // traits.rs:331-358
+        std::vector<Complex64> xc(x.size());
+        for (std::size_t i = 0; i < x.size(); ++i) xc[i] = std::conj(x[i]);
+        std::vector<Complex64> y = apply_transpose(xc);
+        for (auto& v : y) v = std::conj(v);
+        return y;
+    }
+    bool is_square() const { return num_rows() == num_cols(); }
+};
+
+class DenseOperator : public LinearOperator {  // fmm_interface.rs:25-52, device resident
+public:
+    // DenseOperator::new(matrix): row-major n_rows x n_cols host matrix
+    DenseOperator(const Context& ctx, const std::vector<Complex64>& matrix, std::size_t n_rows, std::size_t n_cols) : ctx_(&ctx) {
+        if (matrix.size() != n_rows * n_cols) throw std::invalid_argument("DenseOperator: matrix size does not match its shape");
+        check(bemb200_matrix_from_host(ctx.handle(), reinterpret_cast<const double*>(matrix.data()), n_rows, n_cols, 0, n_rows, &m_),
+              ctx.handle());
+    }
+    DenseOperator(const Context& ctx, bemb200_matrix* owned) : ctx_(&ctx), m_(owned) {}
+    ~DenseOperator() override { bemb200_matrix_free(m_); }
+    DenseOperator(const DenseOperator&) = delete;
+    DenseOperator& operator=(const DenseOperator&) = delete;
+    std::size_t num_rows() const override { return bemb200_num_rows(m_); }
+    std::size_t num_cols() const override { return bemb200_num_cols(m_); }
+    std::vector<Complex64> apply(const std::vector<Complex64>& x) const override {
+        if (x.size() != num_cols()) throw std::invalid_argument("apply: vector length does not match num_cols");
+        std::vector<Complex64> y(num_rows());
+        check(bemb200_apply(m_, reinterpret_cast<const double*>(x.data()), reinterpret_cast<double*>(y.data())), ctx_->handle());
+        return y;
+    }
+    std::vector<Complex64> apply_transpose(const std::vector<Complex64>& x) const override {
+        if (x.size() != num_rows()) throw std::invalid_argument("apply_transpose: vector length does not match num_rows");
+        std::vector<Complex64> y(num_cols());
+        check(bemb200_apply_transpose(m_, reinterpret_cast<const double*>(x.data()), reinterpret_cast<double*>(y.data())),
+              ctx_->handle());
+        return y;
+    }
+    std::vector<Complex64> rows(std::size_t row_begin, std::size_t row_end) const {  // device matrix -> host (row block)
+        std::vector<Complex64> out((row_end - row_begin) * num_cols());
+        check(bemb200_matrix_download(m_, row_begin, row_end, reinterpret_cast<double*>(out.data())), ctx_->handle());
+        return out;
+    }
+    std::vector<Complex64> diagonal() const {
+        std::vector<Complex64> d(num_rows());
+        check(bemb200_matrix_diagonal(m_, reinterpret_cast<double*>(d.data())), ctx_->handle());
+        return d;
+    }
+    bemb200_matrix* handle() const { return m_; }
+    const Context& context() const { return *ctx_; }
+
+private:
+    const Context* ctx_;
+    bemb200_matrix* m_ = nullptr;
+};
+
+// ---- TbemSystem / assembly ---------------------------------------------------------------------------
+struct TbemSystem {  // tbem.rs:13-20; the matrix stays on the device behind the operator
+    std::unique_ptr<DenseOperator> matrix;
+    std::vector<Complex64> rhs;
+    std::size_t num_dofs = 0;
+};
+
+// `nodes`: n_nodes x 3 row-major (Array2<f64>)
+inline TbemSystem build_tbem_system_with_beta(const Context& ctx, const std::vector<Element>& elements,
+                                              const std::vector<double>& nodes, const PhysicsParams& physics, Complex64 beta) {
+    const std::size_t n = elements.size();
+    std::vector<uint32_t> conn(4 * n, 0xFFFFFFFFu), dof(n, 0);
+    std::vector<uint8_t> etype(n), bc_len(n, 1), is_eval(n, 0);
+    std::vector<double> center(3 * n), normal(3 * n), area(n), bc_val(8 * n, 0.0);
+    std::vector<int32_t> bc_type(n, 0);
+    std::size_t ndof = 0;
+    for (std::size_t i = 0; i < n; ++i) {
+        const Element& e = elements[i];
+        etype[i] = e.element_type == ElementType::Tri3 ? 3 : 4;
+        if (e.connectivity.size() != etype[i]) throw std::invalid_argument("element connectivity does not match its type");
+        for (std::size_t v = 0; v < e.connectivity.size(); ++v) conn[4 * i + v] = static_cast<uint32_t>(e.connectivity[v]);
+        for (int d = 0; d < 3; ++d) { center[3 * i + d] = e.center[d]; normal[3 * i + d] = e.normal[d]; }
+        area[i] = e.area;
+        // get_bc_type_and_value(): tbem.rs:234-244
+        const BoundaryCondition& bc = e.boundary_condition;
+        std::vector<Complex64> vals;
+        switch (bc.kind) {
+            case BoundaryCondition::Velocity: case BoundaryCondition::VelocityWithAdmittance: bc_type[i] = 0; vals = bc.values; break;
+            case BoundaryCondition::Pressure: bc_type[i] = 1; vals = bc.values; break;
+            default: bc_type[i] = 2; vals = {Complex64(0.0, 0.0)}; break;
+        }
+        if (vals.empty() || vals.size() > 4) throw std::invalid_argument("boundary condition needs 1..4 values");
+        bc_len[i] = static_cast<uint8_t>(vals.size());
+        for (std::size_t k = 0; k < vals.size(); ++k) { bc_val[8 * i + 2 * k] = vals[k].real(); bc_val[8 * i + 2 * k + 1] = vals[k].imag(); }
+        is_eval[i] = e.property == ElementProperty::Evaluation;
+        if (!is_eval[i]) {
+            if (e.dof_addresses.empty()) throw std::invalid_argument("boundary element without dof address");
+            dof[i] = static_cast<uint32_t>(e.dof_addresses[0]);
+            ++ndof;
+        }
+    }
+    bemb200_mesh mesh{nodes.size() / 3, n, nodes.data(), conn.data(), etype.data(), center.data(), normal.data(), area.data(),
+                      bc_type.data(), bc_len.data(), bc_val.data(), dof.data(), is_eval.data()};
+    bemb200_physics phys{physics.wave_number, physics.harmonic_factor, physics.tau, physics.gamma()};
+    bemb200_matrix* m = nullptr;
+    check(bemb200_assemble(ctx.handle(), &mesh, &phys, beta.real(), beta.imag(), 0, ndof, &m), ctx.handle());
+    TbemSystem sys;
+    sys.matrix = std::make_unique<DenseOperator>(ctx, m);
+    sys.num_dofs = ndof;
+    sys.rhs.resize(ndof);
+    check(bemb200_rhs_download_full(m, reinterpret_cast<double*>(sys.rhs.data())), ctx.handle());
+    return sys;
+}
+inline TbemSystem build_tbem_system(const Context& ctx, const std::vector<Element>& el, const std::vector<double>& nodes,
+                                    const PhysicsParams& ph) {  // tbem.rs:45-51
+    return build_tbem_system_with_beta(ctx, el, nodes, ph, ph.burton_miller_beta());
+}
+inline TbemSystem build_tbem_system_scaled(const Context& ctx, const std::vector<Element>& el, const std::vector<double>& nodes,
+                                           const PhysicsParams& ph, double scale) {  // tbem.rs:85-93
+    return build_tbem_system_with_beta(ctx, el, nodes, ph, ph.burton_miller_beta_scaled(scale));
+}
+inline TbemSystem build_tbem_system_bounded(const Context& ctx, const std::vector<Element>& el, const std::vector<double>& nodes,
+                                            const PhysicsParams& ph, double avg_element_size) {  // tbem.rs:64-72
+    return build_tbem_system_with_beta(ctx, el, nodes, ph, ph.burton_miller_beta_optimal(avg_element_size));
+}
+inline double apply_row_sum_correction(TbemSystem& system) {  // tbem.rs:500-520
+    double avg = 0.0;
+    check(bemb200_row_sum_correction(system.matrix->handle(), &avg), system.matrix->context().handle());
+    return avg;
+}
+
+// ---- GMRES -------------------------------------------------------------------------------------------------
+struct GmresConfig {  // gmres.rs:16-36
+    std::size_t max_iterations = 100;  // restart cycles
+    std::size_t restart = 30;
+    double tolerance = 1e-6;
+    std::size_t print_interval = 0;
+};
+struct GmresSolution {  // gmres.rs:74-85
+    std::vector<Complex64> x;
+    std::size_t iterations = 0, restarts = 0;
+    double residual = 0.0;
+    bool converged = false;
+};
+inline GmresSolution gmres_with_guess(const DenseOperator& op, const std::vector<Complex64>& b, const std::vector<Complex64>* x0,
+                                      const GmresConfig& config) {  // gmres.rs:105
+    if (b.size() != op.num_rows() || (x0 && x0->size() != b.size())) throw std::invalid_argument("gmres: vector lengths must match");
+    GmresSolution s;
+    s.x.resize(b.size());
+    bemb200_gmres_info info{};
+    check(bemb200_gmres(op.handle(), reinterpret_cast<const double*>(b.data()), x0 ? reinterpret_cast<const double*>(x0->data()) : nullptr,
+                        static_cast<uint32_t>(config.max_iterations), static_cast<uint32_t>(config.restart), config.tolerance,
+                        reinterpret_cast<double*>(s.x.data()), &info),
+          op.context().handle());
+    s.iterations = info.iterations; s.restarts = info.restarts; s.residual = info.residual; s.converged = info.converged != 0;
+    return s;
+}
+inline GmresSolution gmres(const DenseOperator& op, const std::vector<Complex64>& b, const GmresConfig& config) {  // gmres.rs:96
+    return gmres_with_guess(op, b, nullptr, config);
+}
+inline GmresSolution solve_gmres(const DenseOperator& op, const std::vector<Complex64>& b, const GmresConfig& config) {
+    return gmres(op, b, config);  // fmm_interface.rs:378-384
+}
+
+struct IdentityPreconditioner {};  // traits.rs:377-385
+struct DiagonalPreconditioner {    // preconditioners/diagonal.rs:20-58
+    std::vector<Complex64> inv_diag;
+    static DiagonalPreconditioner from_diagonal(const std::vector<Complex64>& diag) {
+        DiagonalPreconditioner p;
+        p.inv_diag.resize(diag.size());
+        for (std::size_t i = 0; i < diag.size(); ++i) {
+            const double re = diag[i].real(), im = diag[i].imag(), ns = re * re + im * im;
+            p.inv_diag[i] = std::hypot(re, im) > 1e-30 ? Complex64(re / ns, -im / ns) : Complex64(1.0, 0.0);
+        }
+        return p;
+    }
+};
+inline GmresSolution gmres_preconditioned_impl(const DenseOperator& op, const std::vector<Complex64>* inv_diag,
+                                               const std::vector<Complex64>& b, const std::vector<Complex64>* x0,
+                                               const GmresConfig& config) {
+    if (b.size() != op.num_rows() || (x0 && x0->size() != b.size()) || (inv_diag && inv_diag->size() != b.size()))
+        throw std::invalid_argument("gmres_preconditioned: vector lengths must match");
+    GmresSolution s;
+    s.x.resize(b.size());
+    bemb200_gmres_info info{};
+    check(bemb200_gmres_preconditioned(op.handle(), inv_diag ? reinterpret_cast<const double*>(inv_diag->data()) : nullptr,
+                                       reinterpret_cast<const double*>(b.data()),
+                                       x0 ? reinterpret_cast<const double*>(x0->data()) : nullptr,
+                                       static_cast<uint32_t>(config.max_iterations), static_cast<uint32_t>(config.restart),
+                                       config.tolerance, reinterpret_cast<double*>(s.x.data()), &info),
+          op.context().handle());
+    s.iterations = info.iterations; s.restarts = info.restarts; s.residual = info.residual; s.converged = info.converged != 0;
+    return s;
+}
+inline GmresSolution gmres_preconditioned(const DenseOperator& op, const IdentityPreconditioner&, const std::vector<Complex64>& b,
+                                          const GmresConfig& config) {  // gmres.rs:282
+    return gmres_preconditioned_impl(op, nullptr, b, nullptr, config);
+}
+inline GmresSolution gmres_preconditioned(const DenseOperator& op, const DiagonalPreconditioner& p, const std::vector<Complex64>& b,
+                                          const GmresConfig& config) {
+    return gmres_preconditioned_impl(op, &p.inv_diag, b, nullptr, config);
+}
+inline GmresSolution gmres_preconditioned_with_guess(const DenseOperator& op, const DiagonalPreconditioner& p,
+                                                     const std::vector<Complex64>& b, const std::vector<Complex64>* x0,
+                                                     const GmresConfig& config) {  // gmres.rs:434
+    return gmres_preconditioned_impl(op, &p.inv_diag, b, x0, config);
+}
+
+}  // namespace bemb200

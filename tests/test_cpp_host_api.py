@@ -1,0 +1,36 @@
+"""The C++ host-side mirror of the reference API (include/bemb200.hpp): compiles on CPU (header
+self-consistency, links against libbemb200.so) and, on a B200, runs the C++ tests that restate
+the reference's own tests and check parity against the oracle."""
+import subprocess
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+SRC = ROOT / "tests" / "cpp" / "test_host_api.cpp"
+
+
+def _build(tmp_path, orc):
+    from math_audio_b200 import _capi
+
+    orc.build()
+    exe = tmp_path / "test_host_api"
+    libdir = _capi.LIB_PATH.parent
+    odir = ROOT / "oracle" / "_build"
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-I", str(ROOT / "include"), str(SRC), "-o", str(exe),
+           f"-L{libdir}", "-lbemb200", f"-L{odir}", "-lbem_oracle", f"-Wl,-rpath,{libdir}", f"-Wl,-rpath,{odir}",
+           "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"]
+    subprocess.run(cmd, check=True)
+    return exe
+
+
+def test_cpp_header_compiles_and_links(tmp_path, orc):
+    exe = _build(tmp_path, orc)
+    assert exe.exists()
+
+
+@pytest.mark.gpu
+def test_cpp_host_api_on_gpu(tmp_path, orc):
+    exe = _build(tmp_path, orc)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True, timeout=300)
+    assert "PASS" in out.stdout, out.stdout + out.stderr
