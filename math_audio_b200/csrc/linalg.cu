@@ -27,7 +27,6 @@ namespace {
 // RB rows from registers, 2x unrolled => RB*2 independent 16-byte loads in flight per thread.
 // ------------------------------------------------------------------------------------------
 constexpr int GEMV_THREADS = 256;
-constexpr int GEMV_RB = 4;
 
 __device__ __forceinline__ double2 ld_stream(const cplx* p) { return __ldcs(reinterpret_cast<const double2*>(p)); }
 __device__ __forceinline__ double2 ld_ro(const cplx* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
@@ -39,6 +38,7 @@ __device__ __forceinline__ void cfma(double& are, double& aim, double2 a, double
     aim = fma(a.y, x.x, aim);
 }
 
+template <int GEMV_RB, int GEMV_U>
 __global__ void __launch_bounds__(GEMV_THREADS)
 zgemv_kernel(const cplx* __restrict__ A, uint64_t lda, uint64_t nrows, uint64_t ncols, const cplx* __restrict__ x,
              cplx* __restrict__ y) {
@@ -54,21 +54,20 @@ zgemv_kernel(const cplx* __restrict__ A, uint64_t lda, uint64_t nrows, uint64_t 
             rowp[r] = A + row * lda;
         }
         uint64_t c = tid;
-        for (; c + GEMV_THREADS < ncols; c += 2 * GEMV_THREADS) {
-            double2 a0[GEMV_RB], a1[GEMV_RB];
+        for (; c + (GEMV_U - 1) * GEMV_THREADS < ncols; c += GEMV_U * GEMV_THREADS) {
+            double2 a[GEMV_RB][GEMV_U], xv[GEMV_U];
 #pragma unroll
-            for (int r = 0; r < GEMV_RB; ++r) {
-                a0[r] = ld_stream(rowp[r] + c);
-                a1[r] = ld_stream(rowp[r] + c + GEMV_THREADS);
-            }
-            const double2 x0 = ld_ro(x + c), x1 = ld_ro(x + c + GEMV_THREADS);
+            for (int u = 0; u < GEMV_U; ++u) {
 #pragma unroll
-            for (int r = 0; r < GEMV_RB; ++r) {
-                cfma(are[r], aim[r], a0[r], x0);
-                cfma(are[r], aim[r], a1[r], x1);
+                for (int r = 0; r < GEMV_RB; ++r) a[r][u] = ld_stream(rowp[r] + c + u * GEMV_THREADS);
+                xv[u] = ld_ro(x + c + u * GEMV_THREADS);
             }
+#pragma unroll
+            for (int u = 0; u < GEMV_U; ++u)
+#pragma unroll
+                for (int r = 0; r < GEMV_RB; ++r) cfma(are[r], aim[r], a[r][u], xv[u]);
         }
-        if (c < ncols) {
+        for (; c < ncols; c += GEMV_THREADS) {
             const double2 x0 = ld_ro(x + c);
 #pragma unroll
             for (int r = 0; r < GEMV_RB; ++r) cfma(are[r], aim[r], ld_stream(rowp[r] + c), x0);
@@ -809,10 +808,16 @@ cudaError_t launch_cluster(Kern kern, int cluster, int threads, size_t smem, cud
 
 cudaError_t launch_zgemv(const cplx* A, uint64_t lda, uint64_t nrows, uint64_t ncols, const cplx* x, cplx* y, cudaStream_t s) {
     if (nrows == 0) return cudaSuccess;
-    uint64_t blocks = (nrows + GEMV_RB - 1) / GEMV_RB;
+    static const int variant = []() { const char* v = std::getenv("BEMB200_GEMV_VARIANT"); return v ? std::atoi(v) : 24; }();
+    const int rb = variant / 10, u = variant % 10;
+    uint64_t blocks = (nrows + rb - 1) / rb;
     const uint64_t maxb = 148ull * 8ull * 8ull;
     if (blocks > maxb) blocks = maxb;
-    zgemv_kernel<<<(unsigned)blocks, GEMV_THREADS, 0, s>>>(A, lda, nrows, ncols, x, y);
+#define GEMV_CASE(R, U) \
+    if (rb == R && u == U) { zgemv_kernel<R, U><<<(unsigned)blocks, GEMV_THREADS, 0, s>>>(A, lda, nrows, ncols, x, y); return cudaGetLastError(); }
+    GEMV_CASE(4, 2) GEMV_CASE(2, 2)
+#undef GEMV_CASE
+    zgemv_kernel<2, 4><<<(unsigned)blocks, GEMV_THREADS, 0, s>>>(A, lda, nrows, ncols, x, y);
     return cudaGetLastError();
 }
 
