@@ -96,6 +96,10 @@ void bemb200_ctx_destroy(bemb200_ctx* ctx);
  * persistent grid of 148*blocks_per_sm blocks that leaves registers/shared memory to kernels of
  * other streams (assembly of frequency f+1 underneath the solve of frequency f); 0 = normal. */
 int bemb200_ctx_set_background(bemb200_ctx* ctx, int blocks_per_sm);
+/* shared != 0 tells the SOLVER of this context that kernels of other streams run beside it (the
+ * background assembly above): the Gram-Schmidt step then uses its 16-CTA cluster kernel instead
+ * of the whole-GPU cooperative kernel, whose grid barriers stall behind foreign warps. */
+int bemb200_ctx_set_shared_gpu(bemb200_ctx* ctx, int shared);
 /* Hand a matrix to another context of the SAME device (e.g. a solve context with its own stream
  * while an assembly context fills the next matrix of a frequency sweep).  The caller orders the
  * use of one matrix by the two contexts. */

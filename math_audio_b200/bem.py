@@ -70,6 +70,10 @@ class Context:
     def set_background(self, blocks_per_sm: int) -> None:
         _capi.check(self._lib.bemb200_ctx_set_background(self._h, blocks_per_sm), self._h)
 
+    def set_shared_gpu(self, shared: bool) -> None:
+        """Tell this context's solver that other streams share the GPU (no whole-GPU cooperative kernels)."""
+        _capi.check(self._lib.bemb200_ctx_set_shared_gpu(self._h, 1 if shared else 0), self._h)
+
     def measure_allgather(self, bytes_per_rank: int, iters: int = 200, sync_each: bool = False) -> float:
         t = C.c_double()
         _capi.check(self._lib.bemb200_measure_allgather(self._h, bytes_per_rank, iters, 1 if sync_each else 0, C.byref(t)), self._h)

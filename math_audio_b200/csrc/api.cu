@@ -508,6 +508,12 @@ int bemb200_ctx_set_background(bemb200_ctx* ctx, int blocks_per_sm) {
     return BEMB200_OK;
 }
 
+int bemb200_ctx_set_shared_gpu(bemb200_ctx* ctx, int shared) {
+    if (!ctx) return set_error(ctx, BEMB200_EINVAL, "NULL context");
+    ctx->shared_gpu.store(shared ? 1 : 0);
+    return BEMB200_OK;
+}
+
 int bemb200_matrix_set_context(bemb200_matrix* m, bemb200_ctx* ctx) {
     if (!m || !ctx) return set_error(ctx, BEMB200_EINVAL, "NULL argument");
     if (ctx->device != m->ctx->device || ctx->nranks != m->ctx->nranks || ctx->rank != m->ctx->rank)

@@ -14,6 +14,7 @@ struct bemb200_ctx {
     int rank = 0, nranks = 1;
     cudaStream_t stream = nullptr;
     bool own_stream = true;
+    std::atomic<int> shared_gpu{0};  // != 0: another stream shares the GPU -> solver avoids whole-GPU cooperative kernels
     std::atomic<int> background_blocks_per_sm{0};  // > 0: assembly kernels use a small persistent grid (sweep pipelining)
     void* nccl_comm = nullptr;  // ncclComm_t when nranks > 1
     std::string err;

@@ -84,7 +84,7 @@ static int ensure_workspace(bemb200_matrix* m, uint32_t restart) {
     ws->ldh_slot = restart + 2;
     BEMB_CUDA(ctx, cudaMalloc((void**)&ws->hcol_d, (size_t)(restart + 1) * ws->ldh_slot * sizeof(cplx)));
     BEMB_CUDA(ctx, cudaMalloc((void**)&ws->ycoef_d, (restart + 2) * sizeof(cplx)));
-    BEMB_CUDA(ctx, cudaMalloc((void**)&ws->lmat_d, (size_t)(restart + 1) * (restart + 1) * sizeof(cplx)));
+    BEMB_CUDA(ctx, cudaMalloc((void**)&ws->lmat_d, ((size_t)(restart + 1) * (restart + 1) + mgs_scratch_elems()) * sizeof(cplx)));
     BEMB_CUDA(ctx, cudaMalloc((void**)&ws->scal_d, 4 * sizeof(double)));
     BEMB_CUDA(ctx, cudaMallocHost((void**)&ws->hcol_h, (size_t)(restart + 1) * ws->ldh_slot * sizeof(cplx)));
     ws->it_ev0.resize(restart + 1); ws->it_ev1.resize(restart + 1); ws->it_done.resize(restart + 1);
@@ -237,11 +237,15 @@ static int gmres_core(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t max_it
                 if (rc2 != BEMB200_OK) return rc2;
             }
             cplx* hd = ws->hcol_d + (size_t)j * ws->ldh_slot;
+            bool wrote_host = false;
             BEMB_CUDA(ctx, launch_mgs(ws->V, ws->npad, ws->w, j, n, hd, ws->V + (uint64_t)(j + 1) * ws->npad, pinv, direct_scale,
-                                      ws->lmat_d, (int)ws->restart + 1, s));
+                                      ws->lmat_d, (int)ws->restart + 1,
+                                      ws->lmat_d + (size_t)(ws->restart + 1) * (ws->restart + 1),
+                                      ws->hcol_h + (size_t)j * ws->ldh_slot, &wrote_host, ctx->shared_gpu.load() == 0, s));
             if (g_dbg_split) BEMB_CUDA(ctx, cudaEventRecord(ws->ev0, s));
-            BEMB_CUDA(ctx, cudaMemcpyAsync(ws->hcol_h + (size_t)j * ws->ldh_slot, hd, (j + 2) * sizeof(cplx),
-                                           cudaMemcpyDeviceToHost, s));
+            if (!wrote_host)
+                BEMB_CUDA(ctx, cudaMemcpyAsync(ws->hcol_h + (size_t)j * ws->ldh_slot, hd, (j + 2) * sizeof(cplx),
+                                               cudaMemcpyDeviceToHost, s));
             BEMB_CUDA(ctx, cudaEventRecord(ws->it_done[j], s));
             ws->launched[j] = 1;
             m->last_launches += 2;  // every launch counts, also a speculative iteration that ends up unused

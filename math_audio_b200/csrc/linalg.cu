@@ -242,7 +242,7 @@ template <int EPT>
 __global__ void __launch_bounds__(LS_THREADS)
 mgs_lowsync_kernel(const cplx* __restrict__ V, uint64_t ldv, const cplx* __restrict__ w, int j, uint64_t n, uint64_t S,
                    cplx* __restrict__ Lmat, int ldl, cplx* __restrict__ hcol, cplx* __restrict__ vnext, double breakdown_tol,
-                   const cplx* __restrict__ pinv, int direct_scale) {
+                   const cplx* __restrict__ pinv, int direct_scale, cplx* __restrict__ hcol_host) {
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ ClusterShared sh1;  // single-value all-reduce (norm)
     // dynamic layout: warp_part[LS_WARPS][2*LS_MAXV] | slots[MAX_CLUSTER][2*LS_MAXV] | a[LS_MAXV] | Ls[(j+1)*(j+1)]
@@ -347,7 +347,10 @@ mgs_lowsync_kernel(const cplx* __restrict__ V, uint64_t ldv, const cplx* __restr
             __syncwarp();
         }
         if (me == 0)
-            for (int l = lane; l < nv; l += 32) hcol[l] = avec[l];
+            for (int l = lane; l < nv; l += 32) {
+                hcol[l] = avec[l];
+                if (hcol_host) hcol_host[l] = avec[l];  // mapped pinned memory: the column lands on the host with the kernel
+            }
     }
     __syncthreads();
     // ---- pass 2: w -= sum_l h_l v_l ----------------------------------------------------------------
@@ -372,7 +375,10 @@ mgs_lowsync_kernel(const cplx* __restrict__ V, uint64_t ldv, const cplx* __restr
     for (int e = 0; e < EPT; ++e) acc.re = fma(wr[e].re, wr[e].re, fma(wr[e].im, wr[e].im, acc.re));
     const cplx nn = cluster_allreduce(acc, sh1, 0);
     const double nrm = sqrt(nn.re);
-    if (me == 0 && tid == 0) hcol[j + 1] = C(nrm, 0.0);
+    if (me == 0 && tid == 0) {
+        hcol[j + 1] = C(nrm, 0.0);
+        if (hcol_host) hcol_host[j + 1] = C(nrm, 0.0);
+    }
     if (!(nrm < breakdown_tol)) {
         const double inv = 1.0 / nrm;
         const double sc = inv - 1.0;
@@ -385,6 +391,224 @@ mgs_lowsync_kernel(const cplx* __restrict__ V, uint64_t ldv, const cplx* __restr
         }
     }
     cluster.sync();
+}
+
+// ------------------------------------------------------------------------------------------
+// Whole-GPU form of the low-synchronisation sweep: one CTA per SM (cooperative launch, two
+// grid barriers) instead of one 16-CTA cluster, so the two passes over V run at the bandwidth
+// of 148 SMs instead of 16.  Same algebra as mgs_lowsync_kernel; partial sums cross the grid
+// through a small global scratch and are added in fixed CTA order by every CTA (bit-identical
+// on every rank: the grid size depends on n only).
+// ------------------------------------------------------------------------------------------
+constexpr int GR_THREADS = 128;
+constexpr int GR_WARPS = GR_THREADS / 32;
+constexpr int GR_MAX_CTAS = 148;
+
+// 32 per-lane partial sums -> lane L ends up with the warp total of value L (31 exchanges
+// instead of 32 x 5; fixed order, so deterministic)
+__device__ __forceinline__ double warp_reduce32(double (&v)[32], int lane) {
+#pragma unroll
+    for (int off = 16, cnt = 16; off >= 1; off >>= 1, cnt >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < cnt; ++i) {
+            const double send = upper ? v[i] : v[i + cnt];
+            const double keep = upper ? v[i + cnt] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
+template <int EPT>
+__global__ void __launch_bounds__(GR_THREADS)
+mgs_grid_kernel(const cplx* __restrict__ V, uint64_t ldv, const cplx* __restrict__ w, int j, uint64_t n, uint64_t S,
+                cplx* __restrict__ Lmat, int ldl, cplx* __restrict__ hcol, cplx* __restrict__ vnext, double breakdown_tol,
+                const cplx* __restrict__ pinv, int direct_scale, cplx* __restrict__ part, double* __restrict__ npart,
+                cplx* __restrict__ hcol_host) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    // dynamic layout: warp_part[GR_WARPS][2*LS_MAXV] | a[LS_MAXV] | LsT[(j+1)*(j+1)]  (LsT[l*nv + k] = L_kl)
+    cplx* warp_part = reinterpret_cast<cplx*>(dyn);
+    cplx* avec = warp_part + GR_WARPS * 2 * LS_MAXV;
+    cplx* LsT = avec + LS_MAXV;
+    __shared__ double nred[GR_WARPS];
+    __shared__ double nrm_s;
+    cg::grid_group grid = cg::this_grid();
+    const unsigned G = gridDim.x, me = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nv = j + 1;
+    const uint64_t begin = (uint64_t)me * S;
+    const uint64_t end = begin + S < n ? begin + S : n;
+    const uint64_t len = end > begin ? end - begin : 0;
+
+    cplx wr[EPT], vj[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+        const uint64_t k = tid + (uint64_t)e * GR_THREADS;
+        wr[e] = k < len ? w[begin + k] : C(0, 0);
+        if (pinv && k < len) wr[e] = wr[e] * ldg_c(pinv + begin + k);
+        vj[e] = (k < len) ? ldg_c(V + (uint64_t)j * ldv + begin + k) : C(0, 0);
+    }
+    for (int idx = tid; idx < nv * nv; idx += GR_THREADS) {
+        const int l = idx / nv, k = idx - l * nv;
+        LsT[idx] = (l < k && k < j) ? Lmat[k * ldl + l] : C(0, 0);
+    }
+
+    // ---- pass 1: a_l = v_l^H w (l <= j), g_l = v_j^H v_l (l < j) over this CTA's rows ----------
+    for (int l0 = 0; l0 < nv; l0 += 8) {
+        double acc[32];  // [q]: a.re | [8+q]: a.im | [16+q]: g.re | [24+q]: g.im
+#pragma unroll
+        for (int q = 0; q < 32; ++q) acc[q] = 0.0;
+        cplx v[EPT][8];
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            const uint64_t k = tid + (uint64_t)e * GR_THREADS;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[e][q] = (l0 + q < nv && k < len) ? ldg_c(V + (uint64_t)(l0 + q) * ldv + begin + k) : C(0, 0);
+        }
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                acc[q] = fma(v[e][q].re, wr[e].re, fma(v[e][q].im, wr[e].im, acc[q]));
+                acc[8 + q] = fma(v[e][q].re, wr[e].im, fma(-v[e][q].im, wr[e].re, acc[8 + q]));
+                acc[16 + q] = fma(vj[e].re, v[e][q].re, fma(vj[e].im, v[e][q].im, acc[16 + q]));
+                acc[24 + q] = fma(vj[e].re, v[e][q].im, fma(-vj[e].im, v[e][q].re, acc[24 + q]));
+            }
+        }
+        const double tot = warp_reduce32(acc, lane);  // lane = part*8 + q
+        const int q = lane & 7, prt = lane >> 3;
+        if (l0 + q < nv) {
+            double* dst = reinterpret_cast<double*>(warp_part + warp * 2 * LS_MAXV + (prt >> 1) * LS_MAXV + l0 + q);
+            dst[prt & 1] = tot;
+        }
+    }
+    __syncthreads();
+    // slot idx: [0, nv) -> a_idx ; [LS_MAXV, LS_MAXV + j) -> g_(idx - LS_MAXV)
+    const bool live = tid < nv || (tid >= LS_MAXV && tid < LS_MAXV + j);
+    if (live) {
+        cplx t = C(0, 0);
+#pragma unroll
+        for (int wq = 0; wq < GR_WARPS; ++wq) { t.re += warp_part[wq * 2 * LS_MAXV + tid].re; t.im += warp_part[wq * 2 * LS_MAXV + tid].im; }
+        part[(size_t)me * 2 * LS_MAXV + tid] = t;
+    }
+    grid.sync();
+    // every CTA: totals in fixed CTA order, then the forward substitution (I + L) h = a
+    if (live) {
+        cplx t = C(0, 0);
+        unsigned d = 0;
+        for (; d + 37 <= G; d += 37) {
+            double2 pv[37];
+#pragma unroll
+            for (int u = 0; u < 37; ++u) pv[u] = __ldcg(reinterpret_cast<const double2*>(part + (size_t)(d + u) * 2 * LS_MAXV + tid));
+#pragma unroll
+            for (int u = 0; u < 37; ++u) { t.re += pv[u].x; t.im += pv[u].y; }
+        }
+        for (; d < G; ++d) {
+            const double2 pv = __ldcg(reinterpret_cast<const double2*>(part + (size_t)d * 2 * LS_MAXV + tid));
+            t.re += pv.x;
+            t.im += pv.y;
+        }
+        if (tid < nv) {
+            avec[tid] = t;
+        } else {
+            const int l = tid - LS_MAXV;
+            LsT[l * nv + j] = t;
+            if (me == 0) Lmat[j * ldl + l] = t;
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        // lane holds a[lane] and a[lane + 32]; column l of L comes from LsT row l (conflict-free)
+        cplx a0 = lane < nv ? avec[lane] : C(0, 0);
+        cplx a1 = lane + 32 < nv ? avec[lane + 32] : C(0, 0);
+        for (int l = 0; l < nv; ++l) {
+            const cplx src = l < 32 ? a0 : a1;
+            cplx hl;
+            hl.re = __shfl_sync(0xffffffffu, src.re, l & 31);
+            hl.im = __shfl_sync(0xffffffffu, src.im, l & 31);
+            if (lane > l && lane < nv) {
+                const cplx lk = LsT[l * nv + lane];
+                a0.re -= lk.re * hl.re - lk.im * hl.im;
+                a0.im -= lk.re * hl.im + lk.im * hl.re;
+            }
+            if (lane + 32 > l && lane + 32 < nv) {
+                const cplx lk = LsT[l * nv + lane + 32];
+                a1.re -= lk.re * hl.re - lk.im * hl.im;
+                a1.im -= lk.re * hl.im + lk.im * hl.re;
+            }
+        }
+        if (lane < nv) avec[lane] = a0;
+        if (lane + 32 < nv) avec[lane + 32] = a1;
+        if (me == 0) {
+            if (lane < nv) hcol[lane] = a0;
+            if (lane + 32 < nv) hcol[lane + 32] = a1;
+            if (hcol_host) {
+                if (lane < nv) hcol_host[lane] = a0;
+                if (lane + 32 < nv) hcol_host[lane + 32] = a1;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- pass 2: w -= sum_l h_l v_l ----------------------------------------------------------------
+    for (int l0 = 0; l0 < nv; l0 += 8) {
+        cplx v[EPT][8];
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            const uint64_t k = tid + (uint64_t)e * GR_THREADS;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[e][q] = (l0 + q < nv && k < len) ? ldg_c(V + (uint64_t)(l0 + q) * ldv + begin + k) : C(0, 0);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            if (l0 + q < nv) {
+                const cplx h = avec[l0 + q];
+#pragma unroll
+                for (int e = 0; e < EPT; ++e) {
+                    wr[e].re = fma(-h.re, v[e][q].re, fma(h.im, v[e][q].im, wr[e].re));
+                    wr[e].im = fma(-h.re, v[e][q].im, fma(-h.im, v[e][q].re, wr[e].im));
+                }
+            }
+        }
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) acc = fma(wr[e].re, wr[e].re, fma(wr[e].im, wr[e].im, acc));
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+    if (lane == 0) nred[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int wq = 0; wq < GR_WARPS; ++wq) t += nred[wq];
+        npart[me] = t;
+    }
+    grid.sync();
+    if (warp == 0) {
+        double t = 0.0;
+        for (unsigned d = lane; d < G; d += 32) t += __ldcg(npart + d);
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) t += __shfl_xor_sync(0xffffffffu, t, m);
+        if (lane == 0) nrm_s = sqrt(t);
+    }
+    __syncthreads();
+    const double nrm = nrm_s;
+    if (me == 0 && tid == 0) {
+        hcol[j + 1] = C(nrm, 0.0);
+        if (hcol_host) hcol_host[j + 1] = C(nrm, 0.0);
+    }
+    if (!(nrm < breakdown_tol)) {
+        const double inv = 1.0 / nrm;
+        const double sc = inv - 1.0;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            const uint64_t k = tid + (uint64_t)e * GR_THREADS;
+            if (k < len)
+                vnext[begin + k] = direct_scale ? C(wr[e].re * inv, wr[e].im * inv)
+                                                : C(wr[e].re + wr[e].re * sc, wr[e].im + wr[e].im * sc);
+        }
+    }
 }
 
 // Same step for long vectors: w slice in shared memory (or global/L2 if even that does not
@@ -862,7 +1086,8 @@ static cudaError_t launch_mgs_reg(int cl, const cplx* V, uint64_t ldv, const cpl
 
 template <int EPT>
 static cudaError_t launch_mgs_lowsync(int cl, const cplx* V, uint64_t ldv, const cplx* w, int j, uint64_t n, uint64_t S, cplx* Lmat,
-                                      int ldl, cplx* hcol, cplx* vnext, const cplx* pinv, int direct_scale, cudaStream_t s) {
+                                      int ldl, cplx* hcol, cplx* vnext, const cplx* pinv, int direct_scale, cplx* hcol_host,
+                                      cudaStream_t s) {
     static bool attr_done = false;
     const size_t fixed = (size_t)(LS_WARPS * 2 * LS_MAXV + MAX_CLUSTER * 2 * LS_MAXV + LS_MAXV) * sizeof(cplx);
     if (!attr_done) {
@@ -875,26 +1100,63 @@ static cudaError_t launch_mgs_lowsync(int cl, const cplx* V, uint64_t ldv, const
     }
     const size_t smem = fixed + (size_t)(j + 1) * (j + 1) * sizeof(cplx);
     return launch_cluster(mgs_lowsync_kernel<EPT>, cl, LS_THREADS, smem, s, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, 1e-14, pinv,
-                          direct_scale);
+                          direct_scale, hcol_host);
 }
+
+template <int EPT>
+static cudaError_t launch_mgs_grid(int G, const cplx* V, uint64_t ldv, const cplx* w, int j, uint64_t n, uint64_t S, cplx* Lmat,
+                                   int ldl, cplx* hcol, cplx* vnext, const cplx* pinv, int direct_scale, cplx* scratch,
+                                   cplx* hcol_host, cudaStream_t s) {
+    static bool attr_done = false;
+    const size_t fixed = (size_t)(GR_WARPS * 2 * LS_MAXV + LS_MAXV) * sizeof(cplx);
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(mgs_grid_kernel<EPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(fixed + (size_t)LS_MAXV * LS_MAXV * sizeof(cplx)));
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(G, 1, 1);
+    cfg.blockDim = dim3(GR_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = fixed + (size_t)(j + 1) * (j + 1) * sizeof(cplx);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cplx* part = scratch;
+    double* npart = reinterpret_cast<double*>(scratch + (size_t)GR_MAX_CTAS * 2 * LS_MAXV);
+    const double tol = 1e-14;
+    return cudaLaunchKernelEx(&cfg, mgs_grid_kernel<EPT>, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, tol, pinv, direct_scale,
+                              part, npart, hcol_host);
+}
+
+size_t mgs_scratch_elems() { return (size_t)GR_MAX_CTAS * 2 * LS_MAXV + GR_MAX_CTAS; }
 
 static int g_mgs_mode = []() {
     const char* v = std::getenv("BEMB200_MGS_MODE");
-    return v ? std::atoi(v) : 0;
-}();  // 0: low-sync register kernel (16-CTA cluster) when the slice fits, 2: one-vector register kernel, 1: generic kernel only
+    return v ? std::atoi(v) : 3;
+}();  // 3: whole-GPU cooperative low-sync kernel, 0: low-sync register kernel (16-CTA cluster) when the slice fits, 2: one-vector register kernel, 1: generic kernel only
 
-cudaError_t launch_mgs(const cplx* V, uint64_t ldv, cplx* w, int j, uint64_t n, cplx* hcol, cplx* vnext, const cplx* pinv,
-                       int direct_scale, cplx* Lmat, int ldl, cudaStream_t s) {
+static cudaError_t launch_mgs_cluster_path(int mode_in, const cplx* V, uint64_t ldv, cplx* w, int j, uint64_t n, cplx* hcol,
+                                           cplx* vnext, const cplx* pinv, int direct_scale, cplx* Lmat, int ldl, cplx* hcol_host,
+                                           bool* wrote_host, cudaStream_t s) {
+    *wrote_host = false;
+    // 0: low-sync register kernel (16-CTA cluster) when the slice fits, 2: one-vector register kernel, 1: generic kernel;
+    // a kernel this device cannot place demotes the mode for good
+    static int cluster_mode = mode_in;
+    int& g_mgs_mode = cluster_mode;
     if (g_mgs_mode == 0 && Lmat && j + 1 <= LS_MAXV && n <= 16ull * LS_THREADS * 8ull) {
         const int cl = n >= 2048 ? 16 : (n >= 512 ? 4 : 1);
         const uint64_t S = (n + cl - 1) / cl;
         const uint64_t ept = (S + LS_THREADS - 1) / LS_THREADS;
         cudaError_t e;
-        if (ept <= 1) e = launch_mgs_lowsync<1>(cl, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, s);
-        else if (ept <= 2) e = launch_mgs_lowsync<2>(cl, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, s);
-        else if (ept <= 4) e = launch_mgs_lowsync<4>(cl, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, s);
-        else e = launch_mgs_lowsync<8>(cl, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, s);
-        if (e == cudaSuccess) return e;
+        if (ept <= 1) e = launch_mgs_lowsync<1>(cl, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, hcol_host, s);
+        else if (ept <= 2) e = launch_mgs_lowsync<2>(cl, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, hcol_host, s);
+        else if (ept <= 4) e = launch_mgs_lowsync<4>(cl, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, hcol_host, s);
+        else e = launch_mgs_lowsync<8>(cl, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, hcol_host, s);
+        if (e == cudaSuccess) { *wrote_host = hcol_host != nullptr; return e; }
         cudaGetLastError();
         g_mgs_mode = 2;
     }
@@ -931,6 +1193,30 @@ cudaError_t launch_mgs(const cplx* V, uint64_t ldv, cplx* w, int j, uint64_t n, 
         cudaGetLastError();  // e.g. a 16-CTA / 200 KB cluster that this GPC layout cannot place
         g_cluster_level = 1;
     }
+}
+
+cudaError_t launch_mgs(const cplx* V, uint64_t ldv, cplx* w, int j, uint64_t n, cplx* hcol, cplx* vnext, const cplx* pinv,
+                       int direct_scale, cplx* Lmat, int ldl, cplx* scratch, cplx* hcol_host, bool* wrote_host, bool allow_grid,
+                       cudaStream_t s) {
+    *wrote_host = false;
+    // mode 3 (default): whole-GPU cooperative kernel; the slice per CTA depends on n only
+    static const bool force_grid = std::getenv("BEMB200_MGS_FORCE_GRID") != nullptr;
+    if (g_mgs_mode == 3 && (allow_grid || force_grid) && Lmat && scratch && j + 1 <= LS_MAXV && n >= 4096 && n <= (uint64_t)GR_MAX_CTAS * GR_THREADS * 8ull) {
+        const int G = GR_MAX_CTAS;
+        const uint64_t S = (n + G - 1) / G;
+        const uint64_t ept = (S + GR_THREADS - 1) / GR_THREADS;
+        cudaError_t e;
+        if (ept <= 1) e = launch_mgs_grid<1>(G, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, scratch, hcol_host, s);
+        else if (ept <= 2) e = launch_mgs_grid<2>(G, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, scratch, hcol_host, s);
+        else if (ept <= 4) e = launch_mgs_grid<4>(G, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, scratch, hcol_host, s);
+        else e = launch_mgs_grid<8>(G, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, scratch, hcol_host, s);
+        if (e == cudaSuccess) { *wrote_host = hcol_host != nullptr; return e; }
+        cudaGetLastError();  // cooperative launch not placeable on this device: cluster kernels from now on
+        g_mgs_mode = 0;
+    }
+    // small or very long vectors, or BEMB200_MGS_MODE in {0,1,2}: the cluster kernels
+    return launch_mgs_cluster_path(g_mgs_mode == 3 ? 0 : g_mgs_mode, V, ldv, w, j, n, hcol, vnext, pinv, direct_scale, Lmat, ldl,
+                                   hcol_host, wrote_host, s);
 }
 
 cudaError_t launch_residual(const cplx* b, const cplx* ax, cplx* r, uint64_t n, double* out, const cplx* pinv, cudaStream_t s) {

@@ -7,7 +7,9 @@ cudaError_t launch_zgemv(const cplx* A, uint64_t lda, uint64_t nrows, uint64_t n
 cudaError_t launch_zgemv_t(const cplx* A, uint64_t lda, uint64_t nrows, uint64_t ncols, const cplx* x, cplx* y, cudaStream_t s);
 // Lmat (may be NULL): (ldl x ldl) scratch for the Gram triangle of the current restart cycle (low-sync kernel)
 cudaError_t launch_mgs(const cplx* V, uint64_t ldv, cplx* w, int j, uint64_t n, cplx* hcol, cplx* vnext, const cplx* pinv,
-                       int direct_scale, cplx* Lmat, int ldl, cudaStream_t s);
+                       int direct_scale, cplx* Lmat, int ldl, cplx* scratch, cplx* hcol_host, bool* wrote_host, bool allow_grid,
+                       cudaStream_t s);  // hcol_host: mapped pinned copy of the column (written by the kernel when *wrote_host)
+size_t mgs_scratch_elems();  // cplx elements of scratch launch_mgs needs after the ldl*ldl Gram triangle
 cudaError_t launch_residual(const cplx* b, const cplx* ax, cplx* r, uint64_t n, double* out, const cplx* pinv, cudaStream_t s);
 cudaError_t launch_zgemm_block(const cplx* A, uint64_t lda, uint64_t nrows, uint64_t ncols, const cplx* X, cplx* Y, int nrhs,
                                cudaStream_t s);

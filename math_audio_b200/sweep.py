@@ -61,6 +61,7 @@ class SweepDriver:
         if err:
             raise err[0]
         self.ctx_asm.set_background(self.background_blocks_per_sm)
+        self.ctx_solve.set_shared_gpu(self.overlap)  # assembly kernels run beside the solve from here on
         for i in range(len(cases)):
             t = None
             if i + 1 < len(cases):
