@@ -100,6 +100,11 @@ int bemb200_ctx_set_background(bemb200_ctx* ctx, int blocks_per_sm);
  * background assembly above): the Gram-Schmidt step then uses its 16-CTA cluster kernel instead
  * of the whole-GPU cooperative kernel, whose grid barriers stall behind foreign warps. */
 int bemb200_ctx_set_shared_gpu(bemb200_ctx* ctx, int shared);
+/* Row-sharded solves (nranks > 1): *active = 1 once the ranks have mapped each other's work
+ * vectors (CUDA IPC over NVLink) and the Arnoldi matvec stores its slab of A v straight into
+ * every rank's memory from the ZGEMV epilogue -- no all-gather kernel; 0 = NCCL all-gather
+ * (before the first solve, when the platform refuses peer mappings, or BEMB200_PEER_FUSED=0). */
+int bemb200_ctx_peer_exchange_active(const bemb200_ctx* ctx, int* active);
 /* Hand a matrix to another context of the SAME device (e.g. a solve context with its own stream
  * while an assembly context fills the next matrix of a frequency sweep).  The caller orders the
  * use of one matrix by the two contexts. */

@@ -70,6 +70,12 @@ class Context:
     def set_background(self, blocks_per_sm: int) -> None:
         _capi.check(self._lib.bemb200_ctx_set_background(self._h, blocks_per_sm), self._h)
 
+    def peer_exchange_active(self) -> bool:
+        """True once row-sharded solves exchange A v through peer memory (fused ZGEMV epilogue) instead of NCCL."""
+        a = C.c_int(0)
+        _capi.check(self._lib.bemb200_ctx_peer_exchange_active(self._h, C.byref(a)), self._h)
+        return bool(a.value)
+
     def set_shared_gpu(self, shared: bool) -> None:
         """Tell this context's solver that other streams share the GPU (no whole-GPU cooperative kernels)."""
         _capi.check(self._lib.bemb200_ctx_set_shared_gpu(self._h, 1 if shared else 0), self._h)

@@ -189,6 +189,7 @@ int bemb200_ctx_create_ex(int device, int rank, int nranks, const uint8_t* nccl_
 void bemb200_ctx_destroy(bemb200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    free_peer_exchange(ctx);
     if (ctx->nccl_comm && ncclshim::CommDestroy) ncclshim::CommDestroy(ctx->nccl_comm);
     if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -511,6 +512,12 @@ int bemb200_ctx_set_background(bemb200_ctx* ctx, int blocks_per_sm) {
 int bemb200_ctx_set_shared_gpu(bemb200_ctx* ctx, int shared) {
     if (!ctx) return set_error(ctx, BEMB200_EINVAL, "NULL context");
     ctx->shared_gpu.store(shared ? 1 : 0);
+    return BEMB200_OK;
+}
+
+int bemb200_ctx_peer_exchange_active(const bemb200_ctx* ctx, int* active) {
+    if (!ctx || !active) return set_error(nullptr, BEMB200_EINVAL, "NULL argument");
+    *active = ctx->px.ok ? 1 : 0;
     return BEMB200_OK;
 }
 

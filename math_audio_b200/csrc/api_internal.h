@@ -9,6 +9,17 @@
 #include "../../include/bemb200.h"
 #include "internal.h"
 
+// Peer-memory exchange of the row-sharded solve: one buffer per rank (flags + two work vectors,
+// alternating by epoch), exported with CUDA IPC and mapped by every other rank of the node.
+struct PeerExchange {
+    bool tried = false, ok = false;
+    uint64_t npad = 0;                 // elements per work vector
+    unsigned char* local = nullptr;    // [flags: 8 x u64 | counter | pad to 256 B][w0: npad cplx][w1: npad cplx]
+    unsigned char* base[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // every rank's buffer
+    unsigned long long epoch = 0;      // last epoch published (identical on all ranks: collective call sequence)
+    int* err_h = nullptr;              // mapped pinned int: a consumer kernel timed out waiting for a peer
+};
+
 struct bemb200_ctx {
     int device = 0;
     int rank = 0, nranks = 1;
@@ -17,6 +28,7 @@ struct bemb200_ctx {
     std::atomic<int> shared_gpu{0};  // != 0: another stream shares the GPU -> solver avoids whole-GPU cooperative kernels
     std::atomic<int> background_blocks_per_sm{0};  // > 0: assembly kernels use a small persistent grid (sweep pipelining)
     void* nccl_comm = nullptr;  // ncclComm_t when nranks > 1
+    PeerExchange px;
     std::string err;
     std::mutex mu;  // LinearOperator is Send + Sync: serialise stream submission per context
 };
@@ -50,6 +62,7 @@ namespace bemb {
 int set_error(bemb200_ctx* ctx, int code, const std::string& msg);
 int cuda_fail(bemb200_ctx* ctx, cudaError_t e, const char* what);
 void free_workspace(bemb200_matrix* m);
+void free_peer_exchange(bemb200_ctx* ctx);
 }  // namespace bemb
 
 #define BEMB_CUDA(ctx, call)                                          \

@@ -63,6 +63,101 @@ void free_workspace(bemb200_matrix* m) {
 }
 }  // namespace bemb
 
+// ---- peer-memory exchange (row-sharded solve) ----------------------------------------------
+// Collective over the ranks of ctx (called at the start of a solve, the same sequence on every
+// rank).  On success the Arnoldi matvec stores its slab of y directly into every rank's work
+// vector (ZGEMV epilogue over NVLink) and the Gram-Schmidt kernel waits for the per-rank epoch
+// flags: the NCCL all-gather and its two kernel boundaries leave the iteration.  Any failure
+// (no peer access, IPC refused by the platform) is agreed on by all ranks and leaves the NCCL
+// all-gather path in place.  BEMB200_PEER_FUSED=0 disables it.
+constexpr size_t PX_HEADER = 256;
+namespace bemb {
+void free_peer_exchange(bemb200_ctx* ctx) {
+    PeerExchange& px = ctx->px;
+    for (int p = 0; p < ctx->nranks && p < 8; ++p)
+        if (p != ctx->rank && px.base[p]) cudaIpcCloseMemHandle(px.base[p]);
+    if (px.ok && ctx->nccl_comm) {
+        // nobody frees exported memory while a peer may still have it mapped
+        unsigned char* tok = nullptr;
+        if (cudaMalloc((void**)&tok, (size_t)ctx->nranks) == cudaSuccess) {
+            nccl_allgather_bytes(ctx, tok + ctx->rank, tok, 1);
+            cudaStreamSynchronize(ctx->stream);
+            cudaFree(tok);
+        }
+    }
+    if (px.local) cudaFree(px.local);
+    if (px.err_h) cudaFreeHost(px.err_h);
+    px = PeerExchange();
+    cudaGetLastError();
+}
+}  // namespace bemb
+
+static int ensure_peer_exchange(bemb200_ctx* ctx, uint64_t npad) {
+    PeerExchange& px = ctx->px;
+    static const bool enabled = []() { const char* v = std::getenv("BEMB200_PEER_FUSED"); return v ? std::atoi(v) != 0 : true; }();
+    if (!enabled || ctx->nranks < 2 || ctx->nranks > MAX_PEERS || !ctx->nccl_comm) return BEMB200_OK;
+    if (px.tried && (!px.ok || px.npad >= npad)) return BEMB200_OK;
+    if (px.tried) free_peer_exchange(ctx);  // a larger operator: re-establish (collective, same on every rank)
+    px.tried = true;
+    px.npad = npad;
+    const int P = ctx->nranks;
+    const size_t bytes = PX_HEADER + 2 * npad * sizeof(cplx);
+    int ok = 1;
+    cudaIpcMemHandle_t mine;
+    std::memset(&mine, 0, sizeof(mine));
+    if (cudaMalloc((void**)&px.local, bytes) != cudaSuccess) { ok = 0; px.local = nullptr; }
+    if (ok && cudaMemsetAsync(px.local, 0, bytes, ctx->stream) != cudaSuccess) ok = 0;
+    if (ok && cudaIpcGetMemHandle(&mine, px.local) != cudaSuccess) ok = 0;
+    if (ok && cudaHostAlloc((void**)&px.err_h, sizeof(int), cudaHostAllocMapped) != cudaSuccess) { ok = 0; px.err_h = nullptr; }
+    if (px.err_h) *px.err_h = 0;
+    cudaGetLastError();
+    // exchange {handle, ok} through the communicator
+    struct Slot { cudaIpcMemHandle_t h; int ok; int pad[3]; };
+    static_assert(sizeof(Slot) % 16 == 0, "slot alignment");
+    std::vector<Slot> all(P);
+    Slot me{};
+    me.h = mine;
+    me.ok = ok;
+    unsigned char* stage = nullptr;
+    BEMB_CUDA(ctx, cudaMalloc((void**)&stage, sizeof(Slot) * P));
+    BEMB_CUDA(ctx, cudaMemcpyAsync(stage + sizeof(Slot) * ctx->rank, &me, sizeof(Slot), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = nccl_allgather_bytes(ctx, stage + sizeof(Slot) * ctx->rank, stage, sizeof(Slot));
+    if (rc != BEMB200_OK) { cudaFree(stage); return rc; }
+    BEMB_CUDA(ctx, cudaMemcpyAsync(all.data(), stage, sizeof(Slot) * P, cudaMemcpyDeviceToHost, ctx->stream));
+    BEMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int p = 0; p < P; ++p) ok &= all[p].ok;
+    if (ok) {
+        for (int p = 0; p < P; ++p) {
+            if (p == ctx->rank) { px.base[p] = px.local; continue; }
+            void* ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, all[p].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+            px.base[p] = static_cast<unsigned char*>(ptr);
+        }
+    }
+    // second round: did every rank map every peer?
+    me.ok = ok;
+    BEMB_CUDA(ctx, cudaMemcpyAsync(stage + sizeof(Slot) * ctx->rank, &me, sizeof(Slot), cudaMemcpyHostToDevice, ctx->stream));
+    rc = nccl_allgather_bytes(ctx, stage + sizeof(Slot) * ctx->rank, stage, sizeof(Slot));
+    if (rc != BEMB200_OK) { cudaFree(stage); return rc; }
+    BEMB_CUDA(ctx, cudaMemcpyAsync(all.data(), stage, sizeof(Slot) * P, cudaMemcpyDeviceToHost, ctx->stream));
+    BEMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(stage);
+    for (int p = 0; p < P; ++p) ok &= all[p].ok;
+    px.ok = ok != 0;
+    px.epoch = 0;
+    if (!px.ok) {
+        for (int p = 0; p < P; ++p)
+            if (p != ctx->rank && px.base[p]) { cudaIpcCloseMemHandle(px.base[p]); px.base[p] = nullptr; }
+        if (px.local) { cudaFree(px.local); px.local = nullptr; }
+        cudaGetLastError();
+    }
+    return BEMB200_OK;
+}
+
+static inline cplx* px_work(const PeerExchange& px, int p, unsigned long long epoch) {
+    return reinterpret_cast<cplx*>(px.base[p] + PX_HEADER) + (epoch & 1ull) * px.npad;
+}
+
 static int ensure_workspace(bemb200_matrix* m, uint32_t restart) {
     bemb200_ctx* ctx = m->ctx;
     if (m->ws && m->ws->restart >= restart) return BEMB200_OK;
@@ -202,6 +297,15 @@ static int gmres_core(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t max_it
     uint64_t total_iterations = 0, restarts = 0;
     const int ldh = mm;
     std::vector<cplx> h, cs, sn, g, y;
+    const bool allow_grid = ctx->shared_gpu.load() == 0;
+    rc = ensure_peer_exchange(ctx, ws->npad);
+    if (rc != BEMB200_OK) return rc;
+    const bool peer_fused = ctx->nranks > 1 && ctx->px.ok && ctx->px.npad >= ws->npad && ws->npad == ws->chunk * (uint64_t)ctx->nranks &&
+                            mgs_peer_wait_capable(n, restart, allow_grid);
+    struct PeerErrCheck {  // a consumer kernel that gave up waiting for a peer poisons the solve: report it
+        bemb200_ctx* c; bool on;
+        int check() const { return (on && c->px.err_h && *c->px.err_h) ? 1 : 0; }
+    } peer_err{ctx, peer_fused};
     for (uint32_t outer = 0; outer < max_iterations; ++outer) {
         rc = matvec(m, x, ws->w, true);
         if (rc != BEMB200_OK) return rc;
@@ -229,19 +333,42 @@ static int gmres_core(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t max_it
         auto enqueue_iteration = [&](int j) -> int {
             BEMB_CUDA(ctx, cudaEventRecord(ws->it_ev0[j], s));
             const uint64_t nloc = m->r1 - m->r0;
-            cplx* yloc = ws->w + (ctx->nranks > 1 ? (uint64_t)ctx->rank * ws->chunk : m->r0);
-            BEMB_CUDA(ctx, launch_zgemv(m->A, m->n_cols, nloc, m->n_cols, ws->V + (uint64_t)j * ws->npad, yloc, s));
-            BEMB_CUDA(ctx, cudaEventRecord(ws->it_ev1[j], s));
-            if (ctx->nranks > 1) {
-                int rc2 = nccl_allgather_bytes(ctx, yloc, ws->w, ws->chunk * sizeof(cplx));
-                if (rc2 != BEMB200_OK) return rc2;
+            const cplx* wvec = ws->w;
+            PeerWait pw;
+            if (peer_fused) {
+                // ZGEMV epilogue stores this rank's slab into every rank's work vector; no all-gather
+                PeerExchange& px = ctx->px;
+                const unsigned long long epoch = ++px.epoch;
+                PeerOut po{};
+                po.npeers = ctx->nranks;
+                po.epoch = epoch;
+                po.counter = reinterpret_cast<unsigned int*>(px.local + 8 * sizeof(unsigned long long));
+                for (int p = 0; p < ctx->nranks; ++p) {
+                    po.y[p] = px_work(px, p, epoch) + (uint64_t)ctx->rank * ws->chunk;
+                    po.flag[p] = reinterpret_cast<unsigned long long*>(px.base[p]) + ctx->rank;
+                }
+                BEMB_CUDA(ctx, launch_zgemv_peer(m->A, m->n_cols, nloc, m->n_cols, ws->V + (uint64_t)j * ws->npad, po, s));
+                BEMB_CUDA(ctx, cudaEventRecord(ws->it_ev1[j], s));
+                wvec = px_work(px, ctx->rank, epoch);
+                pw.flags = reinterpret_cast<const unsigned long long*>(px.local);
+                pw.nflags = ctx->nranks;
+                pw.epoch = epoch;
+                pw.err = px.err_h;
+            } else {
+                cplx* yloc = ws->w + (ctx->nranks > 1 ? (uint64_t)ctx->rank * ws->chunk : m->r0);
+                BEMB_CUDA(ctx, launch_zgemv(m->A, m->n_cols, nloc, m->n_cols, ws->V + (uint64_t)j * ws->npad, yloc, s));
+                BEMB_CUDA(ctx, cudaEventRecord(ws->it_ev1[j], s));
+                if (ctx->nranks > 1) {
+                    int rc2 = nccl_allgather_bytes(ctx, yloc, ws->w, ws->chunk * sizeof(cplx));
+                    if (rc2 != BEMB200_OK) return rc2;
+                }
             }
             cplx* hd = ws->hcol_d + (size_t)j * ws->ldh_slot;
             bool wrote_host = false;
-            BEMB_CUDA(ctx, launch_mgs(ws->V, ws->npad, ws->w, j, n, hd, ws->V + (uint64_t)(j + 1) * ws->npad, pinv, direct_scale,
-                                      ws->lmat_d, (int)ws->restart + 1,
+            BEMB_CUDA(ctx, launch_mgs(ws->V, ws->npad, const_cast<cplx*>(wvec), j, n, hd, ws->V + (uint64_t)(j + 1) * ws->npad, pinv,
+                                      direct_scale, ws->lmat_d, (int)ws->restart + 1,
                                       ws->lmat_d + (size_t)(ws->restart + 1) * (ws->restart + 1),
-                                      ws->hcol_h + (size_t)j * ws->ldh_slot, &wrote_host, ctx->shared_gpu.load() == 0, s));
+                                      ws->hcol_h + (size_t)j * ws->ldh_slot, &wrote_host, allow_grid, pw, s));
             if (g_dbg_split) BEMB_CUDA(ctx, cudaEventRecord(ws->ev0, s));
             if (!wrote_host)
                 BEMB_CUDA(ctx, cudaMemcpyAsync(ws->hcol_h + (size_t)j * ws->ldh_slot, hd, (j + 2) * sizeof(cplx),
@@ -283,6 +410,8 @@ static int gmres_core(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t max_it
             }
             g_dbg_launch_us += std::chrono::duration<double, std::micro>(tp1 - tp0).count();
             g_dbg_wait_us += std::chrono::duration<double, std::micro>(tp2 - tp1).count();
+            if (peer_err.check())
+                return set_error(ctx, BEMB200_ENCCL, "peer-memory exchange timed out waiting for another rank's slab of A v");
             const cplx* hcol = ws->hcol_h + (size_t)j * ws->ldh_slot;
             for (int i = 0; i <= j; ++i) h[i * ldh + j] = hcol[i];
             const double w_norm = hcol[j + 1].re;

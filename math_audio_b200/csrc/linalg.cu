@@ -38,10 +38,42 @@ __device__ __forceinline__ void cfma(double& are, double& aim, double2 a, double
     aim = fma(a.y, x.x, aim);
 }
 
-template <int GEMV_RB, int GEMV_U>
+// ---- peer-memory helpers (row-sharded solve: ZGEMV epilogue stores the slab of y straight into
+// every rank's work vector over NVLink, the consumer kernel waits on per-rank epoch flags) --------
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// All threads of the CTA call this; returns after every flag in flags[0..nflags) reached `epoch`
+// (or after PEER_WAIT_TIMEOUT_NS, recording the failure in *err -- never an unbounded spin).
+constexpr unsigned long long PEER_WAIT_TIMEOUT_NS = 4000000000ull;
+__device__ __forceinline__ void wait_peer_flags(const PeerWait& pw) {
+    if (pw.flags == nullptr) return;
+    if ((int)threadIdx.x < pw.nflags) {
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys(pw.flags + threadIdx.x) < pw.epoch) {
+            if (global_timer_ns() - t0 > PEER_WAIT_TIMEOUT_NS) {
+                *reinterpret_cast<volatile int*>(pw.err) = 1;
+                break;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+template <int GEMV_RB, int GEMV_U, bool FUSED>
 __global__ void __launch_bounds__(GEMV_THREADS)
 zgemv_kernel(const cplx* __restrict__ A, uint64_t lda, uint64_t nrows, uint64_t ncols, const cplx* __restrict__ x,
-             cplx* __restrict__ y) {
+             cplx* __restrict__ y, PeerOut po) {
     __shared__ double red[GEMV_RB][2][GEMV_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (uint64_t rb = (uint64_t)blockIdx.x * GEMV_RB; rb < nrows; rb += (uint64_t)gridDim.x * GEMV_RB) {
@@ -86,9 +118,26 @@ zgemv_kernel(const cplx* __restrict__ A, uint64_t lda, uint64_t nrows, uint64_t 
             double sr = 0.0, si = 0.0;
 #pragma unroll
             for (int w = 0; w < GEMV_THREADS / 32; ++w) { sr += red[tid][0][w]; si += red[tid][1][w]; }
-            y[rb + tid] = C(sr, si);
+            if (FUSED) {
+                for (int p = 0; p < po.npeers; ++p) po.y[p][rb + tid] = C(sr, si);  // NVLink stores (own rank: local)
+                __threadfence_system();
+            } else {
+                y[rb + tid] = C(sr, si);
+            }
         }
         __syncthreads();
+    }
+    if (FUSED) {
+        // last block to finish publishes this rank's epoch to every peer
+        if (tid == 0) {
+            __threadfence_system();
+            const unsigned int done = atomicAdd(po.counter, 1u);
+            if (done == gridDim.x - 1) {
+                *po.counter = 0;
+                __threadfence_system();
+                for (int p = 0; p < po.npeers; ++p) st_release_sys(po.flag[p], po.epoch);
+            }
+        }
     }
 }
 
@@ -150,6 +199,10 @@ __device__ __forceinline__ cplx cluster_allreduce(cplx v, ClusterShared& sh, int
     return t;
 }
 
+__device__ __forceinline__ cplx ldcg_c(const cplx* p) {  // L2 only: the data may have been stored by a peer GPU
+    const double2 v = __ldcg(reinterpret_cast<const double2*>(p));
+    return C(v.x, v.y);
+}
 __device__ __forceinline__ cplx ldg_c(const cplx* p) {
     double2 v = __ldg(reinterpret_cast<const double2*>(p));
     return C(v.x, v.y);
@@ -242,7 +295,7 @@ template <int EPT>
 __global__ void __launch_bounds__(LS_THREADS)
 mgs_lowsync_kernel(const cplx* __restrict__ V, uint64_t ldv, const cplx* __restrict__ w, int j, uint64_t n, uint64_t S,
                    cplx* __restrict__ Lmat, int ldl, cplx* __restrict__ hcol, cplx* __restrict__ vnext, double breakdown_tol,
-                   const cplx* __restrict__ pinv, int direct_scale, cplx* __restrict__ hcol_host) {
+                   const cplx* __restrict__ pinv, int direct_scale, cplx* __restrict__ hcol_host, PeerWait pw) {
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ ClusterShared sh1;  // single-value all-reduce (norm)
     // dynamic layout: warp_part[LS_WARPS][2*LS_MAXV] | slots[MAX_CLUSTER][2*LS_MAXV] | a[LS_MAXV] | Ls[(j+1)*(j+1)]
@@ -258,11 +311,12 @@ mgs_lowsync_kernel(const cplx* __restrict__ V, uint64_t ldv, const cplx* __restr
     const uint64_t end = begin + S < n ? begin + S : n;
     const uint64_t len = end > begin ? end - begin : 0;
 
+    wait_peer_flags(pw);  // row-sharded solve: every rank's slab of w has landed
     cplx wr[EPT], vj[EPT];
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
         const uint64_t k = tid + (uint64_t)e * LS_THREADS;
-        wr[e] = k < len ? w[begin + k] : C(0, 0);
+        wr[e] = k < len ? ldcg_c(w + begin + k) : C(0, 0);
         if (pinv && k < len) wr[e] = wr[e] * ldg_c(pinv + begin + k);
         vj[e] = (k < len) ? ldg_c(V + (uint64_t)j * ldv + begin + k) : C(0, 0);
     }
@@ -425,7 +479,7 @@ __global__ void __launch_bounds__(GR_THREADS)
 mgs_grid_kernel(const cplx* __restrict__ V, uint64_t ldv, const cplx* __restrict__ w, int j, uint64_t n, uint64_t S,
                 cplx* __restrict__ Lmat, int ldl, cplx* __restrict__ hcol, cplx* __restrict__ vnext, double breakdown_tol,
                 const cplx* __restrict__ pinv, int direct_scale, cplx* __restrict__ part, double* __restrict__ npart,
-                cplx* __restrict__ hcol_host) {
+                cplx* __restrict__ hcol_host, PeerWait pw) {
     extern __shared__ __align__(16) unsigned char dyn[];
     // dynamic layout: warp_part[GR_WARPS][2*LS_MAXV] | a[LS_MAXV] | LsT[(j+1)*(j+1)]  (LsT[l*nv + k] = L_kl)
     cplx* warp_part = reinterpret_cast<cplx*>(dyn);
@@ -441,11 +495,12 @@ mgs_grid_kernel(const cplx* __restrict__ V, uint64_t ldv, const cplx* __restrict
     const uint64_t end = begin + S < n ? begin + S : n;
     const uint64_t len = end > begin ? end - begin : 0;
 
+    wait_peer_flags(pw);
     cplx wr[EPT], vj[EPT];
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
         const uint64_t k = tid + (uint64_t)e * GR_THREADS;
-        wr[e] = k < len ? w[begin + k] : C(0, 0);
+        wr[e] = k < len ? ldcg_c(w + begin + k) : C(0, 0);
         if (pinv && k < len) wr[e] = wr[e] * ldg_c(pinv + begin + k);
         vj[e] = (k < len) ? ldg_c(V + (uint64_t)j * ldv + begin + k) : C(0, 0);
     }
@@ -1030,19 +1085,36 @@ cudaError_t launch_cluster(Kern kern, int cluster, int threads, size_t smem, cud
 
 }  // namespace
 
-cudaError_t launch_zgemv(const cplx* A, uint64_t lda, uint64_t nrows, uint64_t ncols, const cplx* x, cplx* y, cudaStream_t s) {
-    if (nrows == 0) return cudaSuccess;
+static cudaError_t launch_zgemv_impl(const cplx* A, uint64_t lda, uint64_t nrows, uint64_t ncols, const cplx* x, cplx* y,
+                                     const PeerOut* po, cudaStream_t s) {
+    if (nrows == 0 && !po) return cudaSuccess;
     static const int variant = []() { const char* v = std::getenv("BEMB200_GEMV_VARIANT"); return v ? std::atoi(v) : 24; }();
     const int rb = variant / 10, u = variant % 10;
     uint64_t blocks = (nrows + rb - 1) / rb;
     const uint64_t maxb = 148ull * 8ull * 8ull;
     if (blocks > maxb) blocks = maxb;
+    if (blocks == 0) blocks = 1;  // an empty slab still has to publish its epoch
+    if (po) {
+        zgemv_kernel<2, 4, true><<<(unsigned)((nrows + 1) / 2 > maxb ? maxb : (nrows + 1) / 2 ? (nrows + 1) / 2 : 1), GEMV_THREADS, 0, s>>>(
+            A, lda, nrows, ncols, x, y, *po);
+        return cudaGetLastError();
+    }
+    const PeerOut none{};
 #define GEMV_CASE(R, U) \
-    if (rb == R && u == U) { zgemv_kernel<R, U><<<(unsigned)blocks, GEMV_THREADS, 0, s>>>(A, lda, nrows, ncols, x, y); return cudaGetLastError(); }
+    if (rb == R && u == U) { zgemv_kernel<R, U, false><<<(unsigned)blocks, GEMV_THREADS, 0, s>>>(A, lda, nrows, ncols, x, y, none); return cudaGetLastError(); }
     GEMV_CASE(4, 2) GEMV_CASE(2, 2)
 #undef GEMV_CASE
-    zgemv_kernel<2, 4><<<(unsigned)blocks, GEMV_THREADS, 0, s>>>(A, lda, nrows, ncols, x, y);
+    zgemv_kernel<2, 4, false><<<(unsigned)blocks, GEMV_THREADS, 0, s>>>(A, lda, nrows, ncols, x, y, none);
     return cudaGetLastError();
+}
+
+cudaError_t launch_zgemv(const cplx* A, uint64_t lda, uint64_t nrows, uint64_t ncols, const cplx* x, cplx* y, cudaStream_t s) {
+    return launch_zgemv_impl(A, lda, nrows, ncols, x, y, nullptr, s);
+}
+
+cudaError_t launch_zgemv_peer(const cplx* A, uint64_t lda, uint64_t nrows, uint64_t ncols, const cplx* x, const PeerOut& po,
+                              cudaStream_t s) {
+    return launch_zgemv_impl(A, lda, nrows, ncols, x, nullptr, &po, s);
 }
 
 cudaError_t launch_zgemv_t(const cplx* A, uint64_t lda, uint64_t nrows, uint64_t ncols, const cplx* x, cplx* y, cudaStream_t s) {
@@ -1087,7 +1159,7 @@ static cudaError_t launch_mgs_reg(int cl, const cplx* V, uint64_t ldv, const cpl
 template <int EPT>
 static cudaError_t launch_mgs_lowsync(int cl, const cplx* V, uint64_t ldv, const cplx* w, int j, uint64_t n, uint64_t S, cplx* Lmat,
                                       int ldl, cplx* hcol, cplx* vnext, const cplx* pinv, int direct_scale, cplx* hcol_host,
-                                      cudaStream_t s) {
+                                      const PeerWait& pw, cudaStream_t s) {
     static bool attr_done = false;
     const size_t fixed = (size_t)(LS_WARPS * 2 * LS_MAXV + MAX_CLUSTER * 2 * LS_MAXV + LS_MAXV) * sizeof(cplx);
     if (!attr_done) {
@@ -1100,13 +1172,13 @@ static cudaError_t launch_mgs_lowsync(int cl, const cplx* V, uint64_t ldv, const
     }
     const size_t smem = fixed + (size_t)(j + 1) * (j + 1) * sizeof(cplx);
     return launch_cluster(mgs_lowsync_kernel<EPT>, cl, LS_THREADS, smem, s, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, 1e-14, pinv,
-                          direct_scale, hcol_host);
+                          direct_scale, hcol_host, pw);
 }
 
 template <int EPT>
 static cudaError_t launch_mgs_grid(int G, const cplx* V, uint64_t ldv, const cplx* w, int j, uint64_t n, uint64_t S, cplx* Lmat,
                                    int ldl, cplx* hcol, cplx* vnext, const cplx* pinv, int direct_scale, cplx* scratch,
-                                   cplx* hcol_host, cudaStream_t s) {
+                                   cplx* hcol_host, const PeerWait& pw, cudaStream_t s) {
     static bool attr_done = false;
     const size_t fixed = (size_t)(GR_WARPS * 2 * LS_MAXV + LS_MAXV) * sizeof(cplx);
     if (!attr_done) {
@@ -1129,7 +1201,7 @@ static cudaError_t launch_mgs_grid(int G, const cplx* V, uint64_t ldv, const cpl
     double* npart = reinterpret_cast<double*>(scratch + (size_t)GR_MAX_CTAS * 2 * LS_MAXV);
     const double tol = 1e-14;
     return cudaLaunchKernelEx(&cfg, mgs_grid_kernel<EPT>, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, tol, pinv, direct_scale,
-                              part, npart, hcol_host);
+                              part, npart, hcol_host, pw);
 }
 
 size_t mgs_scratch_elems() { return (size_t)GR_MAX_CTAS * 2 * LS_MAXV + GR_MAX_CTAS; }
@@ -1139,9 +1211,16 @@ static int g_mgs_mode = []() {
     return v ? std::atoi(v) : 3;
 }();  // 3: whole-GPU cooperative low-sync kernel, 0: low-sync register kernel (16-CTA cluster) when the slice fits, 2: one-vector register kernel, 1: generic kernel only
 
+bool mgs_peer_wait_capable(uint64_t n, uint32_t restart, bool allow_grid) {
+    if (restart + 1 > (uint32_t)LS_MAXV) return false;
+    if (g_mgs_mode != 3 && g_mgs_mode != 0) return false;
+    if (n <= 16ull * LS_THREADS * 8ull) return true;  // cluster low-sync kernel
+    return g_mgs_mode == 3 && allow_grid && n <= (uint64_t)GR_MAX_CTAS * GR_THREADS * 8ull;
+}
+
 static cudaError_t launch_mgs_cluster_path(int mode_in, const cplx* V, uint64_t ldv, cplx* w, int j, uint64_t n, cplx* hcol,
                                            cplx* vnext, const cplx* pinv, int direct_scale, cplx* Lmat, int ldl, cplx* hcol_host,
-                                           bool* wrote_host, cudaStream_t s) {
+                                           bool* wrote_host, const PeerWait& pw, cudaStream_t s) {
     *wrote_host = false;
     // 0: low-sync register kernel (16-CTA cluster) when the slice fits, 2: one-vector register kernel, 1: generic kernel;
     // a kernel this device cannot place demotes the mode for good
@@ -1152,14 +1231,15 @@ static cudaError_t launch_mgs_cluster_path(int mode_in, const cplx* V, uint64_t 
         const uint64_t S = (n + cl - 1) / cl;
         const uint64_t ept = (S + LS_THREADS - 1) / LS_THREADS;
         cudaError_t e;
-        if (ept <= 1) e = launch_mgs_lowsync<1>(cl, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, hcol_host, s);
-        else if (ept <= 2) e = launch_mgs_lowsync<2>(cl, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, hcol_host, s);
-        else if (ept <= 4) e = launch_mgs_lowsync<4>(cl, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, hcol_host, s);
-        else e = launch_mgs_lowsync<8>(cl, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, hcol_host, s);
+        if (ept <= 1) e = launch_mgs_lowsync<1>(cl, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, hcol_host, pw, s);
+        else if (ept <= 2) e = launch_mgs_lowsync<2>(cl, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, hcol_host, pw, s);
+        else if (ept <= 4) e = launch_mgs_lowsync<4>(cl, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, hcol_host, pw, s);
+        else e = launch_mgs_lowsync<8>(cl, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, hcol_host, pw, s);
         if (e == cudaSuccess) { *wrote_host = hcol_host != nullptr; return e; }
         cudaGetLastError();
         g_mgs_mode = 2;
     }
+    if (pw.flags) return cudaErrorNotSupported;  // only the two low-sync kernels know how to wait for peer slabs
     if ((g_mgs_mode == 0 || g_mgs_mode == 2) && n <= 16ull * 256ull * 8ull) {
         // register-resident w: 16 CTAs (non-portable cluster size) x 256 threads x <= 8 elements
         const int cl = n >= 2048 ? 16 : (n >= 512 ? 4 : 1);
@@ -1197,7 +1277,7 @@ static cudaError_t launch_mgs_cluster_path(int mode_in, const cplx* V, uint64_t 
 
 cudaError_t launch_mgs(const cplx* V, uint64_t ldv, cplx* w, int j, uint64_t n, cplx* hcol, cplx* vnext, const cplx* pinv,
                        int direct_scale, cplx* Lmat, int ldl, cplx* scratch, cplx* hcol_host, bool* wrote_host, bool allow_grid,
-                       cudaStream_t s) {
+                       const PeerWait& pw, cudaStream_t s) {
     *wrote_host = false;
     // mode 3 (default): whole-GPU cooperative kernel; the slice per CTA depends on n only
     static const bool force_grid = std::getenv("BEMB200_MGS_FORCE_GRID") != nullptr;
@@ -1206,17 +1286,17 @@ cudaError_t launch_mgs(const cplx* V, uint64_t ldv, cplx* w, int j, uint64_t n, 
         const uint64_t S = (n + G - 1) / G;
         const uint64_t ept = (S + GR_THREADS - 1) / GR_THREADS;
         cudaError_t e;
-        if (ept <= 1) e = launch_mgs_grid<1>(G, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, scratch, hcol_host, s);
-        else if (ept <= 2) e = launch_mgs_grid<2>(G, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, scratch, hcol_host, s);
-        else if (ept <= 4) e = launch_mgs_grid<4>(G, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, scratch, hcol_host, s);
-        else e = launch_mgs_grid<8>(G, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, scratch, hcol_host, s);
+        if (ept <= 1) e = launch_mgs_grid<1>(G, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, scratch, hcol_host, pw, s);
+        else if (ept <= 2) e = launch_mgs_grid<2>(G, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, scratch, hcol_host, pw, s);
+        else if (ept <= 4) e = launch_mgs_grid<4>(G, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, scratch, hcol_host, pw, s);
+        else e = launch_mgs_grid<8>(G, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, scratch, hcol_host, pw, s);
         if (e == cudaSuccess) { *wrote_host = hcol_host != nullptr; return e; }
         cudaGetLastError();  // cooperative launch not placeable on this device: cluster kernels from now on
         g_mgs_mode = 0;
     }
     // small or very long vectors, or BEMB200_MGS_MODE in {0,1,2}: the cluster kernels
     return launch_mgs_cluster_path(g_mgs_mode == 3 ? 0 : g_mgs_mode, V, ldv, w, j, n, hcol, vnext, pinv, direct_scale, Lmat, ldl,
-                                   hcol_host, wrote_host, s);
+                                   hcol_host, wrote_host, pw, s);
 }
 
 cudaError_t launch_residual(const cplx* b, const cplx* ax, cplx* r, uint64_t n, double* out, const cplx* pinv, cudaStream_t s) {

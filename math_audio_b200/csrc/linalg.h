@@ -3,12 +3,33 @@
 #include "internal.h"
 
 namespace bemb {
+// Row-sharded solve over peer memory (one process per GPU, buffers mapped with CUDA IPC):
+// PeerOut  - where the ZGEMV epilogue stores this rank's slab of y (every rank's work vector,
+//            own rank included) and which epoch flag it raises on each rank when the slab is out;
+// PeerWait - the flags (one per rank, local memory) a consumer kernel polls before reading y.
+constexpr int MAX_PEERS = 8;
+struct PeerOut {
+    cplx* y[MAX_PEERS];                  // rank p's work vector, already offset to MY first row
+    unsigned long long* flag[MAX_PEERS]; // rank p's flag word for MY rank
+    unsigned int* counter;               // local: blocks of this launch that have finished
+    unsigned long long epoch;
+    int npeers;
+};
+struct PeerWait {
+    const unsigned long long* flags = nullptr;  // nullptr: nothing to wait for
+    int nflags = 0;
+    unsigned long long epoch = 0;
+    int* err = nullptr;                  // mapped host int, set to 1 when the wait timed out
+};
+cudaError_t launch_zgemv_peer(const cplx* A, uint64_t lda, uint64_t nrows, uint64_t ncols, const cplx* x, const PeerOut& po,
+                              cudaStream_t s);
+bool mgs_peer_wait_capable(uint64_t n, uint32_t restart, bool allow_grid);
 cudaError_t launch_zgemv(const cplx* A, uint64_t lda, uint64_t nrows, uint64_t ncols, const cplx* x, cplx* y, cudaStream_t s);
 cudaError_t launch_zgemv_t(const cplx* A, uint64_t lda, uint64_t nrows, uint64_t ncols, const cplx* x, cplx* y, cudaStream_t s);
 // Lmat (may be NULL): (ldl x ldl) scratch for the Gram triangle of the current restart cycle (low-sync kernel)
 cudaError_t launch_mgs(const cplx* V, uint64_t ldv, cplx* w, int j, uint64_t n, cplx* hcol, cplx* vnext, const cplx* pinv,
                        int direct_scale, cplx* Lmat, int ldl, cplx* scratch, cplx* hcol_host, bool* wrote_host, bool allow_grid,
-                       cudaStream_t s);  // hcol_host: mapped pinned copy of the column (written by the kernel when *wrote_host)
+                       const PeerWait& pw, cudaStream_t s);  // hcol_host: mapped pinned copy of the column (written by the kernel when *wrote_host)
 size_t mgs_scratch_elems();  // cplx elements of scratch launch_mgs needs after the ldl*ldl Gram triangle
 cudaError_t launch_residual(const cplx* b, const cplx* ax, cplx* r, uint64_t n, double* out, const cplx* pinv, cudaStream_t s);
 cudaError_t launch_zgemm_block(const cplx* A, uint64_t lda, uint64_t nrows, uint64_t ncols, const cplx* X, cplx* Y, int nrhs,
