@@ -269,7 +269,12 @@ def run_native(args):
     wl = workload(args.workload)
     mesh = wl["mesh"]
     n = mesh.num_dofs
-    overlap = not args.no_overlap
+    # schedule: with 1-4 GPUs the FP64 assembly of frequency f+1 hides under the HBM-bound solve of f (measured 4-6 %
+    # faster); at 8 GPUs the slabs are small, the solver owns the GPU (whole-GPU Gram-Schmidt kernel, ZGEMV epilogue
+    # storing A v into the peers' memory) and the sequential schedule measured faster
+    overlap = (world <= 4) if args.schedule == "auto" else (args.schedule == "pipelined")
+    if args.no_overlap:
+        overlap = False
     driver = SweepDriver(mesh, local_rank, rank, world, nccl_id, solve_stream=s_solve.cuda_stream,
                          assembly_stream=s_asm.cuda_stream, overlap=overlap, background_blocks_per_sm=args.background)
     ctx = driver.ctx_solve
@@ -410,6 +415,9 @@ def run_native(args):
                    "l2": "inputs larger than L2: the matrix slab is re-streamed from HBM by every matvec",
                    "schedule": ("sweep pipeline: assembly of frequency f+1 on a second stream/buffer overlaps the solve of f"
                                 if overlap else "sequential: assemble then solve"),
+                   "exchange": ("single GPU" if world == 1 else
+                                ("peer memory: ZGEMV epilogue stores A v into every rank's work vector (NVLink), consumer waits on in-data flags"
+                                 if ctx.peer_exchange_active() and not overlap else "NCCL all-gather of A v per Arnoldi step")),
                    "frequencies_timed": [st["fi"] for st in stats]},
         "roofline": {"kernel": "zgemv_kernel", "bound": "hbm", "achieved": mv_gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": mv_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
@@ -466,6 +474,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--background", type=int, default=1, help="blocks/SM of the background assembly kernel in the sweep pipeline")
     ap.add_argument("--no-overlap", action="store_true", help="do not overlap assembly(f+1) with solve(f)")
+    ap.add_argument("--schedule", choices=["auto", "pipelined", "sequential"], default="auto",
+                    help="auto: pipelined sweep on 1-4 GPUs, sequential at 8 GPUs on")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3  # timing rule: W >= 3

@@ -104,6 +104,14 @@ public:
     Context(const Context&) = delete;
     Context& operator=(const Context&) = delete;
     bemb200_ctx* handle() const { return h_; }
+    // frequency-sweep controls (no counterpart in the reference: its sweep is a serial loop, bem_solver.rs:403-432)
+    void set_background(int blocks_per_sm) { check(bemb200_ctx_set_background(h_, blocks_per_sm), h_); }
+    void set_shared_gpu(bool shared) { check(bemb200_ctx_set_shared_gpu(h_, shared ? 1 : 0), h_); }
+    bool peer_exchange_active() const {
+        int a = 0;
+        check(bemb200_ctx_peer_exchange_active(h_, &a), h_);
+        return a != 0;
+    }
 
 private:
     bemb200_ctx* h_ = nullptr;

@@ -9,12 +9,12 @@
 #include "../../include/bemb200.h"
 #include "internal.h"
 
-// Peer-memory exchange of the row-sharded solve: one buffer per rank (flags + two work vectors,
+// Peer-memory exchange of the row-sharded solve: one buffer per rank (two flag-in-data work vectors,
 // alternating by epoch), exported with CUDA IPC and mapped by every other rank of the node.
 struct PeerExchange {
     bool tried = false, ok = false;
     uint64_t npad = 0;                 // elements per work vector
-    unsigned char* local = nullptr;    // [flags: 8 x u64 | counter | pad to 256 B][w0: npad cplx][w1: npad cplx]
+    unsigned char* local = nullptr;    // [256 B header][w0: npad x 2 uint4][w1: npad x 2 uint4]  (flag-in-data work vectors)
     unsigned char* base[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // every rank's buffer
     unsigned long long epoch = 0;      // last epoch published (identical on all ranks: collective call sequence)
     int* err_h = nullptr;              // mapped pinned int: a consumer kernel timed out waiting for a peer

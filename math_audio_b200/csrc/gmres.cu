@@ -101,7 +101,7 @@ static int ensure_peer_exchange(bemb200_ctx* ctx, uint64_t npad) {
     px.tried = true;
     px.npad = npad;
     const int P = ctx->nranks;
-    const size_t bytes = PX_HEADER + 2 * npad * sizeof(cplx);
+    const size_t bytes = PX_HEADER + 2 * npad * 2 * sizeof(uint4);  // two epochs x npad elements x 32 B
     int ok = 1;
     cudaIpcMemHandle_t mine;
     std::memset(&mine, 0, sizeof(mine));
@@ -154,8 +154,8 @@ static int ensure_peer_exchange(bemb200_ctx* ctx, uint64_t npad) {
     return BEMB200_OK;
 }
 
-static inline cplx* px_work(const PeerExchange& px, int p, unsigned long long epoch) {
-    return reinterpret_cast<cplx*>(px.base[p] + PX_HEADER) + (epoch & 1ull) * px.npad;
+static inline uint4* px_work(const PeerExchange& px, int p, unsigned long long epoch) {
+    return reinterpret_cast<uint4*>(px.base[p] + PX_HEADER) + (epoch & 1ull) * 2 * px.npad;
 }
 
 static int ensure_workspace(bemb200_matrix* m, uint32_t restart) {
@@ -298,9 +298,13 @@ static int gmres_core(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t max_it
     const int ldh = mm;
     std::vector<cplx> h, cs, sn, g, y;
     const bool allow_grid = ctx->shared_gpu.load() == 0;
-    rc = ensure_peer_exchange(ctx, ws->npad);
-    if (rc != BEMB200_OK) return rc;
-    const bool peer_fused = ctx->nranks > 1 && ctx->px.ok && ctx->px.npad >= ws->npad && ws->npad == ws->chunk * (uint64_t)ctx->nranks &&
+    if (allow_grid) {  // same value on every rank (collective call sequence)
+        rc = ensure_peer_exchange(ctx, ws->npad);
+        if (rc != BEMB200_OK) return rc;
+    }
+    // (with assembly kernels of another stream on the GPU the spinning consumer measured slower than NCCL: keep it for
+    //  the solver-owns-the-GPU case)
+    const bool peer_fused = allow_grid && ctx->nranks > 1 && ctx->px.ok && ctx->px.npad >= ws->npad && ws->npad == ws->chunk * (uint64_t)ctx->nranks &&
                             mgs_peer_wait_capable(n, restart, allow_grid);
     struct PeerErrCheck {  // a consumer kernel that gave up waiting for a peer poisons the solve: report it
         bemb200_ctx* c; bool on;
@@ -338,21 +342,16 @@ static int gmres_core(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t max_it
             if (peer_fused) {
                 // ZGEMV epilogue stores this rank's slab into every rank's work vector; no all-gather
                 PeerExchange& px = ctx->px;
-                const unsigned long long epoch = ++px.epoch;
+                unsigned long long epoch = ++px.epoch;
+                if ((uint32_t)epoch == 0) epoch = ++px.epoch;  // 0 is the "never written" flag
                 PeerOut po{};
                 po.npeers = ctx->nranks;
-                po.epoch = epoch;
-                po.counter = reinterpret_cast<unsigned int*>(px.local + 8 * sizeof(unsigned long long));
-                for (int p = 0; p < ctx->nranks; ++p) {
-                    po.y[p] = px_work(px, p, epoch) + (uint64_t)ctx->rank * ws->chunk;
-                    po.flag[p] = reinterpret_cast<unsigned long long*>(px.base[p]) + ctx->rank;
-                }
+                po.epoch = (uint32_t)epoch;
+                for (int p = 0; p < ctx->nranks; ++p) po.ll[p] = px_work(px, p, epoch) + 2 * (uint64_t)ctx->rank * ws->chunk;
                 BEMB_CUDA(ctx, launch_zgemv_peer(m->A, m->n_cols, nloc, m->n_cols, ws->V + (uint64_t)j * ws->npad, po, s));
                 BEMB_CUDA(ctx, cudaEventRecord(ws->it_ev1[j], s));
-                wvec = px_work(px, ctx->rank, epoch);
-                pw.flags = reinterpret_cast<const unsigned long long*>(px.local);
-                pw.nflags = ctx->nranks;
-                pw.epoch = epoch;
+                pw.ll = px_work(px, ctx->rank, epoch);
+                pw.epoch = (uint32_t)epoch;
                 pw.err = px.err_h;
             } else {
                 cplx* yloc = ws->w + (ctx->nranks > 1 ? (uint64_t)ctx->rank * ws->chunk : m->r0);

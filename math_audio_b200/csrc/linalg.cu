@@ -38,36 +38,69 @@ __device__ __forceinline__ void cfma(double& are, double& aim, double2 a, double
     aim = fma(a.y, x.x, aim);
 }
 
-// ---- peer-memory helpers (row-sharded solve: ZGEMV epilogue stores the slab of y straight into
-// every rank's work vector over NVLink, the consumer kernel waits on per-rank epoch flags) --------
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
+// ---- peer-memory helpers (row-sharded solve) -------------------------------------------------
+// The ZGEMV epilogue stores its slab of y straight into every rank's work vector over NVLink in
+// "flag-in-data" form: each complex number travels as two 16-byte stores {lo32, epoch, hi32, epoch}
+// whose 8-byte halves are written atomically, so the data is its own arrival flag -- no system
+// fence, no counter, no separate signal.  The consumer spins per element until all four epochs
+// match (bounded by PEER_WAIT_TIMEOUT_NS, failure reported through a mapped host int).
 __device__ __forceinline__ unsigned long long global_timer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-// All threads of the CTA call this; returns after every flag in flags[0..nflags) reached `epoch`
-// (or after PEER_WAIT_TIMEOUT_NS, recording the failure in *err -- never an unbounded spin).
+__device__ __forceinline__ void ll_store(uint4* dst, double re, double im, uint32_t flag) {
+    const uint32_t rl = (uint32_t)__double2loint(re), rh = (uint32_t)__double2hiint(re);
+    const uint32_t il = (uint32_t)__double2loint(im), ih = (uint32_t)__double2hiint(im);
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(rl), "r"(flag), "r"(rh), "r"(flag) : "memory");
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 1), "r"(il), "r"(flag), "r"(ih), "r"(flag) : "memory");
+}
 constexpr unsigned long long PEER_WAIT_TIMEOUT_NS = 4000000000ull;
-__device__ __forceinline__ void wait_peer_flags(const PeerWait& pw) {
-    if (pw.flags == nullptr) return;
-    if ((int)threadIdx.x < pw.nflags) {
-        const unsigned long long t0 = global_timer_ns();
-        while (ld_acquire_sys(pw.flags + threadIdx.x) < pw.epoch) {
-            if (global_timer_ns() - t0 > PEER_WAIT_TIMEOUT_NS) {
-                *reinterpret_cast<volatile int*>(pw.err) = 1;
+// loads N elements (element e at src + 2*(first + e*stride), skipped when first + e*stride >= len);
+// every pass issues all outstanding loads back to back, then re-polls only what has not arrived
+template <int N>
+__device__ __forceinline__ void ll_load_many(cplx (&out)[N], const uint4* src, uint64_t first, uint64_t stride, uint64_t len,
+                                             uint32_t flag, int* err) {
+    bool have[N];
+#pragma unroll
+    for (int e = 0; e < N; ++e) {
+        have[e] = first + (uint64_t)e * stride >= len;
+        out[e] = C(0, 0);
+    }
+    unsigned long long t0 = 0;
+    unsigned int spins = 0;
+    for (;;) {
+        uint4 a[N], b[N];
+#pragma unroll
+        for (int e = 0; e < N; ++e) {
+            if (!have[e]) {
+                const uint4* q = src + 2 * (first + (uint64_t)e * stride);
+                asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a[e].x), "=r"(a[e].y), "=r"(a[e].z), "=r"(a[e].w) : "l"(q) : "memory");
+                asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(b[e].x), "=r"(b[e].y), "=r"(b[e].z), "=r"(b[e].w) : "l"(q + 1) : "memory");
+            }
+        }
+        bool all = true;
+#pragma unroll
+        for (int e = 0; e < N; ++e) {
+            if (!have[e]) {
+                if (a[e].y == flag && a[e].w == flag && b[e].y == flag && b[e].w == flag) {
+                    have[e] = true;
+                    out[e] = C(__hiloint2double((int)a[e].z, (int)a[e].x), __hiloint2double((int)b[e].z, (int)b[e].x));
+                } else {
+                    all = false;
+                }
+            }
+        }
+        if (all) break;
+        if ((++spins & 63u) == 0) {
+            const unsigned long long t = global_timer_ns();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > PEER_WAIT_TIMEOUT_NS) {
+                *reinterpret_cast<volatile int*>(err) = 1;
                 break;
             }
         }
     }
-    __syncthreads();
 }
 
 template <int GEMV_RB, int GEMV_U, bool FUSED>
@@ -119,25 +152,14 @@ zgemv_kernel(const cplx* __restrict__ A, uint64_t lda, uint64_t nrows, uint64_t 
 #pragma unroll
             for (int w = 0; w < GEMV_THREADS / 32; ++w) { sr += red[tid][0][w]; si += red[tid][1][w]; }
             if (FUSED) {
-                for (int p = 0; p < po.npeers; ++p) po.y[p][rb + tid] = C(sr, si);  // NVLink stores (own rank: local)
-                __threadfence_system();
+#pragma unroll
+                for (int p = 0; p < MAX_PEERS; ++p)  // constant indices: the pointer table stays in the parameter bank
+                    if (p < po.npeers) ll_store(po.ll[p] + 2 * (rb + tid), sr, si, po.epoch);  // NVLink (own rank: local)
             } else {
                 y[rb + tid] = C(sr, si);
             }
         }
         __syncthreads();
-    }
-    if (FUSED) {
-        // last block to finish publishes this rank's epoch to every peer
-        if (tid == 0) {
-            __threadfence_system();
-            const unsigned int done = atomicAdd(po.counter, 1u);
-            if (done == gridDim.x - 1) {
-                *po.counter = 0;
-                __threadfence_system();
-                for (int p = 0; p < po.npeers; ++p) st_release_sys(po.flag[p], po.epoch);
-            }
-        }
     }
 }
 
@@ -199,10 +221,6 @@ __device__ __forceinline__ cplx cluster_allreduce(cplx v, ClusterShared& sh, int
     return t;
 }
 
-__device__ __forceinline__ cplx ldcg_c(const cplx* p) {  // L2 only: the data may have been stored by a peer GPU
-    const double2 v = __ldcg(reinterpret_cast<const double2*>(p));
-    return C(v.x, v.y);
-}
 __device__ __forceinline__ cplx ldg_c(const cplx* p) {
     double2 v = __ldg(reinterpret_cast<const double2*>(p));
     return C(v.x, v.y);
@@ -311,12 +329,13 @@ mgs_lowsync_kernel(const cplx* __restrict__ V, uint64_t ldv, const cplx* __restr
     const uint64_t end = begin + S < n ? begin + S : n;
     const uint64_t len = end > begin ? end - begin : 0;
 
-    wait_peer_flags(pw);  // row-sharded solve: every rank's slab of w has landed
     cplx wr[EPT], vj[EPT];
+    // row-sharded solve: w arrives from every rank's ZGEMV epilogue in flag-in-data form
+    if (pw.ll) ll_load_many<EPT>(wr, pw.ll + 2 * begin, (uint64_t)tid, (uint64_t)LS_THREADS, len, pw.epoch, pw.err);
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
         const uint64_t k = tid + (uint64_t)e * LS_THREADS;
-        wr[e] = k < len ? ldcg_c(w + begin + k) : C(0, 0);
+        if (!pw.ll) wr[e] = k < len ? w[begin + k] : C(0, 0);
         if (pinv && k < len) wr[e] = wr[e] * ldg_c(pinv + begin + k);
         vj[e] = (k < len) ? ldg_c(V + (uint64_t)j * ldv + begin + k) : C(0, 0);
     }
@@ -454,8 +473,6 @@ mgs_lowsync_kernel(const cplx* __restrict__ V, uint64_t ldv, const cplx* __restr
 // through a small global scratch and are added in fixed CTA order by every CTA (bit-identical
 // on every rank: the grid size depends on n only).
 // ------------------------------------------------------------------------------------------
-constexpr int GR_THREADS = 128;
-constexpr int GR_WARPS = GR_THREADS / 32;
 constexpr int GR_MAX_CTAS = 148;
 
 // 32 per-lane partial sums -> lane L ends up with the warp total of value L (31 exchanges
@@ -474,12 +491,13 @@ __device__ __forceinline__ double warp_reduce32(double (&v)[32], int lane) {
     return v[0];
 }
 
-template <int EPT>
+template <int EPT, int GR_THREADS>
 __global__ void __launch_bounds__(GR_THREADS)
 mgs_grid_kernel(const cplx* __restrict__ V, uint64_t ldv, const cplx* __restrict__ w, int j, uint64_t n, uint64_t S,
                 cplx* __restrict__ Lmat, int ldl, cplx* __restrict__ hcol, cplx* __restrict__ vnext, double breakdown_tol,
                 const cplx* __restrict__ pinv, int direct_scale, cplx* __restrict__ part, double* __restrict__ npart,
                 cplx* __restrict__ hcol_host, PeerWait pw) {
+    constexpr int GR_WARPS = GR_THREADS / 32;
     extern __shared__ __align__(16) unsigned char dyn[];
     // dynamic layout: warp_part[GR_WARPS][2*LS_MAXV] | a[LS_MAXV] | LsT[(j+1)*(j+1)]  (LsT[l*nv + k] = L_kl)
     cplx* warp_part = reinterpret_cast<cplx*>(dyn);
@@ -495,12 +513,12 @@ mgs_grid_kernel(const cplx* __restrict__ V, uint64_t ldv, const cplx* __restrict
     const uint64_t end = begin + S < n ? begin + S : n;
     const uint64_t len = end > begin ? end - begin : 0;
 
-    wait_peer_flags(pw);
     cplx wr[EPT], vj[EPT];
+    if (pw.ll) ll_load_many<EPT>(wr, pw.ll + 2 * begin, (uint64_t)tid, (uint64_t)GR_THREADS, len, pw.epoch, pw.err);
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
         const uint64_t k = tid + (uint64_t)e * GR_THREADS;
-        wr[e] = k < len ? ldcg_c(w + begin + k) : C(0, 0);
+        if (!pw.ll) wr[e] = k < len ? w[begin + k] : C(0, 0);
         if (pinv && k < len) wr[e] = wr[e] * ldg_c(pinv + begin + k);
         vj[e] = (k < len) ? ldg_c(V + (uint64_t)j * ldv + begin + k) : C(0, 0);
     }
@@ -1175,14 +1193,15 @@ static cudaError_t launch_mgs_lowsync(int cl, const cplx* V, uint64_t ldv, const
                           direct_scale, hcol_host, pw);
 }
 
-template <int EPT>
+template <int EPT, int GR_THREADS>
 static cudaError_t launch_mgs_grid(int G, const cplx* V, uint64_t ldv, const cplx* w, int j, uint64_t n, uint64_t S, cplx* Lmat,
                                    int ldl, cplx* hcol, cplx* vnext, const cplx* pinv, int direct_scale, cplx* scratch,
                                    cplx* hcol_host, const PeerWait& pw, cudaStream_t s) {
+    constexpr int GR_WARPS = GR_THREADS / 32;
     static bool attr_done = false;
     const size_t fixed = (size_t)(GR_WARPS * 2 * LS_MAXV + LS_MAXV) * sizeof(cplx);
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(mgs_grid_kernel<EPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(mgs_grid_kernel<EPT, GR_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)(fixed + (size_t)LS_MAXV * LS_MAXV * sizeof(cplx)));
         if (e != cudaSuccess) return e;
         attr_done = true;
@@ -1200,7 +1219,7 @@ static cudaError_t launch_mgs_grid(int G, const cplx* V, uint64_t ldv, const cpl
     cplx* part = scratch;
     double* npart = reinterpret_cast<double*>(scratch + (size_t)GR_MAX_CTAS * 2 * LS_MAXV);
     const double tol = 1e-14;
-    return cudaLaunchKernelEx(&cfg, mgs_grid_kernel<EPT>, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, tol, pinv, direct_scale,
+    return cudaLaunchKernelEx(&cfg, mgs_grid_kernel<EPT, GR_THREADS>, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, tol, pinv, direct_scale,
                               part, npart, hcol_host, pw);
 }
 
@@ -1215,7 +1234,7 @@ bool mgs_peer_wait_capable(uint64_t n, uint32_t restart, bool allow_grid) {
     if (restart + 1 > (uint32_t)LS_MAXV) return false;
     if (g_mgs_mode != 3 && g_mgs_mode != 0) return false;
     if (n <= 16ull * LS_THREADS * 8ull) return true;  // cluster low-sync kernel
-    return g_mgs_mode == 3 && allow_grid && n <= (uint64_t)GR_MAX_CTAS * GR_THREADS * 8ull;
+    return g_mgs_mode == 3 && allow_grid && n <= (uint64_t)GR_MAX_CTAS * 1024ull;
 }
 
 static cudaError_t launch_mgs_cluster_path(int mode_in, const cplx* V, uint64_t ldv, cplx* w, int j, uint64_t n, cplx* hcol,
@@ -1239,7 +1258,7 @@ static cudaError_t launch_mgs_cluster_path(int mode_in, const cplx* V, uint64_t 
         cudaGetLastError();
         g_mgs_mode = 2;
     }
-    if (pw.flags) return cudaErrorNotSupported;  // only the two low-sync kernels know how to wait for peer slabs
+    if (pw.ll) return cudaErrorNotSupported;  // only the two low-sync kernels know how to wait for peer slabs
     if ((g_mgs_mode == 0 || g_mgs_mode == 2) && n <= 16ull * 256ull * 8ull) {
         // register-resident w: 16 CTAs (non-portable cluster size) x 256 threads x <= 8 elements
         const int cl = n >= 2048 ? 16 : (n >= 512 ? 4 : 1);
@@ -1281,15 +1300,16 @@ cudaError_t launch_mgs(const cplx* V, uint64_t ldv, cplx* w, int j, uint64_t n, 
     *wrote_host = false;
     // mode 3 (default): whole-GPU cooperative kernel; the slice per CTA depends on n only
     static const bool force_grid = std::getenv("BEMB200_MGS_FORCE_GRID") != nullptr;
-    if (g_mgs_mode == 3 && (allow_grid || force_grid) && Lmat && scratch && j + 1 <= LS_MAXV && n >= 4096 && n <= (uint64_t)GR_MAX_CTAS * GR_THREADS * 8ull) {
+    if (g_mgs_mode == 3 && (allow_grid || force_grid) && Lmat && scratch && j + 1 <= LS_MAXV && n >= 4096 && n <= (uint64_t)GR_MAX_CTAS * 1024ull) {
         const int G = GR_MAX_CTAS;
         const uint64_t S = (n + G - 1) / G;
-        const uint64_t ept = (S + GR_THREADS - 1) / GR_THREADS;
         cudaError_t e;
-        if (ept <= 1) e = launch_mgs_grid<1>(G, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, scratch, hcol_host, pw, s);
-        else if (ept <= 2) e = launch_mgs_grid<2>(G, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, scratch, hcol_host, pw, s);
-        else if (ept <= 4) e = launch_mgs_grid<4>(G, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, scratch, hcol_host, pw, s);
-        else e = launch_mgs_grid<8>(G, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, scratch, hcol_host, pw, s);
+#define GRID_CASE(E, T) e = launch_mgs_grid<E, T>(G, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, scratch, hcol_host, pw, s)
+        if (S <= 128) GRID_CASE(1, 128);
+        else if (S <= 256) GRID_CASE(2, 128);
+        else if (S <= 512) GRID_CASE(2, 256);
+        else GRID_CASE(4, 256);
+#undef GRID_CASE
         if (e == cudaSuccess) { *wrote_host = hcol_host != nullptr; return e; }
         cudaGetLastError();  // cooperative launch not placeable on this device: cluster kernels from now on
         g_mgs_mode = 0;

@@ -3,23 +3,20 @@
 #include "internal.h"
 
 namespace bemb {
-// Row-sharded solve over peer memory (one process per GPU, buffers mapped with CUDA IPC):
-// PeerOut  - where the ZGEMV epilogue stores this rank's slab of y (every rank's work vector,
-//            own rank included) and which epoch flag it raises on each rank when the slab is out;
-// PeerWait - the flags (one per rank, local memory) a consumer kernel polls before reading y.
+// Row-sharded solve over peer memory (one process per GPU, buffers mapped with CUDA IPC), in
+// flag-in-data form: element i of the work vector is two uint4 {lo32, epoch, hi32, epoch} (re, im).
+// PeerOut  - every rank's buffer (own rank included), offset to MY first row, for the ZGEMV epilogue;
+// PeerWait - the local buffer a consumer kernel reads, spinning per element until the epoch matches.
 constexpr int MAX_PEERS = 8;
 struct PeerOut {
-    cplx* y[MAX_PEERS];                  // rank p's work vector, already offset to MY first row
-    unsigned long long* flag[MAX_PEERS]; // rank p's flag word for MY rank
-    unsigned int* counter;               // local: blocks of this launch that have finished
-    unsigned long long epoch;
+    uint4* ll[MAX_PEERS];
+    uint32_t epoch;
     int npeers;
 };
 struct PeerWait {
-    const unsigned long long* flags = nullptr;  // nullptr: nothing to wait for
-    int nflags = 0;
-    unsigned long long epoch = 0;
-    int* err = nullptr;                  // mapped host int, set to 1 when the wait timed out
+    const uint4* ll = nullptr;  // nullptr: plain work vector, nothing to wait for
+    uint32_t epoch = 0;
+    int* err = nullptr;         // mapped host int, set to 1 when a wait timed out
 };
 cudaError_t launch_zgemv_peer(const cplx* A, uint64_t lda, uint64_t nrows, uint64_t ncols, const cplx* x, const PeerOut& po,
                               cudaStream_t s);

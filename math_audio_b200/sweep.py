@@ -62,21 +62,26 @@ class SweepDriver:
             raise err[0]
         self.ctx_asm.set_background(self.background_blocks_per_sm)
         self.ctx_solve.set_shared_gpu(self.overlap)  # assembly kernels run beside the solve from here on
-        for i in range(len(cases)):
-            t = None
-            if i + 1 < len(cases):
-                if self.overlap:
-                    t = threading.Thread(target=self._assemble, args=((i + 1) % 2, cases[i + 1][0], cases[i + 1][1], mesh_arg, err))
-                    t.start()
-            system = self.buffers[i % 2]
-            self.asm_stats.append(system.matrix.assembly_stats())
-            op = bem.DenseOperator(system)
-            out.append(solve(i, system, op))
-            self.sol_stats.append(system.matrix.solver_stats())
-            if t is not None:
-                t.join()
-            elif i + 1 < len(cases):
-                self._assemble((i + 1) % 2, cases[i + 1][0], cases[i + 1][1], mesh_arg, err)
-            if err:
-                raise err[0]
+        try:
+            for i in range(len(cases)):
+                t = None
+                if i + 1 < len(cases):
+                    if self.overlap:
+                        t = threading.Thread(target=self._assemble, args=((i + 1) % 2, cases[i + 1][0], cases[i + 1][1], mesh_arg, err))
+                        t.start()
+                elif self.overlap:
+                    self.ctx_solve.set_shared_gpu(False)  # last case: nothing left to assemble beside this solve
+                system = self.buffers[i % 2]
+                self.asm_stats.append(system.matrix.assembly_stats())
+                op = bem.DenseOperator(system)
+                out.append(solve(i, system, op))
+                self.sol_stats.append(system.matrix.solver_stats())
+                if t is not None:
+                    t.join()
+                elif i + 1 < len(cases):
+                    self._assemble((i + 1) % 2, cases[i + 1][0], cases[i + 1][1], mesh_arg, err)
+                if err:
+                    raise err[0]
+        finally:
+            self.ctx_solve.set_shared_gpu(False)  # the solver owns the GPU again
         return out

@@ -35,6 +35,9 @@ extern "C" {
                                  cuda_stream: *mut c_void, out: *mut *mut bemb200_ctx) -> c_int;
     pub fn bemb200_nccl_unique_id(out: *mut u8) -> c_int;
     pub fn bemb200_ctx_destroy(ctx: *mut bemb200_ctx);
+    pub fn bemb200_ctx_set_background(ctx: *mut bemb200_ctx, blocks_per_sm: c_int) -> c_int;
+    pub fn bemb200_ctx_set_shared_gpu(ctx: *mut bemb200_ctx, shared: c_int) -> c_int;
+    pub fn bemb200_ctx_peer_exchange_active(ctx: *const bemb200_ctx, active: *mut c_int) -> c_int;
     pub fn bemb200_last_error(ctx: *const bemb200_ctx) -> *const c_char;
     pub fn bemb200_partition(n: u64, nranks: c_int, rank: c_int, row_begin: *mut u64, row_end: *mut u64);
     pub fn bemb200_mesh_stage(ctx: *mut bemb200_ctx, mesh: *const bemb200_mesh, out: *mut *mut bemb200_staged_mesh) -> c_int;

@@ -1,0 +1,77 @@
+"""Row-sharded parity check, one process per GPU:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 scripts/dist_parity.py
+
+Every rank assembles its row block, the ranks solve together (ZGEMV epilogue over peer memory or
+NCCL all-gather, BEMB200_PEER_FUSED=0 forces the latter) and each rank compares against the CPU
+oracle: slab entries (rel 1e-10), operator apply, GMRES iteration count (identical), solution
+(rel 1e-8) and bit-identity of the solution across ranks (replicated Arnoldi).  Exit code != 0 on
+any violation.  The oracle is the checker here, never the thing measured.
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+
+from math_audio_b200 import bem, dist as bdist
+from math_audio_b200.incident import IncidentField
+from math_audio_b200.mesh import generate_icosphere_mesh
+from math_audio_b200.types import PhysicsParams
+from oracle import oracle as orc
+
+rank, local, world = bdist.env_rank()
+torch.cuda.set_device(local)
+bdist.init_process_group("nccl")
+dev = torch.device("cuda", local)
+nid = bdist.broadcast_bytes(bem.Context.nccl_unique_id() if rank == 0 else None, 128, 0, device=dev)
+ctx = bem.Context(local, rank, world, nid)
+a = 0.1
+failures = []
+for sub, ka in [(3, 1.0), (3, 8.0), (4, 2.0)]:
+    mesh = generate_icosphere_mesh(a, sub)
+    if sub == 3:
+        mesh.is_eval[-7:] = 1  # n = 1273: uneven split
+    n = mesh.num_dofs
+    ph = PhysicsParams.from_wave_number(ka / a)
+    beta, _ = ph.burton_miller_beta_adaptive(a)
+    system = bem.build_tbem_system_with_beta(mesh, ph, beta, ctx=ctx)
+    r0, r1 = system.matrix.local_rows
+    Ao, rhso, _ = orc.assemble(mesh, ph.wave_number, beta)
+    Aloc = system.matrix.rows()
+    err = float(np.max(np.abs(Aloc - Ao[r0:r1]) / np.abs(Ao[r0:r1]))) if r1 > r0 else 0.0
+    b = system.rhs_full() + IncidentField.plane_wave_z().compute_rhs_with_beta(mesh.center[:n], mesh.normal[:n], ph, beta)
+    op = bem.DenseOperator(system)
+    x = np.random.default_rng(1).standard_normal(n) + 1j * np.random.default_rng(2).standard_normal(n)
+    y = op.apply(x)
+    apply_err = float(np.linalg.norm(y - Ao @ x) / np.linalg.norm(Ao @ x))
+    sol = bem.gmres(op, b, bem.GmresConfig(1000, 50, 1e-10))
+    xo, io = orc.gmres(Ao, b, max_iterations=1000, restart=50, tolerance=1e-10)
+    dx = float(np.linalg.norm(sol.x - xo) / np.linalg.norm(xo))
+    xs = torch.from_numpy(sol.x.view(np.float64).copy()).to(dev)
+    gl = [torch.zeros_like(xs) for _ in range(world)]
+    dist.all_gather(gl, xs)
+    same = all(bool((g == gl[0]).all()) for g in gl)
+    print(f"[rank {rank}] sub={sub} ka={ka} rows=[{r0},{r1}) entry_err={err:.2e} apply_err={apply_err:.2e} "
+          f"it={sol.iterations}/{io['iterations']} dx={dx:.2e} ranks_bit_identical={same} peer={ctx.peer_exchange_active()}", flush=True)
+    if err > 1e-10:
+        failures.append(f"entries {err}")
+    if apply_err > 1e-12:
+        failures.append(f"apply {apply_err}")
+    if sol.iterations != io["iterations"] or not sol.converged:
+        failures.append(f"iterations {sol.iterations} vs {io['iterations']}")
+    if dx > 1e-8:
+        failures.append(f"solution {dx}")
+    if not same:
+        failures.append("ranks disagree bitwise")
+if os.environ.get("BEMB200_EXPECT_PEER") == "1" and not ctx.peer_exchange_active():
+    failures.append("peer-memory exchange not active")
+dist.barrier()
+dist.destroy_process_group()
+if failures:
+    print(f"[rank {rank}] FAIL: {failures}", flush=True)
+    sys.exit(1)
+print(f"[rank {rank}] OK", flush=True)
