@@ -209,6 +209,12 @@ int bemb200_incident_rhs(const bemb200_staged_mesh* sm, const bemb200_physics* p
  * surface_velocity (may be NULL): num_dofs complex128 in DOF order; out [n_eval] complex128. */
 int bemb200_scattered_field(const bemb200_staged_mesh* sm, const bemb200_physics* phys, uint64_t n_eval, const double* eval_pts,
                             const double* surface_pressure, const double* surface_velocity, double* out);
+/* compute_rcs (math-bem/src/core/postprocess/pressure.rs:438-478) for n_dirs unit directions
+ * dirs[3*n_dirs]: F(d) = sum_j p_j exp(-i k c_j.d) A_j (i k)(n_j.d) with Element.center / normal /
+ * area as staged, rcs_out[d] = 4 pi |F(d)|^2.  surface_pressure: num_dofs complex128 in DOF order
+ * (the reference indexes it by boundary-element enumeration, identical for sequential dof maps). */
+int bemb200_compute_rcs(const bemb200_staged_mesh* sm, const bemb200_physics* phys, uint32_t n_dirs, const double* dirs,
+                        const double* surface_pressure, double* rcs_out);
 
 /* ---- measurement helpers ----------------------------------------------------------- */
 /* register-resident DFMA peak of this device in TFLOP/s (2 flop per DFMA) */

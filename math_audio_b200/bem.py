@@ -409,6 +409,22 @@ def compute_scattered_field(eval_points: np.ndarray, staged: StagedMesh, surface
     return out
 
 
+def compute_rcs(surface_pressure: np.ndarray, staged: StagedMesh, direction, physics: PhysicsParams):
+    """postprocess/pressure.rs:438-478 on the device.  ``direction``: one unit vector (returns a float, as the
+    reference) or an (M, 3) array (returns M values, one kernel launch)."""
+    ps = np.ascontiguousarray(surface_pressure, dtype=np.complex128)
+    if ps.shape != (staged.num_dofs,):
+        raise ValueError("surface_pressure must have num_dofs entries")
+    d = np.ascontiguousarray(direction, dtype=np.float64)
+    single = d.ndim == 1
+    d = d.reshape(-1, 3)
+    out = np.empty(d.shape[0], dtype=np.float64)
+    ph = _cphys(physics)
+    _capi.check(_capi.lib().bemb200_compute_rcs(staged._h, C.byref(ph), d.shape[0], _capi.ptr(d), _capi.ptr(ps), _capi.ptr(out)),
+                staged.ctx._h)
+    return float(out[0]) if single else out
+
+
 class IdentityPreconditioner:
     """traits.rs:377-385."""
 

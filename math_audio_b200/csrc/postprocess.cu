@@ -1,7 +1,8 @@
 // postprocess.cu -- the O(N) / O(M N) neighbours of the hot path:
 //   incident_rhs_kernel      IncidentField::compute_rhs_with_beta   math-bem/src/core/incident.rs:93-342
 //   scattered_field_kernel   compute_scattered_field                 math-bem/src/core/postprocess/pressure.rs:81-259
-// Both work on the staged (DOF-ordered) mesh so that a frequency sweep never leaves the device.
+//   rcs_kernel               compute_rcs                             math-bem/src/core/postprocess/pressure.rs:438-478
+// All work on the staged (DOF-ordered) mesh so that a frequency sweep never leaves the device.
 #include <vector>
 
 #include "api_internal.h"
@@ -117,6 +118,37 @@ scattered_field_kernel(const double* __restrict__ coords, uint32_t n, const doub
     }
 }
 
+// compute_rcs (pressure.rs:438-478): F(d) = sum_j p_j exp(-i k c_j.d) A_j (i k)(n_j.d), RCS = 4 pi |F|^2.
+// One block per direction, threads over elements, deterministic block reduction.
+__global__ void __launch_bounds__(256)
+rcs_kernel(const double* __restrict__ src, const double* __restrict__ area, uint32_t n, const double* __restrict__ dirs,
+           const cplx* __restrict__ ps, double k, double* __restrict__ out) {
+    __shared__ double red[2][8];
+    const double d0 = dirs[3 * blockIdx.x], d1 = dirs[3 * blockIdx.x + 1], d2 = dirs[3 * blockIdx.x + 2];
+    cplx acc = C(0, 0);
+    for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) {
+        const double* c = src + 8ull * j;
+        const double phase = -k * (c[0] * d0 + c[1] * d1 + c[2] * d2);
+        double sn, cs;
+        sincos(phase, &sn, &cs);
+        const double n_dot_d = c[3] * d0 + c[4] * d1 + c[5] * d2;
+        const cplx t = ((ps[j] * C(cs, sn)) * area[j]) * C(0.0, k);
+        acc += t * n_dot_d;
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        acc.re += __shfl_xor_sync(0xffffffffu, acc.re, m);
+        acc.im += __shfl_xor_sync(0xffffffffu, acc.im, m);
+    }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = acc.re; red[1][threadIdx.x >> 5] = acc.im; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tr = 0.0, ti = 0.0;
+        for (int w = 0; w < 8; ++w) { tr += red[0][w]; ti += red[1][w]; }
+        out[blockIdx.x] = 4.0 * 3.14159265358979323846 * (tr * tr + ti * ti);
+    }
+}
+
 }  // namespace
 
 extern "C" int bemb200_incident_rhs(const bemb200_staged_mesh* sm, const bemb200_physics* phys, double beta_re, double beta_im,
@@ -185,5 +217,32 @@ extern "C" int bemb200_scattered_field(const bemb200_staged_mesh* sm, const bemb
     cudaFreeAsync(dev, s); cudaFreeAsync(dps, s); cudaFreeAsync(dout, s);
     if (dvs) cudaFreeAsync(dvs, s);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "scattered_field");
+    return BEMB200_OK;
+}
+
+extern "C" int bemb200_compute_rcs(const bemb200_staged_mesh* sm, const bemb200_physics* phys, uint32_t n_dirs, const double* dirs,
+                                   const double* surface_pressure, double* rcs_out) {
+    if (!sm || !phys || !dirs || !surface_pressure || !rcs_out) return set_error(nullptr, BEMB200_EINVAL, "NULL argument");
+    bemb200_ctx* ctx = sm->ctx;
+    if (n_dirs == 0) return BEMB200_OK;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    BEMB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint32_t n = sm->dm.n;
+    double *ddirs = nullptr, *dout = nullptr;
+    cplx* dps = nullptr;
+    cudaStream_t s = ctx->stream;
+    BEMB_CUDA(ctx, cudaMallocAsync((void**)&ddirs, (size_t)n_dirs * 3 * sizeof(double), s));
+    BEMB_CUDA(ctx, cudaMallocAsync((void**)&dout, (size_t)n_dirs * sizeof(double), s));
+    BEMB_CUDA(ctx, cudaMallocAsync((void**)&dps, (size_t)(n ? n : 1) * sizeof(cplx), s));
+    cudaError_t e = cudaMemcpyAsync(ddirs, dirs, (size_t)n_dirs * 3 * sizeof(double), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess && n) e = cudaMemcpyAsync(dps, surface_pressure, (size_t)n * sizeof(cplx), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) {
+        rcs_kernel<<<n_dirs, 256, 0, s>>>(sm->dm.src, sm->dm.area, n, ddirs, dps, phys->wave_number, dout);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(rcs_out, dout, (size_t)n_dirs * sizeof(double), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFreeAsync(ddirs, s); cudaFreeAsync(dout, s); cudaFreeAsync(dps, s);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "compute_rcs");
     return BEMB200_OK;
 }

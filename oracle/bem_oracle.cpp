@@ -1088,6 +1088,30 @@ void orc_incident_rhs(int kind, const double* vec3, double amp_re, double amp_im
     }
 }
 
+// ---- compute_rcs: postprocess/pressure.rs:438-478 ---------------------------------------
+// F(d) = sum_j p_j exp(-i k c_j.d) A_j (i k) (n_j.d) over boundary elements in enumeration order;
+// RCS = 4 pi |F|^2 (unit-amplitude incident wave).
+void orc_compute_rcs(const orc_mesh* m, const double* surf_p, const double* dirs, uint64_t n_dirs, double k, double* out) {
+    const cplx* ps = (const cplx*)surf_p;
+    for (uint64_t id = 0; id < n_dirs; ++id) {
+        const double* d = dirs + 3 * id;
+        cplx far = C(0, 0);
+        uint64_t jb = 0;
+        for (uint64_t jel = 0; jel < m->n_elem; ++jel) {
+            if (m->is_eval[jel]) continue;
+            const double* c = m->center + 3 * jel;
+            const double* nn = m->normal + 3 * jel;
+            const double phase = -k * (c[0] * d[0] + c[1] * d[1] + c[2] * d[2]);
+            const cplx exp_phase = C(std::cos(phase), std::sin(phase));
+            const double n_dot_d = nn[0] * d[0] + nn[1] * d[1] + nn[2] * d[2];
+            const cplx ik = C(0.0, k);
+            far += ps[jb] * exp_phase * m->area[jel] * ik * n_dot_d;
+            jb++;
+        }
+        out[id] = 4.0 * PI * (far.re * far.re + far.im * far.im);
+    }
+}
+
 // ---- field evaluation: postprocess/pressure.rs:81-259 ----------------------------
 // p_scat(x) = sum_j integrate_element_field (7-point rule; Quad4 = its first triangle)
 void orc_scattered_field(const orc_mesh* m, const double* eval_pts, uint64_t n_eval, const double* surf_p,

@@ -294,6 +294,16 @@ def scattered_field(mesh, eval_points, surface_pressure, k, surface_velocity=Non
     return out
 
 
+def compute_rcs(mesh, surface_pressure, directions, k):
+    """postprocess/pressure.rs:438-478 for one or more unit directions."""
+    cm = _cmesh(mesh)
+    ps = np.ascontiguousarray(surface_pressure, dtype=np.complex128)
+    dirs = np.ascontiguousarray(directions, dtype=np.float64).reshape(-1, 3)
+    out = np.zeros(dirs.shape[0], dtype=np.float64)
+    lib().orc_compute_rcs(C.byref(cm), _p(ps), _p(dirs), C.c_uint64(dirs.shape[0]), C.c_double(k), _p(out))
+    return out
+
+
 def mie_rigid_sphere(k, radius, num_terms, r, theta):
     r = np.ascontiguousarray(r, dtype=np.float64)
     theta = np.ascontiguousarray(theta, dtype=np.float64)

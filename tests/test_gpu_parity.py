@@ -337,6 +337,12 @@ def test_incident_rhs_and_field_evaluation_on_device(bem, orc):
             got = bem.compute_scattered_field(pts, st, p, vel, ph)
             ref = orc.scattered_field(mesh, pts, p, ph.wave_number, surface_velocity=vel)
             assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-12
+        # compute_rcs (pressure.rs:438-478): 32 directions in one launch, and the scalar form
+        dirs = np.array(fibonacci_directions(32))
+        ref = orc.compute_rcs(mesh, p, dirs, ph.wave_number)
+        got = bem.compute_rcs(p, st, dirs, ph)
+        assert got.shape == (32,) and np.max(np.abs(got - ref) / ref) < 1e-11
+        assert abs(bem.compute_rcs(p, st, dirs[3], ph) - ref[3]) / ref[3] < 1e-11
 
 
 def test_sweep_driver_equals_sequential(bem):

@@ -299,6 +299,22 @@ def test_sphere_rcs_limits(orc):
     assert abs(rcs / (2.0 * math.pi) - 1.0) < 0.2
 
 
+def test_compute_rcs_single_element_closed_form(orc):
+    """pressure.rs:438-478 on one element: F = p exp(-i k c.d) A (i k)(n.d)  =>  RCS = 4 pi (|p| A k n.d)^2."""
+    from math_audio_b200.mesh import mesh_from_data
+
+    nodes = np.array([[0.2, 0.1, 0.3], [1.2, 0.1, 0.3], [0.2, 1.1, 0.3]])
+    mesh = mesh_from_data(nodes, [[0, 1, 2]])
+    k = 3.7
+    p = np.array([0.8 - 0.6j])
+    d = np.array([[0.0, 0.6, 0.8], [0.0, 0.0, 1.0], [1.0, 0.0, 0.0]])
+    got = orc.compute_rcs(mesh, p, d, k)
+    ndotd = d @ mesh.normal[0]
+    expect = 4 * math.pi * (abs(p[0]) * mesh.area[0] * k * ndotd) ** 2
+    assert np.allclose(got, expect, rtol=1e-13, atol=1e-300)
+    assert got[2] == 0.0  # grazing direction: n.d = 0
+
+
 def test_mie_finite(orc):
     p = orc.mie_rigid_sphere(1.0, 1.0, 20, [2.0, 2.0, 2.0], [0.0, math.pi / 2, math.pi])
     assert np.isfinite(p.real).all() and np.isfinite(p.imag).all()
