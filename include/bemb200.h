@@ -216,6 +216,43 @@ int bemb200_scattered_field(const bemb200_staged_mesh* sm, const bemb200_physics
 int bemb200_compute_rcs(const bemb200_staged_mesh* sm, const bemb200_physics* phys, uint32_t n_dirs, const double* dirs,
                         const double* surface_pressure, double* rcs_out);
 
+/* ---- room-acoustics dense path: math-bem/src/room_acoustics/solver.rs -------
+ * Point collocation on a RoomMesh (math-xem-common/src/types.rs:185-192): nodes [n_nodes*3],
+ * conn [n_elem*4] node indices (triangles: conn[4e+3] = 0xFFFFFFFF).  Staging computes
+ * element_center_and_normal / element_area (solver.rs:38-122) on the device, once per mesh. */
+typedef struct bemb200_room_mesh bemb200_room_mesh;
+int bemb200_room_mesh_stage(bemb200_ctx* ctx, const double* nodes, uint64_t n_nodes, const uint32_t* conn, uint64_t n_elem,
+                            bemb200_room_mesh** out);
+void bemb200_room_mesh_free(bemb200_room_mesh* rm);
+uint64_t bemb200_room_mesh_num_elements(const bemb200_room_mesh* rm);
+/* staged element data back to the host (any pointer may be NULL): center[3n], normal[3n], area[n] */
+int bemb200_room_mesh_geometry(const bemb200_room_mesh* rm, double* center, double* normal, double* area);
+/* build_bem_matrix_parallel (solver.rs:448-493): rows [row_begin, row_end) of
+ * A[i,j] = dG/dn(|c_i - c_j|, k, (c_i - c_j).n_i / r) area_j, A[j,j] = (0, -k/2pi) area_j, into a
+ * bemb200_matrix handle (NULL *inout: allocate; else reuse) that bemb200_apply / bemb200_gmres accept
+ * (solve_bem_system, solver.rs:412-445 = gmres(100 cycles, restart 50, tol 1e-6) on it).
+ * kernel_ms (may be NULL): device time of the assembly kernel. */
+int bemb200_room_assemble(bemb200_ctx* ctx, const bemb200_room_mesh* rm, double k, uint64_t row_begin, uint64_t row_end,
+                          bemb200_matrix** inout, double* kernel_ms);
+/* Source (math-xem-common/src/source.rs:160-219) as the device needs it: amplitude already
+ * multiplied by crossover.amplitude_at_frequency(f); directivity = DirectivityPattern.magnitude,
+ * row-major [n_vertical][n_horizontal], sampled every 10 degrees, or NULL for omnidirectional. */
+typedef struct bemb200_room_source {
+    double position[3];
+    double amplitude;
+    const double* directivity;
+    uint32_t n_horizontal, n_vertical;
+} bemb200_room_source;
+/* calculate_incident_field_derivative_parallel (solver.rs:638-679):
+ * rhs_i = - sum_s dG/dn(|c_i - x_s|, k, (c_i - x_s).n_i / r) amplitude_towards_s(c_i).
+ * Result (num_elements complex128) to rhs_host and/or rhs_dev (either may be NULL). */
+int bemb200_room_incident_rhs(const bemb200_room_mesh* rm, double k, uint32_t n_sources, const bemb200_room_source* sources,
+                              double* rhs_host, double* rhs_dev);
+/* calculate_field_pressure_bem_parallel (solver.rs:687-748) at points [n_points*3]:
+ * out_p = sum_s G(|x - x_s|) amplitude_towards_s(x) + sum_j dG/dn(|x - c_j|, k, (x - c_j).n_j / r) p_j area_j */
+int bemb200_room_field_pressure(const bemb200_room_mesh* rm, double k, uint32_t n_sources, const bemb200_room_source* sources,
+                                uint64_t n_points, const double* points, const double* surface_pressure, double* out);
+
 /* ---- measurement helpers ----------------------------------------------------------- */
 /* register-resident DFMA peak of this device in TFLOP/s (2 flop per DFMA) */
 int bemb200_measure_fp64_peak(bemb200_ctx* ctx, double* tflops);

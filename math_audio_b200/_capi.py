@@ -46,6 +46,11 @@ class CAssemblyStats(C.Structure):
                 ("total_launches", C.c_uint64), ("far_ms", C.c_double), ("total_ms", C.c_double)]
 
 
+class CRoomSource(C.Structure):
+    _fields_ = [("position", C.c_double * 3), ("amplitude", C.c_double), ("directivity", C.c_void_p),
+                ("n_horizontal", C.c_uint32), ("n_vertical", C.c_uint32)]
+
+
 # every symbol include/bemb200.h declares: (restype, argtypes)
 _VP = C.c_void_p
 _PP = C.POINTER(C.c_void_p)
@@ -93,6 +98,13 @@ SYMBOLS = {
     "bemb200_incident_rhs": (C.c_int, [_VP, C.POINTER(CPhysics), C.c_double, C.c_double, C.c_uint32, _VP, _VP, _VP, _VP, _VP]),
     "bemb200_scattered_field": (C.c_int, [_VP, C.POINTER(CPhysics), C.c_uint64, _VP, _VP, _VP, _VP]),
     "bemb200_compute_rcs": (C.c_int, [_VP, C.POINTER(CPhysics), C.c_uint32, _VP, _VP, _VP]),
+    "bemb200_room_mesh_stage": (C.c_int, [_VP, _VP, C.c_uint64, _VP, C.c_uint64, _PP]),
+    "bemb200_room_mesh_free": (None, [_VP]),
+    "bemb200_room_mesh_num_elements": (C.c_uint64, [_VP]),
+    "bemb200_room_mesh_geometry": (C.c_int, [_VP, _VP, _VP, _VP]),
+    "bemb200_room_assemble": (C.c_int, [_VP, _VP, C.c_double, C.c_uint64, C.c_uint64, _PP, C.POINTER(C.c_double)]),
+    "bemb200_room_incident_rhs": (C.c_int, [_VP, C.c_double, C.c_uint32, C.POINTER(CRoomSource), _VP, _VP]),
+    "bemb200_room_field_pressure": (C.c_int, [_VP, C.c_double, C.c_uint32, C.POINTER(CRoomSource), C.c_uint64, _VP, _VP, _VP]),
     "bemb200_measure_fp64_peak": (C.c_int, [_VP, C.POINTER(C.c_double)]),
     "bemb200_selftest_math": (C.c_int, [_VP, C.c_uint64, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "bemb200_measure_allgather": (C.c_int, [_VP, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_double)]),

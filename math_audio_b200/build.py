@@ -30,6 +30,7 @@ UNITS = {
     "gmres.cu": [],
     "block_gmres.cu": [],
     "postprocess.cu": ["-fmad=false"],
+    "room.cu": [],
     "api.cu": [],
 }
 

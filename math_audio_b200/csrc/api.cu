@@ -374,6 +374,14 @@ static int matrix_alloc(bemb200_ctx* ctx, uint64_t n_rows, uint64_t n_cols, uint
     return BEMB200_OK;
 }
 
+}  // extern "C" (reopened below)
+namespace bemb {
+int matrix_alloc_plain(bemb200_ctx* ctx, uint64_t n_rows, uint64_t n_cols, uint64_t r0, uint64_t r1, bemb200_matrix** out) {
+    return matrix_alloc(ctx, n_rows, n_cols, r0, r1, false, out);
+}
+}  // namespace bemb
+extern "C" {
+
 void bemb200_matrix_free(bemb200_matrix* m) {
     if (!m) return;
     cudaSetDevice(m->ctx->device);
