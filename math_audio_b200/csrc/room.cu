@@ -99,11 +99,20 @@ room_matrix_kernel(const double* __restrict__ center, const double* __restrict__
             v = C(0.0, -k / (2.0 * PI_D) * aj);
         } else {
             const double dx = __ldg(center + 3 * i) - cjx, dy = __ldg(center + 3 * i + 1) - cjy, dz = __ldg(center + 3 * i + 2) - cjz;
-            const double r = sqrt(dx * dx + dy * dy + dz * dz);
-            const double cosang = (dx * __ldg(normal + 3 * i) + dy * __ldg(normal + 3 * i + 1) + dz * __ldg(normal + 3 * i + 2)) / r;
-            v = dgreen(r, k, cosang);
-            v.re *= aj;
-            v.im *= aj;
+            const double r2 = dx * dx + dy * dy + dz * dz;
+            if (r2 < 1e-20) {  // r < 1e-10 (solver.rs:29-31)
+                v = C(0, 0);
+            } else {
+                // 1/r by rsqrt (1 ulp) instead of sqrt + two divisions: the kernel is FP64-issue bound, not store bound
+                const double inv_r = fast_rsqrt(r2);
+                const double r = r2 * inv_r;
+                const double dotn = dx * __ldg(normal + 3 * i) + dy * __ldg(normal + 3 * i + 1) + dz * __ldg(normal + 3 * i + 2);
+                const double sc = dotn * inv_r * (inv_r * inv_r) * (aj * (1.0 / (4.0 * PI_D)));  // cos_angle / (4 pi r^2) * area_j
+                const double kr = k * r;
+                double sn, cs;
+                fast_sincos(kr, sn, cs);
+                v = C((-cs - kr * sn) * sc, (kr * cs - sn) * sc);
+            }
         }
         __stcs(reinterpret_cast<double2*>(A + (i - row_begin) * (uint64_t)n + j), make_double2(v.re, v.im));
     }

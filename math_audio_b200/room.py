@@ -358,6 +358,56 @@ class RoomSimulation:
         return wavenumber(frequency, self.speed_of_sound)
 
 
+def simulation_from_config(config) -> tuple:
+    """RoomConfig (math-xem-common/src/config.rs:12-35, the JSON files under math-bem/configs/) -> (RoomSimulation,
+    mesh_resolution).  ``config``: dict or path of a JSON file.  Rectangular rooms only (the dense path of this
+    repository); sources keep their directivity (omnidirectional / custom) and crossover (config.rs:209-340)."""
+    import json
+    from pathlib import Path
+
+    if not isinstance(config, dict):
+        config = json.loads(Path(config).read_text())
+    rc = config["room"]
+    if rc.get("type") != "rectangular":
+        raise ValueError(f"room type {rc.get('type')!r} is not supported by the dense path (rectangular only)")
+    room = RectangularRoom(float(rc["width"]), float(rc["depth"]), float(rc["height"]))
+    sources = []
+    for sc in config["sources"]:
+        dc = sc.get("directivity", {"type": "omnidirectional"})
+        if dc.get("type", "omnidirectional") == "omnidirectional":
+            pattern = DirectivityPattern.omnidirectional()
+        elif dc["type"] == "custom":
+            mag = np.asarray(dc["magnitude"], dtype=np.float64)
+            if mag.size == 0:
+                raise ValueError("Empty magnitude array")
+            if mag.shape[0] != len(dc["vertical_angles"]) or mag.shape[1] != len(dc["horizontal_angles"]):
+                raise ValueError("directivity angles / magnitude shape mismatch")
+            pattern = DirectivityPattern(np.asarray(dc["horizontal_angles"], float), np.asarray(dc["vertical_angles"], float), mag)
+        else:
+            raise ValueError(f"unknown directivity type {dc['type']!r}")
+        xc = sc.get("crossover", {"type": "fullrange"})
+        kind = xc.get("type", "fullrange")
+        if kind == "fullrange":
+            xo = CrossoverFilter.full_range()
+        elif kind == "lowpass":
+            xo = CrossoverFilter.lowpass(float(xc["cutoff_freq"]), int(xc["order"]))
+        elif kind == "highpass":
+            xo = CrossoverFilter.highpass(float(xc["cutoff_freq"]), int(xc["order"]))
+        elif kind == "bandpass":
+            xo = CrossoverFilter.bandpass(float(xc["low_cutoff"]), float(xc["high_cutoff"]), int(xc["order"]))
+        else:
+            raise ValueError(f"unknown crossover type {kind!r}")
+        pos = sc["position"]
+        sources.append(Source([float(pos["x"]), float(pos["y"]), float(pos["z"])], pattern, float(sc.get("amplitude", 1.0)), xo,
+                              sc.get("name", "Source")))
+    lps = [[float(p["x"]), float(p["y"]), float(p["z"])] for p in config["listening_positions"]]
+    fc = config["frequencies"]
+    gen = lin_space if str(fc.get("spacing", "logarithmic")).lower() == "linear" else log_space
+    freqs = gen(float(fc["min_freq"]), float(fc["max_freq"]), int(fc["num_points"]))
+    sim = RoomSimulation(room, sources, lps, freqs, float(config.get("speed_of_sound", SPEED_OF_SOUND_20C)))
+    return sim, int(config.get("solver", {}).get("mesh_resolution", 2))
+
+
 def run_direct_gmres(simulation: RoomSimulation, mesh_resolution: int, ctx: Optional[bem.Context] = None,
                      details: Optional[list] = None) -> List[float]:
     """room_simulator_bem.rs:225-281 ("direct" mode): per frequency solve_bem_system + field pressure at the first
