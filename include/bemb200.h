@@ -29,6 +29,7 @@ extern "C" {
 #define BEMB200_ENOMEM (-4)     /* device or host allocation failed */
 #define BEMB200_ENCCL (-5)      /* NCCL error / NCCL not loadable */
 #define BEMB200_EUNSUPPORTED (-6)
+#define BEMB200_ESINGULAR (-7)   /* LuError::SingularMatrix (math-solvers/src/direct/lu.rs:15-21) */
 
 typedef struct bemb200_ctx bemb200_ctx;
 typedef struct bemb200_staged_mesh bemb200_staged_mesh;
@@ -178,6 +179,19 @@ int bemb200_matrix_diagonal(const bemb200_matrix* m, double* out);
 /* same with DEVICE pointers (b_dev, x0_dev or NULL, x_dev) */
 int bemb200_gmres_device(const bemb200_matrix* m, const double* b_dev, const double* x0_dev, uint32_t max_iterations,
                          uint32_t restart, double tolerance, double* x_dev, bemb200_gmres_info* info);
+/* lu_solve (math-solvers/src/direct/lu.rs:136-161; LAPACK zgesv in the reference's native build),
+ * the SolverMethod::Direct branch of BemSolver::solve_dense_system (bem_solver.rs:435-441): LU
+ * with partial pivoting + two triangular solves through cuSOLVER (zgetrf / zgetrs, loaded at run
+ * time).  Needs the whole matrix on one GPU.  overwrite_matrix = 0 factors a copy (the reference
+ * borrows `a`), 1 factors in place (the handle then holds L\U).  factor_ms (may be NULL): device
+ * time of the factorisation.  BEMB200_ESINGULAR = LuError::SingularMatrix. */
+int bemb200_lu_solve(const bemb200_matrix* m, const double* b, double* x_out, int overwrite_matrix, double* factor_ms);
+/* bicgstab (math-solvers/src/iterative/bicgstab.rs:53-215), the iterative solver of
+ * BemSolver::solve_dense_system (bem_solver.rs:435-463): x0 = 0, two operator applications per
+ * iteration, breakdown thresholds 1e-30, early exit on ||s||/||b|| < tol.  info->restarts = 0;
+ * `converged` false on breakdown / stagnation / exhausted budget (the reference never errors). */
+int bemb200_bicgstab(const bemb200_matrix* m, const double* b, uint32_t max_iterations, double tolerance, double* x_out,
+                     bemb200_gmres_info* info);
 /* Multi-RHS solve (BASELINE config 5): `nrhs` (<= 32) independent gmres() solves -- the reference
  * would loop `gmres(operator, b_s, config)` over the right-hand sides -- advanced in lockstep so
  * that they share ONE FP64 tensor-core block matvec per iteration (A is streamed once for all

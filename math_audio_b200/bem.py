@@ -498,6 +498,73 @@ def gmres(operator: DenseOperator, b: np.ndarray, config: GmresConfig) -> GmresS
     return gmres_with_guess(operator, b, None, config)
 
 
+@dataclass
+class BiCgstabConfig:
+    """math-solvers/src/iterative/bicgstab.rs:19-37."""
+
+    max_iterations: int = 1000
+    tolerance: float = 1e-6
+    print_interval: int = 0
+
+
+@dataclass
+class BiCgstabSolution:
+    """bicgstab.rs:40-50."""
+
+    x: np.ndarray
+    iterations: int
+    residual: float
+    converged: bool
+
+
+def bicgstab(operator: DenseOperator, b: np.ndarray, config: BiCgstabConfig) -> BiCgstabSolution:
+    """bicgstab.rs:53-215 on the device (x0 = 0; two ZGEMVs per iteration, fused vector kernels)."""
+    b = np.ascontiguousarray(b, dtype=np.complex128)
+    if b.shape != (operator.num_rows(),):
+        raise ValueError("b does not match the operator")
+    x = np.empty_like(b)
+    info = _capi.CGmresInfo()
+    _capi.check(_capi.lib().bemb200_bicgstab(operator.matrix._h, _capi.ptr(b), int(config.max_iterations), float(config.tolerance),
+                                             _capi.ptr(x), C.byref(info)), operator.matrix.ctx._h)
+    return BiCgstabSolution(x, int(info.iterations), float(info.residual), bool(info.converged))
+
+
+class LuError(RuntimeError):
+    """math-solvers/src/direct/lu.rs:15-21."""
+
+
+def lu_solve(a, b: np.ndarray, ctx: Optional[Context] = None, overwrite: bool = False, stats: Optional[dict] = None) -> np.ndarray:
+    """lu.rs:136-161 (LAPACK zgesv in the reference's native build) through cuSOLVER on the device.
+    ``a``: host matrix, DeviceMatrix, TbemSystem or DenseOperator.  Raises LuError for a singular matrix /
+    dimension mismatch."""
+    if isinstance(a, DenseOperator):
+        mat = a.matrix
+    elif isinstance(a, TbemSystem):
+        mat = a.matrix
+    elif isinstance(a, DeviceMatrix):
+        mat = a
+    else:
+        arr = np.asarray(a)
+        if arr.ndim != 2 or arr.shape[0] != arr.shape[1]:
+            raise LuError(f"Matrix dimensions mismatch: expected {arr.shape[0]}, got {arr.shape[-1]}")
+        mat = DenseOperator(arr, ctx).matrix
+        overwrite = True  # private copy
+    b = np.ascontiguousarray(b, dtype=np.complex128)
+    if b.shape != (mat.shape[0],):
+        raise LuError(f"Matrix dimensions mismatch: expected {mat.shape[0]}, got {b.shape[0]}")
+    x = np.empty_like(b)
+    ms = C.c_double(0.0)
+    try:
+        _capi.check(_capi.lib().bemb200_lu_solve(mat._h, _capi.ptr(b), _capi.ptr(x), 1 if overwrite else 0, C.byref(ms)), mat.ctx._h)
+    except _capi.Bemb200Error as e:
+        if e.code == -7:
+            raise LuError("Matrix is singular or nearly singular") from e
+        raise
+    if stats is not None:
+        stats["factor_ms"] = ms.value
+    return x
+
+
 def gmres_batched(operator: DenseOperator, b_all: np.ndarray, config: GmresConfig):
     """``[gmres(operator, b, config) for b in b_all]`` (the reference's way to solve several
     right-hand sides) executed in lockstep on the device with one tensor-core block matvec per

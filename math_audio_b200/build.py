@@ -31,6 +31,7 @@ UNITS = {
     "block_gmres.cu": [],
     "postprocess.cu": ["-fmad=false"],
     "room.cu": [],
+    "direct.cu": [],
     "api.cu": [],
 }
 

@@ -453,6 +453,119 @@ static int gmres_core(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t max_it
     return BEMB200_OK;
 }
 
+// ---- bicgstab (math-solvers/src/iterative/bicgstab.rs:53-215) with device vectors --------------
+// Complex / Complex as num-complex 0.4 evaluates it: (a conj(b)) / |b|^2
+static inline cplx cdiv(cplx a, cplx b) {
+    const double ns = norm_sqr(b);
+    return C((a.re * b.re + a.im * b.im) / ns, (a.im * b.re - a.re * b.im) / ns);
+}
+
+// b, x: device vectors of n (x is overwritten; the reference starts from x = 0).  Workspace rows
+// V[0..6] hold r, r0, p, v, s, t; two A-products per iteration through the same (row-sharded)
+// matvec as GMRES; every vector update is fused with the inner products that follow it and the
+// scalars (4 small D2H reads per iteration) drive the reference's control flow on the host.
+static int bicgstab_core(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t max_iterations, double tol, bemb200_gmres_info* info) {
+    bemb200_ctx* ctx = m->ctx;
+    GmresWorkspace* ws = m->ws;
+    const uint64_t n = m->n_rows;
+    cudaStream_t s = ctx->stream;
+    cplx* r = ws->V;
+    cplx* r0 = ws->V + 1 * ws->npad;
+    cplx* p = ws->V + 2 * ws->npad;
+    cplx* v = ws->V + 3 * ws->npad;
+    cplx* sv = ws->V + 4 * ws->npad;
+    cplx* t = ws->V + 5 * ws->npad;
+    cplx* dsc = ws->hcol_d;                 // device scalars
+    cplx* hsc = ws->hcol_h;                 // pinned mirror
+    auto fetch = [&](int cnt) -> int {
+        BEMB_CUDA(ctx, cudaMemcpyAsync(hsc, dsc, cnt * sizeof(cplx), cudaMemcpyDeviceToHost, s));
+        BEMB_CUDA(ctx, cudaStreamSynchronize(s));
+        return BEMB200_OK;
+    };
+    BEMB_CUDA(ctx, cudaMemsetAsync(x, 0, n * sizeof(cplx), s));
+    // r = r0 = b, p = v = 0; (b, b) gives ||b|| and the first rho_new = (r0, r)
+    BEMB_CUDA(ctx, cudaMemcpyAsync(r, b, n * sizeof(cplx), cudaMemcpyDeviceToDevice, s));
+    BEMB_CUDA(ctx, cudaMemcpyAsync(r0, b, n * sizeof(cplx), cudaMemcpyDeviceToDevice, s));
+    BEMB_CUDA(ctx, cudaMemsetAsync(p, 0, ws->npad * sizeof(cplx), s));
+    BEMB_CUDA(ctx, cudaMemsetAsync(v, 0, ws->npad * sizeof(cplx), s));
+    BEMB_CUDA(ctx, launch_bicg_dot(b, b, n, dsc, s));
+    m->last_launches += 1;
+    int rc = fetch(1);
+    if (rc != BEMB200_OK) return rc;
+    const double b_norm = std::sqrt(hsc[0].re);
+    if (b_norm < 1e-15) {
+        *info = bemb200_gmres_info{0, 0, 0.0, 1};
+        return BEMB200_OK;
+    }
+    cplx rho = C(1, 0), alpha = C(1, 0), omega = C(1, 0);
+    cplx rho_new = hsc[0];
+    double r_norm = b_norm;
+    for (uint32_t iter = 0; iter < max_iterations; ++iter) {
+        if (tnorm(rho_new) < 1e-30) {
+            *info = bemb200_gmres_info{iter, 0, r_norm / b_norm, 0};
+            return BEMB200_OK;
+        }
+        const cplx beta = cdiv(rho_new, rho) * cdiv(alpha, omega);
+        rho = rho_new;
+        BEMB_CUDA(ctx, launch_bicg_p(r, p, v, beta, omega, n, s));
+        rc = matvec(m, p, v, true);
+        if (rc != BEMB200_OK) return rc;
+        BEMB_CUDA(ctx, launch_bicg_dot(r0, v, n, dsc, s));
+        m->last_launches += 2;
+        rc = fetch(1);
+        if (rc != BEMB200_OK) return rc;
+        accumulate_matvec_time(m);
+        const cplx r0v = hsc[0];
+        if (tnorm(r0v) < 1e-30) {
+            *info = bemb200_gmres_info{iter, 0, r_norm / b_norm, 0};
+            return BEMB200_OK;
+        }
+        alpha = cdiv(rho, r0v);
+        BEMB_CUDA(ctx, launch_bicg_s(r, v, alpha, sv, n, dsc, s));
+        m->last_launches += 1;
+        rc = fetch(1);
+        if (rc != BEMB200_OK) return rc;
+        const double s_norm = std::sqrt(hsc[0].re);
+        if (s_norm / b_norm < tol) {
+            BEMB_CUDA(ctx, launch_bicg_axpy(x, p, alpha, n, s));
+            m->last_launches += 1;
+            BEMB_CUDA(ctx, cudaStreamSynchronize(s));
+            *info = bemb200_gmres_info{(uint64_t)iter + 1, 0, s_norm / b_norm, 1};
+            return BEMB200_OK;
+        }
+        rc = matvec(m, sv, t, true);
+        if (rc != BEMB200_OK) return rc;
+        BEMB_CUDA(ctx, launch_bicg_tt(t, sv, n, dsc, s));
+        m->last_launches += 1;
+        rc = fetch(2);
+        if (rc != BEMB200_OK) return rc;
+        accumulate_matvec_time(m);
+        const cplx tt = hsc[0];
+        if (tnorm(tt) < 1e-30) {
+            *info = bemb200_gmres_info{iter, 0, r_norm / b_norm, 0};
+            return BEMB200_OK;
+        }
+        omega = cdiv(hsc[1], tt);
+        BEMB_CUDA(ctx, launch_bicg_update(x, p, sv, t, r, r0, alpha, omega, n, dsc, s));
+        m->last_launches += 1;
+        rc = fetch(2);
+        if (rc != BEMB200_OK) return rc;
+        r_norm = std::sqrt(hsc[0].re);
+        rho_new = hsc[1];
+        const double rel = r_norm / b_norm;
+        if (rel < tol) {
+            *info = bemb200_gmres_info{(uint64_t)iter + 1, 0, rel, 1};
+            return BEMB200_OK;
+        }
+        if (tnorm(omega) < 1e-30) {
+            *info = bemb200_gmres_info{(uint64_t)iter + 1, 0, rel, 0};
+            return BEMB200_OK;
+        }
+    }
+    *info = bemb200_gmres_info{max_iterations, 0, r_norm / b_norm, 0};
+    return BEMB200_OK;
+}
+
 // the solver needs the whole operator: every row owned by exactly one rank, canonical split
 static int check_partition(bemb200_matrix* m) {
     bemb200_ctx* ctx = m->ctx;
@@ -529,6 +642,29 @@ int bemb200_gmres(const bemb200_matrix* cm, const double* b, const double* x0, u
     if (x0) BEMB_CUDA(ctx, cudaMemcpyAsync(ws->xout, x0, nb, cudaMemcpyHostToDevice, ctx->stream));
     else BEMB_CUDA(ctx, cudaMemsetAsync(ws->xout, 0, nb, ctx->stream));
     rc = gmres_core(m, ws->bin, ws->xout, max_iterations, restart, tolerance, info);
+    if (rc != BEMB200_OK) return rc;
+    BEMB_CUDA(ctx, cudaMemcpyAsync(x_out, ws->xout, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    BEMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BEMB200_OK;
+}
+
+int bemb200_bicgstab(const bemb200_matrix* cm, const double* b, uint32_t max_iterations, double tolerance, double* x_out,
+                     bemb200_gmres_info* info) {
+    bemb200_matrix* m = const_cast<bemb200_matrix*>(cm);
+    if (!m || !b || !x_out || !info) return set_error(nullptr, BEMB200_EINVAL, "NULL argument");
+    bemb200_ctx* ctx = m->ctx;
+    if (m->n_rows != m->n_cols) return set_error(ctx, BEMB200_EINVAL, "bicgstab needs a square operator");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    BEMB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = check_partition(m);
+    if (rc != BEMB200_OK) return rc;
+    rc = ensure_workspace(m, 8);
+    if (rc != BEMB200_OK) return rc;
+    reset_stats(m);
+    GmresWorkspace* ws = m->ws;
+    const size_t nb = m->n_rows * sizeof(cplx);
+    BEMB_CUDA(ctx, cudaMemcpyAsync(ws->bin, b, nb, cudaMemcpyHostToDevice, ctx->stream));
+    rc = bicgstab_core(m, ws->bin, ws->xout, max_iterations, tolerance, info);
     if (rc != BEMB200_OK) return rc;
     BEMB_CUDA(ctx, cudaMemcpyAsync(x_out, ws->xout, nb, cudaMemcpyDeviceToHost, ctx->stream));
     BEMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -765,6 +765,107 @@ residual_cluster_kernel(const cplx* __restrict__ b, const cplx* __restrict__ ax,
 }
 
 // ------------------------------------------------------------------------------------------
+// BiCGSTAB vector kernels (math-solvers/src/iterative/bicgstab.rs:88-190): every update of the
+// iteration fused with the inner products that follow it, reduced over an 8-CTA cluster in a
+// fixed order (bit-deterministic, identical on every rank of a row-sharded solve).
+//   out[0..1] = sum conj(a) b   (inner_product, blas_helpers.rs:21-33)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(VEC_THREADS)
+bicg_dot_kernel(const cplx* __restrict__ a, const cplx* __restrict__ b, uint64_t n, uint64_t S, cplx* __restrict__ out) {
+    __shared__ ClusterShared sh;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned me = cluster.block_rank();
+    const uint64_t begin = (uint64_t)me * S, end = begin + S < n ? begin + S : n;
+    cplx acc = C(0, 0);
+    for (uint64_t k = begin + threadIdx.x; k < end; k += blockDim.x) {
+        const cplx x = a[k], y = b[k];
+        acc.re = fma(x.re, y.re, fma(x.im, y.im, acc.re));
+        acc.im = fma(x.re, y.im, fma(-x.im, y.re, acc.im));
+    }
+    const cplx t = cluster_allreduce(acc, sh, 0);
+    if (me == 0 && threadIdx.x == 0) out[0] = t;
+    cluster.sync();
+}
+
+// p = r + beta (p - omega v)       (bicgstab.rs:111)
+__global__ void bicg_p_kernel(const cplx* __restrict__ r, cplx* __restrict__ p, const cplx* __restrict__ v, cplx beta, cplx omega, uint64_t n) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const cplx d = p[k] - v[k] * omega;
+    p[k] = r[k] + d * beta;
+}
+
+// s = r - alpha v ; out[0].re = ||s||^2        (bicgstab.rs:129-132)
+__global__ void __launch_bounds__(VEC_THREADS)
+bicg_s_kernel(const cplx* __restrict__ r, const cplx* __restrict__ v, cplx alpha, cplx* __restrict__ s, uint64_t n, uint64_t S,
+              cplx* __restrict__ out) {
+    __shared__ ClusterShared sh;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned me = cluster.block_rank();
+    const uint64_t begin = (uint64_t)me * S, end = begin + S < n ? begin + S : n;
+    cplx acc = C(0, 0);
+    for (uint64_t k = begin + threadIdx.x; k < end; k += blockDim.x) {
+        const cplx x = r[k] - v[k] * alpha;
+        s[k] = x;
+        acc.re = fma(x.re, x.re, fma(x.im, x.im, acc.re));
+    }
+    const cplx t = cluster_allreduce(acc, sh, 0);
+    if (me == 0 && threadIdx.x == 0) out[0] = t;
+    cluster.sync();
+}
+
+// out[0] = (t, t), out[1] = (t, s)          (bicgstab.rs:147-160)
+__global__ void __launch_bounds__(VEC_THREADS)
+bicg_tt_kernel(const cplx* __restrict__ t, const cplx* __restrict__ s, uint64_t n, uint64_t S, cplx* __restrict__ out) {
+    __shared__ ClusterShared sh;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned me = cluster.block_rank();
+    const uint64_t begin = (uint64_t)me * S, end = begin + S < n ? begin + S : n;
+    cplx a0 = C(0, 0), a1 = C(0, 0);
+    for (uint64_t k = begin + threadIdx.x; k < end; k += blockDim.x) {
+        const cplx x = t[k], y = s[k];
+        a0.re = fma(x.re, x.re, fma(x.im, x.im, a0.re));
+        a1.re = fma(x.re, y.re, fma(x.im, y.im, a1.re));
+        a1.im = fma(x.re, y.im, fma(-x.im, y.re, a1.im));
+    }
+    const cplx r0 = cluster_allreduce(a0, sh, 0);
+    const cplx r1 = cluster_allreduce(a1, sh, 1);
+    if (me == 0 && threadIdx.x == 0) { out[0] = r0; out[1] = r1; }
+    cluster.sync();
+}
+
+// x += alpha p + omega s ; r = s - omega t ; out[0].re = ||r||^2 ; out[1] = (r0, r)   (bicgstab.rs:163-166, 94)
+__global__ void __launch_bounds__(VEC_THREADS)
+bicg_update_kernel(cplx* __restrict__ x, const cplx* __restrict__ p, const cplx* __restrict__ s, const cplx* __restrict__ t,
+                   cplx* __restrict__ r, const cplx* __restrict__ r0, cplx alpha, cplx omega, uint64_t n, uint64_t S,
+                   cplx* __restrict__ out) {
+    __shared__ ClusterShared sh;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned me = cluster.block_rank();
+    const uint64_t begin = (uint64_t)me * S, end = begin + S < n ? begin + S : n;
+    cplx a0 = C(0, 0), a1 = C(0, 0);
+    for (uint64_t k = begin + threadIdx.x; k < end; k += blockDim.x) {
+        x[k] = (x[k] + p[k] * alpha) + s[k] * omega;
+        const cplx rr = s[k] - t[k] * omega;
+        r[k] = rr;
+        const cplx q = r0[k];
+        a0.re = fma(rr.re, rr.re, fma(rr.im, rr.im, a0.re));
+        a1.re = fma(q.re, rr.re, fma(q.im, rr.im, a1.re));
+        a1.im = fma(q.re, rr.im, fma(-q.im, rr.re, a1.im));
+    }
+    const cplx t0 = cluster_allreduce(a0, sh, 0);
+    const cplx t1 = cluster_allreduce(a1, sh, 1);
+    if (me == 0 && threadIdx.x == 0) { out[0] = t0; out[1] = t1; }
+    cluster.sync();
+}
+
+// x += alpha p           (early convergence, bicgstab.rs:135)
+__global__ void bicg_axpy_kernel(cplx* __restrict__ x, const cplx* __restrict__ p, cplx alpha, uint64_t n) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) x[k] = x[k] + p[k] * alpha;
+}
+
+// ------------------------------------------------------------------------------------------
 // K6: block matvec Y = A X for S = 8*NT right-hand sides (multi-RHS scattering, BASELINE config 5).
 // A is read ONCE for all S columns, so the op is a genuine dense contraction (8 N^2 S flops on
 // 16 N^2 bytes): FP64 tensor cores, mma.sync.m8n8k4.f64 (tcgen05 has no f64 kind).  Complex
@@ -1325,6 +1426,41 @@ cudaError_t launch_residual(const cplx* b, const cplx* ax, cplx* r, uint64_t n, 
     uint64_t S;
     int cl = pick_cluster(n, 1, &in_smem, &smem, &S);  // no shared-memory slice needed: 8 CTAs always place
     return launch_cluster(residual_cluster_kernel, cl, VEC_THREADS, 0, s, b, ax, r, n, S, out, pinv);
+}
+
+static inline int bicg_cluster(uint64_t n, uint64_t* S) {
+    const int cl = n >= 4096 ? 8 : 1;
+    *S = (n + cl - 1) / cl;
+    return cl;
+}
+cudaError_t launch_bicg_dot(const cplx* a, const cplx* b, uint64_t n, cplx* out, cudaStream_t s) {
+    uint64_t S;
+    const int cl = bicg_cluster(n, &S);
+    return launch_cluster(bicg_dot_kernel, cl, VEC_THREADS, 0, s, a, b, n, S, out);
+}
+cudaError_t launch_bicg_p(const cplx* r, cplx* p, const cplx* v, cplx beta, cplx omega, uint64_t n, cudaStream_t s) {
+    bicg_p_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(r, p, v, beta, omega, n);
+    return cudaGetLastError();
+}
+cudaError_t launch_bicg_s(const cplx* r, const cplx* v, cplx alpha, cplx* sv, uint64_t n, cplx* out, cudaStream_t s) {
+    uint64_t S;
+    const int cl = bicg_cluster(n, &S);
+    return launch_cluster(bicg_s_kernel, cl, VEC_THREADS, 0, s, r, v, alpha, sv, n, S, out);
+}
+cudaError_t launch_bicg_tt(const cplx* t, const cplx* sv, uint64_t n, cplx* out, cudaStream_t s) {
+    uint64_t S;
+    const int cl = bicg_cluster(n, &S);
+    return launch_cluster(bicg_tt_kernel, cl, VEC_THREADS, 0, s, t, sv, n, S, out);
+}
+cudaError_t launch_bicg_update(cplx* x, const cplx* p, const cplx* sv, const cplx* t, cplx* r, const cplx* r0, cplx alpha, cplx omega,
+                               uint64_t n, cplx* out, cudaStream_t s) {
+    uint64_t S;
+    const int cl = bicg_cluster(n, &S);
+    return launch_cluster(bicg_update_kernel, cl, VEC_THREADS, 0, s, x, p, sv, t, r, r0, alpha, omega, n, S, out);
+}
+cudaError_t launch_bicg_axpy(cplx* x, const cplx* p, cplx alpha, uint64_t n, cudaStream_t s) {
+    bicg_axpy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, p, alpha, n);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_zgemm_block(const cplx* A, uint64_t lda, uint64_t nrows, uint64_t ncols, const cplx* X, cplx* Y, int nrhs,

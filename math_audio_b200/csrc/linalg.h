@@ -29,6 +29,14 @@ cudaError_t launch_mgs(const cplx* V, uint64_t ldv, cplx* w, int j, uint64_t n, 
                        const PeerWait& pw, cudaStream_t s);  // hcol_host: mapped pinned copy of the column (written by the kernel when *wrote_host)
 size_t mgs_scratch_elems();  // cplx elements of scratch launch_mgs needs after the ldl*ldl Gram triangle
 cudaError_t launch_residual(const cplx* b, const cplx* ax, cplx* r, uint64_t n, double* out, const cplx* pinv, cudaStream_t s);
+// BiCGSTAB vector kernels: out = device scratch of >= 2 complex numbers
+cudaError_t launch_bicg_dot(const cplx* a, const cplx* b, uint64_t n, cplx* out, cudaStream_t s);
+cudaError_t launch_bicg_p(const cplx* r, cplx* p, const cplx* v, cplx beta, cplx omega, uint64_t n, cudaStream_t s);
+cudaError_t launch_bicg_s(const cplx* r, const cplx* v, cplx alpha, cplx* sv, uint64_t n, cplx* out, cudaStream_t s);
+cudaError_t launch_bicg_tt(const cplx* t, const cplx* sv, uint64_t n, cplx* out, cudaStream_t s);
+cudaError_t launch_bicg_update(cplx* x, const cplx* p, const cplx* sv, const cplx* t, cplx* r, const cplx* r0, cplx alpha, cplx omega,
+                               uint64_t n, cplx* out, cudaStream_t s);
+cudaError_t launch_bicg_axpy(cplx* x, const cplx* p, cplx alpha, uint64_t n, cudaStream_t s);
 cudaError_t launch_zgemm_block(const cplx* A, uint64_t lda, uint64_t nrows, uint64_t ncols, const cplx* X, cplx* Y, int nrhs,
                                cudaStream_t s);
 cudaError_t launch_mgs_batched(int nrhs, const cplx* Vall, uint64_t ldv, uint64_t vstride, const cplx* Yblk, int j, uint64_t n,

@@ -1051,6 +1051,90 @@ void orc_gmres_preconditioned(const double* A, uint64_t n, const double* inv_dia
     orc_gmres_preconditioned_op(dense_apply, &ctx, n, inv_diag, b, x0, max_iterations, restart, tolerance, x_out, info);
 }
 
+// ---- bicgstab: math-solvers/src/iterative/bicgstab.rs:53-215 on a dense row-major matrix ----
+void orc_bicgstab(const double* A, uint64_t n, const double* b_in, uint32_t max_iterations, double tolerance, double* x_out,
+                  orc_gmres_info* info, int nthreads) {
+    const cplx* b = (const cplx*)b_in;
+    cplx* x = (cplx*)x_out;
+    for (uint64_t i = 0; i < n; ++i) x[i] = C(0, 0);
+    const double b_norm = vector_norm(b, n);
+    if (b_norm < 1e-15) { *info = {0, 0, 0.0, 1}; return; }
+    std::vector<cplx> r(b, b + n), r0(b, b + n), p(n, C(0, 0)), v(n, C(0, 0)), s(n), t(n);
+    cplx rho = C(1, 0), alpha = C(1, 0), omega = C(1, 0);
+    for (uint32_t iter = 0; iter < max_iterations; ++iter) {
+        const cplx rho_new = inner_product(r0.data(), r.data(), n);
+        if (cnorm(rho_new) < 1e-30) { *info = {iter, 0, vector_norm(r.data(), n) / b_norm, 0}; return; }
+        const cplx beta = (rho_new / rho) * (alpha / omega);
+        rho = rho_new;
+        for (uint64_t i = 0; i < n; ++i) p[i] = r[i] + (p[i] - v[i] * omega) * beta;
+        orc_zgemv(A, n, n, (const double*)p.data(), (double*)v.data(), nthreads);
+        const cplx r0v = inner_product(r0.data(), v.data(), n);
+        if (cnorm(r0v) < 1e-30) { *info = {iter, 0, vector_norm(r.data(), n) / b_norm, 0}; return; }
+        alpha = rho / r0v;
+        for (uint64_t i = 0; i < n; ++i) s[i] = r[i] - v[i] * alpha;
+        const double s_norm = vector_norm(s.data(), n);
+        if (s_norm / b_norm < tolerance) {
+            for (uint64_t i = 0; i < n; ++i) x[i] = x[i] + p[i] * alpha;
+            *info = {(uint64_t)iter + 1, 0, s_norm / b_norm, 1};
+            return;
+        }
+        orc_zgemv(A, n, n, (const double*)s.data(), (double*)t.data(), nthreads);
+        const cplx tt = inner_product(t.data(), t.data(), n);
+        if (cnorm(tt) < 1e-30) { *info = {iter, 0, vector_norm(r.data(), n) / b_norm, 0}; return; }
+        omega = inner_product(t.data(), s.data(), n) / tt;
+        for (uint64_t i = 0; i < n; ++i) x[i] = x[i] + p[i] * alpha + s[i] * omega;
+        for (uint64_t i = 0; i < n; ++i) r[i] = s[i] - t[i] * omega;
+        const double rel = vector_norm(r.data(), n) / b_norm;
+        if (rel < tolerance) { *info = {(uint64_t)iter + 1, 0, rel, 1}; return; }
+        if (cnorm(omega) < 1e-30) { *info = {(uint64_t)iter + 1, 0, rel, 0}; return; }
+    }
+    *info = {max_iterations, 0, vector_norm(r.data(), n) / b_norm, 0};
+}
+
+// ---- lu_solve: math-solvers/src/direct/lu.rs:136-161.  The default build (feature "native" =>
+// `ndarray-linalg`, math-solvers/Cargo.toml:48-57) calls LAPACK zgesv (ndarray-linalg 0.18 / lax 0.18 /
+// OpenBLAS, not vendored): partial-pivoting LU + two triangular solves, restated here with the elimination
+// loop of the portable path (lu.rs:81-133).  returns 0, or 1 = LuError::SingularMatrix.
+int orc_lu_solve(const double* A_in, uint64_t n, const double* b_in, double* x_out) {
+    std::vector<cplx> lu((const cplx*)A_in, (const cplx*)A_in + n * n);
+    std::vector<uint64_t> piv(n);
+    for (uint64_t i = 0; i < n; ++i) piv[i] = i;
+    for (uint64_t k = 0; k < n; ++k) {
+        double max_val = cnorm(lu[k * n + k]);
+        uint64_t max_row = k;
+        for (uint64_t i = k + 1; i < n; ++i) {
+            const double val = cnorm(lu[i * n + k]);
+            if (val > max_val) { max_val = val; max_row = i; }
+        }
+        if (max_val < 1e-30) return 1;
+        if (max_row != k) {
+            for (uint64_t j = 0; j < n; ++j) std::swap(lu[k * n + j], lu[max_row * n + j]);
+            std::swap(piv[k], piv[max_row]);
+        }
+        const cplx pivot = lu[k * n + k];
+        for (uint64_t i = k + 1; i < n; ++i) {
+            const cplx mult = lu[i * n + k] * cinv(pivot);
+            lu[i * n + k] = mult;
+            for (uint64_t j = k + 1; j < n; ++j) lu[i * n + j] -= mult * lu[k * n + j];
+        }
+    }
+    // piv is the row permutation (piv[i] = original row now in position i): gather P b, then L y = P b, U x = y.
+    // (The portable LuFactorization::solve, lu.rs:52-58, replays the same vector as a swap sequence, which
+    // differs for 3-cycles; the native build never runs it, so zgesv semantics are the contract.)
+    cplx* x = (cplx*)x_out;
+    const cplx* b = (const cplx*)b_in;
+    for (uint64_t i = 0; i < n; ++i) x[i] = b[piv[i]];
+    for (uint64_t i = 0; i < n; ++i)
+        for (uint64_t j = 0; j < i; ++j) x[i] = x[i] - lu[i * n + j] * x[j];
+    for (uint64_t ii = n; ii-- > 0;) {
+        for (uint64_t j = ii + 1; j < n; ++j) x[ii] = x[ii] - lu[ii * n + j] * x[j];
+        const cplx u = lu[ii * n + ii];
+        if (cnorm(u) < 1e-30) return 1;
+        x[ii] = x[ii] * cinv(u);
+    }
+    return 0;
+}
+
 // ---- incident field: incident.rs:93-166 (pressure), 177-280 (dp/dn), 317-342 ---
 // kind 0 = plane wave (vec = direction), 1 = point source (vec = position).
 // rhs[i] = -(gamma p_inc + beta tau dp_inc/dn); accumulate=1 adds to rhs (multi-source)

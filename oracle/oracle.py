@@ -239,6 +239,32 @@ def gmres(A, b, x0=None, max_iterations=100, restart=30, tolerance=1e-6, nthread
                    converged=bool(info.converged))
 
 
+def bicgstab(A, b, max_iterations=1000, tolerance=1e-6, nthreads=0):
+    """math-solvers/src/iterative/bicgstab.rs:53-215 on a dense row-major matrix -> (x, info dict)."""
+    A = np.ascontiguousarray(A, dtype=np.complex128)
+    b = np.ascontiguousarray(b, dtype=np.complex128)
+    n = b.shape[0]
+    x = np.zeros(n, dtype=np.complex128)
+    info = GmresInfo()
+    lib().orc_bicgstab(_p(A), C.c_uint64(n), _p(b), C.c_uint32(max_iterations), C.c_double(tolerance), _p(x), C.byref(info),
+                       C.c_int(nthreads))
+    return x, dict(iterations=int(info.iterations), residual=float(info.residual), converged=bool(info.converged))
+
+
+def lu_solve(A, b):
+    """math-solvers/src/direct/lu.rs:136-161 -> x; raises np.linalg.LinAlgError for LuError::SingularMatrix."""
+    A = np.ascontiguousarray(A, dtype=np.complex128)
+    b = np.ascontiguousarray(b, dtype=np.complex128)
+    n = b.shape[0]
+    if A.shape != (n, n):
+        raise ValueError("dimension mismatch")
+    x = np.zeros(n, dtype=np.complex128)
+    lib().orc_lu_solve.restype = C.c_int
+    if lib().orc_lu_solve(_p(A), C.c_uint64(n), _p(b), _p(x)) != 0:
+        raise np.linalg.LinAlgError("Matrix is singular or nearly singular")
+    return x
+
+
 def inverse_diagonal(diag) -> np.ndarray:
     """DiagonalPreconditioner::from_diagonal (preconditioners/diagonal.rs:40-50): 1/d, or 1 when |d| <= 1e-30."""
     d = np.asarray(diag, dtype=np.complex128)

@@ -1,0 +1,102 @@
+"""GPU parity of the callers of the hot path (bem_solver.rs): device BiCGSTAB, LU through cuSOLVER
+and the BemSolver / BemSolution mirror, through the C ABI, against the oracle.
+
+Tolerances: solutions relative 1e-8; BiCGSTAB iteration counts equal the oracle's on
+these well-conditioned cases (tree vs sequential inner products change only the last bits)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def bem():
+    from math_audio_b200 import bem as b
+
+    b.default_context()
+    return b
+
+
+def test_bicgstab_kats_and_dense(bem, orc):
+    A = np.array([[4, 1], [1, 3]], dtype=np.complex128)
+    b = np.array([1, 2], dtype=np.complex128)
+    sol = bem.bicgstab(bem.DenseOperator(A), b, bem.BiCgstabConfig(100, 1e-10, 0))       # bicgstab.rs:196-219
+    assert sol.converged and np.linalg.norm(A @ sol.x - b) < 1e-8
+    z = bem.bicgstab(bem.DenseOperator(A), np.zeros(2, dtype=complex), bem.BiCgstabConfig())
+    assert z.converged and z.iterations == 0 and z.residual == 0.0 and not z.x.any()
+    rng = np.random.default_rng(2)
+    for n in (40, 777, 5000):
+        A = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))) / np.sqrt(n) + 3 * np.eye(n)
+        b = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        op = bem.DenseOperator(A)
+        sol = bem.bicgstab(op, b, bem.BiCgstabConfig(500, 1e-11, 0))
+        xo, io = orc.bicgstab(A, b, max_iterations=500, tolerance=1e-11)
+        assert sol.converged and io["converged"]
+        assert sol.iterations == io["iterations"]
+        assert np.linalg.norm(sol.x - xo) / np.linalg.norm(xo) < 1e-8
+        assert abs(sol.residual - np.linalg.norm(A @ sol.x - b) / np.linalg.norm(b)) < 1e-9
+        short = bem.bicgstab(op, b, bem.BiCgstabConfig(3, 1e-14, 0))
+        assert not short.converged and short.iterations == 3
+
+
+def test_lu_solve_kats_and_dense(bem, orc):
+    A = np.array([[4 + 1j, 1], [1, 3 - 1j]])
+    b = np.array([1 + 1j, 2 - 1j])
+    assert np.max(np.abs(A @ bem.lu_solve(A, b) - b)) < 1e-10                            # lu.rs:178-196
+    assert np.allclose(bem.lu_solve(np.eye(5), np.arange(1.0, 6.0)), np.arange(1.0, 6.0), atol=1e-10)
+    with pytest.raises(bem.LuError):
+        bem.lu_solve(np.array([[1.0, 2.0], [2.0, 4.0]]), np.array([1.0, 2.0]))           # lu.rs:211-219
+    with pytest.raises(bem.LuError):
+        bem.lu_solve(np.eye(3), np.ones(4))
+    rng = np.random.default_rng(4)
+    n = 1500
+    A = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    b = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    op = bem.DenseOperator(A)
+    x = bem.lu_solve(op, b)
+    assert np.linalg.norm(x - np.linalg.solve(A, b)) / np.linalg.norm(x) < 1e-9
+    assert np.array_equal(op.matrix.rows(), A)           # the operator is left intact, as `lu_solve(&a, &b)`
+    small = A[:200, :200].copy()
+    assert np.linalg.norm(bem.lu_solve(small, b[:200]) - orc.lu_solve(small, b[:200])) / np.linalg.norm(b[:200]) < 1e-9
+
+
+@pytest.mark.parametrize("method", ["Direct", "BiCgStab"])
+def test_bem_solver_small_problem_and_field(bem, orc, method):
+    """bem_solver.rs:654-686 (+ parity of the whole chain against the oracle)."""
+    from math_audio_b200 import bem_solver as bs
+
+    problem = bs.BemProblem.rigid_sphere_scattering_custom(0.1, 100.0, 343.0, 1.21, 4, 8)
+    solver = bs.BemSolver.new().with_solver_method(getattr(bs.SolverMethod, method))
+    sol = solver.solve(problem)
+    assert sol.num_dofs() > 0 and sol.max_surface_pressure() > 0.0 and sol.mean_surface_pressure() > 0.0
+    p = sol.evaluate_pressure([0.0, 0.0, 0.2])
+    assert abs(p) > 0.0
+    mesh = solver.prepare_elements(problem)
+    ph = problem.physics
+    beta = ph.burton_miller_beta_scaled(4.0)
+    A, rhs0, _ = orc.assemble(mesh, ph.wave_number, beta)
+    rhs, pinc = orc.incident_rhs(0, [0, 0, 1.0], 1.0, mesh.center, mesh.normal, ph.wave_number, beta)
+    xo = orc.lu_solve(A, rhs0 + rhs) if method == "Direct" else orc.bicgstab(A, rhs0 + rhs, 1000, 1e-8)[0]
+    assert np.linalg.norm(sol.surface_pressure - xo) / np.linalg.norm(xo) < (1e-8 if method == "Direct" else 1e-6)
+    pts = np.array([[0.0, 0.0, 0.2], [0.3, -0.1, 0.05]])
+    fps = sol.evaluate_pressure_field(pts)
+    ps = orc.scattered_field(mesh, pts, sol.surface_pressure, ph.wave_number)
+    assert max(abs(fp.p_scattered - q) for fp, q in zip(fps, ps)) < 1e-12
+    assert abs(fps[0].p_total - p) == 0.0 and np.isfinite(fps[0].spl_db())
+
+
+def test_bem_solver_rigid_sphere_mie(bem, orc):
+    """Direct and BiCGSTAB agree with each other and with the Mie series as the QA suite expects (qa_suite.rs:175-179)."""
+    from math_audio_b200 import bem_solver as bs
+
+    problem = bs.BemProblem.rigid_sphere_scattering(0.1, 343.0 * 10.0 / (2 * np.pi), 343.0, 1.21)   # ka = 1 -> icosphere(3)
+    assert problem.mesh.n_elem == 1280
+    stats = {}
+    xd = bs.BemSolver.new().solve(problem, stats=stats).surface_pressure
+    assert stats["factor_ms"] > 0.0
+    xb = bs.BemSolver.new().with_solver_method(bs.SolverMethod.BiCgStab).with_tolerance(1e-10).solve(problem).surface_pressure
+    assert np.linalg.norm(xd - xb) / np.linalg.norm(xd) < 1e-8
+    m = problem.mesh
+    r = np.linalg.norm(m.center, axis=1)
+    mie = orc.mie_rigid_sphere(problem.physics.wave_number, 0.1, 50, r, np.arccos(m.center[:, 2] / r))
+    assert abs(orc.l2_relative(mie, xd) - 0.2724) < 2e-4

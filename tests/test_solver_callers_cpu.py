@@ -1,0 +1,76 @@
+"""bicgstab / lu_solve / BemSolver, CPU side: the reference's own tests for these callers of the
+hot path restated on the oracle, and the host logic of the BemSolver mirror.  No GPU."""
+import math
+
+import numpy as np
+import pytest
+
+from math_audio_b200 import bem_solver as bs
+
+
+# ---- math-solvers/src/iterative/bicgstab.rs:196-219 -------------------------------------------
+def test_bicgstab_simple(orc):
+    A = np.array([[4, 1], [1, 3]], dtype=np.complex128)
+    b = np.array([1, 2], dtype=np.complex128)
+    x, info = orc.bicgstab(A, b, max_iterations=100, tolerance=1e-10)
+    assert info["converged"]
+    assert np.linalg.norm(A @ x - b) < 1e-8
+
+
+def test_bicgstab_zero_rhs_and_budget(orc):
+    A = np.array([[4, 1], [1, 3]], dtype=np.complex128)
+    x, info = orc.bicgstab(A, np.zeros(2, dtype=np.complex128))
+    assert info == dict(iterations=0, residual=0.0, converged=True) and not x.any()   # bicgstab.rs:66-74
+    rng = np.random.default_rng(2)
+    n = 40
+    A = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)) + 6 * np.eye(n)
+    b = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    x, info = orc.bicgstab(A, b, max_iterations=3, tolerance=1e-14)
+    assert not info["converged"] and info["iterations"] == 3                           # bicgstab.rs:207-214
+    x, info = orc.bicgstab(A, b, max_iterations=500, tolerance=1e-11)
+    assert info["converged"] and np.linalg.norm(A @ x - b) / np.linalg.norm(b) < 1e-10
+    assert abs(info["residual"] - np.linalg.norm(A @ x - b) / np.linalg.norm(b)) < 1e-12
+
+
+# ---- math-solvers/src/direct/lu.rs:163-241 ----------------------------------------------------
+def test_lu_solve_kats(orc):
+    A = np.array([[4.0, 1.0], [1.0, 3.0]])
+    b = np.array([1.0, 2.0])
+    assert np.allclose(A @ orc.lu_solve(A, b), b, atol=1e-10)
+    A = np.array([[4 + 1j, 1], [1, 3 - 1j]])
+    b = np.array([1 + 1j, 2 - 1j])
+    assert np.max(np.abs(A @ orc.lu_solve(A, b) - b)) < 1e-10
+    assert np.allclose(orc.lu_solve(np.eye(5), np.arange(1.0, 6.0)), np.arange(1.0, 6.0), atol=1e-10)
+    with pytest.raises(np.linalg.LinAlgError):
+        orc.lu_solve(np.array([[1.0, 2.0], [2.0, 4.0]]), np.array([1.0, 2.0]))
+    A = np.array([[4.0, 1.0, 0.0], [1.0, 3.0, 1.0], [0.0, 1.0, 2.0]])
+    for b in (np.array([1.0, 2.0, 3.0]), np.array([4.0, 5.0, 6.0])):
+        assert np.allclose(A @ orc.lu_solve(A, b), b, atol=1e-10)
+    rng = np.random.default_rng(1)   # pivoting with a genuine 3-cycle permutation
+    A = rng.standard_normal((30, 30)) + 1j * rng.standard_normal((30, 30))
+    b = rng.standard_normal(30) + 1j * rng.standard_normal(30)
+    assert np.linalg.norm(orc.lu_solve(A, b) - np.linalg.solve(A, b)) / np.linalg.norm(b) < 1e-11
+
+
+# ---- math-bem/src/core/bem_solver.rs:633-651 --------------------------------------------------
+def test_bem_problem_creation():
+    p = bs.BemProblem.rigid_sphere_scattering(0.1, 1000.0, 343.0, 1.21)
+    assert p.mesh.n_elem > 0 and p.mesh.n_nodes > 0 and p.ka() > 0.0
+    assert p.mesh.n_elem == 1280                               # ka = 1.83 -> subdivisions 3 (bem_solver.rs:117-125)
+    assert bs.BemProblem.rigid_sphere_scattering(0.1, 100.0, 343.0, 1.21).mesh.n_elem == 320
+    assert bs.BemProblem.rigid_sphere_scattering(0.1, 5000.0, 343.0, 1.21).mesh.n_elem == 5120
+    assert abs(p.ka() - 2 * math.pi * 1000.0 / 343.0 * 0.1) < 1e-9
+    assert p.bc_type == bs.BoundaryConditionType.Rigid and p.use_burton_miller
+
+
+def test_bem_solver_creation_and_prepare_elements():
+    s = bs.BemSolver.new().with_solver_method(bs.SolverMethod.Direct).with_assembly_method(bs.AssemblyMethod.Tbem).with_verbose(False)
+    assert s.solver_method == bs.SolverMethod.Direct and s.assembly_method == bs.AssemblyMethod.Tbem
+    assert (s.max_iterations, s.tolerance, s.beta_scale) == (1000, 1e-8, 4.0)
+    p = bs.BemProblem.rigid_sphere_scattering_custom(0.1, 100.0, 343.0, 1.21, 4, 8)
+    m = s.prepare_elements(p)
+    assert (m.bc_type == 0).all() and (m.bc_len == 1).all() and not m.bc_val.any() and (m.dof == np.arange(m.n_elem)).all()
+    m = s.prepare_elements(p.with_boundary_condition(bs.BoundaryConditionType.Soft))
+    assert (m.bc_type == 1).all()
+    with pytest.raises(bs.BemError):
+        bs.BemSolver.new().with_assembly_method(bs.AssemblyMethod.Mlfmm).solve(p)
