@@ -58,6 +58,12 @@ extern "C" {
     pub fn bemb200_row_sum_correction(m: *mut bemb200_matrix, avg: *mut f64) -> c_int;
     pub fn bemb200_apply(m: *const bemb200_matrix, x: *const f64, y: *mut f64) -> c_int;
     pub fn bemb200_apply_transpose(m: *const bemb200_matrix, x: *const f64, y: *mut f64) -> c_int;
+    pub fn bemb200_bicgstab(m: *const bemb200_matrix, b: *const f64, max_iterations: u32, tolerance: f64, x_out: *mut f64,
+                            info: *mut bemb200_gmres_info) -> c_int;
+    pub fn bemb200_lu_solve(m: *const bemb200_matrix, b: *const f64, x_out: *mut f64, overwrite_matrix: c_int,
+                            factor_ms: *mut f64) -> c_int;
+    pub fn bemb200_compute_rcs(sm: *const bemb200_staged_mesh, phys: *const bemb200_physics, n_dirs: u32, dirs: *const f64,
+                               surface_pressure: *const f64, rcs_out: *mut f64) -> c_int;
     pub fn bemb200_gmres(m: *const bemb200_matrix, b: *const f64, x0: *const f64, max_iterations: u32, restart: u32,
                          tolerance: f64, x_out: *mut f64, info: *mut bemb200_gmres_info) -> c_int;
 }
