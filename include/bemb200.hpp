@@ -11,6 +11,10 @@
 //   math-solvers/src/preconditioners/diagonal.rs DiagonalPreconditioner
 //   math-solvers/src/iterative/gmres.rs:16-585   GmresConfig, GmresSolution, gmres, gmres_with_guess,
 //                                                gmres_preconditioned{,_with_guess}
+//   math-solvers/src/iterative/bicgstab.rs:19-215  BiCgstabConfig, BiCgstabSolution, bicgstab
+//   math-solvers/src/direct/lu.rs:15-161         LuError, lu_solve
+//   math-bem/src/room_acoustics/solver.rs:412-748  RoomMesh, Source, build_bem_matrix_parallel, solve_bem_system,
+//                                                calculate_incident_field_derivative_parallel, calculate_field_pressure_bem_parallel
 // Shape mismatches throw std::invalid_argument (the reference panics); library failures throw
 // bemb200::Error carrying the BEMB200_E* code and bemb200_last_error().
 #pragma once
@@ -325,6 +329,135 @@ inline GmresSolution gmres_preconditioned_with_guess(const DenseOperator& op, co
                                                      const std::vector<Complex64>& b, const std::vector<Complex64>* x0,
                                                      const GmresConfig& config) {  // gmres.rs:434
     return gmres_preconditioned_impl(op, &p.inv_diag, b, x0, config);
+}
+
+// ---- BiCGSTAB / LU (the solvers of BemSolver::solve_dense_system, bem_solver.rs:435-463) ---------------------
+struct BiCgstabConfig {  // bicgstab.rs:19-37
+    std::size_t max_iterations = 1000;
+    double tolerance = 1e-6;
+    std::size_t print_interval = 0;
+};
+struct BiCgstabSolution {  // bicgstab.rs:40-50
+    std::vector<Complex64> x;
+    std::size_t iterations = 0;
+    double residual = 0.0;
+    bool converged = false;
+};
+inline BiCgstabSolution bicgstab(const DenseOperator& op, const std::vector<Complex64>& b, const BiCgstabConfig& config) {  // bicgstab.rs:53
+    if (b.size() != op.num_rows()) throw std::invalid_argument("bicgstab: vector length must match the operator");
+    BiCgstabSolution s;
+    s.x.resize(b.size());
+    bemb200_gmres_info info{};
+    check(bemb200_bicgstab(op.handle(), reinterpret_cast<const double*>(b.data()), static_cast<uint32_t>(config.max_iterations),
+                           config.tolerance, reinterpret_cast<double*>(s.x.data()), &info),
+          op.context().handle());
+    s.iterations = info.iterations; s.residual = info.residual; s.converged = info.converged != 0;
+    return s;
+}
+
+struct LuError : std::runtime_error {  // lu.rs:15-21
+    enum Kind { SingularMatrix, DimensionMismatch } kind;
+    LuError(Kind k, const std::string& m) : std::runtime_error(m), kind(k) {}
+};
+// lu_solve(&a, &b) (lu.rs:136-161): `a` is left intact
+inline std::vector<Complex64> lu_solve(const DenseOperator& a, const std::vector<Complex64>& b) {
+    if (a.num_rows() != a.num_cols() || b.size() != a.num_rows())
+        throw LuError(LuError::DimensionMismatch, "Matrix dimensions mismatch: expected " + std::to_string(a.num_rows()) + ", got " + std::to_string(b.size()));
+    std::vector<Complex64> x(b.size());
+    const int rc = bemb200_lu_solve(a.handle(), reinterpret_cast<const double*>(b.data()), reinterpret_cast<double*>(x.data()), 0, nullptr);
+    if (rc == BEMB200_ESINGULAR) throw LuError(LuError::SingularMatrix, "Matrix is singular or nearly singular");
+    check(rc, a.context().handle());
+    return x;
+}
+
+// ---- room acoustics (math-bem/src/room_acoustics/solver.rs, math-xem-common) ---------------------------------
+struct Point3D { double x = 0, y = 0, z = 0; };             // math-xem-common/src/types.rs
+struct SurfaceElement { std::vector<std::size_t> nodes; };  // types.rs:154-157 (3 or 4 node indices)
+struct RoomMesh {                                           // types.rs:185-192
+    std::vector<Point3D> nodes;
+    std::vector<SurfaceElement> elements;
+};
+struct Source {  // source.rs:160-219 with DirectivityPattern (magnitude[n_vertical][n_horizontal], 10 degree grid; empty = omnidirectional)
+    Point3D position;
+    double amplitude = 1.0;
+    std::vector<double> directivity;
+    std::size_t n_horizontal = 0, n_vertical = 0;
+    double crossover_amplitude = 1.0;  // crossover.amplitude_at_frequency(f), evaluated by the caller per frequency
+};
+class StagedRoomMesh {
+public:
+    StagedRoomMesh(const Context& ctx, const RoomMesh& mesh) : ctx_(&ctx) {
+        std::vector<double> nodes;
+        nodes.reserve(mesh.nodes.size() * 3);
+        for (const Point3D& p : mesh.nodes) nodes.insert(nodes.end(), {p.x, p.y, p.z});
+        std::vector<uint32_t> conn(mesh.elements.size() * 4, 0xFFFFFFFFu);
+        for (std::size_t e = 0; e < mesh.elements.size(); ++e) {
+            const auto& nd = mesh.elements[e].nodes;
+            if (nd.size() != 3 && nd.size() != 4) throw std::invalid_argument("room elements are triangles or quadrilaterals");
+            for (std::size_t v = 0; v < nd.size(); ++v) conn[4 * e + v] = static_cast<uint32_t>(nd[v]);
+        }
+        check(bemb200_room_mesh_stage(ctx.handle(), nodes.data(), mesh.nodes.size(), conn.data(), mesh.elements.size(), &h_), ctx.handle());
+    }
+    ~StagedRoomMesh() { bemb200_room_mesh_free(h_); }
+    StagedRoomMesh(const StagedRoomMesh&) = delete;
+    StagedRoomMesh& operator=(const StagedRoomMesh&) = delete;
+    bemb200_room_mesh* handle() const { return h_; }
+    const Context& context() const { return *ctx_; }
+    std::size_t num_elements() const { return bemb200_room_mesh_num_elements(h_); }
+
+private:
+    const Context* ctx_;
+    bemb200_room_mesh* h_ = nullptr;
+};
+inline std::vector<bemb200_room_source> room_sources_abi(const std::vector<Source>& sources) {
+    std::vector<bemb200_room_source> out(sources.size());
+    for (std::size_t i = 0; i < sources.size(); ++i) {
+        out[i].position[0] = sources[i].position.x; out[i].position[1] = sources[i].position.y; out[i].position[2] = sources[i].position.z;
+        out[i].amplitude = sources[i].amplitude * sources[i].crossover_amplitude;
+        out[i].directivity = sources[i].directivity.empty() ? nullptr : sources[i].directivity.data();
+        out[i].n_horizontal = static_cast<uint32_t>(sources[i].n_horizontal);
+        out[i].n_vertical = static_cast<uint32_t>(sources[i].n_vertical);
+    }
+    return out;
+}
+// build_bem_matrix_parallel (solver.rs:448-493) -> device-resident operator
+inline std::unique_ptr<DenseOperator> build_bem_matrix_parallel(const StagedRoomMesh& mesh, double k) {
+    bemb200_matrix* m = nullptr;
+    check(bemb200_room_assemble(mesh.context().handle(), mesh.handle(), k, 0, mesh.num_elements(), &m, nullptr), mesh.context().handle());
+    return std::make_unique<DenseOperator>(mesh.context(), m);
+}
+inline std::vector<Complex64> calculate_incident_field_derivative_parallel(const StagedRoomMesh& mesh, const std::vector<Source>& sources,
+                                                                          double k) {  // solver.rs:638-679
+    std::vector<Complex64> rhs(mesh.num_elements());
+    auto abi = room_sources_abi(sources);
+    check(bemb200_room_incident_rhs(mesh.handle(), k, static_cast<uint32_t>(abi.size()), abi.data(), reinterpret_cast<double*>(rhs.data()), nullptr),
+          mesh.context().handle());
+    return rhs;
+}
+// solve_bem_system (solver.rs:412-445): GMRES max_iterations 100, restart 50, tolerance 1e-6; returns solution.x
+inline std::vector<Complex64> solve_bem_system(const StagedRoomMesh& mesh, const std::vector<Source>& sources, double k,
+                                               GmresSolution* solution_out = nullptr) {
+    auto op = build_bem_matrix_parallel(mesh, k);
+    GmresSolution s = solve_gmres(*op, calculate_incident_field_derivative_parallel(mesh, sources, k), GmresConfig{100, 50, 1e-6, 0});
+    if (solution_out) *solution_out = s;
+    return s.x;
+}
+inline std::vector<Complex64> calculate_field_pressure_bem_parallel(const StagedRoomMesh& mesh, const std::vector<Complex64>& surface_pressure,
+                                                                   const std::vector<Source>& sources, const std::vector<Point3D>& field_points,
+                                                                   double k) {  // solver.rs:687-748
+    if (surface_pressure.size() != mesh.num_elements()) throw std::invalid_argument("surface_pressure must have one entry per element");
+    std::vector<double> pts;
+    for (const Point3D& p : field_points) pts.insert(pts.end(), {p.x, p.y, p.z});
+    std::vector<Complex64> out(field_points.size());
+    auto abi = room_sources_abi(sources);
+    check(bemb200_room_field_pressure(mesh.handle(), k, static_cast<uint32_t>(abi.size()), abi.data(), field_points.size(), pts.data(),
+                                      reinterpret_cast<const double*>(surface_pressure.data()), reinterpret_cast<double*>(out.data())),
+          mesh.context().handle());
+    return out;
+}
+inline double pressure_to_spl(Complex64 p) {  // math-xem-common/src/types.rs:280-287
+    const double m = std::abs(p);
+    return m > 1e-20 ? 20.0 * std::log10(m / 20e-6) : -120.0;
 }
 
 }  // namespace bemb200

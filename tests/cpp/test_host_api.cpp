@@ -3,6 +3,9 @@
 //   math-bem/src/core/assembly/tbem.rs:536-615           test_build_tbem_system (2-element mesh)
 //   math-solvers/src/iterative/gmres.rs:631-705          test_gmres_simple / test_gmres_identity
 //   math-bem/tests/test_fmm_validation.rs:537-700        test_gmres_with_operator / _restart_behavior
+//   math-solvers/src/iterative/bicgstab.rs:196-219       test_bicgstab_simple
+//   math-solvers/src/direct/lu.rs:178-219                test_lu_solve_complex / _identity / _singular
+//   math-bem/src/room_acoustics/solver.rs:1155-1170      test_greens_function / test_pressure_to_spl (room path smoke)
 // plus entry / solution parity against the CPU oracle (linked: oracle/_build/libbem_oracle.so) on a
 // UV sphere generated like math-bem/src/core/mesh/generators.rs:29-98.
 // Built and run by tests/test_cpp_host_api.py (pytest -m gpu).
@@ -24,6 +27,9 @@ struct orc_mesh {
 struct orc_gmres_info { uint64_t iterations, restarts; double residual; int32_t converged; };
 long orc_assemble(const orc_mesh* m, double k, double harmonic, double tau, double beta_re, double beta_im, uint64_t row_begin,
                   uint64_t row_end, double* A_out, double* rhs_out, int nthreads);
+void orc_bicgstab(const double* A, uint64_t n, const double* b, uint32_t max_iterations, double tolerance, double* x_out,
+                  orc_gmres_info* info, int nthreads);
+int orc_lu_solve(const double* A, uint64_t n, const double* b, double* x_out);
 void orc_gmres(const double* A, uint64_t n, const double* b, const double* x0, uint32_t max_iterations, uint32_t restart,
                double tolerance, double* x_out, orc_gmres_info* info, int nthreads);
 }
@@ -195,6 +201,83 @@ int main() {
         for (std::size_t e = 0; e < n; ++e) { num += std::norm(s.x[e] - xo[e]); den += std::norm(xo[e]); }
         CHECK(s.converged && s.iterations == info.iterations && std::sqrt(num / den) < 1e-8);
         std::printf("sphere N=%zu entry_err=%.2e gmres_it=%zu dx=%.2e\n", n, worst, s.iterations, std::sqrt(num / den));
+    }
+    {  // bicgstab.rs:196-219 test_bicgstab_simple, lu.rs:178-219
+        std::vector<Complex64> a = {{4, 0}, {1, 0}, {1, 0}, {3, 0}};
+        std::vector<Complex64> b = {{1, 0}, {2, 0}};
+        DenseOperator op(ctx, a, 2, 2);
+        BiCgstabSolution s = bicgstab(op, b, BiCgstabConfig{100, 1e-10, 0});
+        CHECK(s.converged);
+        std::vector<Complex64> ax = op.apply(s.x);
+        CHECK(std::sqrt(std::norm(ax[0] - b[0]) + std::norm(ax[1] - b[1])) < 1e-8);
+        std::vector<Complex64> a2 = {{4, 1}, {1, 0}, {1, 0}, {3, -1}};
+        std::vector<Complex64> b2 = {{1, 1}, {2, -1}};
+        DenseOperator op2(ctx, a2, 2, 2);
+        std::vector<Complex64> x = lu_solve(op2, b2);
+        std::vector<Complex64> ax2 = op2.apply(x);
+        CHECK(std::abs(ax2[0] - b2[0]) < 1e-10 && std::abs(ax2[1] - b2[1]) < 1e-10);
+        std::vector<Complex64> eye(25, Complex64(0, 0)), b5(5);
+        for (int i = 0; i < 5; ++i) { eye[6 * i] = 1.0; b5[i] = i + 1.0; }
+        std::vector<Complex64> x5 = lu_solve(DenseOperator(ctx, eye, 5, 5), b5);
+        for (int i = 0; i < 5; ++i) CHECK(std::abs(x5[i] - b5[i]) < 1e-10);
+        bool singular = false, mismatch = false;
+        try { lu_solve(DenseOperator(ctx, {{1, 0}, {2, 0}, {2, 0}, {4, 0}}, 2, 2), {{1, 0}, {2, 0}}); }
+        catch (const LuError& e) { singular = e.kind == LuError::SingularMatrix; }
+        CHECK(singular);
+        try { lu_solve(op2, std::vector<Complex64>(3)); } catch (const LuError& e) { mismatch = e.kind == LuError::DimensionMismatch; }
+        CHECK(mismatch);
+        // a dense, well conditioned 300 x 300 system against the oracle's bicgstab and LU
+        const std::size_t n = 300;
+        std::vector<Complex64> A(n * n), bb(n), xo(n), xl(n);
+        uint64_t st = 88172645463325252ull;
+        auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return (double)(st >> 11) / 9007199254740992.0 - 0.5; };
+        for (auto& v : A) v = Complex64(rnd(), rnd()) * (2.0 / std::sqrt((double)n));
+        for (std::size_t i = 0; i < n; ++i) { A[i * n + i] += 3.0; bb[i] = Complex64(rnd(), rnd()); }
+        DenseOperator opn(ctx, A, n, n);
+        BiCgstabSolution sb = bicgstab(opn, bb, BiCgstabConfig{500, 1e-11, 0});
+        orc_gmres_info info{};
+        orc_bicgstab(reinterpret_cast<const double*>(A.data()), n, reinterpret_cast<const double*>(bb.data()), 500, 1e-11,
+                     reinterpret_cast<double*>(xo.data()), &info, 0);
+        CHECK(orc_lu_solve(reinterpret_cast<const double*>(A.data()), n, reinterpret_cast<const double*>(bb.data()), reinterpret_cast<double*>(xl.data())) == 0);
+        std::vector<Complex64> xg = lu_solve(opn, bb);
+        double e1 = 0, e2 = 0, den = 0;
+        for (std::size_t i = 0; i < n; ++i) { e1 += std::norm(sb.x[i] - xo[i]); e2 += std::norm(xg[i] - xl[i]); den += std::norm(xl[i]); }
+        CHECK(sb.converged && info.converged && sb.iterations == info.iterations);
+        CHECK(std::sqrt(e1 / den) < 1e-8 && std::sqrt(e2 / den) < 1e-10);
+        std::printf("bicgstab it=%zu dx=%.2e  lu dx=%.2e\n", sb.iterations, std::sqrt(e1 / den), std::sqrt(e2 / den));
+    }
+    {  // room path: 2 x 2 x 2 m room at 1 element/m (geometry.rs:773-779), one omnidirectional source
+        RoomMesh mesh;
+        auto add_wall = [&](Point3D o, Point3D u, Point3D v, int nu, int nv) {  // add_surface_mesh, geometry.rs:434-469
+            const std::size_t base = mesh.nodes.size();
+            for (int j = 0; j <= nv; ++j)
+                for (int i = 0; i <= nu; ++i) {
+                    const double a = (double)i / nu, b = (double)j / nv;
+                    mesh.nodes.push_back({o.x + a * (u.x - o.x) + b * (v.x - o.x), o.y + a * (u.y - o.y) + b * (v.y - o.y), o.z + a * (u.z - o.z) + b * (v.z - o.z)});
+                }
+            for (int j = 0; j < nv; ++j)
+                for (int i = 0; i < nu; ++i) {
+                    const std::size_t n0 = base + j * (nu + 1) + i;
+                    mesh.elements.push_back({{n0, n0 + 1, n0 + (std::size_t)(nu + 1) + 1, n0 + (std::size_t)(nu + 1)}});
+                }
+        };
+        const double w = 2, d = 2, h = 2;
+        add_wall({0, 0, 0}, {w, 0, 0}, {0, d, 0}, 2, 2); add_wall({0, 0, h}, {w, 0, h}, {0, d, h}, 2, 2);
+        add_wall({0, 0, 0}, {w, 0, 0}, {0, 0, h}, 2, 2); add_wall({0, d, 0}, {w, d, 0}, {0, d, h}, 2, 2);
+        add_wall({0, 0, 0}, {0, d, 0}, {0, 0, h}, 2, 2); add_wall({w, 0, 0}, {w, d, 0}, {w, 0, h}, 2, 2);
+        CHECK(mesh.nodes.size() == 54 && mesh.elements.size() == 24);
+        StagedRoomMesh st(ctx, mesh);
+        const double k = 2.0 * PI * 100.0 / 343.0;
+        auto A = build_bem_matrix_parallel(st, k);
+        std::vector<Complex64> rows = A->rows(0, 24);
+        for (std::size_t i = 0; i < 24; ++i) CHECK(std::abs(rows[i * 24 + i] - Complex64(0.0, -k / (2.0 * PI) * 1.0)) < 1e-15);  // area 1 m^2
+        std::vector<Source> sources(1);
+        sources[0].position = {0.7, 0.6, 1.1};
+        GmresSolution gs;
+        std::vector<Complex64> x = solve_bem_system(st, sources, k, &gs);
+        std::vector<Complex64> p = calculate_field_pressure_bem_parallel(st, x, sources, {{1.3, 1.2, 0.9}}, k);
+        CHECK(std::isfinite(pressure_to_spl(p[0])) && std::abs(pressure_to_spl(Complex64(1.0, 0.0)) - 94.0) < 1.0);
+        std::printf("room N=24 gmres_it=%zu converged=%d spl=%.2f dB\n", gs.iterations, (int)gs.converged, pressure_to_spl(p[0]));
     }
     std::printf("PASS\n");
     return 0;
