@@ -1,6 +1,7 @@
 """Room-acoustics dense BEM path -- host-side mirror of
 
-* ``math-xem-common/src/geometry.rs``  RectangularRoom::generate_mesh :107-183, add_surface_mesh :434-469
+* ``math-xem-common/src/geometry.rs``  RectangularRoom::generate_mesh :107-183, add_surface_mesh :434-469,
+  LShapedRoom::generate_mesh :500-627
 * ``math-xem-common/src/source.rs``    DirectivityPattern :9-98, CrossoverFilter :103-155, Source :160-219
 * ``math-xem-common/src/types.rs``     wavenumber :275, pressure_to_spl :280-287, log_space :290-302, lin_space :305-312
 * ``math-bem/src/room_acoustics/solver.rs``  build_bem_matrix_parallel :448-493, solve_bem_system :412-445,
@@ -114,6 +115,52 @@ class RectangularRoom:
 
     def volume(self) -> float:
         return self.width * self.depth * self.height
+
+
+@dataclass
+class LShapedRoom:
+    """geometry.rs:474-708: main section width1 x depth1, extension width2 x depth2 behind it (x in [0, width2]),
+    common height.  Ten wall patches, meshed independently (nodes are not shared between patches)."""
+    width1: float
+    depth1: float
+    width2: float
+    depth2: float
+    height: float
+
+    def generate_mesh(self, elements_per_meter: int) -> RoomMesh:
+        e = elements_per_meter
+        nx1 = int(math.ceil(self.width1 * e)); ny1 = int(math.ceil(self.depth1 * e))
+        nx2 = int(math.ceil(self.width2 * e)); ny2 = int(math.ceil(self.depth2 * e))
+        nz = int(math.ceil(self.height * e))
+        w1, d1, w2, d2, h = self.width1, self.depth1, self.width2, self.depth2, self.height
+        td = d1 + d2
+        ny_total = int(math.ceil(td * e))
+        nx_int = int(math.ceil((w1 - w2) * e))
+        walls = [
+            ((0, 0, 0), (w1, 0, 0), (0, d1, 0), nx1, ny1),        # floor, main
+            ((0, d1, 0), (w2, d1, 0), (0, td, 0), nx2, ny2),      # floor, extension
+            ((0, 0, h), (w1, 0, h), (0, d1, h), nx1, ny1),        # ceiling, main
+            ((0, d1, h), (w2, d1, h), (0, td, h), nx2, ny2),      # ceiling, extension
+            ((0, 0, 0), (w1, 0, 0), (0, 0, h), nx1, nz),          # front wall y = 0
+            ((w1, 0, 0), (w1, d1, 0), (w1, 0, h), ny1, nz),       # right wall of the main section
+            ((0, 0, 0), (0, td, 0), (0, 0, h), ny_total, nz),     # left wall x = 0
+            ((0, td, 0), (w2, td, 0), (0, td, h), nx2, nz),       # back wall of the extension
+            ((w2, d1, 0), (w2, td, 0), (w2, d1, h), ny2, nz),     # right wall of the extension
+            ((w2, d1, 0), (w1, d1, 0), (w2, d1, h), nx_int, nz),  # internal wall at the junction
+        ]
+        nodes, elems, base = [], [], 0
+        for o, u, v, nu, nv in walls:
+            nd, q = _surface_mesh(o, u, v, nu, nv, base)
+            nodes.append(nd)
+            elems.append(q)
+            base += nd.shape[0]
+        return RoomMesh(np.ascontiguousarray(np.concatenate(nodes)), np.ascontiguousarray(np.concatenate(elems).astype(np.uint32)))
+
+    def dimensions(self):
+        return max(self.width1, self.width2), self.depth1 + self.depth2, self.height
+
+    def volume(self) -> float:
+        return (self.width1 * self.depth1 + self.width2 * self.depth2) * self.height
 
 
 # ---- source.rs -----------------------------------------------------------------------------
@@ -348,7 +395,7 @@ def calculate_field_pressure_bem_parallel(mesh, surface_pressure: np.ndarray, so
 class RoomSimulation:
     """What run_direct_gmres reads from RoomSimulation (math-xem-common/src/config.rs): room, sources, listening
     positions, frequency grid, speed of sound."""
-    room: RectangularRoom
+    room: object  # RectangularRoom | LShapedRoom (RoomGeometry, geometry.rs:9-14)
     sources: List[Source]
     listening_positions: List[Sequence[float]]
     frequencies: List[float]
@@ -360,17 +407,19 @@ class RoomSimulation:
 
 def simulation_from_config(config) -> tuple:
     """RoomConfig (math-xem-common/src/config.rs:12-35, the JSON files under math-bem/configs/) -> (RoomSimulation,
-    mesh_resolution).  ``config``: dict or path of a JSON file.  Rectangular rooms only (the dense path of this
-    repository); sources keep their directivity (omnidirectional / custom) and crossover (config.rs:209-340)."""
+    mesh_resolution).  ``config``: dict or path of a JSON file.  Rectangular and L-shaped rooms; sources keep their directivity (omnidirectional / custom) and crossover (config.rs:209-340)."""
     import json
     from pathlib import Path
 
     if not isinstance(config, dict):
         config = json.loads(Path(config).read_text())
     rc = config["room"]
-    if rc.get("type") != "rectangular":
-        raise ValueError(f"room type {rc.get('type')!r} is not supported by the dense path (rectangular only)")
-    room = RectangularRoom(float(rc["width"]), float(rc["depth"]), float(rc["height"]))
+    if rc.get("type") == "rectangular":
+        room = RectangularRoom(float(rc["width"]), float(rc["depth"]), float(rc["height"]))
+    elif rc.get("type") == "lshaped":
+        room = LShapedRoom(float(rc["width1"]), float(rc["depth1"]), float(rc["width2"]), float(rc["depth2"]), float(rc["height"]))
+    else:
+        raise ValueError(f"unknown room type {rc.get('type')!r}")
     sources = []
     for sc in config["sources"]:
         dc = sc.get("directivity", {"type": "omnidirectional"})

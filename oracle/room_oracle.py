@@ -10,13 +10,14 @@ Follows, line by line where arithmetic order matters:
       build_bem_matrix_parallel :448-493, solve_bem_system :412-445 (GMRES through oracle.gmres),
       calculate_incident_field_derivative_parallel :638-679,
       calculate_field_pressure_bem_parallel :687-748
-  math-xem-common/src/geometry.rs  RectangularRoom::generate_mesh :107-183, add_surface_mesh :434-469
+  math-xem-common/src/geometry.rs  RectangularRoom::generate_mesh :107-183, add_surface_mesh :434-469,
+      LShapedRoom::generate_mesh :500-627
   math-xem-common/src/source.rs    DirectivityPattern::{omnidirectional, cardioid, interpolate} :19-98,
       CrossoverFilter::amplitude_at_frequency :127-155, Source::amplitude_towards :203-219
   math-xem-common/src/types.rs     pressure_to_spl :280-287, log_space :290-302
 
 Parity status: the reference holds no numeric golden vectors for this path (its tests are the
-sanity checks restated in tests/test_room_oracle.py) => "parity unpinned by reference vectors,
+sanity checks restated in tests/test_room_cpu.py) => "parity unpinned by reference vectors,
 pinned by faithful restatement", as for the TBEM path.
 
 Scalar loops are literal (small cases); the O(N^2) matrix is also offered vectorised with numpy
@@ -266,6 +267,43 @@ def rectangular_room_mesh(width, depth, height, elements_per_meter):
     add_surface_mesh([0.0, dpt, 0.0], [w, dpt, 0.0], [0.0, dpt, h], nx, nz)    # back wall
     add_surface_mesh([0.0, 0.0, 0.0], [0.0, dpt, 0.0], [0.0, 0.0, h], ny, nz)  # left wall
     add_surface_mesh([w, 0.0, 0.0], [w, dpt, 0.0], [w, 0.0, h], ny, nz)        # right wall
+    return np.array(nodes), np.array(elements, dtype=np.int64)
+
+
+def lshaped_room_mesh(width1, depth1, width2, depth2, height, elements_per_meter):
+    """LShapedRoom::generate_mesh (geometry.rs:500-627) with add_surface_mesh_lshaped (:710-745)."""
+    e = elements_per_meter
+    nodes, elements = [], []
+
+    def add(origin, u_dir, v_dir, nu, nv):
+        base_idx = len(nodes)
+        for j in range(nv + 1):
+            for i in range(nu + 1):
+                u = i / nu
+                v = j / nv
+                nodes.append([origin[d] + u * (u_dir[d] - origin[d]) + v * (v_dir[d] - origin[d]) for d in range(3)])
+        for j in range(nv):
+            for i in range(nu):
+                n0 = base_idx + j * (nu + 1) + i
+                elements.append([n0, n0 + 1, base_idx + (j + 1) * (nu + 1) + i + 1, base_idx + (j + 1) * (nu + 1) + i])
+
+    w1, d1, w2, d2, h = float(width1), float(depth1), float(width2), float(depth2), float(height)
+    nx1 = int(math.ceil(w1 * e)); ny1 = int(math.ceil(d1 * e)); nx2 = int(math.ceil(w2 * e)); ny2 = int(math.ceil(d2 * e))
+    nz = int(math.ceil(h * e))
+    add([0.0, 0.0, 0.0], [w1, 0.0, 0.0], [0.0, d1, 0.0], nx1, ny1)
+    add([0.0, d1, 0.0], [w2, d1, 0.0], [0.0, d1 + d2, 0.0], nx2, ny2)
+    add([0.0, 0.0, h], [w1, 0.0, h], [0.0, d1, h], nx1, ny1)
+    add([0.0, d1, h], [w2, d1, h], [0.0, d1 + d2, h], nx2, ny2)
+    add([0.0, 0.0, 0.0], [w1, 0.0, 0.0], [0.0, 0.0, h], nx1, nz)
+    add([w1, 0.0, 0.0], [w1, d1, 0.0], [w1, 0.0, h], ny1, nz)
+    total_depth = d1 + d2
+    ny_total = int(math.ceil(total_depth * e))
+    add([0.0, 0.0, 0.0], [0.0, total_depth, 0.0], [0.0, 0.0, h], ny_total, nz)
+    add([0.0, total_depth, 0.0], [w2, total_depth, 0.0], [0.0, total_depth, h], nx2, nz)
+    add([w2, d1, 0.0], [w2, total_depth, 0.0], [w2, d1, h], ny2, nz)
+    internal_width = w1 - w2
+    nx_internal = int(math.ceil(internal_width * e))
+    add([w2, d1, 0.0], [w1, d1, 0.0], [w2, d1, h], nx_internal, nz)
     return np.array(nodes), np.array(elements, dtype=np.int64)
 
 

@@ -46,6 +46,48 @@ def test_room_mesh_equals_oracle_loops(dims, epm):
     assert np.allclose(np.abs(n).max(axis=1), 1.0)
 
 
+def test_lshaped_room_mesh_equals_oracle_loops():
+    r = room.LShapedRoom(5.0, 4.0, 3.0, 3.0, 2.5)                       # geometry.rs:781-788
+    assert (r.width1, r.depth1, r.width2, r.depth2, r.height) == (5.0, 4.0, 3.0, 3.0, 2.5)
+    for epm in (1, 3):
+        m = r.generate_mesh(epm)
+        nodes, elems = ro.lshaped_room_mesh(5.0, 4.0, 3.0, 3.0, 2.5, epm)
+        assert np.array_equal(m.nodes, nodes) and np.array_equal(m.elements.astype(np.int64), elems)
+    c, n, a = ro.element_data(nodes, elems)
+    # ten patches: two floors, two ceilings, six vertical walls (the junction wall closes the L)
+    floor = 5.0 * 4.0 + 3.0 * 3.0
+    walls = (5.0 + 4.0 + 7.0 + 3.0 + 3.0 + 2.0) * 2.5
+    assert abs(a.sum() - (2 * floor + walls)) < 1e-12
+    sim, res = room.simulation_from_config(dict(room=dict(type="lshaped", width1=5.0, depth1=4.0, width2=3.0, depth2=3.0, height=2.6),
+                                                sources=[dict(position=dict(x=1, y=1, z=1))], listening_positions=[dict(x=2, y=2, z=1)],
+                                                frequencies=dict(min_freq=40.0, max_freq=500.0, num_points=4), solver=dict(mesh_resolution=3)))
+    assert isinstance(sim.room, room.LShapedRoom) and res == 3 and len(sim.frequencies) == 4 and sim.sources[0].amplitude == 1.0
+
+
+def test_simulation_from_config_rectangular():
+    cfg = dict(room=dict(type="rectangular", width=5.5, depth=7.0, height=2.6),
+               sources=[dict(name="Sub", position=dict(x=0.5, y=0.5, z=0.3), amplitude=1.0, directivity=dict(type="omnidirectional"),
+                             crossover=dict(type="lowpass", cutoff_freq=80.0, order=4)),
+                        dict(name="Main", position=dict(x=1.2, y=0.3, z=1.1), amplitude=0.8,
+                             directivity=dict(type="custom", horizontal_angles=[0.0, 10.0], vertical_angles=[0.0, 10.0, 20.0],
+                                              magnitude=[[1.0, 0.5], [0.9, 0.4], [0.8, 0.3]]),
+                             crossover=dict(type="bandpass", low_cutoff=60.0, high_cutoff=3000.0, order=2))],
+               listening_positions=[dict(x=2.75, y=4.5, z=1.2)],
+               frequencies=dict(min_freq=20.0, max_freq=300.0, num_points=100, spacing="linear"), solver=dict(method="gmres"))
+    sim, res = room.simulation_from_config(cfg)
+    assert res == 2                                                      # default_mesh_resolution (config.rs:413-415)
+    assert sim.frequencies[1] - sim.frequencies[0] == pytest.approx(280.0 / 99)
+    assert sim.sources[0].crossover.kind == "lowpass" and sim.sources[0].crossover.order == 4
+    assert sim.sources[1].directivity.magnitude.shape == (3, 2) and not sim.sources[1].directivity.is_omnidirectional()
+    assert sim.speed_of_sound == 343.0
+    with pytest.raises(ValueError):
+        room.simulation_from_config(dict(cfg, room=dict(type="dome")))
+    bad = dict(cfg, sources=[dict(position=dict(x=0, y=0, z=0), directivity=dict(type="custom", horizontal_angles=[0.0], vertical_angles=[0.0],
+                                                                          magnitude=[[1.0, 2.0]]))])
+    with pytest.raises(ValueError):
+        room.simulation_from_config(bad)                                 # config.rs:246-259 angle / magnitude mismatch
+
+
 # ---- math-xem-common/src/source.rs:228-257 ----------------------------------------------------
 def test_omnidirectional_pattern():
     p = room.DirectivityPattern.omnidirectional()
