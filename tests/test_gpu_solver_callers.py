@@ -100,3 +100,56 @@ def test_bem_solver_rigid_sphere_mie(bem, orc):
     r = np.linalg.norm(m.center, axis=1)
     mie = orc.mie_rigid_sphere(problem.physics.wave_number, 0.1, 50, r, np.arccos(m.center[:, 2] / r))
     assert abs(orc.l2_relative(mie, xd) - 0.2724) < 2e-4
+
+
+# ---- math-bem/tests/test_bem_sphere_integration.rs restated through the BemSolver mirror --------------------
+def _field_vs_mie(bem_solver_mod, orc, frequency, n_theta, n_phi, n_pts, terms):
+    radius, c0, rho = 0.1, 343.0, 1.21
+    k = 2.0 * np.pi * frequency / c0
+    problem = bem_solver_mod.BemProblem.rigid_sphere_scattering_custom(radius, frequency, c0, rho, n_theta, n_phi)
+    solution = bem_solver_mod.BemSolver.new().solve(problem)
+    er = 2.0 * radius
+    thetas = np.pi * np.arange(n_pts) / (n_pts - 1)
+    pts = np.column_stack([er * np.sin(thetas), np.zeros(n_pts), er * np.cos(thetas)])
+    field = solution.evaluate_pressure_field(pts)
+    mie = orc.mie_rigid_sphere(k, radius, terms, np.full(n_pts, er), thetas)
+    rel = [abs(abs(fp.p_total) - abs(m)) / abs(m) if abs(m) > 1e-10 else 0.0 for fp, m in zip(field, mie)]
+    return solution, max(rel)
+
+
+def test_bem_vs_analytical_rayleigh(bem, orc):       # test_bem_sphere_integration.rs:23-118
+    from math_audio_b200 import bem_solver as bs
+
+    _, err = _field_vs_mie(bs, orc, 100.0, 6, 12, 9, 20)
+    assert err < 0.5
+
+
+def test_bem_vs_analytical_mie(bem, orc):            # :121-205
+    from math_audio_b200 import bem_solver as bs
+
+    _, err = _field_vs_mie(bs, orc, 546.0, 8, 16, 13, 30)
+    assert err < 0.75
+
+
+def test_bem_surface_pressure_distribution(bem, orc):  # :208-255
+    from math_audio_b200 import bem_solver as bs
+
+    sol = bs.BemSolver.new().solve(bs.BemProblem.rigid_sphere_scattering_custom(0.1, 200.0, 343.0, 1.21, 8, 16))
+    assert sol.max_surface_pressure() > 0.0
+    assert 1.0 < sol.max_surface_pressure() / sol.mean_surface_pressure() < 5.0
+
+
+def test_bem_mesh_convergence_and_sanity(bem, orc):  # :262-346
+    from math_audio_b200 import bem_solver as bs
+
+    k = 2.0 * np.pi * 300.0 / 343.0
+    er, th = 0.2, np.pi / 4
+    mie = abs(orc.mie_rigid_sphere(k, 0.1, 30, np.array([er]), np.array([th]))[0])
+    errs = []
+    for nt, nphi in [(4, 8), (6, 12), (8, 16)]:
+        sol = bs.BemSolver.new().solve(bs.BemProblem.rigid_sphere_scattering_custom(0.1, 300.0, 343.0, 1.21, nt, nphi))
+        p = abs(sol.evaluate_pressure_field([[er * np.sin(th), 0.0, er * np.cos(th)]])[0].p_total)
+        errs.append(abs(p - mie) / mie)
+    assert min(errs) < 0.5
+    sol = bs.BemSolver.new().solve(bs.BemProblem.rigid_sphere_scattering(0.1, 100.0, 343.0, 1.21))
+    assert sol.num_dofs() > 0 and np.isfinite(sol.max_surface_pressure()) and sol.max_surface_pressure() > 0.0
