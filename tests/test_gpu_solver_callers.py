@@ -153,3 +153,77 @@ def test_bem_mesh_convergence_and_sanity(bem, orc):  # :262-346
     assert min(errs) < 0.5
     sol = bs.BemSolver.new().solve(bs.BemProblem.rigid_sphere_scattering(0.1, 100.0, 343.0, 1.21))
     assert sol.num_dofs() > 0 and np.isfinite(sol.max_surface_pressure()) and sol.max_surface_pressure() > 0.0
+
+
+# ---- math-bem/tests/test_accuracy_parity.rs restated (thresholds are the reference's) -----------------------
+def _rel(c, r):                                      # test_accuracy_parity.rs:29-35
+    return abs(c - r) / abs(r) if abs(r) > 1e-15 else abs(c)
+
+
+def _solve_ka(bs, ka, n_theta, n_phi):
+    radius, c0 = 0.1, 343.0
+    k = ka / radius
+    f = k * c0 / (2.0 * np.pi)
+    return bs.BemSolver.new().with_solver_method(bs.SolverMethod.Direct).solve(
+        bs.BemProblem.rigid_sphere_scattering_custom(radius, f, c0, 1.21, n_theta, n_phi)), k
+
+
+def _ring(er, n):
+    th = np.pi * np.arange(n + 1) / n
+    return th, np.column_stack([er * np.sin(th), np.zeros(n + 1), er * np.cos(th)])
+
+
+def test_accuracy_rayleigh_and_higher_frequency(bem, orc):   # :60-148, :266-326
+    from math_audio_b200 import bem_solver as bs
+
+    for ka, (nt, nphi), npts, terms, limit in [(0.1, (8, 16), 8, 30, 0.20), (0.2, (8, 16), 8, 30, 0.20), (0.3, (8, 16), 8, 30, 0.20),
+                                               (2.0, (12, 24), 16, 50, 0.35)]:
+        sol, k = _solve_ka(bs, ka, nt, nphi)
+        th, pts = _ring(0.2, npts)
+        mag = [abs(fp.p_total) for fp in sol.evaluate_pressure_field(pts)]
+        mie = np.abs(orc.mie_rigid_sphere(k, 0.1, terms, np.full(len(th), 0.2), th))
+        assert max(_rel(a, b) for a, b in zip(mag, mie)) < limit, ka
+
+
+def test_accuracy_mie_regime_surface(bem, orc):              # :151-263
+    from math_audio_b200 import bem_solver as bs
+
+    for ka in (1.0, 1.2):
+        sol, k = _solve_ka(bs, ka, 10, 20)
+        th = np.pi * np.arange(13) / 12
+        mie = np.abs(orc.mie_rigid_sphere(k, 0.1, 50, np.full(13, 0.1 * 1.001), th))
+        c = sol.mesh.center
+        elem_theta = np.arccos(c[:, 2] / np.linalg.norm(c, axis=1))
+        worst = 0.0
+        for t, ref in zip(th, mie):
+            if ref < 0.1:
+                continue
+            j = int(np.argmin(np.abs(elem_theta - t)))       # first minimum, as the reference's strict `<` scan
+            worst = max(worst, _rel(abs(sol.surface_pressure[j]), ref))
+        assert worst < 0.30, ka
+
+
+def test_mesh_convergence_forward_back_and_phase(bem, orc):  # :328-416, :419-497, :500-580
+    from math_audio_b200 import bem_solver as bs
+
+    k = 10.0
+    er, th = 0.2, np.pi / 4
+    ref = abs(orc.mie_rigid_sphere(k, 0.1, 50, np.array([er]), np.array([th]))[0])
+    errs = []
+    for nt, nphi in [(6, 12), (8, 16), (10, 20), (12, 24)]:
+        sol, _ = _solve_ka(bs, 1.0, nt, nphi)
+        errs.append(_rel(abs(sol.evaluate_pressure_field([[er * np.sin(th), 0.0, er * np.cos(th)]])[0].p_total), ref))
+    assert errs[-1] < 0.25
+    sol, _ = _solve_ka(bs, 1.0, 10, 20)
+    f = sol.evaluate_pressure_field([[0.0, 0.0, 0.3], [0.0, 0.0, -0.3]])
+    pf, pb = abs(f[0].p_total), abs(f[1].p_total)
+    af = abs(orc.mie_rigid_sphere(k, 0.1, 40, np.array([0.3]), np.array([0.0]))[0])
+    ab = abs(orc.mie_rigid_sphere(k, 0.1, 40, np.array([0.3]), np.array([np.pi]))[0])
+    assert pf > 0.0 and pb > 0.0 and _rel(pf / pb, af / ab) < 0.50
+    thr, pts = _ring(0.2, 8)
+    mie = orc.mie_rigid_sphere(k, 0.1, 40, np.full(9, 0.2), thr)
+    worst = 0.0
+    for fp, m in zip(sol.evaluate_pressure_field(pts), mie):
+        d = abs(np.angle(fp.p_total) - np.angle(m))
+        worst = max(worst, 2 * np.pi - d if d > np.pi else d)
+    assert worst < np.pi / 4
