@@ -189,7 +189,7 @@ int bemb200_ctx_create_ex(int device, int rank, int nranks, const uint8_t* nccl_
 void bemb200_ctx_destroy(bemb200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    free_peer_exchange(ctx);
+    free_peer_exchange(ctx, false);
     if (ctx->nccl_comm && ncclshim::CommDestroy) ncclshim::CommDestroy(ctx->nccl_comm);
     if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

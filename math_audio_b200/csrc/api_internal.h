@@ -62,7 +62,7 @@ namespace bemb {
 int set_error(bemb200_ctx* ctx, int code, const std::string& msg);
 int cuda_fail(bemb200_ctx* ctx, cudaError_t e, const char* what);
 void free_workspace(bemb200_matrix* m);
-void free_peer_exchange(bemb200_ctx* ctx);
+void free_peer_exchange(bemb200_ctx* ctx, bool collective);
 }  // namespace bemb
 
 #define BEMB_CUDA(ctx, call)                                          \

@@ -72,20 +72,27 @@ void free_workspace(bemb200_matrix* m) {
 // all-gather path in place.  BEMB200_PEER_FUSED=0 disables it.
 constexpr size_t PX_HEADER = 256;
 namespace bemb {
-void free_peer_exchange(bemb200_ctx* ctx) {
+void free_peer_exchange(bemb200_ctx* ctx, bool collective) {
     PeerExchange& px = ctx->px;
     for (int p = 0; p < ctx->nranks && p < 8; ++p)
         if (p != ctx->rank && px.base[p]) cudaIpcCloseMemHandle(px.base[p]);
-    if (px.ok && ctx->nccl_comm) {
+    bool may_free = true;
+    if (px.ok) {
         // nobody frees exported memory while a peer may still have it mapped
-        unsigned char* tok = nullptr;
-        if (cudaMalloc((void**)&tok, (size_t)ctx->nranks) == cudaSuccess) {
-            nccl_allgather_bytes(ctx, tok + ctx->rank, tok, 1);
-            cudaStreamSynchronize(ctx->stream);
-            cudaFree(tok);
+        if (collective && ctx->nccl_comm) {
+            unsigned char* tok = nullptr;
+            if (cudaMalloc((void**)&tok, (size_t)ctx->nranks) == cudaSuccess) {
+                nccl_allgather_bytes(ctx, tok + ctx->rank, tok, 1);
+                cudaStreamSynchronize(ctx->stream);
+                cudaFree(tok);
+            }
+        } else {
+            // context destruction is not a collective call (a peer may already be gone, and waiting for it could
+            // hang this process): keep the few MB alive until the process exits rather than risk either
+            may_free = false;
         }
     }
-    if (px.local) cudaFree(px.local);
+    if (px.local && may_free) cudaFree(px.local);
     if (px.err_h) cudaFreeHost(px.err_h);
     px = PeerExchange();
     cudaGetLastError();
@@ -97,7 +104,7 @@ static int ensure_peer_exchange(bemb200_ctx* ctx, uint64_t npad) {
     static const bool enabled = []() { const char* v = std::getenv("BEMB200_PEER_FUSED"); return v ? std::atoi(v) != 0 : true; }();
     if (!enabled || ctx->nranks < 2 || ctx->nranks > MAX_PEERS || !ctx->nccl_comm) return BEMB200_OK;
     if (px.tried && (!px.ok || px.npad >= npad)) return BEMB200_OK;
-    if (px.tried) free_peer_exchange(ctx);  // a larger operator: re-establish (collective, same on every rank)
+    if (px.tried) free_peer_exchange(ctx, true);  // a larger operator: re-establish (collective, same on every rank)
     px.tried = true;
     px.npad = npad;
     const int P = ctx->nranks;
