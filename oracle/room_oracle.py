@@ -1,6 +1,6 @@
 """CPU restatement of the reference's room-acoustics dense path -- TEST INFRASTRUCTURE ONLY.
 
-Only tests/, __graft_entry__.smoke() and the CPU-baseline legs of bench.py / scripts may import
+Only tests/ (incl. the measurement drivers under tests/drivers/), __graft_entry__.smoke() and the CPU-baseline legs of bench.py may import
 this module; the product (math_audio_b200/) never does.
 
 Follows, line by line where arithmetic order matters:

@@ -1,6 +1,6 @@
 """Row-sharded parity check, one process per GPU:
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 scripts/dist_parity.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tests/drivers/dist_parity.py
 
 Every rank assembles its row block, the ranks solve together (ZGEMV epilogue over peer memory or
 NCCL all-gather, BEMB200_PEER_FUSED=0 forces the latter) and each rank compares against the CPU
@@ -13,7 +13,7 @@ import sys
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import torch.distributed as dist
 

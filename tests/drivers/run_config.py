@@ -3,7 +3,7 @@
 parity by sampled rows against the CPU oracle and by an independent residual, and write a
 JSON summary to gpurun_out/config<k>_g<N>.json (copied to profiles/ by hand).
 
-    torchrun --nproc-per-node N scripts/run_config.py --config 4 [--rows-checked 64]
+    torchrun --nproc-per-node N tests/drivers/run_config.py --config 4 [--rows-checked 64]
 
 config 3: "cabinet" 0.32 x 0.44 x 0.64 m closed Quad4 box, 64x88x128 -> 50 176 elements, piston
           (full-length velocity BC v=1 within 80 mm of the front-wall centre), f = 1 kHz, beta = i/k.
@@ -19,7 +19,7 @@ from pathlib import Path
 
 import numpy as np
 
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 
 

@@ -9,7 +9,7 @@ from pathlib import Path
 
 import numpy as np
 
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 from math_audio_b200 import bem  # noqa: E402
 from math_audio_b200.incident import IncidentField  # noqa: E402

@@ -5,7 +5,7 @@ restated from math-bem/configs/home_theater_2_1.json (5.5 x 7.0 x 2.6 m, two mai
 80 Hz + a subwoofer low-passed at 80 Hz, listening position (2.75, 4.5, 1.2), 20-300 Hz log grid,
 mesh_resolution 10 -> 14 200 Quad4 elements).
 
-    python scripts/run_room.py [--frequencies 12] [--mesh-resolution 10] [--rows-checked 48]
+    python tests/drivers/run_room.py [--frequencies 12] [--mesh-resolution 10] [--rows-checked 48]
 
 Per frequency: build_bem_matrix_parallel + incident right-hand side + GMRES(restart 50, tol 1e-6,
 100 cycles) + field pressure at the listening position -> SPL.  Reports seconds per frequency,
@@ -22,7 +22,7 @@ from pathlib import Path
 
 import numpy as np
 
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 
 CONFIG = {

@@ -1,4 +1,4 @@
-"""Multi-GPU parity (needs >= 2 GPUs on the box; skipped otherwise): scripts/dist_parity.py under
+"""Multi-GPU parity (needs >= 2 GPUs on the box; skipped otherwise): tests/drivers/dist_parity.py under
 torchrun, once over peer memory (ZGEMV epilogue -> every rank's work vector) and once over the
 NCCL all-gather fallback.  Both must agree with the oracle and be bit-identical across ranks."""
 import os
@@ -26,7 +26,7 @@ def test_row_sharded_parity_two_ranks(peer):
     env = dict(os.environ, BEMB200_PEER_FUSED=peer)
     port = 29600 + (os.getpid() % 200) + (1 if peer == "1" else 0)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", str(port), os.path.join(ROOT, "scripts", "dist_parity.py")]
+           "--master-port", str(port), os.path.join(ROOT, "tests", "drivers", "dist_parity.py")]
     r = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("OK") >= 2
