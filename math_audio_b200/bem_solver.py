@@ -22,6 +22,7 @@ import numpy as np
 
 from . import bem
 from .incident import IncidentField
+from .postprocess import FieldPoint, compute_total_field
 from .mesh import BC_PRESSURE, BC_VELOCITY, Mesh, generate_icosphere_mesh, generate_sphere_mesh
 from .types import PhysicsParams
 
@@ -90,21 +91,6 @@ class BemProblem:
 
 
 @dataclass
-class FieldPoint:
-    """postprocess/pressure.rs:24-56."""
-    position: np.ndarray
-    p_incident: complex
-    p_scattered: complex
-
-    @property
-    def p_total(self) -> complex:
-        return self.p_incident + self.p_scattered
-
-    def spl_db(self) -> float:
-        return 20.0 * math.log10(abs(self.p_total) / 20e-6)
-
-
-@dataclass
 class BemSolution:
     surface_pressure: np.ndarray
     mesh: Mesh                       # elements + nodes with the boundary conditions the solve used
@@ -114,12 +100,9 @@ class BemSolution:
 
     def evaluate_pressure_field(self, points) -> List[FieldPoint]:
         """compute_total_field (pressure.rs:273-309): incident + scattered (device field kernel)."""
-        pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
         if self.staged is None:
             self.staged = bem.StagedMesh(self.mesh)
-        p_inc = self.incident_field.evaluate_pressure(pts, self.physics)
-        p_sc = bem.compute_scattered_field(pts, self.staged, self.surface_pressure, None, self.physics)
-        return [FieldPoint(pts[i].copy(), complex(p_inc[i]), complex(p_sc[i])) for i in range(pts.shape[0])]
+        return compute_total_field(points, self.staged, self.surface_pressure, None, self.incident_field, self.physics)
 
     def evaluate_pressure(self, point) -> complex:
         return self.evaluate_pressure_field(np.asarray(point, dtype=np.float64).reshape(1, 3))[0].p_total

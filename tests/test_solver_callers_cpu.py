@@ -74,3 +74,20 @@ def test_bem_solver_creation_and_prepare_elements():
     assert (m.bc_type == 1).all()
     with pytest.raises(bs.BemError):
         bs.BemSolver.new().with_assembly_method(bs.AssemblyMethod.Mlfmm).solve(p)
+
+
+# ---- math-bem/src/core/postprocess/pressure.rs:493-546 ----------------------------------------
+def test_field_point_and_eval_point_generators():
+    from math_audio_b200 import postprocess as pp
+
+    fp = pp.FieldPoint(np.array([1.0, 0.0, 0.0]), 1.0 + 0j, 0.5 + 0.3j)
+    assert abs(fp.p_total - (1.5 + 0.3j)) < 1e-10 and fp.magnitude() > 0.0 and np.isfinite(fp.spl_db())
+    pts = pp.generate_sphere_eval_points(2.0, 10, 20)
+    assert pts.shape == (200, 3) and np.allclose(np.linalg.norm(pts, axis=1), 2.0, atol=1e-10)
+    line = pp.generate_line_eval_points([0.0, 0.0, 0.0], [1.0, 0.0, 0.0], 11)
+    assert line.shape == (11, 3) and abs(line[0, 0]) < 1e-10 and abs(line[10, 0] - 1.0) < 1e-10 and abs(line[1, 0] - line[0, 0] - 0.1) < 1e-10
+    assert pp.generate_line_eval_points([1.0, 2.0, 3.0], [4.0, 5.0, 6.0], 1).tolist() == [[1.0, 2.0, 3.0]]   # (n-1).max(1)
+    plane = pp.generate_plane_eval_points([0.0, 0.0, 0.0], [0.0, 0.0, 1.0], 1.0, 5)
+    assert plane.shape == (25, 3) and np.all(np.abs(plane[:, 2]) < 1e-10)
+    tilted = pp.generate_plane_eval_points([1.0, 1.0, 1.0], [2.0, 0.0, 0.0], 0.5, 3)          # |n.x| >= 0.9 branch
+    assert np.allclose(tilted[:, 0], 1.0) and np.allclose(tilted.mean(axis=0), [1.0, 1.0, 1.0])
