@@ -25,6 +25,10 @@ class IncidentField:
         return IncidentField(plane_waves=[(np.array([0.0, 0.0, 1.0]), 1.0 + 0j)])
 
     @staticmethod
+    def plane_wave_neg_z() -> "IncidentField":  # incident.rs:54-59
+        return IncidentField.plane_wave([0.0, 0.0, -1.0], 1.0)
+
+    @staticmethod
     def plane_wave(direction, amplitude: float = 1.0) -> "IncidentField":  # incident.rs:62-76
         d = np.asarray(direction, dtype=np.float64)
         ln = math.sqrt(d[0] ** 2 + d[1] ** 2 + d[2] ** 2)

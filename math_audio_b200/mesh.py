@@ -186,6 +186,87 @@ def generate_sphere_mesh(radius: float, n_theta: int, n_phi: int) -> Mesh:
     return mesh_from_data(np.array(nodes), np.array(el, dtype=np.uint32))
 
 
+def generate_cylinder_mesh(radius: float, height: float, n_circumference: int, n_height: int) -> Mesh:
+    """Open cylinder (lateral surface only), Quad4: generators.rs:242-285."""
+    nodes, el = [], []
+    z_min = -height / 2.0
+    dz = height / n_height
+    for i in range(n_height + 1):
+        z = z_min + i * dz
+        for j in range(n_circumference):
+            phi = 2.0 * math.pi * j / n_circumference
+            nodes.append([radius * math.cos(phi), radius * math.sin(phi), z])
+    for i in range(n_height):
+        r0, r1 = i * n_circumference, (i + 1) * n_circumference
+        for j in range(n_circumference):
+            jn = (j + 1) % n_circumference
+            el.append([r0 + j, r0 + jn, r1 + jn, r1 + j])
+    return mesh_from_data(np.array(nodes), np.array(el, dtype=np.uint32))
+
+
+def generate_closed_cylinder_mesh(radius: float, height: float, n_circumference: int, n_height: int, n_cap_rings: int) -> Mesh:
+    """Cylinder with end caps (Quad4 lateral surface and cap rings, Tri3 fans at the cap centres):
+    generators.rs:287-432."""
+    nodes, el = [], []
+    z_min, z_max = -height / 2.0, height / 2.0
+    dz = height / n_height
+    nc = n_circumference
+    for i in range(n_height + 1):
+        z = z_min + i * dz
+        for j in range(nc):
+            phi = 2.0 * math.pi * j / nc
+            nodes.append([radius * math.cos(phi), radius * math.sin(phi), z])
+    bottom_center = len(nodes)
+    nodes.append([0.0, 0.0, z_min])
+    for ring in range(1, n_cap_rings + 1):
+        r = radius * ring / n_cap_rings
+        for j in range(nc):
+            phi = 2.0 * math.pi * j / nc
+            nodes.append([r * math.cos(phi), r * math.sin(phi), z_min])
+    top_center = len(nodes)
+    nodes.append([0.0, 0.0, z_max])
+    for ring in range(1, n_cap_rings + 1):
+        r = radius * ring / n_cap_rings
+        for j in range(nc):
+            phi = 2.0 * math.pi * j / nc
+            nodes.append([r * math.cos(phi), r * math.sin(phi), z_max])
+    for i in range(n_height):
+        r0, r1 = i * nc, (i + 1) * nc
+        for j in range(nc):
+            jn = (j + 1) % nc
+            el.append([r0 + j, r0 + jn, r1 + jn, r1 + j])
+    b1 = bottom_center + 1
+    for j in range(nc):
+        jn = (j + 1) % nc
+        el.append([bottom_center, b1 + jn, b1 + j])
+    for ring in range(n_cap_rings - 1):
+        rs = bottom_center + 1 + ring * nc
+        ns = rs + nc
+        for j in range(nc):
+            jn = (j + 1) % nc
+            el.append([rs + j, rs + jn, ns + jn, ns + j])
+    outer_bottom = bottom_center + 1 + (n_cap_rings - 1) * nc
+    for j in range(nc):
+        jn = (j + 1) % nc
+        el.append([outer_bottom + j, outer_bottom + jn, jn, j])
+    t1 = top_center + 1
+    for j in range(nc):
+        jn = (j + 1) % nc
+        el.append([top_center, t1 + j, t1 + jn])
+    for ring in range(n_cap_rings - 1):
+        rs = top_center + 1 + ring * nc
+        ns = rs + nc
+        for j in range(nc):
+            jn = (j + 1) % nc
+            el.append([rs + j, ns + j, ns + jn, rs + jn])
+    outer_top = top_center + 1 + (n_cap_rings - 1) * nc
+    top_row = n_height * nc
+    for j in range(nc):
+        jn = (j + 1) % nc
+        el.append([top_row + j, top_row + jn, outer_top + jn, outer_top + j])
+    return mesh_from_data(np.array(nodes), el)
+
+
 _ICO_FACES = [
     [0, 11, 5], [0, 5, 1], [0, 1, 7], [0, 7, 10], [0, 10, 11],
     [1, 5, 9], [5, 11, 4], [11, 10, 2], [10, 7, 6], [7, 1, 8],

@@ -58,6 +58,24 @@ class PhysicsParams:
             return complex(0.0, self.harmonic_factor / (self.wave_number + k_ref))
         return 0j
 
+    def burton_miller_beta_floored(self, edge_e_magnitude: float, min_beta_e: float) -> complex:  # types.rs:100-117
+        if self.tau > 0.0:
+            eta = max(1.0 / self.wave_number, min_beta_e / edge_e_magnitude)
+            return complex(0.0, self.harmonic_factor * eta)
+        return 0j
+
+    @staticmethod
+    def optimal_beta_scale(ka: float) -> float:  # types.rs:201-213
+        if ka < 0.85:
+            return 32.0
+        if ka < 0.92:
+            return 8.0
+        if ka < 1.2:
+            return 4.0
+        if ka < 1.8:
+            return 8.0
+        return 16.0
+
     def burton_miller_beta_optimal(self, element_size: float) -> complex:  # types.rs:124-131
         if self.tau > 0.0:
             k_ref = 1.0 / element_size

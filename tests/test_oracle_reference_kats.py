@@ -354,3 +354,38 @@ def test_qa_suite_scattering(orc, sub, ka, limit, expect):
     assert err < limit
     # the survey's independent (numba) restatement measured these values
     assert abs(err - expect) < 2e-4
+
+
+# ---- math-bem/src/core/mesh/generators.rs:242-432, 649-671 ------------------------------------
+def test_cylinder_mesh_generation():
+    from math_audio_b200.mesh import generate_closed_cylinder_mesh, generate_cylinder_mesh
+
+    m = generate_cylinder_mesh(1.0, 2.0, 16, 8)
+    assert m.n_nodes == 9 * 16 and m.n_elem == 8 * 16
+    assert np.abs(np.hypot(m.nodes[:, 0], m.nodes[:, 1]) - 1.0).max() < 1e-10
+    assert (m.etype == 4).all() and (m.area > 0.0).all()
+    c = generate_closed_cylinder_mesh(0.5, 1.2, 12, 4, 3)
+    # lateral quads + per cap: centre fan (Tri3) + (rings-1) quad rings + the ring joining the lateral surface
+    assert c.n_elem == 4 * 12 + 2 * (12 + 2 * 12 + 12) and (c.etype == 3).sum() == 24
+    assert c.n_nodes == 5 * 12 + 2 * (1 + 3 * 12)
+    # the outermost cap ring duplicates the rim nodes of the lateral surface, so the 2 x 12 quads joining them are
+    # degenerate (zero area, zero normal) -- a property of the reference's generator, mirrored as is
+    degenerate = c.area < 1e-14
+    assert degenerate.sum() == 24 and not c.normal[degenerate].any()
+    assert ((c.normal * c.center).sum(1)[~degenerate] > 0).all()         # stored normals flipped outward
+    # polygonal cross-section: caps are regular 12-gons, the wall has 12 flat strips
+    poly = 0.5 * 12 * 0.5 ** 2 * math.sin(2 * math.pi / 12)
+    side = 12 * 2 * 0.5 * math.sin(math.pi / 12) * 1.2
+    assert abs(c.area.sum() - (2 * poly + side)) < 1e-10
+
+
+def test_beta_helpers_and_neg_z_wave():
+    ph = PhysicsParams.from_wave_number(10.0)
+    assert abs(ph.burton_miller_beta_floored(80.0, 5.0) - complex(0.0, 0.1)) < 1e-15   # 1/k = 0.1 > 5/80
+    assert ph.burton_miller_beta_floored(20.0, 5.0) == complex(0.0, 0.25)              # floor 5/20 wins
+    assert [PhysicsParams.optimal_beta_scale(x) for x in (0.5, 0.9, 1.0, 1.5, 2.0)] == [32.0, 8.0, 4.0, 8.0, 16.0]
+    from math_audio_b200.incident import IncidentField
+
+    w = IncidentField.plane_wave_neg_z()
+    p = w.evaluate_pressure(np.array([[0.0, 0.0, 0.3]]), ph)
+    assert abs(p[0] - np.exp(-1j * 3.0)) < 1e-15
