@@ -141,6 +141,24 @@ def test_config1_uv_sphere_solve_and_mie(bem, orc):
     assert np.linalg.norm(fg - fo) / np.linalg.norm(fo) < X_TOL
 
 
+def test_cylinder_quad_mesh_parity(bem, orc):
+    """generate_cylinder_mesh (generators.rs:242-285): an open Quad4 shell off the coordinate planes
+    (rectangular, hence flat, quads through the affine far kernel; normals flipped outward by the generator)."""
+    from math_audio_b200.mesh import generate_cylinder_mesh
+
+    mesh = generate_cylinder_mesh(0.12, 0.4, 24, 16)
+    assert mesh.n_elem == 384 and (mesh.etype == 4).all()
+    for ka in (0.3, 2.5):
+        ph = PhysicsParams.from_wave_number(ka / 0.12)
+        beta = ph.burton_miller_beta_scaled(4.0)
+        system = bem.build_tbem_system_with_beta(mesh, ph, beta)
+        Ao, rhso, _ = orc.assemble(mesh, ph.wave_number, beta)
+        rel, rown = entry_err(system.matrix.rows(), Ao)
+        assert rel < ENTRY_TOL and rown < ENTRY_TOL, (ka, rel, rown)
+        st = system.matrix.assembly_stats()
+        assert st["special_pairs"] == 0 and st["near_pairs"] > 0
+
+
 def test_mixed_bc_and_element_types(bem, orc):
     """Pressure / transfer BCs, 1-entry non-zero velocity (the N0-weighted quirk of
     regular.rs:159-164), Tri3 + Quad4 in one mesh, a warped (non-planar) Quad4."""
