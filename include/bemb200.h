@@ -101,6 +101,12 @@ int bemb200_ctx_set_background(bemb200_ctx* ctx, int blocks_per_sm);
  * background assembly above): the Gram-Schmidt step then uses its 16-CTA cluster kernel instead
  * of the whole-GPU cooperative kernel, whose grid barriers stall behind foreign warps. */
 int bemb200_ctx_set_shared_gpu(bemb200_ctx* ctx, int shared);
+/* While an assembly into `m` runs as a background grid on another context/stream (another thread is
+ * inside bemb200_assemble_staged), start additional far-kernel blocks on `ctx`'s stream that pull
+ * work items from the same counter: the assembly then finishes at full speed.  Meant for the
+ * moment the solver of a pipelined sweep has finished and the GPU would otherwise idle behind the
+ * polite background grid.  No-op when nothing is in flight. */
+int bemb200_matrix_boost_assembly(bemb200_matrix* m, bemb200_ctx* ctx);
 /* Row-sharded solves (nranks > 1): *active = 1 once the ranks have mapped each other's work
  * vectors (CUDA IPC over NVLink) and the Arnoldi matvec stores its slab of A v straight into
  * every rank's memory from the ZGEMV epilogue -- no all-gather kernel; 0 = NCCL all-gather

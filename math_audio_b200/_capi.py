@@ -64,6 +64,7 @@ SYMBOLS = {
     "bemb200_matrix_set_context": (C.c_int, [_VP, _VP]),
     "bemb200_ctx_set_background": (C.c_int, [_VP, C.c_int]),
     "bemb200_ctx_set_shared_gpu": (C.c_int, [_VP, C.c_int]),
+    "bemb200_matrix_boost_assembly": (C.c_int, [_VP, _VP]),
     "bemb200_ctx_peer_exchange_active": (C.c_int, [_VP, C.POINTER(C.c_int)]),
     "bemb200_last_error": (C.c_char_p, [_VP]),
     "bemb200_partition": (None, [C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),

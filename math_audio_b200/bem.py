@@ -181,6 +181,11 @@ class DeviceMatrix:
     def device_ptr(self) -> int:
         return int(self._lib.bemb200_matrix_device_ptr(self._h) or 0)
 
+    def boost_assembly(self, ctx: "Context") -> None:
+        """Join a background assembly into this matrix (running in another thread/context) with extra far-kernel blocks
+        on ``ctx``'s stream; no-op when none is in flight."""
+        _capi.check(self._lib.bemb200_matrix_boost_assembly(self._h, ctx._h), ctx._h)
+
     def set_context(self, ctx: "Context") -> None:
         """Hand the matrix to another context of the same device (frequency-sweep pipelining)."""
         _capi.check(self._lib.bemb200_matrix_set_context(self._h, ctx._h), ctx._h)

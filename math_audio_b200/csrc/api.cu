@@ -364,6 +364,9 @@ static int matrix_alloc(bemb200_ctx* ctx, uint64_t n_rows, uint64_t n_cols, uint
         m->near_cap = (unsigned int)(nloc * 64 + 4096);
         e = cudaMalloc((void**)&m->near_list, (size_t)m->near_cap * sizeof(uint2));
         if (e == cudaSuccess) e = cudaMalloc((void**)&m->near_count, sizeof(unsigned int));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&m->work_counters, 2 * sizeof(unsigned int));
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->far_ready_ev, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->boost_ev, cudaEventDisableTiming);
     }
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&m->ev[i]);
     if (e != cudaSuccess) {
@@ -390,6 +393,9 @@ void bemb200_matrix_free(bemb200_matrix* m) {
     if (m->rhs) cudaFree(m->rhs);
     if (m->near_list) cudaFree(m->near_list);
     if (m->near_count) cudaFree(m->near_count);
+    if (m->work_counters) cudaFree(m->work_counters);
+    if (m->far_ready_ev) cudaEventDestroy(m->far_ready_ev);
+    if (m->boost_ev) cudaEventDestroy(m->boost_ev);
     for (int i = 0; i < 4; ++i)
         if (m->ev[i]) cudaEventDestroy(m->ev[i]);
     delete m;
@@ -439,12 +445,41 @@ int bemb200_assemble_staged(bemb200_ctx* ctx, const bemb200_staged_mesh* sm, con
     ASM_CUDA(cudaEventRecord(m->ev[0], s));
     for (int attempt = 0; attempt < 2; ++attempt) {
         ASM_CUDA(cudaMemsetAsync(m->near_count, 0, sizeof(unsigned int), s));
+        const int bg = ctx->background_blocks_per_sm.load();
+        const bool boostable = bg > 0 && attempt == 0 && m->work_counters;
+        if (boostable) {
+            ASM_CUDA(cudaMemsetAsync(m->work_counters, 0, 2 * sizeof(unsigned int), s));
+            ASM_CUDA(cudaEventRecord(m->far_ready_ev, s));  // everything the far pass depends on is enqueued before this
+        }
         ASM_CUDA(cudaEventRecord(m->ev[1], s));
-        ASM_CUDA(launch_far(dm, ph, row_begin, row_end, m->A, dm.n, m->near_list, m->near_cap, m->near_count,
-                            ctx->background_blocks_per_sm.load(), s));
+        {
+            std::lock_guard<std::mutex> bl(m->boost_mu);
+            m->relaunch.clear();
+            m->boost_pending = false;
+            cudaError_t fe = launch_far(dm, ph, row_begin, row_end, m->A, dm.n, m->near_list, m->near_cap, m->near_count, bg,
+                                        boostable ? m->work_counters : nullptr, boostable ? &m->relaunch : nullptr, s);
+            if (fe != cudaSuccess) return fail(cuda_fail(ctx, fe, "launch_far"));
+            m->far_running = boostable;
+        }
         ASM_CUDA(cudaEventRecord(m->ev[2], s));
         ASM_CUDA(cudaMemcpyAsync(&count, m->near_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
         ASM_CUDA(cudaStreamSynchronize(s));
+        {
+            // the persistent blocks are done; helper blocks of a boost may still hold their last items
+            bool pending;
+            {
+                std::lock_guard<std::mutex> bl(m->boost_mu);
+                m->far_running = false;
+                pending = m->boost_pending;
+                m->boost_pending = false;
+                m->relaunch.clear();
+            }
+            if (pending) {
+                ASM_CUDA(cudaEventSynchronize(m->boost_ev));
+                ASM_CUDA(cudaMemcpyAsync(&count, m->near_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+                ASM_CUDA(cudaStreamSynchronize(s));
+            }
+        }
         if (count <= m->near_cap) break;
         // list overflow (pathological mesh): grow and redo the far pass once
         cudaFree(m->near_list);
@@ -520,6 +555,20 @@ int bemb200_ctx_set_background(bemb200_ctx* ctx, int blocks_per_sm) {
 int bemb200_ctx_set_shared_gpu(bemb200_ctx* ctx, int shared) {
     if (!ctx) return set_error(ctx, BEMB200_EINVAL, "NULL context");
     ctx->shared_gpu.store(shared ? 1 : 0);
+    return BEMB200_OK;
+}
+
+int bemb200_matrix_boost_assembly(bemb200_matrix* m, bemb200_ctx* ctx) {
+    if (!m || !ctx) return set_error(ctx, BEMB200_EINVAL, "NULL argument");
+    if (ctx->device != m->ctx->device) return set_error(ctx, BEMB200_EINVAL, "contexts must share the device");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::lock_guard<std::mutex> bl(m->boost_mu);
+    if (!m->far_running || m->relaunch.empty() || m->boost_pending) return BEMB200_OK;  // nothing in flight (or already boosted)
+    BEMB_CUDA(ctx, cudaSetDevice(ctx->device));
+    BEMB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, m->far_ready_ev, 0));
+    for (auto& fn : m->relaunch) BEMB_CUDA(ctx, fn(ctx->stream));
+    BEMB_CUDA(ctx, cudaEventRecord(m->boost_ev, ctx->stream));
+    m->boost_pending = true;
     return BEMB200_OK;
 }
 

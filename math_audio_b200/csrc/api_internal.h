@@ -53,6 +53,13 @@ struct bemb200_matrix {
     bemb200_assembly_stats stats{};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     GmresWorkspace* ws = nullptr;
+    // background assembly that a second stream may join (bemb200_matrix_boost_assembly)
+    unsigned int* work_counters = nullptr;  // 2 device counters (Tri3 / Quad4 far pass)
+    std::mutex boost_mu;
+    bool far_running = false;               // the far pass of an assembly into this matrix is in flight
+    bool boost_pending = false;             // helper blocks were started: wait for boost_ev before using the far results
+    bemb::FarRelaunch relaunch;
+    cudaEvent_t far_ready_ev = nullptr, boost_ev = nullptr;
     // solver statistics of the last call
     uint64_t last_launches = 0, last_matvecs = 0;
     double last_matvec_ms = 0.0;

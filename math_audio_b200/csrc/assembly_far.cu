@@ -59,8 +59,10 @@ far_kernel(const double* __restrict__ far_k, const double* __restrict__ far_c, c
            const double* __restrict__ srcdat, uint32_t n, uint64_t row_begin, uint64_t row_end, uint32_t rows_per_block,
            uint32_t nchunks, uint32_t total_items, uint32_t items_per_block,
            double wavruim, double k2, double cH, double beta_re, double beta_im, cplx* __restrict__ A, uint64_t lda,
-           uint2* __restrict__ near_list, unsigned int near_cap, unsigned int* __restrict__ near_count) {
+           uint2* __restrict__ near_list, unsigned int near_cap, unsigned int* __restrict__ near_count,
+           unsigned int* __restrict__ work_counter) {
     __shared__ __align__(128) double sm_k[NQ * TILE];  // kappa_q, [q][column]
+    __shared__ uint32_t s_item;
     __shared__ __align__(16) double2 sm_tab[SINCOS_TAB];
     __shared__ __align__(8) unsigned long long mbar;
 
@@ -82,6 +84,8 @@ far_kernel(const double* __restrict__ far_k, const double* __restrict__ far_c, c
     // that consecutive items share the tile (one item per block in the normal launch; a
     // "background" launch -- assembly of the next frequency underneath a running solve -- uses a
     // small persistent grid so that it leaves registers and shared memory to the solver's kernels).
+    // With a work counter the items are pulled dynamically instead, so that a second launch of this
+    // kernel ("boost", once the solver has left the GPU) can join in and finish the same assembly.
     const uint32_t item_first = blockIdx.x * items_per_block;
     const uint32_t item_last = (item_first + items_per_block < total_items) ? item_first + items_per_block : total_items;
     uint32_t cur_tile = 0xffffffffu, loads = 0;
@@ -91,7 +95,18 @@ far_kernel(const double* __restrict__ far_k, const double* __restrict__ far_c, c
     uint32_t col = 0;
     const double* kq = sm_k + t;
 
-    for (uint32_t item = item_first; item < item_last; ++item) {
+    for (uint32_t it = 0;; ++it) {
+    uint32_t item;
+    if (work_counter) {
+        __syncthreads();
+        if (t == 0) s_item = atomicAdd(work_counter, 1u);
+        __syncthreads();
+        item = s_item;
+        if (item >= total_items) break;
+    } else {
+        item = item_first + it;
+        if (item >= item_last) break;
+    }
     const uint32_t tile = item / nchunks, chunk = item - tile * nchunks;
     if (tile != cur_tile) {
         cur_tile = tile;
@@ -261,7 +276,7 @@ int env_int(const char* name, int dflt) {
 template <int NQ, bool BIMAG, int MINB>
 cudaError_t launch_far_v(const DeviceMesh& m, const Phys& ph, uint64_t row_begin, uint64_t row_end, cplx* A, uint64_t lda,
                          uint2* near_list, unsigned int near_cap, unsigned int* near_count, int background_blocks_per_sm,
-                         cudaStream_t s) {
+                         unsigned int* work_counter, FarRelaunch* relaunch, cudaStream_t s) {
     const uint64_t nrows = row_end - row_begin;
     // enough work items to fill 148 SMs x MINB resident blocks several times over, but row chunks
     // long enough to amortise the per-block set-up
@@ -270,25 +285,39 @@ cudaError_t launch_far_v(const DeviceMesh& m, const Phys& ph, uint64_t row_begin
     const uint32_t nchunks = (uint32_t)((nrows + rpb - 1) / rpb);
     const uint32_t total = m.ntiles * nchunks;
     uint32_t grid = total, ipb = 1;
+    unsigned int* counter = nullptr;
     if (background_blocks_per_sm > 0 && total > 148u * (uint32_t)background_blocks_per_sm) {
         grid = 148u * (uint32_t)background_blocks_per_sm;  // persistent, polite grid
         ipb = (total + grid - 1) / grid;
         grid = (total + ipb - 1) / ipb;
+        counter = work_counter;  // dynamic item distribution (pre-zeroed by the caller) when a boost may join
     }
     const double cH = ph.sign * ph.gamma * ph.tau;
-    far_kernel<NQ, BIMAG, MINB><<<grid, TILE, 0, s>>>(m.far_k, m.far_c, m.col_class, m.src, m.n, row_begin, row_end, rpb, nchunks,
-                                                      total, ipb, ph.wavruim, ph.k2, cH, ph.beta.re, ph.beta.im, A, lda,
-                                                      near_list, near_cap, near_count);
-    return cudaGetLastError();
+    const double *far_k = m.far_k, *far_c = m.far_c, *src = m.src;
+    const uint8_t* col_class = m.col_class;
+    const uint32_t n = m.n;
+    const double wavruim = ph.wavruim, k2 = ph.k2, bre = ph.beta.re, bim = ph.beta.im;
+    auto launch = [=](cudaStream_t st, unsigned int g, unsigned int* ctr) -> cudaError_t {
+        far_kernel<NQ, BIMAG, MINB><<<g, TILE, 0, st>>>(far_k, far_c, col_class, src, n, row_begin, row_end, rpb, nchunks, total, ipb,
+                                                       wavruim, k2, cH, bre, bim, A, lda, near_list, near_cap, near_count, ctr);
+        return cudaGetLastError();
+    };
+    if (counter && relaunch) {
+        // helper launch for bemb200_matrix_boost_assembly: a full-occupancy grid pulling from the same counter
+        const unsigned int hg = total < 148u * 4u ? total : 148u * 4u;
+        relaunch->push_back([=](cudaStream_t st) { return launch(st, hg, counter); });
+    }
+    return launch(s, grid, counter);
 }
 
 template <int NQ>
 cudaError_t launch_far_t(const DeviceMesh& m, const Phys& ph, uint64_t row_begin, uint64_t row_end, cplx* A, uint64_t lda,
-                         uint2* near_list, unsigned int near_cap, unsigned int* near_count, int bg, cudaStream_t s) {
+                         uint2* near_list, unsigned int near_cap, unsigned int* near_count, int bg, unsigned int* work_counter,
+                         FarRelaunch* relaunch, cudaStream_t s) {
     const bool bimag = (ph.beta.re == 0.0);
     const int minb = env_int("BEMB200_FAR_MINB", 4);
 #define FAR_DISPATCH(B, M) \
-    return launch_far_v<NQ, B, M>(m, ph, row_begin, row_end, A, lda, near_list, near_cap, near_count, bg, s)
+    return launch_far_v<NQ, B, M>(m, ph, row_begin, row_end, A, lda, near_list, near_cap, near_count, bg, work_counter, relaunch, s)
     if (bimag) {
         if (minb == 2) FAR_DISPATCH(true, 2);
         if (minb == 3) FAR_DISPATCH(true, 3);
@@ -306,16 +335,18 @@ int far_kernel_launch_count(const DeviceMesh& m) { return (m.n_flat_tri ? 1 : 0)
 
 cudaError_t launch_far(const DeviceMesh& m, const Phys& ph, uint64_t row_begin, uint64_t row_end, cplx* A, uint64_t lda,
                        uint2* near_list, unsigned int near_cap, unsigned int* near_count, int background_blocks_per_sm,
-                       cudaStream_t s) {
+                       unsigned int* work_counters, FarRelaunch* relaunch, cudaStream_t s) {
     if (row_end <= row_begin) return cudaSuccess;
     cudaError_t e = upload_tables();
     if (e != cudaSuccess) return e;
     if (m.n_flat_tri) {
-        e = launch_far_t<NQ_TRI>(m, ph, row_begin, row_end, A, lda, near_list, near_cap, near_count, background_blocks_per_sm, s);
+        e = launch_far_t<NQ_TRI>(m, ph, row_begin, row_end, A, lda, near_list, near_cap, near_count, background_blocks_per_sm,
+                                 work_counters ? work_counters + 0 : nullptr, relaunch, s);
         if (e != cudaSuccess) return e;
     }
     if (m.n_flat_quad) {
-        e = launch_far_t<NQ_QUAD>(m, ph, row_begin, row_end, A, lda, near_list, near_cap, near_count, background_blocks_per_sm, s);
+        e = launch_far_t<NQ_QUAD>(m, ph, row_begin, row_end, A, lda, near_list, near_cap, near_count, background_blocks_per_sm,
+                                  work_counters ? work_counters + 1 : nullptr, relaunch, s);
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;

@@ -2,8 +2,10 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
-#include <string>
+#include <functional>
 #include <mutex>
+#include <string>
+#include <vector>
 
 #include "common.cuh"
 
@@ -51,9 +53,13 @@ struct AssemblyStats {
 
 // launchers (assembly_exact.cu / assembly_far.cu)
 cudaError_t launch_prep(const DeviceMesh& m, cudaStream_t s);
+// work_counters (may be NULL): two pre-zeroed device counters (Tri3 / Quad4 pass); with them a background launch pulls its
+// work items dynamically and `relaunch` receives one closure per pass that starts additional blocks on another stream
+// pulling from the same counter ("boost": finish the assembly at full speed once the solver has left the GPU).
+typedef std::vector<std::function<cudaError_t(cudaStream_t)>> FarRelaunch;
 cudaError_t launch_far(const DeviceMesh& m, const Phys& ph, uint64_t row_begin, uint64_t row_end, cplx* A, uint64_t lda,
                        uint2* near_list, unsigned int near_cap, unsigned int* near_count, int background_blocks_per_sm,
-                       cudaStream_t s);
+                       unsigned int* work_counters, FarRelaunch* relaunch, cudaStream_t s);
 cudaError_t launch_near_list(const DeviceMesh& m, const Phys& ph, uint64_t row_begin, cplx* A, uint64_t lda, cplx* rhs,
                              const uint2* near_list, unsigned int count, cudaStream_t s);
 cudaError_t launch_special(const DeviceMesh& m, const Phys& ph, uint64_t row_begin, uint64_t row_end, cplx* A,

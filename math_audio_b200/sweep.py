@@ -8,6 +8,7 @@ schedule changes.
 """
 from __future__ import annotations
 
+import os
 import threading
 from typing import Callable, List, Optional, Sequence, Tuple
 
@@ -33,6 +34,9 @@ class SweepDriver:
         self.buffers: List[Optional[bem.TbemSystem]] = [None, None]
         self.asm_stats: List[dict] = []
         self.sol_stats: List[dict] = []
+        self.boosts = 0
+        # join a still-running background assembly with full-speed blocks once the solve of the current frequency is done
+        self.boost = os.environ.get("BEMB200_SWEEP_BOOST", "1") != "0"
 
     def _assemble(self, slot: int, physics: PhysicsParams, beta: complex, mesh_for_stage: Optional[Mesh], err: list):
         try:
@@ -77,6 +81,10 @@ class SweepDriver:
                 out.append(solve(i, system, op))
                 self.sol_stats.append(system.matrix.solver_stats())
                 if t is not None:
+                    nxt = self.buffers[(i + 1) % 2]
+                    if self.boost and nxt is not None and t.is_alive():
+                        nxt.matrix.boost_assembly(self.ctx_solve)  # the solver has left the GPU: finish the assembly at full speed
+                        self.boosts += 1
                     t.join()
                 elif i + 1 < len(cases):
                     self._assemble((i + 1) % 2, cases[i + 1][0], cases[i + 1][1], mesh_arg, err)

@@ -396,6 +396,50 @@ def test_sweep_driver_equals_sequential(bem):
             assert (s0.iterations, s0.restarts) == (s1.iterations, s1.restarts) and (s0.x == s1.x).all()
 
 
+def test_boosted_background_assembly_same_bits(bem):
+    """bemb200_matrix_boost_assembly: a second launch of the far kernel on another stream joins a
+    background assembly (both pull work items from one device counter).  Whatever the split between
+    the polite grid and the helper blocks, the matrix must come out bit-identical to the foreground
+    assembly (every entry is written by exactly one work item)."""
+    import threading
+    import time
+
+    a = 0.1
+    mesh = generate_icosphere_mesh(a, 4)  # 5 120 elements: 40 column tiles, enough items for a persistent grid
+    ph = PhysicsParams.from_wave_number(3.0 / a)
+    beta = ph.burton_miller_beta_adaptive(a)[0]
+    ph2 = PhysicsParams.from_wave_number(0.7 / a)
+    ctx_a, ctx_b = bem.Context(0), bem.Context(0)
+    staged = bem.StagedMesh(mesh, ctx_a)
+    system = bem.build_tbem_system_with_beta(staged, ph, beta, ctx=ctx_a)
+    A0, rhs0 = system.matrix.rows(), system.rhs.copy()
+    near0 = system.matrix.assembly_stats()["near_pairs"]
+    for trial in range(3):
+        ctx_a.set_background(0)
+        bem.build_tbem_system_with_beta(staged, ph2, ph2.burton_miller_beta(), ctx=ctx_a, reuse=system)  # overwrite
+        ctx_a.set_background(1)
+        err = []
+
+        def work():
+            try:
+                bem.build_tbem_system_with_beta(staged, ph, beta, ctx=ctx_a, reuse=system, fetch_rhs=False)
+            except Exception as e:
+                err.append(e)
+
+        t = threading.Thread(target=work)
+        t.start()
+        time.sleep(0.002 * trial)
+        while t.is_alive():
+            system.matrix.boost_assembly(ctx_b)  # no-op until the far pass is in flight, and after the first boost
+            time.sleep(0.0005)
+        t.join()
+        assert not err, err
+        assert system.matrix.assembly_stats()["near_pairs"] == near0
+        assert (system.matrix.rows() == A0).all()
+        assert (system.matrix.rhs() == rhs0).all()
+    ctx_a.set_background(0)
+
+
 def test_gmres_preconditioned(bem, orc):
     """gmres_preconditioned (gmres.rs:282-585) with the identity and the Jacobi preconditioner on an
     assembled BEM matrix and on the reference's tridiagonal KAT."""
