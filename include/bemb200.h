@@ -198,6 +198,13 @@ int bemb200_lu_solve(const bemb200_matrix* m, const double* b, double* x_out, in
  * `converged` false on breakdown / stagnation / exhausted budget (the reference never errors). */
 int bemb200_bicgstab(const bemb200_matrix* m, const double* b, uint32_t max_iterations, double tolerance, double* x_out,
                      bemb200_gmres_info* info);
+/* cgs (math-solvers/src/iterative/cgs.rs:46-155), reached through solve_cgs / solve_with_ilu /
+ * solve_tbem_with_ilu (math-bem/src/core/solver/fmm_interface.rs:360-366,389-447; the "ILU"
+ * variants run this unpreconditioned solver on the dense TBEM matrix): x0 = 0, two operator
+ * applications per iteration, breakdown thresholds 1e-30 (sigma, and the previous rho as in
+ * cgs.rs:122).  info->restarts = 0; `converged` false on breakdown / exhausted budget. */
+int bemb200_cgs(const bemb200_matrix* m, const double* b, uint32_t max_iterations, double tolerance, double* x_out,
+                bemb200_gmres_info* info);
 /* Multi-RHS solve (BASELINE config 5): `nrhs` (<= 32) independent gmres() solves -- the reference
  * would loop `gmres(operator, b_s, config)` over the right-hand sides -- advanced in lockstep so
  * that they share ONE FP64 tensor-core block matvec per iteration (A is streamed once for all

@@ -12,6 +12,7 @@
 //   math-solvers/src/iterative/gmres.rs:16-585   GmresConfig, GmresSolution, gmres, gmres_with_guess,
 //                                                gmres_preconditioned{,_with_guess}
 //   math-solvers/src/iterative/bicgstab.rs:19-215  BiCgstabConfig, BiCgstabSolution, bicgstab
+//   math-solvers/src/iterative/cgs.rs:12-155       CgsConfig, CgsSolution, cgs (+ solve_cgs / solve_with_ilu wrappers)
 //   math-solvers/src/direct/lu.rs:15-161         LuError, lu_solve
 //   math-bem/src/room_acoustics/solver.rs:412-748  RoomMesh, Source, build_bem_matrix_parallel, solve_bem_system,
 //                                                calculate_incident_field_derivative_parallel, calculate_field_pressure_bem_parallel
@@ -354,6 +355,34 @@ inline BiCgstabSolution bicgstab(const DenseOperator& op, const std::vector<Comp
     s.iterations = info.iterations; s.residual = info.residual; s.converged = info.converged != 0;
     return s;
 }
+
+// ---- CGS (solve_cgs / solve_with_ilu / solve_tbem_with_ilu, fmm_interface.rs:360-366,389-447) -----------------
+struct CgsConfig {  // cgs.rs:12-30
+    std::size_t max_iterations = 1000;
+    double tolerance = 1e-6;
+    std::size_t print_interval = 0;
+};
+struct CgsSolution {  // cgs.rs:33-43
+    std::vector<Complex64> x;
+    std::size_t iterations = 0;
+    double residual = 0.0;
+    bool converged = false;
+};
+inline CgsSolution cgs(const DenseOperator& op, const std::vector<Complex64>& b, const CgsConfig& config) {  // cgs.rs:46
+    if (b.size() != op.num_rows()) throw std::invalid_argument("cgs: vector length must match the operator");
+    CgsSolution s;
+    s.x.resize(b.size());
+    bemb200_gmres_info info{};
+    check(bemb200_cgs(op.handle(), reinterpret_cast<const double*>(b.data()), static_cast<uint32_t>(config.max_iterations),
+                      config.tolerance, reinterpret_cast<double*>(s.x.data()), &info),
+          op.context().handle());
+    s.iterations = info.iterations; s.residual = info.residual; s.converged = info.converged != 0;
+    return s;
+}
+inline CgsSolution solve_cgs(const DenseOperator& op, const std::vector<Complex64>& b, const CgsConfig& c) { return cgs(op, b, c); }  // fmm_interface.rs:360
+// the reference's "ILU" wrappers run unpreconditioned CGS on the dense matrix (fmm_interface.rs:389-417, 441-447)
+inline CgsSolution solve_with_ilu(const DenseOperator& op, const std::vector<Complex64>& b, const CgsConfig& c) { return cgs(op, b, c); }
+inline CgsSolution solve_tbem_with_ilu(const DenseOperator& op, const std::vector<Complex64>& b, const CgsConfig& c) { return cgs(op, b, c); }
 
 struct LuError : std::runtime_error {  // lu.rs:15-21
     enum Kind { SingularMatrix, DimensionMismatch } kind;

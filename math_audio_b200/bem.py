@@ -534,6 +534,37 @@ def bicgstab(operator: DenseOperator, b: np.ndarray, config: BiCgstabConfig) -> 
     return BiCgstabSolution(x, int(info.iterations), float(info.residual), bool(info.converged))
 
 
+@dataclass
+class CgsConfig:
+    """math-solvers/src/iterative/cgs.rs:12-30."""
+
+    max_iterations: int = 1000
+    tolerance: float = 1e-6
+    print_interval: int = 0
+
+
+@dataclass
+class CgsSolution:
+    """cgs.rs:33-43."""
+
+    x: np.ndarray
+    iterations: int
+    residual: float
+    converged: bool
+
+
+def cgs(operator: DenseOperator, b: np.ndarray, config: CgsConfig) -> CgsSolution:
+    """cgs.rs:46-155 on the device (x0 = 0; two ZGEMVs per iteration, fused vector kernels)."""
+    b = np.ascontiguousarray(b, dtype=np.complex128)
+    if b.shape != (operator.num_rows(),):
+        raise ValueError("b does not match the operator")
+    x = np.empty_like(b)
+    info = _capi.CGmresInfo()
+    _capi.check(_capi.lib().bemb200_cgs(operator.matrix._h, _capi.ptr(b), int(config.max_iterations), float(config.tolerance),
+                                        _capi.ptr(x), C.byref(info)), operator.matrix.ctx._h)
+    return CgsSolution(x, int(info.iterations), float(info.residual), bool(info.converged))
+
+
 class LuError(RuntimeError):
     """math-solvers/src/direct/lu.rs:15-21."""
 
@@ -604,3 +635,24 @@ def apply_block(operator: DenseOperator, x_all: np.ndarray):
 
 def solve_gmres(operator: DenseOperator, b: np.ndarray, config: GmresConfig) -> GmresSolution:  # fmm_interface.rs:378-384
     return gmres(operator, b, config)
+
+
+def solve_cgs(operator: DenseOperator, b: np.ndarray, config: CgsConfig) -> CgsSolution:  # fmm_interface.rs:360-366
+    return cgs(operator, b, config)
+
+
+def solve_bicgstab(operator: DenseOperator, b: np.ndarray, config: BiCgstabConfig) -> BiCgstabSolution:  # fmm_interface.rs:369-375
+    return bicgstab(operator, b, config)
+
+
+def solve_with_ilu(matrix, b: np.ndarray, config: CgsConfig, ctx: Optional[Context] = None) -> CgsSolution:
+    """fmm_interface.rs:389-417: despite its name the reference builds an ILU factorisation it never
+    uses and runs **unpreconditioned** CGS on the dense matrix (it prints a warning saying so).  The
+    result is therefore that of `cgs`; the unused factorisation is not reproduced.  ``matrix``: a
+    DenseOperator / TbemSystem (device resident) or a host array (uploaded, as `DenseOperator::new`)."""
+    op = matrix if isinstance(matrix, DenseOperator) else DenseOperator(matrix, ctx=ctx)
+    return cgs(op, b, config)
+
+
+def solve_tbem_with_ilu(matrix, b: np.ndarray, config: CgsConfig, ctx: Optional[Context] = None) -> CgsSolution:  # fmm_interface.rs:441-447
+    return solve_with_ilu(matrix, b, config, ctx=ctx)

@@ -573,6 +573,90 @@ static int bicgstab_core(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t max
     return BEMB200_OK;
 }
 
+// ---- cgs (math-solvers/src/iterative/cgs.rs:46-155) with device vectors ------------------------
+// Workspace rows V[0..7] hold r, r0, p, u, q, v, u+q, w; two A-products per iteration; three fused
+// vector kernels; 2 scalar read-backs per iteration drive the reference's control flow on the host
+// (including its test of the OLD rho after rho_new has been formed, cgs.rs:122).
+static int cgs_core(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t max_iterations, double tol, bemb200_gmres_info* info) {
+    bemb200_ctx* ctx = m->ctx;
+    GmresWorkspace* ws = m->ws;
+    const uint64_t n = m->n_rows;
+    cudaStream_t s = ctx->stream;
+    cplx* r = ws->V;
+    cplx* r0 = ws->V + 1 * ws->npad;
+    cplx* p = ws->V + 2 * ws->npad;
+    cplx* u = ws->V + 3 * ws->npad;
+    cplx* q = ws->V + 4 * ws->npad;
+    cplx* v = ws->V + 5 * ws->npad;
+    cplx* uq = ws->V + 6 * ws->npad;
+    cplx* w = ws->V + 7 * ws->npad;
+    cplx* dsc = ws->hcol_d;
+    cplx* hsc = ws->hcol_h;
+    auto fetch = [&](int cnt) -> int {
+        BEMB_CUDA(ctx, cudaMemcpyAsync(hsc, dsc, cnt * sizeof(cplx), cudaMemcpyDeviceToHost, s));
+        BEMB_CUDA(ctx, cudaStreamSynchronize(s));
+        return BEMB200_OK;
+    };
+    BEMB_CUDA(ctx, cudaMemsetAsync(x, 0, n * sizeof(cplx), s));
+    // r = r0 = p = u = b; (b, b) gives ||b|| and the first rho = (r0, r)
+    for (cplx* dst : {r, r0, p, u}) {
+        BEMB_CUDA(ctx, cudaMemsetAsync(dst, 0, ws->npad * sizeof(cplx), s));
+        BEMB_CUDA(ctx, cudaMemcpyAsync(dst, b, n * sizeof(cplx), cudaMemcpyDeviceToDevice, s));
+    }
+    BEMB_CUDA(ctx, cudaMemsetAsync(uq, 0, ws->npad * sizeof(cplx), s));
+    BEMB_CUDA(ctx, launch_bicg_dot(b, b, n, dsc, s));
+    m->last_launches += 1;
+    int rc = fetch(1);
+    if (rc != BEMB200_OK) return rc;
+    const double b_norm = std::sqrt(hsc[0].re);
+    if (b_norm < 1e-15) {
+        *info = bemb200_gmres_info{0, 0, 0.0, 1};
+        return BEMB200_OK;
+    }
+    cplx rho = hsc[0];
+    double r_norm = b_norm;
+    for (uint32_t iter = 0; iter < max_iterations; ++iter) {
+        rc = matvec(m, p, v, true);
+        if (rc != BEMB200_OK) return rc;
+        BEMB_CUDA(ctx, launch_bicg_dot(r0, v, n, dsc, s));
+        m->last_launches += 1;
+        rc = fetch(1);
+        if (rc != BEMB200_OK) return rc;
+        accumulate_matvec_time(m);
+        const cplx sigma = hsc[0];
+        if (tnorm(sigma) < 1e-30) {
+            *info = bemb200_gmres_info{iter, 0, r_norm / b_norm, 0};
+            return BEMB200_OK;
+        }
+        const cplx alpha = cdiv(rho, sigma);
+        BEMB_CUDA(ctx, launch_cgs_q(u, v, alpha, q, uq, n, s));
+        rc = matvec(m, uq, w, true);
+        if (rc != BEMB200_OK) return rc;
+        BEMB_CUDA(ctx, launch_cgs_update(x, uq, w, r, r0, alpha, n, dsc, s));
+        m->last_launches += 2;
+        rc = fetch(2);
+        if (rc != BEMB200_OK) return rc;
+        accumulate_matvec_time(m);
+        r_norm = std::sqrt(hsc[0].re);
+        const cplx rho_new = hsc[1];
+        const double rel = r_norm / b_norm;
+        if (rel < tol) {
+            *info = bemb200_gmres_info{(uint64_t)iter + 1, 0, rel, 1};
+            return BEMB200_OK;
+        }
+        if (tnorm(rho) < 1e-30) {
+            *info = bemb200_gmres_info{(uint64_t)iter + 1, 0, rel, 0};
+            return BEMB200_OK;
+        }
+        const cplx beta = cdiv(rho_new, rho);
+        rho = rho_new;
+        BEMB_CUDA(ctx, launch_cgs_p(r, q, beta, u, p, n, s));
+        m->last_launches += 1;
+    }
+    *info = bemb200_gmres_info{max_iterations, 0, r_norm / b_norm, 0};
+    return BEMB200_OK;
+}
+
 // the solver needs the whole operator: every row owned by exactly one rank, canonical split
 static int check_partition(bemb200_matrix* m) {
     bemb200_ctx* ctx = m->ctx;
@@ -672,6 +756,29 @@ int bemb200_bicgstab(const bemb200_matrix* cm, const double* b, uint32_t max_ite
     const size_t nb = m->n_rows * sizeof(cplx);
     BEMB_CUDA(ctx, cudaMemcpyAsync(ws->bin, b, nb, cudaMemcpyHostToDevice, ctx->stream));
     rc = bicgstab_core(m, ws->bin, ws->xout, max_iterations, tolerance, info);
+    if (rc != BEMB200_OK) return rc;
+    BEMB_CUDA(ctx, cudaMemcpyAsync(x_out, ws->xout, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    BEMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BEMB200_OK;
+}
+
+int bemb200_cgs(const bemb200_matrix* cm, const double* b, uint32_t max_iterations, double tolerance, double* x_out,
+                bemb200_gmres_info* info) {
+    bemb200_matrix* m = const_cast<bemb200_matrix*>(cm);
+    if (!m || !b || !x_out || !info) return set_error(nullptr, BEMB200_EINVAL, "NULL argument");
+    bemb200_ctx* ctx = m->ctx;
+    if (m->n_rows != m->n_cols) return set_error(ctx, BEMB200_EINVAL, "cgs needs a square operator");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    BEMB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = check_partition(m);
+    if (rc != BEMB200_OK) return rc;
+    rc = ensure_workspace(m, 8);
+    if (rc != BEMB200_OK) return rc;
+    reset_stats(m);
+    GmresWorkspace* ws = m->ws;
+    const size_t nb = m->n_rows * sizeof(cplx);
+    BEMB_CUDA(ctx, cudaMemcpyAsync(ws->bin, b, nb, cudaMemcpyHostToDevice, ctx->stream));
+    rc = cgs_core(m, ws->bin, ws->xout, max_iterations, tolerance, info);
     if (rc != BEMB200_OK) return rc;
     BEMB_CUDA(ctx, cudaMemcpyAsync(x_out, ws->xout, nb, cudaMemcpyDeviceToHost, ctx->stream));
     BEMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -866,6 +866,57 @@ __global__ void bicg_axpy_kernel(cplx* __restrict__ x, const cplx* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------
+// CGS vector kernels (math-solvers/src/iterative/cgs.rs:71-140): two element-wise updates and one
+// update fused with the two reductions that follow it (same fixed-order cluster reduction as above).
+// ------------------------------------------------------------------------------------------
+// q = u - alpha v ; uq = u + q       (cgs.rs:89-93)
+__global__ void cgs_q_kernel(const cplx* __restrict__ u, const cplx* __restrict__ v, cplx alpha, cplx* __restrict__ q,
+                             cplx* __restrict__ uq, uint64_t n) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const cplx uu = u[k];
+    const cplx qq = uu - v[k] * alpha;
+    q[k] = qq;
+    uq[k] = uu + qq;
+}
+
+// x += alpha uq ; r -= alpha w ; out[0].re = ||r||^2 ; out[1] = (r0, r)      (cgs.rs:96-102, 121)
+__global__ void __launch_bounds__(VEC_THREADS)
+cgs_update_kernel(cplx* __restrict__ x, const cplx* __restrict__ uq, const cplx* __restrict__ w, cplx* __restrict__ r,
+                  const cplx* __restrict__ r0, cplx alpha, uint64_t n, uint64_t S, cplx* __restrict__ out) {
+    __shared__ ClusterShared sh;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned me = cluster.block_rank();
+    const uint64_t begin = (uint64_t)me * S, end = begin + S < n ? begin + S : n;
+    cplx a0 = C(0, 0), a1 = C(0, 0);
+    for (uint64_t k = begin + threadIdx.x; k < end; k += blockDim.x) {
+        x[k] = x[k] + uq[k] * alpha;
+        const cplx rr = r[k] - w[k] * alpha;
+        r[k] = rr;
+        const cplx q = r0[k];
+        a0.re = fma(rr.re, rr.re, fma(rr.im, rr.im, a0.re));
+        a1.re = fma(q.re, rr.re, fma(q.im, rr.im, a1.re));
+        a1.im = fma(q.re, rr.im, fma(-q.im, rr.re, a1.im));
+    }
+    const cplx t0 = cluster_allreduce(a0, sh, 0);
+    const cplx t1 = cluster_allreduce(a1, sh, 1);
+    if (me == 0 && threadIdx.x == 0) { out[0] = t0; out[1] = t1; }
+    cluster.sync();
+}
+
+// u = r + beta q ; p = u + beta (q + beta p)      (cgs.rs:134-139)
+__global__ void cgs_p_kernel(const cplx* __restrict__ r, const cplx* __restrict__ q, cplx beta, cplx* __restrict__ u,
+                             cplx* __restrict__ p, uint64_t n) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const cplx qq = q[k];
+    const cplx uu = r[k] + qq * beta;
+    u[k] = uu;
+    const cplx qp = qq + p[k] * beta;
+    p[k] = uu + qp * beta;
+}
+
+// ------------------------------------------------------------------------------------------
 // K6: block matvec Y = A X for S = 8*NT right-hand sides (multi-RHS scattering, BASELINE config 5).
 // A is read ONCE for all S columns, so the op is a genuine dense contraction (8 N^2 S flops on
 // 16 N^2 bytes): FP64 tensor cores, mma.sync.m8n8k4.f64 (tcgen05 has no f64 kind).  Complex
@@ -1460,6 +1511,21 @@ cudaError_t launch_bicg_update(cplx* x, const cplx* p, const cplx* sv, const cpl
 }
 cudaError_t launch_bicg_axpy(cplx* x, const cplx* p, cplx alpha, uint64_t n, cudaStream_t s) {
     bicg_axpy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, p, alpha, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cgs_q(const cplx* u, const cplx* v, cplx alpha, cplx* q, cplx* uq, uint64_t n, cudaStream_t s) {
+    cgs_q_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(u, v, alpha, q, uq, n);
+    return cudaGetLastError();
+}
+cudaError_t launch_cgs_update(cplx* x, const cplx* uq, const cplx* w, cplx* r, const cplx* r0, cplx alpha, uint64_t n, cplx* out,
+                              cudaStream_t s) {
+    uint64_t S;
+    const int cl = bicg_cluster(n, &S);
+    return launch_cluster(cgs_update_kernel, cl, VEC_THREADS, 0, s, x, uq, w, r, r0, alpha, n, S, out);
+}
+cudaError_t launch_cgs_p(const cplx* r, const cplx* q, cplx beta, cplx* u, cplx* p, uint64_t n, cudaStream_t s) {
+    cgs_p_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(r, q, beta, u, p, n);
     return cudaGetLastError();
 }
 

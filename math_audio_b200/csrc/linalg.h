@@ -37,6 +37,11 @@ cudaError_t launch_bicg_tt(const cplx* t, const cplx* sv, uint64_t n, cplx* out,
 cudaError_t launch_bicg_update(cplx* x, const cplx* p, const cplx* sv, const cplx* t, cplx* r, const cplx* r0, cplx alpha, cplx omega,
                                uint64_t n, cplx* out, cudaStream_t s);
 cudaError_t launch_bicg_axpy(cplx* x, const cplx* p, cplx alpha, uint64_t n, cudaStream_t s);
+// CGS (cgs.rs:71-140)
+cudaError_t launch_cgs_q(const cplx* u, const cplx* v, cplx alpha, cplx* q, cplx* uq, uint64_t n, cudaStream_t s);
+cudaError_t launch_cgs_update(cplx* x, const cplx* uq, const cplx* w, cplx* r, const cplx* r0, cplx alpha, uint64_t n, cplx* out,
+                              cudaStream_t s);
+cudaError_t launch_cgs_p(const cplx* r, const cplx* q, cplx beta, cplx* u, cplx* p, uint64_t n, cudaStream_t s);
 cudaError_t launch_zgemm_block(const cplx* A, uint64_t lda, uint64_t nrows, uint64_t ncols, const cplx* X, cplx* Y, int nrhs,
                                cudaStream_t s);
 cudaError_t launch_mgs_batched(int nrhs, const cplx* Vall, uint64_t ldv, uint64_t vstride, const cplx* Yblk, int j, uint64_t n,

@@ -1091,6 +1091,38 @@ void orc_bicgstab(const double* A, uint64_t n, const double* b_in, uint32_t max_
     *info = {max_iterations, 0, vector_norm(r.data(), n) / b_norm, 0};
 }
 
+// ---- cgs: math-solvers/src/iterative/cgs.rs:46-155 on a dense row-major matrix ----
+void orc_cgs(const double* A, uint64_t n, const double* b_in, uint32_t max_iterations, double tolerance, double* x_out,
+             orc_gmres_info* info, int nthreads) {
+    const cplx* b = (const cplx*)b_in;
+    cplx* x = (cplx*)x_out;
+    for (uint64_t i = 0; i < n; ++i) x[i] = C(0, 0);
+    const double b_norm = vector_norm(b, n);
+    if (b_norm < 1e-15) { *info = {0, 0, 0.0, 1}; return; }
+    std::vector<cplx> r(b, b + n), r0(b, b + n), p(b, b + n), u(b, b + n), v(n), q(n), uq(n), w(n);
+    cplx rho = inner_product(r0.data(), r.data(), n);
+    for (uint32_t iter = 0; iter < max_iterations; ++iter) {
+        orc_zgemv(A, n, n, (const double*)p.data(), (double*)v.data(), nthreads);
+        const cplx sigma = inner_product(r0.data(), v.data(), n);
+        if (cnorm(sigma) < 1e-30) { *info = {iter, 0, vector_norm(r.data(), n) / b_norm, 0}; return; }
+        const cplx alpha = rho / sigma;
+        for (uint64_t i = 0; i < n; ++i) q[i] = u[i] - v[i] * alpha;
+        for (uint64_t i = 0; i < n; ++i) uq[i] = u[i] + q[i];
+        orc_zgemv(A, n, n, (const double*)uq.data(), (double*)w.data(), nthreads);
+        for (uint64_t i = 0; i < n; ++i) x[i] = x[i] + uq[i] * alpha;
+        for (uint64_t i = 0; i < n; ++i) r[i] = r[i] - w[i] * alpha;
+        const double rel = vector_norm(r.data(), n) / b_norm;
+        if (rel < tolerance) { *info = {(uint64_t)iter + 1, 0, rel, 1}; return; }
+        const cplx rho_new = inner_product(r0.data(), r.data(), n);
+        if (cnorm(rho) < 1e-30) { *info = {(uint64_t)iter + 1, 0, rel, 0}; return; }  // the OLD rho, as cgs.rs:122
+        const cplx beta = rho_new / rho;
+        rho = rho_new;
+        for (uint64_t i = 0; i < n; ++i) u[i] = r[i] + q[i] * beta;
+        for (uint64_t i = 0; i < n; ++i) p[i] = u[i] + (q[i] + p[i] * beta) * beta;
+    }
+    *info = {max_iterations, 0, vector_norm(r.data(), n) / b_norm, 0};
+}
+
 // ---- lu_solve: math-solvers/src/direct/lu.rs:136-161.  The default build (feature "native" =>
 // `ndarray-linalg`, math-solvers/Cargo.toml:48-57) calls LAPACK zgesv (ndarray-linalg 0.18 / lax 0.18 /
 // OpenBLAS, not vendored): partial-pivoting LU + two triangular solves, restated here with the elimination

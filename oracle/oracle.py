@@ -251,6 +251,18 @@ def bicgstab(A, b, max_iterations=1000, tolerance=1e-6, nthreads=0):
     return x, dict(iterations=int(info.iterations), residual=float(info.residual), converged=bool(info.converged))
 
 
+def cgs(A, b, max_iterations=1000, tolerance=1e-6, nthreads=0):
+    """math-solvers/src/iterative/cgs.rs:46-155 on a dense row-major matrix -> (x, info dict)."""
+    A = np.ascontiguousarray(A, dtype=np.complex128)
+    b = np.ascontiguousarray(b, dtype=np.complex128)
+    n = b.shape[0]
+    x = np.zeros(n, dtype=np.complex128)
+    info = GmresInfo()
+    lib().orc_cgs(_p(A), C.c_uint64(n), _p(b), C.c_uint32(max_iterations), C.c_double(tolerance), _p(x), C.byref(info),
+                  C.c_int(nthreads))
+    return x, dict(iterations=int(info.iterations), residual=float(info.residual), converged=bool(info.converged))
+
+
 def lu_solve(A, b):
     """math-solvers/src/direct/lu.rs:136-161 -> x; raises np.linalg.LinAlgError for LuError::SingularMatrix."""
     A = np.ascontiguousarray(A, dtype=np.complex128)

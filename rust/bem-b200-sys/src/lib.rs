@@ -7,7 +7,7 @@
 use std::os::raw::{c_char, c_double, c_int, c_void};
 
 use math_audio_bem::core::types::{BoundaryCondition, Element, ElementType, PhysicsParams};
-use math_audio_solvers::iterative::{GmresConfig, GmresSolution};
+use math_audio_solvers::iterative::{BiCgstabConfig, BiCgstabSolution, CgsConfig, CgsSolution, GmresConfig, GmresSolution};
 use math_audio_solvers::traits::LinearOperator;
 use ndarray::{Array1, Array2};
 use num_complex::Complex64;
@@ -60,6 +60,8 @@ extern "C" {
     pub fn bemb200_apply_transpose(m: *const bemb200_matrix, x: *const f64, y: *mut f64) -> c_int;
     pub fn bemb200_bicgstab(m: *const bemb200_matrix, b: *const f64, max_iterations: u32, tolerance: f64, x_out: *mut f64,
                             info: *mut bemb200_gmres_info) -> c_int;
+    pub fn bemb200_cgs(m: *const bemb200_matrix, b: *const f64, max_iterations: u32, tolerance: f64, x_out: *mut f64,
+                       info: *mut bemb200_gmres_info) -> c_int;
     pub fn bemb200_lu_solve(m: *const bemb200_matrix, b: *const f64, x_out: *mut f64, overwrite_matrix: c_int,
                             factor_ms: *mut f64) -> c_int;
     pub fn bemb200_compute_rcs(sm: *const bemb200_staged_mesh, phys: *const bemb200_physics, n_dirs: u32, dirs: *const f64,
@@ -160,6 +162,35 @@ impl GpuDenseOperator {
         assert_eq!(rc, 0, "libbemb200: {}", last_error(std::ptr::null()));
         GmresSolution { x, iterations: info.iterations as usize, restarts: info.restarts as usize,
                         residual: info.residual, converged: info.converged != 0 }
+    }
+    /// `bicgstab(operator, b, config)` (bicgstab.rs:53), the solver of `BemSolver::solve_dense_system`.
+    pub fn bicgstab(&self, b: &Array1<Complex64>, config: &BiCgstabConfig<f64>) -> BiCgstabSolution<Complex64> {
+        assert_eq!(b.len(), self.num_rows(), "Vector lengths must match");
+        let mut x = Array1::<Complex64>::zeros(b.len());
+        let mut info = bemb200_gmres_info::default();
+        let rc = unsafe { bemb200_bicgstab(self.0, b.as_ptr() as *const f64, config.max_iterations as u32, config.tolerance,
+                                           x.as_mut_ptr() as *mut f64, &mut info) };
+        assert_eq!(rc, 0, "libbemb200: {}", last_error(std::ptr::null()));
+        BiCgstabSolution { x, iterations: info.iterations as usize, residual: info.residual, converged: info.converged != 0 }
+    }
+    /// `cgs(operator, b, config)` (cgs.rs:46); what `solve_cgs` / `solve_with_ilu` / `solve_tbem_with_ilu`
+    /// (fmm_interface.rs:360-366,389-447) run on a dense matrix.
+    pub fn cgs(&self, b: &Array1<Complex64>, config: &CgsConfig<f64>) -> CgsSolution<Complex64> {
+        assert_eq!(b.len(), self.num_rows(), "Vector lengths must match");
+        let mut x = Array1::<Complex64>::zeros(b.len());
+        let mut info = bemb200_gmres_info::default();
+        let rc = unsafe { bemb200_cgs(self.0, b.as_ptr() as *const f64, config.max_iterations as u32, config.tolerance,
+                                      x.as_mut_ptr() as *mut f64, &mut info) };
+        assert_eq!(rc, 0, "libbemb200: {}", last_error(std::ptr::null()));
+        CgsSolution { x, iterations: info.iterations as usize, residual: info.residual, converged: info.converged != 0 }
+    }
+    /// `lu_solve(&a, &b)` (direct/lu.rs:136): cuSOLVER zgetrf + zgetrs on a copy; `Err` = `LuError::SingularMatrix`.
+    pub fn lu_solve(&self, b: &Array1<Complex64>) -> Result<Array1<Complex64>, String> {
+        if b.len() != self.num_rows() { return Err("Matrix dimensions mismatch".into()); }
+        let mut x = Array1::<Complex64>::zeros(b.len());
+        let rc = unsafe { bemb200_lu_solve(self.0, b.as_ptr() as *const f64, x.as_mut_ptr() as *mut f64, 0, std::ptr::null_mut()) };
+        if rc != 0 { return Err(last_error(std::ptr::null())); }
+        Ok(x)
     }
 }
 

@@ -1,10 +1,10 @@
 #!/usr/bin/env python3
-"""The three dense solvers behind BemSolver::solve_dense_system / solve_gmres on one assembled
+"""The dense solvers behind BemSolver::solve_dense_system / solve_gmres / solve_cgs on one assembled
 system (icosphere(5), 20 480 elements, ka = 2, beta = 4 i/k as BemSolver's default beta_scale):
 
-    GMRES(50) tol 1e-10 (gmres.rs)  |  BiCGSTAB tol 1e-10 (bicgstab.rs)  |  LU (lu.rs -> cuSOLVER zgetrf/zgetrs)
+    GMRES(50) tol 1e-10 (gmres.rs)  |  BiCGSTAB tol 1e-10 (bicgstab.rs)  |  CGS tol 1e-10 (cgs.rs)  |  LU (lu.rs -> cuSOLVER zgetrf/zgetrs)
 
-Reports device/wall times, matvec counts, residuals and mutual agreement of the three solutions.
+Reports device/wall times, matvec counts, residuals and mutual agreement of the solutions.
 Writes gpurun_out/solvers_20480.json.
 """
 import json
@@ -52,13 +52,18 @@ def main():
     sb = system.matrix.solver_stats()
     out["bicgstab"] = dict(seconds=tb, iterations=bc.iterations, matvecs=sb["matvecs"], residual=bc.residual, converged=bc.converged,
                            matvec_gbs=(16 * n * n + 32 * n) * sb["matvecs"] / (sb["matvec_ms"] * 1e-3) / 1e9)
+    cg, tc = timed(lambda: bem.cgs(op, b, bem.CgsConfig(1000, 1e-10, 0)))
+    sc = system.matrix.solver_stats()
+    out["cgs"] = dict(seconds=tc, iterations=cg.iterations, matvecs=sc["matvecs"], residual=cg.residual, converged=cg.converged,
+                      matvec_gbs=(16 * n * n + 32 * n) * sc["matvecs"] / (sc["matvec_ms"] * 1e-3) / 1e9)
     st = {}
     x_lu, tl = timed(lambda: bem.lu_solve(system, b, stats=st))
     flops = 8.0 / 3.0 * n ** 3
     out["lu"] = dict(seconds=tl, factor_ms=st["factor_ms"], factor_tflops=flops / (st["factor_ms"] * 1e-3) / 1e12,
                      residual=float(np.linalg.norm(op.apply(x_lu) - b) / np.linalg.norm(b)))
     out["agreement"] = dict(gmres_vs_lu=float(np.linalg.norm(g.x - x_lu) / np.linalg.norm(x_lu)),
-                            bicgstab_vs_lu=float(np.linalg.norm(bc.x - x_lu) / np.linalg.norm(x_lu)))
+                            bicgstab_vs_lu=float(np.linalg.norm(bc.x - x_lu) / np.linalg.norm(x_lu)),
+                            cgs_vs_lu=float(np.linalg.norm(cg.x - x_lu) / np.linalg.norm(x_lu)))
     (ROOT / "gpurun_out").mkdir(exist_ok=True)
     (ROOT / "gpurun_out" / f"solvers_{n}.json").write_text(json.dumps(out, indent=1))
     print(json.dumps(out))

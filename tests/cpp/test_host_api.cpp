@@ -4,6 +4,7 @@
 //   math-solvers/src/iterative/gmres.rs:631-705          test_gmres_simple / test_gmres_identity
 //   math-bem/tests/test_fmm_validation.rs:537-700        test_gmres_with_operator / _restart_behavior
 //   math-solvers/src/iterative/bicgstab.rs:196-219       test_bicgstab_simple
+//   math-solvers/src/iterative/cgs.rs:164-185            test_cgs_simple
 //   math-solvers/src/direct/lu.rs:178-219                test_lu_solve_complex / _identity / _singular
 //   math-bem/src/room_acoustics/solver.rs:1155-1170      test_greens_function / test_pressure_to_spl (room path smoke)
 // plus entry / solution parity against the CPU oracle (linked: oracle/_build/libbem_oracle.so) on a
@@ -27,6 +28,8 @@ struct orc_mesh {
 struct orc_gmres_info { uint64_t iterations, restarts; double residual; int32_t converged; };
 long orc_assemble(const orc_mesh* m, double k, double harmonic, double tau, double beta_re, double beta_im, uint64_t row_begin,
                   uint64_t row_end, double* A_out, double* rhs_out, int nthreads);
+void orc_cgs(const double* A, uint64_t n, const double* b, uint32_t max_iterations, double tolerance, double* x_out,
+             orc_gmres_info* info, int nthreads);
 void orc_bicgstab(const double* A, uint64_t n, const double* b, uint32_t max_iterations, double tolerance, double* x_out,
                   orc_gmres_info* info, int nthreads);
 int orc_lu_solve(const double* A, uint64_t n, const double* b, double* x_out);
@@ -245,6 +248,19 @@ int main() {
         CHECK(sb.converged && info.converged && sb.iterations == info.iterations);
         CHECK(std::sqrt(e1 / den) < 1e-8 && std::sqrt(e2 / den) < 1e-10);
         std::printf("bicgstab it=%zu dx=%.2e  lu dx=%.2e\n", sb.iterations, std::sqrt(e1 / den), std::sqrt(e2 / den));
+        // cgs.rs:164-185 test_cgs_simple, then the same 300 x 300 system against the oracle's cgs
+        CgsSolution sc0 = cgs(op, b, CgsConfig{100, 1e-10, 0});
+        CHECK(sc0.converged);
+        std::vector<Complex64> axc = op.apply(sc0.x);
+        CHECK(std::sqrt(std::norm(axc[0] - b[0]) + std::norm(axc[1] - b[1])) < 1e-8);
+        CgsSolution sc = solve_tbem_with_ilu(opn, bb, CgsConfig{500, 1e-11, 0});
+        orc_gmres_info ic{};
+        orc_cgs(reinterpret_cast<const double*>(A.data()), n, reinterpret_cast<const double*>(bb.data()), 500, 1e-11,
+                reinterpret_cast<double*>(xo.data()), &ic, 0);
+        double e3 = 0;
+        for (std::size_t i = 0; i < n; ++i) e3 += std::norm(sc.x[i] - xo[i]);
+        CHECK(sc.converged && ic.converged && sc.iterations == ic.iterations && std::sqrt(e3 / den) < 1e-8);
+        std::printf("cgs it=%zu dx=%.2e\n", sc.iterations, std::sqrt(e3 / den));
     }
     {  // room path: 2 x 2 x 2 m room at 1 element/m (geometry.rs:773-779), one omnidirectional source
         RoomMesh mesh;

@@ -39,6 +39,93 @@ def test_bicgstab_kats_and_dense(bem, orc):
         assert not short.converged and short.iterations == 3
 
 
+def test_cgs_kats_and_dense(bem, orc):
+    """cgs.rs:46-155 through bemb200_cgs, and the fmm_interface.rs wrappers that reach it
+    (solve_cgs :360, solve_with_ilu :389 -- which runs unpreconditioned CGS -- solve_tbem_with_ilu :441)."""
+    A = np.array([[4, 1], [1, 3]], dtype=np.complex128)
+    b = np.array([1, 2], dtype=np.complex128)
+    sol = bem.cgs(bem.DenseOperator(A), b, bem.CgsConfig(100, 1e-10, 0))                 # cgs.rs:164-185
+    assert sol.converged and np.linalg.norm(A @ sol.x - b) < 1e-8
+    z = bem.cgs(bem.DenseOperator(A), np.zeros(2, dtype=complex), bem.CgsConfig())
+    assert z.converged and z.iterations == 0 and z.residual == 0.0 and not z.x.any()
+    rng = np.random.default_rng(5)
+    for n in (40, 777, 5000):
+        A = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))) / np.sqrt(n) + 3 * np.eye(n)
+        b = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        op = bem.DenseOperator(A)
+        sol = bem.solve_cgs(op, b, bem.CgsConfig(500, 1e-11, 0))
+        xo, io = orc.cgs(A, b, max_iterations=500, tolerance=1e-11)
+        assert sol.converged and io["converged"]
+        assert sol.iterations == io["iterations"]
+        assert np.linalg.norm(sol.x - xo) / np.linalg.norm(xo) < 1e-8
+        assert abs(sol.residual - np.linalg.norm(A @ sol.x - b) / np.linalg.norm(b)) < 1e-8
+        short = bem.cgs(op, b, bem.CgsConfig(3, 1e-14, 0))
+        assert not short.converged and short.iterations == 3
+        ilu = bem.solve_tbem_with_ilu(op, b, bem.CgsConfig(500, 1e-11, 0))
+        assert ilu.iterations == sol.iterations and (ilu.x == sol.x).all()
+    with pytest.raises(ValueError):
+        bem.cgs(bem.DenseOperator(A), b[:-1], bem.CgsConfig())
+
+
+def test_cgs_fmm_validation_cases(bem, orc):
+    """math-bem/tests/test_fmm_validation.rs:246-300 (test_iterative_solver_with_operator), :480-530
+    (test_solve_tbem_convenience), :714-785 (test_gmres_vs_cgs_convergence), :787-870 (robustness) on the device."""
+    import math
+
+    def tridiag(n, d, lo, up):
+        A = np.zeros((n, n), dtype=np.complex128)
+        for i in range(n):
+            A[i, i] = d
+            if i > 0:
+                A[i, i - 1] = lo
+            if i < n - 1:
+                A[i, i + 1] = up
+        return A
+
+    for A, w, budget, fn in ((tridiag(10, 10.0, complex(-1.0, 0.1), complex(-1.0, -0.1)), 0.3, 200, bem.solve_cgs),
+                             (tridiag(20, 10.0, complex(-1.0, 0.1), complex(-1.0, -0.1)), 0.3, 200, bem.solve_tbem_with_ilu),
+                             (tridiag(20, 10.0, -1.0, -1.0), 0.25, 100, bem.solve_cgs)):
+        n = A.shape[0]
+        b = np.array([math.sin(i * w) for i in range(n)], dtype=np.complex128)
+        op = bem.DenseOperator(A)
+        sol = fn(op, b, bem.CgsConfig(budget, 1e-10, 0))
+        xo, io = orc.cgs(A, b, max_iterations=budget, tolerance=1e-10)
+        assert sol.converged and sol.iterations == io["iterations"]
+        assert np.linalg.norm(b - A @ sol.x) / np.linalg.norm(b) < 1e-6
+        assert np.linalg.norm(sol.x - xo) / np.linalg.norm(xo) < 1e-10
+        g = bem.solve_gmres(op, b, bem.GmresConfig(100, 20, 1e-10))
+        assert g.converged and np.linalg.norm(g.x - sol.x) / np.linalg.norm(g.x) < 1e-6
+    A = tridiag(25, complex(6.0, 0.3), complex(-2.0, 0.1), complex(-1.5, -0.1))
+    b = np.array([math.sin(i * 0.25) for i in range(25)], dtype=np.complex128)
+    op = bem.DenseOperator(A)
+    g = bem.solve_gmres(op, b, bem.GmresConfig(100, 25, 1e-10))
+    c = bem.solve_cgs(op, b, bem.CgsConfig(100, 1e-10, 0))
+    xo, io = orc.cgs(A, b, max_iterations=100, tolerance=1e-10)
+    assert g.converged and np.linalg.norm(A @ g.x - b) / np.linalg.norm(b) < 1e-8
+    assert c.converged == io["converged"] and abs(c.iterations - io["iterations"]) <= 1
+
+
+def test_cgs_on_tbem_system(bem, orc):
+    """CGS on an assembled TBEM matrix (what solve_tbem_with_ilu is called on), vs the oracle's CGS on the oracle's matrix."""
+    from math_audio_b200.incident import IncidentField
+    from math_audio_b200.mesh import generate_icosphere_mesh
+    from math_audio_b200.types import PhysicsParams
+
+    a = 0.1
+    mesh = generate_icosphere_mesh(a, 3)
+    ph = PhysicsParams.from_wave_number(1.5 / a)
+    beta = ph.burton_miller_beta_adaptive(a)[0]
+    system = bem.build_tbem_system_with_beta(mesh, ph, beta)
+    b = system.rhs + IncidentField.plane_wave_z().compute_rhs_with_beta(mesh.center, mesh.normal, ph, beta)
+    sol = bem.solve_with_ilu(system, b, bem.CgsConfig(1000, 1e-10, 0))
+    Ao, _, _ = orc.assemble(mesh, ph.wave_number, beta)
+    xo, io = orc.cgs(Ao, b, max_iterations=1000, tolerance=1e-10)
+    assert sol.converged and io["converged"] and abs(sol.iterations - io["iterations"]) <= 1
+    assert np.linalg.norm(sol.x - xo) / np.linalg.norm(xo) < 1e-8
+    xg = bem.gmres(bem.DenseOperator(system), b, bem.GmresConfig(max_iterations=100, restart=50, tolerance=1e-11)).x
+    assert np.linalg.norm(sol.x - xg) / np.linalg.norm(xg) < 1e-8
+
+
 def test_lu_solve_kats_and_dense(bem, orc):
     A = np.array([[4 + 1j, 1], [1, 3 - 1j]])
     b = np.array([1 + 1j, 2 - 1j])

@@ -273,6 +273,30 @@ def test_gmres_preconditioned_identity_equals_plain(orc):
     assert orc.inverse_diagonal(np.array([0.0, 2.0, 1e-31]))[0] == 1.0  # |d| <= 1e-30 -> 1 (diagonal.rs:29-35)
 
 
+# ---- math-bem/tests/test_fmm_validation.rs:246-300, 480-530, 714-870 (CGS through solve_cgs / solve_tbem_with_ilu,
+# which run the unpreconditioned cgs of math-solvers/src/iterative/cgs.rs on a DenseOperator)
+def test_fmm_validation_cgs_cases(orc):
+    cases = (("test_iterative_solver_with_operator", tridiag(10, 10.0, complex(-1.0, 0.1), complex(-1.0, -0.1)), 0.3, 200),
+             ("test_solve_tbem_convenience", tridiag(20, 10.0, complex(-1.0, 0.1), complex(-1.0, -0.1)), 0.3, 200),
+             ("test_gmres_vs_cgs_convergence", tridiag(20, 10.0, -1.0, -1.0), 0.25, 100))
+    for name, A, w, budget in cases:
+        n = A.shape[0]
+        b = np.array([math.sin(i * w) for i in range(n)], dtype=np.complex128)
+        x, info = orc.cgs(A, b, max_iterations=budget, tolerance=1e-10)
+        assert info["converged"], name
+        assert np.linalg.norm(b - A @ x) / np.linalg.norm(b) < 1e-6, name
+        if name == "test_gmres_vs_cgs_convergence":
+            xg, ig = orc.gmres(A, b, max_iterations=100, restart=20, tolerance=1e-10)
+            assert ig["converged"] and np.linalg.norm(xg - x) / np.linalg.norm(xg) < 1e-6
+    # test_gmres_robustness_vs_cgs (:787-870): GMRES must converge; CGS may or may not
+    A = tridiag(25, complex(6.0, 0.3), complex(-2.0, 0.1), complex(-1.5, -0.1))
+    b = np.array([math.sin(i * 0.25) for i in range(25)], dtype=np.complex128)
+    xg, ig = orc.gmres(A, b, max_iterations=100, restart=25, tolerance=1e-10)
+    assert ig["converged"] and np.linalg.norm(A @ xg - b) / np.linalg.norm(b) < 1e-8
+    xc, ic = orc.cgs(A, b, max_iterations=100, tolerance=1e-10)
+    assert ic["iterations"] <= 100 and (not ic["converged"] or np.linalg.norm(xc - xg) / np.linalg.norm(xg) < 1e-6)
+
+
 # ---- math-wave/src/analytical/solutions_3d.rs:385-525 -----------------------------
 def test_spherical_bessel_and_legendre(orc):
     assert abs(orc.spherical_bessel_j(0, 1.0) - math.sin(1.0)) < 1e-10

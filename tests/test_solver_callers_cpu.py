@@ -32,6 +32,61 @@ def test_bicgstab_zero_rhs_and_budget(orc):
     assert abs(info["residual"] - np.linalg.norm(A @ x - b) / np.linalg.norm(b)) < 1e-12
 
 
+# ---- math-solvers/src/iterative/cgs.rs:157-186 -------------------------------------------------
+def test_cgs_simple(orc):
+    A = np.array([[4, 1], [1, 3]], dtype=np.complex128)
+    b = np.array([1, 2], dtype=np.complex128)
+    x, info = orc.cgs(A, b, max_iterations=100, tolerance=1e-10)
+    assert info["converged"]
+    assert np.linalg.norm(A @ x - b) < 1e-8
+
+
+def test_cgs_zero_rhs_budget_and_literal_restatement(orc):
+    A = np.array([[4, 1], [1, 3]], dtype=np.complex128)
+    x, info = orc.cgs(A, np.zeros(2, dtype=np.complex128))
+    assert info == dict(iterations=0, residual=0.0, converged=True) and not x.any()   # cgs.rs:55-62
+    rng = np.random.default_rng(3)
+    n = 40
+    A = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))) / np.sqrt(n) + 3 * np.eye(n)
+    b = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    x, info = orc.cgs(A, b, max_iterations=3, tolerance=1e-14)
+    assert not info["converged"] and info["iterations"] == 3                           # cgs.rs:142-149
+    x, info = orc.cgs(A, b, max_iterations=500, tolerance=1e-11)
+    assert info["converged"] and np.linalg.norm(A @ x - b) / np.linalg.norm(b) < 1e-9
+
+    # second, independent restatement of cgs.rs:64-140 in numpy (statement by statement)
+    def cgs_np(A, b, max_iterations, tol):
+        x = np.zeros_like(b)
+        bn = np.linalg.norm(b)
+        r = b.copy(); r0 = r.copy(); rho = np.vdot(r0, r); p = r.copy(); u = r.copy()
+        for it in range(max_iterations):
+            v = A @ p
+            sigma = np.vdot(r0, v)
+            if abs(sigma) < 1e-30:
+                return x, it, False
+            alpha = rho / sigma
+            q = u - alpha * v
+            upq = u + q
+            w = A @ upq
+            x = x + alpha * upq
+            r = r - alpha * w
+            rel = np.linalg.norm(r) / bn
+            if rel < tol:
+                return x, it + 1, True
+            rho_new = np.vdot(r0, r)
+            if abs(rho) < 1e-30:
+                return x, it + 1, False
+            beta = rho_new / rho
+            rho = rho_new
+            u = r + beta * q
+            p = u + beta * (q + beta * p)
+        return x, max_iterations, False
+
+    x2, it2, conv2 = cgs_np(A, b, 500, 1e-11)
+    assert conv2 and it2 == info["iterations"]
+    assert np.linalg.norm(x - x2) / np.linalg.norm(x2) < 1e-9
+
+
 # ---- math-solvers/src/direct/lu.rs:163-241 ----------------------------------------------------
 def test_lu_solve_kats(orc):
     A = np.array([[4.0, 1.0], [1.0, 3.0]])
