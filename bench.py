@@ -322,9 +322,14 @@ def run_native(args):
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(s_asm)     # the first timed kernel is an assembly kernel on the assembly stream
+    if driver.trace is not None:
+        driver.trace.clear()
     sols = driver.run(cases[args.warmup:], cfg, make_solve_device(args.warmup))
     ev1.record(s_solve)   # the last one is the solution update on the solve stream
     boosts_timed = driver.boosts - boosts_warm
+    if driver.trace is not None and rank == 0:
+        for lab, ci, ts in sorted(driver.trace, key=lambda r: r[2]):
+            print(f"[value trace] {ts * 1e3:9.2f} ms  {lab:12s} case {ci}", file=sys.stderr)
     barrier()
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -382,8 +387,13 @@ def run_native(args):
         driver.run(e2e_cases[:2], cfg, solve_host, restage_host_mesh=True)  # untimed: first use of the host path in the driver
         barrier()
         t0 = time.perf_counter()
+        if driver.trace is not None:
+            driver.trace.clear()
         sols_e2e = driver.run(e2e_cases, cfg, solve_host, restage_host_mesh=True)
         barrier()
+        if driver.trace is not None and rank == 0:
+            for lab, ci, ts in sorted(driver.trace, key=lambda r: r[2]):
+                print(f"[e2e trace] {ts * 1e3:9.2f} ms  {lab:12s} case {ci}", file=sys.stderr)
         e2e_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)

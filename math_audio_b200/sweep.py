@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import os
 import threading
+import time
 from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -37,15 +38,25 @@ class SweepDriver:
         self.boosts = 0
         # join a still-running background assembly with full-speed blocks once the solve of the current frequency is done
         self.boost = os.environ.get("BEMB200_SWEEP_BOOST", "1") != "0"
+        # BEMB200_SWEEP_TRACE=1: (label, case, seconds since run() started) of every phase boundary, both threads
+        self.trace: Optional[list] = [] if os.environ.get("BEMB200_SWEEP_TRACE") else None
+        self._t0 = 0.0
 
-    def _assemble(self, slot: int, physics: PhysicsParams, beta: complex, mesh_for_stage: Optional[Mesh], err: list):
+    def _mark(self, label: str, i: int) -> None:
+        if self.trace is not None:
+            self.trace.append((label, i, time.perf_counter() - self._t0))
+
+    def _assemble(self, slot: int, physics: PhysicsParams, beta: complex, mesh_for_stage: Optional[Mesh], err: list, case: int = -1):
         try:
+            self._mark("asm_begin", case)
             staged = self.staged if mesh_for_stage is None else bem.StagedMesh(mesh_for_stage, self.ctx_asm)
+            self._mark("asm_staged", case)
             first = self.buffers[slot] is None
             self.buffers[slot] = bem.build_tbem_system_with_beta(staged, physics, beta, ctx=self.ctx_asm, rows=self.rows,
                                                                 reuse=self.buffers[slot], fetch_rhs=False)
             if first and self.overlap:
                 self.buffers[slot].matrix.set_context(self.ctx_solve)
+            self._mark("asm_end", case)
         except Exception as e:  # surfaced in the caller thread
             err.append(e)
 
@@ -60,8 +71,9 @@ class SweepDriver:
         mesh_arg = self.mesh if restage_host_mesh else None
         if not cases:
             return out
+        self._t0 = time.perf_counter()
         self.ctx_asm.set_background(0)  # nothing to hide behind yet: full-speed assembly
-        self._assemble(0, cases[0][0], cases[0][1], mesh_arg, err)
+        self._assemble(0, cases[0][0], cases[0][1], mesh_arg, err, 0)
         if err:
             raise err[0]
         self.ctx_asm.set_background(self.background_blocks_per_sm)
@@ -71,14 +83,16 @@ class SweepDriver:
                 t = None
                 if i + 1 < len(cases):
                     if self.overlap:
-                        t = threading.Thread(target=self._assemble, args=((i + 1) % 2, cases[i + 1][0], cases[i + 1][1], mesh_arg, err))
+                        t = threading.Thread(target=self._assemble, args=((i + 1) % 2, cases[i + 1][0], cases[i + 1][1], mesh_arg, err, i + 1))
                         t.start()
                 elif self.overlap:
                     self.ctx_solve.set_shared_gpu(False)  # last case: nothing left to assemble beside this solve
                 system = self.buffers[i % 2]
                 self.asm_stats.append(system.matrix.assembly_stats())
                 op = bem.DenseOperator(system)
+                self._mark("solve_begin", i)
                 out.append(solve(i, system, op))
+                self._mark("solve_end", i)
                 self.sol_stats.append(system.matrix.solver_stats())
                 if t is not None:
                     nxt = self.buffers[(i + 1) % 2]
@@ -86,8 +100,9 @@ class SweepDriver:
                         nxt.matrix.boost_assembly(self.ctx_solve)  # the solver has left the GPU: finish the assembly at full speed
                         self.boosts += 1
                     t.join()
+                    self._mark("joined", i)
                 elif i + 1 < len(cases):
-                    self._assemble((i + 1) % 2, cases[i + 1][0], cases[i + 1][1], mesh_arg, err)
+                    self._assemble((i + 1) % 2, cases[i + 1][0], cases[i + 1][1], mesh_arg, err, i + 1)
                 if err:
                     raise err[0]
         finally:
