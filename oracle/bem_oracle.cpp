@@ -1051,6 +1051,13 @@ void orc_gmres_preconditioned(const double* A, uint64_t n, const double* inv_dia
     orc_gmres_preconditioned_op(dense_apply, &ctx, n, inv_diag, b, x0, max_iterations, restart, tolerance, x_out, info);
 }
 
+// ---- the Arnoldi vector primitives (math-solvers/src/blas_helpers.rs:21-56), exported for their reference tests ----
+void orc_inner_product(const double* x, const double* y, uint64_t n, double* out2) {
+    const cplx r = inner_product((const cplx*)x, (const cplx*)y, n);
+    out2[0] = r.re; out2[1] = r.im;
+}
+double orc_vector_norm(const double* x, uint64_t n) { return vector_norm((const cplx*)x, n); }
+
 // ---- bicgstab: math-solvers/src/iterative/bicgstab.rs:53-215 on a dense row-major matrix ----
 void orc_bicgstab(const double* A, uint64_t n, const double* b_in, uint32_t max_iterations, double tolerance, double* x_out,
                   orc_gmres_info* info, int nthreads) {

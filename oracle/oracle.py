@@ -239,6 +239,23 @@ def gmres(A, b, x0=None, max_iterations=100, restart=30, tolerance=1e-6, nthread
                    converged=bool(info.converged))
 
 
+def inner_product(x, y) -> complex:
+    """blas_helpers.rs:21-33: sum conj(x_i) y_i, sequential."""
+    x = np.ascontiguousarray(x, dtype=np.complex128)
+    y = np.ascontiguousarray(y, dtype=np.complex128)
+    assert x.shape == y.shape
+    out = np.zeros(2)
+    lib().orc_inner_product(_p(x), _p(y), C.c_uint64(x.shape[0]), _p(out))
+    return complex(out[0], out[1])
+
+
+def vector_norm(x) -> float:
+    """blas_helpers.rs:38-56: sqrt(sum |x_i|^2), sequential."""
+    x = np.ascontiguousarray(x, dtype=np.complex128)
+    lib().orc_vector_norm.restype = C.c_double
+    return float(lib().orc_vector_norm(_p(x), C.c_uint64(x.shape[0])))
+
+
 def bicgstab(A, b, max_iterations=1000, tolerance=1e-6, nthreads=0):
     """math-solvers/src/iterative/bicgstab.rs:53-215 on a dense row-major matrix -> (x, info dict)."""
     A = np.ascontiguousarray(A, dtype=np.complex128)
