@@ -444,6 +444,24 @@ def run_native(args):
             traffic = json.loads(tp.read_text()).get(f"zgemv_{wl['name']}_{world}")
         except Exception:
             traffic = None
+    # FP64 far kernel.  `achieved` = the kernel as a foreground launch (the sequential host-buffer calls of this very run time it
+    # with nothing beside it); in the pipelined sweep it deliberately runs as a polite one-block-per-SM grid underneath the
+    # solve, which `in_sweep` reports (there its duration is hidden, not minimised).
+    fg_ms = float(np.mean(e2e_far_ms)) if e2e_far_ms else None
+    fa = {"kernel": "far_kernel<13>", "bound": "fp64", "peak": fp64_nominal, "unit": "TFLOP/s",
+          "peak_measured_dfma": fp64_meas, "algorithmic_flop_per_launch": far_flop,
+          "peak_source": "nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz; measured = register-resident DFMA loop on this GPU"}
+    in_sweep = {"achieved": far_tf, "frac": far_tf / fp64_nominal, "avg_launch_ms": far_ms / K, "share_of_step": far_ms / total_ms,
+                "assembly_share_of_step": asm_ms / total_ms,
+                "note": ("background grid (148 persistent blocks pulling work items from a device counter) underneath the solve of the previous frequency"
+                         if overlap else "foreground launch of the timed sweep (sequential schedule)")}
+    if fg_ms:
+        fg_tf = far_flop / (fg_ms * 1e-3) / 1e12
+        fa.update(achieved=fg_tf, frac=fg_tf / fp64_nominal, frac_of_measured=(fg_tf / fp64_meas if fp64_meas > 0 else None),
+                  avg_launch_ms=fg_ms, launches=len(e2e_far_ms),
+                  note="foreground launches of this run (the sequential host-buffer calls; nothing overlaps the kernel)", in_sweep=in_sweep)
+    else:
+        fa.update(in_sweep, frac_of_measured=(far_tf / fp64_meas if fp64_meas > 0 else None))
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
         "ms_per_step": total_ms / K, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
@@ -465,17 +483,7 @@ def run_native(args):
                      "isolated": (None if not iso_ms else {"avg_launch_ms": iso_ms, "achieved": mv_bytes / (iso_ms * 1e-3) / 1e9,
                                                            "frac": mv_bytes / (iso_ms * 1e-3) / 1e9 / hbm_peak,
                                                            "note": "same kernel with nothing else running (no overlapped assembly)"})},
-        "roofline_assembly": {"kernel": "far_kernel<13>", "bound": "fp64", "achieved": far_tf, "peak": fp64_nominal,
-                              "unit": "TFLOP/s", "frac": far_tf / fp64_nominal, "peak_measured_dfma": fp64_meas,
-                              "frac_of_measured": far_tf / fp64_meas if fp64_meas > 0 else None,
-                              "algorithmic_flop_per_launch": far_flop, "avg_launch_ms": far_ms / K,
-                              "share_of_step": far_ms / total_ms, "assembly_share_of_step": asm_ms / total_ms,
-                              "isolated": (None if not e2e_far_ms else {
-                                  "avg_launch_ms": float(np.mean(e2e_far_ms)), "achieved": far_flop / (float(np.mean(e2e_far_ms)) * 1e-3) / 1e12,
-                                  "frac": far_flop / (float(np.mean(e2e_far_ms)) * 1e-3) / 1e12 / fp64_nominal,
-                                  "note": "same kernel in the foreground (sequential end-to-end calls of this run); in the pipelined sweep it "
-                                          "runs as a one-block-per-SM background grid underneath the solve, which is what `achieved` shows"}),
-                              "peak_source": "nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz; measured = register-resident DFMA loop on this GPU"},
+        "roofline_assembly": fa,
         "e2e": {"value": float(e2e_s.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d // e2e_steps),
                 "d2h_bytes_per_step": int(d2h // e2e_steps), "steps": e2e_steps, "schedule": e2e_schedule,
                 "sequential_value": float(e2e_seq_s.item())},
