@@ -203,6 +203,38 @@ def test_mixed_bc_and_element_types(bem, orc):
         assert system.matrix.assembly_stats()["special_pairs"] > 0
 
 
+@pytest.mark.parametrize("tau,harmonic,beta", [
+    (-1.0, 1.0, 0j),                 # interior problem: PhysicsParams::new(.., is_internal = true), beta = 0 (types.rs:45, 64-70)
+    (-1.0, 1.0, 0.25j),              # interior with an explicit coupling passed to build_tbem_system_with_beta
+    (1.0, 1.0, 0.03 + 0.4j),         # beta with a real part: the general (non purely imaginary) far-kernel instantiation
+    (1.0, -1.0, 0.4j),               # harmonic_factor = -1, exp(-ikr): carried by the ABI, never set by PhysicsParams::new
+    (-1.0, -1.0, -0.02 + 0.3j),
+])
+def test_interior_complex_beta_and_time_convention(bem, orc, tau, harmonic, beta):
+    """Every parameter of `bemb200_physics` away from the exterior / exp(+ikr) / purely imaginary beta case the
+    reference's callers use, against the oracle on all entries (Tri3 sphere across the dG/dn sign switch, and the
+    Quad4 box with a vibrating piston, i.e. the right-hand-side path with its unscaled-beta quirk: 0 for tau < 0)."""
+    a = 0.1
+    mesh = generate_icosphere_mesh(a, 2)
+    for ka in (0.3, 2.0):
+        ph = PhysicsParams.from_wave_number(ka / a)
+        ph.tau, ph.harmonic_factor = tau, harmonic
+        system = bem.build_tbem_system_with_beta(mesh, ph, beta)
+        Ao, rhso, _ = orc.assemble(mesh, ph.wave_number, beta, harmonic=harmonic, tau=tau)
+        rel, rown = entry_err(system.matrix.rows(), Ao)
+        assert rel < ENTRY_TOL and rown < 1e-13, (ka, rel, rown)
+        assert not system.rhs.any() and not rhso.any()
+    box, front = box_piston_mesh()
+    ph = PhysicsParams.new(1000.0, 343.0, 1.21, tau < 0)
+    ph.harmonic_factor = harmonic
+    system = bem.build_tbem_system_with_beta(box, ph, beta)
+    Ao, rhso, _ = orc.assemble(box, ph.wave_number, beta, harmonic=harmonic, tau=tau)
+    rel, rown = entry_err(system.matrix.rows(), Ao)
+    assert rown < 1e-13, (rel, rown)
+    assert np.max(np.abs(system.rhs - rhso)) <= 1e-12 * max(1.0, np.max(np.abs(rhso)))
+    assert np.abs(rhso).max() > 0.0
+
+
 def test_row_blocks_eval_elements_and_dof_permutation(bem, orc):
     mesh = generate_icosphere_mesh(0.1, 2)
     ph = PhysicsParams.from_wave_number(15.0)
