@@ -235,6 +235,82 @@ def test_interior_complex_beta_and_time_convention(bem, orc, tau, harmonic, beta
     assert np.abs(rhso).max() > 0.0
 
 
+def test_tiny_offcentre_and_scaled_meshes(bem, orc):
+    """Edge shapes of the input: the reference's own 2-element fixture (tbem.rs:542-598, hand-set centres/normals/areas,
+    1-entry non-zero velocity -> RHS), a single element, 20 elements (less than one 128-column tile), a sphere translated
+    away from the origin (the dG/dn sign heuristic of tbem.rs:108-123 then sees k*|centre| >= 0.5) and the same problem
+    at two length scales (ka fixed)."""
+    nodes = np.array([[0.0, 0.0, 0.0], [1.0, 0.0, 0.0], [0.5, 1.0, 0.0], [1.5, 1.0, 0.0]])
+    m = mesh_from_data(nodes, np.array([[0, 1, 2], [1, 3, 2]], dtype=np.uint32))
+    m.normal[:] = [0.0, 0.0, 1.0]
+    m.center[0] = [0.5, 1.0 / 3.0, 0.0]
+    m.center[1] = [1.0, 2.0 / 3.0, 0.0]
+    m.area[:] = 0.5
+    m.bc_val[0, 0] = 1.0
+    ph = PhysicsParams.new(100.0, 343.0, 1.21, False)
+    system = bem.build_tbem_system(m, ph)
+    A = system.matrix.rows()
+    Ao, rhso, _ = orc.assemble(m, ph.wave_number, ph.burton_miller_beta())
+    assert system.num_dofs == 2 and A.shape == (2, 2) and system.rhs.shape == (2,)
+    assert abs(A[0, 0]) > 1e-15 and abs(A[1, 1]) > 1e-15                   # tbem.rs:594-597
+    assert np.max(np.abs(A - Ao) / np.abs(Ao)) < ENTRY_TOL
+    assert np.max(np.abs(system.rhs - rhso) / np.abs(rhso)) < ENTRY_TOL and abs(rhso[0]) > 0 and abs(rhso[1]) > 0
+    one = mesh_from_data(nodes[:3], np.array([[0, 1, 2]], dtype=np.uint32))
+    s1 = bem.build_tbem_system(one, ph)
+    A1, _, _ = orc.assemble(one, ph.wave_number, ph.burton_miller_beta())
+    assert s1.matrix.rows().shape == (1, 1) and abs(s1.matrix.rows()[0, 0] - A1[0, 0]) / abs(A1[0, 0]) < ENTRY_TOL
+    sol = bem.gmres(bem.DenseOperator(s1), np.array([1.0 + 2.0j]), bem.GmresConfig(10, 5, 1e-12))
+    assert sol.converged and abs(sol.x[0] - (1.0 + 2.0j) / A1[0, 0]) < 1e-12 * abs(sol.x[0])
+    a = 0.1
+    ico0 = generate_icosphere_mesh(a, 0)
+    assert ico0.n_elem == 20
+    for ka in (0.3, 1.0, 4.0):
+        p = PhysicsParams.from_wave_number(ka / a)
+        beta = p.burton_miller_beta_adaptive(a)[0]
+        Ao, _, _ = orc.assemble(ico0, p.wave_number, beta)
+        assert entry_err(bem.build_tbem_system_with_beta(ico0, p, beta).matrix.rows(), Ao)[0] < ENTRY_TOL
+    # off-centre: same sphere shifted by (0.3, -0.2, 0.5) m
+    mesh = generate_icosphere_mesh(a, 2)
+    shift = np.array([0.3, -0.2, 0.5])
+    moved = mesh_from_data(mesh.nodes + shift, mesh.conn[:, :3].copy())
+    moved.normal[:] = mesh.normal
+    p = PhysicsParams.from_wave_number(0.2 / a)                            # ka = 0.2 but k |centre| = 1.2 -> sign flips
+    beta = p.burton_miller_beta()
+    assert orc.dg_dn_sign(mesh, p.wave_number) == 1.0 and orc.dg_dn_sign(moved, p.wave_number) == -1.0
+    Ao, _, _ = orc.assemble(moved, p.wave_number, beta)
+    assert entry_err(bem.build_tbem_system_with_beta(moved, p, beta).matrix.rows(), Ao)[0] < ENTRY_TOL
+    # length scales: a = 25 m and a = 2 mm at ka = 1.5
+    for radius in (25.0, 2e-3):
+        big = generate_icosphere_mesh(radius, 2)
+        p = PhysicsParams.from_wave_number(1.5 / radius)
+        beta = p.burton_miller_beta_adaptive(radius)[0]
+        Ao, _, _ = orc.assemble(big, p.wave_number, beta)
+        rel, rown = entry_err(bem.build_tbem_system_with_beta(big, p, beta).matrix.rows(), Ao)
+        assert rel < ENTRY_TOL and rown < 1e-13, (radius, rel, rown)
+
+
+def test_gmres_extreme_configurations(bem, orc):
+    """restart = 1 (every iteration restarts), a tolerance already met by x0 = 0 never happens for b != 0 but a loose one
+    stops after one iteration, max_iterations = 0 returns the initial residual unconverged (gmres.rs:137, 264-276)."""
+    rng = np.random.default_rng(11)
+    n = 300
+    A = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))) / np.sqrt(n) + 3 * np.eye(n)
+    b = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    op = bem.DenseOperator(A)
+    for cfg in ((200, 1, 1e-8), (5, 3, 1e-12), (50, 7, 0.5), (0, 10, 1e-8), (3, 400, 1e-10)):
+        sol = bem.gmres(op, b, bem.GmresConfig(*cfg))
+        xo, io = orc.gmres(A, b, max_iterations=cfg[0], restart=cfg[1], tolerance=cfg[2])
+        assert (sol.iterations, sol.restarts, sol.converged) == (io["iterations"], io["restarts"], io["converged"]), cfg
+        assert abs(sol.residual - io["residual"]) <= 1e-9 * max(io["residual"], 1e-300) + 1e-15, cfg
+        assert np.linalg.norm(sol.x - xo) <= 1e-10 * max(np.linalg.norm(xo), 1e-300), cfg
+    # a long cycle: restart 150 > the 64 basis vectors of the low-synchronisation kernels (103 iterations without restart)
+    A2 = A - 1.4 * np.eye(n)
+    sol = bem.gmres(bem.DenseOperator(A2), b, bem.GmresConfig(3, 150, 1e-10))
+    xo, io = orc.gmres(A2, b, max_iterations=3, restart=150, tolerance=1e-10)
+    assert io["iterations"] > 64 and (sol.iterations, sol.restarts, sol.converged) == (io["iterations"], io["restarts"], io["converged"])
+    assert np.linalg.norm(sol.x - xo) <= 1e-9 * np.linalg.norm(xo)
+
+
 def test_row_blocks_eval_elements_and_dof_permutation(bem, orc):
     mesh = generate_icosphere_mesh(0.1, 2)
     ph = PhysicsParams.from_wave_number(15.0)
