@@ -1,0 +1,15 @@
+"""Three foreground assemblies at 20 480 elements (for an ncu capture of far_kernel)."""
+import sys
+sys.path.insert(0, str(__import__('pathlib').Path(__file__).resolve().parents[2]))
+from math_audio_b200 import bem
+from math_audio_b200.mesh import generate_icosphere_mesh
+from math_audio_b200.types import PhysicsParams
+a = 0.1
+mesh = generate_icosphere_mesh(a, 5)
+st = bem.StagedMesh(mesh)
+ph = PhysicsParams.from_wave_number(2.0 / a)
+beta, _ = ph.burton_miller_beta_adaptive(a)
+sysg = None
+for rep in range(3):
+    sysg = bem.build_tbem_system_with_beta(st, ph, beta, reuse=sysg, fetch_rhs=False)
+    print(sysg.matrix.assembly_stats())
