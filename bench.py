@@ -460,6 +460,12 @@ def run_native(args):
         fa.update(achieved=fg_tf, frac=fg_tf / fp64_nominal, frac_of_measured=(fg_tf / fp64_meas if fp64_meas > 0 else None),
                   avg_launch_ms=fg_ms, launches=len(e2e_far_ms),
                   note="foreground launches of this run (the sequential host-buffer calls; nothing overlaps the kernel)", in_sweep=in_sweep)
+        mhz = (clocks or {}).get("sm_mhz")
+        if mhz:
+            # the board runs this run's sustained FP64 load under its power cap: the same kernel against the DFMA peak at the SM
+            # clock nvidia-smi reported during the timed sweep (burst launches at 1.96 GHz: profiles/r01e_ncu_far_summary.json)
+            pk = 148 * 64 * 2 * mhz * 1e6 / 1e12
+            fa["at_sampled_clock"] = {"sm_mhz": mhz, "peak": pk, "frac": fg_tf / pk}
     else:
         fa.update(in_sweep, frac_of_measured=(far_tf / fp64_meas if fp64_meas > 0 else None))
     line = {
