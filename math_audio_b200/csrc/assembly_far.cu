@@ -20,13 +20,13 @@
 //     r_q^2        = |d0|^2 + a_q (2 d0.e1) + b_q (2 d0.e2) + kappa_q            3 DP ops
 //     (y_q-x).n_x  = d0.n_x + a_q (e1.n_x) + b_q (e2.n_x)                       2 DP ops
 //     (y_q-x).n_y  = d0.n_y                                   (constant over the element)
-// then one MUFU-seeded rsqrt (5), one table-based sincos (pi/64 reduction, 128-entry (cos,sin) table in
-// shared memory, degree-6/7 kernels, one rotation: 16) and the kernel algebra
+// then one MUFU-seeded rsqrt (5), one table-based sincos (pi/256 reduction, 512-entry (cos,sin) table in
+// shared memory, degree-4/5 kernels, one rotation: 14) and the kernel algebra
 // with H and E folded into ONE complex accumulator:
 //     A_ij = sum_q zg_q * [ cH h rho (-rho + ik) + beta (P_q - i Q_q) ],
 //     P = rho^2 t - k^2 rq,  Q = k rho t,  t = 3 rq + n_x.n_y,  rq = (h rho)(-m rho)
-// ~46 DP-pipe instructions per quadrature point (purely imaginary beta, the reference's
-// beta = i*scale/k).  Nothing but the 16-byte result touches HBM.
+// (for purely imaginary beta -- the reference's beta = i*scale/k -- the bracket factors as rho (X + iY), see the
+// loop) ~41 DP-pipe instructions per quadrature point.  Nothing but the 16-byte result touches HBM.
 // Pairs that fail the (guard-banded) ratio test are appended to a compact list for the exact
 // near-field kernel, which re-takes the decision bit-faithfully and overwrites the entry.
 #include <cmath>
@@ -49,7 +49,7 @@ struct RuleConst {
 };
 __device__ __constant__ RuleConst d_rule_tri;
 __device__ __constant__ RuleConst d_rule_quad;
-__device__ double2 d_sincos_tab[SINCOS_TAB];  // (cos, sin)(i*pi/64), filled by upload_tables()
+__device__ double2 d_sincos_tab[SINCOS_TAB];  // (cos, sin)(i*pi/256), filled by upload_tables()
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -71,13 +71,13 @@ far_kernel(const double* __restrict__ far_k, const double* __restrict__ far_c, c
     constexpr bool QUAD = (NQ == NQ_QUAD);
     const uint8_t want = QUAD ? COL_FLAT_QUAD : COL_FLAT_TRI;
     const RuleConst& rc = QUAD ? d_rule_quad : d_rule_tri;
-    const double bk = beta_im * wavruim, bk2 = beta_im * k2;
+    const double bk = beta_im * wavruim, bk2 = beta_im * k2, bk3 = 3.0 * bk, b3 = 3.0 * beta_im;
 
     if (t == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (t < SINCOS_TAB) sm_tab[t] = d_sincos_tab[t];
+    for (uint32_t i = t; i < SINCOS_TAB; i += TILE) sm_tab[i] = d_sincos_tab[i];
     __syncthreads();
 
     // Work item = (column tile, row chunk); a block owns a contiguous range of items, ordered so
@@ -184,8 +184,12 @@ far_kernel(const double* __restrict__ far_k, const double* __restrict__ far_c, c
         //   H factor  cH (h rho)(-rho + ik)             = (-cH h) rho^2 + i (cH h k) rho
         //   E factor  (rho^2 t - k^2 rq) - i (k rho) t
         const double nh = -h;
-        const double nhc = -cH * h;          // A1 = nhc * rho^2
+        const double nhc = -cH * h;             // A1 = nhc * rho^2
         const double hck = (cH * h) * wavruim;  // A2 = hck * rho
+        // purely imaginary beta = i b: with u = rho^2, nm = -h m the bracket factors as rho (X + iY),
+        //   X = nhc rho + 3 b k nm u + b k nn,   Y = rho [nm (3 b u - b k^2) + b nn] + hck
+        // and the contribution of the point is  w u (cs + i sn)(X + iY)
+        const double c3 = bk * nn, c2 = beta_im * nn;
         double are = 0.0, aim = 0.0;
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
@@ -194,27 +198,30 @@ far_kernel(const double* __restrict__ far_k, const double* __restrict__ far_c, c
             const double r = r2 * rho;
             double sn, cs;
             fast_sincos_tab(wavruim * r, sm_tab, sn, cs);
-            const double g = rho * rc.w[q];  // w / r   (J/(4 pi) is applied once per pair)
-            const double zgr = g * cs, zgi = g * sn;
             const double m = (q == 0) ? M0 : fma(rc.a[q], E1, fma(rc.b[q], E2, M0));  // (y_q - x).n_x
             const double rho2 = rho * rho;
-            const double rq = (nh * m) * rho2;
-            const double t3 = fma(3.0, rq, nn);
-            const double A1 = nhc * rho2;
-            const double A2 = hck * rho;
-            double fre, fim;
             if (BIMAG) {
-                // beta = i b:  beta (P - iQ) = b Q + i b P,  Q = k rho t,  P = rho^2 t - k^2 rq
-                fre = fma(bk * rho, t3, A1);
-                fim = fma(beta_im * rho2, t3, fma(-bk2, rq, A2));
+                const double nm = nh * m;
+                const double X = fma(nhc, rho, fma(bk3 * nm, rho2, c3));
+                const double Z = fma(nm, fma(b3, rho2, -bk2), c2);
+                const double Y = fma(rho, Z, hck);
+                const double G = rc.w[q] * rho2;  // w / r^2   (J/(4 pi) is applied once per pair)
+                are = fma(G, fma(cs, X, -(sn * Y)), are);
+                aim = fma(G, fma(cs, Y, sn * X), aim);
             } else {
+                const double g = rho * rc.w[q];  // w / r
+                const double zgr = g * cs, zgi = g * sn;
+                const double rq = (nh * m) * rho2;
+                const double t3 = fma(3.0, rq, nn);
+                const double A1 = nhc * rho2;
+                const double A2 = hck * rho;
                 const double P = fma(rho2, t3, -(k2 * rq));
                 const double Q = (wavruim * rho) * t3;
-                fre = fma(beta_re, P, fma(beta_im, Q, A1));
-                fim = fma(beta_im, P, fma(-beta_re, Q, A2));
+                const double fre = fma(beta_re, P, fma(beta_im, Q, A1));
+                const double fim = fma(beta_im, P, fma(-beta_re, Q, A2));
+                are = fma(zgr, fre, fma(-zgi, fim, are));
+                aim = fma(zgr, fim, fma(zgi, fre, aim));
             }
-            are = fma(zgr, fre, fma(-zgi, fim, are));
-            aim = fma(zgr, fim, fma(zgi, fre, aim));
         }
         if (active) {
             double2 v = make_double2(are * j4pi, aim * j4pi);
@@ -253,10 +260,11 @@ cudaError_t upload_tables() {
     {
         double2 tab[SINCOS_TAB];
         for (int i = 0; i < SINCOS_TAB; ++i) {
-            const double ang = (double)i * (PI / 64.0);
-            tab[i] = make_double2(std::cos(ang), std::sin(ang));
+            const long double ang = (long double)i * (3.14159265358979323846264338327950288L / (long double)SINCOS_STEPS_PER_PI);
+            tab[i] = make_double2((double)cosl(ang), (double)sinl(ang));
         }
-        tab[0] = make_double2(1.0, 0.0); tab[32] = make_double2(0.0, 1.0); tab[64] = make_double2(-1.0, 0.0); tab[96] = make_double2(0.0, -1.0);
+        tab[0] = make_double2(1.0, 0.0); tab[SINCOS_TAB / 4] = make_double2(0.0, 1.0);
+        tab[SINCOS_TAB / 2] = make_double2(-1.0, 0.0); tab[3 * SINCOS_TAB / 4] = make_double2(0.0, -1.0);
         e = cudaMemcpyToSymbol(d_sincos_tab, tab, sizeof tab);
         if (e != cudaSuccess) return e;
     }

@@ -89,22 +89,23 @@ __device__ __forceinline__ void fast_sincos(double x, double& s_out, double& c_o
     c_out = cc;
 }
 
-// Table variant for the far kernel: reduction by pi/64 against a 128-entry (cos, sin) table held in
-// shared memory, degree-6/7 Taylor kernels on |t| <= pi/128 (truncation < 1e-17) and one complex
-// rotation: 16 DP-pipe instructions, no quadrant selects.  tab[i] = (cos(i*pi/64), sin(i*pi/64)).
-constexpr int SINCOS_TAB = 128;
+// Table variant for the far kernel: reduction by pi/256 against a 512-entry (cos, sin) table held in
+// shared memory (8 KB), degree-4/5 kernels on |t| <= pi/512 (the cos kernel's z^2 coefficient absorbs the
+// truncated z^3/720 at the interval end: max abs error 1.7e-16 over [0, 5000], checked on the host with
+// long-double references and on the device by bemb200_selftest_math) and one complex rotation:
+// 14 DP-pipe instructions, no quadrant selects.  tab[i] = (cos(i*pi/256), sin(i*pi/256)).
+constexpr int SINCOS_TAB = 512;
+constexpr double SINCOS_STEPS_PER_PI = 256.0;
 __device__ __forceinline__ void fast_sincos_tab(double x, const double2* __restrict__ tab, double& s_out, double& c_out) {
     const double MAGIC = 6755399441055744.0;
-    double tq = fma(x, 20.371832715762604, MAGIC);  // 64/pi
+    double tq = fma(x, 81.48733086305042, MAGIC);   // 256/pi
     const int idx = __double2loint(tq) & (SINCOS_TAB - 1);
     const double q = tq - MAGIC;
-    double t = fma(-q, 0.04908738521234052, x);     // pi/64 hi
-    t = fma(-q, 1.9135106236677394e-18, t);         // pi/64 lo
+    double t = fma(-q, 0.01227184630308513, x);     // pi/256 hi  (= pi/64 hi / 4, exact scaling)
+    t = fma(-q, 4.783776559169348e-19, t);         // pi/256 lo
     const double z = t * t;
-    double ps = fma(z, -1.9841269841269841e-04, 8.3333333333333332e-03);  // -1/5040, 1/120
-    double pc = fma(z, -1.3888888888888889e-03, 4.1666666666666664e-02);  // -1/720, 1/24
-    ps = fma(z, ps, -1.6666666666666666e-01);
-    pc = fma(z, pc, -0.5);
+    const double ps = fma(z, 8.3333333333333332e-03, -1.6666666666666666e-01);   // 1/120, -1/6
+    const double pc = fma(z, 4.166661437562094e-02, -0.5);                      // 1/24 - (pi/512)^2/720, -1/2
     const double sn = fma(t * z, ps, t);
     const double cs = fma(z, pc, 1.0);
     const double2 CS = tab[idx];

@@ -1210,7 +1210,7 @@ __global__ void math_selftest_kernel(uint64_t n, double xmax, double* err) {
     __shared__ double2 tab[SINCOS_TAB];
     for (int i = threadIdx.x; i < SINCOS_TAB; i += blockDim.x) {
         double sv, cv;
-        sincospi((double)i / 64.0, &sv, &cv);
+        sincospi((double)i / SINCOS_STEPS_PER_PI, &sv, &cv);
         tab[i] = make_double2(cv, sv);
     }
     __syncthreads();
