@@ -165,3 +165,24 @@ def test_capi_partition_and_loud_failure_without_gpu():
         with pytest.raises(_capi.Bemb200Error) as ei:
             bem.Context(0)
         assert ei.value.code == -2 and "no CPU fallback" in str(ei.value)
+
+
+def test_rust_shim_matches_the_build_and_the_header():
+    """The Rust FFI crate cannot be compiled here (no cargo): keep at least its build recipe and its extern
+    block in step with what this repository builds and exports."""
+    import re
+
+    from math_audio_b200 import _capi
+    from math_audio_b200.build import UNITS
+
+    root = Path(__file__).resolve().parent.parent
+    rs = (root / "rust" / "bem-b200-sys" / "build.rs").read_text()
+    units = {m.group(1): re.findall(r'"([^"]+)"', m.group(2)) for m in re.finditer(r'\("(\w+\.cu)", &\[(.*?)\]\)', rs)}
+    assert units == {k: list(v) for k, v in UNITS.items()}          # same translation units, same per-unit flags
+    assert "arch=compute_100a,code=sm_100a" in rs
+    lib_rs = (root / "rust" / "bem-b200-sys" / "src" / "lib.rs").read_text()
+    declared = set(re.findall(r"pub fn (bemb200_\w+)\(", lib_rs))
+    assert declared and declared <= set(_capi.SYMBOLS), declared - set(_capi.SYMBOLS)
+    header = (root / "include" / "bemb200.h").read_text()
+    for name in declared:
+        assert re.search(rf"\b{name}\(", header), name
