@@ -186,3 +186,26 @@ def test_rust_shim_matches_the_build_and_the_header():
     header = (root / "include" / "bemb200.h").read_text()
     for name in declared:
         assert re.search(rf"\b{name}\(", header), name
+
+
+def test_binding_arities_match_the_header():
+    """ctypes table (math_audio_b200/_capi.py) and the Rust extern block: same number of arguments as include/bemb200.h."""
+    import re
+
+    from math_audio_b200 import _capi
+
+    root = Path(__file__).resolve().parent.parent
+    header = re.sub(r"/\*.*?\*/", "", (root / "include" / "bemb200.h").read_text(), flags=re.S)
+
+    def nargs(s):
+        s = s.strip()
+        return 0 if s in ("", "void") else len([a for a in s.split(",") if a.strip()])
+
+    decl = {m.group(1): nargs(m.group(2)) for m in re.finditer(r"\b(bemb200_\w+)\s*\(([^)]*)\)\s*;", header)}
+    assert len(decl) > 40
+    for name, (_, argtypes) in _capi.SYMBOLS.items():
+        if name in decl:
+            assert len(argtypes) == decl[name], (name, len(argtypes), decl[name])
+    lib_rs = (root / "rust" / "bem-b200-sys" / "src" / "lib.rs").read_text()
+    for m in re.finditer(r"pub fn (bemb200_\w+)\(([^)]*)\)", lib_rs, flags=re.S):
+        assert nargs(m.group(2)) == decl[m.group(1)], m.group(1)
