@@ -14,6 +14,8 @@
 //   math-solvers/src/iterative/bicgstab.rs:19-215  BiCgstabConfig, BiCgstabSolution, bicgstab
 //   math-solvers/src/iterative/cgs.rs:12-155       CgsConfig, CgsSolution, cgs (+ solve_cgs / solve_with_ilu wrappers)
 //   math-solvers/src/direct/lu.rs:15-161         LuError, lu_solve
+//   math-bem/src/core/incident.rs:19-342         IncidentField (plane waves / point sources), compute_rhs{,_with_beta}
+//   math-bem/src/core/postprocess/pressure.rs:81-259,438-478  compute_scattered_field, compute_rcs
 //   math-bem/src/room_acoustics/solver.rs:412-748  RoomMesh, Source, build_bem_matrix_parallel, solve_bem_system,
 //                                                calculate_incident_field_derivative_parallel, calculate_field_pressure_bem_parallel
 // Shape mismatches throw std::invalid_argument (the reference panics); library failures throw
@@ -191,51 +193,104 @@ struct TbemSystem {  // tbem.rs:13-20; the matrix stays on the device behind the
     std::size_t num_dofs = 0;
 };
 
-// `nodes`: n_nodes x 3 row-major (Array2<f64>)
-inline TbemSystem build_tbem_system_with_beta(const Context& ctx, const std::vector<Element>& elements,
-                                              const std::vector<double>& nodes, const PhysicsParams& physics, Complex64 beta) {
-    const std::size_t n = elements.size();
-    std::vector<uint32_t> conn(4 * n, 0xFFFFFFFFu), dof(n, 0);
-    std::vector<uint8_t> etype(n), bc_len(n, 1), is_eval(n, 0);
-    std::vector<double> center(3 * n), normal(3 * n), area(n), bc_val(8 * n, 0.0);
-    std::vector<int32_t> bc_type(n, 0);
-    std::size_t ndof = 0;
-    for (std::size_t i = 0; i < n; ++i) {
-        const Element& e = elements[i];
-        etype[i] = e.element_type == ElementType::Tri3 ? 3 : 4;
-        if (e.connectivity.size() != etype[i]) throw std::invalid_argument("element connectivity does not match its type");
-        for (std::size_t v = 0; v < e.connectivity.size(); ++v) conn[4 * i + v] = static_cast<uint32_t>(e.connectivity[v]);
-        for (int d = 0; d < 3; ++d) { center[3 * i + d] = e.center[d]; normal[3 * i + d] = e.normal[d]; }
-        area[i] = e.area;
-        // get_bc_type_and_value(): tbem.rs:234-244
-        const BoundaryCondition& bc = e.boundary_condition;
-        std::vector<Complex64> vals;
-        switch (bc.kind) {
-            case BoundaryCondition::Velocity: case BoundaryCondition::VelocityWithAdmittance: bc_type[i] = 0; vals = bc.values; break;
-            case BoundaryCondition::Pressure: bc_type[i] = 1; vals = bc.values; break;
-            default: bc_type[i] = 2; vals = {Complex64(0.0, 0.0)}; break;
-        }
-        if (vals.empty() || vals.size() > 4) throw std::invalid_argument("boundary condition needs 1..4 values");
-        bc_len[i] = static_cast<uint8_t>(vals.size());
-        for (std::size_t k = 0; k < vals.size(); ++k) { bc_val[8 * i + 2 * k] = vals[k].real(); bc_val[8 * i + 2 * k + 1] = vals[k].imag(); }
-        is_eval[i] = e.property == ElementProperty::Evaluation;
-        if (!is_eval[i]) {
-            if (e.dof_addresses.empty()) throw std::invalid_argument("boundary element without dof address");
-            dof[i] = static_cast<uint32_t>(e.dof_addresses[0]);
-            ++ndof;
+// &[Element] + nodes flattened to the SoA arrays of `bemb200_mesh` (owns the storage the view points into)
+struct MeshSoA {
+    std::vector<uint32_t> conn, dof;
+    std::vector<uint8_t> etype, bc_len, is_eval;
+    std::vector<double> center, normal, area, bc_val;
+    std::vector<int32_t> bc_type;
+    std::size_t n_elem = 0, ndof = 0;
+    // `nodes`: n_nodes x 3 row-major (Array2<f64>)
+    MeshSoA(const std::vector<Element>& elements) {
+        const std::size_t n = elements.size();
+        n_elem = n;
+        conn.assign(4 * n, 0xFFFFFFFFu); dof.assign(n, 0);
+        etype.resize(n); bc_len.assign(n, 1); is_eval.assign(n, 0);
+        center.resize(3 * n); normal.resize(3 * n); area.resize(n); bc_val.assign(8 * n, 0.0);
+        bc_type.assign(n, 0);
+        for (std::size_t i = 0; i < n; ++i) {
+            const Element& e = elements[i];
+            etype[i] = e.element_type == ElementType::Tri3 ? 3 : 4;
+            if (e.connectivity.size() != etype[i]) throw std::invalid_argument("element connectivity does not match its type");
+            for (std::size_t v = 0; v < e.connectivity.size(); ++v) conn[4 * i + v] = static_cast<uint32_t>(e.connectivity[v]);
+            for (int d = 0; d < 3; ++d) { center[3 * i + d] = e.center[d]; normal[3 * i + d] = e.normal[d]; }
+            area[i] = e.area;
+            // get_bc_type_and_value(): tbem.rs:234-244
+            const BoundaryCondition& bc = e.boundary_condition;
+            std::vector<Complex64> vals;
+            switch (bc.kind) {
+                case BoundaryCondition::Velocity: case BoundaryCondition::VelocityWithAdmittance: bc_type[i] = 0; vals = bc.values; break;
+                case BoundaryCondition::Pressure: bc_type[i] = 1; vals = bc.values; break;
+                default: bc_type[i] = 2; vals = {Complex64(0.0, 0.0)}; break;
+            }
+            if (vals.empty() || vals.size() > 4) throw std::invalid_argument("boundary condition needs 1..4 values");
+            bc_len[i] = static_cast<uint8_t>(vals.size());
+            for (std::size_t k = 0; k < vals.size(); ++k) { bc_val[8 * i + 2 * k] = vals[k].real(); bc_val[8 * i + 2 * k + 1] = vals[k].imag(); }
+            is_eval[i] = e.property == ElementProperty::Evaluation;
+            if (!is_eval[i]) {
+                if (e.dof_addresses.empty()) throw std::invalid_argument("boundary element without dof address");
+                dof[i] = static_cast<uint32_t>(e.dof_addresses[0]);
+                ++ndof;
+            }
         }
     }
-    bemb200_mesh mesh{nodes.size() / 3, n, nodes.data(), conn.data(), etype.data(), center.data(), normal.data(), area.data(),
-                      bc_type.data(), bc_len.data(), bc_val.data(), dof.data(), is_eval.data()};
-    bemb200_physics phys{physics.wave_number, physics.harmonic_factor, physics.tau, physics.gamma()};
-    bemb200_matrix* m = nullptr;
-    check(bemb200_assemble(ctx.handle(), &mesh, &phys, beta.real(), beta.imag(), 0, ndof, &m), ctx.handle());
+    bemb200_mesh view(const std::vector<double>& nodes) const {
+        return bemb200_mesh{nodes.size() / 3, n_elem, nodes.data(), conn.data(), etype.data(), center.data(), normal.data(), area.data(),
+                            bc_type.data(), bc_len.data(), bc_val.data(), dof.data(), is_eval.data()};
+    }
+};
+inline bemb200_physics physics_abi(const PhysicsParams& p) { return bemb200_physics{p.wave_number, p.harmonic_factor, p.tau, p.gamma()}; }
+
+inline TbemSystem tbem_system_from_handle(const Context& ctx, bemb200_matrix* m, std::size_t ndof) {
     TbemSystem sys;
     sys.matrix = std::make_unique<DenseOperator>(ctx, m);
     sys.num_dofs = ndof;
     sys.rhs.resize(ndof);
     check(bemb200_rhs_download_full(m, reinterpret_cast<double*>(sys.rhs.data())), ctx.handle());
     return sys;
+}
+
+// `nodes`: n_nodes x 3 row-major (Array2<f64>)
+inline TbemSystem build_tbem_system_with_beta(const Context& ctx, const std::vector<Element>& elements,
+                                              const std::vector<double>& nodes, const PhysicsParams& physics, Complex64 beta) {
+    const MeshSoA soa(elements);
+    const bemb200_mesh mesh = soa.view(nodes);
+    const bemb200_physics phys = physics_abi(physics);
+    bemb200_matrix* m = nullptr;
+    check(bemb200_assemble(ctx.handle(), &mesh, &phys, beta.real(), beta.imag(), 0, soa.ndof, &m), ctx.handle());
+    return tbem_system_from_handle(ctx, m, soa.ndof);
+}
+
+// Frequency-independent device copy of the mesh: staged once, reused by every frequency of a sweep and by the
+// right-hand-side / field kernels below (no counterpart in the reference, which re-reads `&[Element]` per call).
+class StagedMesh {
+public:
+    StagedMesh(const Context& ctx, const std::vector<Element>& elements, const std::vector<double>& nodes) : ctx_(&ctx) {
+        const MeshSoA soa(elements);
+        const bemb200_mesh mesh = soa.view(nodes);
+        check(bemb200_mesh_stage(ctx.handle(), &mesh, &h_), ctx.handle());
+        num_dofs_ = soa.ndof;
+    }
+    ~StagedMesh() { bemb200_staged_mesh_free(h_); }
+    StagedMesh(const StagedMesh&) = delete;
+    StagedMesh& operator=(const StagedMesh&) = delete;
+    bemb200_staged_mesh* handle() const { return h_; }
+    const Context& context() const { return *ctx_; }
+    std::size_t num_dofs() const { return num_dofs_; }
+    double dg_dn_sign(double wave_number) const { return bemb200_dg_dn_sign(h_, wave_number); }  // tbem.rs:108-123
+
+private:
+    const Context* ctx_;
+    bemb200_staged_mesh* h_ = nullptr;
+    std::size_t num_dofs_ = 0;
+};
+// build_tbem_system_with_beta on a staged mesh (all rows)
+inline TbemSystem build_tbem_system_with_beta(const StagedMesh& mesh, const PhysicsParams& physics, Complex64 beta) {
+    const bemb200_physics phys = physics_abi(physics);
+    bemb200_matrix* m = nullptr;
+    check(bemb200_assemble_staged(mesh.context().handle(), mesh.handle(), &phys, beta.real(), beta.imag(), 0, mesh.num_dofs(), &m),
+          mesh.context().handle());
+    return tbem_system_from_handle(mesh.context(), m, mesh.num_dofs());
 }
 inline TbemSystem build_tbem_system(const Context& ctx, const std::vector<Element>& el, const std::vector<double>& nodes,
                                     const PhysicsParams& ph) {  // tbem.rs:45-51
@@ -253,6 +308,13 @@ inline double apply_row_sum_correction(TbemSystem& system) {  // tbem.rs:500-520
     double avg = 0.0;
     check(bemb200_row_sum_correction(system.matrix->handle(), &avg), system.matrix->context().handle());
     return avg;
+}
+
+inline std::pair<TbemSystem, double> build_tbem_system_corrected(const Context& ctx, const std::vector<Element>& el,
+                                                                 const std::vector<double>& nodes, const PhysicsParams& ph) {  // tbem.rs:526-534
+    TbemSystem system = build_tbem_system(ctx, el, nodes, ph);
+    const double avg = apply_row_sum_correction(system);
+    return {std::move(system), avg};
 }
 
 // ---- GMRES -------------------------------------------------------------------------------------------------
@@ -383,6 +445,103 @@ inline CgsSolution solve_cgs(const DenseOperator& op, const std::vector<Complex6
 // the reference's "ILU" wrappers run unpreconditioned CGS on the dense matrix (fmm_interface.rs:389-417, 441-447)
 inline CgsSolution solve_with_ilu(const DenseOperator& op, const std::vector<Complex64>& b, const CgsConfig& c) { return cgs(op, b, c); }
 inline CgsSolution solve_tbem_with_ilu(const DenseOperator& op, const std::vector<Complex64>& b, const CgsConfig& c) { return cgs(op, b, c); }
+
+inline BiCgstabSolution solve_bicgstab(const DenseOperator& op, const std::vector<Complex64>& b, const BiCgstabConfig& c) {  // fmm_interface.rs:369
+    return bicgstab(op, b, c);
+}
+
+// ---- several right-hand sides (BASELINE config 5): what the reference does with a loop of gmres() calls ----------
+// b_all: nrhs vectors of num_rows, each contiguous; one GmresSolution per right-hand side, semantics of gmres() each
+inline std::vector<GmresSolution> gmres_batched(const DenseOperator& op, const std::vector<Complex64>& b_all, std::size_t nrhs,
+                                                const GmresConfig& config) {
+    const std::size_t n = op.num_rows();
+    if (nrhs == 0 || b_all.size() != nrhs * n) throw std::invalid_argument("gmres_batched: b_all must hold nrhs vectors of num_rows");
+    std::vector<Complex64> x_all(nrhs * n);
+    std::vector<bemb200_gmres_info> infos(nrhs);
+    check(bemb200_gmres_batched(op.handle(), reinterpret_cast<const double*>(b_all.data()), static_cast<uint32_t>(nrhs),
+                                static_cast<uint32_t>(config.max_iterations), static_cast<uint32_t>(config.restart), config.tolerance,
+                                reinterpret_cast<double*>(x_all.data()), infos.data(), nullptr, nullptr),
+          op.context().handle());
+    std::vector<GmresSolution> out(nrhs);
+    for (std::size_t s = 0; s < nrhs; ++s) {
+        out[s].x.assign(x_all.begin() + s * n, x_all.begin() + (s + 1) * n);
+        out[s].iterations = infos[s].iterations; out[s].restarts = infos[s].restarts;
+        out[s].residual = infos[s].residual; out[s].converged = infos[s].converged != 0;
+    }
+    return out;
+}
+// Y = A X for nrhs vectors at once (tensor-core block matvec); x_all / result: nrhs contiguous vectors
+inline std::vector<Complex64> apply_block(const DenseOperator& op, const std::vector<Complex64>& x_all, std::size_t nrhs) {
+    if (nrhs == 0 || x_all.size() != nrhs * op.num_cols()) throw std::invalid_argument("apply_block: x_all must hold nrhs vectors of num_cols");
+    std::vector<Complex64> y_all(nrhs * op.num_rows());
+    check(bemb200_apply_block(op.handle(), reinterpret_cast<const double*>(x_all.data()), static_cast<uint32_t>(nrhs),
+                              reinterpret_cast<double*>(y_all.data()), nullptr),
+          op.context().handle());
+    return y_all;
+}
+
+// ---- incident field, field evaluation, RCS on the staged mesh (incident.rs, postprocess/pressure.rs) ------------------
+struct IncidentField {  // incident.rs:19-84: plane waves (unit direction, amplitude) and point sources (position, strength)
+    std::vector<int32_t> kinds;
+    std::vector<double> vecs, amps;
+    static IncidentField plane_wave(const double dir[3], double amplitude = 1.0) {  // incident.rs:62-76 (normalised; zero -> -z)
+        const double len = std::sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+        IncidentField f;
+        f.kinds = {0};
+        if (len > 1e-10) f.vecs = {dir[0] / len, dir[1] / len, dir[2] / len};
+        else f.vecs = {0.0, 0.0, -1.0};
+        f.amps = {amplitude, 0.0};
+        return f;
+    }
+    static IncidentField plane_wave_z() { const double d[3] = {0.0, 0.0, 1.0}; return plane_wave(d, 1.0); }       // incident.rs:46-51
+    static IncidentField plane_wave_neg_z() { const double d[3] = {0.0, 0.0, -1.0}; return plane_wave(d, 1.0); }  // incident.rs:54-59
+    static IncidentField point_source(const double pos[3], double strength = 1.0) {  // incident.rs:79-84
+        IncidentField f;
+        f.kinds = {1};
+        f.vecs = {pos[0], pos[1], pos[2]};
+        f.amps = {strength, 0.0};
+        return f;
+    }
+    // compute_rhs_with_beta (incident.rs:317-342) at the staged collocation points: -(gamma p_inc + beta tau dp_inc/dn)
+    std::vector<Complex64> compute_rhs_with_beta(const StagedMesh& mesh, const PhysicsParams& physics, Complex64 beta) const {
+        const bemb200_physics phys = physics_abi(physics);
+        std::vector<Complex64> rhs(mesh.num_dofs());
+        check(bemb200_incident_rhs(mesh.handle(), &phys, beta.real(), beta.imag(), static_cast<uint32_t>(kinds.size()), kinds.data(),
+                                   vecs.data(), amps.data(), reinterpret_cast<double*>(rhs.data()), nullptr),
+              mesh.context().handle());
+        return rhs;
+    }
+    std::vector<Complex64> compute_rhs(const StagedMesh& mesh, const PhysicsParams& physics, bool use_burton_miller) const {  // incident.rs:293-315
+        return compute_rhs_with_beta(mesh, physics, use_burton_miller ? physics.burton_miller_beta() : Complex64(0.0, 0.0));
+    }
+};
+// compute_scattered_field (pressure.rs:81-259): eval_points n_eval x 3 row-major; surface_velocity may be empty
+inline std::vector<Complex64> compute_scattered_field(const StagedMesh& mesh, const std::vector<double>& eval_points,
+                                                      const std::vector<Complex64>& surface_pressure,
+                                                      const std::vector<Complex64>& surface_velocity, const PhysicsParams& physics) {
+    if (eval_points.size() % 3 != 0) throw std::invalid_argument("compute_scattered_field: eval_points must be n x 3");
+    if (surface_pressure.size() != mesh.num_dofs() || (!surface_velocity.empty() && surface_velocity.size() != mesh.num_dofs()))
+        throw std::invalid_argument("compute_scattered_field: surface vectors must have num_dofs entries");
+    const bemb200_physics phys = physics_abi(physics);
+    std::vector<Complex64> out(eval_points.size() / 3);
+    check(bemb200_scattered_field(mesh.handle(), &phys, out.size(), eval_points.data(), reinterpret_cast<const double*>(surface_pressure.data()),
+                                  surface_velocity.empty() ? nullptr : reinterpret_cast<const double*>(surface_velocity.data()),
+                                  reinterpret_cast<double*>(out.data())),
+          mesh.context().handle());
+    return out;
+}
+// compute_rcs (pressure.rs:438-478) for n x 3 unit directions
+inline std::vector<double> compute_rcs(const StagedMesh& mesh, const std::vector<Complex64>& surface_pressure,
+                                       const std::vector<double>& directions, const PhysicsParams& physics) {
+    if (directions.size() % 3 != 0) throw std::invalid_argument("compute_rcs: directions must be n x 3");
+    if (surface_pressure.size() != mesh.num_dofs()) throw std::invalid_argument("compute_rcs: surface_pressure must have num_dofs entries");
+    const bemb200_physics phys = physics_abi(physics);
+    std::vector<double> out(directions.size() / 3);
+    check(bemb200_compute_rcs(mesh.handle(), &phys, static_cast<uint32_t>(out.size()), directions.data(),
+                              reinterpret_cast<const double*>(surface_pressure.data()), out.data()),
+          mesh.context().handle());
+    return out;
+}
 
 struct LuError : std::runtime_error {  // lu.rs:15-21
     enum Kind { SingularMatrix, DimensionMismatch } kind;

@@ -30,6 +30,11 @@ long orc_assemble(const orc_mesh* m, double k, double harmonic, double tau, doub
                   uint64_t row_end, double* A_out, double* rhs_out, int nthreads);
 void orc_cgs(const double* A, uint64_t n, const double* b, uint32_t max_iterations, double tolerance, double* x_out,
              orc_gmres_info* info, int nthreads);
+void orc_incident_rhs(int kind, const double* vec3, double amp_re, double amp_im, const double* centers, const double* normals,
+                      uint64_t n, double k, double tau, double beta_re, double beta_im, double* rhs_io, double* pinc_out, int accumulate);
+void orc_compute_rcs(const orc_mesh* m, const double* surf_p, const double* dirs, uint64_t n_dirs, double k, double* out);
+void orc_scattered_field(const orc_mesh* m, const double* eval_pts, uint64_t n_eval, const double* surf_p, const double* surf_v_or_null,
+                         double k, double harmonic, double* out, int nthreads);
 void orc_bicgstab(const double* A, uint64_t n, const double* b, uint32_t max_iterations, double tolerance, double* x_out,
                   orc_gmres_info* info, int nthreads);
 int orc_lu_solve(const double* A, uint64_t n, const double* b, double* x_out);
@@ -204,6 +209,50 @@ int main() {
         for (std::size_t e = 0; e < n; ++e) { num += std::norm(s.x[e] - xo[e]); den += std::norm(xo[e]); }
         CHECK(s.converged && s.iterations == info.iterations && std::sqrt(num / den) < 1e-8);
         std::printf("sphere N=%zu entry_err=%.2e gmres_it=%zu dx=%.2e\n", n, worst, s.iterations, std::sqrt(num / den));
+        // the staged-mesh neighbours of the path (incident.rs, pressure.rs) through the C++ mirror, against the oracle
+        StagedMesh staged(ctx, elements, nodes);
+        CHECK(staged.num_dofs() == n && staged.dg_dn_sign(k) == -1.0);       // k * |centre| = 1 >= 0.5 (tbem.rs:118-123)
+        TbemSystem sys2 = build_tbem_system_with_beta(staged, physics, beta);
+        std::vector<Complex64> A2 = sys2.matrix->rows(0, n);
+        bool same = true;
+        for (std::size_t i = 0; i < n * n; ++i) same = same && A2[i] == A[i];
+        CHECK(same);                                                          // staged and one-shot assembly: same kernels, same bits
+        std::vector<Complex64> bd = IncidentField::plane_wave_z().compute_rhs_with_beta(staged, physics, beta), bo(n), pinc(n);
+        orc_incident_rhs(0, std::vector<double>{0.0, 0.0, 1.0}.data(), 1.0, 0.0, cen.data(), nor.data(), n, k, 1.0, beta.real(), beta.imag(),
+                         reinterpret_cast<double*>(bo.data()), reinterpret_cast<double*>(pinc.data()), 0);
+        double eb = 0, nb = 0;
+        for (std::size_t e = 0; e < n; ++e) { eb = std::fmax(eb, std::abs(bd[e] - bo[e])); nb = std::fmax(nb, std::abs(bo[e])); }
+        CHECK(eb < 1e-13 * nb);
+        const double src[3] = {0.4, -0.1, 0.3};
+        std::vector<Complex64> bp = IncidentField::point_source(src, 2.0).compute_rhs_with_beta(staged, physics, beta);
+        orc_incident_rhs(1, src, 2.0, 0.0, cen.data(), nor.data(), n, k, 1.0, beta.real(), beta.imag(), reinterpret_cast<double*>(bo.data()),
+                         reinterpret_cast<double*>(pinc.data()), 0);
+        eb = 0; nb = 0;
+        for (std::size_t e = 0; e < n; ++e) { eb = std::fmax(eb, std::abs(bp[e] - bo[e])); nb = std::fmax(nb, std::abs(bo[e])); }
+        CHECK(eb < 1e-13 * nb);
+        std::vector<double> pts = {0.0, 0.0, 1.0, 0.7, 0.1, -0.4, -0.3, 0.9, 0.2};
+        std::vector<Complex64> fd = compute_scattered_field(staged, pts, s.x, {}, physics), fo(3);
+        orc_scattered_field(&om, pts.data(), 3, reinterpret_cast<const double*>(s.x.data()), nullptr, k, 1.0, reinterpret_cast<double*>(fo.data()), 0);
+        for (int i = 0; i < 3; ++i) CHECK(std::abs(fd[i] - fo[i]) < 1e-11 * std::abs(fo[i]));
+        std::vector<double> dirs = {0.0, 0.0, 1.0, 0.0, 0.0, -1.0, 0.6, 0.0, 0.8};
+        std::vector<double> rd = compute_rcs(staged, s.x, dirs, physics), ro(3);
+        orc_compute_rcs(&om, reinterpret_cast<const double*>(s.x.data()), dirs.data(), 3, k, ro.data());
+        for (int i = 0; i < 3; ++i) CHECK(std::fabs(rd[i] - ro[i]) < 1e-10 * ro[i]);
+        // three right-hand sides in lockstep (block matvec) = three gmres() calls
+        std::vector<Complex64> ball(3 * n);
+        for (std::size_t e = 0; e < n; ++e) { ball[e] = b[e]; ball[n + e] = bp[e]; ball[2 * n + e] = b[e] * Complex64(0.0, 2.0) + bp[e]; }
+        std::vector<GmresSolution> sols = gmres_batched(*system.matrix, ball, 3, GmresConfig{1000, 50, 1e-10, 0});
+        CHECK(sols.size() == 3 && sols[0].converged && sols[1].converged && sols[2].converged && sols[0].iterations == s.iterations);
+        double e0 = 0;
+        for (std::size_t e = 0; e < n; ++e) e0 += std::norm(sols[0].x[e] - s.x[e]);
+        CHECK(std::sqrt(e0 / den) < 1e-8);
+        std::vector<Complex64> yall = apply_block(*system.matrix, ball, 3), y1 = system.matrix->apply(bp);
+        double ey = 0, ny = 0;
+        for (std::size_t e = 0; e < n; ++e) { ey += std::norm(yall[n + e] - y1[e]); ny += std::norm(y1[e]); }
+        CHECK(std::sqrt(ey / ny) < 1e-12);
+        BiCgstabSolution sb2 = solve_bicgstab(*system.matrix, b, BiCgstabConfig{1000, 1e-10, 0});
+        CHECK(sb2.converged);
+        std::printf("staged neighbours ok: rhs %.1e field/rcs ok, batched it=%zu/%zu/%zu\n", eb / nb, sols[0].iterations, sols[1].iterations, sols[2].iterations);
     }
     {  // bicgstab.rs:196-219 test_bicgstab_simple, lu.rs:178-219
         std::vector<Complex64> a = {{4, 0}, {1, 0}, {1, 0}, {3, 0}};
