@@ -66,6 +66,18 @@ extern "C" {
                             factor_ms: *mut f64) -> c_int;
     pub fn bemb200_compute_rcs(sm: *const bemb200_staged_mesh, phys: *const bemb200_physics, n_dirs: u32, dirs: *const f64,
                                surface_pressure: *const f64, rcs_out: *mut f64) -> c_int;
+    pub fn bemb200_gmres_preconditioned(m: *const bemb200_matrix, inv_diag: *const f64, b: *const f64, x0: *const f64,
+                                        max_iterations: u32, restart: u32, tolerance: f64, x_out: *mut f64,
+                                        info: *mut bemb200_gmres_info) -> c_int;
+    pub fn bemb200_matrix_diagonal(m: *const bemb200_matrix, out: *mut f64) -> c_int;
+    pub fn bemb200_gmres_batched(m: *const bemb200_matrix, b_all: *const f64, nrhs: u32, max_iterations: u32, restart: u32,
+                                 tolerance: f64, x_all: *mut f64, infos: *mut bemb200_gmres_info, block_matvec_ms: *mut f64,
+                                 block_matvecs: *mut u64) -> c_int;
+    pub fn bemb200_incident_rhs(sm: *const bemb200_staged_mesh, phys: *const bemb200_physics, beta_re: f64, beta_im: f64,
+                                n_sources: u32, kinds: *const i32, vecs: *const f64, amps: *const f64, rhs_host: *mut f64,
+                                rhs_dev: *mut f64) -> c_int;
+    pub fn bemb200_scattered_field(sm: *const bemb200_staged_mesh, phys: *const bemb200_physics, n_eval: u64, eval_pts: *const f64,
+                                   surface_pressure: *const f64, surface_velocity: *const f64, out: *mut f64) -> c_int;
     pub fn bemb200_gmres(m: *const bemb200_matrix, b: *const f64, x0: *const f64, max_iterations: u32, restart: u32,
                          tolerance: f64, x_out: *mut f64, info: *mut bemb200_gmres_info) -> c_int;
 }
@@ -162,6 +174,47 @@ impl GpuDenseOperator {
         assert_eq!(rc, 0, "libbemb200: {}", last_error(std::ptr::null()));
         GmresSolution { x, iterations: info.iterations as usize, restarts: info.restarts as usize,
                         residual: info.residual, converged: info.converged != 0 }
+    }
+    /// `gmres_preconditioned(operator, &DiagonalPreconditioner::from_diagonal(&diag), b, config)` (gmres.rs:282,
+    /// preconditioners/diagonal.rs:40-50) with the Jacobi preconditioner of the matrix itself; `jacobi = false`
+    /// is `IdentityPreconditioner` (traits.rs:377-385).
+    pub fn gmres_preconditioned(&self, jacobi: bool, b: &Array1<Complex64>, config: &GmresConfig<f64>) -> GmresSolution<Complex64> {
+        assert_eq!(b.len(), self.num_rows(), "Vector lengths must match");
+        let n = b.len();
+        let mut inv = Array1::<Complex64>::from_elem(n, Complex64::new(1.0, 0.0));
+        if jacobi {
+            let mut d = Array1::<Complex64>::zeros(n);
+            let rc = unsafe { bemb200_matrix_diagonal(self.0, d.as_mut_ptr() as *mut f64) };
+            assert_eq!(rc, 0, "libbemb200: {}", last_error(std::ptr::null()));
+            for i in 0..n { if d[i].norm() > 1e-30 { inv[i] = d[i].inv(); } }   // diagonal.rs:29-35
+        }
+        let mut x = Array1::<Complex64>::zeros(n);
+        let mut info = bemb200_gmres_info::default();
+        let pinv = if jacobi { inv.as_ptr() as *const f64 } else { std::ptr::null() };
+        let rc = unsafe { bemb200_gmres_preconditioned(self.0, pinv, b.as_ptr() as *const f64, std::ptr::null(),
+                                                       config.max_iterations as u32, config.restart as u32, config.tolerance,
+                                                       x.as_mut_ptr() as *mut f64, &mut info) };
+        assert_eq!(rc, 0, "libbemb200: {}", last_error(std::ptr::null()));
+        GmresSolution { x, iterations: info.iterations as usize, restarts: info.restarts as usize,
+                        residual: info.residual, converged: info.converged != 0 }
+    }
+    /// Several right-hand sides at once (what the reference does with a loop of `gmres` calls): the solves advance in
+    /// lockstep on one tensor-core block matvec; each result has the semantics of its own `gmres` call.  At most 32.
+    pub fn gmres_batched(&self, bs: &[Array1<Complex64>], config: &GmresConfig<f64>) -> Vec<GmresSolution<Complex64>> {
+        let n = self.num_rows();
+        let nrhs = bs.len();
+        let mut b_all = Vec::<Complex64>::with_capacity(nrhs * n);
+        for b in bs { assert_eq!(b.len(), n, "Vector lengths must match"); b_all.extend(b.iter().cloned()); }
+        let mut x_all = vec![Complex64::new(0.0, 0.0); nrhs * n];
+        let mut infos = vec![bemb200_gmres_info::default(); nrhs];
+        let rc = unsafe { bemb200_gmres_batched(self.0, b_all.as_ptr() as *const f64, nrhs as u32, config.max_iterations as u32,
+                                                config.restart as u32, config.tolerance, x_all.as_mut_ptr() as *mut f64,
+                                                infos.as_mut_ptr(), std::ptr::null_mut(), std::ptr::null_mut()) };
+        assert_eq!(rc, 0, "libbemb200: {}", last_error(std::ptr::null()));
+        (0..nrhs).map(|s| GmresSolution {
+            x: Array1::from(x_all[s * n..(s + 1) * n].to_vec()), iterations: infos[s].iterations as usize,
+            restarts: infos[s].restarts as usize, residual: infos[s].residual, converged: infos[s].converged != 0,
+        }).collect()
     }
     /// `bicgstab(operator, b, config)` (bicgstab.rs:53), the solver of `BemSolver::solve_dense_system`.
     pub fn bicgstab(&self, b: &Array1<Complex64>, config: &BiCgstabConfig<f64>) -> BiCgstabSolution<Complex64> {
