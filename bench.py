@@ -252,7 +252,7 @@ def run_native(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libbemb200 has no CPU fallback (use --impl reference for the CPU arm)")
     if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
-        os.environ.pop("NCCL_DEBUG")  # keep NCCL's version banner off stdout (ONE JSON line)  # keep NCCL's version banner off stdout: ONE JSON line only
+        os.environ.pop("NCCL_DEBUG")  # keep NCCL's version banner off stdout: ONE JSON line only
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
