@@ -656,3 +656,40 @@ def solve_with_ilu(matrix, b: np.ndarray, config: CgsConfig, ctx: Optional[Conte
 
 def solve_tbem_with_ilu(matrix, b: np.ndarray, config: CgsConfig, ctx: Optional[Context] = None) -> CgsSolution:  # fmm_interface.rs:441-447
     return solve_with_ilu(matrix, b, config, ctx=ctx)
+
+
+# ---- mesh sizing helpers of the same module (fmm_interface.rs:543-602): host scalars --------------------------------
+def recommended_mesh_resolution(frequency: float, speed_of_sound: float, elements_per_wavelength: int) -> float:
+    """fmm_interface.rs:544-551: elements per metre for `elements_per_wavelength` elements per wavelength."""
+    wavelength = speed_of_sound / frequency
+    return float(elements_per_wavelength) / wavelength
+
+
+def mesh_resolution_for_frequency_range(min_freq: float, max_freq: float, speed_of_sound: float, elements_per_wavelength: int) -> float:
+    """fmm_interface.rs:554-561: the highest frequency decides (min_freq is unused, as in the reference)."""
+    return recommended_mesh_resolution(max_freq, speed_of_sound, elements_per_wavelength)
+
+
+def estimate_element_count(room_dimensions, mesh_resolution: float) -> int:
+    """fmm_interface.rs:564-570: ceil(surface area of the box / element area)."""
+    w, d, h = room_dimensions
+    surface_area = 2.0 * (w * d + w * h + d * h)
+    element_size = 1.0 / mesh_resolution
+    return int(np.ceil(surface_area / (element_size * element_size)))
+
+
+@dataclass
+class AdaptiveMeshConfig:
+    """fmm_interface.rs:573-602."""
+
+    base_resolution: float
+    source_refinement: float
+    source_refinement_radius: float
+
+    @staticmethod
+    def for_frequency_range(min_freq: float, max_freq: float) -> "AdaptiveMeshConfig":
+        return AdaptiveMeshConfig(mesh_resolution_for_frequency_range(min_freq, max_freq, 343.0, 6), 1.5, 0.5)
+
+    @staticmethod
+    def from_resolution(resolution: float) -> "AdaptiveMeshConfig":
+        return AdaptiveMeshConfig(resolution, 1.0, 0.0)

@@ -139,3 +139,16 @@ def test_identity_and_diagonal_preconditioner(orc):
     out = bem.DiagonalPreconditioner.from_diagonal(np.diag(A)).apply(np.array([4.0, 4.0], dtype=np.complex128))
     assert np.allclose(out.real, [1.0, 2.0], atol=1e-10)
     assert np.allclose(pre.inv_diag, orc.inverse_diagonal(np.array([2.0, 4.0, 1.0])))
+
+
+# ---- fmm_interface.rs:543-602 (mesh sizing helpers beside DenseOperator) ---------------------------------------------
+def test_mesh_sizing_helpers():
+    assert abs(bem.recommended_mesh_resolution(343.0, 343.0, 6) - 6.0) < 1e-12          # wavelength 1 m
+    assert abs(bem.recommended_mesh_resolution(1000.0, 343.0, 8) - 8.0 / 0.343) < 1e-12
+    assert bem.mesh_resolution_for_frequency_range(20.0, 500.0, 343.0, 6) == bem.recommended_mesh_resolution(500.0, 343.0, 6)
+    assert bem.estimate_element_count((5.0, 4.0, 3.0), 2.0) == 376                      # 94 m^2 / 0.25 m^2
+    assert bem.estimate_element_count((1.0, 1.0, 1.0), 1.5) == 14                       # ceil(6 * 2.25)
+    cfg = bem.AdaptiveMeshConfig.for_frequency_range(20.0, 200.0)
+    assert abs(cfg.base_resolution - 6.0 * 200.0 / 343.0) < 1e-12 and (cfg.source_refinement, cfg.source_refinement_radius) == (1.5, 0.5)
+    fixed = bem.AdaptiveMeshConfig.from_resolution(4.0)
+    assert (fixed.base_resolution, fixed.source_refinement, fixed.source_refinement_radius) == (4.0, 1.0, 0.0)
