@@ -487,6 +487,10 @@ int bemb200_assemble_staged(bemb200_ctx* ctx, const bemb200_staged_mesh* sm, con
         m->near_cap = count + 1024;
         ASM_CUDA(cudaMalloc((void**)&m->near_list, (size_t)m->near_cap * sizeof(uint2)));
     }
+    if (count > m->near_cap) {  // still overflowing after the regrown second pass: never index past the list
+        if (!*inout) bemb200_matrix_free(m);
+        return set_error(ctx, BEMB200_ENOMEM, "near-field pair list overflowed twice (pathological mesh: more near pairs than the list can hold)");
+    }
     ASM_CUDA(launch_near_list(dm, ph, row_begin, m->A, dm.n, m->rhs, m->near_list, count, s));
     ASM_CUDA(launch_special(dm, ph, row_begin, row_end, m->A, dm.n, m->rhs, s));
     ASM_CUDA(launch_self(dm, ph, row_begin, row_end, m->A, dm.n, m->rhs, s));

@@ -323,7 +323,7 @@ cudaError_t launch_far_t(const DeviceMesh& m, const Phys& ph, uint64_t row_begin
                          uint2* near_list, unsigned int near_cap, unsigned int* near_count, int bg, unsigned int* work_counter,
                          FarRelaunch* relaunch, cudaStream_t s) {
     const bool bimag = (ph.beta.re == 0.0);
-    const int minb = env_int("BEMB200_FAR_MINB", 4);
+    static const int minb = env_int("BEMB200_FAR_MINB", 4);  // read once, not on every launch
 #define FAR_DISPATCH(B, M) \
     return launch_far_v<NQ, B, M>(m, ph, row_begin, row_end, A, lda, near_list, near_cap, near_count, bg, work_counter, relaunch, s)
     if (bimag) {

@@ -116,12 +116,12 @@ extern "C" int bemb200_gmres_batched(const bemb200_matrix* cm, const double* b_a
     std::vector<double> scal_h(S);
     std::vector<int> cnt_h(S);
     std::vector<unsigned char> active_h(S);
-    cudaEvent_t e0, e1;
-    BEMB_CUDA(ctx, cudaEventCreate(&e0));
-    BEMB_CUDA(ctx, cudaEventCreate(&e1));
+    struct EvGuard { cudaEvent_t a = nullptr, b = nullptr; ~EvGuard() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); } } evg;
+    BEMB_CUDA(ctx, cudaEventCreate(&evg.a));  // the guard owns both events from the start: nothing leaks if the second create fails
+    BEMB_CUDA(ctx, cudaEventCreate(&evg.b));
+    const cudaEvent_t e0 = evg.a, e1 = evg.b;
     double mv_ms = 0.0;
     uint64_t mv_count = 0;
-    struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } evg{e0, e1};
 
     BEMB_CUDA(ctx, cudaMemsetAsync(Vall, 0, (size_t)S * vstride * sizeof(cplx), s));
     BEMB_CUDA(ctx, cudaMemsetAsync(Xblk, 0, npad * S * sizeof(cplx), s));
@@ -326,10 +326,10 @@ extern "C" int bemb200_apply_block(const bemb200_matrix* cm, const double* x_all
     BEMB_CUDA(ctx, buf.alloc(&Xb, nc * S));
     BEMB_CUDA(ctx, buf.alloc(&Yb, nr * S));
     BEMB_CUDA(ctx, buf.alloc(&stage, (size_t)nrhs * (nc > nr ? nc : nr)));
-    cudaEvent_t e0, e1;
-    BEMB_CUDA(ctx, cudaEventCreate(&e0));
-    BEMB_CUDA(ctx, cudaEventCreate(&e1));
-    struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } evg{e0, e1};
+    struct EvGuard { cudaEvent_t a = nullptr, b = nullptr; ~EvGuard() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); } } evg;
+    BEMB_CUDA(ctx, cudaEventCreate(&evg.a));
+    BEMB_CUDA(ctx, cudaEventCreate(&evg.b));
+    const cudaEvent_t e0 = evg.a, e1 = evg.b;
     BEMB_CUDA(ctx, cudaMemcpyAsync(stage, x_all, (size_t)nrhs * nc * sizeof(cplx), cudaMemcpyHostToDevice, s));
     BEMB_CUDA(ctx, launch_interleave(stage, Xb, nc, (int)nrhs, S, 1, s));
     BEMB_CUDA(ctx, launch_zgemm_block(m->A, nc, nloc, nc, Xb, Yb, S, s));  // warm-up

@@ -46,9 +46,7 @@ struct GmresWorkspace {
     uint32_t ldh_slot = 0;
 };
 
-namespace bemb {
-void free_workspace(bemb200_matrix* m) {
-    GmresWorkspace* ws = m->ws;
+static void destroy_workspace(GmresWorkspace* ws) {
     if (!ws) return;
     cudaFree(ws->V); cudaFree(ws->w); cudaFree(ws->r); cudaFree(ws->xin); cudaFree(ws->bin); cudaFree(ws->xout);
     cudaFree(ws->hcol_d); cudaFree(ws->ycoef_d); cudaFree(ws->scal_d); cudaFree(ws->lmat_d);
@@ -56,9 +54,16 @@ void free_workspace(bemb200_matrix* m) {
     if (ws->scal_h) cudaFreeHost(ws->scal_h);
     if (ws->ev0) cudaEventDestroy(ws->ev0);
     if (ws->ev1) cudaEventDestroy(ws->ev1);
-    for (auto& v : {ws->it_ev0, ws->it_ev1, ws->it_done})
-        for (cudaEvent_t e : v) cudaEventDestroy(e);
+    for (auto* v : {&ws->it_ev0, &ws->it_ev1, &ws->it_done})
+        for (cudaEvent_t e : *v)
+            if (e) cudaEventDestroy(e);
     delete ws;
+    cudaGetLastError();
+}
+
+namespace bemb {
+void free_workspace(bemb200_matrix* m) {
+    destroy_workspace(m->ws);
     m->ws = nullptr;
 }
 }  // namespace bemb
@@ -119,12 +124,17 @@ static int ensure_peer_exchange(bemb200_ctx* ctx, uint64_t npad) {
     if (px.err_h) *px.err_h = 0;
     cudaGetLastError();
     // exchange {handle, ok} through the communicator
-    struct Slot { cudaIpcMemHandle_t h; int ok; int pad[3]; };
+    struct Slot { cudaIpcMemHandle_t h; int ok; int pad[3]; char uuid[16]; };
     static_assert(sizeof(Slot) % 16 == 0, "slot alignment");
     std::vector<Slot> all(P);
     Slot me{};
     me.h = mine;
     me.ok = ok;
+    {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess) std::memcpy(me.uuid, prop.uuid.bytes, 16);
+        else { cudaGetLastError(); me.ok = ok = 0; }
+    }
     unsigned char* stage = nullptr;
     BEMB_CUDA(ctx, cudaMalloc((void**)&stage, sizeof(Slot) * P));
     BEMB_CUDA(ctx, cudaMemcpyAsync(stage + sizeof(Slot) * ctx->rank, &me, sizeof(Slot), cudaMemcpyHostToDevice, ctx->stream));
@@ -133,6 +143,11 @@ static int ensure_peer_exchange(bemb200_ctx* ctx, uint64_t npad) {
     BEMB_CUDA(ctx, cudaMemcpyAsync(all.data(), stage, sizeof(Slot) * P, cudaMemcpyDeviceToHost, ctx->stream));
     BEMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     for (int p = 0; p < P; ++p) ok &= all[p].ok;
+    // two ranks on ONE device cannot run the spinning consumer and the producer ZGEMV side by side (separate
+    // processes time-slice a GPU): such a job keeps the NCCL all-gather
+    for (int p = 0; p < P; ++p)
+        for (int q = p + 1; q < P; ++q)
+            if (std::memcmp(all[p].uuid, all[q].uuid, 16) == 0) ok = 0;
     if (ok) {
         for (int p = 0; p < P; ++p) {
             if (p == ctx->rank) { px.base[p] = px.local; continue; }
@@ -165,12 +180,11 @@ static inline uint4* px_work(const PeerExchange& px, int p, unsigned long long e
     return reinterpret_cast<uint4*>(px.base[p] + PX_HEADER) + (epoch & 1ull) * 2 * px.npad;
 }
 
-static int ensure_workspace(bemb200_matrix* m, uint32_t restart) {
+// The workspace is built in a local object and attached to the matrix only when EVERY allocation has
+// succeeded: a failed attempt (OOM next to a slab that nearly fills HBM is realistic) leaves the handle
+// without a workspace instead of a half-built one that later calls would dereference.
+static int build_workspace(bemb200_matrix* m, uint32_t restart, GmresWorkspace* ws) {
     bemb200_ctx* ctx = m->ctx;
-    if (m->ws && m->ws->restart >= restart) return BEMB200_OK;
-    free_workspace(m);
-    GmresWorkspace* ws = new GmresWorkspace();
-    m->ws = ws;
     ws->n = m->n_rows;
     ws->chunk = (m->n_rows + ctx->nranks - 1) / ctx->nranks;
     ws->npad = ws->chunk * ctx->nranks;
@@ -189,7 +203,7 @@ static int ensure_workspace(bemb200_matrix* m, uint32_t restart) {
     BEMB_CUDA(ctx, cudaMalloc((void**)&ws->lmat_d, ((size_t)(restart + 1) * (restart + 1) + mgs_scratch_elems()) * sizeof(cplx)));
     BEMB_CUDA(ctx, cudaMalloc((void**)&ws->scal_d, 4 * sizeof(double)));
     BEMB_CUDA(ctx, cudaMallocHost((void**)&ws->hcol_h, (size_t)(restart + 1) * ws->ldh_slot * sizeof(cplx)));
-    ws->it_ev0.resize(restart + 1); ws->it_ev1.resize(restart + 1); ws->it_done.resize(restart + 1);
+    ws->it_ev0.assign(restart + 1, nullptr); ws->it_ev1.assign(restart + 1, nullptr); ws->it_done.assign(restart + 1, nullptr);
     ws->launched.assign(restart + 1, 0);
     for (uint32_t i = 0; i <= restart; ++i) {
         BEMB_CUDA(ctx, cudaEventCreate(&ws->it_ev0[i]));
@@ -200,6 +214,21 @@ static int ensure_workspace(bemb200_matrix* m, uint32_t restart) {
     BEMB_CUDA(ctx, cudaEventCreate(&ws->ev0));
     BEMB_CUDA(ctx, cudaEventCreate(&ws->ev1));
     BEMB_CUDA(ctx, cudaMemsetAsync(ws->w, 0, vb, ctx->stream));
+    return BEMB200_OK;
+}
+
+static int ensure_workspace(bemb200_matrix* m, uint32_t restart) {
+    if (m->ws && m->ws->restart >= restart) return BEMB200_OK;
+    free_workspace(m);
+    if ((uint64_t)restart + 1 > (1ull << 40) / ((m->n_rows + 1) * sizeof(cplx)))  // > 1 TiB of basis vectors: refuse before asking CUDA
+        return set_error(m->ctx, BEMB200_ENOMEM, "GMRES workspace: restart x n does not fit any device");
+    GmresWorkspace* ws = new GmresWorkspace();
+    const int rc = build_workspace(m, restart, ws);
+    if (rc != BEMB200_OK) {
+        destroy_workspace(ws);
+        return rc;
+    }
+    m->ws = ws;
     return BEMB200_OK;
 }
 
@@ -311,8 +340,29 @@ static int gmres_core(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t max_it
     }
     // (with assembly kernels of another stream on the GPU the spinning consumer measured slower than NCCL: keep it for
     //  the solver-owns-the-GPU case)
+    if (ctx->nranks > 1 && ctx->px.tried && ctx->nccl_comm) {
+        // a rank whose consumer kernel once timed out has left peer mode; the ranks agree on the path of THIS solve
+        // (one 4-byte all-gather per solve) so that nobody waits in a protocol the others no longer speak
+        int* st = reinterpret_cast<int*>(ws->hcol_d);
+        const int mine = ctx->px.ok ? 1 : 0;
+        std::vector<int> all(ctx->nranks, 0);
+        BEMB_CUDA(ctx, cudaMemcpyAsync(st + ctx->rank, &mine, sizeof(int), cudaMemcpyHostToDevice, s));
+        rc = nccl_allgather_bytes(ctx, st + ctx->rank, st, sizeof(int));
+        if (rc != BEMB200_OK) return rc;
+        BEMB_CUDA(ctx, cudaMemcpyAsync(all.data(), st, sizeof(int) * ctx->nranks, cudaMemcpyDeviceToHost, s));
+        BEMB_CUDA(ctx, cudaStreamSynchronize(s));
+        bool every = true;
+        for (int v : all) every = every && v != 0;
+        if (!every) ctx->px.ok = false;
+        if (ctx->px.err_h) *ctx->px.err_h = 0;
+    }
     const bool peer_fused = allow_grid && ctx->nranks > 1 && ctx->px.ok && ctx->px.npad >= ws->npad && ws->npad == ws->chunk * (uint64_t)ctx->nranks &&
                             mgs_peer_wait_capable(n, restart, allow_grid);
+    static const unsigned long long peer_timeout_ns = []() {
+        const char* v = std::getenv("BEMB200_PEER_TIMEOUT_MS");
+        const long long ms = v ? std::atoll(v) : 4000;
+        return (unsigned long long)(ms > 0 ? ms : 4000) * 1000000ull;
+    }();
     struct PeerErrCheck {  // a consumer kernel that gave up waiting for a peer poisons the solve: report it
         bemb200_ctx* c; bool on;
         int check() const { return (on && c->px.err_h && *c->px.err_h) ? 1 : 0; }
@@ -360,6 +410,7 @@ static int gmres_core(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t max_it
                 pw.ll = px_work(px, ctx->rank, epoch);
                 pw.epoch = (uint32_t)epoch;
                 pw.err = px.err_h;
+                pw.timeout_ns = peer_timeout_ns;
             } else {
                 cplx* yloc = ws->w + (ctx->nranks > 1 ? (uint64_t)ctx->rank * ws->chunk : m->r0);
                 BEMB_CUDA(ctx, launch_zgemv(m->A, m->n_cols, nloc, m->n_cols, ws->V + (uint64_t)j * ws->npad, yloc, s));
@@ -374,7 +425,7 @@ static int gmres_core(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t max_it
             BEMB_CUDA(ctx, launch_mgs(ws->V, ws->npad, const_cast<cplx*>(wvec), j, n, hd, ws->V + (uint64_t)(j + 1) * ws->npad, pinv,
                                       direct_scale, ws->lmat_d, (int)ws->restart + 1,
                                       ws->lmat_d + (size_t)(ws->restart + 1) * (ws->restart + 1),
-                                      ws->hcol_h + (size_t)j * ws->ldh_slot, &wrote_host, allow_grid, pw, s));
+                                      ws->hcol_h + (size_t)j * ws->ldh_slot, &wrote_host, allow_grid, pw, ctx->nranks > 1, s));
             if (g_dbg_split) BEMB_CUDA(ctx, cudaEventRecord(ws->ev0, s));
             if (!wrote_host)
                 BEMB_CUDA(ctx, cudaMemcpyAsync(ws->hcol_h + (size_t)j * ws->ldh_slot, hd, (j + 2) * sizeof(cplx),
@@ -416,8 +467,13 @@ static int gmres_core(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t max_it
             }
             g_dbg_launch_us += std::chrono::duration<double, std::micro>(tp1 - tp0).count();
             g_dbg_wait_us += std::chrono::duration<double, std::micro>(tp2 - tp1).count();
-            if (peer_err.check())
+            if (peer_err.check()) {
+                // this solve is lost (the peers run into their own bounded waits); later solves of this context use the
+                // NCCL all-gather, which the ranks agree on at the start of the next solve
+                ctx->px.ok = false;
+                *ctx->px.err_h = 0;
                 return set_error(ctx, BEMB200_ENCCL, "peer-memory exchange timed out waiting for another rank's slab of A v");
+            }
             const cplx* hcol = ws->hcol_h + (size_t)j * ws->ldh_slot;
             for (int i = 0; i <= j; ++i) h[i * ldh + j] = hcol[i];
             const double w_norm = hcol[j + 1].re;

@@ -11,6 +11,7 @@
 //                       barriers instead of j+1 kernel launches / host round trips.
 //   residual / scale / update kernels for gmres.rs:143-172,238-262
 #include <cooperative_groups.h>
+#include <atomic>
 #include <cstdlib>
 
 #include "linalg.h"
@@ -18,6 +19,27 @@
 namespace cg = cooperative_groups;
 
 namespace bemb {
+
+// Function attributes (dynamic shared memory, non-portable cluster size) and "this kernel cannot be
+// placed here" demotions are PER DEVICE: a process may hold contexts on several GPUs.
+constexpr int MAX_DEVICES = 64;
+static inline int cur_dev() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); d = 0; }
+    return d >= 0 && d < MAX_DEVICES ? d : MAX_DEVICES - 1;
+}
+struct PerDeviceFlag {
+    std::atomic<unsigned char> v[MAX_DEVICES];
+    PerDeviceFlag() { for (auto& x : v) x.store(0); }
+    bool get() const { return v[cur_dev()].load() != 0; }
+    void set() { v[cur_dev()].store(1); }
+};
+struct PerDeviceInt {  // starts at `init` on every device
+    std::atomic<int> v[MAX_DEVICES];
+    explicit PerDeviceInt(int init) { for (auto& x : v) x.store(init); }
+    int get() const { return v[cur_dev()].load(); }
+    void set(int val) { v[cur_dev()].store(val); }
+};
 
 namespace {
 
@@ -55,12 +77,11 @@ __device__ __forceinline__ void ll_store(uint4* dst, double re, double im, uint3
     asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(rl), "r"(flag), "r"(rh), "r"(flag) : "memory");
     asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 1), "r"(il), "r"(flag), "r"(ih), "r"(flag) : "memory");
 }
-constexpr unsigned long long PEER_WAIT_TIMEOUT_NS = 4000000000ull;
 // loads N elements (element e at src + 2*(first + e*stride), skipped when first + e*stride >= len);
 // every pass issues all outstanding loads back to back, then re-polls only what has not arrived
 template <int N>
 __device__ __forceinline__ void ll_load_many(cplx (&out)[N], const uint4* src, uint64_t first, uint64_t stride, uint64_t len,
-                                             uint32_t flag, int* err) {
+                                             uint32_t flag, int* err, unsigned long long timeout_ns) {
     bool have[N];
 #pragma unroll
     for (int e = 0; e < N; ++e) {
@@ -95,7 +116,7 @@ __device__ __forceinline__ void ll_load_many(cplx (&out)[N], const uint4* src, u
         if ((++spins & 63u) == 0) {
             const unsigned long long t = global_timer_ns();
             if (t0 == 0) t0 = t;
-            else if (t - t0 > PEER_WAIT_TIMEOUT_NS) {
+            else if (t - t0 > timeout_ns) {
                 *reinterpret_cast<volatile int*>(err) = 1;
                 break;
             }
@@ -163,19 +184,28 @@ zgemv_kernel(const cplx* __restrict__ A, uint64_t lda, uint64_t nrows, uint64_t 
     }
 }
 
-// y[j] += sum_i A[i,j] x[i] over a chunk of rows (y pre-zeroed)
-constexpr int GEMVT_ROWS = 64;
+// apply_transpose, deterministic two-pass column reduction: pass 1 writes the partial sum of every row
+// chunk to part[chunk][col] (each thread owns its column: coalesced reads of A, no atomics), pass 2 adds the
+// chunks of a column in chunk order.  At most GEMVT_MAX_CHUNKS chunks, so the scratch stays 32 n complex numbers.
+constexpr int GEMVT_MAX_CHUNKS = 32;
 __global__ void __launch_bounds__(256)
-zgemv_t_kernel(const cplx* __restrict__ A, uint64_t lda, uint64_t nrows, uint64_t ncols, const cplx* __restrict__ x,
-               cplx* __restrict__ y) {
+zgemv_t_partial_kernel(const cplx* __restrict__ A, uint64_t lda, uint64_t nrows, uint64_t ncols, uint64_t rows_per_chunk,
+                       const cplx* __restrict__ x, cplx* __restrict__ part) {
     const uint64_t col = (uint64_t)blockIdx.x * 256 + threadIdx.x;
-    const uint64_t r0 = (uint64_t)blockIdx.y * GEMVT_ROWS;
-    const uint64_t r1 = r0 + GEMVT_ROWS < nrows ? r0 + GEMVT_ROWS : nrows;
+    const uint64_t r0 = (uint64_t)blockIdx.y * rows_per_chunk;
+    const uint64_t r1 = r0 + rows_per_chunk < nrows ? r0 + rows_per_chunk : nrows;
     if (col >= ncols) return;
     double sr = 0.0, si = 0.0;
     for (uint64_t r = r0; r < r1; ++r) cfma(sr, si, ld_stream(A + r * lda + col), ld_ro(x + r));
-    atomicAdd(&y[col].re, sr);
-    atomicAdd(&y[col].im, si);
+    part[(uint64_t)blockIdx.y * ncols + col] = C(sr, si);
+}
+__global__ void __launch_bounds__(256)
+zgemv_t_reduce_kernel(const cplx* __restrict__ part, uint64_t ncols, int nchunks, cplx* __restrict__ y) {
+    const uint64_t col = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (col >= ncols) return;
+    double sr = 0.0, si = 0.0;
+    for (int c = 0; c < nchunks; ++c) { sr += part[(uint64_t)c * ncols + col].re; si += part[(uint64_t)c * ncols + col].im; }
+    y[col] = C(sr, si);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -331,7 +361,7 @@ mgs_lowsync_kernel(const cplx* __restrict__ V, uint64_t ldv, const cplx* __restr
 
     cplx wr[EPT], vj[EPT];
     // row-sharded solve: w arrives from every rank's ZGEMV epilogue in flag-in-data form
-    if (pw.ll) ll_load_many<EPT>(wr, pw.ll + 2 * begin, (uint64_t)tid, (uint64_t)LS_THREADS, len, pw.epoch, pw.err);
+    if (pw.ll) ll_load_many<EPT>(wr, pw.ll + 2 * begin, (uint64_t)tid, (uint64_t)LS_THREADS, len, pw.epoch, pw.err, pw.timeout_ns);
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
         const uint64_t k = tid + (uint64_t)e * LS_THREADS;
@@ -514,7 +544,7 @@ mgs_grid_kernel(const cplx* __restrict__ V, uint64_t ldv, const cplx* __restrict
     const uint64_t len = end > begin ? end - begin : 0;
 
     cplx wr[EPT], vj[EPT];
-    if (pw.ll) ll_load_many<EPT>(wr, pw.ll + 2 * begin, (uint64_t)tid, (uint64_t)GR_THREADS, len, pw.epoch, pw.err);
+    if (pw.ll) ll_load_many<EPT>(wr, pw.ll + 2 * begin, (uint64_t)tid, (uint64_t)GR_THREADS, len, pw.epoch, pw.err, pw.timeout_ns);
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
         const uint64_t k = tid + (uint64_t)e * GR_THREADS;
@@ -1288,11 +1318,18 @@ cudaError_t launch_zgemv_peer(const cplx* A, uint64_t lda, uint64_t nrows, uint6
 }
 
 cudaError_t launch_zgemv_t(const cplx* A, uint64_t lda, uint64_t nrows, uint64_t ncols, const cplx* x, cplx* y, cudaStream_t s) {
-    cudaError_t e = cudaMemsetAsync(y, 0, ncols * sizeof(cplx), s);
-    if (e != cudaSuccess || nrows == 0) return e;
-    dim3 grid((unsigned)((ncols + 255) / 256), (unsigned)((nrows + GEMVT_ROWS - 1) / GEMVT_ROWS));
-    zgemv_t_kernel<<<grid, 256, 0, s>>>(A, lda, nrows, ncols, x, y);
-    return cudaGetLastError();
+    if (nrows == 0) return cudaMemsetAsync(y, 0, ncols * sizeof(cplx), s);
+    const uint64_t rpc = (nrows + GEMVT_MAX_CHUNKS - 1) / GEMVT_MAX_CHUNKS;
+    const int nchunks = (int)((nrows + rpc - 1) / rpc);
+    cplx* part = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&part, (size_t)nchunks * ncols * sizeof(cplx), s);
+    if (e != cudaSuccess) return e;
+    dim3 grid((unsigned)((ncols + 255) / 256), (unsigned)nchunks);
+    zgemv_t_partial_kernel<<<grid, 256, 0, s>>>(A, lda, nrows, ncols, rpc, x, part);
+    zgemv_t_reduce_kernel<<<(unsigned)((ncols + 255) / 256), 256, 0, s>>>(part, ncols, nchunks, y);
+    e = cudaGetLastError();
+    cudaFreeAsync(part, s);
+    return e;
 }
 
 // cluster size / slice / where w lives.  `level` 0: preferred (w in shared memory, 16 CTAs if a
@@ -1312,16 +1349,16 @@ static int pick_cluster(uint64_t n, int level, bool* w_in_smem, size_t* smem_byt
     return cl;
 }
 
-static int g_cluster_level = 0;
+static PerDeviceInt g_cluster_level(0);
 
 template <int EPT>
 static cudaError_t launch_mgs_reg(int cl, const cplx* V, uint64_t ldv, const cplx* w, int j, uint64_t n, uint64_t S, cplx* hcol,
                                   cplx* vnext, const cplx* pinv, int direct_scale, cudaStream_t s) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceFlag attr_done;
+    if (!attr_done.get()) {
         cudaError_t e = cudaFuncSetAttribute(mgs_cluster_reg_kernel<EPT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_done.set();
     }
     return launch_cluster(mgs_cluster_reg_kernel<EPT>, cl, 256, 0, s, V, ldv, w, j, n, S, hcol, vnext, 1e-14, pinv, direct_scale);
 }
@@ -1330,15 +1367,15 @@ template <int EPT>
 static cudaError_t launch_mgs_lowsync(int cl, const cplx* V, uint64_t ldv, const cplx* w, int j, uint64_t n, uint64_t S, cplx* Lmat,
                                       int ldl, cplx* hcol, cplx* vnext, const cplx* pinv, int direct_scale, cplx* hcol_host,
                                       const PeerWait& pw, cudaStream_t s) {
-    static bool attr_done = false;
+    static PerDeviceFlag attr_done;
     const size_t fixed = (size_t)(LS_WARPS * 2 * LS_MAXV + MAX_CLUSTER * 2 * LS_MAXV + LS_MAXV) * sizeof(cplx);
-    if (!attr_done) {
+    if (!attr_done.get()) {
         cudaError_t e = cudaFuncSetAttribute(mgs_lowsync_kernel<EPT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(mgs_lowsync_kernel<EPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)(fixed + (size_t)LS_MAXV * LS_MAXV * sizeof(cplx)));
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_done.set();
     }
     const size_t smem = fixed + (size_t)(j + 1) * (j + 1) * sizeof(cplx);
     return launch_cluster(mgs_lowsync_kernel<EPT>, cl, LS_THREADS, smem, s, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, 1e-14, pinv,
@@ -1350,13 +1387,13 @@ static cudaError_t launch_mgs_grid(int G, const cplx* V, uint64_t ldv, const cpl
                                    int ldl, cplx* hcol, cplx* vnext, const cplx* pinv, int direct_scale, cplx* scratch,
                                    cplx* hcol_host, const PeerWait& pw, cudaStream_t s) {
     constexpr int GR_WARPS = GR_THREADS / 32;
-    static bool attr_done = false;
+    static PerDeviceFlag attr_done;
     const size_t fixed = (size_t)(GR_WARPS * 2 * LS_MAXV + LS_MAXV) * sizeof(cplx);
-    if (!attr_done) {
+    if (!attr_done.get()) {
         cudaError_t e = cudaFuncSetAttribute(mgs_grid_kernel<EPT, GR_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)(fixed + (size_t)LS_MAXV * LS_MAXV * sizeof(cplx)));
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_done.set();
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(G, 1, 1);
@@ -1377,27 +1414,33 @@ static cudaError_t launch_mgs_grid(int G, const cplx* V, uint64_t ldv, const cpl
 
 size_t mgs_scratch_elems() { return (size_t)GR_MAX_CTAS * 2 * LS_MAXV + GR_MAX_CTAS; }
 
-static int g_mgs_mode = []() {
+static const int g_mgs_mode_env = []() {
     const char* v = std::getenv("BEMB200_MGS_MODE");
     return v ? std::atoi(v) : 3;
-}();  // 3: whole-GPU cooperative low-sync kernel, 0: low-sync register kernel (16-CTA cluster) when the slice fits, 2: one-vector register kernel, 1: generic kernel only
+}();
+static PerDeviceInt g_mgs_mode(g_mgs_mode_env);  // 3: whole-GPU cooperative low-sync kernel, 0: low-sync register kernel (16-CTA cluster) when the slice fits, 2: one-vector register kernel, 1: generic kernel only
 
 bool mgs_peer_wait_capable(uint64_t n, uint32_t restart, bool allow_grid) {
     if (restart + 1 > (uint32_t)LS_MAXV) return false;
-    if (g_mgs_mode != 3 && g_mgs_mode != 0) return false;
+    const int mode = g_mgs_mode.get();
+    if (mode != 3 && mode != 0) return false;
     if (n <= 16ull * LS_THREADS * 8ull) return true;  // cluster low-sync kernel
-    return g_mgs_mode == 3 && allow_grid && n <= (uint64_t)GR_MAX_CTAS * 1024ull;
+    return mode == 3 && allow_grid && n <= (uint64_t)GR_MAX_CTAS * 1024ull;
 }
 
+// `strict`: the caller is one rank of a row-sharded solve.  Every rank must run the SAME Arnoldi kernel
+// (convergence decisions are not all-reduced; they agree because the arithmetic is identical), so a
+// kernel that cannot be placed on this device is an error there, never a silent per-rank fallback.
 static cudaError_t launch_mgs_cluster_path(int mode_in, const cplx* V, uint64_t ldv, cplx* w, int j, uint64_t n, cplx* hcol,
                                            cplx* vnext, const cplx* pinv, int direct_scale, cplx* Lmat, int ldl, cplx* hcol_host,
-                                           bool* wrote_host, const PeerWait& pw, cudaStream_t s) {
+                                           bool* wrote_host, const PeerWait& pw, bool strict, cudaStream_t s) {
     *wrote_host = false;
     // 0: low-sync register kernel (16-CTA cluster) when the slice fits, 2: one-vector register kernel, 1: generic kernel;
-    // a kernel this device cannot place demotes the mode for good
-    static int cluster_mode = mode_in;
-    int& g_mgs_mode = cluster_mode;
-    if (g_mgs_mode == 0 && Lmat && j + 1 <= LS_MAXV && n <= 16ull * LS_THREADS * 8ull) {
+    // a kernel this device cannot place demotes the mode of THIS device for good
+    static PerDeviceInt cluster_mode(-1);
+    if (cluster_mode.get() < 0) cluster_mode.set(mode_in);
+    int mode = cluster_mode.get();
+    if (mode == 0 && Lmat && j + 1 <= LS_MAXV && n <= 16ull * LS_THREADS * 8ull) {
         const int cl = n >= 2048 ? 16 : (n >= 512 ? 4 : 1);
         const uint64_t S = (n + cl - 1) / cl;
         const uint64_t ept = (S + LS_THREADS - 1) / LS_THREADS;
@@ -1407,11 +1450,13 @@ static cudaError_t launch_mgs_cluster_path(int mode_in, const cplx* V, uint64_t 
         else if (ept <= 4) e = launch_mgs_lowsync<4>(cl, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, hcol_host, pw, s);
         else e = launch_mgs_lowsync<8>(cl, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, hcol_host, pw, s);
         if (e == cudaSuccess) { *wrote_host = hcol_host != nullptr; return e; }
+        if (strict) return e;
         cudaGetLastError();
-        g_mgs_mode = 2;
+        mode = 2;
+        cluster_mode.set(mode);
     }
     if (pw.ll) return cudaErrorNotSupported;  // only the two low-sync kernels know how to wait for peer slabs
-    if ((g_mgs_mode == 0 || g_mgs_mode == 2) && n <= 16ull * 256ull * 8ull) {
+    if ((mode == 0 || mode == 2) && n <= 16ull * 256ull * 8ull) {
         // register-resident w: 16 CTAs (non-portable cluster size) x 256 threads x <= 8 elements
         const int cl = n >= 2048 ? 16 : (n >= 512 ? 4 : 1);
         const uint64_t S = (n + cl - 1) / cl;
@@ -1422,38 +1467,42 @@ static cudaError_t launch_mgs_cluster_path(int mode_in, const cplx* V, uint64_t 
         else if (ept <= 4) e = launch_mgs_reg<4>(cl, V, ldv, w, j, n, S, hcol, vnext, pinv, direct_scale, s);
         else e = launch_mgs_reg<8>(cl, V, ldv, w, j, n, S, hcol, vnext, pinv, direct_scale, s);
         if (e == cudaSuccess) return e;
+        if (strict) return e;
         cudaGetLastError();  // a 16-CTA cluster this device cannot place: fall back for good
-        g_mgs_mode = 1;
+        cluster_mode.set(1);
     }
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceFlag attr_done;
+    if (!attr_done.get()) {
         cudaError_t e = cudaFuncSetAttribute(mgs_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(mgs_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_done.set();
     }
     for (;;) {
         bool in_smem;
         size_t smem;
         uint64_t S;
-        int cl = pick_cluster(n, g_cluster_level, &in_smem, &smem, &S);
+        // a row-sharded solve always uses the conservative placement (8 CTAs, w in global): identical on every rank
+        const int level = strict ? 1 : g_cluster_level.get();
+        int cl = pick_cluster(n, level, &in_smem, &smem, &S);
         cudaError_t e = launch_cluster(mgs_cluster_kernel, cl, VEC_THREADS, smem, s, V, ldv, w, j, n, S, (int)in_smem, hcol,
                                        vnext, 1e-14, pinv, direct_scale);
-        if (e == cudaSuccess || g_cluster_level == 1) return e;
+        if (e == cudaSuccess || level == 1) return e;
         cudaGetLastError();  // e.g. a 16-CTA / 200 KB cluster that this GPC layout cannot place
-        g_cluster_level = 1;
+        g_cluster_level.set(1);
     }
 }
 
 cudaError_t launch_mgs(const cplx* V, uint64_t ldv, cplx* w, int j, uint64_t n, cplx* hcol, cplx* vnext, const cplx* pinv,
                        int direct_scale, cplx* Lmat, int ldl, cplx* scratch, cplx* hcol_host, bool* wrote_host, bool allow_grid,
-                       const PeerWait& pw, cudaStream_t s) {
+                       const PeerWait& pw, bool strict, cudaStream_t s) {
     *wrote_host = false;
     // mode 3 (default): whole-GPU cooperative kernel; the slice per CTA depends on n only
     static const bool force_grid = std::getenv("BEMB200_MGS_FORCE_GRID") != nullptr;
-    if (g_mgs_mode == 3 && (allow_grid || force_grid) && Lmat && scratch && j + 1 <= LS_MAXV && n >= 4096 && n <= (uint64_t)GR_MAX_CTAS * 1024ull) {
-        const int G = GR_MAX_CTAS;
+    const int mode = g_mgs_mode.get();
+    if (mode == 3 && (allow_grid || force_grid) && Lmat && scratch && j + 1 <= LS_MAXV && n >= 4096 && n <= (uint64_t)GR_MAX_CTAS * 1024ull) {
+        const int G = GR_MAX_CTAS;  // fixed (not the SM count of the device): the summation order must not depend on the rank's GPU
         const uint64_t S = (n + G - 1) / G;
         cudaError_t e;
 #define GRID_CASE(E, T) e = launch_mgs_grid<E, T>(G, V, ldv, w, j, n, S, Lmat, ldl, hcol, vnext, pinv, direct_scale, scratch, hcol_host, pw, s)
@@ -1463,12 +1512,14 @@ cudaError_t launch_mgs(const cplx* V, uint64_t ldv, cplx* w, int j, uint64_t n, 
         else GRID_CASE(4, 256);
 #undef GRID_CASE
         if (e == cudaSuccess) { *wrote_host = hcol_host != nullptr; return e; }
+        if (strict) return e;  // e.g. a device with fewer than 148 SMs in a multi-rank job: fail loudly
         cudaGetLastError();  // cooperative launch not placeable on this device: cluster kernels from now on
-        g_mgs_mode = 0;
+        g_mgs_mode.set(0);
     }
     // small or very long vectors, or BEMB200_MGS_MODE in {0,1,2}: the cluster kernels
-    return launch_mgs_cluster_path(g_mgs_mode == 3 ? 0 : g_mgs_mode, V, ldv, w, j, n, hcol, vnext, pinv, direct_scale, Lmat, ldl,
-                                   hcol_host, wrote_host, pw, s);
+    const int m2 = g_mgs_mode.get();
+    return launch_mgs_cluster_path(m2 == 3 ? 0 : m2, V, ldv, w, j, n, hcol, vnext, pinv, direct_scale, Lmat, ldl,
+                                   hcol_host, wrote_host, pw, strict, s);
 }
 
 cudaError_t launch_residual(const cplx* b, const cplx* ax, cplx* r, uint64_t n, double* out, const cplx* pinv, cudaStream_t s) {
@@ -1547,11 +1598,11 @@ template <int EPT>
 static cudaError_t launch_mgs_batched_t(int cl, int nrhs, const cplx* Vall, uint64_t ldv, uint64_t vstride, const cplx* Yblk,
                                         int j, uint64_t n, uint64_t S, cplx* hcol_all, uint64_t hstride, cplx* Xblk,
                                         const unsigned char* active, cudaStream_t s) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceFlag attr_done;
+    if (!attr_done.get()) {
         cudaError_t e = cudaFuncSetAttribute(mgs_batched_kernel<EPT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_done.set();
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(cl, nrhs, 1);

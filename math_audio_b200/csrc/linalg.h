@@ -17,6 +17,7 @@ struct PeerWait {
     const uint4* ll = nullptr;  // nullptr: plain work vector, nothing to wait for
     uint32_t epoch = 0;
     int* err = nullptr;         // mapped host int, set to 1 when a wait timed out
+    unsigned long long timeout_ns = 4000000000ull;  // BEMB200_PEER_TIMEOUT_MS
 };
 cudaError_t launch_zgemv_peer(const cplx* A, uint64_t lda, uint64_t nrows, uint64_t ncols, const cplx* x, const PeerOut& po,
                               cudaStream_t s);
@@ -26,7 +27,7 @@ cudaError_t launch_zgemv_t(const cplx* A, uint64_t lda, uint64_t nrows, uint64_t
 // Lmat (may be NULL): (ldl x ldl) scratch for the Gram triangle of the current restart cycle (low-sync kernel)
 cudaError_t launch_mgs(const cplx* V, uint64_t ldv, cplx* w, int j, uint64_t n, cplx* hcol, cplx* vnext, const cplx* pinv,
                        int direct_scale, cplx* Lmat, int ldl, cplx* scratch, cplx* hcol_host, bool* wrote_host, bool allow_grid,
-                       const PeerWait& pw, cudaStream_t s);  // hcol_host: mapped pinned copy of the column (written by the kernel when *wrote_host)
+                       const PeerWait& pw, bool strict, cudaStream_t s);  // strict: one rank of a row-sharded solve, no per-rank kernel fallback  // hcol_host: mapped pinned copy of the column (written by the kernel when *wrote_host)
 size_t mgs_scratch_elems();  // cplx elements of scratch launch_mgs needs after the ldl*ldl Gram triangle
 cudaError_t launch_residual(const cplx* b, const cplx* ax, cplx* r, uint64_t n, double* out, const cplx* pinv, cudaStream_t s);
 // BiCGSTAB vector kernels: out = device scratch of >= 2 complex numbers
