@@ -28,6 +28,7 @@ UNITS = {
     "assembly_far.cu": [],
     "linalg.cu": [],
     "gmres.cu": [],
+    "gmres_fused.cu": [],
     "block_gmres.cu": [],
     "postprocess.cu": ["-fmad=false"],
     "room.cu": [],

@@ -20,6 +20,19 @@ struct PeerExchange {
     int* err_h = nullptr;              // mapped pinned int: a consumer kernel timed out waiting for a peer
 };
 
+// Buffers of the persistent fused GMRES kernel (gmres_fused.cu) that stay local to the rank: the inbox of CTA
+// partials, the broadcast slots and the result record.  The exchange vectors and the inbox of rank partials live in the
+// PeerExchange allocation (they are written by other ranks).
+struct FusedLocal {
+    uint4* cpart = nullptr;
+    uint4* hbuf = nullptr;
+    void* result_h = nullptr;   // FusedResult, mapped pinned
+    void* result_d = nullptr;   // device alias of result_h
+    int grid = 0;               // CTAs the buffers were sized for
+    uint32_t er = 0;            // last reduction-round epoch used
+    bool disabled = false;      // a solve timed out: stay on the per-iteration kernels
+};
+
 struct bemb200_ctx {
     int device = 0;
     int rank = 0, nranks = 1;
@@ -29,6 +42,8 @@ struct bemb200_ctx {
     std::atomic<int> background_blocks_per_sm{0};  // > 0: assembly kernels use a small persistent grid (sweep pipelining)
     void* nccl_comm = nullptr;  // ncclComm_t when nranks > 1
     PeerExchange px;
+    FusedLocal fx;
+    int fused_grid = 0;  // > 0: CTAs of the fused GMRES kernel (several ranks sharing one device); 0: one per SM
     std::string err;
     std::mutex mu;  // LinearOperator is Send + Sync: serialise stream submission per context
 };
@@ -63,6 +78,7 @@ struct bemb200_matrix {
     // solver statistics of the last call
     uint64_t last_launches = 0, last_matvecs = 0;
     double last_matvec_ms = 0.0;
+    double last_solve_ms = 0.0;  // fused kernel: CUDA-event duration of the one launch
 };
 
 namespace bemb {

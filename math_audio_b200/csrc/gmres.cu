@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "api_internal.h"
+#include "gmres_fused.h"
 #include "linalg.h"
 
 using namespace bemb;
@@ -76,6 +77,8 @@ void free_workspace(bemb200_matrix* m) {
 // (no peer access, IPC refused by the platform) is agreed on by all ranks and leaves the NCCL
 // all-gather path in place.  BEMB200_PEER_FUSED=0 disables it.
 constexpr size_t PX_HEADER = 256;
+constexpr size_t PX_RPART_BYTES = 2 * (size_t)MAX_PEERS * FUSED_KMAX * 2 * sizeof(uint4);
+static inline size_t px_bytes(uint64_t npad) { return PX_HEADER + 2 * npad * 2 * sizeof(uint4) + PX_RPART_BYTES; }
 namespace bemb {
 void free_peer_exchange(bemb200_ctx* ctx, bool collective) {
     PeerExchange& px = ctx->px;
@@ -100,6 +103,11 @@ void free_peer_exchange(bemb200_ctx* ctx, bool collective) {
     if (px.local && may_free) cudaFree(px.local);
     if (px.err_h) cudaFreeHost(px.err_h);
     px = PeerExchange();
+    FusedLocal& fx = ctx->fx;
+    if (fx.cpart) cudaFree(fx.cpart);
+    if (fx.hbuf) cudaFree(fx.hbuf);
+    if (fx.result_h) cudaFreeHost(fx.result_h);
+    fx = FusedLocal();
     cudaGetLastError();
 }
 }  // namespace bemb
@@ -113,7 +121,7 @@ static int ensure_peer_exchange(bemb200_ctx* ctx, uint64_t npad) {
     px.tried = true;
     px.npad = npad;
     const int P = ctx->nranks;
-    const size_t bytes = PX_HEADER + 2 * npad * 2 * sizeof(uint4);  // two epochs x npad elements x 32 B
+    const size_t bytes = px_bytes(npad);  // two epochs x npad elements x 32 B + the fused kernel's inbox of rank partials
     int ok = 1;
     cudaIpcMemHandle_t mine;
     std::memset(&mine, 0, sizeof(mine));
@@ -311,6 +319,161 @@ static int update_x(bemb200_matrix* m, cplx* x, const std::vector<cplx>& y) {
     return BEMB200_OK;
 }
 
+// ---- persistent fused solve (gmres_fused.cu) ----------------------------------------------------------------
+static const bool g_fused_enabled = []() { const char* v = std::getenv("BEMB200_GMRES_FUSED"); return v ? std::atoi(v) != 0 : true; }();
+static const bool g_fused_shared = []() { const char* v = std::getenv("BEMB200_FUSED_SHARED"); return v ? std::atoi(v) != 0 : false; }();
+static double g_fused_total_ms = 0.0, g_fused_matvec_ms = 0.0, g_fused_round_ms = 0.0;
+static unsigned long long g_fused_rounds = 0;
+
+// Exchange vectors for the fused kernel.  One rank: a plain local allocation in the PeerExchange layout; several
+// ranks: the IPC-mapped allocation of ensure_peer_exchange (collective).  Returns with *ok = false when the
+// platform refused peer mappings (the caller then stays on the per-iteration kernels -- agreed by all ranks).
+static int ensure_fused_exchange(bemb200_ctx* ctx, uint64_t npad, bool* ok) {
+    *ok = false;
+    PeerExchange& px = ctx->px;
+    if (ctx->nranks > 1) {
+        int rc = ensure_peer_exchange(ctx, npad);
+        if (rc != BEMB200_OK) return rc;
+        if (!px.ok || px.npad < npad) return BEMB200_OK;
+    } else if (!px.local || px.npad < npad) {
+        if (px.local) { cudaFree(px.local); px.local = nullptr; }
+        BEMB_CUDA(ctx, cudaMalloc((void**)&px.local, px_bytes(npad)));
+        BEMB_CUDA(ctx, cudaMemsetAsync(px.local, 0, px_bytes(npad), ctx->stream));
+        px.npad = npad;
+        px.epoch = 0;
+        px.base[0] = px.local;
+        ctx->fx.er = 0;
+    }
+    FusedLocal& fx = ctx->fx;
+    int grid = ctx->fused_grid;
+    if (grid <= 0) {
+        static const int env_grid = []() { const char* v = std::getenv("BEMB200_FUSED_GRID"); return v ? std::atoi(v) : 0; }();
+        grid = env_grid;
+    }
+    if (grid <= 0) {
+        int sms = 0;
+        BEMB_CUDA(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+        grid = sms;
+    }
+    if (!fx.cpart || fx.grid != grid) {
+        if (fx.cpart) cudaFree(fx.cpart);
+        if (fx.hbuf) cudaFree(fx.hbuf);
+        fx.cpart = fx.hbuf = nullptr;
+        const size_t cb = 2 * (size_t)grid * FUSED_KMAX * 2 * sizeof(uint4), hb = 2 * (size_t)FUSED_KMAX * 2 * sizeof(uint4);
+        BEMB_CUDA(ctx, cudaMalloc((void**)&fx.cpart, cb));
+        BEMB_CUDA(ctx, cudaMalloc((void**)&fx.hbuf, hb));
+        BEMB_CUDA(ctx, cudaMemsetAsync(fx.cpart, 0, cb, ctx->stream));
+        BEMB_CUDA(ctx, cudaMemsetAsync(fx.hbuf, 0, hb, ctx->stream));
+        fx.grid = grid;
+        // epochs of the old buffers mean nothing for the new ones, but the inbox of rank partials is older: keep counting
+    }
+    if (!fx.result_h) {
+        BEMB_CUDA(ctx, cudaHostAlloc(&fx.result_h, sizeof(FusedResult), cudaHostAllocMapped));
+        BEMB_CUDA(ctx, cudaHostGetDevicePointer(&fx.result_d, fx.result_h, 0));
+    }
+    *ok = true;
+    return BEMB200_OK;
+}
+
+// *used = false: the fused kernel does not apply here (restart too long, shared-memory budget, no peer mapping) and
+// nothing was done; otherwise the solve is complete and *info is set.
+static int gmres_fused_solve(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t max_iterations, uint32_t restart, double tol,
+                             bemb200_gmres_info* info, bool precond, const cplx* pinv, bool* used) {
+    *used = false;
+    bemb200_ctx* ctx = m->ctx;
+    GmresWorkspace* ws = m->ws;
+    if (!g_fused_enabled || ctx->fx.disabled || restart > (uint32_t)FUSED_MAX_RESTART || m->n_rows > 0x7fffffffull) return BEMB200_OK;
+    if (ctx->shared_gpu.load() != 0 && !g_fused_shared) return BEMB200_OK;  // a whole-GPU persistent kernel beside a background assembly
+    if (ctx->nranks > MAX_PEERS) return BEMB200_OK;
+    bool ok = false;
+    int rc = ensure_fused_exchange(ctx, ws->npad, &ok);
+    if (rc != BEMB200_OK) return rc;
+    if (!ok) return BEMB200_OK;
+    FusedLocal& fx = ctx->fx;
+    PeerExchange& px = ctx->px;
+    FusedParams p{};
+    p.A = m->A;
+    p.lda = m->n_cols;
+    p.n = (uint32_t)m->n_rows;
+    p.row0 = (uint32_t)m->r0;
+    p.nloc = (uint32_t)(m->r1 - m->r0);
+    p.npad = (uint32_t)px.npad;
+    p.rank = ctx->rank;
+    p.nranks = ctx->nranks;
+    p.b = b;
+    p.x = x;
+    p.V = ws->V;
+    p.ldv = ws->npad;
+    p.pinv = pinv;
+    p.direct_scale = precond ? 1 : 0;
+    for (int r = 0; r < ctx->nranks; ++r) {
+        p.xbuf[r] = reinterpret_cast<uint4*>(px.base[r] + PX_HEADER);
+        p.rpart[r] = p.xbuf[r] + 4 * (size_t)px.npad;
+    }
+    p.cpart = fx.cpart;
+    p.hbuf = fx.hbuf;
+    p.restart = restart;
+    p.max_cycles = max_iterations;
+    p.tol = tol;
+    p.ex0 = (uint32_t)px.epoch;
+    p.er0 = fx.er;
+    static const unsigned long long timeout_ns = []() {
+        const char* v = std::getenv("BEMB200_PEER_TIMEOUT_MS");
+        const long long ms = v ? std::atoll(v) : 4000;
+        return (unsigned long long)(ms > 0 ? ms : 4000) * 1000000ull;
+    }();
+    p.timeout_ns = timeout_ns;
+    p.result = static_cast<FusedResult*>(fx.result_d);
+    const uint32_t G = (uint32_t)fx.grid;
+    p.S = (p.nloc + G - 1) / G;
+    if (p.S == 0) p.S = 1;
+    p.rblk = fused_pick_rblk(p.S);
+    const size_t smem = fused_smem_bytes(p.S, p.rblk, restart);
+    if (smem > 200 * 1024) return BEMB200_OK;
+    FusedResult* res = static_cast<FusedResult*>(fx.result_h);
+    std::memset(res, 0, sizeof(FusedResult));
+    cudaStream_t s = ctx->stream;
+    BEMB_CUDA(ctx, cudaEventRecord(ws->ev0, s));
+    cudaError_t le = launch_gmres_fused(p, (int)G, smem, s);
+    if (le != cudaSuccess) {
+        // e.g. cooperative launch too large for what is free on this device: not an error of the solve
+        cudaGetLastError();
+        if (ctx->nranks > 1) return cuda_fail(ctx, le, "fused GMRES launch (row-sharded solve: no per-rank fallback)");
+        fx.disabled = true;
+        return BEMB200_OK;
+    }
+    BEMB_CUDA(ctx, cudaEventRecord(ws->ev1, s));
+    BEMB_CUDA(ctx, cudaStreamSynchronize(s));
+    *used = true;
+    if (res->error || !res->done) {
+        fx.disabled = true;
+        px.epoch += 1u << 20;  // whatever the aborted kernel left in the buffers is older than anything written from now on
+        fx.er += 1u << 20;
+        if (ctx->nranks > 1) px.ok = false;
+        return set_error(ctx, BEMB200_ENCCL, "fused GMRES kernel: a bounded wait timed out (a rank or a CTA never delivered its data)");
+    }
+    px.epoch = res->ex_final;
+    fx.er = res->er_final;
+    *info = bemb200_gmres_info{res->iterations, res->restarts, res->residual, res->converged};
+    m->last_launches += 1;
+    m->last_matvecs += res->matvecs;
+    m->last_matvec_ms += (double)res->t_matvec_ns * 1e-6;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ws->ev0, ws->ev1) == cudaSuccess) m->last_solve_ms = ms;
+    else cudaGetLastError();
+    g_fused_total_ms += (double)res->t_total_ns * 1e-6;
+    g_fused_matvec_ms += (double)res->t_matvec_ns * 1e-6;
+    g_fused_round_ms += (double)res->t_round_ns * 1e-6;
+    g_fused_rounds += res->iterations + res->restarts + 1;
+    return BEMB200_OK;
+}
+
+extern "C" void bemb200_debug_fused_times(double* total_ms, double* matvec_ms, double* round_ms, unsigned long long* rounds) {
+    *total_ms = g_fused_total_ms; *matvec_ms = g_fused_matvec_ms; *round_ms = g_fused_round_ms; *rounds = g_fused_rounds;
+    g_fused_total_ms = g_fused_matvec_ms = g_fused_round_ms = 0.0;
+    g_fused_rounds = 0;
+}
+
 // gmres_with_guess (gmres.rs:105-277) with device vectors b, x (x holds x0 on entry).
 // `precond` selects the left-preconditioned variant gmres_preconditioned_with_guess
 // (gmres.rs:434-585): pinv = inverse diagonal on the device (DiagonalPreconditioner) or nullptr
@@ -322,6 +485,11 @@ static int gmres_core(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t max_it
     const uint64_t n = m->n_rows;
     const int mm = (int)restart;
     cudaStream_t s = ctx->stream;
+    {
+        bool used = false;
+        int frc = gmres_fused_solve(m, b, x, max_iterations, restart, tol, info, precond, pinv, &used);
+        if (frc != BEMB200_OK || used) return frc;
+    }
     double b_norm = 0.0;
     int rc = norm_of(m, b, nullptr, nullptr, &b_norm, pinv);  // ||b|| resp. ||M^-1 b|| (gmres.rs:455-457)
     if (rc != BEMB200_OK) return rc;
@@ -739,6 +907,7 @@ static void reset_stats(bemb200_matrix* m) {
     m->last_launches = 0;
     m->last_matvecs = 0;
     m->last_matvec_ms = 0.0;
+    m->last_solve_ms = 0.0;
 }
 
 extern "C" {

@@ -8,11 +8,12 @@ fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "nvcc".into());
     // (translation unit, extra flags): the decision-taking kernels forbid FMA contraction
-    let units: [(&str, &[&str]); 9] = [
+    let units: [(&str, &[&str]); 10] = [
         ("assembly_exact.cu", &["-fmad=false"]),
         ("assembly_far.cu", &[]),
         ("linalg.cu", &[]),
         ("gmres.cu", &[]),
+        ("gmres_fused.cu", &[]),
         ("block_gmres.cu", &[]),
         ("postprocess.cu", &["-fmad=false"]),
         ("room.cu", &[]),
