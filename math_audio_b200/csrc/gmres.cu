@@ -10,6 +10,7 @@
 // vectors, so all ranks hold bit-identical Krylov bases and Hessenberg columns and take the
 // same convergence decisions without any all-reduce.
 #include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cmath>
 #include <cstring>
@@ -340,9 +341,8 @@ static int ensure_fused_exchange(bemb200_ctx* ctx, uint64_t npad, bool* ok) {
         BEMB_CUDA(ctx, cudaMalloc((void**)&px.local, px_bytes(npad)));
         BEMB_CUDA(ctx, cudaMemsetAsync(px.local, 0, px_bytes(npad), ctx->stream));
         px.npad = npad;
-        px.epoch = 0;
         px.base[0] = px.local;
-        ctx->fx.er = 0;
+        // (the epochs keep counting: the CTA inboxes and broadcast slots are older than this allocation)
     }
     FusedLocal& fx = ctx->fx;
     int grid = ctx->fused_grid;
@@ -430,6 +430,13 @@ static int gmres_fused_solve(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t
     p.rblk = fused_pick_rblk(p.S);
     const size_t smem = fused_smem_bytes(p.S, p.rblk, restart);
     if (smem > 200 * 1024) return BEMB200_OK;
+    static const bool want_trace = std::getenv("BEMB200_FUSED_TRACE") != nullptr;
+    unsigned long long* trace_d = nullptr;
+    if (want_trace) {
+        BEMB_CUDA(ctx, cudaMalloc((void**)&trace_d, (size_t)G * 3 * sizeof(unsigned long long)));
+        BEMB_CUDA(ctx, cudaMemsetAsync(trace_d, 0, (size_t)G * 3 * sizeof(unsigned long long), ctx->stream));
+    }
+    p.trace = trace_d;
     FusedResult* res = static_cast<FusedResult*>(fx.result_h);
     std::memset(res, 0, sizeof(FusedResult));
     cudaStream_t s = ctx->stream;
@@ -445,6 +452,27 @@ static int gmres_fused_solve(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t
     BEMB_CUDA(ctx, cudaEventRecord(ws->ev1, s));
     BEMB_CUDA(ctx, cudaStreamSynchronize(s));
     *used = true;
+    if (trace_d) {
+        std::vector<unsigned long long> tr((size_t)G * 3);
+        cudaMemcpy(tr.data(), trace_d, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+        cudaFree(trace_d);
+        double mn = 1e30, mx = 0, av = 0, wmn = 1e30, wmx = 0;
+        int imx = 0, imn = 0;
+        for (uint32_t c = 0; c < G; ++c) {
+            const double t = (double)tr[3 * c] * 1e-6, w = (double)tr[3 * c + 1] * 1e-6;
+            if (tr[3 * c + 2] == p.S) { if (t < mn) { mn = t; imn = (int)c; } if (t > mx) { mx = t; imx = (int)c; } }
+            av += t / G;
+            if (w < wmn) wmn = w;
+            if (w > wmx) wmx = w;
+        }
+        std::fprintf(stderr, "[fused trace rank %d] matvec ms per CTA (full CTAs): min %.3f (cta %d) max %.3f (cta %d) avg(all) %.3f; round wait ms min %.3f max %.3f; total %.3f ms, %llu matvecs\n",
+                     ctx->rank, mn, imn, mx, imx, av, wmn, wmx, (double)res->t_total_ns * 1e-6, res->matvecs);
+        for (uint32_t c = 0; c < G; c += 8) {
+            std::fprintf(stderr, "   cta %3u:", c);
+            for (uint32_t e = c; e < c + 8 && e < G; ++e) std::fprintf(stderr, " %7.3f/%6.3f", (double)tr[3 * e] * 1e-6, (double)tr[3 * e + 1] * 1e-6);
+            std::fprintf(stderr, "\n");
+        }
+    }
     if (res->error || !res->done) {
         fx.disabled = true;
         px.epoch += 1u << 20;  // whatever the aborted kernel left in the buffers is older than anything written from now on

@@ -90,6 +90,28 @@ __device__ __forceinline__ void ll_wait_many(cplx (&out)[N], const uint4* const 
         for (int e = 0; e < N; ++e)
             if (!have[e]) { have[e] = ll_try(q[e], flag, out[e]); all = all && have[e]; }
         if (all) return;
+        // back off between passes: thousands of threads spinning on L2 would starve the producers they are waiting for
+        __nanosleep(spins < 4 ? 40u : (spins < 16 ? 120u : 400u));
+        if ((++spins & 255u) == 0) {
+            if (*ctl.abort_s) return;
+            const unsigned long long t = gtimer();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > ctl.timeout_ns) {
+                *ctl.abort_s = 1;
+                ctl.result->error = 1;
+                return;
+            }
+        }
+    }
+}
+// spin (bounded, with back-off) until ONE element carries `flag`; used by a few probe lanes so that the bulk of the
+// consumers touches the buffer only when the data is (almost certainly) there
+__device__ __forceinline__ void ll_probe(const uint4* q, uint32_t flag, const Ctl& ctl) {
+    cplx dummy;
+    unsigned long long t0 = 0;
+    unsigned spins = 0;
+    while (!ll_try(q, flag, dummy)) {
+        __nanosleep(spins < 8 ? 60u : 250u);
         if ((++spins & 255u) == 0) {
             if (*ctl.abort_s) return;
             const unsigned long long t = gtimer();
@@ -204,6 +226,9 @@ __device__ __forceinline__ void matvec_rows(const FusedParams& p, const Smem& sm
                     col[c] = cc < n ? cc : n - 1;  // clamped address, zero x: contributes nothing
                     q[c] = xin + 2 * (size_t)col[c];
                 }
+                // two probe lanes per warp wait for the ends of the warp's 128-column slab, then everybody loads
+                if ((lane == 0 && want[0]) || (lane == 31 && want[CPL - 1])) ll_probe(lane == 0 ? q[0] : q[CPL - 1], ex, ctl);
+                __syncwarp();
                 ll_wait_many<CPL>(xr, q, want, ex, ctl);
             }
             for (uint32_t rp = 0; rp < npairs; rp += 2) {
@@ -325,8 +350,10 @@ __device__ __forceinline__ void round_broadcast(const FusedParams& p, const Smem
     if (blockIdx.x == 0) {
         __syncthreads();  // bc_s complete
         if (tid < nb) ll_put(p.hbuf + ((size_t)(er & 1u) * KMAX + tid) * 2, sm.bc_s[tid], er);
-    } else if (tid < nb) {
-        sm.bc_s[tid] = ll_wait1(p.hbuf + ((size_t)(er & 1u) * KMAX + tid) * 2, er, ctl);
+    } else {
+        if (tid == 0) ll_probe(p.hbuf + ((size_t)(er & 1u) * KMAX + nb - 1) * 2, er, ctl);  // one prober per CTA
+        __syncthreads();
+        if (tid < nb) sm.bc_s[tid] = ll_wait1(p.hbuf + ((size_t)(er & 1u) * KMAX + tid) * 2, er, ctl);
     }
     __syncthreads();
 }
@@ -430,6 +457,7 @@ __device__ __forceinline__ void gmres_body(const FusedParams& p) {
     unsigned long long total_iterations = 0, restarts = 0, matvecs = 0;
     double b_norm = 0.0;
     unsigned long long t_begin = 0, t_mv = 0, t_round = 0;
+    unsigned long long tc_mv = 0, tc_wait = 0, tc_mark = 0;  // per-CTA trace (thread 0): time inside matvec_rows, time from posting partials to payload
     if (cta == 0 && tid == 0) t_begin = gtimer();
     int final_code = 0;       // 1: converged, 0: cycle budget exhausted
     double final_res = 0.0;
@@ -499,10 +527,10 @@ __device__ __forceinline__ void gmres_body(const FusedParams& p) {
             if (!norm_only) {
                 next_epoch(ex);
                 publish_rows(p, sm.u_s, rb, sc, ex);
-                if (cta == 0 && tid == 0) tm0 = gtimer();
+                if (tid == 0) tm0 = gtimer();
                 matvec_rows(p, sm, rb, sc, ex, ctl);
                 ABORT_CHECK();
-                if (cta == 0 && tid == 0) { t_mv += gtimer() - tm0; matvecs += 1; }
+                if (tid == 0) { const unsigned long long dt = gtimer() - tm0; tc_mv += dt; if (cta == 0) { t_mv += dt; matvecs += 1; } }
                 if (p.pinv) {
                     for (uint32_t i = tid; i < sc; i += FT) sm.w_s[i] = sm.w_s[i] * ldcg_c(p.pinv + p.row0 + rb + i);
                     __syncthreads();
@@ -565,6 +593,7 @@ __device__ __forceinline__ void gmres_body(const FusedParams& p) {
             }
             __syncthreads();
             next_epoch(er);
+            if (tid == 0) tc_mark = gtimer();
             round_gather(p, sm, K, er, ctl);
             ABORT_CHECK();
             // ---- reducer: norm, scaling, forward substitution, Givens of the previous column, decision ----------
@@ -651,6 +680,7 @@ __device__ __forceinline__ void gmres_body(const FusedParams& p) {
             }
             round_broadcast(p, sm, nb, er, ctl);
             ABORT_CHECK();
+            if (tid == 0) tc_wait += gtimer() - tc_mark;
             if (cta == 0 && tid == 0) t_round += gtimer() - tr0;
             const int code = (int)sm.bc_s[0].re;
             if (code == 0) {
@@ -735,6 +765,11 @@ __device__ __forceinline__ void gmres_body(const FusedParams& p) {
     }
     __syncthreads();
     if (abort_s) return;
+    if (p.trace && tid == 0) {
+        p.trace[3 * cta + 0] = tc_mv;
+        p.trace[3 * cta + 1] = tc_wait;
+        p.trace[3 * cta + 2] = sc;
+    }
     if (cta == 0 && tid == 0) {
         FusedResult* r = p.result;
         r->iterations = total_iterations;

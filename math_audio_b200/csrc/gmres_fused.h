@@ -43,6 +43,7 @@ struct FusedParams {
     FusedResult* result; // device-visible (mapped pinned) record
     uint32_t S;          // rows per CTA
     uint32_t rblk;       // rows per matvec pass inside a CTA (even)
+    unsigned long long* trace;  // optional [G][3]: per CTA ns inside matvec_rows, ns waiting for round payloads, rows owned
 };
 
 size_t fused_smem_bytes(uint32_t S, uint32_t rblk, uint32_t restart);
