@@ -31,6 +31,12 @@ struct FusedLocal {
     int grid = 0;               // CTAs the buffers were sized for
     uint32_t er = 0;            // last reduction-round epoch used
     bool disabled = false;      // a solve timed out: stay on the per-iteration kernels
+    // row ownership weighted by the measured streaming speed of the SM under every CTA (see gmres_fused_solve)
+    unsigned long long* trace_d = nullptr;  // [grid][4]
+    uint32_t* row_off_d = nullptr;          // [grid + 1]
+    std::vector<double> speed;              // rows per ns of CTA c's SM (empty: not calibrated)
+    std::vector<unsigned> smid;             // SM id CTA c ran on when `speed` was measured
+    int calib_runs = 0;
 };
 
 struct bemb200_ctx {

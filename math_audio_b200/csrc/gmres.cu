@@ -107,6 +107,8 @@ void free_peer_exchange(bemb200_ctx* ctx, bool collective) {
     FusedLocal& fx = ctx->fx;
     if (fx.cpart) cudaFree(fx.cpart);
     if (fx.hbuf) cudaFree(fx.hbuf);
+    if (fx.trace_d) cudaFree(fx.trace_d);
+    if (fx.row_off_d) cudaFree(fx.row_off_d);
     if (fx.result_h) cudaFreeHost(fx.result_h);
     fx = FusedLocal();
     cudaGetLastError();
@@ -358,7 +360,16 @@ static int ensure_fused_exchange(bemb200_ctx* ctx, uint64_t npad, bool* ok) {
     if (!fx.cpart || fx.grid != grid) {
         if (fx.cpart) cudaFree(fx.cpart);
         if (fx.hbuf) cudaFree(fx.hbuf);
+        if (fx.trace_d) cudaFree(fx.trace_d);
+        if (fx.row_off_d) cudaFree(fx.row_off_d);
         fx.cpart = fx.hbuf = nullptr;
+        fx.trace_d = nullptr;
+        fx.row_off_d = nullptr;
+        fx.speed.clear();
+        fx.smid.clear();
+        fx.calib_runs = 0;
+        BEMB_CUDA(ctx, cudaMalloc((void**)&fx.trace_d, (size_t)grid * 4 * sizeof(unsigned long long)));
+        BEMB_CUDA(ctx, cudaMalloc((void**)&fx.row_off_d, ((size_t)grid + 1) * sizeof(uint32_t)));
         const size_t cb = 2 * (size_t)grid * FUSED_KMAX * 2 * sizeof(uint4), hb = 2 * (size_t)FUSED_KMAX * 2 * sizeof(uint4);
         BEMB_CUDA(ctx, cudaMalloc((void**)&fx.cpart, cb));
         BEMB_CUDA(ctx, cudaMalloc((void**)&fx.hbuf, hb));
@@ -427,16 +438,37 @@ static int gmres_fused_solve(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t
     const uint32_t G = (uint32_t)fx.grid;
     p.S = (p.nloc + G - 1) / G;
     if (p.S == 0) p.S = 1;
+    // Row ownership.  SMs do not stream from HBM equally fast (the SMs of fuller GPCs share their path to L2: 86 ... 103 ms per
+    // 100 matvecs at 20 480 unknowns), and the slowest CTA sets the pace of every iteration.  The first sizeable solve of a context
+    // runs with equal shares and measures rows/ns per CTA (and the SM it sat on); later solves split the slab proportionally.
+    // One refinement, then the table is frozen (same inputs -> same bits from then on); BEMB200_FUSED_BALANCE=0 keeps equal shares.
+    static const int balance = []() { const char* v = std::getenv("BEMB200_FUSED_BALANCE"); return v ? std::atoi(v) : 1; }();
+    p.row_off = nullptr;
+    std::vector<uint32_t> off;
+    if (balance && fx.speed.size() == G && p.nloc >= 8 * G) {
+        double tot = 0.0;
+        for (double v : fx.speed) tot += v;
+        off.assign(G + 1, 0);
+        double cum = 0.0;
+        uint32_t smax = 0;
+        for (uint32_t c = 0; c < G; ++c) {
+            cum += fx.speed[c] / tot;
+            uint32_t e = c + 1 == G ? p.nloc : (uint32_t)std::llround(cum * (double)p.nloc);
+            if (e < off[c]) e = off[c];
+            if (e > p.nloc) e = p.nloc;
+            off[c + 1] = e;
+            if (e - off[c] > smax) smax = e - off[c];
+        }
+        p.S = smax ? smax : 1;
+        BEMB_CUDA(ctx, cudaMemcpyAsync(fx.row_off_d, off.data(), (G + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        BEMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `off` is pageable host memory
+        p.row_off = fx.row_off_d;
+    }
     p.rblk = fused_pick_rblk(p.S);
     const size_t smem = fused_smem_bytes(p.S, p.rblk, restart);
     if (smem > 200 * 1024) return BEMB200_OK;
     static const bool want_trace = std::getenv("BEMB200_FUSED_TRACE") != nullptr;
-    unsigned long long* trace_d = nullptr;
-    if (want_trace) {
-        BEMB_CUDA(ctx, cudaMalloc((void**)&trace_d, (size_t)G * 3 * sizeof(unsigned long long)));
-        BEMB_CUDA(ctx, cudaMemsetAsync(trace_d, 0, (size_t)G * 3 * sizeof(unsigned long long), ctx->stream));
-    }
-    p.trace = trace_d;
+    p.trace = fx.trace_d;
     FusedResult* res = static_cast<FusedResult*>(fx.result_h);
     std::memset(res, 0, sizeof(FusedResult));
     cudaStream_t s = ctx->stream;
@@ -452,25 +484,47 @@ static int gmres_fused_solve(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t
     BEMB_CUDA(ctx, cudaEventRecord(ws->ev1, s));
     BEMB_CUDA(ctx, cudaStreamSynchronize(s));
     *used = true;
-    if (trace_d) {
-        std::vector<unsigned long long> tr((size_t)G * 3);
-        cudaMemcpy(tr.data(), trace_d, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-        cudaFree(trace_d);
-        double mn = 1e30, mx = 0, av = 0, wmn = 1e30, wmx = 0;
-        int imx = 0, imn = 0;
-        for (uint32_t c = 0; c < G; ++c) {
-            const double t = (double)tr[3 * c] * 1e-6, w = (double)tr[3 * c + 1] * 1e-6;
-            if (tr[3 * c + 2] == p.S) { if (t < mn) { mn = t; imn = (int)c; } if (t > mx) { mx = t; imx = (int)c; } }
-            av += t / G;
-            if (w < wmn) wmn = w;
-            if (w > wmx) wmx = w;
+    if (res->done && !res->error) {
+        std::vector<unsigned long long> tr((size_t)G * 4);
+        BEMB_CUDA(ctx, cudaMemcpy(tr.data(), fx.trace_d, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        bool same_map = fx.smid.size() == G;
+        for (uint32_t c = 0; c < G && same_map; ++c) same_map = fx.smid[c] == (unsigned)tr[4 * c + 3];
+        const bool sizeable = p.nloc >= 16 * G && res->matvecs >= 10;
+        if (balance && sizeable && (fx.calib_runs < 2 || !same_map)) {
+            if (!same_map) fx.calib_runs = 0;
+            std::vector<double> sp(G, 0.0);
+            bool good = true;
+            for (uint32_t c = 0; c < G; ++c) {
+                if (tr[4 * c + 2] == 0 || tr[4 * c] == 0) { good = false; break; }
+                sp[c] = (double)tr[4 * c + 2] / (double)tr[4 * c];
+            }
+            if (good) {
+                fx.speed = sp;
+                fx.smid.resize(G);
+                for (uint32_t c = 0; c < G; ++c) fx.smid[c] = (unsigned)tr[4 * c + 3];
+                fx.calib_runs += 1;
+            }
         }
-        std::fprintf(stderr, "[fused trace rank %d] matvec ms per CTA (full CTAs): min %.3f (cta %d) max %.3f (cta %d) avg(all) %.3f; round wait ms min %.3f max %.3f; total %.3f ms, %llu matvecs\n",
-                     ctx->rank, mn, imn, mx, imx, av, wmn, wmx, (double)res->t_total_ns * 1e-6, res->matvecs);
-        for (uint32_t c = 0; c < G; c += 8) {
-            std::fprintf(stderr, "   cta %3u:", c);
-            for (uint32_t e = c; e < c + 8 && e < G; ++e) std::fprintf(stderr, " %7.3f/%6.3f", (double)tr[3 * e] * 1e-6, (double)tr[3 * e + 1] * 1e-6);
-            std::fprintf(stderr, "\n");
+        if (want_trace) {
+            double mn = 1e30, mx = 0, av = 0, wmn = 1e30, wmx = 0;
+            for (uint32_t c = 0; c < G; ++c) {
+                const double t = (double)tr[4 * c] * 1e-6, w = (double)tr[4 * c + 1] * 1e-6;
+                if (t < mn) mn = t;
+                if (t > mx) mx = t;
+                av += t / G;
+                if (w < wmn) wmn = w;
+                if (w > wmx) wmx = w;
+            }
+            std::fprintf(stderr, "[fused trace rank %d] matvec ms per CTA: min %.3f max %.3f avg %.3f; round wait ms min %.3f max %.3f; total %.3f ms, %llu matvecs, "
+                         "weighted %d calib_runs %d S %u\n", ctx->rank, mn, mx, av, wmn, wmx, (double)res->t_total_ns * 1e-6, res->matvecs,
+                         p.row_off ? 1 : 0, fx.calib_runs, p.S);
+            if (std::getenv("BEMB200_FUSED_TRACE_FULL"))
+                for (uint32_t c = 0; c < G; c += 8) {
+                    std::fprintf(stderr, "   cta %3u:", c);
+                    for (uint32_t e = c; e < c + 8 && e < G; ++e)
+                        std::fprintf(stderr, " %7.3f/%6.3f/%llu@%llu", (double)tr[4 * e] * 1e-6, (double)tr[4 * e + 1] * 1e-6, tr[4 * e + 2], tr[4 * e + 3]);
+                    std::fprintf(stderr, "\n");
+                }
         }
     }
     if (res->error || !res->done) {

@@ -40,9 +40,6 @@ namespace {
 
 constexpr int FT = FUSED_THREADS;   // threads per CTA
 constexpr int NW = FT / 32;         // warps per CTA
-constexpr int CPL = 4;              // matrix columns per lane and segment
-constexpr int WCOLS = 32 * CPL;     // columns per warp and segment
-constexpr int SEGW = NW * WCOLS;    // columns per segment (2048)
 constexpr int KMAX = FUSED_KMAX;    // values per reduction round: 2 (restart + 1) + 2 <= 130
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -175,7 +172,7 @@ __device__ __forceinline__ double rnorm(cplx a) { return __dsqrt_rn(rnorm_sqr(a)
 
 // shared-memory carve-up (dynamic)
 struct Smem {
-    double* ypart;   // [pairs_blk][NW][4]  matvec partial sums (re0, im0, re1, im1) per row pair and warp; P2 aliases it
+    double* ypart;   // [rblk][NW][2]  matvec partial sums (re, im) per row and warp; P2 aliases it
     cplx* w_s;       // [S]  A z on this CTA's rows
     cplx* u_s;       // [S]  u_j (un-normalised current basis vector) on this CTA's rows
     cplx* part_s;    // [KMAX] this CTA's partials of the round
@@ -200,17 +197,19 @@ __device__ __forceinline__ int rp_off(int c) { return (c * (c + 1)) / 2; }      
 // segment sg: its 4 x-values per lane stay in registers while it walks the CTA's rows two pairs at a time (16
 // independent 16-byte streaming loads in flight per lane); per (row pair, warp) partial sums are accumulated in shared
 // memory in segment order and added over the warps in warp order: deterministic.
+template <int RB, int CPL>
 __device__ __forceinline__ void matvec_rows(const FusedParams& p, const Smem& sm, uint32_t rb, uint32_t sc, uint32_t ex, const Ctl& ctl) {
+    constexpr int WCOLS = 32 * CPL;   // columns per warp and segment
+    constexpr int SEGW = NW * WCOLS;  // columns per segment
+    static_assert(RB == 2 || RB == 4, "rows per step");
     const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
     const uint4* xin = p.xbuf[p.rank] + (size_t)(ex & 1u) * 2 * p.npad;
     const uint32_t n = p.n;
     const uint32_t nseg = (n + SEGW - 1) / SEGW;
     for (uint32_t blk = 0; blk < sc; blk += p.rblk) {
         const uint32_t nrows = sc - blk < p.rblk ? sc - blk : p.rblk;
-        const uint32_t npairs = (nrows + 1) / 2;
-        for (uint32_t e = tid; e < npairs * NW * 4; e += FT) sm.ypart[e] = 0.0;
+        for (uint32_t e = tid; e < nrows * NW * 2; e += FT) sm.ypart[e] = 0.0;
         __syncthreads();
-        const uint32_t row_last = rb + sc - 1;
         for (uint32_t sg = 0; sg < nseg; ++sg) {
             const uint32_t cbase = sg * SEGW + wq * WCOLS;
             if (cbase >= n) break;  // warp-uniform: no columns left for this warp
@@ -226,45 +225,46 @@ __device__ __forceinline__ void matvec_rows(const FusedParams& p, const Smem& sm
                     col[c] = cc < n ? cc : n - 1;  // clamped address, zero x: contributes nothing
                     q[c] = xin + 2 * (size_t)col[c];
                 }
-                // two probe lanes per warp wait for the ends of the warp's 128-column slab, then everybody loads
+                // two probe lanes per warp wait for the ends of the warp's column slab, then everybody loads
                 if ((lane == 0 && want[0]) || (lane == 31 && want[CPL - 1])) ll_probe(lane == 0 ? q[0] : q[CPL - 1], ex, ctl);
                 __syncwarp();
                 ll_wait_many<CPL>(xr, q, want, ex, ctl);
             }
-            for (uint32_t rp = 0; rp < npairs; rp += 2) {
-                const cplx* rowp[4];
+            const cplx* arow = p.A + (size_t)(rb + blk) * p.lda;
+            for (uint32_t r0 = 0; r0 < nrows; r0 += RB, arow += RB * p.lda) {
+                const uint32_t nr = nrows - r0;  // rows left (warp-uniform); rows beyond it are neither loaded nor stored
+                double2 a[RB][CPL];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    uint32_t row = rb + blk + 2 * rp + r;
-                    row = row < row_last ? row : row_last;
-                    rowp[r] = p.A + (size_t)row * p.lda;
+                for (int r = 0; r < RB; ++r) {
+                    if ((uint32_t)r < nr) {
+#pragma unroll
+                        for (int c = 0; c < CPL; ++c) a[r][c] = __ldcs(reinterpret_cast<const double2*>(arow + (size_t)r * p.lda + col[c]));
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < CPL; ++c) a[r][c] = make_double2(0.0, 0.0);
+                    }
                 }
-                double2 a[4][CPL];
+                double acc[2 * RB];
 #pragma unroll
-                for (int r = 0; r < 4; ++r)
-#pragma unroll
-                    for (int c = 0; c < CPL; ++c) a[r][c] = __ldcs(reinterpret_cast<const double2*>(rowp[r] + col[c]));
-                double acc[8];
-#pragma unroll
-                for (int v = 0; v < 8; ++v) acc[v] = 0.0;
+                for (int v = 0; v < 2 * RB; ++v) acc[v] = 0.0;
 #pragma unroll
                 for (int c = 0; c < CPL; ++c)
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) cfma2(acc[2 * r], acc[2 * r + 1], a[r][c], xr[c]);
-                const double tot = warp_fold<8>(acc, lane);  // lane 4 v holds value v = 2 r + (re | im)
-                if ((lane & 3) == 0) {
-                    const int v = lane >> 2;
-                    const uint32_t pair = rp + (v >> 2);
-                    if (pair < npairs) sm.ypart[((size_t)pair * NW + wq) * 4 + (v & 3)] += tot;
+                    for (int r = 0; r < RB; ++r) cfma2(acc[2 * r], acc[2 * r + 1], a[r][c], xr[c]);
+                const double tot = warp_fold<2 * RB>(acc, lane);  // lane (32 / (2 RB)) v holds value v = 2 r + (re | im)
+                constexpr int LSH = RB == 4 ? 2 : 3;
+                if ((lane & ((1 << LSH) - 1)) == 0) {
+                    const int v = lane >> LSH;
+                    if ((uint32_t)(v >> 1) < nr) sm.ypart[((size_t)(r0 + (v >> 1)) * NW + wq) * 2 + (v & 1)] += tot;
                 }
             }
         }
         __syncthreads();
         for (uint32_t t = tid; t < nrows; t += FT) {
-            const double* yp = sm.ypart + (size_t)(t >> 1) * NW * 4 + (t & 1) * 2;
+            const double* yp = sm.ypart + (size_t)t * NW * 2;
             double sr = 0.0, si = 0.0;
 #pragma unroll
-            for (int w = 0; w < NW; ++w) { sr += yp[w * 4]; si += yp[w * 4 + 1]; }
+            for (int w = 0; w < NW; ++w) { sr += yp[w * 2]; si += yp[w * 2 + 1]; }
             sm.w_s[blk + t] = C(sr, si);
         }
         __syncthreads();
@@ -414,7 +414,7 @@ __device__ void back_substitute(const Smem& sm, int k) {
     }
 }
 
-template <bool POLITE>
+template <int RB, int CPL>
 __device__ __forceinline__ void gmres_body(const FusedParams& p) {
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ int abort_s;
@@ -426,8 +426,8 @@ __device__ __forceinline__ void gmres_body(const FusedParams& p) {
     {
         unsigned char* q = dyn;
         auto take = [&](size_t bytes) { unsigned char* r = q; q += (bytes + 15) & ~(size_t)15; return r; };
-        sm.ypart = reinterpret_cast<double*>(take((size_t)((p.rblk + 1) / 2) * NW * 4 * sizeof(double) > FT * sizeof(cplx)
-                                                      ? (size_t)((p.rblk + 1) / 2) * NW * 4 * sizeof(double) : FT * sizeof(cplx)));
+        sm.ypart = reinterpret_cast<double*>(take((size_t)p.rblk * NW * 2 * sizeof(double) > FT * sizeof(cplx)
+                                                      ? (size_t)p.rblk * NW * 2 * sizeof(double) : FT * sizeof(cplx)));
         sm.w_s = reinterpret_cast<cplx*>(take((size_t)p.S * sizeof(cplx)));
         sm.u_s = reinterpret_cast<cplx*>(take((size_t)p.S * sizeof(cplx)));
         sm.part_s = reinterpret_cast<cplx*>(take(KMAX * sizeof(cplx)));
@@ -446,10 +446,19 @@ __device__ __forceinline__ void gmres_body(const FusedParams& p) {
     __syncthreads();
     Ctl ctl{&abort_s, p.timeout_ns, p.result};
 
-    // rows of this CTA inside the rank's slab
-    const uint32_t rb = cta * p.S < p.nloc ? cta * p.S : p.nloc;
-    const uint32_t re = rb + p.S < p.nloc ? rb + p.S : p.nloc;
-    const uint32_t sc = re - rb;
+    // rows of this CTA inside the rank's slab: equal shares, or the host's table (shares proportional to the measured
+    // streaming speed of the SM each CTA sits on: SMs of fuller GPCs get less HBM bandwidth)
+    uint32_t rb, sc;
+    if (p.row_off) {
+        rb = p.row_off[cta];
+        sc = p.row_off[cta + 1] - rb;
+    } else {
+        rb = cta * p.S < p.nloc ? cta * p.S : p.nloc;
+        const uint32_t re = rb + p.S < p.nloc ? rb + p.S : p.nloc;
+        sc = re - rb;
+    }
+    unsigned smid = 0;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     uint32_t ex = p.ex0, er = p.er0;
     auto next_epoch = [](uint32_t& e) { e += 1; if (e == 0) e = 1; };
 
@@ -474,7 +483,7 @@ __device__ __forceinline__ void gmres_body(const FusedParams& p) {
         publish_rows(p, p.x + p.row0 + rb, rb, sc, ex);
         unsigned long long tm0 = 0;
         if (cta == 0 && tid == 0) tm0 = gtimer();
-        matvec_rows(p, sm, rb, sc, ex, ctl);
+        matvec_rows<RB, CPL>(p, sm, rb, sc, ex, ctl);
         ABORT_CHECK();
         if (cta == 0 && tid == 0) { t_mv += gtimer() - tm0; matvecs += 1; }
         double bn2 = 0.0, rn2 = 0.0;
@@ -528,7 +537,7 @@ __device__ __forceinline__ void gmres_body(const FusedParams& p) {
                 next_epoch(ex);
                 publish_rows(p, sm.u_s, rb, sc, ex);
                 if (tid == 0) tm0 = gtimer();
-                matvec_rows(p, sm, rb, sc, ex, ctl);
+                matvec_rows<RB, CPL>(p, sm, rb, sc, ex, ctl);
                 ABORT_CHECK();
                 if (tid == 0) { const unsigned long long dt = gtimer() - tm0; tc_mv += dt; if (cta == 0) { t_mv += dt; matvecs += 1; } }
                 if (p.pinv) {
@@ -766,9 +775,10 @@ __device__ __forceinline__ void gmres_body(const FusedParams& p) {
     __syncthreads();
     if (abort_s) return;
     if (p.trace && tid == 0) {
-        p.trace[3 * cta + 0] = tc_mv;
-        p.trace[3 * cta + 1] = tc_wait;
-        p.trace[3 * cta + 2] = sc;
+        p.trace[4 * cta + 0] = tc_mv;
+        p.trace[4 * cta + 1] = tc_wait;
+        p.trace[4 * cta + 2] = sc;
+        p.trace[4 * cta + 3] = smid;
     }
     if (cta == 0 && tid == 0) {
         FusedResult* r = p.result;
@@ -787,35 +797,37 @@ __device__ __forceinline__ void gmres_body(const FusedParams& p) {
     }
 }
 
-__global__ void __launch_bounds__(FUSED_THREADS, 1) gmres_fused_kernel(const __grid_constant__ FusedParams p) { gmres_body<false>(p); }
+__global__ void __launch_bounds__(FUSED_THREADS, 1) gmres_fused_kernel(const __grid_constant__ FusedParams p) { gmres_body<4, 4>(p); }
+__global__ void __launch_bounds__(FUSED_THREADS, 1) gmres_fused_kernel_w(const __grid_constant__ FusedParams p) { gmres_body<2, 8>(p); }
 
 }  // namespace
 
 size_t fused_smem_bytes(uint32_t S, uint32_t rblk, uint32_t restart) {
     const size_t m = restart, m1 = m + 1;
     auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
-    size_t yb = (size_t)((rblk + 1) / 2) * NW * 4 * sizeof(double);
+    size_t yb = (size_t)rblk * NW * 2 * sizeof(double);
     if (yb < FT * sizeof(cplx)) yb = FT * sizeof(cplx);
     size_t t = al(yb) + 2 * al((size_t)S * sizeof(cplx)) + 2 * al(KMAX * sizeof(cplx)) + al((FT + 32) * sizeof(cplx)) + al(KMAX * sizeof(cplx));
     t += 2 * al((m1 * m / 2 + 1) * sizeof(cplx)) + 2 * al(m1 * sizeof(cplx)) + 2 * al((m1 + 1) * sizeof(cplx)) + al(m1 * sizeof(cplx));
     return t;
 }
 
-// rows per pass of the matvec inside a CTA: as many as fit 64 KB of partial sums, even
+// rows per pass of the matvec inside a CTA: as many as fit 64 KB of partial sums
 uint32_t fused_pick_rblk(uint32_t S) {
     const uint32_t cap = 256;
-    uint32_t r = S < cap ? S : cap;
-    if (r & 1u) r += 1;
-    return r ? r : 2;
+    const uint32_t r = S < cap ? S : cap;
+    return r ? r : 1;
 }
 
 cudaError_t launch_gmres_fused(const FusedParams& p, int grid, size_t smem, cudaStream_t s) {
     static std::atomic<unsigned long long> attr_done[64];
+    static const int variant = []() { const char* v = std::getenv("BEMB200_FUSED_VARIANT"); return v ? std::atoi(v) : 0; }();
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) dev = 63;
     if (attr_done[dev].load() < smem) {
         cudaError_t e = cudaFuncSetAttribute(gmres_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gmres_fused_kernel_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_done[dev].store(smem);
     }
@@ -829,6 +841,7 @@ cudaError_t launch_gmres_fused(const FusedParams& p, int grid, size_t smem, cuda
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (variant == 1) return cudaLaunchKernelEx(&cfg, gmres_fused_kernel_w, p);
     return cudaLaunchKernelEx(&cfg, gmres_fused_kernel, p);
 }
 

@@ -41,9 +41,10 @@ struct FusedParams {
     uint32_t ex0, er0;   // last epochs used on these buffers
     unsigned long long timeout_ns;
     FusedResult* result; // device-visible (mapped pinned) record
-    uint32_t S;          // rows per CTA
-    uint32_t rblk;       // rows per matvec pass inside a CTA (even)
-    unsigned long long* trace;  // optional [G][3]: per CTA ns inside matvec_rows, ns waiting for round payloads, rows owned
+    uint32_t S;          // rows per CTA (the largest share when row_off is given)
+    uint32_t rblk;       // rows per matvec pass inside a CTA
+    const uint32_t* row_off;    // optional [G + 1]: first slab row of every CTA (weighted shares); nullptr: equal shares of S rows
+    unsigned long long* trace;  // optional [G][4]: per CTA ns inside matvec_rows, ns waiting for round payloads, rows owned, SM id
 };
 
 size_t fused_smem_bytes(uint32_t S, uint32_t rblk, uint32_t restart);

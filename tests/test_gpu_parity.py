@@ -675,6 +675,12 @@ def test_config2_sampled_rows_and_solve(bem, orc, big, ka):
     for r in rows[:8]:
         Ao, _, _ = orc.assemble(mesh, ph.wave_number, beta, row_begin=r, row_end=r + 1)
         assert abs(y2[r] - (Ao @ x2)[0]) < 1e-12 * np.linalg.norm(Ao) * np.linalg.norm(x2)
+    # full x parity against the committed oracle solution (LAPACK LU of the oracle's matrix) and the
+    # oracle's GMRES iteration / restart counts at this size (tests/golden/make_golden_large.py config2)
+    tag = f"{ka:g}".replace(".", "p")
+    gold = np.load(Path(__file__).resolve().parent / "golden" / f"config2_x_ka{tag}.npz")
+    assert np.linalg.norm(sol.x - gold["x"]) / np.linalg.norm(gold["x"]) < X_TOL
+    assert sol.iterations == int(gold["iterations"]) and sol.restarts == int(gold["restarts"])
     if ka < 0.5:
         # +K' branch: closed-surface row sums = -1/2 + K'[1] + beta E[1] ~ -1 (tbem.rs:487-493); the
         # beta E[1] quadrature residue is O(0.1) here, exactly as in the oracle

@@ -1,0 +1,106 @@
+"""The C++ oracle (oracle/bem_oracle.cpp) against a SECOND restatement written independently from the Rust sources
+(oracle/independent/bem_numpy.py; its tables come from its own parser of gauss.rs).  With no Rust toolchain and no
+numeric golden vectors in the reference this is the strongest pin of the oracle available: every
+matrix entry to 1e-13, every GMRES iteration / restart count, and the table of BASELINE.md section 3."""
+import numpy as np
+import pytest
+
+from math_audio_b200.incident import IncidentField
+from math_audio_b200.mesh import generate_box_mesh_quad, generate_icosphere_mesh
+from math_audio_b200.types import PhysicsParams
+from oracle import oracle as orc
+from oracle.independent import bem_numpy as ind
+
+A_RADIUS = 0.1
+TOL = 1e-13
+
+
+def _case(sub, ka):
+    mesh = generate_icosphere_mesh(A_RADIUS, sub)
+    ph = PhysicsParams.from_wave_number(ka / A_RADIUS)
+    beta, _ = ph.burton_miller_beta_adaptive(A_RADIUS)
+    conn = [list(map(int, c[: mesh.etype[i]])) for i, c in enumerate(mesh.conn)]
+    return mesh, ph, complex(beta), conn
+
+
+def _rows(mesh, ph, beta, conn, rows):
+    return ind.assemble_rows(mesh.nodes, conn, mesh.etype, mesh.center, mesh.normal, mesh.area, ph.wave_number, beta, rows)
+
+
+def test_tables_match_the_oracles():
+    """two independent transcriptions of gauss.rs: the json parsed here vs the header the oracle / kernels compile"""
+    for order in (1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 16, 20):
+        x, w = orc.gauss_legendre(order)
+        xi, wi = ind.gauss_legendre(order)
+        assert np.array_equal(x, xi) and np.array_equal(w, wi)
+    for order in (1, 2, 3, 4):
+        assert np.array_equal(orc.triangle_quadrature(order), ind.triangle_quadrature(order))
+    assert len(ind.gauss_legendre(9)[0]) == 12 and len(ind.gauss_legendre(13)[0]) == 16  # rounds UP (gauss.rs:43-57)
+
+
+def test_icosphere2_every_entry_and_gmres_counts():
+    """icosphere(2), N = 320, ka = 0.2 (+K' branch, beta = i/k): all 102 400 entries,
+    GMRES(50) 14 iterations at 1e-6 and 21 at 1e-10, L2 error vs Mie 0.483 %."""
+    mesh, ph, beta, conn = _case(2, 0.2)
+    Ao, rhs0, _ = orc.assemble(mesh, ph.wave_number, beta)
+    Ai = _rows(mesh, ph, beta, conn, list(range(mesh.n_elem)))
+    assert np.max(np.abs(Ai - Ao) / np.abs(Ao)) < TOL
+    b = rhs0 + IncidentField.plane_wave_z().compute_rhs_with_beta(mesh.center, mesh.normal, ph, beta)
+    for tol, expect in ((1e-6, 14), (1e-10, 21)):
+        xo, io = orc.gmres(Ao, b, max_iterations=100, restart=50, tolerance=tol)
+        xi, ii = ind.gmres(lambda v: Ai @ v, b, 50, tol, 100, sequential_blas=True)
+        assert io["iterations"] == ii["iterations"] == expect and io["restarts"] == ii["restarts"] == 0
+        assert np.linalg.norm(xi - xo) / np.linalg.norm(xo) < 1e-12
+    xlu = np.linalg.solve(Ai, b)
+    r = np.linalg.norm(mesh.center, axis=1)  # the reference evaluates the series at the collocation points (qa_suite.rs)
+    mie = orc.mie_rigid_sphere(ph.wave_number, A_RADIUS, 50, r, np.arccos(mesh.center[:, 2] / r))
+    l2 = np.linalg.norm(xlu - mie) / np.linalg.norm(mie)
+    assert abs(l2 - 0.00483) < 2e-5, l2
+
+
+@pytest.mark.parametrize("ka, its6, its10", [(1.0, 23, 33), (3.0, 26, 37), (6.0, 37, 55)])
+def test_icosphere3_sampled_rows_and_gmres_counts(ka, its6, its10):
+    """icosphere(3), N = 1 280 (-K' branch, beta = 4i/k resp. 16i/k): 32 sampled rows (every
+    near pair and self term of those rows) and the GMRES counts 23/33, 26/37, 37/55 with the independent solver on the
+    oracle's matrix.  (ka = 6 at 1e-10 crosses the restart at 50: both restatements count 55 Arnoldi iterations + 1 restart;
+    the survey's throw-away probe noted 54 "matvecs" there -- a counting difference of that probe across the restart, every
+    count that does not cross a restart is identical in all three.)"""
+    mesh, ph, beta, conn = _case(3, ka)
+    Ao, rhs0, _ = orc.assemble(mesh, ph.wave_number, beta)
+    rows = [0, 1, 2, 3, 639, 640, 1278, 1279] + list(np.random.default_rng(5).integers(4, 1278, 24))
+    Ai = _rows(mesh, ph, beta, conn, rows)
+    assert np.max(np.abs(Ai - Ao[rows]) / np.abs(Ao[rows])) < TOL
+    b = rhs0 + IncidentField.plane_wave_z().compute_rhs_with_beta(mesh.center, mesh.normal, ph, beta)
+    for tol, expect in ((1e-6, its6), (1e-10, its10)):
+        _, io = orc.gmres(Ao, b, max_iterations=100, restart=50, tolerance=tol)
+        _, ii = ind.gmres(lambda v: Ao @ v, b, 50, tol, 100)
+        assert io["iterations"] == ii["iterations"] == expect, (io, ii)
+
+
+def test_singular_quirk_and_restarts():
+    """k h_e >= 1 (icosphere(3) at ka = 8 and 16): nsec2 = 3 / 4 integrates the second sub-triangle nsec2 - 1 times
+    (singular.rs:268-278); restart 10 forces restart cycles through both GMRES implementations."""
+    for ka in (8.0, 16.0):
+        mesh, ph, beta, conn = _case(3, ka)
+        rows = [0, 7, 500, 1279]
+        Ao, rhs0, _ = orc.assemble(mesh, ph.wave_number, beta)
+        Ai = _rows(mesh, ph, beta, conn, rows)
+        assert np.max(np.abs(Ai - Ao[rows]) / np.abs(Ao[rows])) < TOL
+    b = rhs0 + IncidentField.plane_wave_z().compute_rhs_with_beta(mesh.center, mesh.normal, ph, beta)
+    _, io = orc.gmres(Ao, b, max_iterations=8, restart=10, tolerance=1e-10)
+    _, ii = ind.gmres(lambda v: Ao @ v, b, 10, 1e-10, 8)
+    assert io["iterations"] == ii["iterations"] and io["restarts"] == ii["restarts"] and io["converged"] == ii["converged"]
+    assert abs(io["residual"] - ii["residual"]) < 1e-9 * max(io["residual"], 1e-30) + 1e-16
+
+
+def test_quad4_box_rows():
+    """Quad4 path (4x4 Gauss rule, centre + scale sub-elements, CSI8/ETA8 self term) on a closed box, rigid."""
+    mesh = generate_box_mesh_quad(0.32, 0.44, 0.64, 4, 6, 8)
+    ph = PhysicsParams.new(500.0, 343.0, 1.21, False)
+    beta = complex(ph.burton_miller_beta())
+    conn = [list(map(int, c[:4])) for c in mesh.conn]
+    rows = [0, 5, 40, 100, mesh.n_elem - 1]
+    Ao, _, _ = orc.assemble(mesh, ph.wave_number, beta)
+    Ai = _rows(mesh, ph, beta, conn, rows)
+    scale = np.max(np.abs(Ao[rows]), axis=1, keepdims=True)
+    assert np.max(np.abs(Ai - Ao[rows]) / scale) < TOL
