@@ -323,14 +323,18 @@ int bemb200_mesh_stage(bemb200_ctx* ctx, const bemb200_mesh* mesh, bemb200_stage
         bemb200_staged_mesh_free(sm);
         return cuda_fail(ctx, e, "prep_kernel");
     }
-    std::vector<uint32_t> special;
+    std::vector<uint32_t> special, rhs_tri, rhs_quad;
     for (uint32_t j = 0; j < dm.n; ++j) {
         if (cls[j] == COL_SPECIAL) special.push_back(j);
-        else if (cls[j] == COL_FLAT_TRI) dm.n_flat_tri++;
-        else if (cls[j] == COL_FLAT_QUAD) dm.n_flat_quad++;
+        else if (cls[j] == COL_FLAT_TRI) { dm.n_flat_tri++; if (nz[j]) rhs_tri.push_back(j); }
+        else if (cls[j] == COL_FLAT_QUAD) { dm.n_flat_quad++; if (nz[j]) rhs_quad.push_back(j); }
     }
     dm.n_special = (uint32_t)special.size();
+    dm.n_rhs_tri = (uint32_t)rhs_tri.size();
+    dm.n_rhs_quad = (uint32_t)rhs_quad.size();
     STAGE_TRY(dev_alloc_copy(sm, &dm.special_cols, special));
+    STAGE_TRY(dev_alloc_copy(sm, &dm.rhs_cols_tri, rhs_tri));
+    STAGE_TRY(dev_alloc_copy(sm, &dm.rhs_cols_quad, rhs_quad));
     e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
         bemb200_staged_mesh_free(sm);
@@ -492,6 +496,7 @@ int bemb200_assemble_staged(bemb200_ctx* ctx, const bemb200_staged_mesh* sm, con
         return set_error(ctx, BEMB200_ENOMEM, "near-field pair list overflowed twice (pathological mesh: more near pairs than the list can hold)");
     }
     ASM_CUDA(launch_near_list(dm, ph, row_begin, m->A, dm.n, m->rhs, m->near_list, count, s));
+    ASM_CUDA(launch_rhs_far(dm, ph, row_begin, row_end, m->rhs, s));
     ASM_CUDA(launch_special(dm, ph, row_begin, row_end, m->A, dm.n, m->rhs, s));
     ASM_CUDA(launch_self(dm, ph, row_begin, row_end, m->A, dm.n, m->rhs, s));
     ASM_CUDA(cudaEventRecord(m->ev[3], s));
@@ -503,7 +508,8 @@ int bemb200_assemble_staged(bemb200_ctx* ctx, const bemb200_staged_mesh* sm, con
     m->stats.near_pairs = count;
     m->stats.special_pairs = (uint64_t)dm.n_special * nloc;
     m->stats.far_kernel_launches = (uint64_t)far_kernel_launch_count(dm);
-    m->stats.total_launches = m->stats.far_kernel_launches + (count ? 1 : 0) + (dm.n_special ? 1 : 0) + 1;
+    m->stats.total_launches = m->stats.far_kernel_launches + (count ? 1 : 0) + (dm.n_special ? 1 : 0) + 1 +
+                              (dm.n_rhs_tri ? 1 : 0) + (dm.n_rhs_quad ? 1 : 0);
     m->stats.far_ms = far_ms;
     m->stats.total_ms = tot_ms;
     *inout = m;

@@ -689,7 +689,9 @@ __global__ void prep_kernel(DeviceMesh m) {
     // flat <=> n_y*J constant over the rule (1e-13 relative) and the affine model reproduces the
     // quadrature points to 1e-12 of the element size
     const double len = sqrt(dot3(e1, e1)) + sqrt(dot3(e2, e2));
-    bool special = (m.bc_type[j] != 0) || (m.nonzero_bc[j] != 0) || !(j0 > 1e-15) || (dev > 1e-13 * j0) ||
+    // (a non-zero prescribed VELOCITY keeps the column in the far kernel: the entry is that of a rigid element, the
+    //  right-hand-side term is added by rhs_far_kernel; pressure / transfer BCs and warped quads take the generic path)
+    bool special = (m.bc_type[j] != 0) || !(j0 > 1e-15) || (dev > 1e-13 * j0) ||
                    (devp > 1e-12 * len) || !(m.area[j] > 0.0);
     m.col_class[j] = special ? COL_SPECIAL : (et == 3 ? COL_FLAT_TRI : COL_FLAT_QUAD);
 }

@@ -46,6 +46,8 @@ struct RuleConst {
     double b2[NQ_MAX];  // 2 b_q
     double ac, bc;      // ratio-test centre relative to (xi_0, eta_0)
     double ac2, bc2;
+    double xi[NQ_MAX];  // absolute local coordinates of the points (shape functions of the BC interpolation)
+    double eta[NQ_MAX];
 };
 __device__ __constant__ RuleConst d_rule_tri;
 __device__ __constant__ RuleConst d_rule_quad;
@@ -231,6 +233,92 @@ far_kernel(const double* __restrict__ far_k, const double* __restrict__ far_c, c
     }  // work items
 }
 
+
+// Right-hand-side term of the un-subdivided pairs of columns that carry a non-zero prescribed velocity
+// (regular.rs:157-177 with bc_type == 0):  rhs_i += sum_q (zg gamma tau + zht beta0) * (sum_n bc_n N_n(xi_q, eta_q)),
+// zg = w J e^{ikr} / (4 pi r),  zht = zg (ik - 1/r) (-(y_q - x).n_x / r),  beta0 = physics.burton_miller_beta() -- the UNSCALED
+// coupling, whatever beta the matrix was built with.  One warp per row, lanes over the listed columns; the near / far split is
+// the far kernel's (pairs inside the guard band belong to the exact near kernel, which adds their term itself).
+template <int NQ>
+__global__ void __launch_bounds__(256)
+rhs_far_kernel(const double* __restrict__ far_k, const double* __restrict__ far_c, const uint32_t* __restrict__ cols, uint32_t ncols,
+               const double* __restrict__ srcdat, const cplx* __restrict__ bc_val, const uint8_t* __restrict__ bc_len,
+               uint64_t row_begin, uint64_t row_end, double wavruim, double gamtau, cplx beta0, cplx* __restrict__ rhs) {
+    constexpr bool QUAD = (NQ == NQ_QUAD);
+    const RuleConst& rc = QUAD ? d_rule_quad : d_rule_tri;
+    const int lane = threadIdx.x & 31;
+    const uint64_t row = row_begin + (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (row >= row_end) return;
+    const double* sp = srcdat + 8ull * row;
+    const double sx = sp[0], sy = sp[1], sz = sp[2], nxx = sp[3], nxy = sp[4], nxz = sp[5];
+    double accr = 0.0, acci = 0.0;
+    for (uint32_t ci = lane; ci < ncols; ci += 32) {
+        const uint32_t col = cols[ci];
+        if ((uint64_t)col == row) continue;  // the self term belongs to self_kernel
+        const uint32_t tile = col / TILE, t = col % TILE;
+        const double* fc = far_c + (uint64_t)tile * FAR_NCONST * TILE + t;
+        const double* fk = far_k + (uint64_t)tile * NQ_MAX * TILE + t;
+        const double dx = fc[FC_Y0X * TILE] - sx, dy = fc[FC_Y0Y * TILE] - sy, dz = fc[FC_Y0Z * TILE] - sz;
+        const double e1x = fc[FC_E1X * TILE], e1y = fc[FC_E1Y * TILE], e1z = fc[FC_E1Z * TILE];
+        const double e2x = fc[FC_E2X * TILE], e2y = fc[FC_E2Y * TILE], e2z = fc[FC_E2Z * TILE];
+        const double D = fma(dz, dz, fma(dy, dy, dx * dx));
+        const double p1 = fma(dz, e1z, fma(dy, e1y, dx * e1x));
+        const double p2 = fma(dz, e2z, fma(dy, e2y, dx * e2x));
+        double d2c = D;
+        if (QUAD) d2c = fma(rc.ac2, p1, fma(rc.bc2, p2, D + fc[FC_KC * TILE]));
+        if (d2c < fc[FC_THR * TILE]) continue;  // near pair: the exact kernel integrates it (and its right-hand-side term)
+        const double M0 = fma(dz, nxz, fma(dy, nxy, dx * nxx));
+        const double E1 = fma(e1z, nxz, fma(e1y, nxy, e1x * nxx));
+        const double E2 = fma(e2z, nxz, fma(e2y, nxy, e2x * nxx));
+        const int bl = bc_len[col];
+        cplx bc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) bc[i] = i < bl ? bc_val[4ull * col + i] : C(0, 0);
+        double pr = 0.0, pi = 0.0;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const double r2 = (q == 0) ? D : fma(rc.a2[q], p1, fma(rc.b2[q], p2, D + fk[q * TILE]));
+            const double rho = fast_rsqrt(r2);
+            const double r = r2 * rho;
+            double sn, cs;
+            fast_sincos(wavruim * r, sn, cs);
+            const double m = (q == 0) ? M0 : fma(rc.a[q], E1, fma(rc.b[q], E2, M0));
+            // shape functions at the point (only the first bc_len take part: regular.rs:159-164)
+            double N[4];
+            if (QUAD) {
+                const double s1 = 0.25 * (rc.xi[q] + 1.0), s2 = 0.25 * (rc.xi[q] - 1.0), t1 = rc.eta[q] + 1.0, t2 = rc.eta[q] - 1.0;
+                N[0] = s1 * t1; N[1] = -s2 * t1; N[2] = s2 * t2; N[3] = -s1 * t2;
+            } else {
+                N[0] = 1.0 - rc.xi[q] - rc.eta[q]; N[1] = rc.xi[q]; N[2] = rc.eta[q]; N[3] = 0.0;
+            }
+            double zr = 0.0, zi = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { zr = fma(bc[i].re, N[i], zr); zi = fma(bc[i].im, N[i], zi); }
+            const double g = rc.w[q] * rho;               // w / r   (J / 4 pi applied once per pair)
+            const double gr = g * cs, gi = g * sn;        // zg
+            // zht = zg (-rho + i k) (-m rho) = zg (m rho^2 - i k m rho)
+            const double hr = m * rho * rho, hi = -wavruim * m * rho;
+            const double tr = gr * hr - gi * hi, ti = gr * hi + gi * hr;
+            // (zg gamma tau + zht beta0) * zbgao
+            const double fr = gr * gamtau + (tr * beta0.re - ti * beta0.im), fi = gi * gamtau + (tr * beta0.im + ti * beta0.re);
+            pr += fr * zr - fi * zi;
+            pi += fr * zi + fi * zr;
+        }
+        const double j4pi = fc[FC_J4PI * TILE];
+        accr = fma(pr, j4pi, accr);
+        acci = fma(pi, j4pi, acci);
+    }
+#pragma unroll
+    for (int mm = 16; mm >= 1; mm >>= 1) {
+        accr += __shfl_xor_sync(0xffffffffu, accr, mm);
+        acci += __shfl_xor_sync(0xffffffffu, acci, mm);
+    }
+    if (lane == 0) {
+        atomicAdd(&rhs[row - row_begin].re, accr);
+        atomicAdd(&rhs[row - row_begin].im, acci);
+    }
+}
+
 bool g_tables_uploaded[64] = {false};
 
 cudaError_t upload_tables() {
@@ -243,6 +331,8 @@ cudaError_t upload_tables() {
         tri.w[q] = hosttab::BEMQ_TR13[q][2] * 0.5;
         tri.a[q] = hosttab::BEMQ_TR13[q][0] - hosttab::BEMQ_TR13[0][0];
         tri.b[q] = hosttab::BEMQ_TR13[q][1] - hosttab::BEMQ_TR13[0][1];
+        tri.xi[q] = hosttab::BEMQ_TR13[q][0];
+        tri.eta[q] = hosttab::BEMQ_TR13[q][1];
     }
     tri.ac = 0.0; tri.bc = 0.0;  // q = 0 of TR13 is the centroid
     for (int i = 0; i < 4; ++i)
@@ -251,6 +341,8 @@ cudaError_t upload_tables() {
             quad.w[q] = hosttab::BEMQ_GL4_W[i] * hosttab::BEMQ_GL4_W[j];
             quad.a[q] = hosttab::BEMQ_GL4_X[i] - hosttab::BEMQ_GL4_X[0];
             quad.b[q] = hosttab::BEMQ_GL4_X[j] - hosttab::BEMQ_GL4_X[0];
+            quad.xi[q] = hosttab::BEMQ_GL4_X[i];
+            quad.eta[q] = hosttab::BEMQ_GL4_X[j];
         }
     quad.ac = -hosttab::BEMQ_GL4_X[0]; quad.bc = -hosttab::BEMQ_GL4_X[0];  // centre (0,0) relative to q = 0
     for (RuleConst* r : {&tri, &quad}) {
@@ -338,6 +430,22 @@ cudaError_t launch_far_t(const DeviceMesh& m, const Phys& ph, uint64_t row_begin
 }
 
 }  // namespace
+
+cudaError_t launch_rhs_far(const DeviceMesh& m, const Phys& ph, uint64_t row_begin, uint64_t row_end, cplx* rhs, cudaStream_t s) {
+    if (row_end <= row_begin || (m.n_rhs_tri == 0 && m.n_rhs_quad == 0)) return cudaSuccess;
+    cudaError_t e = upload_tables();
+    if (e != cudaSuccess) return e;
+    const uint64_t nrows = row_end - row_begin;
+    const unsigned blocks = (unsigned)((nrows * 32 + 255) / 256);
+    const double gamtau = ph.gamma * ph.tau;
+    if (m.n_rhs_tri)
+        rhs_far_kernel<NQ_TRI><<<blocks, 256, 0, s>>>(m.far_k, m.far_c, m.rhs_cols_tri, m.n_rhs_tri, m.src, m.bc_val, m.bc_len, row_begin,
+                                                     row_end, ph.wavruim, gamtau, ph.beta_unscaled, rhs);
+    if (m.n_rhs_quad)
+        rhs_far_kernel<NQ_QUAD><<<blocks, 256, 0, s>>>(m.far_k, m.far_c, m.rhs_cols_quad, m.n_rhs_quad, m.src, m.bc_val, m.bc_len, row_begin,
+                                                      row_end, ph.wavruim, gamtau, ph.beta_unscaled, rhs);
+    return cudaGetLastError();
+}
 
 int far_kernel_launch_count(const DeviceMesh& m) { return (m.n_flat_tri ? 1 : 0) + (m.n_flat_quad ? 1 : 0); }
 

@@ -323,8 +323,9 @@ static int update_x(bemb200_matrix* m, cplx* x, const std::vector<cplx>& y) {
 }
 
 // ---- persistent fused solve (gmres_fused.cu) ----------------------------------------------------------------
-static const bool g_fused_enabled = []() { const char* v = std::getenv("BEMB200_GMRES_FUSED"); return v ? std::atoi(v) != 0 : true; }();
-static const bool g_fused_shared = []() { const char* v = std::getenv("BEMB200_FUSED_SHARED"); return v ? std::atoi(v) != 0 : false; }();
+// BEMB200_GMRES_FUSED: 0 never, 1 whenever the kernel applies, unset = auto (row-sharded solves: yes; one GPU: the
+// per-iteration kernels, whose hardware-scheduled ZGEMV measured 7 % faster per iteration there -- DESIGN.md section 4.4)
+static const int g_fused_mode = []() { const char* v = std::getenv("BEMB200_GMRES_FUSED"); return v ? (std::atoi(v) != 0 ? 1 : 0) : -1; }();
 static double g_fused_total_ms = 0.0, g_fused_matvec_ms = 0.0, g_fused_round_ms = 0.0;
 static unsigned long long g_fused_rounds = 0;
 
@@ -393,8 +394,9 @@ static int gmres_fused_solve(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t
     *used = false;
     bemb200_ctx* ctx = m->ctx;
     GmresWorkspace* ws = m->ws;
-    if (!g_fused_enabled || ctx->fx.disabled || restart > (uint32_t)FUSED_MAX_RESTART || m->n_rows > 0x7fffffffull) return BEMB200_OK;
-    if (ctx->shared_gpu.load() != 0 && !g_fused_shared) return BEMB200_OK;  // a whole-GPU persistent kernel beside a background assembly
+    if (g_fused_mode == 0 || ctx->fx.disabled || restart > (uint32_t)FUSED_MAX_RESTART || m->n_rows > 0x7fffffffull) return BEMB200_OK;
+    if (g_fused_mode < 0 && ctx->nranks == 1) return BEMB200_OK;
+    const bool polite = ctx->shared_gpu.load() != 0;  // a background assembly shares the SMs: 96-register build
     if (ctx->nranks > MAX_PEERS) return BEMB200_OK;
     bool ok = false;
     int rc = ensure_fused_exchange(ctx, ws->npad, &ok);
@@ -473,7 +475,7 @@ static int gmres_fused_solve(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t
     std::memset(res, 0, sizeof(FusedResult));
     cudaStream_t s = ctx->stream;
     BEMB_CUDA(ctx, cudaEventRecord(ws->ev0, s));
-    cudaError_t le = launch_gmres_fused(p, (int)G, smem, s);
+    cudaError_t le = launch_gmres_fused(p, (int)G, smem, polite, s);
     if (le != cudaSuccess) {
         // e.g. cooperative launch too large for what is free on this device: not an error of the solve
         cudaGetLastError();

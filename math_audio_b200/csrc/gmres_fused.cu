@@ -799,6 +799,9 @@ __device__ __forceinline__ void gmres_body(const FusedParams& p) {
 
 __global__ void __launch_bounds__(FUSED_THREADS, 1) gmres_fused_kernel(const __grid_constant__ FusedParams p) { gmres_body<4, 4>(p); }
 __global__ void __launch_bounds__(FUSED_THREADS, 1) gmres_fused_kernel_w(const __grid_constant__ FusedParams p) { gmres_body<2, 8>(p); }
+// "polite" build: at most 96 registers per thread, so that a background assembly block (128 threads x 128 registers) fits
+// beside a solver CTA on every SM (frequency sweeps: assembly of f + 1 underneath the solve of f)
+__global__ void __maxnreg__(96) gmres_fused_kernel_polite(const __grid_constant__ FusedParams p) { gmres_body<2, 4>(p); }
 
 }  // namespace
 
@@ -819,7 +822,7 @@ uint32_t fused_pick_rblk(uint32_t S) {
     return r ? r : 1;
 }
 
-cudaError_t launch_gmres_fused(const FusedParams& p, int grid, size_t smem, cudaStream_t s) {
+cudaError_t launch_gmres_fused(const FusedParams& p, int grid, size_t smem, bool polite, cudaStream_t s) {
     static std::atomic<unsigned long long> attr_done[64];
     static const int variant = []() { const char* v = std::getenv("BEMB200_FUSED_VARIANT"); return v ? std::atoi(v) : 0; }();
     int dev = 0;
@@ -828,6 +831,7 @@ cudaError_t launch_gmres_fused(const FusedParams& p, int grid, size_t smem, cuda
     if (attr_done[dev].load() < smem) {
         cudaError_t e = cudaFuncSetAttribute(gmres_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gmres_fused_kernel_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gmres_fused_kernel_polite, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_done[dev].store(smem);
     }
@@ -841,6 +845,7 @@ cudaError_t launch_gmres_fused(const FusedParams& p, int grid, size_t smem, cuda
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (polite) return cudaLaunchKernelEx(&cfg, gmres_fused_kernel_polite, p);
     if (variant == 1) return cudaLaunchKernelEx(&cfg, gmres_fused_kernel_w, p);
     return cudaLaunchKernelEx(&cfg, gmres_fused_kernel, p);
 }

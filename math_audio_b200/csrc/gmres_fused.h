@@ -49,6 +49,7 @@ struct FusedParams {
 
 size_t fused_smem_bytes(uint32_t S, uint32_t rblk, uint32_t restart);
 uint32_t fused_pick_rblk(uint32_t S);
-cudaError_t launch_gmres_fused(const FusedParams& p, int grid, size_t smem, cudaStream_t s);
+// polite: the 96-register build that leaves room for a background assembly block on every SM
+cudaError_t launch_gmres_fused(const FusedParams& p, int grid, size_t smem, bool polite, cudaStream_t s);
 
 }  // namespace bemb

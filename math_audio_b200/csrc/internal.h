@@ -31,6 +31,11 @@ struct DeviceMesh {
     uint32_t* special_cols = nullptr;  // [n_special]
     uint32_t n_special = 0;
     uint32_t n_flat_tri = 0, n_flat_quad = 0;
+    // flat velocity-BC columns with a NON-ZERO prescribed velocity: the matrix entry does not depend on the BC value, so they
+    // stay in the far kernel; only their right-hand-side term (regular.rs:157-177) is added by rhs_far_kernel
+    uint32_t* rhs_cols_tri = nullptr;   // [n_rhs_tri]
+    uint32_t* rhs_cols_quad = nullptr;  // [n_rhs_quad]
+    uint32_t n_rhs_tri = 0, n_rhs_quad = 0;
     double avg_radius_first100 = 0.0;  // mean |center| of the first <=100 ELEMENTS (tbem.rs:108-117)
 };
 
@@ -60,6 +65,8 @@ typedef std::vector<std::function<cudaError_t(cudaStream_t)>> FarRelaunch;
 cudaError_t launch_far(const DeviceMesh& m, const Phys& ph, uint64_t row_begin, uint64_t row_end, cplx* A, uint64_t lda,
                        uint2* near_list, unsigned int near_cap, unsigned int* near_count, int background_blocks_per_sm,
                        unsigned int* work_counters, FarRelaunch* relaunch, cudaStream_t s);
+// right-hand-side term of the un-subdivided (row, non-zero-velocity column) pairs; same near/far split as launch_far
+cudaError_t launch_rhs_far(const DeviceMesh& m, const Phys& ph, uint64_t row_begin, uint64_t row_end, cplx* rhs, cudaStream_t s);
 cudaError_t launch_near_list(const DeviceMesh& m, const Phys& ph, uint64_t row_begin, cplx* A, uint64_t lda, cplx* rhs,
                              const uint2* near_list, unsigned int count, cudaStream_t s);
 cudaError_t launch_special(const DeviceMesh& m, const Phys& ph, uint64_t row_begin, uint64_t row_end, cplx* A,
