@@ -594,7 +594,7 @@ def run_native(args):
 
     # ---- the north-star target (config 4) rides along whenever all 8 GPUs of the box are in the job
     config4 = None
-    if world >= 8 or os.environ.get("BENCH_CONFIG4"):
+    if (world >= 8 or os.environ.get("BENCH_CONFIG4")) and not os.environ.get("BENCH_NO_CONFIG4"):
         try:
             del sys_e2e, op_iso
             driver.buffers = [None, None]

@@ -210,9 +210,13 @@ __device__ __forceinline__ void matvec_rows(const FusedParams& p, const Smem& sm
         const uint32_t nrows = sc - blk < p.rblk ? sc - blk : p.rblk;
         for (uint32_t e = tid; e < nrows * NW * 2; e += FT) sm.ypart[e] = 0.0;
         __syncthreads();
-        for (uint32_t sg = 0; sg < nseg; ++sg) {
+        // segments are visited starting with the rank's OWN columns (their part of the vector is published locally and
+        // is there first); the other ranks' parts cross NVLink while this rank already streams
+        const uint32_t sg0 = (uint32_t)(((uint64_t)p.row0 + SEGW / 2) / SEGW) % nseg;
+        for (uint32_t si = 0; si < nseg; ++si) {
+            const uint32_t sg = si + sg0 < nseg ? si + sg0 : si + sg0 - nseg;
             const uint32_t cbase = sg * SEGW + wq * WCOLS;
-            if (cbase >= n) break;  // warp-uniform: no columns left for this warp
+            if (cbase >= n) continue;  // warp-uniform: no columns for this warp in this segment
             cplx xr[CPL];
             uint32_t col[CPL];
             {
@@ -516,7 +520,7 @@ __device__ __forceinline__ void gmres_body(const FusedParams& p) {
             next_epoch(er);
             round_gather(p, sm, 2, er, ctl);
             ABORT_CHECK();
-            if (cta == 0 && tid == 0) {
+            if (cta == 0 && tid == 32) {  // thread 32 owns the solve state (norms, counts, decision)
                 if (need_bnorm) b_norm = __dsqrt_rn(sm.tot_s[1].re);
                 const double rn = __dsqrt_rn(sm.tot_s[0].re);
                 final_code = 0;
@@ -612,7 +616,9 @@ __device__ __forceinline__ void gmres_body(const FusedParams& p) {
                 __shared__ double s_rel;    // relative residual of the column just completed
                 __shared__ int s_code;      // 0 continue, 1 stop, 2 restart
                 __shared__ int s_k;         // columns in the solution update
-                if (tid == 0) {
+                // thread 32 (warp 1): norm, Givens update of the previous column, decision, back substitution;
+                // warp 0, at the same time: forward substitution (I + L) h = a for the new column (discarded on a stop)
+                if (tid == 32) {
                     const double sigma = norm_only ? sm.tot_s[0].re : sm.tot_s[nv + j].re;
                     const double nrm = __dsqrt_rn(sigma);
                     int code = 0, k = 0;
@@ -645,40 +651,41 @@ __device__ __forceinline__ void gmres_body(const FusedParams& p) {
                     s_k = k;
                     if (code == 1) final_res = rel;
                 }
+                if (wq == 0 && !norm_only) {
+                    const double s = __ddiv_rn(1.0, __dsqrt_rn(sm.tot_s[nv + j].re));
+                    // new Gram row L(j, l) = s g'_l
+                    for (int l = lane; l < j; l += 32) sm.Lp[lp_off(l, m1) + j] = C(sm.tot_s[nv + l].re * s, sm.tot_s[nv + l].im * s);
+                    __syncwarp();
+                    auto scaled_a = [&](int k) -> cplx {
+                        if (k >= nv) return C(0, 0);
+                        const double f = k == j ? s * s : s;
+                        return C(sm.tot_s[k].re * f, sm.tot_s[k].im * f);
+                    };
+                    cplx a0 = scaled_a(lane), a1 = scaled_a(lane + 32);
+                    for (int l = 0; l < nv; ++l) {
+                        const cplx src = l < 32 ? a0 : a1;
+                        cplx hl;
+                        hl.re = __shfl_sync(0xffffffffu, src.re, l & 31);
+                        hl.im = __shfl_sync(0xffffffffu, src.im, l & 31);
+                        if (lane > l && lane < nv) {
+                            const cplx lk = sm.Lp[lp_off(l, m1) + lane];
+                            a0.re -= lk.re * hl.re - lk.im * hl.im;
+                            a0.im -= lk.re * hl.im + lk.im * hl.re;
+                        }
+                        if (lane + 32 > l && lane + 32 < nv) {
+                            const cplx lk = sm.Lp[lp_off(l, m1) + lane + 32];
+                            a1.re -= lk.re * hl.re - lk.im * hl.im;
+                            a1.im -= lk.re * hl.im + lk.im * hl.re;
+                        }
+                    }
+                    // (hprev is read by the Givens thread of THIS round: the new column is parked in red4 and moved below)
+                    if (lane < nv) sm.red4[lane] = a0;
+                    if (lane + 32 < nv) sm.red4[lane + 32] = a1;
+                }
                 __syncthreads();
                 const int code = s_code;
                 if (code == 0) {
-                    // (I + L) h = a with the lagged scalings; warp 0, lane = row index (two rows per lane: m + 1 <= 64)
-                    if (wq == 0) {
-                        const double s = s_scal;
-                        // new Gram row L(j, l) = s g'_l
-                        for (int l = lane; l < j; l += 32) sm.Lp[lp_off(l, m1) + j] = C(sm.tot_s[nv + l].re * s, sm.tot_s[nv + l].im * s);
-                        __syncwarp();
-                        auto scaled_a = [&](int k) -> cplx {
-                            if (k >= nv) return C(0, 0);
-                            const double f = k == j ? s * s : s;
-                            return C(sm.tot_s[k].re * f, sm.tot_s[k].im * f);
-                        };
-                        cplx a0 = scaled_a(lane), a1 = scaled_a(lane + 32);
-                        for (int l = 0; l < nv; ++l) {
-                            const cplx src = l < 32 ? a0 : a1;
-                            cplx hl;
-                            hl.re = __shfl_sync(0xffffffffu, src.re, l & 31);
-                            hl.im = __shfl_sync(0xffffffffu, src.im, l & 31);
-                            if (lane > l && lane < nv) {
-                                const cplx lk = sm.Lp[lp_off(l, m1) + lane];
-                                a0.re -= lk.re * hl.re - lk.im * hl.im;
-                                a0.im -= lk.re * hl.im + lk.im * hl.re;
-                            }
-                            if (lane + 32 > l && lane + 32 < nv) {
-                                const cplx lk = sm.Lp[lp_off(l, m1) + lane + 32];
-                                a1.re -= lk.re * hl.re - lk.im * hl.im;
-                                a1.im -= lk.re * hl.im + lk.im * hl.re;
-                            }
-                        }
-                        if (lane < nv) { sm.hprev[lane] = a0; sm.bc_s[2 + lane] = a0; }
-                        if (lane + 32 < nv) { sm.hprev[lane + 32] = a1; sm.bc_s[2 + lane + 32] = a1; }
-                    }
+                    for (int i = tid; i < nv; i += FT) { sm.hprev[i] = sm.red4[i]; sm.bc_s[2 + i] = sm.red4[i]; }
                 } else {
                     for (int i = tid; i < nb - 2; i += FT) sm.bc_s[2 + i] = i < s_k ? sm.ycoef[i] : C(0, 0);
                 }
@@ -705,11 +712,22 @@ __device__ __forceinline__ void gmres_body(const FusedParams& p) {
                     cplx acc = C(0, 0);
                     if (grp < ngrp && i < cnt) {
                         const cplx* vcol = p.V + rb + base + i;
-                        for (int l = (int)grp; l < j; l += (int)ngrp) {
-                            const cplx v = ldcg_c(vcol + (size_t)l * p.ldv);
-                            const cplx h = sm.bc_s[2 + l];
-                            acc.re = fma(h.re, v.re, fma(-h.im, v.im, acc.re));
-                            acc.im = fma(h.re, v.im, fma(h.im, v.re, acc.im));
+                        for (int l0 = (int)grp; l0 < j; l0 += 8 * (int)ngrp) {  // 8 independent loads in flight
+                            cplx v[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const int l = l0 + e * (int)ngrp;
+                                v[e] = l < j ? ldcg_c(vcol + (size_t)l * p.ldv) : C(0, 0);
+                            }
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const int l = l0 + e * (int)ngrp;
+                                if (l < j) {
+                                    const cplx h = sm.bc_s[2 + l];
+                                    acc.re = fma(h.re, v[e].re, fma(-h.im, v[e].im, acc.re));
+                                    acc.im = fma(h.re, v[e].im, fma(h.im, v[e].re, acc.im));
+                                }
+                            }
                         }
                     }
                     if (ngrp > 1) {
@@ -780,12 +798,19 @@ __device__ __forceinline__ void gmres_body(const FusedParams& p) {
         p.trace[4 * cta + 2] = sc;
         p.trace[4 * cta + 3] = smid;
     }
-    if (cta == 0 && tid == 0) {
+    __shared__ int fin_flag;
+    if (cta == 0 && tid == 32) {
         FusedResult* r = p.result;
         r->iterations = total_iterations;
         r->restarts = restarts;
         r->residual = final_res;
         r->converged = final_code;
+        __threadfence_system();
+    }
+    if (tid == 0) fin_flag = 1;
+    __syncthreads();
+    if (cta == 0 && tid == 0 && fin_flag) {
+        FusedResult* r = p.result;
         r->matvecs = matvecs;
         r->ex_final = ex;
         r->er_final = er;
