@@ -296,6 +296,41 @@ def run_reference(args):
     return 0
 
 
+def run_sharded_parity(ctx, rank, world, dev):
+    """Row-sharded parity inside the bench job (the driver's scaling lease is the only place with several GPUs): the committed
+    golden fixtures tests/golden/ico2_ka0p2.npz and ico2_ka6.npz (oracle matrix, right-hand side, GMRES solution and iteration
+    count, frozen by tests/golden/make_golden.py) against this job's ranks -- slab entries, solution, iteration / restart counts.
+    Collective; returns the block on rank 0.  No oracle import."""
+    import torch
+    import torch.distributed as dist
+
+    from math_audio_b200 import bem
+
+    out = {}
+    for name in ("ico2_ka0p2", "ico2_ka6"):
+        gp = ROOT / "tests" / "golden" / f"{name}.npz"
+        if not gp.exists():
+            continue
+        g = np.load(gp)
+        mesh = generate_icosphere_mesh(float(g["a"]), int(g["sub"]))
+        ph = PhysicsParams.from_wave_number(float(g["k"]))
+        system = bem.build_tbem_system_with_beta(mesh, ph, complex(g["beta"]), ctx=ctx)
+        r0, r1 = system.matrix.local_rows
+        A = system.matrix.rows()
+        ent = float(np.max(np.abs(A - g["A"][r0:r1]) / np.abs(g["A"][r0:r1]))) if r1 > r0 else 0.0
+        sol = bem.gmres(bem.DenseOperator(system), g["b"], bem.GmresConfig(max_iterations=1000, restart=50, tolerance=1e-10))
+        dx = float(np.linalg.norm(sol.x - g["x"]) / np.linalg.norm(g["x"]))
+        same = 1.0 if (sol.iterations == int(g["iterations"]) and sol.restarts == int(g["restarts"]) and sol.converged) else 0.0
+        t = torch.tensor([ent, dx, -same], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out[name] = {"max_entry_rel_err": float(t[0]), "x_rel_err": float(t[1]), "iterations": sol.iterations,
+                     "golden_iterations": int(g["iterations"]), "counts_equal_on_every_rank": bool(t[2] <= -1.0),
+                     "ok": bool(t[0] < 1e-10 and t[1] < 1e-8 and t[2] <= -1.0)}
+    out["ranks"] = world
+    return out if rank == 0 else None
+
+
 def run_config4(ctx, rank, world, dev, reps=2):
     """BASELINE.json configs[3] / the north-star target inside the driver-run bench: 121 680-element rigid
     geodesic sphere, ka = 16, adaptive beta, row-sharded over all ranks, one assemble + GMRES(50, 1e-10)
@@ -592,6 +627,8 @@ def run_native(args):
     except Exception as e:  # diagnostics only
         print(f"isolated zgemv measurement failed: {e}", file=sys.stderr)
 
+    # ---- row-sharded parity against the committed golden fixtures (several GPUs exist only in the driver's scaling lease)
+    sharded_parity = run_sharded_parity(ctx, rank, world, dev) if world > 1 else None
     # ---- the north-star target (config 4) rides along whenever all 8 GPUs of the box are in the job
     config4 = None
     if (world >= 8 or os.environ.get("BENCH_CONFIG4")) and not os.environ.get("BENCH_NO_CONFIG4"):
@@ -686,6 +723,8 @@ def run_native(args):
                                   "wall": total_ms / K, "boosted_assemblies": int(boosts_timed),
                                   "note": "kernel times are per-kernel CUDA-event durations; with the sweep pipeline assembly overlaps the solve, so they do not add up to wall"},
     }
+    if sharded_parity is not None:
+        line["sharded_parity"] = sharded_parity
     if config4 is not None:
         line["config4"] = config4
     if world == 1 and not args.no_cpu_baseline:

@@ -29,6 +29,7 @@
 // loop) ~41 DP-pipe instructions per quadrature point.  Nothing but the 16-byte result touches HBM.
 // Pairs that fail the (guard-banded) ratio test are appended to a compact list for the exact
 // near-field kernel, which re-takes the decision bit-faithfully and overwrites the entry.
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 
@@ -51,7 +52,7 @@ struct RuleConst {
 };
 __device__ __constant__ RuleConst d_rule_tri;
 __device__ __constant__ RuleConst d_rule_quad;
-__device__ double2 d_sincos_tab[SINCOS_TAB];  // (cos, sin)(i*pi/256), filled by upload_tables()
+__device__ double2 d_sincos_tab[SINCOS_TAB];  // (cos, sin)(i*pi/1024), filled by upload_tables()
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -65,7 +66,7 @@ far_kernel(const double* __restrict__ far_k, const double* __restrict__ far_c, c
            unsigned int* __restrict__ work_counter) {
     __shared__ __align__(128) double sm_k[NQ * TILE];  // kappa_q, [q][column]
     __shared__ uint32_t s_item;
-    __shared__ __align__(16) double2 sm_tab[SINCOS_TAB];
+    extern __shared__ __align__(16) double2 sm_tab[];  // [SINCOS_TAB] (cos, sin) table: 32 KB, dynamic (static + dynamic > 48 KB)
     __shared__ __align__(8) unsigned long long mbar;
 
     const uint32_t t = threadIdx.x;
@@ -192,6 +193,7 @@ far_kernel(const double* __restrict__ far_k, const double* __restrict__ far_c, c
         //   X = nhc rho + 3 b k nm u + b k nn,   Y = rho [nm (3 b u - b k^2) + b nn] + hck
         // and the contribution of the point is  w u (cs + i sn)(X + iY)
         const double c3 = bk * nn, c2 = beta_im * nn;
+        const double bk3nh = bk3 * nh, b3nh = b3 * nh, bk2nh = bk2 * nh;
         double are = 0.0, aim = 0.0;
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
@@ -203,9 +205,9 @@ far_kernel(const double* __restrict__ far_k, const double* __restrict__ far_c, c
             const double m = (q == 0) ? M0 : fma(rc.a[q], E1, fma(rc.b[q], E2, M0));  // (y_q - x).n_x
             const double rho2 = rho * rho;
             if (BIMAG) {
-                const double nm = nh * m;
-                const double X = fma(nhc, rho, fma(bk3 * nm, rho2, c3));
-                const double Z = fma(nm, fma(b3, rho2, -bk2), c2);
+                // X = nhc rho + (3 b k nh) m rho^2 + c3,  Y = rho [m (3 b nh rho^2 - b k^2 nh) + c2] + hck   (nh = -h folded per pair)
+                const double X = fma(bk3nh, m * rho2, fma(nhc, rho, c3));
+                const double Z = fma(m, fma(b3nh, rho2, -bk2nh), c2);
                 const double Y = fma(rho, Z, hck);
                 const double G = rc.w[q] * rho2;  // w / r^2   (J/(4 pi) is applied once per pair)
                 are = fma(G, fma(cs, X, -(sn * Y)), are);
@@ -397,8 +399,20 @@ cudaError_t launch_far_v(const DeviceMesh& m, const Phys& ph, uint64_t row_begin
     const uint8_t* col_class = m.col_class;
     const uint32_t n = m.n;
     const double wavruim = ph.wavruim, k2 = ph.k2, bre = ph.beta.re, bim = ph.beta.im;
+    constexpr size_t TAB_BYTES = SINCOS_TAB * sizeof(double2);
+    {
+        static std::atomic<unsigned char> attr_done[64];
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64) dev = 63;
+        if (!attr_done[dev].load()) {
+            cudaError_t ae = cudaFuncSetAttribute(far_kernel<NQ, BIMAG, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAB_BYTES);
+            if (ae != cudaSuccess) return ae;
+            attr_done[dev].store(1);
+        }
+    }
     auto launch = [=](cudaStream_t st, unsigned int g, unsigned int* ctr) -> cudaError_t {
-        far_kernel<NQ, BIMAG, MINB><<<g, TILE, 0, st>>>(far_k, far_c, col_class, src, n, row_begin, row_end, rpb, nchunks, total, ipb,
+        far_kernel<NQ, BIMAG, MINB><<<g, TILE, TAB_BYTES, st>>>(far_k, far_c, col_class, src, n, row_begin, row_end, rpb, nchunks, total, ipb,
                                                        wavruim, k2, cH, bre, bim, A, lda, near_list, near_cap, near_count, ctr);
         return cudaGetLastError();
     };

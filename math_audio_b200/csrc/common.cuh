@@ -89,25 +89,22 @@ __device__ __forceinline__ void fast_sincos(double x, double& s_out, double& c_o
     c_out = cc;
 }
 
-// Table variant for the far kernel: reduction by pi/256 against a 512-entry (cos, sin) table held in
-// shared memory (8 KB), degree-4/5 kernels on |t| <= pi/512 (the cos kernel's z^2 coefficient absorbs the
-// truncated z^3/720 at the interval end: max abs error 1.7e-16 over [0, 5000], checked on the host with
-// long-double references and on the device by bemb200_selftest_math) and one complex rotation:
-// 14 DP-pipe instructions, no quadrant selects.  tab[i] = (cos(i*pi/256), sin(i*pi/256)).
-constexpr int SINCOS_TAB = 512;
-constexpr double SINCOS_STEPS_PER_PI = 256.0;
+// Table variant for the far kernel: reduction by pi/1024 against a 2048-entry (cos, sin) table held in shared memory
+// (32 KB), cubic / quartic Taylor kernels on |t| <= pi/2048 (truncation t^5/120 = 7e-17 resp. t^6/720 = 2e-20; max abs error
+// 1.7e-16 over [0, 5000], checked on the host with long-double references and on the device by bemb200_selftest_math) and one
+// complex rotation: 13 DP-pipe instructions, no quadrant selects.  tab[i] = (cos(i*pi/1024), sin(i*pi/1024)).
+constexpr int SINCOS_TAB = 2048;
+constexpr double SINCOS_STEPS_PER_PI = 1024.0;
 __device__ __forceinline__ void fast_sincos_tab(double x, const double2* __restrict__ tab, double& s_out, double& c_out) {
     const double MAGIC = 6755399441055744.0;
-    double tq = fma(x, 81.48733086305042, MAGIC);   // 256/pi
+    double tq = fma(x, 325.94932345220167, MAGIC);  // 1024/pi
     const int idx = __double2loint(tq) & (SINCOS_TAB - 1);
     const double q = tq - MAGIC;
-    double t = fma(-q, 0.01227184630308513, x);     // pi/256 hi  (= pi/64 hi / 4, exact scaling)
-    t = fma(-q, 4.783776559169348e-19, t);         // pi/256 lo
+    double t = fma(-q, 0.0030679615757712823, x);   // pi/1024 hi
+    t = fma(-q, 1.195944139792337e-19, t);          // pi/1024 lo
     const double z = t * t;
-    const double ps = fma(z, 8.3333333333333332e-03, -1.6666666666666666e-01);   // 1/120, -1/6
-    const double pc = fma(z, 4.166661437562094e-02, -0.5);                      // 1/24 - (pi/512)^2/720, -1/2
-    const double sn = fma(t * z, ps, t);
-    const double cs = fma(z, pc, 1.0);
+    const double sn = fma(t * z, -1.6666666666666666e-01, t);
+    const double cs = fma(z, fma(z, 4.1666666666666664e-02, -0.5), 1.0);
     const double2 CS = tab[idx];
     c_out = fma(CS.x, cs, -(CS.y * sn));
     s_out = fma(CS.y, cs, CS.x * sn);
