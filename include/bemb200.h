@@ -280,6 +280,51 @@ int bemb200_room_incident_rhs(const bemb200_room_mesh* rm, double k, uint32_t n_
 int bemb200_room_field_pressure(const bemb200_room_mesh* rm, double k, uint32_t n_sources, const bemb200_room_source* sources,
                                 uint64_t n_points, const double* points, const double* surface_pressure, double* out);
 
+/* ---- pipelined frequency sweep (reference shape: math-bem/examples/audio_frequency_sweep.rs; the per-frequency body of
+ * BemSolver::solve, math-bem/src/core/bem_solver.rs:273-322) ------------------------------------------------------------
+ * The mesh is staged once; with overlap != 0 the FP64 assembly of frequency f+1 runs as a polite background grid
+ * (background_blocks_per_sm persistent blocks per SM, 0 = default 1) on a second stream / matrix buffer underneath the
+ * HBM-bound solve of frequency f, and is joined by full-speed helper blocks when the solve ends first.  Every frequency
+ * is still exactly build_tbem_system_with_beta + gmres.  submit() queues a frequency (any number may be queued; two
+ * matrix buffers exist), next() blocks until the OLDEST queued frequency is solved.  One rank of a row-sharded job:
+ * rank / nranks / nccl_id as for bemb200_ctx_create_ex (every rank submits the same sequence). */
+typedef struct bemb200_sweep bemb200_sweep;
+int bemb200_sweep_create(int device, int rank, int nranks, const uint8_t* nccl_id, const bemb200_mesh* mesh, int overlap,
+                         int background_blocks_per_sm, bemb200_sweep** out);
+uint64_t bemb200_sweep_num_dofs(const bemb200_sweep* sw);
+/* rhs_extra (host, num_dofs complex128, may be NULL) is added to TbemSystem.rhs to form b -- the incident-field term a
+ * caller computes with IncidentField::compute_rhs_with_beta; max_iterations / restart / tolerance = GmresConfig */
+int bemb200_sweep_submit(bemb200_sweep* sw, const bemb200_physics* phys, double beta_re, double beta_im, const double* rhs_extra,
+                         uint32_t max_iterations, uint32_t restart, double tolerance);
+/* x_out: num_dofs complex128 (host); stats and rhs_out (the b that was solved) may be NULL */
+int bemb200_sweep_next(bemb200_sweep* sw, double* x_out, bemb200_gmres_info* info, bemb200_assembly_stats* stats, double* rhs_out);
+uint64_t bemb200_sweep_boosts(const bemb200_sweep* sw);
+void bemb200_sweep_destroy(bemb200_sweep* sw);
+
+/* ---- one process, several devices (SURVEY 8b "Threading": every reference caller -- BemSolver::solve, qa_suite -- is one
+ * process) ----------------------------------------------------------------------------------------------------------------
+ * The group owns one rank context per entry of devices[] (1..8; the same device may be listed more than once: its SMs are
+ * then split between the ranks -- used by the single-GPU test of the sharded solver).  Rows are block partitioned
+ * (bemb200_partition); assembly needs no communication; bemb200_multi_gmres runs the persistent fused GMRES kernel on every
+ * device, the ranks exchanging Krylov vectors and reduction partials through peer-mapped memory
+ * (cudaDeviceEnablePeerAccess; no CUDA IPC, no NCCL).  Calls on one group must not overlap. */
+typedef struct bemb200_multi bemb200_multi;
+typedef struct bemb200_multi_matrix bemb200_multi_matrix;
+int bemb200_multi_create(const int* devices, int n, bemb200_multi** out);
+void bemb200_multi_destroy(bemb200_multi* mg);
+int bemb200_multi_num_ranks(const bemb200_multi* mg);
+const char* bemb200_multi_last_error(const bemb200_multi* mg);
+/* build_tbem_system_with_beta (tbem.rs:96-222), every device assembling its own row block */
+int bemb200_multi_assemble(bemb200_multi* mg, const bemb200_mesh* mesh, const bemb200_physics* phys, double beta_re, double beta_im,
+                           bemb200_multi_matrix** out);
+void bemb200_multi_matrix_free(bemb200_multi_matrix* mm);
+uint64_t bemb200_multi_num_rows(const bemb200_multi_matrix* mm);
+int bemb200_multi_rhs_download(const bemb200_multi_matrix* mm, double* out);  /* TbemSystem.rhs, all rows */
+int bemb200_multi_matrix_download(const bemb200_multi_matrix* mm, uint64_t row_begin, uint64_t row_end, double* out);
+/* gmres / gmres_with_guess (gmres.rs:96-277) on the sharded operator; b, x0 (may be NULL), x_out on the host */
+int bemb200_multi_gmres(const bemb200_multi_matrix* mm, const double* b, const double* x0, uint32_t max_iterations, uint32_t restart,
+                        double tolerance, double* x_out, bemb200_gmres_info* info);
+
 /* ---- measurement helpers ----------------------------------------------------------- */
 /* register-resident DFMA peak of this device in TFLOP/s (2 flop per DFMA) */
 int bemb200_measure_fp64_peak(bemb200_ctx* ctx, double* tflops);

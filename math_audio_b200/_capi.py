@@ -113,6 +113,22 @@ SYMBOLS = {
     "bemb200_selftest_math": (C.c_int, [_VP, C.c_uint64, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "bemb200_measure_allgather": (C.c_int, [_VP, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "bemb200_matrix_device_ptr": (_VP, [_VP]),
+    "bemb200_sweep_create": (C.c_int, [C.c_int, C.c_int, C.c_int, _VP, C.POINTER(CMesh), C.c_int, C.c_int, _PP]),
+    "bemb200_sweep_num_dofs": (C.c_uint64, [_VP]),
+    "bemb200_sweep_submit": (C.c_int, [_VP, C.POINTER(CPhysics), C.c_double, C.c_double, _VP, C.c_uint32, C.c_uint32, C.c_double]),
+    "bemb200_sweep_next": (C.c_int, [_VP, _VP, C.POINTER(CGmresInfo), C.POINTER(CAssemblyStats), _VP]),
+    "bemb200_sweep_boosts": (C.c_uint64, [_VP]),
+    "bemb200_sweep_destroy": (None, [_VP]),
+    "bemb200_multi_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, _PP]),
+    "bemb200_multi_destroy": (None, [_VP]),
+    "bemb200_multi_num_ranks": (C.c_int, [_VP]),
+    "bemb200_multi_last_error": (C.c_char_p, [_VP]),
+    "bemb200_multi_assemble": (C.c_int, [_VP, C.POINTER(CMesh), C.POINTER(CPhysics), C.c_double, C.c_double, _PP]),
+    "bemb200_multi_matrix_free": (None, [_VP]),
+    "bemb200_multi_num_rows": (C.c_uint64, [_VP]),
+    "bemb200_multi_rhs_download": (C.c_int, [_VP, _VP]),
+    "bemb200_multi_matrix_download": (C.c_int, [_VP, C.c_uint64, C.c_uint64, _VP]),
+    "bemb200_multi_gmres": (C.c_int, [_VP, _VP, _VP, C.c_uint32, C.c_uint32, C.c_double, _VP, C.POINTER(CGmresInfo)]),
 }
 
 _lib = None

@@ -100,6 +100,82 @@ class Context:
 _default_ctx: Optional[Context] = None
 
 
+class MultiGpu:
+    """One process, several devices (`bemb200_multi_*`, csrc/sweep.cu): the shape of every reference caller
+    (BemSolver::solve, qa_suite are single processes).  Rows are block partitioned over `devices`; the solve is the
+    persistent fused GMRES kernel on every device with peer-memory exchange.  The same device may be listed twice (its SMs
+    are split): that is how the sharded solver is exercised on a single GPU."""
+
+    def __init__(self, devices):
+        self._lib = _capi.lib()
+        self._h = C.c_void_p()
+        arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+        _capi.check(self._lib.bemb200_multi_create(arr, len(devices), C.byref(self._h)), None)
+        self.nranks = len(devices)
+
+    def build_tbem_system_with_beta(self, mesh: Mesh, physics: PhysicsParams, beta: complex) -> "MultiSystem":
+        cm = _capi.cmesh(mesh)
+        ph = _cphys(physics)
+        beta = complex(beta)
+        h = C.c_void_p()
+        _capi.check(self._lib.bemb200_multi_assemble(self._h, C.byref(cm), C.byref(ph), beta.real, beta.imag, C.byref(h)), None)
+        return MultiSystem(self, h)
+
+    def close(self):
+        if self._h:
+            self._lib.bemb200_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiSystem:
+    """TbemSystem whose matrix is row-sharded over the devices of a MultiGpu group."""
+
+    def __init__(self, group: MultiGpu, handle):
+        self.group, self._h, self._lib = group, handle, _capi.lib()
+        self.num_dofs = int(self._lib.bemb200_multi_num_rows(self._h))
+
+    @property
+    def rhs(self) -> np.ndarray:
+        out = np.empty(self.num_dofs, dtype=np.complex128)
+        _capi.check(self._lib.bemb200_multi_rhs_download(self._h, _capi.ptr(out)), None)
+        return out
+
+    def rows(self, row_begin: int = 0, row_end: Optional[int] = None) -> np.ndarray:
+        row_end = self.num_dofs if row_end is None else row_end
+        out = np.empty((row_end - row_begin, self.num_dofs), dtype=np.complex128)
+        _capi.check(self._lib.bemb200_multi_matrix_download(self._h, row_begin, row_end, _capi.ptr(out)), None)
+        return out
+
+    def gmres(self, b: np.ndarray, config: "GmresConfig", x0: Optional[np.ndarray] = None) -> "GmresSolution":
+        b = np.ascontiguousarray(b, dtype=np.complex128)
+        if b.shape != (self.num_dofs,):
+            raise ValueError("gmres: b has the wrong length")
+        x0a = np.ascontiguousarray(x0, dtype=np.complex128) if x0 is not None else None
+        x = np.empty(self.num_dofs, dtype=np.complex128)
+        info = _capi.CGmresInfo()
+        _capi.check(self._lib.bemb200_multi_gmres(self._h, _capi.ptr(b), _capi.ptr(x0a) if x0a is not None else None,
+                                                  config.max_iterations, config.restart, config.tolerance, _capi.ptr(x), C.byref(info)), None)
+        return GmresSolution(x=x, iterations=int(info.iterations), restarts=int(info.restarts), residual=float(info.residual),
+                             converged=bool(info.converged))
+
+    def close(self):
+        if self._h:
+            self._lib.bemb200_multi_matrix_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def default_context() -> Context:
     global _default_ctx
     if _default_ctx is None:

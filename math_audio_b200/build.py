@@ -33,6 +33,7 @@ UNITS = {
     "postprocess.cu": ["-fmad=false"],
     "room.cu": [],
     "direct.cu": [],
+    "sweep.cu": [],
     "api.cu": [],
 }
 

@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <atomic>
+#include <condition_variable>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -19,6 +21,25 @@ struct PeerExchange {
     unsigned long long epoch = 0;      // last epoch published (identical on all ranks: collective call sequence)
     int* err_h = nullptr;              // mapped pinned int: a consumer kernel timed out waiting for a peer
 };
+
+// Ranks of ONE process (bemb200_multi_*): the exchange buffers are plain device pointers shared through this table instead
+// of CUDA IPC handles; `exchange` is a reusable barrier that hands every rank the pointers of all ranks.
+namespace bemb {
+constexpr int MAX_GROUP_RANKS = 8;
+struct PeerGroup {
+    int nranks = 0;
+    int device[MAX_GROUP_RANKS] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bool peer_ok = true;  // cudaDeviceEnablePeerAccess worked for every pair of distinct devices
+    std::mutex mu;
+    std::condition_variable cv;
+    unsigned char* posted[MAX_GROUP_RANKS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    unsigned char* snap[MAX_GROUP_RANKS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int arrived = 0;
+    unsigned long long generation = 0;
+    // every rank posts `mine` (may be NULL = "I failed"); returns false on a time-out (a rank never arrived)
+    bool exchange(int rank, unsigned char* mine, unsigned char** all);
+};
+}  // namespace bemb
 
 // Buffers of the persistent fused GMRES kernel (gmres_fused.cu) that stay local to the rank: the inbox of CTA
 // partials, the broadcast slots and the result record.  The exchange vectors and the inbox of rank partials live in the
@@ -49,6 +70,7 @@ struct bemb200_ctx {
     void* nccl_comm = nullptr;  // ncclComm_t when nranks > 1
     PeerExchange px;
     FusedLocal fx;
+    std::shared_ptr<bemb::PeerGroup> group;  // set for the rank contexts of a bemb200_multi (one process, several devices)
     int fused_grid = 0;  // > 0: CTAs of the fused GMRES kernel (several ranks sharing one device); 0: one per SM
     std::string err;
     std::mutex mu;  // LinearOperator is Send + Sync: serialise stream submission per context

@@ -83,8 +83,9 @@ static inline size_t px_bytes(uint64_t npad) { return PX_HEADER + 2 * npad * 2 *
 namespace bemb {
 void free_peer_exchange(bemb200_ctx* ctx, bool collective) {
     PeerExchange& px = ctx->px;
-    for (int p = 0; p < ctx->nranks && p < 8; ++p)
-        if (p != ctx->rank && px.base[p]) cudaIpcCloseMemHandle(px.base[p]);
+    if (!ctx->group)  // (ranks of one process share plain pointers: nothing to unmap)
+        for (int p = 0; p < ctx->nranks && p < 8; ++p)
+            if (p != ctx->rank && px.base[p]) cudaIpcCloseMemHandle(px.base[p]);
     bool may_free = true;
     if (px.ok) {
         // nobody frees exported memory while a peer may still have it mapped
@@ -332,10 +333,58 @@ static unsigned long long g_fused_rounds = 0;
 // Exchange vectors for the fused kernel.  One rank: a plain local allocation in the PeerExchange layout; several
 // ranks: the IPC-mapped allocation of ensure_peer_exchange (collective).  Returns with *ok = false when the
 // platform refused peer mappings (the caller then stays on the per-iteration kernels -- agreed by all ranks).
+bool bemb::PeerGroup::exchange(int rank, unsigned char* mine, unsigned char** all) {
+    std::unique_lock<std::mutex> lk(mu);
+    posted[rank] = mine;
+    const unsigned long long gen = generation;
+    if (++arrived == nranks) {
+        for (int p = 0; p < nranks; ++p) snap[p] = posted[p];
+        arrived = 0;
+        generation += 1;
+        cv.notify_all();
+    } else if (!cv.wait_for(lk, std::chrono::seconds(60), [&] { return generation != gen; })) {
+        arrived -= 1;
+        return false;
+    }
+    for (int p = 0; p < nranks; ++p) all[p] = snap[p];
+    return true;
+}
+
 static int ensure_fused_exchange(bemb200_ctx* ctx, uint64_t npad, bool* ok) {
     *ok = false;
     PeerExchange& px = ctx->px;
-    if (ctx->nranks > 1) {
+    if (ctx->nranks > 1 && ctx->group) {
+        // ranks of one process: plain pointers, exchanged through the group table (collective: every rank of the group is
+        // inside the same solve call on its own host thread)
+        if (!px.local || px.npad < npad) {
+            if (px.local) { cudaFree(px.local); px.local = nullptr; }
+            unsigned char* mine = nullptr;
+            if (ctx->group->peer_ok && cudaMalloc((void**)&mine, px_bytes(npad)) == cudaSuccess) {
+                if (cudaMemsetAsync(mine, 0, px_bytes(npad), ctx->stream) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+                    cudaFree(mine);
+                    mine = nullptr;
+                }
+            }
+            cudaGetLastError();
+            unsigned char* all[MAX_GROUP_RANKS];
+            if (!ctx->group->exchange(ctx->rank, mine, all)) {
+                if (mine) cudaFree(mine);
+                return set_error(ctx, BEMB200_ENCCL, "multi-GPU group: a rank never reached the exchange set-up");
+            }
+            bool every = true;
+            for (int p = 0; p < ctx->nranks; ++p) every = every && all[p] != nullptr;
+            // second barrier: nobody frees or writes before everybody has taken the table
+            unsigned char* dummy[MAX_GROUP_RANKS];
+            ctx->group->exchange(ctx->rank, mine, dummy);
+            if (!every) {
+                if (mine) cudaFree(mine);
+                return set_error(ctx, BEMB200_EUNSUPPORTED, "multi-GPU group: peer access between the devices is not available");
+            }
+            px.local = mine;
+            px.npad = npad;
+            for (int p = 0; p < ctx->nranks; ++p) px.base[p] = all[p];
+        }
+    } else if (ctx->nranks > 1) {
         int rc = ensure_peer_exchange(ctx, npad);
         if (rc != BEMB200_OK) return rc;
         if (!px.ok || px.npad < npad) return BEMB200_OK;
@@ -396,6 +445,7 @@ static int gmres_fused_solve(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t
     GmresWorkspace* ws = m->ws;
     if (g_fused_mode == 0 || ctx->fx.disabled || restart > (uint32_t)FUSED_MAX_RESTART || m->n_rows > 0x7fffffffull) return BEMB200_OK;
     if (g_fused_mode < 0 && ctx->nranks == 1) return BEMB200_OK;
+    if (ctx->nranks > 1 && !ctx->group && !ctx->nccl_comm) return BEMB200_OK;
     const bool polite = ctx->shared_gpu.load() != 0;  // a background assembly shares the SMs: 96-register build
     if (ctx->nranks > MAX_PEERS) return BEMB200_OK;
     bool ok = false;

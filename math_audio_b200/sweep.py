@@ -20,7 +20,89 @@ from .mesh import Mesh
 from .types import PhysicsParams
 
 
+class Sweep:
+    """The pipelined frequency sweep behind the C ABI (`bemb200_sweep_*`, csrc/sweep.cu): what a Rust / C caller uses.
+    Host buffers in, host buffers out; the schedule (assembly of frequency f + 1 underneath the solve of f, helper
+    launch when the solve ends first) lives in the library.
+
+        sw = Sweep(mesh)
+        for ph, beta, rhs in cases[:2]: sw.submit(ph, beta, rhs, cfg)      # keep two frequencies in flight
+        for i in range(len(cases)):
+            sol, stats, b = sw.next()
+            if i + 2 < len(cases): sw.submit(*cases[i + 2], cfg)
+    """
+
+    def __init__(self, mesh: Mesh, device: int = 0, rank: int = 0, nranks: int = 1, nccl_id: Optional[bytes] = None,
+                 overlap: bool = True, background_blocks_per_sm: int = 1):
+        import ctypes as C
+
+        from . import _capi
+
+        self._capi, self._C = _capi, C
+        self._lib = _capi.lib()
+        self._h = C.c_void_p()
+        cm = _capi.cmesh(mesh)
+        idbuf = (C.c_uint8 * 128).from_buffer_copy(nccl_id) if nccl_id else None
+        _capi.check(self._lib.bemb200_sweep_create(device, rank, nranks, idbuf, C.byref(cm), 1 if overlap else 0,
+                                                   background_blocks_per_sm, C.byref(self._h)), None)
+        self.n = int(self._lib.bemb200_sweep_num_dofs(self._h))
+        self.mesh_nbytes = _capi.mesh_nbytes(mesh)
+
+    def submit(self, physics: PhysicsParams, beta: complex, rhs_extra: Optional[np.ndarray], config: "bem.GmresConfig") -> None:
+        ph = bem._cphys(physics)
+        beta = complex(beta)
+        extra = None
+        if rhs_extra is not None:
+            extra = np.ascontiguousarray(rhs_extra, dtype=np.complex128)
+            if extra.shape != (self.n,):
+                raise ValueError("rhs_extra has the wrong length")
+        self._capi.check(self._lib.bemb200_sweep_submit(self._h, self._C.byref(ph), beta.real, beta.imag,
+                                                        self._capi.ptr(extra) if extra is not None else None,
+                                                        config.max_iterations, config.restart, config.tolerance), None)
+
+    def next(self):
+        x = np.empty(self.n, dtype=np.complex128)
+        b = np.empty(self.n, dtype=np.complex128)
+        info = self._capi.CGmresInfo()
+        st = self._capi.CAssemblyStats()
+        self._capi.check(self._lib.bemb200_sweep_next(self._h, self._capi.ptr(x), self._C.byref(info), self._C.byref(st),
+                                                      self._capi.ptr(b)), None)
+        sol = bem.GmresSolution(x=x, iterations=int(info.iterations), restarts=int(info.restarts), residual=float(info.residual),
+                                converged=bool(info.converged))
+        return sol, {k: getattr(st, k) for k, _ in st._fields_}, b
+
+    def solve_all(self, cases, config: "bem.GmresConfig") -> list:
+        """cases: sequence of (physics, beta, rhs_extra); two frequencies are kept in flight."""
+        out = []
+        for c in cases[:2]:
+            self.submit(c[0], c[1], c[2], config)
+        for i in range(len(cases)):
+            out.append(self.next())
+            if i + 2 < len(cases):
+                c = cases[i + 2]
+                self.submit(c[0], c[1], c[2], config)
+        return out
+
+    @property
+    def boosts(self) -> int:
+        return int(self._lib.bemb200_sweep_boosts(self._h))
+
+    def close(self):
+        if self._h:
+            self._lib.bemb200_sweep_destroy(self._h)
+            self._h = self._C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class SweepDriver:
+    """The same schedule driven from Python with DEVICE pointers handed to a user callback -- kept for the benchmark's
+    device-resident leg (`value`), which must not touch host buffers; everything else uses `Sweep`."""
+
     def __init__(self, mesh: Mesh, device: int = 0, rank: int = 0, nranks: int = 1, nccl_id: Optional[bytes] = None,
                  solve_stream: int = 0, assembly_stream: int = 0, overlap: bool = True, background_blocks_per_sm: int = 1):
         # the solve context owns the communicator; the assembly context needs none

@@ -8,7 +8,7 @@ fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "nvcc".into());
     // (translation unit, extra flags): the decision-taking kernels forbid FMA contraction
-    let units: [(&str, &[&str]); 10] = [
+    let units: [(&str, &[&str]); 11] = [
         ("assembly_exact.cu", &["-fmad=false"]),
         ("assembly_far.cu", &[]),
         ("linalg.cu", &[]),
@@ -18,6 +18,7 @@ fn main() {
         ("postprocess.cu", &["-fmad=false"]),
         ("room.cu", &[]),
         ("direct.cu", &[]),
+        ("sweep.cu", &[]),
         ("api.cu", &[]),
     ];
     let mut objs = Vec::new();

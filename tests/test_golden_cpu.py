@@ -186,6 +186,40 @@ def test_rust_shim_matches_the_build_and_the_header():
     header = (root / "include" / "bemb200.h").read_text()
     for name in declared:
         assert re.search(rf"\b{name}\(", header), name
+    # every FFI symbol the safe crate calls is declared by the sys crate
+    safe = (root / "rust" / "math-bem-b200" / "src" / "lib.rs").read_text()
+    used = set(re.findall(r"\b(bemb200_\w+)\(", safe))
+    assert used and used <= declared, used - declared
+
+
+def test_rust_manifests_resolve_against_the_reference_workspace():
+    """Cargo resolves dependencies by PACKAGE name (math-solvers, math-bem) while the code imports the LIB names
+    (math_audio_solvers, math_audio_bem); the FFI crate must not depend on the workspace (no cycle), and math-bem must
+    not be asked to depend on the GPU crates."""
+    import re
+    import tomllib
+
+    root = Path(__file__).resolve().parent.parent
+    sysm = tomllib.loads((root / "rust" / "bem-b200-sys" / "Cargo.toml").read_text())
+    safem = tomllib.loads((root / "rust" / "math-bem-b200" / "Cargo.toml").read_text())
+    assert sysm["package"]["name"] == "bem-b200-sys" and sysm["package"]["links"] == "bemb200"
+    assert not sysm.get("dependencies")                      # raw FFI: nothing of the workspace, no cycle possible
+    deps = safem["dependencies"]
+    assert set(deps) == {"bem-b200-sys", "math-solvers", "math-bem", "ndarray", "num-complex"}
+    assert deps["bem-b200-sys"]["path"] == "../bem-b200-sys"
+    expected = {"math-solvers": "math_audio_solvers", "math-bem": "math_audio_bem"}
+    src = (root / "rust" / "math-bem-b200" / "src" / "lib.rs").read_text() + (root / "rust" / "math-bem-b200" / "examples" / "frequency_sweep_b200.rs").read_text()
+    for pkg, libname in expected.items():
+        assert deps[pkg]["path"].endswith(pkg)
+        assert re.search(rf"\buse {libname}::", src), libname
+        ref = Path("/root/reference") / pkg / "Cargo.toml"
+        if ref.exists():  # this container only: the package / lib names are the reference's own
+            m = tomllib.loads(ref.read_text())
+            assert m["package"]["name"] == pkg and m["lib"]["name"] == libname
+            assert "math-bem-b200" not in ref.read_text() and "bem-b200-sys" not in ref.read_text()
+    assert "use bem_b200_sys::" in src and "use math_bem_b200::" in src
+    integ = (root / "INTEGRATION.md").read_text()
+    assert 'cfg(feature = "b200")' not in integ              # the switch is made by the caller, not inside math-bem
 
 
 def test_binding_arities_match_the_header():

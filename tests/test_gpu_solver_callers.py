@@ -6,6 +6,9 @@ these well-conditioned cases (tree vs sequential inner products change only the 
 import numpy as np
 import pytest
 
+from math_audio_b200.mesh import generate_icosphere_mesh
+from math_audio_b200.types import PhysicsParams
+
 pytestmark = pytest.mark.gpu
 
 
@@ -314,3 +317,60 @@ def test_mesh_convergence_forward_back_and_phase(bem, orc):  # :328-416, :419-49
         d = abs(np.angle(fp.p_total) - np.angle(m))
         worst = max(worst, 2 * np.pi - d if d > np.pi else d)
     assert worst < np.pi / 4
+
+
+# ---- the boundary extensions of round 2: single-process multi-GPU group, sweep behind the C ABI ------------------------
+def test_single_process_group_two_ranks_on_one_gpu(bem, orc):
+    """bemb200_multi_*: one process, two rank contexts.  Listing device 0 twice splits its SMs between the two persistent
+    solver kernels, so the row-sharded code path (peer-buffer exchange of the Krylov vector, cross-rank reduction round,
+    sharded Gram-Schmidt) runs on the single GPU of the driver's test box.  Entries, iteration counts, solution vs oracle."""
+    from math_audio_b200.incident import IncidentField
+
+    a = 0.1
+    grp = bem.MultiGpu([0, 0])
+    for sub, ka, restart in ((2, 1.0, 50), (3, 3.0, 50), (3, 8.0, 10)):
+        mesh = generate_icosphere_mesh(a, sub)
+        if sub == 3:
+            mesh.is_eval[-7:] = 1  # n = 1273: uneven split
+        n = mesh.num_dofs
+        ph = PhysicsParams.from_wave_number(ka / a)
+        beta, _ = ph.burton_miller_beta_adaptive(a)
+        system = grp.build_tbem_system_with_beta(mesh, ph, beta)
+        Ao, rhso, _ = orc.assemble(mesh, ph.wave_number, beta)
+        A = system.rows()
+        assert np.max(np.abs(A - Ao) / np.abs(Ao)) < 1e-10
+        b = system.rhs + IncidentField.plane_wave_z().compute_rhs_with_beta(mesh.center[:n], mesh.normal[:n], ph, beta)
+        cfg = bem.GmresConfig(max_iterations=30, restart=restart, tolerance=1e-10)
+        sol = system.gmres(b, cfg)
+        xo, io = orc.gmres(Ao, b, max_iterations=30, restart=restart, tolerance=1e-10)
+        assert (sol.iterations, sol.restarts, sol.converged) == (io["iterations"], io["restarts"], io["converged"])
+        assert np.linalg.norm(sol.x - xo) / np.linalg.norm(xo) < 1e-8
+        system.close()
+    grp.close()
+
+
+def test_c_sweep_equals_sequential_solves(bem, orc):
+    """bemb200_sweep_*: the pipelined schedule behind the C ABI returns, frequency by frequency, what
+    build_tbem_system_with_beta + gmres return when called one after the other (iteration counts equal, x to 1e-9)."""
+    from math_audio_b200.incident import IncidentField
+    from math_audio_b200.sweep import Sweep
+
+    a = 0.1
+    mesh = generate_icosphere_mesh(a, 4)
+    inc = IncidentField.plane_wave_z()
+    cfg = bem.GmresConfig(max_iterations=1000, restart=50, tolerance=1e-10)
+    cases = []
+    for ka in (0.3, 1.0, 2.0, 4.0, 7.0):
+        ph = PhysicsParams.from_wave_number(ka / a)
+        beta, _ = ph.burton_miller_beta_adaptive(a)
+        cases.append((ph, beta, inc.compute_rhs_with_beta(mesh.center, mesh.normal, ph, beta)))
+    sw = Sweep(mesh)
+    got = sw.solve_all(cases, cfg)
+    sw.close()
+    for (ph, beta, rhs), (sol, stats, b) in zip(cases, got):
+        system = bem.build_tbem_system_with_beta(mesh, ph, beta)
+        ref = bem.gmres(bem.DenseOperator(system), system.rhs + rhs, cfg)
+        assert np.array_equal(b, system.rhs + rhs)
+        assert (sol.iterations, sol.restarts, sol.converged) == (ref.iterations, ref.restarts, ref.converged)
+        assert np.linalg.norm(sol.x - ref.x) / np.linalg.norm(ref.x) < 1e-9
+        assert stats["near_pairs"] > 0
