@@ -482,7 +482,7 @@ def run_native(args):
     # schedule: with 1-4 GPUs the FP64 assembly of frequency f+1 hides under the HBM-bound solve of f (measured 4-6 %
     # faster); at 8 GPUs the slabs are small, the solver owns the GPU (whole-GPU Gram-Schmidt kernel, ZGEMV epilogue
     # storing A v into the peers' memory) and the sequential schedule measured faster
-    overlap = (world <= 4) if args.schedule == "auto" else (args.schedule == "pipelined")
+    overlap = (world < 4) if args.schedule == "auto" else (args.schedule == "pipelined")
     if args.no_overlap:
         overlap = False
     driver = SweepDriver(mesh, local_rank, rank, world, nccl_id, solve_stream=s_solve.cuda_stream,
@@ -580,36 +580,50 @@ def run_native(args):
     e2e_seq_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_seq_s, op=dist.ReduceOp.MAX)
-    e2e_s, e2e_schedule = e2e_seq_s, "sequential host-buffer calls: build_tbem_system_with_beta(host mesh) then gmres(host b) per frequency"
-    # (multi-GPU: opt-in with BENCH_E2E_PIPELINED=1; the default there stays the sequential figure)
-    if overlap and not os.environ.get("BENCH_E2E_SEQUENTIAL") and (world == 1 or os.environ.get("BENCH_E2E_PIPELINED")):
-        # the same host-buffer calls issued through the sweep driver (the repo's public sweep API): the host mesh is
-        # re-staged (H2D) for every frequency, TbemSystem.rhs comes back (D2H), b goes up and x comes down per frequency;
-        # only the schedule differs -- assembly of frequency f+1 runs underneath the solve of f
-        def solve_host(i, system, op):
-            ph, beta = cases[args.warmup + i]
-            b = system.rhs_full() + inc.compute_rhs_with_beta(mesh.center, mesh.normal, ph, beta)
-            sol = bem.gmres(op, b, cfg)
-            x_pinned[:] = sol.x
-            return sol
+    # ---- the same frequencies through the sweep API of the C ABI (bemb200_sweep_*, what a Rust / C caller of a sweep uses): the
+    # mesh is staged once by the sweep object, every frequency passes HOST buffers -- physics, the incident right-hand side
+    # computed on the host, b H2D inside bemb200_gmres, TbemSystem.rhs and x D2H -- and the library pipelines the assembly of
+    # frequency f + 1 underneath the solve of f (1-2 GPUs) or runs them back to back with the fused solver (4 GPUs on)
+    from math_audio_b200.sweep import Sweep
 
-        e2e_cases = cases[args.warmup: args.warmup + e2e_steps]
-        driver.run(e2e_cases[:2], cfg, solve_host, restage_host_mesh=True)  # untimed: first use of the host path in the driver
-        barrier()
-        t0 = time.perf_counter()
-        if driver.trace is not None:
-            driver.trace.clear()
-        sols_e2e = driver.run(e2e_cases, cfg, solve_host, restage_host_mesh=True)
-        barrier()
-        if driver.trace is not None and rank == 0:
-            for lab, ci, ts in sorted(driver.trace, key=lambda r: r[2]):
-                print(f"[e2e trace] {ts * 1e3:9.2f} ms  {lab:12s} case {ci}", file=sys.stderr)
-        e2e_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-        assert all(so.converged for so in sols_e2e)
-        e2e_schedule = ("sweep driver with host buffers: host mesh staged, rhs fetched, b uploaded and x downloaded per frequency; "
-                        "assembly of frequency f+1 overlaps the solve of f")
+    nid2 = None
+    if world > 1:
+        nid2 = bdist.broadcast_bytes(bem.Context.nccl_unique_id() if rank == 0 else None, 128, 0, device=dev)
+    csw = Sweep(mesh, local_rank, rank, world, nid2, overlap=overlap, background_blocks_per_sm=args.background)
+    e2e_cases = cases[args.warmup: args.warmup + e2e_steps]
+
+    def run_csweep(cs):
+        outs = []
+
+        def sub(c):
+            ph, beta = c
+            csw.submit(ph, beta, inc.compute_rhs_with_beta(mesh.center, mesh.normal, ph, beta), cfg)
+
+        for c in cs[:2]:
+            sub(c)
+        for i in range(len(cs)):
+            sol, _st, _b = csw.next()
+            x_pinned[:] = sol.x
+            outs.append(sol)
+            if i + 2 < len(cs):
+                sub(cs[i + 2])
+        return outs
+
+    run_csweep(e2e_cases[:2])  # untimed: buffers of the sweep object, first use of its solver workspace
+    barrier()
+    t0 = time.perf_counter()
+    sols_e2e = run_csweep(e2e_cases)
+    barrier()
+    e2e_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    assert all(so.converged for so in sols_e2e)
+    h2d_sw = n * 16                 # b
+    d2h_sw = nloc * 16 + n * 16     # TbemSystem.rhs (local rows; the other ranks' rows arrive over NVLink) + x
+    e2e_schedule = ("bemb200_sweep_* (C ABI) with host buffers: mesh staged once at sweep creation; per frequency the incident right-hand "
+                    "side is computed on the host, b goes up, TbemSystem.rhs and x come down; "
+                    + ("assembly of frequency f+1 overlaps the solve of f" if overlap else "assembly and solve back to back"))
+    csw.close()
 
     # ---- the ZGEMV alone (nothing else on the GPU): 20 launches through the operator boundary
     iso_ms = None
@@ -659,6 +673,7 @@ def run_native(args):
     fp64_meas = ctx.measure_fp64_peak()
     fp64_nominal = 148 * 64 * 2 * 1.965e9 / 1e12
     launches = int(sum(st["asm_total_launches"] + st["sol_kernel_launches"] for st in stats))
+    fused_used = all(st["sol_kernel_launches"] == 1 for st in stats)  # the persistent kernel is ONE launch per solve
     traffic = None
     tp = ROOT / "profiles" / "ncu_traffic.json"
     if tp.exists():
@@ -699,8 +714,11 @@ def run_native(args):
                 "schedule": ("sweep pipeline: assembly of frequency f+1 on a second stream/buffer overlaps the solve of f"
                              if overlap else "sequential: assemble then solve"),
                 "exchange": ("single GPU" if world == 1 else
-                             ("peer memory: ZGEMV epilogue stores A v into every rank's work vector (NVLink), consumer waits on in-data flags"
-                              if ctx.peer_exchange_active() and not overlap else "NCCL all-gather of A v per Arnoldi step")),
+                             ("persistent fused GMRES kernel per rank: Krylov vector and reduction partials through peer memory (flag-in-data)"
+                              if fused_used else
+                              ("peer memory: ZGEMV epilogue stores A v into every rank's work vector (NVLink), consumer waits on in-data flags"
+                               if ctx.peer_exchange_active() and not overlap else "NCCL all-gather of A v per Arnoldi step"))),
+                "solver": ("gmres_fused_kernel (one launch per solve)" if fused_used else "zgemv_kernel + one Gram-Schmidt kernel per Arnoldi step"),
                 "frequencies_timed": [st["fi"] for st in stats]},
         "roofline": {"kernel": "zgemv_kernel", "bound": "hbm", "achieved": mv_gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": mv_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
@@ -710,9 +728,11 @@ def run_native(args):
                                                            "frac": mv_bytes / (iso_ms * 1e-3) / 1e9 / hbm_peak,
                                                            "note": "same kernel with nothing else running (no overlapped assembly)"})},
         "roofline_assembly": fa,
-        "e2e": {"value": float(e2e_s.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d // e2e_steps),
-                "d2h_bytes_per_step": int(d2h // e2e_steps), "steps": e2e_steps, "schedule": e2e_schedule,
-                "sequential_value": float(e2e_seq_s.item())},
+        "e2e": {"value": float(e2e_s.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d_sw),
+                "d2h_bytes_per_step": int(d2h_sw), "steps": e2e_steps, "schedule": e2e_schedule,
+                "sequential_value": float(e2e_seq_s.item()),
+                "sequential": {"schedule": "drop-in calls one after the other: build_tbem_system_with_beta(HOST mesh, re-staged every frequency) then gmres(host b)",
+                               "h2d_bytes_per_step": int(h2d // e2e_steps), "d2h_bytes_per_step": int(d2h // e2e_steps)}},
         "gpu_launches": launches,
         "clocks": clocks,
         "gmres": {"matvecs_per_step": mv_cnt / K, "iterations": [st["iterations"] for st in stats],
@@ -758,7 +778,7 @@ def main():
     ap.add_argument("--background", type=int, default=1, help="blocks/SM of the background assembly kernel in the sweep pipeline")
     ap.add_argument("--no-overlap", action="store_true", help="do not overlap assembly(f+1) with solve(f)")
     ap.add_argument("--schedule", choices=["auto", "pipelined", "sequential"], default="auto",
-                    help="auto: pipelined sweep on 1-4 GPUs, sequential at 8 GPUs on")
+                    help="auto: pipelined sweep on 1-2 GPUs, sequential (persistent fused solver) from 4 GPUs on")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3  # timing rule: W >= 3

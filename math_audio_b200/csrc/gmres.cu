@@ -324,8 +324,10 @@ static int update_x(bemb200_matrix* m, cplx* x, const std::vector<cplx>& y) {
 }
 
 // ---- persistent fused solve (gmres_fused.cu) ----------------------------------------------------------------
-// BEMB200_GMRES_FUSED: 0 never, 1 whenever the kernel applies, unset = auto (row-sharded solves: yes; one GPU: the
-// per-iteration kernels, whose hardware-scheduled ZGEMV measured 7 % faster per iteration there -- DESIGN.md section 4.4)
+// BEMB200_GMRES_FUSED: 0 never, 1 whenever the kernel applies, unset = auto: the ranks of a single-process group always;
+// process-per-GPU jobs from 4 ranks on when the solver owns the GPU.  Measured: 8 GPUs 17.6 vs 20.0 ms
+// per frequency, 4 GPUs 33.6 vs 33.8, 2 GPUs 63.6 vs 60.6, 1 GPU 124 vs 118 -- below 4 ranks the hardware-scheduled ZGEMV
+// of the per-iteration path (perfect load balance for free) outweighs the saved launches and the sharded Gram-Schmidt.
 static const int g_fused_mode = []() { const char* v = std::getenv("BEMB200_GMRES_FUSED"); return v ? (std::atoi(v) != 0 ? 1 : 0) : -1; }();
 static double g_fused_total_ms = 0.0, g_fused_matvec_ms = 0.0, g_fused_round_ms = 0.0;
 static unsigned long long g_fused_rounds = 0;
@@ -444,9 +446,9 @@ static int gmres_fused_solve(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t
     bemb200_ctx* ctx = m->ctx;
     GmresWorkspace* ws = m->ws;
     if (g_fused_mode == 0 || ctx->fx.disabled || restart > (uint32_t)FUSED_MAX_RESTART || m->n_rows > 0x7fffffffull) return BEMB200_OK;
-    if (g_fused_mode < 0 && ctx->nranks == 1) return BEMB200_OK;
-    if (ctx->nranks > 1 && !ctx->group && !ctx->nccl_comm) return BEMB200_OK;
     const bool polite = ctx->shared_gpu.load() != 0;  // a background assembly shares the SMs: 96-register build
+    if (g_fused_mode < 0 && !ctx->group && (ctx->nranks < 4 || polite)) return BEMB200_OK;
+    if (ctx->nranks > 1 && !ctx->group && !ctx->nccl_comm) return BEMB200_OK;
     if (ctx->nranks > MAX_PEERS) return BEMB200_OK;
     bool ok = false;
     int rc = ensure_fused_exchange(ctx, ws->npad, &ok);

@@ -72,7 +72,9 @@ static void sweep_worker(bemb200_sweep* sw) {
             job = sw->queue[sw->next_to_assemble];
             sw->next_to_assemble += 1;
             sw->slot_busy[job->slot] = true;
-            foreground = !sw->solving;  // nothing to hide behind: assemble at full speed
+            // only the job at the head of the queue has nothing to hide behind (its own solve cannot start before it is
+            // assembled): full speed.  Every other job is assembled underneath the solve of its predecessor: polite grid.
+            foreground = job == sw->queue.front();
         }
         bemb200_ctx_set_background(sw->ctx_asm, (sw->overlap && !foreground) ? sw->background : 0);
         int rc = bemb200_assemble_staged(sw->ctx_asm, sw->staged, &job->phys, job->beta_re, job->beta_im, sw->r0, sw->r1, &sw->buf[job->slot]);
