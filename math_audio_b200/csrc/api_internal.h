@@ -54,7 +54,8 @@ struct FusedLocal {
     bool disabled = false;      // a solve timed out: stay on the per-iteration kernels
     // row ownership weighted by the measured streaming speed of the SM under every CTA (see gmres_fused_solve)
     unsigned long long* trace_d = nullptr;  // [grid][4]
-    uint32_t* row_off_d = nullptr;          // [grid + 1]
+    uint32_t* row_off_d = nullptr;          // [grid + 1] CTA boundaries (rows, or (row, segment) units)
+    uint4* frag = nullptr;                  // [2][grid] flag-in-data slots for boundary-row partial sums
     std::vector<double> speed;              // rows per ns of CTA c's SM (empty: not calibrated)
     std::vector<unsigned> smid;             // SM id CTA c ran on when `speed` was measured
     int calib_runs = 0;

@@ -110,6 +110,7 @@ void free_peer_exchange(bemb200_ctx* ctx, bool collective) {
     if (fx.hbuf) cudaFree(fx.hbuf);
     if (fx.trace_d) cudaFree(fx.trace_d);
     if (fx.row_off_d) cudaFree(fx.row_off_d);
+    if (fx.frag) cudaFree(fx.frag);
     if (fx.result_h) cudaFreeHost(fx.result_h);
     fx = FusedLocal();
     cudaGetLastError();
@@ -414,6 +415,8 @@ static int ensure_fused_exchange(bemb200_ctx* ctx, uint64_t npad, bool* ok) {
         if (fx.hbuf) cudaFree(fx.hbuf);
         if (fx.trace_d) cudaFree(fx.trace_d);
         if (fx.row_off_d) cudaFree(fx.row_off_d);
+        if (fx.frag) cudaFree(fx.frag);
+        fx.frag = nullptr;
         fx.cpart = fx.hbuf = nullptr;
         fx.trace_d = nullptr;
         fx.row_off_d = nullptr;
@@ -422,6 +425,8 @@ static int ensure_fused_exchange(bemb200_ctx* ctx, uint64_t npad, bool* ok) {
         fx.calib_runs = 0;
         BEMB_CUDA(ctx, cudaMalloc((void**)&fx.trace_d, (size_t)grid * 4 * sizeof(unsigned long long)));
         BEMB_CUDA(ctx, cudaMalloc((void**)&fx.row_off_d, ((size_t)grid + 1) * sizeof(uint32_t)));
+        BEMB_CUDA(ctx, cudaMalloc((void**)&fx.frag, 2 * ((size_t)grid + 1) * 2 * sizeof(uint4)));
+        BEMB_CUDA(ctx, cudaMemsetAsync(fx.frag, 0, 2 * ((size_t)grid + 1) * 2 * sizeof(uint4), ctx->stream));
         const size_t cb = 2 * (size_t)grid * FUSED_KMAX * 2 * sizeof(uint4), hb = 2 * (size_t)FUSED_KMAX * 2 * sizeof(uint4);
         BEMB_CUDA(ctx, cudaMalloc((void**)&fx.cpart, cb));
         BEMB_CUDA(ctx, cudaMalloc((void**)&fx.hbuf, hb));
@@ -498,8 +503,39 @@ static int gmres_fused_solve(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t
     // One refinement, then the table is frozen (same inputs -> same bits from then on); BEMB200_FUSED_BALANCE=0 keeps equal shares.
     static const int balance = []() { const char* v = std::getenv("BEMB200_FUSED_BALANCE"); return v ? std::atoi(v) : 1; }();
     p.row_off = nullptr;
+    p.unit_off = nullptr;
+    p.units_per_row = 0;
+    p.frag = fx.frag;
     std::vector<uint32_t> off;
-    if (balance && fx.speed.size() == G && p.nloc >= 8 * G) {
+    const bool have_speed = balance && fx.speed.size() == G;
+    if (balance && p.nloc >= 4 * G) {
+        // CTA boundaries in units of (row, segment): shares proportional to the measured speeds (equal before the calibration)
+        const uint32_t nsegu = (p.n + fused_segment_width(polite) - 1) / fused_segment_width(polite);
+        const uint64_t total_units = (uint64_t)p.nloc * nsegu;
+        double tot = 0.0;
+        for (uint32_t c = 0; c < G; ++c) tot += have_speed ? fx.speed[c] : 1.0;
+        off.assign(G + 1, 0);
+        double cum = 0.0;
+        uint32_t smax = 0;
+        bool ok_units = total_units < 0xffffffffull;
+        for (uint32_t c = 0; c < G && ok_units; ++c) {
+            cum += (have_speed ? fx.speed[c] : 1.0) / tot;
+            uint64_t e = c + 1 == G ? total_units : (uint64_t)std::llround(cum * (double)total_units);
+            if (e > total_units) e = total_units;
+            if (e < (uint64_t)off[c] + 2ull * nsegu) ok_units = false;  // every CTA keeps at least two whole rows of work
+            off[c + 1] = (uint32_t)e;
+            const uint32_t own0 = (off[c] + nsegu - 1) / nsegu, own1 = (off[c + 1] + nsegu - 1) / nsegu;
+            if (own1 - own0 + 1 > smax) smax = own1 - own0 + 1;  // + 1: the head-fragment slot
+        }
+        if (ok_units && smax <= 256) {
+            p.S = smax;
+            p.units_per_row = nsegu;
+            BEMB_CUDA(ctx, cudaMemcpyAsync(fx.row_off_d, off.data(), (G + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+            BEMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `off` is pageable host memory
+            p.unit_off = fx.row_off_d;
+        }
+    }
+    if (!p.unit_off && have_speed && p.nloc >= 8 * G) {
         double tot = 0.0;
         for (double v : fx.speed) tot += v;
         off.assign(G + 1, 0);
@@ -570,8 +606,8 @@ static int gmres_fused_solve(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t
                 if (w > wmx) wmx = w;
             }
             std::fprintf(stderr, "[fused trace rank %d] matvec ms per CTA: min %.3f max %.3f avg %.3f; round wait ms min %.3f max %.3f; total %.3f ms, %llu matvecs, "
-                         "weighted %d calib_runs %d S %u\n", ctx->rank, mn, mx, av, wmn, wmx, (double)res->t_total_ns * 1e-6, res->matvecs,
-                         p.row_off ? 1 : 0, fx.calib_runs, p.S);
+                         "weighted %d units %d calib_runs %d S %u\n", ctx->rank, mn, mx, av, wmn, wmx, (double)res->t_total_ns * 1e-6, res->matvecs,
+                         (p.row_off || (p.unit_off && have_speed)) ? 1 : 0, p.unit_off ? 1 : 0, fx.calib_runs, p.S);
             if (std::getenv("BEMB200_FUSED_TRACE_FULL"))
                 for (uint32_t c = 0; c < G; c += 8) {
                     std::fprintf(stderr, "   cta %3u:", c);

@@ -197,8 +197,20 @@ __device__ __forceinline__ int rp_off(int c) { return (c * (c + 1)) / 2; }      
 // segment sg: its 4 x-values per lane stay in registers while it walks the CTA's rows two pairs at a time (16
 // independent 16-byte streaming loads in flight per lane); per (row pair, warp) partial sums are accumulated in shared
 // memory in segment order and added over the warps in warp order: deterministic.
+// Boundary rows.  With `units` (p.unit_off) the CTA boundaries sit at (row, segment) granularity -- a row is nseg units,
+// so shares are balanced to a fraction of a percent even when a CTA owns only ~17 rows (8 ranks) -- and the row a boundary
+// cuts through is computed by TWO CTAs: the upper one (which owns the row: it holds the row's first segments in visiting
+// order) and the next CTA, which computes the remaining segments ("head fragment") and hands its partial sum to the owner
+// through one flag-in-data slot.  Frag describes that for one CTA.
+struct Frag {
+    bool has_head;   // this CTA computes the tail segments (visiting positions >= s0) of row rb - 1 for CTA cta - 1
+    uint32_t s0;
+    uint32_t s1;     // visiting positions < s1 of this CTA's LAST owned row are computed here, the rest by CTA cta + 1
+};
+
 template <int RB, int CPL>
-__device__ __forceinline__ void matvec_rows(const FusedParams& p, const Smem& sm, uint32_t rb, uint32_t sc, uint32_t ex, const Ctl& ctl) {
+__device__ __forceinline__ void matvec_rows(const FusedParams& p, const Smem& sm, uint32_t rb, uint32_t sc, const Frag& fr, uint32_t ex,
+                                            const Ctl& ctl) {
     constexpr int WCOLS = 32 * CPL;   // columns per warp and segment
     constexpr int SEGW = NW * WCOLS;  // columns per segment
     static_assert(RB == 2 || RB == 4, "rows per step");
@@ -206,9 +218,11 @@ __device__ __forceinline__ void matvec_rows(const FusedParams& p, const Smem& sm
     const uint4* xin = p.xbuf[p.rank] + (size_t)(ex & 1u) * 2 * p.npad;
     const uint32_t n = p.n;
     const uint32_t nseg = (n + SEGW - 1) / SEGW;
-    for (uint32_t blk = 0; blk < sc; blk += p.rblk) {
-        const uint32_t nrows = sc - blk < p.rblk ? sc - blk : p.rblk;
-        for (uint32_t e = tid; e < nrows * NW * 2; e += FT) sm.ypart[e] = 0.0;
+    const uint32_t head = fr.has_head ? 1u : 0u;
+    // slot 0 of ypart is the head-fragment row (row rb - 1) when there is one; owned row i sits in slot head + i
+    for (uint32_t blk = 0; blk < sc + head; blk += p.rblk) {
+        const uint32_t nslots = sc + head - blk < p.rblk ? sc + head - blk : p.rblk;
+        for (uint32_t e = tid; e < nslots * NW * 2; e += FT) sm.ypart[e] = 0.0;
         __syncthreads();
         // segments are visited starting with the rank's OWN columns (their part of the vector is published locally and
         // is there first); the other ranks' parts cross NVLink while this rank already streams
@@ -217,6 +231,12 @@ __device__ __forceinline__ void matvec_rows(const FusedParams& p, const Smem& sm
             const uint32_t sg = si + sg0 < nseg ? si + sg0 : si + sg0 - nseg;
             const uint32_t cbase = sg * SEGW + wq * WCOLS;
             if (cbase >= n) continue;  // warp-uniform: no columns for this warp in this segment
+            // slots of this block that take part in this segment: the head row only from position s0 on, the last owned row
+            // only before position s1
+            uint32_t lo = 0, hi = nslots;
+            if (blk == 0 && head && si < fr.s0) lo = 1;
+            if (blk + nslots == sc + head && sc > 0 && si >= fr.s1) hi -= 1;
+            if (lo >= hi) continue;
             cplx xr[CPL];
             uint32_t col[CPL];
             {
@@ -234,9 +254,9 @@ __device__ __forceinline__ void matvec_rows(const FusedParams& p, const Smem& sm
                 __syncwarp();
                 ll_wait_many<CPL>(xr, q, want, ex, ctl);
             }
-            const cplx* arow = p.A + (size_t)(rb + blk) * p.lda;
-            for (uint32_t r0 = 0; r0 < nrows; r0 += RB, arow += RB * p.lda) {
-                const uint32_t nr = nrows - r0;  // rows left (warp-uniform); rows beyond it are neither loaded nor stored
+            const cplx* arow = p.A + ((size_t)rb + blk + lo - head) * p.lda;  // slot s <-> slab row rb - head + blk + s
+            for (uint32_t r0 = lo; r0 < hi; r0 += RB, arow += RB * p.lda) {
+                const uint32_t nr = hi - r0;  // rows left (warp-uniform); rows beyond it are neither loaded nor stored
                 double2 a[RB][CPL];
 #pragma unroll
                 for (int r = 0; r < RB; ++r) {
@@ -264,12 +284,27 @@ __device__ __forceinline__ void matvec_rows(const FusedParams& p, const Smem& sm
             }
         }
         __syncthreads();
-        for (uint32_t t = tid; t < nrows; t += FT) {
+        for (uint32_t t = tid; t < nslots; t += FT) {
             const double* yp = sm.ypart + (size_t)t * NW * 2;
             double sr = 0.0, si = 0.0;
 #pragma unroll
             for (int w = 0; w < NW; ++w) { sr += yp[w * 2]; si += yp[w * 2 + 1]; }
-            sm.w_s[blk + t] = C(sr, si);
+            const uint32_t slot = blk + t;
+            if (head && slot == 0) {
+                // head fragment: partial sum of row rb - 1 for its owner, CTA cta - 1
+                ll_put(p.frag + ((size_t)(ex & 1u) * gridDim.x + blockIdx.x) * 2, C(sr, si), ex);
+            } else {
+                sm.w_s[slot - head] = C(sr, si);
+            }
+        }
+        __syncthreads();
+    }
+    if (sc > 0 && fr.s1 < nseg) {
+        // the rest of my last row comes from the next CTA
+        if (tid == 0) {
+            const cplx o = ll_wait1(p.frag + ((size_t)(ex & 1u) * gridDim.x + blockIdx.x + 1) * 2, ex, ctl);
+            sm.w_s[sc - 1].re += o.re;
+            sm.w_s[sc - 1].im += o.im;
         }
         __syncthreads();
     }
@@ -302,18 +337,19 @@ __device__ __forceinline__ void round_gather(const FusedParams& p, const Smem& s
         const uint32_t c0 = q * per < G ? q * per : G, c1 = (c0 + per < G) ? c0 + per : G;
         cplx t = C(0, 0);
         if (k < K && q < nstr) {
-            for (uint32_t c = c0; c < c1; c += 8) {
-                cplx v[8];
-                const uint4* qq[8];
-                bool want[8];
+            constexpr int GB = 10;  // partials in flight per thread and pass (148 CTAs in 8 strands: two passes)
+            for (uint32_t c = c0; c < c1; c += GB) {
+                cplx v[GB];
+                const uint4* qq[GB];
+                bool want[GB];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
+                for (int e = 0; e < GB; ++e) {
                     want[e] = c + e < c1;
                     qq[e] = p.cpart + (((size_t)(er & 1u) * G + (want[e] ? c + e : c)) * KMAX + k) * 2;
                 }
-                ll_wait_many<8>(v, qq, want, er, ctl);
+                ll_wait_many<GB>(v, qq, want, er, ctl);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) { t.re += v[e].re; t.im += v[e].im; }
+                for (int e = 0; e < GB; ++e) { t.re += v[e].re; t.im += v[e].im; }
             }
             sm.red4[q * kpad + k] = t;
         }
@@ -354,10 +390,8 @@ __device__ __forceinline__ void round_broadcast(const FusedParams& p, const Smem
     if (blockIdx.x == 0) {
         __syncthreads();  // bc_s complete
         if (tid < nb) ll_put(p.hbuf + ((size_t)(er & 1u) * KMAX + tid) * 2, sm.bc_s[tid], er);
-    } else {
-        if (tid == 0) ll_probe(p.hbuf + ((size_t)(er & 1u) * KMAX + nb - 1) * 2, er, ctl);  // one prober per CTA
-        __syncthreads();
-        if (tid < nb) sm.bc_s[tid] = ll_wait1(p.hbuf + ((size_t)(er & 1u) * KMAX + tid) * 2, er, ctl);
+    } else if (tid < nb) {
+        sm.bc_s[tid] = ll_wait1(p.hbuf + ((size_t)(er & 1u) * KMAX + tid) * 2, er, ctl);  // (ll_wait_many backs off between polls)
     }
     __syncthreads();
 }
@@ -453,7 +487,19 @@ __device__ __forceinline__ void gmres_body(const FusedParams& p) {
     // rows of this CTA inside the rank's slab: equal shares, or the host's table (shares proportional to the measured
     // streaming speed of the SM each CTA sits on: SMs of fuller GPCs get less HBM bandwidth)
     uint32_t rb, sc;
-    if (p.row_off) {
+    Frag fr{false, 0u, 0xffffffffu};
+    if (p.unit_off) {
+        // boundaries in units of (row, segment position); a row is owned by the CTA holding its first position
+        const uint32_t nsegu = p.units_per_row;
+        const uint32_t U0 = p.unit_off[cta], U1 = p.unit_off[cta + 1];
+        rb = (U0 + nsegu - 1) / nsegu;
+        const uint32_t own1 = (U1 + nsegu - 1) / nsegu;
+        sc = own1 > rb ? own1 - rb : 0;
+        fr.s0 = U0 % nsegu;
+        fr.has_head = fr.s0 != 0 && U1 > U0;
+        fr.s1 = (U1 % nsegu) ? (U1 % nsegu) : nsegu;
+        if (sc == 0) fr.s1 = nsegu;
+    } else if (p.row_off) {
         rb = p.row_off[cta];
         sc = p.row_off[cta + 1] - rb;
     } else {
@@ -487,7 +533,7 @@ __device__ __forceinline__ void gmres_body(const FusedParams& p) {
         publish_rows(p, p.x + p.row0 + rb, rb, sc, ex);
         unsigned long long tm0 = 0;
         if (cta == 0 && tid == 0) tm0 = gtimer();
-        matvec_rows<RB, CPL>(p, sm, rb, sc, ex, ctl);
+        matvec_rows<RB, CPL>(p, sm, rb, sc, fr, ex, ctl);
         ABORT_CHECK();
         if (cta == 0 && tid == 0) { t_mv += gtimer() - tm0; matvecs += 1; }
         double bn2 = 0.0, rn2 = 0.0;
@@ -541,7 +587,7 @@ __device__ __forceinline__ void gmres_body(const FusedParams& p) {
                 next_epoch(ex);
                 publish_rows(p, sm.u_s, rb, sc, ex);
                 if (tid == 0) tm0 = gtimer();
-                matvec_rows<RB, CPL>(p, sm, rb, sc, ex, ctl);
+                matvec_rows<RB, CPL>(p, sm, rb, sc, fr, ex, ctl);
                 ABORT_CHECK();
                 if (tid == 0) { const unsigned long long dt = gtimer() - tm0; tc_mv += dt; if (cta == 0) { t_mv += dt; matvecs += 1; } }
                 if (p.pinv) {
@@ -567,29 +613,50 @@ __device__ __forceinline__ void gmres_body(const FusedParams& p) {
                     sm.part_s[0] = C(t, 0.0);
                 }
             } else {
-                for (int l = wq; l < nv; l += NW) {
-                    double v4[4] = {0.0, 0.0, 0.0, 0.0};  // a.re, a.im, g.re, g.im
-                    const cplx* vl = p.V + (size_t)l * p.ldv + rb;
+                // warp wq owns the vectors l = wq, wq + 16, wq + 32, wq + 48 (restart <= 63); their rows are loaded together so that
+                // the L2 round trips of the (up to four) vectors overlap
+                {
+                    constexpr int NP = (FUSED_MAX_RESTART + 1 + NW - 1) / NW;  // 4
+                    double acc[NP][4];  // a.re, a.im, g.re, g.im per owned vector
+#pragma unroll
+                    for (int pq = 0; pq < NP; ++pq)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) acc[pq][c] = 0.0;
                     for (uint32_t i = lane; i < sc; i += 32) {
                         const cplx u = sm.u_s[i], w = sm.w_s[i];
-                        if (l < j) {
-                            const cplx v = ldcg_c(vl + i);
-                            v4[0] = fma(v.re, w.re, fma(v.im, w.im, v4[0]));
-                            v4[1] = fma(v.re, w.im, fma(-v.im, w.re, v4[1]));
-                            v4[2] = fma(u.re, v.re, fma(u.im, v.im, v4[2]));
-                            v4[3] = fma(u.re, v.im, fma(-u.im, v.re, v4[3]));
-                        } else {
-                            v4[0] = fma(u.re, w.re, fma(u.im, w.im, v4[0]));
-                            v4[1] = fma(u.re, w.im, fma(-u.im, w.re, v4[1]));
-                            v4[2] = fma(u.re, u.re, fma(u.im, u.im, v4[2]));  // |u|^2 rides in the g slot of l = j
+                        cplx v[NP];
+#pragma unroll
+                        for (int pq = 0; pq < NP; ++pq) {
+                            const int l = wq + pq * NW;
+                            v[pq] = l < j ? ldcg_c(p.V + (size_t)l * p.ldv + rb + i) : C(0, 0);
+                        }
+#pragma unroll
+                        for (int pq = 0; pq < NP; ++pq) {
+                            const int l = wq + pq * NW;
+                            if (l < j) {
+                                acc[pq][0] = fma(v[pq].re, w.re, fma(v[pq].im, w.im, acc[pq][0]));
+                                acc[pq][1] = fma(v[pq].re, w.im, fma(-v[pq].im, w.re, acc[pq][1]));
+                                acc[pq][2] = fma(u.re, v[pq].re, fma(u.im, v[pq].im, acc[pq][2]));
+                                acc[pq][3] = fma(u.re, v[pq].im, fma(-u.im, v[pq].re, acc[pq][3]));
+                            } else if (l == j) {
+                                acc[pq][0] = fma(u.re, w.re, fma(u.im, w.im, acc[pq][0]));
+                                acc[pq][1] = fma(u.re, w.im, fma(-u.im, w.re, acc[pq][1]));
+                                acc[pq][2] = fma(u.re, u.re, fma(u.im, u.im, acc[pq][2]));  // |u|^2 rides in the g slot of l = j
+                            }
                         }
                     }
-                    const double tot = warp_fold<4>(v4, lane);  // lane 8 v holds value v
                     double* dst = reinterpret_cast<double*>(sm.part_s);
-                    if (lane == 0) dst[2 * l] = tot;
-                    if (lane == 8) dst[2 * l + 1] = tot;
-                    if (lane == 16) dst[2 * (nv + l)] = tot;
-                    if (lane == 24) dst[2 * (nv + l) + 1] = tot;
+#pragma unroll
+                    for (int pq = 0; pq < NP; ++pq) {
+                        const int l = wq + pq * NW;
+                        if (l < nv) {  // warp-uniform
+                            const double tot = warp_fold<4>(acc[pq], lane);  // lane 8 v holds value v
+                            if (lane == 0) dst[2 * l] = tot;
+                            if (lane == 8) dst[2 * l + 1] = tot;
+                            if (lane == 16) dst[2 * (nv + l)] = tot;
+                            if (lane == 24) dst[2 * (nv + l) + 1] = tot;
+                        }
+                    }
                 }
                 if (K > 2 * nv) {  // ||b||^2 (resp. ||M^-1 b||^2) rides along in the very first round
                     __shared__ double bn_s[NW];
@@ -795,7 +862,7 @@ __device__ __forceinline__ void gmres_body(const FusedParams& p) {
     if (p.trace && tid == 0) {
         p.trace[4 * cta + 0] = tc_mv;
         p.trace[4 * cta + 1] = tc_wait;
-        p.trace[4 * cta + 2] = sc;
+        p.trace[4 * cta + 2] = p.unit_off ? (unsigned long long)(p.unit_off[cta + 1] - p.unit_off[cta]) : (unsigned long long)sc * 16ull;  // work share
         p.trace[4 * cta + 3] = smid;
     }
     __shared__ int fin_flag;
@@ -845,6 +912,11 @@ uint32_t fused_pick_rblk(uint32_t S) {
     const uint32_t cap = 256;
     const uint32_t r = S < cap ? S : cap;
     return r ? r : 1;
+}
+
+uint32_t fused_segment_width(bool polite) {
+    static const int variant = []() { const char* v = std::getenv("BEMB200_FUSED_VARIANT"); return v ? std::atoi(v) : 0; }();
+    return (uint32_t)(NW * 32 * ((!polite && variant == 1) ? 8 : 4));
 }
 
 cudaError_t launch_gmres_fused(const FusedParams& p, int grid, size_t smem, bool polite, cudaStream_t s) {

@@ -44,11 +44,15 @@ struct FusedParams {
     uint32_t S;          // rows per CTA (the largest share when row_off is given)
     uint32_t rblk;       // rows per matvec pass inside a CTA
     const uint32_t* row_off;    // optional [G + 1]: first slab row of every CTA (weighted shares); nullptr: equal shares of S rows
+    const uint32_t* unit_off;   // optional [G + 1]: CTA boundaries in units of (row, segment position), units_per_row per row
+    uint32_t units_per_row;     // segments per row the unit table was built for (must be the kernel's nseg)
+    uint4* frag;                // [2][G] flag-in-data slots: head-fragment partial sums handed to the owning CTA
     unsigned long long* trace;  // optional [G][4]: per CTA ns inside matvec_rows, ns waiting for round payloads, rows owned, SM id
 };
 
 size_t fused_smem_bytes(uint32_t S, uint32_t rblk, uint32_t restart);
 uint32_t fused_pick_rblk(uint32_t S);
+uint32_t fused_segment_width(bool polite);  // matrix columns per segment of the kernel variant in use
 // polite: the 96-register build that leaves room for a background assembly block on every SM
 cudaError_t launch_gmres_fused(const FusedParams& p, int grid, size_t smem, bool polite, cudaStream_t s);
 
