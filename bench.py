@@ -443,6 +443,207 @@ def run_config4(ctx, rank, world, dev, reps=2):
     return block
 
 
+def run_config5(ctx, dev):
+    """BASELINE.json configs[4] inside the driver-run bench (one GPU): icosphere(5), ka = 2, adaptive beta, 32 plane-wave
+    directions on the Fibonacci sphere; ONE batched GMRES(50, 1e-10) over the FP64 tensor-core block matvec (reference
+    semantics: 32 independent gmres() calls).  Parity against the COMMITTED oracle record tests/golden/config5_rhs32.npz
+    (per-right-hand-side iteration / restart counts of 32 oracle solves, LAPACK solutions of columns 0, 13, 31).  No oracle import."""
+    import torch
+
+    from math_audio_b200 import bem
+    from math_audio_b200.incident import IncidentField
+    from math_audio_b200.mesh import fibonacci_directions
+
+    a, ka, nrhs = 0.1, 2.0, 32
+    mesh = generate_icosphere_mesh(a, 5)
+    n = mesh.num_dofs
+    ph = PhysicsParams.from_wave_number(ka / a)
+    beta, _ = ph.burton_miller_beta_adaptive(a)
+    system = bem.build_tbem_system_with_beta(mesh, ph, beta, ctx=ctx)
+    op = bem.DenseOperator(system)
+    B = np.stack([system.rhs + IncidentField.plane_wave(d).compute_rhs_with_beta(mesh.center, mesh.normal, ph, beta)
+                  for d in fibonacci_directions(nrhs)])
+    cfg = bem.GmresConfig(max_iterations=GMRES_MAX_CYCLES, restart=GMRES_RESTART, tolerance=GMRES_TOL)
+    bem.gmres_batched(op, B[:8], bem.GmresConfig(1, 2, GMRES_TOL))  # untimed: workspace of the batched solver
+    X = np.random.default_rng(1).standard_normal((nrhs, n)) + 1j * np.random.default_rng(2).standard_normal((nrhs, n))
+    kms = min(bem.apply_block(op, X)[1] for _ in range(3))
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    sols, st = bem.gmres_batched(op, B, cfg)
+    torch.cuda.synchronize(dev)
+    t_batched = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    singles = [bem.gmres(op, B[i], cfg) for i in (0, 13, 31)]
+    t_single = (time.perf_counter() - t0) / 3
+    res = [float(np.linalg.norm(B[i] - op.apply(sols[i].x)) / np.linalg.norm(B[i])) for i in (0, 13, 31)]
+    flops = 8.0 * n * n * nrhs
+    fp64_nominal = 148 * 64 * 2 * 1.965e9 / 1e12
+    block = {"workload": "sphere20k_rhs32", "description": "rigid icosphere(5), 20480 Tri3, ka = 2, 32 plane-wave directions, batched GMRES(50) tol 1e-10",
+             "n_elements": int(n), "nrhs": nrhs, "s_per_batch": t_batched, "s_per_rhs": t_batched / nrhs,
+             "single_rhs_solve_s": t_single, "speedup_vs_sequential_solves": t_single * nrhs / t_batched,
+             "block_matvec": {"kernel": "zgemm_block_kernel (mma.sync m8n8k4 f64)", "ms": kms, "tflops": flops / (kms * 1e-3) / 1e12,
+                              "frac_of_nominal_fp64": flops / (kms * 1e-3) / 1e12 / fp64_nominal, "launches": int(st.get("block_matvecs", 0)),
+                              "algorithmic_flop_per_launch": flops, "bytes_per_launch": 16.0 * n * n + 32.0 * n * nrhs},
+             "iterations": [so.iterations for so in sols], "all_converged": all(so.converged for so in sols),
+             "independent_residuals": res,
+             "max_dx_vs_single_rhs_device_solve": max(float(np.linalg.norm(sols[i].x - singles[j].x) / np.linalg.norm(singles[j].x))
+                                                      for j, i in enumerate((0, 13, 31)))}
+    gp = ROOT / "tests" / "golden" / "config5_rhs32.npz"
+    if gp.exists():
+        g = np.load(gp)
+        dx = max(float(np.linalg.norm(sols[int(c)].x - g["x"][j]) / np.linalg.norm(g["x"][j])) for j, c in enumerate(g["x_cols"]))
+        same = bool(np.array_equal(np.array([so.iterations for so in sols]), g["iterations"])
+                    and np.array_equal(np.array([so.restarts for so in sols]), g["restarts"]))
+        block["parity"] = {"golden": "tests/golden/config5_rhs32.npz (32 oracle GMRES solves + LAPACK solutions of 3 columns, committed)",
+                           "iteration_and_restart_counts_equal": same, "max_x_rel_err_vs_lapack": dx, "bar_x": 1e-8, "ok": bool(same and dx < 1e-8)}
+    else:
+        block["parity"] = {"skipped": "tests/golden/config5_rhs32.npz missing"}
+    system.matrix.close()
+    return block
+
+
+def cabinet_mesh(scale: float):
+    """BASELINE.json configs[2]: closed 0.32 x 0.44 x 0.64 m Quad4 box, 64 x 88 x 128 subdivisions at
+    scale 1 (50 176 elements), piston = full-length velocity BC v = 1 on the front-wall elements within 80 mm of the wall
+    centre, rigid elsewhere.  Same construction as tests/golden/make_golden_large.py."""
+    from math_audio_b200.mesh import generate_box_mesh_quad
+
+    nx, ny, nz = int(64 * scale), int(88 * scale), int(128 * scale)
+    mesh = generate_box_mesh_quad(0.32, 0.44, 0.64, nx, ny, nz)
+    front = (np.abs(mesh.center[:, 1] + 0.22) < 1e-9) & (np.hypot(mesh.center[:, 0], mesh.center[:, 2]) < 0.08)
+    v = np.zeros((mesh.n_elem, 4), dtype=np.complex128)
+    v[front] = 1.0
+    mesh.set_velocity_bc(v)
+    mesh.bc_len[~front] = 1
+    return mesh
+
+
+def run_config3(ctx, rank, world, dev, reps=2):
+    """BASELINE.json configs[2] inside the driver-run bench (2 and 4 GPUs): the 50 176-element Quad4 cabinet with a piston,
+    f = 1 kHz, beta = i/k, row-sharded over all ranks: assemble (matrix AND the right-hand side the velocity BC generates) +
+    GMRES(50, 1e-10), timed end to end.  Parity against COMMITTED oracle data (tests/golden/make_golden_large.py):
+    config3_rows.npz -- 16 sampled rows (entries at the 256 nearest + every 32nd column, whole-row dot products, right-hand-side
+    entries) -- and config3_coarse_x.npz -- the 4x-coarsened copy (12 544 elements) assembled and solved in full by this job
+    against the oracle's LAPACK solution and GMRES counts.  Collective; returns the block on rank 0.  No oracle import."""
+    import torch
+    import torch.distributed as dist
+
+    from math_audio_b200 import bem
+
+    def allmax(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    ph = PhysicsParams.new(1000.0, 343.0, 1.21, False)
+    beta = ph.burton_miller_beta()
+    cfg = bem.GmresConfig(max_iterations=GMRES_MAX_CYCLES, restart=GMRES_RESTART, tolerance=GMRES_TOL)
+    block = {"workload": "cabinet50k", "description": "closed Quad4 box 64x88x128 = 50 176 elements, piston velocity BC, f = 1 kHz, beta = i/k",
+             "n_gpus": world}
+    # ---- the 4x-coarsened copy, solved in full and compared with the oracle's solution ---------------------------------
+    gx = ROOT / "tests" / "golden" / "config3_coarse_x.npz"
+    if gx.exists():
+        g = np.load(gx)
+        mesh_c = cabinet_mesh(0.5)
+        sys_c = bem.build_tbem_system_with_beta(mesh_c, ph, beta, ctx=ctx)
+        b_c = sys_c.rhs_full()
+        sol = bem.gmres(bem.DenseOperator(sys_c), b_c, cfg)
+        e = allmax([float(np.linalg.norm(b_c - g["b"]) / np.linalg.norm(g["b"])), float(np.linalg.norm(sol.x - g["x"]) / np.linalg.norm(g["x"])),
+                    0.0 if (sol.iterations == int(g["iterations"]) and sol.restarts == int(g["restarts"]) and sol.converged) else 1.0])
+        block["coarse_copy"] = {"n_elements": int(mesh_c.num_dofs), "golden": "tests/golden/config3_coarse_x.npz (oracle LAPACK solution, committed)",
+                                "rhs_rel_err": e[0], "x_rel_err": e[1], "iterations": sol.iterations, "golden_iterations": int(g["iterations"]),
+                                "counts_equal_on_every_rank": e[2] == 0.0, "bar_x": 1e-8, "ok": bool(e[0] < 1e-10 and e[1] < 1e-8 and e[2] == 0.0)}
+        sys_c.matrix.close()
+        del sys_c
+    # ---- the full-size problem ------------------------------------------------------------------------------------------
+    mesh = cabinet_mesh(1.0)
+    n = mesh.num_dofs
+    r0, r1 = ctx.partition(n)
+    nloc = r1 - r0
+    free_b, _tot = torch.cuda.mem_get_info(dev)
+    need = 16.0 * nloc * n + 52 * 16.0 * n + (1 << 30)
+    if allmax([0.0 if free_b > need else 1.0])[0] > 0.0:
+        block["skipped"] = f"needs {need / 1e9:.0f} GB per GPU at {world} GPUs"
+        return block if rank == 0 else None
+    staged = bem.StagedMesh(mesh, ctx)
+    x_dev = torch.zeros(n, dtype=torch.complex128, device=dev)
+    y_dev = torch.zeros(n, dtype=torch.complex128, device=dev)
+    system, best = None, None
+    for rep in range(reps):
+        barrier()
+        t0 = time.perf_counter()
+        system = bem.build_tbem_system_with_beta(staged, ph, beta, ctx=ctx, rows=(r0, r1), reuse=system, fetch_rhs=False)
+        b = system.rhs_full()  # the piston's right-hand side: local rows D2H, the other ranks' rows over the communicator
+        torch.cuda.synchronize(dev)
+        t1 = time.perf_counter()
+        sol = bem.gmres(bem.DenseOperator(system), b, cfg)
+        barrier()
+        t2 = time.perf_counter()
+        st_a, st_s = system.matrix.assembly_stats(), system.matrix.solver_stats()
+        tim = allmax([t2 - t0, t1 - t0, st_a["far_ms"], st_a["total_ms"], st_s["matvec_ms"] / max(1, st_s["matvecs"])])
+        cur = dict(s=tim[0], asm_s=tim[1], far_ms=tim[2], asm_ms=tim[3], mv_ms=tim[4], sol=sol, special=int(st_a["special_pairs"]),
+                   launches=int(st_a["total_launches"] + st_s["kernel_launches"]))
+        if rep > 0 and (best is None or cur["s"] < best["s"]):
+            best = cur
+    best = best or cur
+    sol = best["sol"]
+    op = bem.DenseOperator(system)
+    x_dev.copy_(torch.from_numpy(sol.x))
+    b_dev = torch.from_numpy(b).to(dev)
+    bem.apply_device(op, x_dev.data_ptr(), y_dev.data_ptr())
+    res = float((torch.linalg.vector_norm(b_dev - y_dev) / torch.linalg.vector_norm(b_dev)).item())
+    gpath = ROOT / "tests" / "golden" / "config3_rows.npz"
+    errs, checked = [0.0, 0.0, 0.0, 0.0], 0
+    if gpath.exists():
+        g = np.load(gpath)
+        xp = np.random.default_rng(1234)
+        xprobe = xp.standard_normal(n) + 1j * xp.standard_normal(n)
+        bem.apply_device(op, torch.from_numpy(xprobe).to(dev).data_ptr(), y_dev.data_ptr())
+        yh = y_dev.cpu().numpy()
+        xn = float(np.linalg.norm(xprobe))
+        bscale = float(np.max(np.abs(g["rhs"])))
+        for i, r in enumerate(g["rows"]):
+            r = int(r)
+            errs[2] = max(errs[2], abs(yh[r] - g["rowdot"][i]) / (float(g["rownorm"][i]) * xn))
+            errs[3] = max(errs[3], abs(b[r] - g["rhs"][i]) / bscale)
+            if r0 <= r < r1:
+                got, ref = system.matrix.rows(r, r + 1)[0][g["cols"][i]], g["vals"][i]
+                errs[0] = max(errs[0], float(np.max(np.abs(got - ref) / np.abs(ref))))
+                errs[1] = max(errs[1], float(np.max(np.abs(got - ref)) / np.max(np.abs(ref))))
+                checked += 1
+    errs = allmax(errs)
+    cnt = torch.tensor([float(checked)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    del system
+    if rank != 0:
+        return None
+    far_flop = (FLOP_PER_QP * 16 + FLOP_PER_PAIR) * nloc * (n - 1)
+    mv_bytes = 16.0 * nloc * n + 16.0 * n + 16.0 * nloc
+    fp64_nominal = 148 * 64 * 2 * 1.965e9 / 1e12
+    hbm_peak, _src = load_peaks()
+    block.update({
+        "n_elements": int(n), "rows_per_gpu": int(nloc), "matrix_gb_per_gpu": 16.0 * nloc * n / 1e9,
+        "s_per_frequency": best["s"], "assemble_s": best["asm_s"], "assemble_ms_device": best["asm_ms"], "far_ms": best["far_ms"],
+        "special_pairs_rank0": best["special"],
+        "far_tflops_per_gpu": far_flop / (best["far_ms"] * 1e-3) / 1e12, "far_frac_of_nominal_fp64": far_flop / (best["far_ms"] * 1e-3) / 1e12 / fp64_nominal,
+        "matvec_ms": best["mv_ms"], "matvec_gbs_per_gpu": mv_bytes / (best["mv_ms"] * 1e-3) / 1e9,
+        "matvec_frac_of_measured_hbm": mv_bytes / (best["mv_ms"] * 1e-3) / 1e9 / hbm_peak,
+        "iterations": sol.iterations, "restarts": sol.restarts, "residual": sol.residual, "converged": sol.converged,
+        "independent_residual": res, "gpu_launches": best["launches"],
+        "parity": ({"golden": "tests/golden/config3_rows.npz (oracle rows, committed)", "rows_checked": int(cnt.item()),
+                    "max_entry_rel_err": errs[0], "max_row_normwise_err": errs[1], "max_rowdot_err": errs[2], "max_rhs_err": errs[3],
+                    "bar": 1e-10} if gpath.exists() else {"skipped": "tests/golden/config3_rows.npz missing"}),
+    })
+    return block
+
+
 # -------------------------------------------------------------------------------------------
 # native arm
 # -------------------------------------------------------------------------------------------
@@ -643,6 +844,22 @@ def run_native(args):
 
     # ---- row-sharded parity against the committed golden fixtures (several GPUs exist only in the driver's scaling lease)
     sharded_parity = run_sharded_parity(ctx, rank, world, dev) if world > 1 else None
+    # ---- 32 right-hand sides on the tensor-core block matvec (config 5) ride along on one GPU
+    config5 = None
+    if world == 1 and not os.environ.get("BENCH_NO_CONFIG5"):
+        try:
+            config5 = run_config5(ctx, dev)
+        except Exception as e:  # the headline line must survive a failure of the side block
+            config5 = {"error": f"{type(e).__name__}: {e}"}
+    # ---- the Quad4 cabinet (config 3) rides along at 2 and 4 GPUs (the sizes BASELINE.json quotes it on)
+    config3 = None
+    if (world in (2, 4) or os.environ.get("BENCH_CONFIG3")) and not os.environ.get("BENCH_NO_CONFIG3"):
+        try:
+            del sys_e2e, op_iso
+            driver.buffers = [None, None]
+        except Exception:
+            pass
+        config3 = run_config3(ctx, rank, world, dev)
     # ---- the north-star target (config 4) rides along whenever all 8 GPUs of the box are in the job
     config4 = None
     if (world >= 8 or os.environ.get("BENCH_CONFIG4")) and not os.environ.get("BENCH_NO_CONFIG4"):
@@ -745,6 +962,10 @@ def run_native(args):
     }
     if sharded_parity is not None:
         line["sharded_parity"] = sharded_parity
+    if config5 is not None:
+        line["config5"] = config5
+    if config3 is not None:
+        line["config3"] = config3
     if config4 is not None:
         line["config4"] = config4
     if world == 1 and not args.no_cpu_baseline:

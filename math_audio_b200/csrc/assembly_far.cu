@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(TILE, MINB)
 far_kernel(const double* __restrict__ far_k, const double* __restrict__ far_c, const uint8_t* __restrict__ col_class,
            const double* __restrict__ srcdat, uint32_t n, uint64_t row_begin, uint64_t row_end, uint32_t rows_per_block,
            uint32_t nchunks, uint32_t total_items, uint32_t items_per_block,
-           double wavruim, double k2, double cH, double beta_re, double beta_im, cplx* __restrict__ A, uint64_t lda,
+           double wavruim, CisConst cis, double k2, double cH, double beta_re, double beta_im, cplx* __restrict__ A, uint64_t lda,
            uint2* __restrict__ near_list, unsigned int near_cap, unsigned int* __restrict__ near_count,
            unsigned int* __restrict__ work_counter) {
     __shared__ __align__(128) double sm_k[NQ * TILE];  // kappa_q, [q][column]
@@ -201,7 +201,7 @@ far_kernel(const double* __restrict__ far_k, const double* __restrict__ far_c, c
             const double rho = fast_rsqrt(r2);  // 1/r
             const double r = r2 * rho;
             double sn, cs;
-            fast_sincos_tab(wavruim * r, sm_tab, sn, cs);
+            fast_cis_tab(r, cis, sm_tab, sn, cs);
             const double m = (q == 0) ? M0 : fma(rc.a[q], E1, fma(rc.b[q], E2, M0));  // (y_q - x).n_x
             const double rho2 = rho * rho;
             if (BIMAG) {
@@ -399,6 +399,7 @@ cudaError_t launch_far_v(const DeviceMesh& m, const Phys& ph, uint64_t row_begin
     const uint8_t* col_class = m.col_class;
     const uint32_t n = m.n;
     const double wavruim = ph.wavruim, k2 = ph.k2, bre = ph.beta.re, bim = ph.beta.im;
+    const CisConst cis = make_cis_const(ph.wavruim);
     constexpr size_t TAB_BYTES = SINCOS_TAB * sizeof(double2);
     {
         static std::atomic<unsigned char> attr_done[64];
@@ -413,7 +414,7 @@ cudaError_t launch_far_v(const DeviceMesh& m, const Phys& ph, uint64_t row_begin
     }
     auto launch = [=](cudaStream_t st, unsigned int g, unsigned int* ctr) -> cudaError_t {
         far_kernel<NQ, BIMAG, MINB><<<g, TILE, TAB_BYTES, st>>>(far_k, far_c, col_class, src, n, row_begin, row_end, rpb, nchunks, total, ipb,
-                                                       wavruim, k2, cH, bre, bim, A, lda, near_list, near_cap, near_count, ctr);
+                                                       wavruim, cis, k2, cH, bre, bim, A, lda, near_list, near_cap, near_count, ctr);
         return cudaGetLastError();
     };
     if (counter && relaunch) {

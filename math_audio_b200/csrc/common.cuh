@@ -89,22 +89,41 @@ __device__ __forceinline__ void fast_sincos(double x, double& s_out, double& c_o
     c_out = cc;
 }
 
-// Table variant for the far kernel: reduction by pi/1024 against a 2048-entry (cos, sin) table held in shared memory
-// (32 KB), cubic / quartic Taylor kernels on |t| <= pi/2048 (truncation t^5/120 = 7e-17 resp. t^6/720 = 2e-20; max abs error
-// 1.7e-16 over [0, 5000], checked on the host with long-double references and on the device by bemb200_selftest_math) and one
-// complex rotation: 13 DP-pipe instructions, no quadrant selects.  tab[i] = (cos(i*pi/1024), sin(i*pi/1024)).
+// Table variant for the far kernel: e^{i kappa r} straight from the distance r.  kappa (= harmonic_factor * k) is folded into
+// the reduction constants and the Taylor coefficients, so neither the product kappa*r nor a second Cody-Waite term is computed:
+//     q = rint(r * c1),  c1 = 1024 kappa / pi;      t' = r - q * c2,  c2 = pi / (1024 kappa)      (theta = q pi/1024 + kappa t')
+//     sin(kappa t') = t' (kappa - kappa^3/6 t'^2),   cos(kappa t') = 1 - kappa^2/2 t'^2 + kappa^4/24 t'^4      (|kappa t'| <= pi/2048:
+//     truncation 7e-17 resp. 2e-20), then one complex rotation by the table entry (cos, sin)(q pi/1024): 12 DP-pipe instructions,
+//     no quadrant selects.  The only error that grows with the argument is the rounding of c2 (relative 1.1e-16, i.e. at most
+//     1.1e-16 * |kappa r| in the phase) -- the same size as the rounding of the product kappa*r that the reference's sin(k*r) starts
+//     from.  Checked on the device against a double-double reference by bemb200_selftest_math.
 constexpr int SINCOS_TAB = 2048;
 constexpr double SINCOS_STEPS_PER_PI = 1024.0;
-__device__ __forceinline__ void fast_sincos_tab(double x, const double2* __restrict__ tab, double& s_out, double& c_out) {
+struct CisConst {
+    double c1, c2;       // reduction
+    double s1, s3;       // kappa, -kappa^3/6
+    double k2h, k4;      // -kappa^2/2, kappa^4/24
+};
+// host side (the launchers): c2 is rounded ONCE from the long-double quotient
+inline CisConst make_cis_const(double kappa) {
+    CisConst c;
+    c.c1 = kappa * 325.94932345220167;  // 1024/pi
+    c.c2 = kappa != 0.0 ? (double)(0.0030679615757712823008853099L / (long double)kappa) : 0.0;  // pi/1024  (kappa = 0: q = 0, sin = 0, cos = 1)
+    c.s1 = kappa;
+    c.s3 = -(kappa * kappa * kappa) / 6.0;
+    c.k2h = -0.5 * kappa * kappa;
+    c.k4 = (kappa * kappa) * (kappa * kappa) / 24.0;
+    return c;
+}
+__device__ __forceinline__ void fast_cis_tab(double r, const CisConst& cc, const double2* __restrict__ tab, double& s_out, double& c_out) {
     const double MAGIC = 6755399441055744.0;
-    double tq = fma(x, 325.94932345220167, MAGIC);  // 1024/pi
+    const double tq = fma(r, cc.c1, MAGIC);
     const int idx = __double2loint(tq) & (SINCOS_TAB - 1);
     const double q = tq - MAGIC;
-    double t = fma(-q, 0.0030679615757712823, x);   // pi/1024 hi
-    t = fma(-q, 1.195944139792337e-19, t);          // pi/1024 lo
+    const double t = fma(-q, cc.c2, r);
     const double z = t * t;
-    const double sn = fma(t * z, -1.6666666666666666e-01, t);
-    const double cs = fma(z, fma(z, 4.1666666666666664e-02, -0.5), 1.0);
+    const double sn = t * fma(z, cc.s3, cc.s1);
+    const double cs = fma(z, fma(z, cc.k4, cc.k2h), 1.0);
     const double2 CS = tab[idx];
     c_out = fma(CS.x, cs, -(CS.y * sn));
     s_out = fma(CS.y, cs, CS.x * sn);

@@ -1236,7 +1236,11 @@ dfma_peak_kernel(double* out, int iters, double a, double b) {
 __device__ __forceinline__ void atomic_max_pos(double* addr, double v) {
     atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
 }
-__global__ void math_selftest_kernel(uint64_t n, double xmax, double* err) {
+struct SelftestKappas {
+    double kap[8];
+    CisConst pos[8], neg[8];
+};
+__global__ void math_selftest_kernel(uint64_t n, double xmax, double* err, SelftestKappas kk) {
     __shared__ double2 tab[SINCOS_TAB];
     for (int i = threadIdx.x; i < SINCOS_TAB; i += blockDim.x) {
         double sv, cv;
@@ -1254,10 +1258,18 @@ __global__ void math_selftest_kernel(uint64_t n, double xmax, double* err) {
         sincos(x, &s, &c);
         fast_sincos(x, fs, fc);
         e_sc = fmax(e_sc, fmax(fabs(fs - s), fabs(fc - c)));
-        fast_sincos_tab(x, tab, fs, fc);   // the far kernel's variant
-        e_sc = fmax(e_sc, fmax(fabs(fs - s), fabs(fc - c)));
-        fast_sincos_tab(-x, tab, fs, fc);  // harmonic_factor = -1
-        e_sc = fmax(e_sc, fmax(fabs(fs + s), fabs(fc - c)));
+        // the far kernel's variant takes the distance r and has kappa folded into its constants: reference = sin / cos of the
+        // EXACT product kappa * r (double-double: p + e), first-order corrected
+        const int ki = (int)(k & 7);
+        const double kap = kk.kap[ki];
+        const double r = x / kap;
+        const double p = kap * r, e = fma(kap, r, -p);
+        sincos(p, &s, &c);
+        const double s_ref = fma(e, c, s), c_ref = fma(-e, s, c);
+        fast_cis_tab(r, kk.pos[ki], tab, fs, fc);
+        e_sc = fmax(e_sc, fmax(fabs(fs - s_ref), fabs(fc - c_ref)));
+        fast_cis_tab(r, kk.neg[ki], tab, fs, fc);  // harmonic_factor = -1
+        e_sc = fmax(e_sc, fmax(fabs(fs + s_ref), fabs(fc - c_ref)));
         double a = x * x + 1e-12;
         double ref = 1.0 / sqrt(a);
         e_rs = fmax(e_rs, fabs(fast_rsqrt(a) - ref) / ref);
@@ -1692,7 +1704,14 @@ cudaError_t launch_dfma_peak(double* out, int iters, cudaStream_t s) {
 }
 
 cudaError_t launch_math_selftest(uint64_t n, double xmax, double* err, cudaStream_t s) {
-    math_selftest_kernel<<<148 * 4, 256, 0, s>>>(n, xmax, err);
+    SelftestKappas kk;
+    const double kaps[8] = {1.0, 2.5, 9.162978572970230, 18.31686157546442, 20.0, 36.63372315092884, 0.3, 146.5348926037154};
+    for (int i = 0; i < 8; ++i) {
+        kk.kap[i] = kaps[i];
+        kk.pos[i] = make_cis_const(kaps[i]);
+        kk.neg[i] = make_cis_const(-kaps[i]);
+    }
+    math_selftest_kernel<<<148 * 4, 256, 0, s>>>(n, xmax, err, kk);
     return cudaGetLastError();
 }
 
