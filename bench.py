@@ -464,7 +464,7 @@ def run_config5(ctx, dev):
     B = np.stack([system.rhs + IncidentField.plane_wave(d).compute_rhs_with_beta(mesh.center, mesh.normal, ph, beta)
                   for d in fibonacci_directions(nrhs)])
     cfg = bem.GmresConfig(max_iterations=GMRES_MAX_CYCLES, restart=GMRES_RESTART, tolerance=GMRES_TOL)
-    bem.gmres_batched(op, B[:8], bem.GmresConfig(1, 2, GMRES_TOL))  # untimed: workspace of the batched solver
+    bem.gmres_batched(op, B, bem.GmresConfig(1, GMRES_RESTART, GMRES_TOL))  # untimed: allocates the 32 Krylov bases of the batched solver
     X = np.random.default_rng(1).standard_normal((nrhs, n)) + 1j * np.random.default_rng(2).standard_normal((nrhs, n))
     kms = min(bem.apply_block(op, X)[1] for _ in range(3))
     torch.cuda.synchronize(dev)

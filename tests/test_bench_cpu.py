@@ -2,6 +2,7 @@
 (tests/golden/make_golden_large.py)."""
 import json
 import os
+import re
 import subprocess
 import sys
 from pathlib import Path
@@ -84,3 +85,50 @@ def test_config2_solution_fixture_is_consistent(tag):
     assert g["x"].shape == (20480,) and g["x"].dtype == np.complex128
     assert float(g["gmres_vs_lu"]) < 1e-8 and float(g["residual"]) < 1e-10
     assert 20 <= int(g["iterations"]) <= 300
+
+
+def test_config3_golden_rows_match_the_oracle():
+    """bench.py builds the same cabinet as the fixture generator, and the committed rows of the 50 176-element Quad4 box are what
+    the oracle computes today (entries, whole-row dot product and the piston's right-hand-side term of two of the 16 rows)."""
+    sys.path.insert(0, str(ROOT))
+    import bench
+    from math_audio_b200.types import PhysicsParams
+    from oracle import oracle as orc
+
+    g = np.load(GOLD / "config3_rows.npz")
+    mesh = bench.cabinet_mesh(1.0)
+    assert mesh.num_dofs == int(g["n"]) == 50176
+    assert int(np.count_nonzero(np.abs(mesh.bc_val[:, 0]) > 0)) > 100  # the piston
+    ph = PhysicsParams.new(1000.0, 343.0, 1.21, False)
+    beta = ph.burton_miller_beta()
+    assert abs(beta - complex(g["beta"])) == 0.0 and ph.wave_number == float(g["k"])
+    rng = np.random.default_rng(1234)
+    xprobe = rng.standard_normal(mesh.num_dofs) + 1j * rng.standard_normal(mesh.num_dofs)
+    assert np.max(np.abs(g["rhs"])) > 0.0
+    for i in (1, len(g["rows"]) - 1):
+        r = int(g["rows"][i])
+        A, rhs, _ = orc.assemble(mesh, ph.wave_number, beta, row_begin=r, row_end=r + 1)
+        assert np.array_equal(A[0, g["cols"][i]], g["vals"][i])
+        assert np.dot(A[0], xprobe) == g["rowdot"][i] and rhs[0] == g["rhs"][i]
+
+
+def test_config3_and_config5_solution_fixtures_are_consistent():
+    g = np.load(GOLD / "config3_coarse_x.npz")
+    assert int(g["n"]) == 12544 and g["x"].shape == (12544,) and g["b"].shape == (12544,)
+    assert float(g["gmres_vs_lu"]) < 1e-8 and float(g["residual"]) < 1e-10 and int(g["iterations"]) == 195
+    g = np.load(GOLD / "config5_rhs32.npz")
+    assert g["iterations"].shape == (32,) and g["restarts"].shape == (32,) and g["x"].shape == (3, 20480)
+    assert list(g["x_cols"]) == [0, 13, 31] and float(np.max(g["residual"])) < 1e-10
+    assert 90 <= int(g["iterations"].min()) and int(g["iterations"].max()) <= 100
+
+
+def test_side_blocks_are_wired_into_the_native_line():
+    """The configurations BASELINE.json names beside the headline ride along in the driver-run bench: config 5 on one GPU,
+    config 3 at 2 and 4 GPUs, config 4 at 8 -- and none of them imports the oracle."""
+    src = (ROOT / "bench.py").read_text()
+    for key in ('line["config3"]', 'line["config4"]', 'line["config5"]'):
+        assert key in src
+    for fn in ("run_config3", "run_config4", "run_config5", "run_sharded_parity"):
+        body = src[src.index(f"def {fn}("):]
+        body = body[: body.index("\ndef ", 10)]
+        assert not re.search(r"^\s*(from\s+oracle|import\s+oracle)", body, re.M), fn

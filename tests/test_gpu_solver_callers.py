@@ -320,14 +320,21 @@ def test_mesh_convergence_forward_back_and_phase(bem, orc):  # :328-416, :419-49
 
 
 # ---- the boundary extensions of round 2: single-process multi-GPU group, sweep behind the C ABI ------------------------
-def test_single_process_group_two_ranks_on_one_gpu(bem, orc):
-    """bemb200_multi_*: one process, two rank contexts.  Listing device 0 twice splits its SMs between the two persistent
-    solver kernels, so the row-sharded code path (peer-buffer exchange of the Krylov vector, cross-rank reduction round,
-    sharded Gram-Schmidt) runs on the single GPU of the driver's test box.  Entries, iteration counts, solution vs oracle."""
+@pytest.mark.parametrize("devices", [[0, 0], [0, 1], [0, 1, 2, 3]], ids=["one_gpu_twice", "two_gpus", "four_gpus"])
+def test_single_process_group_two_ranks_on_one_gpu(bem, orc, devices):
+    """bemb200_multi_*: one process, one rank context per listed device.  Listing device 0 twice splits its SMs between the two
+    persistent solver kernels, so the row-sharded code path (peer-buffer exchange of the Krylov vector, cross-rank reduction
+    round, sharded Gram-Schmidt) runs on the single GPU of the driver's test box; [0, 1] and [0, 1, 2, 3] are the real thing
+    (cudaDeviceEnablePeerAccess between the devices; skipped when the box has fewer GPUs).  Entries, iteration counts,
+    solution vs oracle."""
+    import torch
+
     from math_audio_b200.incident import IncidentField
 
+    if max(devices) >= torch.cuda.device_count():
+        pytest.skip(f"needs {max(devices) + 1} GPUs")
     a = 0.1
-    grp = bem.MultiGpu([0, 0])
+    grp = bem.MultiGpu(devices)
     for sub, ka, restart in ((2, 1.0, 50), (3, 3.0, 50), (3, 8.0, 10)):
         mesh = generate_icosphere_mesh(a, sub)
         if sub == 3:

@@ -3,8 +3,8 @@
 
     python tools/far_sass_count.py [object-or-library] [kernel-name-substring ...]
 
-Disassembles with cuobjdump -sass, takes for each matching kernel the LAST backward branch that spans the largest
-body (the row loop), and counts the instructions in it by class.  DP = DFMA + DMUL + DADD (+ DSETP): what the FP64
+Disassembles with cuobjdump -sass, takes for each matching kernel the smallest backward-branch span holding >= 90 % of
+its DFMAs (the loop over collocation rows) and counts the instructions in it by class.  DP = DFMA + DMUL + DADD (+ DSETP): what the FP64
 pipe executes per pair; 924 algorithmic flops per Tri3 pair = 462 DFMA equivalents."""
 import collections
 import re
@@ -33,13 +33,16 @@ def kernels(path):
 
 
 def row_loop(body):
+    """The smallest backward-branch span that holds at least 90 % of the kernel's DFMAs: the loop over collocation rows."""
+    dfma = [a for a, i in body if classify(i) == "DFMA"]
     best = None
     for addr, ins in body:
         m = re.search(r"BRA(?:\.U)?(?:\.ANY)?\s+(?:\S+,\s*)?0x([0-9a-f]+)", ins)
         if m:
             tgt = int(m.group(1), 16)
-            if tgt < addr and (best is None or addr - tgt > best[1] - best[0]):
-                best = (tgt, addr)
+            if tgt < addr and sum(1 for a in dfma if tgt <= a <= addr) >= 0.9 * len(dfma):
+                if best is None or addr - tgt < best[1] - best[0]:
+                    best = (tgt, addr)
     return best
 
 
