@@ -331,6 +331,46 @@ def run_sharded_parity(ctx, rank, world, dev):
     return out if rank == 0 else None
 
 
+def block_jacobi_leg(bem, op, b, cfg, world, dev, block_size, x_plain, plain_iterations, plain_solve_s):
+    """gmres_preconditioned with the device-built block-Jacobi preconditioner (AdditiveSchwarzPreconditioner, overlap 0,
+    math-solvers/src/preconditioners/schwarz.rs) on rank-aligned contiguous diagonal blocks of about `block_size` DOFs, next to
+    the plain solve of the same system: set-up time, iterations, solve time, independent true residual, distance to the plain
+    solution.  Collective; every rank returns the block."""
+    import torch
+    import torch.distributed as dist
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    n = op.num_rows()
+    parts = bem.schwarz_partition_aligned(n, world, block_size)
+    barrier()
+    t0 = time.perf_counter()
+    pre = bem.AdditiveSchwarzPreconditioner.from_operator(op, subdomains=parts)
+    barrier()
+    t1 = time.perf_counter()
+    sol = bem.gmres_preconditioned(op, pre, b, cfg)
+    barrier()
+    t2 = time.perf_counter()
+    st = pre.stats()
+    res = float(np.linalg.norm(op.apply(sol.x) - b) / np.linalg.norm(b))
+    dx = float(np.linalg.norm(sol.x - x_plain) / np.linalg.norm(x_plain)) if x_plain is not None else None
+    tim = torch.tensor([t1 - t0, t2 - t1, st["factor_ms"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tim, op=dist.ReduceOp.MAX)
+    pre.close()
+    return {"preconditioner": "block-Jacobi = AdditiveSchwarzPreconditioner, overlap 0 (schwarz.rs), contiguous rank-aligned blocks; "
+                              "explicit inverse blocks applied as one batched block GEMV per Arnoldi step",
+            "blocks": int(st["num_subdomains"]), "block_size_max": int(st["max_size"]),
+            "inverse_mb_per_gpu": st["inverse_bytes"] / 1e6, "setup_s": float(tim[0]), "setup_ms_device": float(tim[2]),
+            "iterations": sol.iterations, "restarts": sol.restarts, "converged": sol.converged,
+            "preconditioned_residual": sol.residual, "independent_true_residual": res, "solve_s": float(tim[1]),
+            "setup_plus_solve_s": float(tim[0] + tim[1]), "plain_iterations": plain_iterations, "plain_solve_s": plain_solve_s,
+            "x_rel_diff_vs_plain": dx, "host_buffers": True}
+
+
 def run_config4(ctx, rank, world, dev, reps=2):
     """BASELINE.json configs[3] / the north-star target inside the driver-run bench: 121 680-element rigid
     geodesic sphere, ka = 16, adaptive beta, row-sharded over all ranks, one assemble + GMRES(50, 1e-10)
@@ -387,7 +427,7 @@ def run_config4(ctx, rank, world, dev, reps=2):
         if world > 1:
             dist.all_reduce(tim, op=dist.ReduceOp.MAX)
         cur = dict(s=float(tim[0]), asm_s=float(tim[1]), far_ms=float(tim[2]), asm_ms=float(tim[3]), mv_ms=float(tim[4]), sol=sol,
-                   launches=int(st_a["total_launches"] + st_s["kernel_launches"]))
+                   launches=int(st_a["total_launches"] + st_s["kernel_launches"]), solve_s=float(tim[0] - tim[1]))
         if rep > 0 and (best is None or cur["s"] < best["s"]):
             best = cur
     best = best or cur
@@ -395,6 +435,14 @@ def run_config4(ctx, rank, world, dev, reps=2):
     # independent residual through the operator boundary
     bem.apply_device(op, x_dev.data_ptr(), y_dev.data_ptr())
     res = float((torch.linalg.vector_norm(b_dev - y_dev) / torch.linalg.vector_norm(b_dev)).item())
+    # the same system through gmres_preconditioned with the device-built block-Jacobi preconditioner
+    bj = None
+    if not os.environ.get("BENCH_NO_BLOCK_JACOBI"):
+        try:
+            bj = block_jacobi_leg(bem, op, b, cfg, world, dev, int(os.environ.get("BENCH_BJ_BLOCK", "256")), x_dev.cpu().numpy(),
+                                  best["sol"].iterations, best["solve_s"])
+        except Exception as e:  # the north-star block must survive a failure of the side leg
+            bj = {"error": f"{type(e).__name__}: {e}"}
     block = {"workload": wl["name"], "description": wl["desc"], "n_elements": int(n), "n_gpus": world, "rows_per_gpu": int(nloc),
              "matrix_gb_per_gpu": 16.0 * nloc * n / 1e9}
     errs = torch.zeros(3, dtype=torch.float64, device=dev)
@@ -440,7 +488,39 @@ def run_config4(ctx, rank, world, dev, reps=2):
                     "max_entry_rel_err": float(errs[0]), "max_row_normwise_err": float(errs[1]), "max_rowdot_err": float(errs[2]),
                     "bar": 1e-10} if gpath.exists() else {"skipped": "tests/golden/config4_rows.npz missing"}),
     })
+    if bj is not None:
+        block["block_jacobi"] = bj
     return block
+
+
+def run_precond_config2(ctx, dev):
+    """Block-Jacobi on the headline workload's mesh (icosphere(5), one GPU) at the two ends of its frequency range that need
+    the most iterations: plain gmres() against gmres_preconditioned() with 64-DOF diagonal blocks (the icosphere's element
+    order is hierarchical, 64 consecutive elements = one level-2 parent triangle).  The headline `value` stays the plain solve."""
+    from math_audio_b200 import bem
+    from math_audio_b200.incident import IncidentField
+
+    a = 0.1
+    mesh = generate_icosphere_mesh(a, 5)
+    n = mesh.num_dofs
+    cfg = bem.GmresConfig(max_iterations=GMRES_MAX_CYCLES, restart=GMRES_RESTART, tolerance=GMRES_TOL)
+    out = {"workload": "sphere20k", "n_elements": int(n), "block_size": 64, "cases": []}
+    system = None
+    for ka in (2.0, 8.0):
+        ph = PhysicsParams.from_wave_number(ka / a)
+        beta, _ = ph.burton_miller_beta_adaptive(a)
+        system = bem.build_tbem_system_with_beta(mesh, ph, beta, ctx=ctx, reuse=system)
+        b = system.rhs_full() + IncidentField.plane_wave_z().compute_rhs_with_beta(mesh.center, mesh.normal, ph, beta)
+        op = bem.DenseOperator(system)
+        bem.gmres(op, b, bem.GmresConfig(1, 2, GMRES_TOL))
+        t0 = time.perf_counter()
+        plain = bem.gmres(op, b, cfg)
+        t_plain = time.perf_counter() - t0
+        leg = block_jacobi_leg(bem, op, b, cfg, 1, dev, 64, plain.x, plain.iterations, t_plain)
+        leg["ka"] = ka
+        out["cases"].append(leg)
+    system.matrix.close()
+    return out
 
 
 def run_config5(ctx, dev):
@@ -851,6 +931,13 @@ def run_native(args):
             config5 = run_config5(ctx, dev)
         except Exception as e:  # the headline line must survive a failure of the side block
             config5 = {"error": f"{type(e).__name__}: {e}"}
+    # ---- block-Jacobi preconditioned solves of the same mesh ride along on one GPU
+    precond = None
+    if world == 1 and not os.environ.get("BENCH_NO_BLOCK_JACOBI") and not os.environ.get("BENCH_NO_CONFIG5"):
+        try:
+            precond = run_precond_config2(ctx, dev)
+        except Exception as e:
+            precond = {"error": f"{type(e).__name__}: {e}"}
     # ---- the Quad4 cabinet (config 3) rides along at 2 and 4 GPUs (the sizes BASELINE.json quotes it on)
     config3 = None
     if (world in (2, 4) or os.environ.get("BENCH_CONFIG3")) and not os.environ.get("BENCH_NO_CONFIG3"):
@@ -964,6 +1051,8 @@ def run_native(args):
         line["sharded_parity"] = sharded_parity
     if config5 is not None:
         line["config5"] = config5
+    if precond is not None:
+        line["block_jacobi"] = precond
     if config3 is not None:
         line["config3"] = config3
     if config4 is not None:

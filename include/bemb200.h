@@ -182,6 +182,40 @@ int bemb200_gmres_preconditioned(const bemb200_matrix* m, const double* inv_diag
                                  bemb200_gmres_info* info);
 /* diagonal of the (square) matrix, all ranks receive all num_rows entries */
 int bemb200_matrix_diagonal(const bemb200_matrix* m, double* out);
+/* Block-Jacobi / additive Schwarz preconditioner built on the device from the assembled operator:
+ * AdditiveSchwarzPreconditioner::from_csr(matrix, num_subdomains, overlap)
+ * (math-solvers/src/preconditioners/schwarz.rs:66-125) with the local solve of schwarz.rs:252-380 -- ILU(0) of the
+ * extracted block, which for the dense block of a BEM operator is LU without pivoting, then forward / backward
+ * substitution -- and the weighted combination of schwarz.rs:399-417.
+ *   sub_ptr == NULL: the reference's contiguous partition into num_subdomains blocks (overlap 0, i.e. block-Jacobi on the
+ *                    diagonal blocks: the near field of consecutive DOF clusters, cf. compute_near_block,
+ *                    math-bem/src/core/assembly/slfmm.rs:538-608);
+ *   otherwise subdomain k holds the global DOF indices sub_idx[sub_ptr[k] .. sub_ptr[k+1]) in the order that becomes its
+ *   local numbering (the reference keeps them ascending, schwarz.rs:199-202); sets may overlap (weights 1 / multiplicity).
+ * A subdomain holds at most 4096 unknowns.  On a row-sharded operator every rank passes the same subdomains and each must
+ * lie inside one rank's row block (BEMB200_EINVAL otherwise): M^-1 then acts on a rank's slab without communication.
+ * The handle is independent of the matrix after creation (it stores the inverse blocks). */
+typedef struct bemb200_precond bemb200_precond;
+typedef struct bemb200_precond_stats {
+    uint32_t num_subdomains;   /* stats() of schwarz.rs:135-158: count, min / max / average size */
+    uint32_t local_subdomains; /* owned by this rank */
+    uint32_t min_size, max_size;
+    double avg_size;
+    uint64_t inverse_bytes;    /* bytes one application streams on this rank */
+    double factor_ms;          /* device time of gather + factorisation + inversion */
+    int32_t disjoint;          /* 1: every local row in exactly one subdomain (block-Jacobi) */
+} bemb200_precond_stats;
+int bemb200_schwarz_create(const bemb200_matrix* m, uint32_t num_subdomains, const uint64_t* sub_ptr, const uint64_t* sub_idx,
+                           bemb200_precond** out);
+void bemb200_precond_free(bemb200_precond* p);
+int bemb200_precond_stats_get(const bemb200_precond* p, bemb200_precond_stats* out);
+/* Preconditioner::apply (math-solvers/src/traits.rs:366-371): z = M^-1 r, num_rows complex128 on the HOST (collective on a
+ * row-sharded operator; every rank receives the whole z) */
+int bemb200_precond_apply(const bemb200_precond* p, const double* r, double* z);
+/* gmres_preconditioned_with_guess (gmres.rs:434-585) with that preconditioner: per Arnoldi step the ZGEMV, the block
+ * solve on the rank's slab, the exchange, one Gram-Schmidt kernel.  Arguments as bemb200_gmres_preconditioned. */
+int bemb200_gmres_schwarz(const bemb200_matrix* m, const bemb200_precond* precond, const double* b, const double* x0,
+                          uint32_t max_iterations, uint32_t restart, double tolerance, double* x_out, bemb200_gmres_info* info);
 /* same with DEVICE pointers (b_dev, x0_dev or NULL, x_dev) */
 int bemb200_gmres_device(const bemb200_matrix* m, const double* b_dev, const double* x0_dev, uint32_t max_iterations,
                          uint32_t restart, double tolerance, double* x_dev, bemb200_gmres_info* info);

@@ -46,6 +46,11 @@ class CAssemblyStats(C.Structure):
                 ("total_launches", C.c_uint64), ("far_ms", C.c_double), ("total_ms", C.c_double)]
 
 
+class CPrecondStats(C.Structure):
+    _fields_ = [("num_subdomains", C.c_uint32), ("local_subdomains", C.c_uint32), ("min_size", C.c_uint32), ("max_size", C.c_uint32),
+                ("avg_size", C.c_double), ("inverse_bytes", C.c_uint64), ("factor_ms", C.c_double), ("disjoint", C.c_int32)]
+
+
 class CRoomSource(C.Structure):
     _fields_ = [("position", C.c_double * 3), ("amplitude", C.c_double), ("directivity", C.c_void_p),
                 ("n_horizontal", C.c_uint32), ("n_vertical", C.c_uint32)]
@@ -91,6 +96,11 @@ SYMBOLS = {
     "bemb200_gmres": (C.c_int, [_VP, _VP, _VP, C.c_uint32, C.c_uint32, C.c_double, _VP, C.POINTER(CGmresInfo)]),
     "bemb200_gmres_preconditioned": (C.c_int, [_VP, _VP, _VP, _VP, C.c_uint32, C.c_uint32, C.c_double, _VP, C.POINTER(CGmresInfo)]),
     "bemb200_matrix_diagonal": (C.c_int, [_VP, _VP]),
+    "bemb200_schwarz_create": (C.c_int, [_VP, C.c_uint32, _VP, _VP, _PP]),
+    "bemb200_precond_free": (None, [_VP]),
+    "bemb200_precond_stats_get": (C.c_int, [_VP, C.POINTER(CPrecondStats)]),
+    "bemb200_precond_apply": (C.c_int, [_VP, _VP, _VP]),
+    "bemb200_gmres_schwarz": (C.c_int, [_VP, _VP, _VP, _VP, C.c_uint32, C.c_uint32, C.c_double, _VP, C.POINTER(CGmresInfo)]),
     "bemb200_gmres_device": (C.c_int, [_VP, _VP, _VP, C.c_uint32, C.c_uint32, C.c_double, _VP, C.POINTER(CGmresInfo)]),
     "bemb200_gmres_batched": (C.c_int, [_VP, _VP, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, _VP, C.POINTER(CGmresInfo),
                                         C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),

@@ -20,7 +20,7 @@ from __future__ import annotations
 
 import ctypes as C
 from dataclasses import dataclass
-from typing import Optional
+from typing import List, Optional, Sequence
 
 import numpy as np
 
@@ -546,18 +546,188 @@ class DiagonalPreconditioner:
         return r * self.inv_diag
 
 
+def schwarz_partition(n: int, num_subdomains: int) -> List[np.ndarray]:
+    """The contiguous partition of AdditiveSchwarzPreconditioner::from_csr (schwarz.rs:67-83): ``n / S`` DOFs per
+    subdomain, the first ``n % S`` one larger."""
+    S = min(max(int(num_subdomains), 1), n)
+    base, rem = divmod(n, S)
+    out, start = [], 0
+    for i in range(S):
+        size = base + (1 if i < rem else 0)
+        out.append(np.arange(start, start + size, dtype=np.uint64))
+        start += size
+    return out
+
+
+def schwarz_partition_aligned(n: int, nranks: int, block_size: int) -> List[np.ndarray]:
+    """Contiguous subdomains of about ``block_size`` DOFs that never straddle two ranks' row blocks (bemb200_partition):
+    the reference's partition applied inside every rank's rows."""
+    chunk = (n + nranks - 1) // nranks
+    out = []
+    for r in range(nranks):
+        b, e = min(chunk * r, n), min(chunk * (r + 1), n)
+        if e > b:
+            S = max(1, int(round((e - b) / max(1, block_size))))
+            out.extend(p + np.uint64(b) for p in schwarz_partition(e - b, S))
+    return out
+
+
+def spatial_subdomains(centers: np.ndarray, nranks: int, block_size: int) -> List[np.ndarray]:
+    """Compact clusters of at most ``block_size`` DOFs inside every rank's row block: recursive bisection of the collocation
+    points along the longest axis of their bounding box (median split).  The clusters play the role of SLFMM's leaf clusters
+    (slfmm.rs:444-460 maps clusters to DOF lists; their self blocks are the near field block-Jacobi inverts); indices inside
+    a cluster ascend, as in the reference's subdomains (schwarz.rs:199-202).  ``centers``: (n, 3) in DOF order."""
+    centers = np.asarray(centers, dtype=np.float64)
+    n = centers.shape[0]
+    chunk = (n + nranks - 1) // nranks
+    out: List[np.ndarray] = []
+
+    def split(ids: np.ndarray) -> None:
+        if len(ids) <= block_size:
+            out.append(np.sort(ids).astype(np.uint64))
+            return
+        c = centers[ids]
+        axis = int(np.argmax(c.max(axis=0) - c.min(axis=0)))
+        order = ids[np.argsort(c[:, axis], kind="stable")]
+        half = len(order) // 2
+        split(order[:half])
+        split(order[half:])
+
+    for r in range(nranks):
+        b, e = min(chunk * r, n), min(chunk * (r + 1), n)
+        if e > b:
+            split(np.arange(b, e, dtype=np.int64))
+    return out
+
+
+def voronoi_subdomains(centers: np.ndarray, nranks: int, block_size: int, iterations: int = 12) -> List[np.ndarray]:
+    """Like ``spatial_subdomains`` but the bisection clusters are relaxed by Lloyd iterations (every DOF joins the nearest
+    cluster centroid, centroids are recomputed): Voronoi patches of roughly ``block_size`` DOFs, as round as the mesh allows.
+    Deterministic.  Cluster sizes vary; a cluster never leaves its rank's row block."""
+    centers = np.asarray(centers, dtype=np.float64)
+    n = centers.shape[0]
+    chunk = (n + nranks - 1) // nranks
+    out: List[np.ndarray] = []
+    for r in range(nranks):
+        b, e = min(chunk * r, n), min(chunk * (r + 1), n)
+        if e <= b:
+            continue
+        c = centers[b:e]
+        seeds = spatial_subdomains(c, 1, block_size)
+        cent = np.array([c[s.astype(np.int64)].mean(axis=0) for s in seeds])
+        label = np.zeros(e - b, dtype=np.int64)
+        for _ in range(iterations):
+            d2 = (c * c).sum(1)[:, None] - 2.0 * (c @ cent.T) + (cent * cent).sum(1)[None, :]
+            label = np.argmin(d2, axis=1)
+            for k in range(len(cent)):
+                sel = label == k
+                if sel.any():
+                    cent[k] = c[sel].mean(axis=0)
+        for k in range(len(cent)):
+            ids = np.nonzero(label == k)[0]
+            if len(ids):
+                out.append((ids + b).astype(np.uint64))
+    return out
+
+
+def extend_partition(partition: Sequence[int], adjacency: Sequence[Sequence[int]], overlap: int, n: int) -> np.ndarray:
+    """schwarz.rs:177-203: grow a subdomain by ``overlap`` layers of neighbours, result sorted ascending."""
+    inside = np.zeros(n, dtype=bool)
+    inside[np.asarray(partition, dtype=np.int64)] = True
+    frontier = [int(i) for i in partition]
+    for _ in range(overlap):
+        new = []
+        for i in frontier:
+            for j in adjacency[i]:
+                if not inside[j]:
+                    inside[j] = True
+                    new.append(int(j))
+        frontier = new
+    return np.nonzero(inside)[0].astype(np.uint64)
+
+
+class AdditiveSchwarzPreconditioner:
+    """math-solvers/src/preconditioners/schwarz.rs on the device: block-Jacobi (overlap 0) / additive Schwarz built from the
+    assembled operator -- local solve = LU without pivoting of the dense diagonal block (ILU(0) of a full pattern)."""
+
+    def __init__(self, operator: DenseOperator, handle):
+        self.operator = operator
+        self.ctx = operator.matrix.ctx
+        self._h = handle
+        self.inv_diag = None
+
+    @staticmethod
+    def from_operator(operator: DenseOperator, num_subdomains: int = 0, overlap: int = 0,
+                      subdomains: Optional[Sequence[np.ndarray]] = None,
+                      adjacency: Optional[Sequence[Sequence[int]]] = None) -> "AdditiveSchwarzPreconditioner":
+        """``from_csr(matrix, num_subdomains, overlap)`` (schwarz.rs:66-125).  ``subdomains``: explicit index sets instead of
+        the contiguous partition (e.g. spatial clusters, rank-aligned blocks).  ``overlap`` > 0 needs ``adjacency`` (the
+        reference takes it from the sparsity pattern, schwarz.rs:161-174; a dense operator has none of its own)."""
+        n = operator.num_rows()
+        if overlap > 0:
+            if adjacency is None:
+                raise ValueError("overlap > 0 needs an adjacency (a dense operator couples every pair of DOFs)")
+            base = subdomains if subdomains is not None else schwarz_partition(n, num_subdomains)
+            subdomains = [extend_partition(p, adjacency, overlap, n) for p in base]
+        h = C.c_void_p()
+        m = operator.matrix
+        if subdomains is None:
+            _capi.check(_capi.lib().bemb200_schwarz_create(m._h, int(num_subdomains), None, None, C.byref(h)), m.ctx._h)
+        else:
+            ptr = np.zeros(len(subdomains) + 1, dtype=np.uint64)
+            ptr[1:] = np.cumsum([len(p) for p in subdomains])
+            idx = (np.concatenate([np.asarray(p, dtype=np.uint64) for p in subdomains]) if len(subdomains)
+                   else np.zeros(0, dtype=np.uint64))
+            idx = np.ascontiguousarray(idx)
+            _capi.check(_capi.lib().bemb200_schwarz_create(m._h, len(subdomains), _capi.ptr(ptr), _capi.ptr(idx), C.byref(h)), m.ctx._h)
+        return AdditiveSchwarzPreconditioner(operator, h)
+
+    def apply(self, r: np.ndarray) -> np.ndarray:  # Preconditioner::apply (traits.rs:366-371)
+        r = np.ascontiguousarray(r, dtype=np.complex128)
+        if r.shape != (self.operator.num_rows(),):
+            raise ValueError("preconditioner: wrong vector length")
+        z = np.empty_like(r)
+        _capi.check(_capi.lib().bemb200_precond_apply(self._h, _capi.ptr(r), _capi.ptr(z)), self.ctx._h)
+        return z
+
+    def stats(self) -> dict:  # schwarz.rs:135-158 (+ device figures)
+        st = _capi.CPrecondStats()
+        _capi.check(_capi.lib().bemb200_precond_stats_get(self._h, C.byref(st)), self.ctx._h)
+        return {k: getattr(st, k) for k, _ in st._fields_}
+
+    def close(self) -> None:
+        if self._h:
+            _capi.lib().bemb200_precond_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def gmres_preconditioned_with_guess(operator: DenseOperator, precond, b: np.ndarray, x0: Optional[np.ndarray],
                                     config: GmresConfig) -> GmresSolution:
     """gmres.rs:434-585: left-preconditioned restarted GMRES on the device.  ``precond`` is an
-    IdentityPreconditioner or a DiagonalPreconditioner (the two preconditioners of the reference that
-    apply to a dense operator without an O(N^3) factorisation)."""
-    if not isinstance(precond, (IdentityPreconditioner, DiagonalPreconditioner)):
-        raise TypeError("the device solver supports IdentityPreconditioner and DiagonalPreconditioner")
+    IdentityPreconditioner, a DiagonalPreconditioner or an AdditiveSchwarzPreconditioner (block-Jacobi) -- the
+    preconditioners of the reference that apply to a dense operator without an O(N^3) factorisation."""
+    if not isinstance(precond, (IdentityPreconditioner, DiagonalPreconditioner, AdditiveSchwarzPreconditioner)):
+        raise TypeError("the device solver supports IdentityPreconditioner, DiagonalPreconditioner and AdditiveSchwarzPreconditioner")
     b = np.ascontiguousarray(b, dtype=np.complex128)
     n = operator.num_rows()
     if b.shape != (n,):
         raise ValueError(f"gmres: b has shape {b.shape}, operator has {n} rows")
     x0a = np.ascontiguousarray(x0, dtype=np.complex128) if x0 is not None else None
+    if isinstance(precond, AdditiveSchwarzPreconditioner):
+        x = np.empty(n, dtype=np.complex128)
+        info = _capi.CGmresInfo()
+        _capi.check(_capi.lib().bemb200_gmres_schwarz(operator.matrix._h, precond._h, _capi.ptr(b),
+                                                      _capi.ptr(x0a) if x0a is not None else None, config.max_iterations,
+                                                      config.restart, config.tolerance, _capi.ptr(x), C.byref(info)),
+                    operator.matrix.ctx._h)
+        return GmresSolution(x=x, iterations=int(info.iterations), restarts=int(info.restarts), residual=float(info.residual),
+                             converged=bool(info.converged))
     idg = precond.inv_diag
     if idg is not None and idg.shape != (n,):
         raise ValueError("preconditioner has the wrong length")

@@ -30,6 +30,7 @@ UNITS = {
     "gmres.cu": [],
     "gmres_fused.cu": [],
     "block_gmres.cu": [],
+    "schwarz.cu": [],
     "postprocess.cu": ["-fmad=false"],
     "room.cu": [],
     "direct.cu": [],

@@ -19,6 +19,7 @@
 #include "api_internal.h"
 #include "gmres_fused.h"
 #include "linalg.h"
+#include "schwarz.h"
 
 using namespace bemb;
 
@@ -311,6 +312,27 @@ static int norm_of(bemb200_matrix* m, const cplx* b, const cplx* ax, cplx* r, do
     BEMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *out = std::sqrt(ws->scal_h[0]);
     return BEMB200_OK;
+}
+
+// dst (npad, device) = M^-1 src for the Schwarz preconditioner: every rank solves on its slab, then the slabs are gathered
+static int schwarz_full(bemb200_matrix* m, const bemb200_precond* sp, const cplx* src, cplx* dst) {
+    bemb200_ctx* ctx = m->ctx;
+    GmresWorkspace* ws = m->ws;
+    const uint64_t off = ctx->nranks > 1 ? (uint64_t)ctx->rank * ws->chunk : m->r0;
+    BEMB_CUDA(ctx, schwarz_apply_local(sp, src + m->r0, dst + off, ctx->stream));
+    m->last_launches += schwarz_apply_launches(sp);
+    if (ctx->nranks > 1) return nccl_allgather_bytes(ctx, dst + off, dst, ws->chunk * sizeof(cplx));
+    return BEMB200_OK;
+}
+// r = M^-1 (b - A x) with A x in ws->w; *out = ||r||  (gmres.rs:473-476)
+static int schwarz_residual(bemb200_matrix* m, const bemb200_precond* sp, const cplx* b, double* out) {
+    bemb200_ctx* ctx = m->ctx;
+    GmresWorkspace* ws = m->ws;
+    BEMB_CUDA(ctx, launch_residual(b, ws->w, ws->r, m->n_rows, ws->scal_d, nullptr, ctx->stream));  // r = b - A x
+    m->last_launches += 1;
+    int rc = schwarz_full(m, sp, ws->r, ws->w);
+    if (rc != BEMB200_OK) return rc;
+    return norm_of(m, ws->w, nullptr, ws->r, out);  // r = M^-1 (b - A x), its norm
 }
 
 static int update_x(bemb200_matrix* m, cplx* x, const std::vector<cplx>& y) {
@@ -650,20 +672,28 @@ extern "C" void bemb200_debug_fused_times(double* total_ms, double* matvec_ms, d
 // `precond` selects the left-preconditioned variant gmres_preconditioned_with_guess
 // (gmres.rs:434-585): pinv = inverse diagonal on the device (DiagonalPreconditioner) or nullptr
 // with precond = true (IdentityPreconditioner).
+// `sp`: additive Schwarz / block-Jacobi preconditioner (schwarz.cu) instead of a diagonal one: M^-1 acts on the rank's slab of
+// A v between the ZGEMV and the exchange; the Gram-Schmidt kernel then sees an already preconditioned vector.
 static int gmres_core(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t max_iterations, uint32_t restart, double tol,
-                      bemb200_gmres_info* info, bool precond = false, const cplx* pinv = nullptr) {
+                      bemb200_gmres_info* info, bool precond = false, const cplx* pinv = nullptr, const bemb200_precond* sp = nullptr) {
     bemb200_ctx* ctx = m->ctx;
     GmresWorkspace* ws = m->ws;
     const uint64_t n = m->n_rows;
     const int mm = (int)restart;
     cudaStream_t s = ctx->stream;
-    {
+    if (!sp) {
         bool used = false;
         int frc = gmres_fused_solve(m, b, x, max_iterations, restart, tol, info, precond, pinv, &used);
         if (frc != BEMB200_OK || used) return frc;
     }
     double b_norm = 0.0;
-    int rc = norm_of(m, b, nullptr, nullptr, &b_norm, pinv);  // ||b|| resp. ||M^-1 b|| (gmres.rs:455-457)
+    int rc = BEMB200_OK;
+    if (sp) {
+        rc = schwarz_full(m, sp, b, ws->w);  // M^-1 b
+        if (rc == BEMB200_OK) rc = norm_of(m, ws->w, nullptr, nullptr, &b_norm);
+    } else {
+        rc = norm_of(m, b, nullptr, nullptr, &b_norm, pinv);  // ||b|| resp. ||M^-1 b|| (gmres.rs:455-457)
+    }
     if (rc != BEMB200_OK) return rc;
     const int direct_scale = precond ? 1 : 0;
     if (b_norm < 1e-15) {
@@ -696,7 +726,7 @@ static int gmres_core(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t max_it
         if (!every) ctx->px.ok = false;
         if (ctx->px.err_h) *ctx->px.err_h = 0;
     }
-    const bool peer_fused = allow_grid && ctx->nranks > 1 && ctx->px.ok && ctx->px.npad >= ws->npad && ws->npad == ws->chunk * (uint64_t)ctx->nranks &&
+    const bool peer_fused = !sp && allow_grid && ctx->nranks > 1 && ctx->px.ok && ctx->px.npad >= ws->npad && ws->npad == ws->chunk * (uint64_t)ctx->nranks &&
                             mgs_peer_wait_capable(n, restart, allow_grid);
     static const unsigned long long peer_timeout_ns = []() {
         const char* v = std::getenv("BEMB200_PEER_TIMEOUT_MS");
@@ -711,7 +741,7 @@ static int gmres_core(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t max_it
         rc = matvec(m, x, ws->w, true);
         if (rc != BEMB200_OK) return rc;
         double beta = 0.0;
-        rc = norm_of(m, b, ws->w, ws->r, &beta, pinv);
+        rc = sp ? schwarz_residual(m, sp, b, &beta) : norm_of(m, b, ws->w, ws->r, &beta, pinv);
         if (rc != BEMB200_OK) return rc;
         accumulate_matvec_time(m);
         double rel = beta / b_norm;
@@ -753,8 +783,12 @@ static int gmres_core(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t max_it
                 pw.timeout_ns = peer_timeout_ns;
             } else {
                 cplx* yloc = ws->w + (ctx->nranks > 1 ? (uint64_t)ctx->rank * ws->chunk : m->r0);
-                BEMB_CUDA(ctx, launch_zgemv(m->A, m->n_cols, nloc, m->n_cols, ws->V + (uint64_t)j * ws->npad, yloc, s));
+                BEMB_CUDA(ctx, launch_zgemv(m->A, m->n_cols, nloc, m->n_cols, ws->V + (uint64_t)j * ws->npad, sp ? sp->tmp : yloc, s));
                 BEMB_CUDA(ctx, cudaEventRecord(ws->it_ev1[j], s));
+                if (sp) {  // w = M^-1 (A v_j) on this rank's rows (gmres.rs:513-514)
+                    BEMB_CUDA(ctx, schwarz_apply_local(sp, sp->tmp, yloc, s));
+                    m->last_launches += schwarz_apply_launches(sp);
+                }
                 if (ctx->nranks > 1) {
                     int rc2 = nccl_allgather_bytes(ctx, yloc, ws->w, ws->chunk * sizeof(cplx));
                     if (rc2 != BEMB200_OK) return rc2;
@@ -849,7 +883,7 @@ static int gmres_core(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t max_it
     rc = matvec(m, x, ws->w, true);
     if (rc != BEMB200_OK) return rc;
     double rn = 0.0;
-    rc = norm_of(m, b, ws->w, ws->r, &rn, pinv);
+    rc = sp ? schwarz_residual(m, sp, b, &rn) : norm_of(m, b, ws->w, ws->r, &rn, pinv);
     if (rc != BEMB200_OK) return rc;
     accumulate_matvec_time(m);
     *info = bemb200_gmres_info{total_iterations, restarts, rn / b_norm, 0};
@@ -1208,6 +1242,34 @@ int bemb200_gmres_preconditioned(const bemb200_matrix* cm, const double* inv_dia
         pinv = ws->xin;
     }
     rc = gmres_core(m, ws->bin, ws->xout, max_iterations, restart, tolerance, info, true, pinv);
+    if (rc != BEMB200_OK) return rc;
+    BEMB_CUDA(ctx, cudaMemcpyAsync(x_out, ws->xout, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    BEMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BEMB200_OK;
+}
+
+int bemb200_gmres_schwarz(const bemb200_matrix* cm, const bemb200_precond* precond, const double* b, const double* x0,
+                          uint32_t max_iterations, uint32_t restart, double tolerance, double* x_out, bemb200_gmres_info* info) {
+    bemb200_matrix* m = const_cast<bemb200_matrix*>(cm);
+    if (!m || !precond || !b || !x_out || !info) return set_error(nullptr, BEMB200_EINVAL, "NULL argument");
+    bemb200_ctx* ctx = m->ctx;
+    if (m->n_rows != m->n_cols) return set_error(ctx, BEMB200_EINVAL, "gmres needs a square operator");
+    if (restart == 0) return set_error(ctx, BEMB200_EINVAL, "restart must be >= 1");
+    if (precond->ctx != ctx || precond->n != m->n_rows || precond->r0 != m->r0 || precond->r1 != m->r1)
+        return set_error(ctx, BEMB200_EINVAL, "preconditioner was built for another operator shape / context");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    BEMB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = check_partition(m);
+    if (rc != BEMB200_OK) return rc;
+    rc = ensure_workspace(m, restart);
+    if (rc != BEMB200_OK) return rc;
+    reset_stats(m);
+    GmresWorkspace* ws = m->ws;
+    const size_t nb = m->n_rows * sizeof(cplx);
+    BEMB_CUDA(ctx, cudaMemcpyAsync(ws->bin, b, nb, cudaMemcpyHostToDevice, ctx->stream));
+    if (x0) BEMB_CUDA(ctx, cudaMemcpyAsync(ws->xout, x0, nb, cudaMemcpyHostToDevice, ctx->stream));
+    else BEMB_CUDA(ctx, cudaMemsetAsync(ws->xout, 0, nb, ctx->stream));
+    rc = gmres_core(m, ws->bin, ws->xout, max_iterations, restart, tolerance, info, true, nullptr, precond);
     if (rc != BEMB200_OK) return rc;
     BEMB_CUDA(ctx, cudaMemcpyAsync(x_out, ws->xout, nb, cudaMemcpyDeviceToHost, ctx->stream));
     BEMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -942,13 +942,20 @@ void orc_gmres_op(orc_apply_fn apply, void* user, uint64_t n, const double* b_in
 // gmres_preconditioned_with_guess(): gmres.rs:434-585 (left preconditioning).  The preconditioner
 // is IdentityPreconditioner (inv_diag == NULL, traits.rs:377-385: r.clone()) or
 // DiagonalPreconditioner (preconditioners/diagonal.rs:60-80: r_i * inv_diag_i).
-static void precond_apply(const double* inv_diag, const cplx* r, cplx* out, uint64_t n) {
+static void bem_oracle_precond_apply(const double* inv_diag, const cplx* r, cplx* out, uint64_t n) {
     const cplx* d = (const cplx*)inv_diag;
     for (uint64_t i = 0; i < n; ++i) out[i] = d ? r[i] * d[i] : r[i];
 }
-void orc_gmres_preconditioned_op(orc_apply_fn apply, void* user, uint64_t n, const double* inv_diag, const double* b_in,
-                                 const double* x0_in, uint32_t max_iterations, uint32_t restart, double tolerance,
-                                 double* x_out, orc_gmres_info* info) {
+// The loop below is gmres_preconditioned_with_guess for any Preconditioner::apply (traits.rs:366-371): `papply`
+// non-NULL is a caller-supplied preconditioner (e.g. the additive Schwarz restatement of oracle/schwarz_oracle.py),
+// otherwise the identity / diagonal one above.
+static void gmres_preconditioned_impl(orc_apply_fn apply, void* user, uint64_t n, const double* inv_diag, orc_apply_fn papply,
+                                      void* puser, const double* b_in, const double* x0_in, uint32_t max_iterations,
+                                      uint32_t restart, double tolerance, double* x_out, orc_gmres_info* info) {
+    auto precond_apply = [&](const double* idg, const cplx* r, cplx* out, uint64_t nn) {
+        if (papply) papply(puser, (const double*)r, (double*)out);
+        else bem_oracle_precond_apply(idg, r, out, nn);
+    };
     const cplx* b = (const cplx*)b_in;
     cplx* x = (cplx*)x_out;
     const int m = (int)restart;
@@ -1032,6 +1039,17 @@ void orc_gmres_preconditioned_op(orc_apply_fn apply, void* user, uint64_t n, con
     precond_apply(inv_diag, residual.data(), r.data(), n);
     double rel = vector_norm(r.data(), n) / b_norm;
     *info = {total_iterations, restarts, rel, 0};
+}
+void orc_gmres_preconditioned_op(orc_apply_fn apply, void* user, uint64_t n, const double* inv_diag, const double* b_in,
+                                 const double* x0_in, uint32_t max_iterations, uint32_t restart, double tolerance,
+                                 double* x_out, orc_gmres_info* info) {
+    gmres_preconditioned_impl(apply, user, n, inv_diag, nullptr, nullptr, b_in, x0_in, max_iterations, restart, tolerance, x_out, info);
+}
+// operator AND preconditioner as callbacks
+void orc_gmres_preconditioned_cb(orc_apply_fn apply, void* user, orc_apply_fn papply, void* puser, uint64_t n, const double* b_in,
+                                 const double* x0_in, uint32_t max_iterations, uint32_t restart, double tolerance,
+                                 double* x_out, orc_gmres_info* info) {
+    gmres_preconditioned_impl(apply, user, n, nullptr, papply, puser, b_in, x0_in, max_iterations, restart, tolerance, x_out, info);
 }
 void orc_gmres_preconditioned(const double* A, uint64_t n, const double* inv_diag, const double* b, const double* x0,
                               uint32_t max_iterations, uint32_t restart, double tolerance, double* x_out,

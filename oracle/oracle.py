@@ -321,6 +321,31 @@ def gmres_preconditioned(A, b, inv_diag=None, x0=None, max_iterations=100, resta
                    converged=bool(info.converged))
 
 
+_APPLY_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p)
+
+
+def gmres_preconditioned_cb(apply, precond_apply, n, b, x0=None, max_iterations=100, restart=30, tolerance=1e-6):
+    """gmres_preconditioned_with_guess (gmres.rs:434-585) with operator AND preconditioner as Python callables
+    (``apply(x) -> A x``, ``precond_apply(r) -> M^-1 r``), e.g. oracle/schwarz_oracle.py's restatement of schwarz.rs."""
+    b = np.ascontiguousarray(b, dtype=np.complex128)
+    x = np.zeros(n, dtype=np.complex128)
+    x0a = np.ascontiguousarray(x0, dtype=np.complex128) if x0 is not None else None
+
+    def _wrap(fn):
+        def _cb(_user, xp, yp):
+            xv = np.ctypeslib.as_array(C.cast(xp, C.POINTER(C.c_double)), shape=(2 * n,)).view(np.complex128)
+            yv = np.ctypeslib.as_array(C.cast(yp, C.POINTER(C.c_double)), shape=(2 * n,)).view(np.complex128)
+            yv[:] = fn(xv.copy())
+        return _APPLY_FN(_cb)
+
+    cb_a, cb_p = _wrap(apply), _wrap(precond_apply)
+    info = GmresInfo()
+    lib().orc_gmres_preconditioned_cb(cb_a, None, cb_p, None, C.c_uint64(n), _p(b), _p(x0a) if x0a is not None else None,
+                                      C.c_uint32(max_iterations), C.c_uint32(restart), C.c_double(tolerance), _p(x), C.byref(info))
+    return x, dict(iterations=int(info.iterations), restarts=int(info.restarts), residual=float(info.residual),
+                   converged=bool(info.converged))
+
+
 def incident_rhs(kind, vec, amplitude, centers, normals, k, beta, tau=1.0):
     """compute_rhs_with_beta for one plane wave (kind=0) or point source (kind=1) -> (rhs, p_inc)."""
     centers = np.ascontiguousarray(centers, dtype=np.float64)
@@ -391,9 +416,6 @@ def l2_relative(analytical, bem) -> float:
     num = np.sqrt((np.abs(a - b) ** 2).sum())
     den = np.sqrt((np.abs(a) ** 2).sum())
     return float(num / den) if den > 1e-15 else float(num)
-
-
-_APPLY_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p)
 
 
 def gmres_op(apply, n, b, x0=None, max_iterations=100, restart=30, tolerance=1e-6):

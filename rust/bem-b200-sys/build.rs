@@ -8,13 +8,14 @@ fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "nvcc".into());
     // (translation unit, extra flags): the decision-taking kernels forbid FMA contraction
-    let units: [(&str, &[&str]); 11] = [
+    let units: [(&str, &[&str]); 12] = [
         ("assembly_exact.cu", &["-fmad=false"]),
         ("assembly_far.cu", &[]),
         ("linalg.cu", &[]),
         ("gmres.cu", &[]),
         ("gmres_fused.cu", &[]),
         ("block_gmres.cu", &[]),
+        ("schwarz.cu", &[]),
         ("postprocess.cu", &["-fmad=false"]),
         ("room.cu", &[]),
         ("direct.cu", &[]),

@@ -10,6 +10,10 @@ use std::os::raw::{c_char, c_double, c_int, c_void};
 #[repr(C)] pub struct bemb200_staged_mesh { _p: [u8; 0] }
 #[repr(C)] pub struct bemb200_matrix { _p: [u8; 0] }
 #[repr(C)] pub struct bemb200_sweep { _p: [u8; 0] }
+#[repr(C)] pub struct bemb200_precond { _p: [u8; 0] }
+#[repr(C)] #[derive(Clone, Copy, Default)]
+pub struct bemb200_precond_stats { pub num_subdomains: u32, pub local_subdomains: u32, pub min_size: u32, pub max_size: u32,
+                                   pub avg_size: f64, pub inverse_bytes: u64, pub factor_ms: f64, pub disjoint: i32 }
 #[repr(C)] pub struct bemb200_multi { _p: [u8; 0] }
 #[repr(C)] pub struct bemb200_multi_matrix { _p: [u8; 0] }
 #[repr(C)] #[derive(Clone, Copy, Default)]
@@ -70,6 +74,15 @@ extern "C" {
                                         max_iterations: u32, restart: u32, tolerance: f64, x_out: *mut f64,
                                         info: *mut bemb200_gmres_info) -> c_int;
     pub fn bemb200_matrix_diagonal(m: *const bemb200_matrix, out: *mut f64) -> c_int;
+    // block-Jacobi / additive Schwarz preconditioner (schwarz.rs) built on the device
+    pub fn bemb200_schwarz_create(m: *const bemb200_matrix, num_subdomains: u32, sub_ptr: *const u64, sub_idx: *const u64,
+                                  out: *mut *mut bemb200_precond) -> c_int;
+    pub fn bemb200_precond_free(p: *mut bemb200_precond);
+    pub fn bemb200_precond_stats_get(p: *const bemb200_precond, out: *mut bemb200_precond_stats) -> c_int;
+    pub fn bemb200_precond_apply(p: *const bemb200_precond, r: *const f64, z: *mut f64) -> c_int;
+    pub fn bemb200_gmres_schwarz(m: *const bemb200_matrix, precond: *const bemb200_precond, b: *const f64, x0: *const f64,
+                                 max_iterations: u32, restart: u32, tolerance: f64, x_out: *mut f64,
+                                 info: *mut bemb200_gmres_info) -> c_int;
     pub fn bemb200_gmres_batched(m: *const bemb200_matrix, b_all: *const f64, nrhs: u32, max_iterations: u32, restart: u32,
                                  tolerance: f64, x_all: *mut f64, infos: *mut bemb200_gmres_info, block_matvec_ms: *mut f64,
                                  block_matvecs: *mut u64) -> c_int;

@@ -66,6 +66,20 @@ for sub, ka in [(3, 1.0), (3, 8.0), (4, 2.0)]:
     # both sides must converge to the same solution, the counts only have to be of the same order
     if not sb.converged or not ib["converged"] or abs(sb.iterations - ib["iterations"]) > 0.25 * ib["iterations"] + 2 or dxb > 1e-7:
         failures.append(f"bicgstab {sb.iterations} vs {ib['iterations']} dx {dxb}")
+    # block-Jacobi (additive Schwarz, overlap 0) on rank-aligned diagonal blocks: every rank inverts and applies its own blocks
+    from oracle import schwarz_oracle as so
+    parts = bem.schwarz_partition_aligned(n, world, 96)
+    pre = bem.AdditiveSchwarzPreconditioner.from_operator(op, subdomains=parts)
+    dsw = so.DenseSchwarz(Ao, subdomains=[q.astype(np.int64) for q in parts])
+    zerr = float(np.linalg.norm(pre.apply(x) - dsw.apply(x)) / np.linalg.norm(dsw.apply(x)))
+    sp = bem.gmres_preconditioned(op, pre, b, bem.GmresConfig(1000, 50, 1e-10))
+    xp, ip = orc.gmres_preconditioned_cb(lambda v: Ao @ v, dsw.apply, n, b, max_iterations=1000, restart=50, tolerance=1e-10)
+    dxp = float(np.linalg.norm(sp.x - xp) / np.linalg.norm(xp))
+    print(f"[rank {rank}]   block-jacobi {len(parts)} blocks: apply_err={zerr:.2e} it={sp.iterations}/{ip['iterations']} "
+          f"(plain {sol.iterations}) dx={dxp:.2e}", flush=True)
+    if zerr > 1e-11 or not sp.converged or sp.iterations != ip["iterations"] or dxp > 1e-8:
+        failures.append(f"block-jacobi apply {zerr} it {sp.iterations} vs {ip['iterations']} dx {dxp}")
+    pre.close()
     if err > 1e-10:
         failures.append(f"entries {err}")
     if apply_err > 1e-12:
