@@ -760,10 +760,11 @@ def run_native(args):
     wl = workload(args.workload)
     mesh = wl["mesh"]
     n = mesh.num_dofs
-    # schedule: with 1-4 GPUs the FP64 assembly of frequency f+1 hides under the HBM-bound solve of f (measured 4-6 %
-    # faster); at 8 GPUs the slabs are small, the solver owns the GPU (whole-GPU Gram-Schmidt kernel, ZGEMV epilogue
-    # storing A v into the peers' memory) and the sequential schedule measured faster
-    overlap = (world < 4) if args.schedule == "auto" else (args.schedule == "pipelined")
+    # schedule: on one GPU the FP64 assembly of frequency f+1 hides under the HBM-bound solve of f (101.0 against 103.9 ms
+    # sequential); from two GPUs on the solver owns the GPU -- the persistent fused GMRES kernel with its sharded
+    # Gram-Schmidt and one peer-memory exchange per iteration -- and assembly and solve run back to back (2 GPUs: 57.3
+    # against 61.7 ms pipelined, profiles/r02e_bench_2gpu*.json)
+    overlap = (world < 2) if args.schedule == "auto" else (args.schedule == "pipelined")
     if args.no_overlap:
         overlap = False
     driver = SweepDriver(mesh, local_rank, rank, world, nccl_id, solve_stream=s_solve.cuda_stream,
@@ -864,7 +865,7 @@ def run_native(args):
     # ---- the same frequencies through the sweep API of the C ABI (bemb200_sweep_*, what a Rust / C caller of a sweep uses): the
     # mesh is staged once by the sweep object, every frequency passes HOST buffers -- physics, the incident right-hand side
     # computed on the host, b H2D inside bemb200_gmres, TbemSystem.rhs and x D2H -- and the library pipelines the assembly of
-    # frequency f + 1 underneath the solve of f (1-2 GPUs) or runs them back to back with the fused solver (4 GPUs on)
+    # frequency f + 1 underneath the solve of f (1 GPU) or runs them back to back with the fused solver (2 GPUs on)
     from math_audio_b200.sweep import Sweep
 
     nid2 = None
@@ -1088,7 +1089,7 @@ def main():
     ap.add_argument("--background", type=int, default=1, help="blocks/SM of the background assembly kernel in the sweep pipeline")
     ap.add_argument("--no-overlap", action="store_true", help="do not overlap assembly(f+1) with solve(f)")
     ap.add_argument("--schedule", choices=["auto", "pipelined", "sequential"], default="auto",
-                    help="auto: pipelined sweep on 1-2 GPUs, sequential (persistent fused solver) from 4 GPUs on")
+                    help="auto: pipelined sweep on 1 GPU, sequential (persistent fused solver) from 2 GPUs on")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3  # timing rule: W >= 3

@@ -348,9 +348,11 @@ static int update_x(bemb200_matrix* m, cplx* x, const std::vector<cplx>& y) {
 
 // ---- persistent fused solve (gmres_fused.cu) ----------------------------------------------------------------
 // BEMB200_GMRES_FUSED: 0 never, 1 whenever the kernel applies, unset = auto: the ranks of a single-process group always;
-// process-per-GPU jobs from 4 ranks on when the solver owns the GPU.  Measured: 8 GPUs 17.6 vs 20.0 ms
-// per frequency, 4 GPUs 33.6 vs 33.8, 2 GPUs 63.6 vs 60.6, 1 GPU 124 vs 118 -- below 4 ranks the hardware-scheduled ZGEMV
-// of the per-iteration path (perfect load balance for free) outweighs the saved launches and the sharded Gram-Schmidt.
+// process-per-GPU jobs from 2 ranks on when the solver owns the GPU.  Measured with the final kernel (DESIGN.md section 4.4,
+// s/frequency of the config-2 sweep, sequential schedule): 2 GPUs 57.3 ms fused against 61.7 ms for the pipelined per-iteration
+// path; 1 GPU 110.3 fused against 103.9 sequential / 101.0 pipelined per-iteration -- on one GPU the hardware-scheduled ZGEMV
+// (perfect load balance for free) outweighs the saved launches, from two ranks on the sharded Gram-Schmidt and the single
+// exchange per iteration win.
 static const int g_fused_mode = []() { const char* v = std::getenv("BEMB200_GMRES_FUSED"); return v ? (std::atoi(v) != 0 ? 1 : 0) : -1; }();
 static double g_fused_total_ms = 0.0, g_fused_matvec_ms = 0.0, g_fused_round_ms = 0.0;
 static unsigned long long g_fused_rounds = 0;
@@ -474,7 +476,7 @@ static int gmres_fused_solve(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t
     GmresWorkspace* ws = m->ws;
     if (g_fused_mode == 0 || ctx->fx.disabled || restart > (uint32_t)FUSED_MAX_RESTART || m->n_rows > 0x7fffffffull) return BEMB200_OK;
     const bool polite = ctx->shared_gpu.load() != 0;  // a background assembly shares the SMs: 96-register build
-    if (g_fused_mode < 0 && !ctx->group && (ctx->nranks < 4 || polite)) return BEMB200_OK;
+    if (g_fused_mode < 0 && !ctx->group && (ctx->nranks < 2 || polite)) return BEMB200_OK;
     if (ctx->nranks > 1 && !ctx->group && !ctx->nccl_comm) return BEMB200_OK;
     if (ctx->nranks > MAX_PEERS) return BEMB200_OK;
     bool ok = false;
