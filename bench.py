@@ -561,7 +561,8 @@ def run_config5(ctx, dev):
     block = {"workload": "sphere20k_rhs32", "description": "rigid icosphere(5), 20480 Tri3, ka = 2, 32 plane-wave directions, batched GMRES(50) tol 1e-10",
              "n_elements": int(n), "nrhs": nrhs, "s_per_batch": t_batched, "s_per_rhs": t_batched / nrhs,
              "single_rhs_solve_s": t_single, "speedup_vs_sequential_solves": t_single * nrhs / t_batched,
-             "block_matvec": {"kernel": "zgemm_block_kernel (mma.sync m8n8k4 f64)", "ms": kms, "tflops": flops / (kms * 1e-3) / 1e12,
+             "block_matvec": {"kernel": ("zgemm_block_kernel (round-1 kernel, mma.sync m8n8k4 f64 from global fragments)" if os.environ.get("BEMB200_BLOCK_MATVEC") == "legacy"
+                                         else "zgemm_streamk_kernel (DMMA.8x8x4 from swizzled shared-memory tiles, cp.async ring, stream-K over 148 CTAs) + block_fixup_kernel"), "ms": kms, "tflops": flops / (kms * 1e-3) / 1e12,
                               "frac_of_nominal_fp64": flops / (kms * 1e-3) / 1e12 / fp64_nominal, "launches": int(st.get("block_matvecs", 0)),
                               "algorithmic_flop_per_launch": flops, "bytes_per_launch": 16.0 * n * n + 32.0 * n * nrhs},
              "iterations": [so.iterations for so in sols], "all_converged": all(so.converged for so in sols),

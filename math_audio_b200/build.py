@@ -31,6 +31,7 @@ UNITS = {
     "gmres_fused.cu": [],
     "block_gmres.cu": [],
     "schwarz.cu": [],
+    "block_matvec.cu": [],
     "postprocess.cu": ["-fmad=false"],
     "room.cu": [],
     "direct.cu": [],

@@ -14,6 +14,8 @@
 #include <atomic>
 #include <cstdlib>
 
+#include <string>
+
 #include "linalg.h"
 
 namespace cg = cooperative_groups;
@@ -1595,6 +1597,8 @@ cudaError_t launch_cgs_p(const cplx* r, const cplx* q, cplx beta, cplx* u, cplx*
 cudaError_t launch_zgemm_block(const cplx* A, uint64_t lda, uint64_t nrows, uint64_t ncols, const cplx* X, cplx* Y, int nrhs,
                                cudaStream_t s) {
     if (nrows == 0) return cudaSuccess;
+    static const bool use_dmma = []() { const char* v = std::getenv("BEMB200_BLOCK_MATVEC"); return v && std::string(v) == "legacy"; }();
+    if (!use_dmma) return launch_zgemm_block_streamk(A, lda, nrows, ncols, X, Y, nrhs, s);
     const unsigned blocks = (unsigned)((nrows + BM_ROWS - 1) / BM_ROWS);
     switch (nrhs) {
         case 8: zgemm_block_kernel<1><<<blocks, BM_WARPS * 32, 0, s>>>(A, lda, nrows, ncols, X, Y); break;

@@ -45,6 +45,10 @@ cudaError_t launch_cgs_update(cplx* x, const cplx* uq, const cplx* w, cplx* r, c
 cudaError_t launch_cgs_p(const cplx* r, const cplx* q, cplx beta, cplx* u, cplx* p, uint64_t n, cudaStream_t s);
 cudaError_t launch_zgemm_block(const cplx* A, uint64_t lda, uint64_t nrows, uint64_t ncols, const cplx* X, cplx* Y, int nrhs,
                                cudaStream_t s);
+// block_matvec.cu: DMMA.8x8x4 kernel with shared-memory staging and a stream-K decomposition (the default behind
+// launch_zgemm_block; BEMB200_BLOCK_MATVEC=legacy selects the round-1 kernel of linalg.cu)
+cudaError_t launch_zgemm_block_streamk(const cplx* A, uint64_t lda, uint64_t nrows, uint64_t ncols, const cplx* X, cplx* Y, int nrhs,
+                                       cudaStream_t s);
 cudaError_t launch_mgs_batched(int nrhs, const cplx* Vall, uint64_t ldv, uint64_t vstride, const cplx* Yblk, int j, uint64_t n,
                                cplx* hcol_all, uint64_t hstride, cplx* Xblk, const unsigned char* active, cudaStream_t s);
 cudaError_t launch_block_residual(const cplx* B, const cplx* AX, cplx* R, uint64_t n, int nrhs, double* out, cudaStream_t s);

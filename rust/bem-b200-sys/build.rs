@@ -8,7 +8,7 @@ fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "nvcc".into());
     // (translation unit, extra flags): the decision-taking kernels forbid FMA contraction
-    let units: [(&str, &[&str]); 12] = [
+    let units: [(&str, &[&str]); 13] = [
         ("assembly_exact.cu", &["-fmad=false"]),
         ("assembly_far.cu", &[]),
         ("linalg.cu", &[]),
@@ -16,6 +16,7 @@ fn main() {
         ("gmres_fused.cu", &[]),
         ("block_gmres.cu", &[]),
         ("schwarz.cu", &[]),
+        ("block_matvec.cu", &[]),
         ("postprocess.cu", &["-fmad=false"]),
         ("room.cu", &[]),
         ("direct.cu", &[]),
