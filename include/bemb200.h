@@ -250,7 +250,8 @@ int bemb200_gmres_batched(const bemb200_matrix* m, const double* b_all, uint32_t
                           uint32_t restart, double tolerance, double* x_all, bemb200_gmres_info* infos,
                           double* block_matvec_ms, uint64_t* block_matvecs);
 /* Y = A X for nrhs (<= 32) vectors at once with the tensor-core block kernel; kernel_ms (may be
- * NULL) receives the device time of one block matvec */
+ * NULL) receives the device time of one block matvec.  Row-sharded operators: collective, every rank multiplies its row
+ * block and receives the whole Y.  (bemb200_gmres_batched: up to 196 608 unknowns, also row-sharded.) */
 int bemb200_apply_block(const bemb200_matrix* m, const double* x_all, uint32_t nrhs, double* y_all, double* kernel_ms);
 /* number of kernels launched and device milliseconds spent inside the zgemv kernel by
  * the last bemb200_gmres* / bemb200_apply* call on this matrix */

@@ -78,7 +78,7 @@ extern "C" int bemb200_gmres_batched(const bemb200_matrix* cm, const double* b_a
     if (m->n_rows != m->n_cols) return set_error(ctx, BEMB200_EINVAL, "gmres needs a square operator");
     if (restart == 0 || nrhs == 0 || nrhs > 32) return set_error(ctx, BEMB200_EINVAL, "need 1 <= nrhs <= 32 and restart >= 1");
     const uint64_t n = m->n_rows;
-    if (n > 32768) return set_error(ctx, BEMB200_EUNSUPPORTED, "batched GMRES supports up to 32768 unknowns in this version");
+    if (n > 196608) return set_error(ctx, BEMB200_EUNSUPPORTED, "batched GMRES supports up to 196608 unknowns in this version");
     {
         uint64_t b = 0, e = 0;
         bemb200_partition(n, ctx->nranks, ctx->rank, &b, &e);
@@ -314,17 +314,21 @@ extern "C" int bemb200_apply_block(const bemb200_matrix* cm, const double* x_all
     if (!m || !x_all || !y_all) return set_error(nullptr, BEMB200_EINVAL, "NULL argument");
     bemb200_ctx* ctx = m->ctx;
     if (nrhs == 0 || nrhs > 32) return set_error(ctx, BEMB200_EINVAL, "need 1 <= nrhs <= 32");
-    if (ctx->nranks > 1) return set_error(ctx, BEMB200_EUNSUPPORTED, "apply_block on a row-sharded matrix: use gmres_batched");
+    {
+        uint64_t b = 0, e = 0;  // row-sharded operator: every rank multiplies its canonical row block, the slabs are gathered
+        bemb200_partition(m->n_rows, ctx->nranks, ctx->rank, &b, &e);
+        if (m->r0 != b || m->r1 != e) return set_error(ctx, BEMB200_EINVAL, "apply_block needs the whole operator (every rank its canonical row block)");
+    }
     std::lock_guard<std::mutex> lk(ctx->mu);
     BEMB_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     const int S = (int)((nrhs + 7) / 8 * 8);
     const uint64_t nc = m->n_cols, nr = m->n_rows, nloc = m->r1 - m->r0;
-    if (m->r0 != 0 || m->r1 != nr) return set_error(ctx, BEMB200_EINVAL, "apply_block needs the whole operator on this device");
+    const uint64_t chunk = (nr + ctx->nranks - 1) / ctx->nranks, npad = chunk * ctx->nranks;
     DevBuf buf;
     cplx *Xb, *Yb, *stage;
     BEMB_CUDA(ctx, buf.alloc(&Xb, nc * S));
-    BEMB_CUDA(ctx, buf.alloc(&Yb, nr * S));
+    BEMB_CUDA(ctx, buf.alloc(&Yb, npad * S));
     BEMB_CUDA(ctx, buf.alloc(&stage, (size_t)nrhs * (nc > nr ? nc : nr)));
     struct EvGuard { cudaEvent_t a = nullptr, b = nullptr; ~EvGuard() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); } } evg;
     BEMB_CUDA(ctx, cudaEventCreate(&evg.a));
@@ -332,10 +336,15 @@ extern "C" int bemb200_apply_block(const bemb200_matrix* cm, const double* x_all
     const cudaEvent_t e0 = evg.a, e1 = evg.b;
     BEMB_CUDA(ctx, cudaMemcpyAsync(stage, x_all, (size_t)nrhs * nc * sizeof(cplx), cudaMemcpyHostToDevice, s));
     BEMB_CUDA(ctx, launch_interleave(stage, Xb, nc, (int)nrhs, S, 1, s));
-    BEMB_CUDA(ctx, launch_zgemm_block(m->A, nc, nloc, nc, Xb, Yb, S, s));  // warm-up
+    cplx* yloc = Yb + m->r0 * S;  // r0 = rank * chunk
+    BEMB_CUDA(ctx, launch_zgemm_block(m->A, nc, nloc, nc, Xb, yloc, S, s));  // warm-up
     BEMB_CUDA(ctx, cudaEventRecord(e0, s));
-    BEMB_CUDA(ctx, launch_zgemm_block(m->A, nc, nloc, nc, Xb, Yb, S, s));
+    BEMB_CUDA(ctx, launch_zgemm_block(m->A, nc, nloc, nc, Xb, yloc, S, s));
     BEMB_CUDA(ctx, cudaEventRecord(e1, s));
+    if (ctx->nranks > 1) {
+        int rc = nccl_allgather_bytes(ctx, yloc, Yb, chunk * S * sizeof(cplx));
+        if (rc != BEMB200_OK) return rc;
+    }
     BEMB_CUDA(ctx, launch_interleave(Yb, stage, nr, (int)nrhs, S, 0, s));
     BEMB_CUDA(ctx, cudaMemcpyAsync(y_all, stage, (size_t)nrhs * nr * sizeof(cplx), cudaMemcpyDeviceToHost, s));
     BEMB_CUDA(ctx, cudaStreamSynchronize(s));

@@ -1122,6 +1122,68 @@ mgs_batched_kernel(const cplx* __restrict__ Vall, uint64_t ldv, uint64_t vstride
     cluster.sync();
 }
 
+// Same step for slices that do not fit the registers (n > 32 768): the CTA keeps its slice of w in SHARED memory (up to
+// 12 288 complex numbers = 192 KB per CTA, 16 CTAs per cluster => n <= 196 608) and streams the basis vectors through
+// registers; every thread owns the same elements k = tid + 256 e in all passes, so no block barrier is needed between
+// them, and the summation order per thread equals the register variant's.
+__global__ void __launch_bounds__(256)
+mgs_batched_smem_kernel(const cplx* __restrict__ Vall, uint64_t ldv, uint64_t vstride, const cplx* __restrict__ Yblk, int S_rhs,
+                        int j, uint64_t n, uint64_t S, cplx* __restrict__ hcol_all, uint64_t hstride, cplx* __restrict__ Xblk,
+                        double breakdown_tol, const unsigned char* __restrict__ active) {
+    extern __shared__ __align__(16) unsigned char mgs_smem_raw[];
+    cplx* w_s = reinterpret_cast<cplx*>(mgs_smem_raw);
+    __shared__ ClusterShared sh;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned me = cluster.block_rank();
+    const int rhs = blockIdx.y;
+    if (active && !active[rhs]) return;  // whole cluster leaves together
+    const cplx* V = Vall + (uint64_t)rhs * vstride;
+    cplx* hcol = hcol_all + (uint64_t)rhs * hstride;
+    const uint64_t begin = (uint64_t)me * S;
+    const uint64_t end = begin + S < n ? begin + S : n;
+    const uint64_t len = end > begin ? end - begin : 0;
+    for (uint64_t k = threadIdx.x; k < len; k += 256) w_s[k] = ldg_c(Yblk + (begin + k) * S_rhs + rhs);
+    int parity = 0;
+    for (int i = 0; i <= j; ++i) {
+        const cplx* vi = V + (uint64_t)i * ldv + begin;
+        cplx acc = C(0, 0);
+        for (uint64_t k = threadIdx.x; k < len; k += 256) {
+            const cplx v = ldg_c(vi + k), w = w_s[k];
+            acc.re = fma(v.re, w.re, fma(v.im, w.im, acc.re));
+            acc.im = fma(v.re, w.im, fma(-v.im, w.re, acc.im));
+        }
+        const cplx h = cluster_allreduce(acc, sh, parity);
+        parity ^= 1;
+        if (me == 0 && threadIdx.x == 0) hcol[i] = h;
+        for (uint64_t k = threadIdx.x; k < len; k += 256) {
+            const cplx v = ldg_c(vi + k);
+            cplx w = w_s[k];
+            w.re = fma(-h.re, v.re, fma(h.im, v.im, w.re));
+            w.im = fma(-h.re, v.im, fma(-h.im, v.re, w.im));
+            w_s[k] = w;
+        }
+    }
+    cplx acc = C(0, 0);
+    for (uint64_t k = threadIdx.x; k < len; k += 256) {
+        const cplx w = w_s[k];
+        acc.re = fma(w.re, w.re, fma(w.im, w.im, acc.re));
+    }
+    const cplx nn = cluster_allreduce(acc, sh, parity);
+    const double nrm = sqrt(nn.re);
+    if (me == 0 && threadIdx.x == 0) hcol[j + 1] = C(nrm, 0.0);
+    if (!(nrm < breakdown_tol)) {
+        const double sc = 1.0 / nrm - 1.0;
+        cplx* vnext = const_cast<cplx*>(V) + (uint64_t)(j + 1) * ldv;
+        for (uint64_t k = threadIdx.x; k < len; k += 256) {
+            const cplx w = w_s[k];
+            const cplx v = C(w.re + w.re * sc, w.im + w.im * sc);
+            vnext[begin + k] = v;
+            Xblk[(begin + k) * S_rhs + rhs] = v;
+        }
+    }
+    cluster.sync();
+}
+
 // per-RHS residual of a block: R[:, s] = B[:, s] - AX[:, s] (interleaved [n][S]); out[s] = sum |R[:, s]|^2.
 // One block per RHS (deterministic block reduction).
 __global__ void __launch_bounds__(1024)
@@ -1638,7 +1700,34 @@ static cudaError_t launch_mgs_batched_t(int cl, int nrhs, const cplx* Vall, uint
 
 cudaError_t launch_mgs_batched(int nrhs, const cplx* Vall, uint64_t ldv, uint64_t vstride, const cplx* Yblk, int j, uint64_t n,
                                cplx* hcol_all, uint64_t hstride, cplx* Xblk, const unsigned char* active, cudaStream_t s) {
-    if (n > 16ull * 256ull * 8ull) return cudaErrorInvalidValue;  // register-resident variant only (n <= 32768)
+    if (n > 16ull * 256ull * 8ull) {  // slices beyond the register-resident variant: w in shared memory
+        constexpr uint64_t SMEM_ELEMS = 12288;  // 192 KB per CTA
+        const int clb = 16;
+        const uint64_t Sb = (n + clb - 1) / clb;
+        if (Sb > SMEM_ELEMS) return cudaErrorInvalidValue;  // n > 196 608
+        static PerDeviceFlag attr_done_b;
+        if (!attr_done_b.get()) {
+            cudaError_t e = cudaFuncSetAttribute(mgs_batched_smem_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(mgs_batched_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_ELEMS * sizeof(cplx)));
+            if (e != cudaSuccess) return e;
+            attr_done_b.set();
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(clb, nrhs, 1);
+        cfg.blockDim = dim3(256, 1, 1);
+        cfg.dynamicSmemBytes = Sb * sizeof(cplx);
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = clb;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, mgs_batched_smem_kernel, Vall, ldv, vstride, Yblk, nrhs, j, n, Sb, hcol_all, hstride, Xblk, 1e-14,
+                                  active);
+    }
     const int cl = n >= 2048 ? 16 : (n >= 512 ? 4 : 1);
     const uint64_t S = (n + cl - 1) / cl;
     const uint64_t ept = (S + 255) / 256;

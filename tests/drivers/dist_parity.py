@@ -80,6 +80,19 @@ for sub, ka in [(3, 1.0), (3, 8.0), (4, 2.0)]:
     if zerr > 1e-11 or not sp.converged or sp.iterations != ip["iterations"] or dxp > 1e-8:
         failures.append(f"block-jacobi apply {zerr} it {sp.iterations} vs {ip['iterations']} dx {dxp}")
     pre.close()
+    # several right-hand sides in lockstep on the row-sharded operator (block matvec per rank + all-gather of the block)
+    Bm = np.stack([b, b[::-1].copy(), 1j * b])
+    sb3, _st = bem.gmres_batched(op, Bm, bem.GmresConfig(1000, 50, 1e-10))
+    Yb, _ms = bem.apply_block(op, Bm)
+    berr = float(np.linalg.norm(Yb - Bm @ Ao.T) / np.linalg.norm(Bm @ Ao.T))
+    for i3, s3 in enumerate(sb3):
+        x3, i3o = orc.gmres(Ao, Bm[i3], max_iterations=1000, restart=50, tolerance=1e-10)
+        d3 = float(np.linalg.norm(s3.x - x3) / np.linalg.norm(x3))
+        if not s3.converged or s3.iterations != i3o["iterations"] or d3 > 1e-8:
+            failures.append(f"batched rhs {i3}: it {s3.iterations} vs {i3o['iterations']} dx {d3}")
+    print(f"[rank {rank}]   batched 3 rhs: it={[s3.iterations for s3 in sb3]} apply_block err={berr:.2e}", flush=True)
+    if berr > 1e-12:
+        failures.append(f"apply_block {berr}")
     if err > 1e-10:
         failures.append(f"entries {err}")
     if apply_err > 1e-12:

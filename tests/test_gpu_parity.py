@@ -726,6 +726,36 @@ def test_block_matvec_and_batched_gmres(bem, orc):
         assert abs(sol.residual - np.linalg.norm(B[i] - A @ sol.x) / np.linalg.norm(B[i])) < 1e-10
 
 
+def test_batched_gmres_beyond_32768_unknowns(bem):
+    """33 620 unknowns (geodesic sphere, nu = 41): the batched Gram-Schmidt step keeps its slice of w in shared memory
+    instead of registers.  No oracle at this size: the batched solve must reproduce independent single-right-hand-side
+    device solves (which the oracle pins at small sizes) -- iteration / restart counts, solutions, true residuals."""
+    from math_audio_b200.incident import IncidentField
+    from math_audio_b200.mesh import fibonacci_directions, generate_geodesic_sphere_mesh
+
+    a = 0.1
+    mesh = generate_geodesic_sphere_mesh(a, 41)
+    n = mesh.num_dofs
+    assert n == 33620
+    ph = PhysicsParams.from_wave_number(3.0 / a)
+    beta, _ = ph.burton_miller_beta_adaptive(a)
+    system = bem.build_tbem_system_with_beta(mesh, ph, beta, fetch_rhs=False)
+    op = bem.DenseOperator(system)
+    cfg = bem.GmresConfig(max_iterations=1000, restart=30, tolerance=1e-10)
+    B = np.stack([IncidentField.plane_wave(d).compute_rhs_with_beta(mesh.center, mesh.normal, ph, beta) for d in fibonacci_directions(5)])
+    sols, st = bem.gmres_batched(op, B, cfg)
+    assert st["block_matvecs"] > 0
+    X = np.stack([s.x for s in sols])
+    R, _ = bem.apply_block(op, X)
+    for i, sol in enumerate(sols):
+        single = bem.gmres(op, B[i], cfg)
+        assert sol.converged and single.converged
+        assert (sol.iterations, sol.restarts) == (single.iterations, single.restarts) and sol.restarts >= 1
+        assert np.linalg.norm(sol.x - single.x) / np.linalg.norm(single.x) < 1e-9
+        assert np.linalg.norm(B[i] - R[i]) / np.linalg.norm(B[i]) < 2e-10
+    system.matrix.close()
+
+
 # ---- full benchmark size: size-independent properties ---------------------------------------------
 @pytest.fixture(scope="module")
 def big(bem):
