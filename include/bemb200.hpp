@@ -9,6 +9,7 @@
 //   math-bem/src/core/solver/fmm_interface.rs:25-52,378-384  DenseOperator, solve_gmres
 //   math-solvers/src/traits.rs:316-385           LinearOperator, IdentityPreconditioner
 //   math-solvers/src/preconditioners/diagonal.rs DiagonalPreconditioner
+//   math-solvers/src/preconditioners/schwarz.rs  AdditiveSchwarzPreconditioner (built on the device from the operator)
 //   math-solvers/src/iterative/gmres.rs:16-585   GmresConfig, GmresSolution, gmres, gmres_with_guess,
 //                                                gmres_preconditioned{,_with_guess}
 //   math-solvers/src/iterative/bicgstab.rs:19-215  BiCgstabConfig, BiCgstabSolution, bicgstab
@@ -392,6 +393,69 @@ inline GmresSolution gmres_preconditioned_with_guess(const DenseOperator& op, co
                                                      const std::vector<Complex64>& b, const std::vector<Complex64>* x0,
                                                      const GmresConfig& config) {  // gmres.rs:434
     return gmres_preconditioned_impl(op, &p.inv_diag, b, x0, config);
+}
+
+// AdditiveSchwarzPreconditioner (math-solvers/src/preconditioners/schwarz.rs:31-417) built on the device from the assembled
+// operator: from_csr(matrix, num_subdomains, overlap = 0) = block-Jacobi on the contiguous diagonal blocks, or explicit
+// subdomains (global DOF indices; overlapping sets get the reference's weights).
+class AdditiveSchwarzPreconditioner {
+public:
+    static AdditiveSchwarzPreconditioner from_operator(const DenseOperator& op, std::size_t num_subdomains) {  // schwarz.rs:66
+        AdditiveSchwarzPreconditioner p(op);
+        check(bemb200_schwarz_create(op.handle(), static_cast<uint32_t>(num_subdomains), nullptr, nullptr, &p.h_), op.context().handle());
+        return p;
+    }
+    static AdditiveSchwarzPreconditioner from_subdomains(const DenseOperator& op, const std::vector<std::vector<uint64_t>>& subdomains) {
+        AdditiveSchwarzPreconditioner p(op);
+        std::vector<uint64_t> ptr(1, 0), idx;
+        for (const auto& sd : subdomains) {
+            idx.insert(idx.end(), sd.begin(), sd.end());
+            ptr.push_back(idx.size());
+        }
+        check(bemb200_schwarz_create(op.handle(), static_cast<uint32_t>(subdomains.size()), ptr.data(), idx.empty() ? ptr.data() : idx.data(),
+                                     &p.h_), op.context().handle());
+        return p;
+    }
+    AdditiveSchwarzPreconditioner(AdditiveSchwarzPreconditioner&& o) noexcept : op_(o.op_), h_(o.h_) { o.h_ = nullptr; }
+    AdditiveSchwarzPreconditioner(const AdditiveSchwarzPreconditioner&) = delete;
+    AdditiveSchwarzPreconditioner& operator=(const AdditiveSchwarzPreconditioner&) = delete;
+    ~AdditiveSchwarzPreconditioner() { if (h_) bemb200_precond_free(h_); }
+    std::vector<Complex64> apply(const std::vector<Complex64>& r) const {  // Preconditioner::apply (traits.rs:366-371)
+        if (r.size() != op_->num_rows()) throw std::invalid_argument("preconditioner: vector lengths must match");
+        std::vector<Complex64> z(r.size());
+        check(bemb200_precond_apply(h_, reinterpret_cast<const double*>(r.data()), reinterpret_cast<double*>(z.data())), op_->context().handle());
+        return z;
+    }
+    bemb200_precond_stats stats() const {  // schwarz.rs:135-158
+        bemb200_precond_stats st{};
+        check(bemb200_precond_stats_get(h_, &st), op_->context().handle());
+        return st;
+    }
+    const bemb200_precond* handle() const { return h_; }
+
+private:
+    explicit AdditiveSchwarzPreconditioner(const DenseOperator& op) : op_(&op) {}
+    const DenseOperator* op_;
+    bemb200_precond* h_ = nullptr;
+};
+inline GmresSolution gmres_preconditioned_with_guess(const DenseOperator& op, const AdditiveSchwarzPreconditioner& p,
+                                                     const std::vector<Complex64>& b, const std::vector<Complex64>* x0,
+                                                     const GmresConfig& config) {  // gmres.rs:434
+    if (b.size() != op.num_rows() || (x0 && x0->size() != b.size()))
+        throw std::invalid_argument("gmres_preconditioned: vector lengths must match");
+    GmresSolution s;
+    s.x.resize(b.size());
+    bemb200_gmres_info info{};
+    check(bemb200_gmres_schwarz(op.handle(), p.handle(), reinterpret_cast<const double*>(b.data()),
+                                x0 ? reinterpret_cast<const double*>(x0->data()) : nullptr, static_cast<uint32_t>(config.max_iterations),
+                                static_cast<uint32_t>(config.restart), config.tolerance, reinterpret_cast<double*>(s.x.data()), &info),
+          op.context().handle());
+    s.iterations = info.iterations; s.restarts = info.restarts; s.residual = info.residual; s.converged = info.converged != 0;
+    return s;
+}
+inline GmresSolution gmres_preconditioned(const DenseOperator& op, const AdditiveSchwarzPreconditioner& p, const std::vector<Complex64>& b,
+                                          const GmresConfig& config) {  // gmres.rs:282
+    return gmres_preconditioned_with_guess(op, p, b, nullptr, config);
 }
 
 // ---- BiCGSTAB / LU (the solvers of BemSolver::solve_dense_system, bem_solver.rs:435-463) ---------------------
