@@ -530,6 +530,31 @@ def run_precond_config2(ctx, dev):
     return out
 
 
+def run_precond_sweep(mesh, cases, b_extra, cfg, e2e_plain_s, background):
+    """The headline frequencies once more through the C sweep API (host buffers) with bemb200_sweep_set_block_jacobi: every
+    frequency is solved by gmres_preconditioned + block-Jacobi (320 blocks of 64 DOFs) rebuilt from its own matrix."""
+    from math_audio_b200.sweep import Sweep
+
+    # with the solve halved the pipelined schedule is bound by its polite one-block-per-SM background assembly (measured
+    # 100.5 ms per frequency): assembly at full speed and the solve back to back is the faster schedule here
+    mode = os.environ.get("BENCH_PC_SWEEP", "sequential")
+    overlap = mode != "sequential"
+    if mode.startswith("bg"):
+        background = int(mode[2:])
+    sw = Sweep(mesh, 0, 0, 1, None, overlap=overlap, background_blocks_per_sm=background)
+    sw.set_block_jacobi(mesh.num_dofs // 64)
+    jobs = [(ph, beta, b_extra(ph, beta)) for ph, beta in cases]
+    sw.solve_all(jobs[:2], cfg)  # untimed: buffers, workspaces
+    t0 = time.perf_counter()
+    got = sw.solve_all(jobs, cfg)
+    dt = (time.perf_counter() - t0) / len(jobs)
+    sw.close()
+    return {"s_per_frequency_e2e": dt, "plain_s_per_frequency_e2e": e2e_plain_s, "iterations": [g[0].iterations for g in got],
+            "all_converged": all(g[0].converged for g in got), "max_preconditioned_residual": max(g[0].residual for g in got),
+            "schedule": ("bemb200_sweep_* with host buffers, " + ("assembly of f+1 underneath the preconditioned solve of f"
+                                                                   if overlap else "assembly and preconditioned solve back to back"))}
+
+
 def run_config5(ctx, dev):
     """BASELINE.json configs[4] inside the driver-run bench (one GPU): icosphere(5), ka = 2, adaptive beta, 32 plane-wave
     directions on the Fibonacci sphere; ONE batched GMRES(50, 1e-10) over the FP64 tensor-core block matvec (reference
@@ -945,6 +970,8 @@ def run_native(args):
     if world == 1 and not os.environ.get("BENCH_NO_BLOCK_JACOBI") and not os.environ.get("BENCH_NO_CONFIG5"):
         try:
             precond = run_precond_config2(ctx, dev)
+            precond["sweep"] = run_precond_sweep(mesh, e2e_cases, lambda ph, beta: inc.compute_rhs_with_beta(mesh.center, mesh.normal, ph, beta),
+                                                 cfg, float(e2e_s.item()), args.background)
         except Exception as e:
             precond = {"error": f"{type(e).__name__}: {e}"}
     # ---- the Quad4 cabinet (config 3) rides along at 2 and 4 GPUs (the sizes BASELINE.json quotes it on)

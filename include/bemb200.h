@@ -334,6 +334,10 @@ int bemb200_sweep_submit(bemb200_sweep* sw, const bemb200_physics* phys, double 
 /* x_out: num_dofs complex128 (host); stats and rhs_out (the b that was solved) may be NULL */
 int bemb200_sweep_next(bemb200_sweep* sw, double* x_out, bemb200_gmres_info* info, bemb200_assembly_stats* stats, double* rhs_out);
 uint64_t bemb200_sweep_boosts(const bemb200_sweep* sw);
+/* Solve every frequency returned from now on with gmres_preconditioned (gmres.rs:282) and the block-Jacobi / additive Schwarz
+ * preconditioner of bemb200_schwarz_create, rebuilt from each frequency's matrix (arguments as there; num_subdomains = 0
+ * switches back to plain gmres).  The subdomains are copied. */
+int bemb200_sweep_set_block_jacobi(bemb200_sweep* sw, uint32_t num_subdomains, const uint64_t* sub_ptr, const uint64_t* sub_idx);
 void bemb200_sweep_destroy(bemb200_sweep* sw);
 
 /* ---- one process, several devices (SURVEY 8b "Threading": every reference caller -- BemSolver::solve, qa_suite -- is one

@@ -128,6 +128,7 @@ SYMBOLS = {
     "bemb200_sweep_submit": (C.c_int, [_VP, C.POINTER(CPhysics), C.c_double, C.c_double, _VP, C.c_uint32, C.c_uint32, C.c_double]),
     "bemb200_sweep_next": (C.c_int, [_VP, _VP, C.POINTER(CGmresInfo), C.POINTER(CAssemblyStats), _VP]),
     "bemb200_sweep_boosts": (C.c_uint64, [_VP]),
+    "bemb200_sweep_set_block_jacobi": (C.c_int, [_VP, C.c_uint32, _VP, _VP]),
     "bemb200_sweep_destroy": (None, [_VP]),
     "bemb200_multi_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, _PP]),
     "bemb200_multi_destroy": (None, [_VP]),

@@ -54,6 +54,11 @@ struct bemb200_sweep {
     bool stop = false;
     uint64_t submitted = 0, boosts = 0;
     std::string err;
+    // optional block-Jacobi / additive Schwarz preconditioner of every solve (bemb200_sweep_set_block_jacobi)
+    bool precond = false;
+    uint32_t pc_subdomains = 0;
+    std::vector<uint64_t> pc_ptr, pc_idx;
+    double pc_setup_ms = 0.0;  // device time of the last preconditioner set-up
 };
 
 static void sweep_worker(bemb200_sweep* sw) {
@@ -176,7 +181,25 @@ int bemb200_sweep_next(bemb200_sweep* sw, double* x_out, bemb200_gmres_info* inf
         if (!job->rhs_extra.empty())
             for (size_t i = 0; i < b.size(); ++i) b[i] += job->rhs_extra[i];
         if (rhs_out) std::memcpy(rhs_out, b.data(), b.size() * sizeof(double));
-        rc = bemb200_gmres(m, b.data(), nullptr, job->max_iterations, job->restart, job->tolerance, x_out, info);
+        bool use_pc;
+        uint32_t nsub;
+        std::vector<uint64_t> pptr, pidx;
+        {
+            std::lock_guard<std::mutex> lk(sw->mu);
+            use_pc = sw->precond; nsub = sw->pc_subdomains; pptr = sw->pc_ptr; pidx = sw->pc_idx;
+        }
+        if (!use_pc) {
+            rc = bemb200_gmres(m, b.data(), nullptr, job->max_iterations, job->restart, job->tolerance, x_out, info);
+        } else {  // gmres_preconditioned with the block-Jacobi preconditioner of THIS frequency's matrix
+            bemb200_precond* pc = nullptr;
+            rc = bemb200_schwarz_create(m, nsub, pptr.empty() ? nullptr : pptr.data(), pptr.empty() ? nullptr : pidx.data(), &pc);
+            if (rc == BEMB200_OK) {
+                bemb200_precond_stats st{};
+                if (bemb200_precond_stats_get(pc, &st) == BEMB200_OK) sw->pc_setup_ms = st.factor_ms;
+                rc = bemb200_gmres_schwarz(m, pc, b.data(), nullptr, job->max_iterations, job->restart, job->tolerance, x_out, info);
+            }
+            bemb200_precond_free(pc);
+        }
     }
     bool boost = false;
     {
@@ -202,6 +225,20 @@ int bemb200_sweep_next(bemb200_sweep* sw, double* x_out, bemb200_gmres_info* inf
 }
 
 uint64_t bemb200_sweep_boosts(const bemb200_sweep* sw) { return sw ? sw->boosts : 0; }
+
+int bemb200_sweep_set_block_jacobi(bemb200_sweep* sw, uint32_t num_subdomains, const uint64_t* sub_ptr, const uint64_t* sub_idx) {
+    if (!sw) return set_error(nullptr, BEMB200_EINVAL, "NULL argument");
+    if ((sub_ptr == nullptr) != (sub_idx == nullptr)) return set_error(sw->ctx_solve, BEMB200_EINVAL, "sub_ptr and sub_idx go together");
+    std::lock_guard<std::mutex> lk(sw->mu);
+    sw->precond = num_subdomains > 0;
+    sw->pc_subdomains = num_subdomains;
+    sw->pc_ptr.clear(); sw->pc_idx.clear();
+    if (sw->precond && sub_ptr) {
+        sw->pc_ptr.assign(sub_ptr, sub_ptr + num_subdomains + 1);
+        sw->pc_idx.assign(sub_idx, sub_idx + sub_ptr[num_subdomains]);
+    }
+    return BEMB200_OK;
+}
 
 void bemb200_sweep_destroy(bemb200_sweep* sw) {
     if (!sw) return;

@@ -83,6 +83,18 @@ class Sweep:
                 self.submit(c[0], c[1], c[2], config)
         return out
 
+    def set_block_jacobi(self, num_subdomains: int = 0, subdomains=None) -> None:
+        """Solve the frequencies returned from now on with gmres_preconditioned + the block-Jacobi / additive Schwarz
+        preconditioner (schwarz.rs) rebuilt from every frequency's matrix: ``num_subdomains`` contiguous blocks, or explicit
+        ``subdomains`` (index arrays, e.g. ``bem.voronoi_subdomains``); ``set_block_jacobi(0)`` switches back to plain gmres."""
+        if subdomains is None:
+            self._capi.check(self._lib.bemb200_sweep_set_block_jacobi(self._h, int(num_subdomains), None, None), None)
+            return
+        ptr = np.zeros(len(subdomains) + 1, dtype=np.uint64)
+        ptr[1:] = np.cumsum([len(p) for p in subdomains])
+        idx = np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.uint64) for p in subdomains]))
+        self._capi.check(self._lib.bemb200_sweep_set_block_jacobi(self._h, len(subdomains), self._capi.ptr(ptr), self._capi.ptr(idx)), None)
+
     @property
     def boosts(self) -> int:
         return int(self._lib.bemb200_sweep_boosts(self._h))

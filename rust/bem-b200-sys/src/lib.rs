@@ -101,6 +101,8 @@ extern "C" {
                                 rhs_extra: *const f64, max_iterations: u32, restart: u32, tolerance: f64) -> c_int;
     pub fn bemb200_sweep_next(sw: *mut bemb200_sweep, x_out: *mut f64, info: *mut bemb200_gmres_info,
                               stats: *mut bemb200_assembly_stats, rhs_out: *mut f64) -> c_int;
+    pub fn bemb200_sweep_boosts(sw: *const bemb200_sweep) -> u64;
+    pub fn bemb200_sweep_set_block_jacobi(sw: *mut bemb200_sweep, num_subdomains: u32, sub_ptr: *const u64, sub_idx: *const u64) -> c_int;
     pub fn bemb200_sweep_destroy(sw: *mut bemb200_sweep);
     // one process, several devices
     pub fn bemb200_multi_create(devices: *const c_int, n: c_int, out: *mut *mut bemb200_multi) -> c_int;

@@ -373,11 +373,24 @@ def test_c_sweep_equals_sequential_solves(bem, orc):
         cases.append((ph, beta, inc.compute_rhs_with_beta(mesh.center, mesh.normal, ph, beta)))
     sw = Sweep(mesh)
     got = sw.solve_all(cases, cfg)
+    # the same sweep with gmres_preconditioned + block-Jacobi (80 blocks of 64 DOFs) rebuilt from every frequency's matrix
+    sw.set_block_jacobi(80)
+    got_pc = sw.solve_all(cases, cfg)
+    sw.set_block_jacobi(0)
+    again = sw.solve_all(cases[:1], cfg)
     sw.close()
-    for (ph, beta, rhs), (sol, stats, b) in zip(cases, got):
+    assert again[0][0].iterations == got[0][0].iterations
+    for (ph, beta, rhs), (sol, stats, b), (solp, _sp, _bp) in zip(cases, got, got_pc):
         system = bem.build_tbem_system_with_beta(mesh, ph, beta)
-        ref = bem.gmres(bem.DenseOperator(system), system.rhs + rhs, cfg)
+        op = bem.DenseOperator(system)
+        ref = bem.gmres(op, system.rhs + rhs, cfg)
         assert np.array_equal(b, system.rhs + rhs)
         assert (sol.iterations, sol.restarts, sol.converged) == (ref.iterations, ref.restarts, ref.converged)
         assert np.linalg.norm(sol.x - ref.x) / np.linalg.norm(ref.x) < 1e-9
         assert stats["near_pairs"] > 0
+        pre = bem.AdditiveSchwarzPreconditioner.from_operator(op, 80)
+        refp = bem.gmres_preconditioned(op, pre, system.rhs + rhs, cfg)
+        pre.close()
+        assert (solp.iterations, solp.restarts, solp.converged) == (refp.iterations, refp.restarts, True)
+        assert np.linalg.norm(solp.x - refp.x) / np.linalg.norm(refp.x) < 1e-9
+        assert np.linalg.norm(solp.x - ref.x) / np.linalg.norm(ref.x) < 1e-8 and solp.iterations < sol.iterations
