@@ -212,13 +212,11 @@ block_fixup_kernel(uint64_t nrows, unsigned nk, unsigned G, const cplx* __restri
     }
 }
 
-struct SkWorkspace {
-    cplx* buf = nullptr;
-    size_t elems = 0;
+struct SkDevice {
     int sms = 0;
-    bool attr[16] = {};
+    bool attr[8] = {};
 };
-SkWorkspace g_sk[64];
+SkDevice g_sk[64];
 std::mutex g_sk_mu;
 
 template <int NT>
@@ -229,40 +227,37 @@ cudaError_t launch_streamk_t(const cplx* A, uint64_t lda, uint64_t nrows, uint64
     if (e != cudaSuccess) return e;
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
     const size_t smem = (size_t)SK_STAGES * (SK_BM * SK_LDA + SK_BK * S) * sizeof(cplx);
-    cplx* partial = nullptr;
     unsigned G = 0;
     {
         std::lock_guard<std::mutex> lk(g_sk_mu);
-        SkWorkspace& w = g_sk[dev];
+        SkDevice& w = g_sk[dev];
         if (w.sms == 0) {
             e = cudaDeviceGetAttribute(&w.sms, cudaDevAttrMultiProcessorCount, dev);
             if (e != cudaSuccess) return e;
         }
         G = (unsigned)w.sms;
-        const size_t need = (size_t)G * 2 * SK_BM * 32;  // sized for S = 32 once
-        if (w.elems < need) {
-            if (w.buf) cudaFree(w.buf);
-            w.buf = nullptr; w.elems = 0;
-            e = cudaMalloc((void**)&w.buf, need * sizeof(cplx));
-            if (e != cudaSuccess) return e;
-            w.elems = need;
-        }
         if (!w.attr[NT]) {
             e = cudaFuncSetAttribute(zgemm_streamk_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             w.attr[NT] = true;
         }
-        partial = w.buf;
     }
     const unsigned nk = (unsigned)((ncols + SK_BK - 1) / SK_BK);
     const unsigned long long ntiles = (nrows + SK_BM - 1) / SK_BM;
     if (ntiles * nk < G) G = (unsigned)(ntiles * nk);
     if (6ull * ntiles < G) G = (unsigned)(6ull * ntiles);  // a tile has at most G / ntiles + 2 <= 8 contributors (block_fixup_kernel's table)
+    // partial tiles: stream-ordered scratch of THIS launch (two contexts of one device may run block products concurrently)
+    cplx* partial = nullptr;
+    e = cudaMallocAsync((void**)&partial, (size_t)G * 2 * SK_BM * S * sizeof(cplx), s);
+    if (e != cudaSuccess) return e;
     zgemm_streamk_kernel<NT><<<G, SK_THREADS, smem, s>>>(A, lda, nrows, ncols, X, Y, partial, nk);
     e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    block_fixup_kernel<S><<<dim3((unsigned)ntiles, 4), 256, 0, s>>>(nrows, nk, G, partial, Y);
-    return cudaGetLastError();
+    if (e == cudaSuccess) {
+        block_fixup_kernel<S><<<dim3((unsigned)ntiles, 4), 256, 0, s>>>(nrows, nk, G, partial, Y);
+        e = cudaGetLastError();
+    }
+    const cudaError_t fe = cudaFreeAsync(partial, s);
+    return e != cudaSuccess ? e : fe;
 }
 
 }  // namespace

@@ -38,6 +38,20 @@ inc, _ = orc.incident_rhs(0, [0, 0, 1.0], 1.0, mesh.center[:n], mesh.normal[:n],
 b = rhs + inc
 x, info = orc.gmres_op(lambda v: bdist.allgather_rows(orc.zgemv(A_loc, v, nthreads=1), n), n, b,
                        max_iterations=50, restart=10, tolerance=1e-10)
+# row-sharded block-Jacobi (csrc/schwarz.cu): rank-aligned subdomains, every rank factors and applies ONLY the blocks of its own
+# rows on its slab of A v, then the preconditioned slabs are gathered -- must equal the global additive Schwarz preconditioner
+from math_audio_b200 import bem
+from oracle import schwarz_oracle as so
+parts = bem.schwarz_partition_aligned(n, world, 10)
+mine = [p.astype(np.int64) for p in parts if r0 <= int(p[0]) and int(p[-1]) < r1]
+assert sum(len(p) for p in mine) == r1 - r0
+local = so.DenseSchwarz(A_loc[:, r0:r1], subdomains=[p - r0 for p in mine])
+def precond(v):
+    return bdist.allgather_rows(local.apply(v[r0:r1]), n)
+xp, infop = orc.gmres_preconditioned_cb(lambda v: bdist.allgather_rows(orc.zgemv(A_loc, v, nthreads=1), n), precond, n, b,
+                                        max_iterations=50, restart=10, tolerance=1e-10)
+np.save(os.path.join(os.environ["OUT_DIR"], f"xp_{rank}.npy"), xp)
+np.save(os.path.join(os.environ["OUT_DIR"], f"infop_{rank}.npy"), np.array([infop["iterations"], infop["restarts"], int(infop["converged"])]))
 np.save(os.path.join(os.environ["OUT_DIR"], f"x_{rank}.npy"), x)
 np.save(os.path.join(os.environ["OUT_DIR"], f"info_{rank}.npy"), np.array([info["iterations"], info["restarts"], int(info["converged"])]))
 if rank == 0:
@@ -45,6 +59,11 @@ if rank == 0:
     xs, infos = orc.gmres(A, rhs_full + inc, max_iterations=50, restart=10, tolerance=1e-10, nthreads=1)
     np.save(os.path.join(os.environ["OUT_DIR"], "x_single.npy"), xs)
     np.save(os.path.join(os.environ["OUT_DIR"], "info_single.npy"), np.array([infos["iterations"], infos["restarts"], int(infos["converged"])]))
+    glob = so.DenseSchwarz(A, subdomains=[p.astype(np.int64) for p in parts])
+    xps, infops = orc.gmres_preconditioned_cb(lambda v: orc.zgemv(A, v, nthreads=1), glob.apply, n, rhs_full + inc,
+                                              max_iterations=50, restart=10, tolerance=1e-10)
+    np.save(os.path.join(os.environ["OUT_DIR"], "xp_single.npy"), xps)
+    np.save(os.path.join(os.environ["OUT_DIR"], "infop_single.npy"), np.array([infops["iterations"], infops["restarts"], int(infops["converged"])]))
 '''
 
 
@@ -61,3 +80,7 @@ def test_sharded_matvec_replicated_arnoldi_gloo(tmp_path, orc):
     assert (x0 == x1).all(), "ranks diverged"
     assert (x0 == xs).all(), "sharded solve differs from the single-process solve"
     assert (i0 == i1).all() and (i0 == isg).all() and i0[2] == 1 and i0[1] >= 1  # restarted at least once
+    p0, p1, ps = (np.load(tmp_path / f) for f in ("xp_0.npy", "xp_1.npy", "xp_single.npy"))
+    j0, j1, js = (np.load(tmp_path / f) for f in ("infop_0.npy", "infop_1.npy", "infop_single.npy"))
+    assert (p0 == p1).all() and (p0 == ps).all(), "row-sharded block-Jacobi differs from the global preconditioner"
+    assert (j0 == j1).all() and (j0 == js).all() and j0[2] == 1 and j0[0] < i0[0]  # and it does precondition
