@@ -1030,7 +1030,7 @@ def run_native(args):
           "peak_source": "nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz; measured = register-resident DFMA loop on this GPU"}
     in_sweep = {"achieved": far_tf, "frac": far_tf / fp64_nominal, "avg_launch_ms": far_ms / K, "share_of_step": far_ms / total_ms,
                 "assembly_share_of_step": asm_ms / total_ms,
-                "note": ("background grid (148 persistent blocks pulling work items from a device counter) underneath the solve of the previous frequency"
+                "note": (f"background grid ({148 * args.background} persistent blocks pulling work items from a device counter) underneath the solve of the previous frequency"
                          if overlap else "foreground launch of the timed sweep (sequential schedule)")}
     if fg_ms:
         fg_tf = far_flop / (fg_ms * 1e-3) / 1e12
@@ -1121,7 +1121,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="sphere20k_sweep64")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--background", type=int, default=1, help="blocks/SM of the background assembly kernel in the sweep pipeline")
+    ap.add_argument("--background", type=int, default=2, help="blocks/SM of the background assembly kernel in the sweep pipeline")
     ap.add_argument("--no-overlap", action="store_true", help="do not overlap assembly(f+1) with solve(f)")
     ap.add_argument("--schedule", choices=["auto", "pipelined", "sequential"], default="auto",
                     help="auto: pipelined sweep on 1 GPU, sequential (persistent fused solver) from 2 GPUs on")

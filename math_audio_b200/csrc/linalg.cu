@@ -1575,7 +1575,11 @@ cudaError_t launch_mgs(const cplx* V, uint64_t ldv, cplx* w, int j, uint64_t n, 
                        const PeerWait& pw, bool strict, cudaStream_t s) {
     *wrote_host = false;
     // mode 3 (default): whole-GPU cooperative kernel; the slice per CTA depends on n only
-    static const bool force_grid = std::getenv("BEMB200_MGS_FORCE_GRID") != nullptr;
+    // The whole-GPU cooperative kernel also beside a background assembly (BEMB200_MGS_FORCE_GRID=0 restores the 16-CTA cluster
+    // kernel there): with the counter-driven far kernel at two persistent blocks per SM it measured 100.4 against 104.3 ms per
+    // frequency for cluster kernel + one block per SM on the same box (profiles/r02r_*.json); the cluster kernel cannot be
+    // placed while two far blocks sit on every SM, the cooperative grid (one small CTA per SM) can.
+    static const bool force_grid = []() { const char* v = std::getenv("BEMB200_MGS_FORCE_GRID"); return v ? std::atoi(v) != 0 : true; }();
     const int mode = g_mgs_mode.get();
     if (mode == 3 && (allow_grid || force_grid) && Lmat && scratch && j + 1 <= LS_MAXV && n >= 4096 && n <= (uint64_t)GR_MAX_CTAS * 1024ull) {
         const int G = GR_MAX_CTAS;  // fixed (not the SM count of the device): the summation order must not depend on the rank's GPU

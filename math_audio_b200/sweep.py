@@ -33,7 +33,7 @@ class Sweep:
     """
 
     def __init__(self, mesh: Mesh, device: int = 0, rank: int = 0, nranks: int = 1, nccl_id: Optional[bytes] = None,
-                 overlap: bool = True, background_blocks_per_sm: int = 1):
+                 overlap: bool = True, background_blocks_per_sm: int = 2):
         import ctypes as C
 
         from . import _capi
@@ -116,7 +116,7 @@ class SweepDriver:
     device-resident leg (`value`), which must not touch host buffers; everything else uses `Sweep`."""
 
     def __init__(self, mesh: Mesh, device: int = 0, rank: int = 0, nranks: int = 1, nccl_id: Optional[bytes] = None,
-                 solve_stream: int = 0, assembly_stream: int = 0, overlap: bool = True, background_blocks_per_sm: int = 1):
+                 solve_stream: int = 0, assembly_stream: int = 0, overlap: bool = True, background_blocks_per_sm: int = 2):
         # the solve context owns the communicator; the assembly context needs none
         self.ctx_solve = bem.Context(device, rank, nranks, nccl_id, cuda_stream=solve_stream)
         self.ctx_asm = bem.Context(device, rank, nranks, None, cuda_stream=assembly_stream) if overlap else self.ctx_solve
