@@ -259,7 +259,7 @@ int bemb200_schwarz_create(const bemb200_matrix* m, uint32_t num_subdomains, con
     std::vector<uint32_t> lidx;
     std::vector<uint32_t> count(nloc, 0);
     uint32_t gmin = 0xffffffffu, gmax = 0;
-    std::vector<unsigned char> seen;
+    std::vector<uint32_t> stamp(nloc, 0);  // stamp[li] == k + 1: local row li already occurs in subdomain k
     for (uint32_t k = 0; k < S; ++k) {
         const uint64_t b = ptr[k], e = ptr[k + 1], sz = e - b;
         if (sz == 0) continue;
@@ -276,11 +276,10 @@ int bemb200_schwarz_create(const bemb200_matrix* m, uint32_t num_subdomains, con
                                  "a subdomain straddles two ranks' row blocks (row-sharded operators need rank-aligned subdomains)");
         }
         if (owner != (uint64_t)ctx->rank) continue;
-        seen.assign(nloc, 0);
         for (uint64_t q = b; q < e; ++q) {
             const uint32_t li = (uint32_t)(gidx[q] - m->r0);
-            if (seen[li]) return set_error(ctx, BEMB200_EINVAL, "an index occurs twice inside one subdomain");
-            seen[li] = 1;
+            if (stamp[li] == k + 1) return set_error(ctx, BEMB200_EINVAL, "an index occurs twice inside one subdomain");
+            stamp[li] = k + 1;
             lidx.push_back(li);
             count[li] += 1;
         }
