@@ -249,6 +249,11 @@ int bemb200_cgs(const bemb200_matrix* m, const double* b, uint32_t max_iteration
 int bemb200_gmres_batched(const bemb200_matrix* m, const double* b_all, uint32_t nrhs, uint32_t max_iterations,
                           uint32_t restart, double tolerance, double* x_all, bemb200_gmres_info* infos,
                           double* block_matvec_ms, uint64_t* block_matvecs);
+/* The same with nrhs independent gmres_preconditioned() solves (gmres.rs:282) sharing the block-Jacobi preconditioner of
+ * bemb200_schwarz_create (disjoint subdomains covering every row; BEMB200_EUNSUPPORTED for overlapping ones). */
+int bemb200_gmres_batched_schwarz(const bemb200_matrix* m, const bemb200_precond* precond, const double* b_all, uint32_t nrhs,
+                                  uint32_t max_iterations, uint32_t restart, double tolerance, double* x_all,
+                                  bemb200_gmres_info* infos, double* block_matvec_ms, uint64_t* block_matvecs);
 /* Y = A X for nrhs (<= 32) vectors at once with the tensor-core block kernel; kernel_ms (may be
  * NULL) receives the device time of one block matvec.  Row-sharded operators: collective, every rank multiplies its row
  * block and receives the whole Y.  (bemb200_gmres_batched: up to 196 608 unknowns, also row-sharded.) */

@@ -847,10 +847,11 @@ def lu_solve(a, b: np.ndarray, ctx: Optional[Context] = None, overwrite: bool = 
     return x
 
 
-def gmres_batched(operator: DenseOperator, b_all: np.ndarray, config: GmresConfig):
+def gmres_batched(operator: DenseOperator, b_all: np.ndarray, config: GmresConfig, precond: "Optional[AdditiveSchwarzPreconditioner]" = None):
     """``[gmres(operator, b, config) for b in b_all]`` (the reference's way to solve several
     right-hand sides) executed in lockstep on the device with one tensor-core block matvec per
-    iteration.  ``b_all``: (nrhs, n).  Returns (list of GmresSolution, stats dict)."""
+    iteration.  ``b_all``: (nrhs, n).  Returns (list of GmresSolution, stats dict).  ``precond``: a block-Jacobi
+    AdditiveSchwarzPreconditioner -> ``[gmres_preconditioned(operator, precond, b, config) for b in b_all]``."""
     b_all = np.ascontiguousarray(b_all, dtype=np.complex128)
     n = operator.num_rows()
     if b_all.ndim != 2 or b_all.shape[1] != n:
@@ -859,9 +860,14 @@ def gmres_batched(operator: DenseOperator, b_all: np.ndarray, config: GmresConfi
     x_all = np.empty_like(b_all)
     infos = (_capi.CGmresInfo * nrhs)()
     ms, cnt = C.c_double(), C.c_uint64()
-    _capi.check(_capi.lib().bemb200_gmres_batched(operator.matrix._h, _capi.ptr(b_all), nrhs, config.max_iterations, config.restart,
-                                                  config.tolerance, _capi.ptr(x_all), infos, C.byref(ms), C.byref(cnt)),
-                operator.matrix.ctx._h)
+    if precond is None:
+        _capi.check(_capi.lib().bemb200_gmres_batched(operator.matrix._h, _capi.ptr(b_all), nrhs, config.max_iterations, config.restart,
+                                                      config.tolerance, _capi.ptr(x_all), infos, C.byref(ms), C.byref(cnt)),
+                    operator.matrix.ctx._h)
+    else:
+        _capi.check(_capi.lib().bemb200_gmres_batched_schwarz(operator.matrix._h, precond._h, _capi.ptr(b_all), nrhs, config.max_iterations,
+                                                              config.restart, config.tolerance, _capi.ptr(x_all), infos, C.byref(ms),
+                                                              C.byref(cnt)), operator.matrix.ctx._h)
     sols = [GmresSolution(x=x_all[i], iterations=int(infos[i].iterations), restarts=int(infos[i].restarts),
                           residual=float(infos[i].residual), converged=bool(infos[i].converged)) for i in range(nrhs)]
     return sols, dict(block_matvec_ms=float(ms.value), block_matvecs=int(cnt.value))

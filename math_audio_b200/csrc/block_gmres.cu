@@ -14,6 +14,7 @@
 
 #include "api_internal.h"
 #include "linalg.h"
+#include "schwarz.h"
 
 using namespace bemb;
 
@@ -69,12 +70,18 @@ struct DevBuf {
 
 }  // namespace
 
-extern "C" int bemb200_gmres_batched(const bemb200_matrix* cm, const double* b_all, uint32_t nrhs, uint32_t max_iterations,
-                                     uint32_t restart, double tolerance, double* x_all, bemb200_gmres_info* infos,
-                                     double* block_matvec_ms, uint64_t* block_matvecs) {
+// `sp` != NULL: nrhs independent gmres_preconditioned() solves (gmres.rs:282-585) with the block-Jacobi preconditioner: M^-1 acts on
+// the rank's slab of the block product before the exchange, residuals are M^-1 (B - A X), norms relative to ||M^-1 b||.
+static int gmres_batched_impl(const bemb200_matrix* cm, const bemb200_precond* sp, const double* b_all, uint32_t nrhs,
+                              uint32_t max_iterations, uint32_t restart, double tolerance, double* x_all, bemb200_gmres_info* infos,
+                              double* block_matvec_ms, uint64_t* block_matvecs) {
     bemb200_matrix* m = const_cast<bemb200_matrix*>(cm);
     if (!m || !b_all || !x_all || !infos) return set_error(nullptr, BEMB200_EINVAL, "NULL argument");
     bemb200_ctx* ctx = m->ctx;
+    if (sp && (sp->ctx != ctx || sp->n != m->n_rows || sp->r0 != m->r0 || sp->r1 != m->r1))
+        return set_error(ctx, BEMB200_EINVAL, "preconditioner was built for another operator shape / context");
+    if (sp && !sp->disjoint)
+        return set_error(ctx, BEMB200_EUNSUPPORTED, "batched GMRES takes block-Jacobi (disjoint subdomains covering every row) only");
     if (m->n_rows != m->n_cols) return set_error(ctx, BEMB200_EINVAL, "gmres needs a square operator");
     if (restart == 0 || nrhs == 0 || nrhs > 32) return set_error(ctx, BEMB200_EINVAL, "need 1 <= nrhs <= 32 and restart >= 1");
     const uint64_t n = m->n_rows;
@@ -107,6 +114,8 @@ extern "C" int bemb200_gmres_batched(const bemb200_matrix* cm, const double* b_a
     BEMB_CUDA(ctx, buf.alloc(&Rblk, npad * S));
     BEMB_CUDA(ctx, buf.alloc(&Xsol, npad * S));
     BEMB_CUDA(ctx, buf.alloc(&stage, (size_t)nrhs * n));
+    cplx* Pslab = nullptr;  // this rank's slab of a block before M^-1
+    if (sp) BEMB_CUDA(ctx, buf.alloc(&Pslab, (nloc ? nloc : 1) * (size_t)S));
     BEMB_CUDA(ctx, buf.alloc(&hcol_d, (size_t)S * hstride));
     BEMB_CUDA(ctx, buf.alloc(&ycoef_d, (size_t)S * mm));
     BEMB_CUDA(ctx, buf.alloc(&scal_d, (size_t)S));
@@ -130,11 +139,20 @@ extern "C" int bemb200_gmres_batched(const bemb200_matrix* cm, const double* b_a
     BEMB_CUDA(ctx, cudaMemcpyAsync(stage, b_all, (size_t)nrhs * n * sizeof(cplx), cudaMemcpyHostToDevice, s));
     BEMB_CUDA(ctx, launch_interleave(stage, Bblk, n, (int)nrhs, S, 1, s));
 
+    bool precond_in_matvec = false;  // on inside the Arnoldi loop; the residual products need the bare A X
+    // Z (npad x S) = M^-1 R for a whole block: every rank solves on its slab, the slabs are gathered
+    auto precond_full = [&](const cplx* R, cplx* Z) -> int {
+        const uint64_t off = (ctx->nranks > 1 ? (uint64_t)ctx->rank * chunk : m->r0) * S;
+        BEMB_CUDA(ctx, schwarz_apply_block_local(sp, R + m->r0 * S, Z + off, S, s));
+        if (ctx->nranks > 1) return nccl_allgather_bytes(ctx, Z + off, Z, chunk * S * sizeof(cplx));
+        return BEMB200_OK;
+    };
     auto block_matvec = [&](const cplx* X, cplx* Y) -> int {
         cplx* yloc = Y + (ctx->nranks > 1 ? (uint64_t)ctx->rank * chunk : m->r0) * S;
         BEMB_CUDA(ctx, cudaEventRecord(e0, s));
-        BEMB_CUDA(ctx, launch_zgemm_block(m->A, m->n_cols, nloc, m->n_cols, X, yloc, S, s));
+        BEMB_CUDA(ctx, launch_zgemm_block(m->A, m->n_cols, nloc, m->n_cols, X, precond_in_matvec ? Pslab : yloc, S, s));
         BEMB_CUDA(ctx, cudaEventRecord(e1, s));
+        if (precond_in_matvec) BEMB_CUDA(ctx, schwarz_apply_block_local(sp, Pslab, yloc, S, s));  // w = M^-1 (A v) on this rank's rows
         if (ctx->nranks > 1) {
             int rc = nccl_allgather_bytes(ctx, yloc, Y, chunk * S * sizeof(cplx));
             if (rc != BEMB200_OK) return rc;
@@ -165,7 +183,13 @@ extern "C" int bemb200_gmres_batched(const bemb200_matrix* cm, const double* b_a
     };
 
     std::vector<Rhs> R(S);
-    int rc = norms(Bblk, nullptr, nullptr);
+    int rc = BEMB200_OK;
+    if (sp) {  // ||M^-1 b|| (gmres.rs:455-457)
+        rc = precond_full(Bblk, Yblk);
+        if (rc == BEMB200_OK) rc = norms(Yblk, nullptr, nullptr);
+    } else {
+        rc = norms(Bblk, nullptr, nullptr);
+    }
     if (rc != BEMB200_OK) return rc;
     for (int q = 0; q < S; ++q) {
         R[q].b_norm = std::sqrt(scal_h[q]);
@@ -182,11 +206,17 @@ extern "C" int bemb200_gmres_batched(const bemb200_matrix* cm, const double* b_a
     };
 
     for (uint32_t outer = 0; outer < max_iterations && !all_done(); ++outer) {
+        precond_in_matvec = false;
         rc = block_matvec(Xsol, Yblk);
         if (rc != BEMB200_OK) return rc;
         rc = norms(Bblk, Yblk, Rblk);
+        if (rc == BEMB200_OK && sp) {  // r = M^-1 (b - A x) (gmres.rs:473-476)
+            rc = precond_full(Rblk, Yblk);
+            if (rc == BEMB200_OK) rc = norms(Yblk, nullptr, Rblk);
+        }
         if (rc != BEMB200_OK) return rc;
         add_mv_time();
+        precond_in_matvec = sp != nullptr;
         for (int q = 0; q < S; ++q) R[q].active = false;
         std::vector<double> scale(S, 0.0);
         for (int q = 0; q < S; ++q) {
@@ -286,9 +316,14 @@ extern "C" int bemb200_gmres_batched(const bemb200_matrix* cm, const double* b_a
         if (rc != BEMB200_OK) return rc;
     }
     if (!all_done()) {  // budget exhausted: true residual, converged = false (gmres.rs:264-276)
+        precond_in_matvec = false;
         rc = block_matvec(Xsol, Yblk);
         if (rc != BEMB200_OK) return rc;
         rc = norms(Bblk, Yblk, Rblk);
+        if (rc == BEMB200_OK && sp) {
+            rc = precond_full(Rblk, Yblk);
+            if (rc == BEMB200_OK) rc = norms(Yblk, nullptr, Rblk);
+        }
         if (rc != BEMB200_OK) return rc;
         add_mv_time();
         for (int q = 0; q < (int)nrhs; ++q)
@@ -305,6 +340,19 @@ extern "C" int bemb200_gmres_batched(const bemb200_matrix* cm, const double* b_a
     if (block_matvec_ms) *block_matvec_ms = mv_ms;
     if (block_matvecs) *block_matvecs = mv_count;
     return BEMB200_OK;
+}
+
+extern "C" int bemb200_gmres_batched(const bemb200_matrix* cm, const double* b_all, uint32_t nrhs, uint32_t max_iterations,
+                                     uint32_t restart, double tolerance, double* x_all, bemb200_gmres_info* infos,
+                                     double* block_matvec_ms, uint64_t* block_matvecs) {
+    return gmres_batched_impl(cm, nullptr, b_all, nrhs, max_iterations, restart, tolerance, x_all, infos, block_matvec_ms, block_matvecs);
+}
+
+extern "C" int bemb200_gmres_batched_schwarz(const bemb200_matrix* cm, const bemb200_precond* precond, const double* b_all, uint32_t nrhs,
+                                             uint32_t max_iterations, uint32_t restart, double tolerance, double* x_all,
+                                             bemb200_gmres_info* infos, double* block_matvec_ms, uint64_t* block_matvecs) {
+    if (!precond) return set_error(nullptr, BEMB200_EINVAL, "NULL argument");
+    return gmres_batched_impl(cm, precond, b_all, nrhs, max_iterations, restart, tolerance, x_all, infos, block_matvec_ms, block_matvecs);
 }
 
 // Y = A X for a block of nrhs right-hand sides (each contiguous on the host): the tensor-core

@@ -25,6 +25,7 @@
 #include "schwarz.h"
 
 #include <algorithm>
+#include <atomic>
 #include <vector>
 
 using namespace bemb;
@@ -161,6 +162,62 @@ schwarz_apply_kernel(const uint64_t* __restrict__ sub_off, const uint64_t* __res
     }
 }
 
+// The same product for S interleaved right-hand sides (batched GMRES): Z[idx_k[l]][s] = sum_c X_k[l][c] R[idx_k[c]][s].  Lane = right-
+// hand side; the inverse-block entry is a warp-uniform load, the R chunk (BLK_CH rows x S) sits in shared memory.  Disjoint
+// subdomains only (block-Jacobi).
+constexpr int BLK_CH = 128;
+__global__ void __launch_bounds__(APPLY_THREADS)
+schwarz_apply_block_kernel(const uint64_t* __restrict__ sub_off, const uint64_t* __restrict__ inv_off, const uint32_t* __restrict__ idx,
+                           const cplx* __restrict__ inv, const uint32_t* __restrict__ cta_sub, const uint32_t* __restrict__ cta_row,
+                           const cplx* __restrict__ R_loc, cplx* __restrict__ Z_loc, int S) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx* s_r = reinterpret_cast<cplx*>(smem_raw);  // [BLK_CH][S]
+    const uint32_t k = cta_sub[blockIdx.x], row0 = cta_row[blockIdx.x];
+    const uint64_t o = sub_off[k];
+    const uint32_t sz = (uint32_t)(sub_off[k + 1] - o);
+    const uint32_t* id = idx + o;
+    const cplx* Xk = inv + inv_off[k];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t row_end = row0 + APPLY_ROWS < sz ? row0 + APPLY_ROWS : sz;
+    constexpr int RPW = APPLY_ROWS / (APPLY_THREADS / 32);  // rows per warp
+    double ar[RPW], ai[RPW];
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) ar[r] = ai[r] = 0.0;
+    for (uint32_t c0 = 0; c0 < sz; c0 += BLK_CH) {
+        const uint32_t nch = sz - c0 < (uint32_t)BLK_CH ? sz - c0 : (uint32_t)BLK_CH;
+        __syncthreads();
+        for (uint32_t e = threadIdx.x; e < nch * (uint32_t)S; e += APPLY_THREADS) {
+            const uint32_t cc = e / (uint32_t)S, q = e - cc * (uint32_t)S;
+            s_r[e] = R_loc[(uint64_t)id[c0 + cc] * S + q];
+        }
+        __syncthreads();
+        if ((int)lane < S) {
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) {
+                const uint32_t l = row0 + warp + (APPLY_THREADS / 32) * r;
+                if (l < row_end) {
+                    const double2* row = reinterpret_cast<const double2*>(Xk + (uint64_t)l * sz + c0);
+                    double xr = ar[r], xi = ai[r];
+                    for (uint32_t cc = 0; cc < nch; ++cc) {
+                        const double2 a = row[cc];
+                        const cplx x = s_r[cc * S + lane];
+                        xr = fma(a.x, x.re, fma(-a.y, x.im, xr));
+                        xi = fma(a.x, x.im, fma(a.y, x.re, xi));
+                    }
+                    ar[r] = xr; ai[r] = xi;
+                }
+            }
+        }
+    }
+    if ((int)lane < S) {
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+            const uint32_t l = row0 + warp + (APPLY_THREADS / 32) * r;
+            if (l < row_end) Z_loc[(uint64_t)id[l] * S + lane] = C(ar[r], ai[r]);
+        }
+    }
+}
+
 // result[g] += solution[l] * weight[g], subdomains in their order (schwarz.rs:409-413); rows in no subdomain stay 0
 __global__ void __launch_bounds__(256)
 schwarz_combine_kernel(uint64_t nloc, const uint64_t* __restrict__ dof_ptr, const uint64_t* __restrict__ dof_pos,
@@ -206,6 +263,27 @@ cudaError_t schwarz_apply_local(const bemb200_precond* p, const cplx* r_loc, cpl
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || p->disjoint) return e;
     schwarz_combine_kernel<<<(unsigned)((nloc + 255) / 256), 256, 0, s>>>(nloc, p->dof_ptr, p->dof_pos, p->weight, p->sol, z_loc);
+    return cudaGetLastError();
+}
+
+// Z_loc[nloc][S] = M^-1 R_loc[nloc][S] (interleaved right-hand sides); block-Jacobi (disjoint subdomains) only
+cudaError_t schwarz_apply_block_local(const bemb200_precond* p, const cplx* R_loc, cplx* Z_loc, int S, cudaStream_t s) {
+    const uint64_t nloc = p->r1 - p->r0;
+    if (nloc == 0) return cudaSuccess;
+    if (!p->disjoint || S < 1 || S > 32) return cudaErrorNotSupported;
+    const size_t smem = (size_t)BLK_CH * S * sizeof(cplx);
+    static std::atomic<unsigned char> attr_done[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) dev = 63;
+    if (!attr_done[dev].load()) {
+        e = cudaFuncSetAttribute(schwarz_apply_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BLK_CH * 32 * sizeof(cplx)));
+        if (e != cudaSuccess) return e;
+        attr_done[dev].store(1);
+    }
+    schwarz_apply_block_kernel<<<p->ncta, APPLY_THREADS, smem, s>>>(p->sub_off, p->inv_off, p->idx, p->inv, p->cta_sub, p->cta_row, R_loc,
+                                                                    Z_loc, S);
     return cudaGetLastError();
 }
 

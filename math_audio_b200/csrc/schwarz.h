@@ -38,4 +38,6 @@ namespace bemb {
 // z_loc = M^-1 r_loc on this rank's slab (both nloc long, device); stream-ordered, no synchronisation
 cudaError_t schwarz_apply_local(const bemb200_precond* p, const cplx* r_loc, cplx* z_loc, cudaStream_t s);
 int schwarz_apply_launches(const bemb200_precond* p);
+// Z_loc[nloc][S] = M^-1 R_loc[nloc][S] for S interleaved right-hand sides (batched GMRES); disjoint subdomains only
+cudaError_t schwarz_apply_block_local(const bemb200_precond* p, const cplx* R_loc, cplx* Z_loc, int S, cudaStream_t s);
 }  // namespace bemb

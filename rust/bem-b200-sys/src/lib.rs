@@ -86,6 +86,9 @@ extern "C" {
     pub fn bemb200_gmres_batched(m: *const bemb200_matrix, b_all: *const f64, nrhs: u32, max_iterations: u32, restart: u32,
                                  tolerance: f64, x_all: *mut f64, infos: *mut bemb200_gmres_info, block_matvec_ms: *mut f64,
                                  block_matvecs: *mut u64) -> c_int;
+    pub fn bemb200_gmres_batched_schwarz(m: *const bemb200_matrix, precond: *const bemb200_precond, b_all: *const f64, nrhs: u32,
+                                         max_iterations: u32, restart: u32, tolerance: f64, x_all: *mut f64,
+                                         infos: *mut bemb200_gmres_info, block_matvec_ms: *mut f64, block_matvecs: *mut u64) -> c_int;
     pub fn bemb200_incident_rhs(sm: *const bemb200_staged_mesh, phys: *const bemb200_physics, beta_re: f64, beta_im: f64,
                                 n_sources: u32, kinds: *const i32, vecs: *const f64, amps: *const f64, rhs_host: *mut f64,
                                 rhs_dev: *mut f64) -> c_int;

@@ -719,6 +719,15 @@ def test_block_matvec_and_batched_gmres(bem, orc):
                 continue
             assert np.linalg.norm(sol.x - xo) / np.linalg.norm(xo) < X_TOL
             assert np.linalg.norm(B[i] - A @ sol.x) / np.linalg.norm(B[i]) < 2e-10
+    # the same batch through gmres_preconditioned with block-Jacobi (20 blocks of 64): per right-hand side what the single call gives
+    pre = bem.AdditiveSchwarzPreconditioner.from_operator(op, 20)
+    solp, _ = bem.gmres_batched(op, B, cfg, precond=pre)
+    for i in (0, 7, 31):
+        one = bem.gmres_preconditioned(op, pre, B[i], cfg)
+        assert solp[i].converged and (solp[i].iterations, solp[i].restarts) == (one.iterations, one.restarts)
+        assert np.linalg.norm(solp[i].x - one.x) / np.linalg.norm(one.x) < 1e-9
+        assert np.linalg.norm(solp[i].x - sols[i].x) / np.linalg.norm(sols[i].x) < X_TOL and solp[i].iterations < sols[i].iterations
+    pre.close()
     # budget exhaustion: converged = false, true residual (per right-hand side)
     sols, _ = bem.gmres_batched(op, B[:8], bem.GmresConfig(max_iterations=1, restart=5, tolerance=1e-14))
     for i, sol in enumerate(sols):
