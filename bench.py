@@ -752,9 +752,19 @@ def run_config3(ctx, rank, world, dev, reps=2):
     cnt = torch.tensor([float(checked)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    # the same system through gmres_preconditioned + block-Jacobi on rank-aligned Voronoi clusters
+    bj = None
+    if not os.environ.get("BENCH_NO_BLOCK_JACOBI"):
+        try:
+            bj = block_jacobi_leg(bem, op, b, cfg, world, dev, int(os.environ.get("BENCH_BJ_BLOCK", "256")), sol.x, sol.iterations,
+                                  best["s"] - best["asm_s"], centers=mesh.center)
+        except Exception as e:
+            bj = {"error": f"{type(e).__name__}: {e}"}
     del system
     if rank != 0:
         return None
+    if bj is not None:
+        block["block_jacobi"] = bj
     far_flop = (FLOP_PER_QP * 16 + FLOP_PER_PAIR) * nloc * (n - 1)
     mv_bytes = 16.0 * nloc * n + 16.0 * n + 16.0 * nloc
     fp64_nominal = 148 * 64 * 2 * 1.965e9 / 1e12
