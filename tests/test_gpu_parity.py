@@ -626,6 +626,16 @@ def test_block_jacobi_schwarz_preconditioner(bem, orc):
         if S == 20:  # compact near-field patches do precondition the Burton-Miller operator (measured 47 against 80); blocks
             assert sol.iterations < 0.7 * plain.iterations  # of 128 at this k h (two patches each) make it worse -- parity only
         pre.close()
+    # the committed fixture of the LINE-BY-LINE restatement of schwarz.rs on the ico1 golden system (tests/golden/make_golden_schwarz.py)
+    g1, f1 = np.load(GOLD / "ico1_ka0p5.npz"), np.load(GOLD / "schwarz_ico1.npz")
+    op1 = bem.DenseOperator(g1["A"])
+    for S in (4, 7):
+        pre1 = bem.AdditiveSchwarzPreconditioner.from_operator(op1, S)
+        assert np.max(np.abs(pre1.apply(f1["r"]) - f1[f"z_S{S}"])) < 1e-13 * np.max(np.abs(f1[f"z_S{S}"]))
+        s1 = bem.gmres_preconditioned(op1, pre1, g1["b"], bem.GmresConfig(100, 20, 1e-10))
+        assert [s1.iterations, s1.restarts, int(s1.converged)] == list(f1[f"info_S{S}"])
+        assert np.linalg.norm(s1.x - f1[f"x_S{S}"]) / np.linalg.norm(s1.x) < X_TOL
+        pre1.close()
     # overlapping subdomains: the contiguous blocks grown by one layer of mesh neighbours (elements within 1.6 edge lengths),
     # exactly what extend_partition does with a sparsity pattern (schwarz.rs:177-203); weights 1 / multiplicity
     d = np.linalg.norm(mesh.center[:, None, :] - mesh.center[None, :, :], axis=2)

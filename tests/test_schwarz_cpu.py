@@ -85,6 +85,24 @@ def test_tiny_pivot_is_skipped_like_the_reference():
     assert np.allclose(zc, zd, rtol=0, atol=0)
 
 
+def test_golden_schwarz_fixture(orc):
+    """tests/golden/schwarz_ico1.npz was produced by the line-by-line CSR restatement; the dense-block restatement (what the GPU
+    tests compare against at larger sizes) must reproduce it, M^-1 r to rounding and the preconditioned GMRES counts exactly."""
+    from pathlib import Path
+
+    gold = Path(__file__).resolve().parent / "golden"
+    g, f = np.load(gold / "ico1_ka0p5.npz"), np.load(gold / "schwarz_ico1.npz")
+    A, b, n = g["A"], g["b"], g["A"].shape[0]
+    for S in (4, 7):
+        ds = so.DenseSchwarz(A, S)
+        z = ds.apply(f["r"])
+        assert np.max(np.abs(z - f[f"z_S{S}"])) < 1e-13 * np.max(np.abs(z))
+        x, info = orc.gmres_preconditioned_cb(lambda v: A @ v, ds.apply, n, b, max_iterations=100, restart=20, tolerance=1e-10)
+        assert [info["iterations"], info["restarts"], int(info["converged"])] == list(f[f"info_S{S}"])
+        assert np.linalg.norm(x - f[f"x_S{S}"]) / np.linalg.norm(x) < 1e-10
+        assert np.linalg.norm(A @ x - b) / np.linalg.norm(b) < 1e-9
+
+
 def test_partition_helpers():
     for n, S in [(20, 4), (10, 3), (7, 7), (5, 9), (1280, 10), (20480, 160)]:
         a = bem.schwarz_partition(n, S)
