@@ -89,7 +89,14 @@ lu_nopivot_kernel(const uint64_t* __restrict__ sub_off, const uint64_t* __restri
             for (uint32_t i = p + 1 + ty; i < sz; i += nty) {
                 cplx* irow = Fk + (uint64_t)i * sz;
                 const cplx l = irow[p];
-                for (uint32_t j = p + 1 + tx; j < sz; j += 32u) irow[j] = irow[j] - l * prow[j];
+                // four independent (load, load, fma, store) groups in flight per thread: the step is bound by L2 latency
+                uint32_t j = p + 1 + tx;
+                for (; j + 96u < sz; j += 128u) {
+                    const cplx a0 = irow[j], a1 = irow[j + 32u], a2 = irow[j + 64u], a3 = irow[j + 96u];
+                    const cplx b0 = prow[j], b1 = prow[j + 32u], b2 = prow[j + 64u], b3 = prow[j + 96u];
+                    irow[j] = a0 - l * b0; irow[j + 32u] = a1 - l * b1; irow[j + 64u] = a2 - l * b2; irow[j + 96u] = a3 - l * b3;
+                }
+                for (; j < sz; j += 32u) irow[j] = irow[j] - l * prow[j];
             }
         }
         __syncthreads();
@@ -106,16 +113,31 @@ invert_kernel(const uint64_t* __restrict__ sub_off, const uint64_t* __restrict__
     const cplx* Fk = F + inv_off[k];
     cplx* Xk = X + inv_off[k];
     for (uint32_t c = threadIdx.x; c < sz; c += blockDim.x) {
+        // the sums run over four interleaved partial accumulators (j = 4 t + u): four loads in flight per thread instead of a
+        // chain of dependent L2 round trips; the reference adds left to right -- a rounding-level difference in the inverse
         for (uint32_t i = 0; i < sz; ++i) {  // forward: y_i = e_i - sum_{j<i} l_ij y_j
-            cplx acc = C(i == c ? 1.0 : 0.0, 0.0);
             const cplx* Li = Fk + (uint64_t)i * sz;
-            for (uint32_t j = 0; j < i; ++j) acc = acc - Li[j] * Xk[(uint64_t)j * sz + c];
-            Xk[(uint64_t)i * sz + c] = acc;
+            cplx p0 = C(0, 0), p1 = C(0, 0), p2 = C(0, 0), p3 = C(0, 0);
+            uint32_t j = 0;
+            for (; j + 3u < i; j += 4u) {
+                const cplx y0 = Xk[(uint64_t)j * sz + c], y1 = Xk[(uint64_t)(j + 1u) * sz + c], y2 = Xk[(uint64_t)(j + 2u) * sz + c],
+                           y3 = Xk[(uint64_t)(j + 3u) * sz + c];
+                p0 = p0 + Li[j] * y0; p1 = p1 + Li[j + 1u] * y1; p2 = p2 + Li[j + 2u] * y2; p3 = p3 + Li[j + 3u] * y3;
+            }
+            for (; j < i; ++j) p0 = p0 + Li[j] * Xk[(uint64_t)j * sz + c];
+            Xk[(uint64_t)i * sz + c] = C(i == c ? 1.0 : 0.0, 0.0) - ((p0 + p1) + (p2 + p3));
         }
         for (uint32_t i = sz; i-- > 0;) {    // backward: x_i = (y_i - sum_{j>i} u_ij x_j) * inv(u_ii)
-            cplx acc = Xk[(uint64_t)i * sz + c];
             const cplx* Ui = Fk + (uint64_t)i * sz;
-            for (uint32_t j = i + 1; j < sz; ++j) acc = acc - Ui[j] * Xk[(uint64_t)j * sz + c];
+            cplx p0 = C(0, 0), p1 = C(0, 0), p2 = C(0, 0), p3 = C(0, 0);
+            uint32_t j = i + 1;
+            for (; j + 3u < sz; j += 4u) {
+                const cplx x0 = Xk[(uint64_t)j * sz + c], x1 = Xk[(uint64_t)(j + 1u) * sz + c], x2 = Xk[(uint64_t)(j + 2u) * sz + c],
+                           x3 = Xk[(uint64_t)(j + 3u) * sz + c];
+                p0 = p0 + Ui[j] * x0; p1 = p1 + Ui[j + 1u] * x1; p2 = p2 + Ui[j + 2u] * x2; p3 = p3 + Ui[j + 3u] * x3;
+            }
+            for (; j < sz; ++j) p0 = p0 + Ui[j] * Xk[(uint64_t)j * sz + c];
+            cplx acc = Xk[(uint64_t)i * sz + c] - ((p0 + p1) + (p2 + p3));
             const cplx d = Ui[i];
             if (cnorm(d) > 1e-30) acc = acc * cinv(d);
             Xk[(uint64_t)i * sz + c] = acc;
