@@ -865,7 +865,21 @@ def run_native(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def fused_phase_times():
+        """device-side phase clocks of the persistent fused GMRES kernel accumulated since the last call (rank-local):
+        (kernel ms, ms inside its ZGEMV phases, ms inside its reduction rounds, number of rounds = Arnoldi steps)"""
+        import ctypes as C
+
+        from math_audio_b200 import _capi
+
+        f = _capi.lib().bemb200_debug_fused_times
+        f.restype = None
+        a, b_, c, d = C.c_double(), C.c_double(), C.c_double(), C.c_ulonglong()
+        f(C.byref(a), C.byref(b_), C.byref(c), C.byref(d))
+        return a.value, b_.value, c.value, int(d.value)
+
     driver.run(cases[: args.warmup], cfg, make_solve_device(0))
+    fused_phase_times()  # reset
     driver.asm_stats.clear()
     driver.sol_stats.clear()
     boosts_warm = driver.boosts
@@ -880,6 +894,7 @@ def run_native(args):
     sols = driver.run(cases[args.warmup:], cfg, make_solve_device(args.warmup))
     ev1.record(s_solve)   # the last one is the solution update on the solve stream
     boosts_timed = driver.boosts - boosts_warm
+    fused_ph = fused_phase_times()
     if driver.trace is not None and rank == 0:
         for lab, ci, ts in sorted(driver.trace, key=lambda r: r[2]):
             print(f"[value trace] {ts * 1e3:9.2f} ms  {lab:12s} case {ci}", file=sys.stderr)
@@ -1111,6 +1126,12 @@ def run_native(args):
                                   "wall": total_ms / K, "boosted_assemblies": int(boosts_timed),
                                   "note": "kernel times are per-kernel CUDA-event durations; with the sweep pipeline assembly overlaps the solve, so they do not add up to wall"},
     }
+    if fused_used and fused_ph[3] > 0:
+        tot, mvp, rnd, nr = fused_ph
+        line["fused_kernel"] = {"kernel_ms_per_step": tot / K, "zgemv_phase_ms_per_step": mvp / K, "reduction_round_ms_per_step": rnd / K,
+                                "arnoldi_steps": nr, "non_matvec_us_per_arnoldi_step": (tot - mvp) / nr * 1e3,
+                                "reduction_round_us_per_arnoldi_step": rnd / nr * 1e3,
+                                "note": "device-side clocks (%globaltimer) of CTA 0 on rank 0 inside gmres_fused_kernel over the timed solves; waiting for slower CTAs or ranks counts as non-matvec time"}
     if sharded_parity is not None:
         line["sharded_parity"] = sharded_parity
     if config5 is not None:

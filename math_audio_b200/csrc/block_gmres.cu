@@ -55,16 +55,20 @@ struct Rhs {
     bemb200_gmres_info info{0, 0, 0.0, 0};
 };
 
+// Workspace of one call: stream-ordered allocations from the device's (cached) memory pool -- cudaMalloc / cudaFree of half a
+// gigabyte of Krylov bases per call synchronise the device and were measured to cost anything between 1 and 200 ms.
 struct DevBuf {
+    cudaStream_t stream = nullptr;
     std::vector<void*> ptrs;
+    explicit DevBuf(cudaStream_t s) : stream(s) {}
     template <class T>
     cudaError_t alloc(T** p, size_t count) {
-        cudaError_t e = cudaMalloc((void**)p, (count ? count : 1) * sizeof(T));
+        cudaError_t e = cudaMallocAsync((void**)p, (count ? count : 1) * sizeof(T), stream);
         if (e == cudaSuccess) ptrs.push_back(*p);
         return e;
     }
     ~DevBuf() {
-        for (void* p : ptrs) cudaFree(p);
+        for (void* p : ptrs) cudaFreeAsync(p, stream);
     }
 };
 
@@ -102,7 +106,7 @@ static int gmres_batched_impl(const bemb200_matrix* cm, const bemb200_precond* s
     const uint64_t ldv = npad, vstride = (uint64_t)(mm + 1) * npad;
     const uint64_t hstride = (uint64_t)(mm + 2);
 
-    DevBuf buf;
+    DevBuf buf(s);
     cplx *Vall, *Xblk, *Yblk, *Bblk, *Rblk, *Xsol, *stage, *hcol_d, *ycoef_d;
     double *scal_d;
     int* cnt_d;
@@ -373,7 +377,7 @@ extern "C" int bemb200_apply_block(const bemb200_matrix* cm, const double* x_all
     const int S = (int)((nrhs + 7) / 8 * 8);
     const uint64_t nc = m->n_cols, nr = m->n_rows, nloc = m->r1 - m->r0;
     const uint64_t chunk = (nr + ctx->nranks - 1) / ctx->nranks, npad = chunk * ctx->nranks;
-    DevBuf buf;
+    DevBuf buf(s);
     cplx *Xb, *Yb, *stage;
     BEMB_CUDA(ctx, buf.alloc(&Xb, nc * S));
     BEMB_CUDA(ctx, buf.alloc(&Yb, npad * S));

@@ -256,7 +256,7 @@ template <typename T>
 cudaError_t upload(T** dst, const std::vector<T>& src, cudaStream_t s) {
     *dst = nullptr;
     const size_t bytes = std::max<size_t>(src.size(), 1) * sizeof(T);
-    cudaError_t e = cudaMalloc((void**)dst, bytes);
+    cudaError_t e = cudaMallocAsync((void**)dst, bytes, s);  // stream-ordered, from the cached pool: no device-wide synchronisation
     if (e != cudaSuccess) return e;
     if (!src.empty()) e = cudaMemcpyAsync(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, s);
     return e;
@@ -265,9 +265,10 @@ cudaError_t upload(T** dst, const std::vector<T>& src, cudaStream_t s) {
 void destroy(bemb200_precond* p) {
     if (!p) return;
     cudaSetDevice(p->ctx->device);
-    cudaFree(p->sub_off); cudaFree(p->inv_off); cudaFree(p->idx); cudaFree(p->inv); cudaFree(p->sol);
-    cudaFree(p->dof_ptr); cudaFree(p->dof_pos); cudaFree(p->weight); cudaFree(p->cta_sub); cudaFree(p->cta_row);
-    cudaFree(p->tmp);
+    cudaStream_t s = p->ctx->stream;  // the context outlives its handles (as for matrices)
+    void* ptrs[] = {p->sub_off, p->inv_off, p->idx, p->inv, p->sol, p->dof_ptr, p->dof_pos, p->weight, p->cta_sub, p->cta_row, p->tmp};
+    for (void* q : ptrs)
+        if (q) cudaFreeAsync(q, s);
     delete p;
 }
 
@@ -420,7 +421,7 @@ int bemb200_schwarz_create(const bemb200_matrix* m, uint32_t num_subdomains, con
     PC_CUDA(upload(&p->idx, lidx, s));
     PC_CUDA(upload(&p->cta_sub, cta_sub, s));
     PC_CUDA(upload(&p->cta_row, cta_row, s));
-    PC_CUDA(cudaMalloc((void**)&p->tmp, std::max<uint64_t>(nloc, 1) * sizeof(cplx)));
+    PC_CUDA(cudaMallocAsync((void**)&p->tmp, std::max<uint64_t>(nloc, 1) * sizeof(cplx), s));
     if (!p->disjoint) {
         std::vector<uint64_t> dof_ptr(nloc + 1, 0), dof_pos(lidx.size());
         for (uint64_t d = 0; d < nloc; ++d) dof_ptr[d + 1] = dof_ptr[d] + count[d];
@@ -431,15 +432,15 @@ int bemb200_schwarz_create(const bemb200_matrix* m, uint32_t num_subdomains, con
         PC_CUDA(upload(&p->dof_ptr, dof_ptr, s));
         PC_CUDA(upload(&p->dof_pos, dof_pos, s));
         PC_CUDA(upload(&p->weight, w, s));
-        PC_CUDA(cudaMalloc((void**)&p->sol, std::max<uint64_t>(lidx.size(), 1) * sizeof(cplx)));
+        PC_CUDA(cudaMallocAsync((void**)&p->sol, std::max<uint64_t>(lidx.size(), 1) * sizeof(cplx), s));
     }
     if (p->max_size * sizeof(cplx) > 48 * 1024)
         PC_CUDA(cudaFuncSetAttribute(schwarz_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MAX_SUBDOMAIN * sizeof(cplx))));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (p->nsub) {
         cplx* F = nullptr;
-        PC_CUDA(cudaMalloc((void**)&p->inv, p->inv_elems * sizeof(cplx)));
-        cudaError_t fe = cudaMalloc((void**)&F, p->inv_elems * sizeof(cplx));
+        PC_CUDA(cudaMallocAsync((void**)&p->inv, p->inv_elems * sizeof(cplx), s));
+        cudaError_t fe = cudaMallocAsync((void**)&F, p->inv_elems * sizeof(cplx), s);
         if (fe != cudaSuccess) { PC_CUDA(fe); }
         cudaEventCreate(&e0); cudaEventCreate(&e1);
         cudaEventRecord(e0, s);
@@ -456,7 +457,7 @@ int bemb200_schwarz_create(const bemb200_matrix* m, uint32_t num_subdomains, con
         if (ke == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
         p->factor_ms = ms;
         cudaEventDestroy(e0); cudaEventDestroy(e1);
-        cudaFree(F);
+        cudaFreeAsync(F, s);
         PC_CUDA(ke);
     } else {
         PC_CUDA(cudaStreamSynchronize(s));
@@ -491,7 +492,7 @@ int bemb200_precond_apply(const bemb200_precond* cp, const double* r, double* z)
     const uint64_t chunk = (p->n + (uint64_t)ctx->nranks - 1) / (uint64_t)ctx->nranks;
     const uint64_t npad = chunk * (uint64_t)ctx->nranks, nloc = p->r1 - p->r0;
     cplx* full = nullptr;
-    BEMB_CUDA(ctx, cudaMalloc((void**)&full, npad * sizeof(cplx)));
+    BEMB_CUDA(ctx, cudaMallocAsync((void**)&full, npad * sizeof(cplx), ctx->stream));
     cudaError_t e = cudaMemsetAsync(full, 0, npad * sizeof(cplx), ctx->stream);
     if (e == cudaSuccess && nloc)
         e = cudaMemcpyAsync(p->tmp, reinterpret_cast<const cplx*>(r) + p->r0, nloc * sizeof(cplx), cudaMemcpyHostToDevice, ctx->stream);
@@ -500,7 +501,7 @@ int bemb200_precond_apply(const bemb200_precond* cp, const double* r, double* z)
     if (e == cudaSuccess && ctx->nranks > 1) rc = nccl_allgather_bytes(ctx, full + p->r0, full, chunk * sizeof(cplx));
     if (e == cudaSuccess && rc == BEMB200_OK) e = cudaMemcpyAsync(z, full, p->n * sizeof(cplx), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(full);
+    cudaFreeAsync(full, ctx->stream);
     if (rc != BEMB200_OK) return rc;
     BEMB_CUDA(ctx, e);
     return BEMB200_OK;
