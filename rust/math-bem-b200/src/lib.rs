@@ -258,7 +258,7 @@ impl GpuSweep {
         let flat = flatten(elements, nodes)?;
         let mesh = flat.view();
         let mut h = std::ptr::null_mut();
-        let rc = unsafe { bemb200_sweep_create(device, 0, 1, std::ptr::null(), &mesh, 1, 1, &mut h) };
+        let rc = unsafe { bemb200_sweep_create(device, 0, 1, std::ptr::null(), &mesh, 1, 2, &mut h) };  // pipelined, 2 background blocks per SM
         if rc != 0 { return Err(last_error(std::ptr::null())); }
         let n = unsafe { bemb200_sweep_num_dofs(h) } as usize;
         Ok(Self { h, n })
@@ -269,6 +269,14 @@ impl GpuSweep {
         let phys = physics_of(physics);
         let rc = unsafe { bemb200_sweep_submit(self.h, &phys, beta.re, beta.im, contiguous(rhs_extra).as_ptr() as *const f64,
                                                config.max_iterations as u32, config.restart as u32, config.tolerance) };
+        if rc != 0 { return Err(last_error(std::ptr::null())); }
+        Ok(())
+    }
+    /// Solve the frequencies returned from now on with `gmres_preconditioned` + the block-Jacobi preconditioner
+    /// (`AdditiveSchwarzPreconditioner::from_csr(.., num_subdomains, 0)`, schwarz.rs:66) rebuilt from every frequency's matrix;
+    /// `0` switches back to plain `gmres`.
+    pub fn set_block_jacobi(&mut self, num_subdomains: usize) -> Result<(), String> {
+        let rc = unsafe { bemb200_sweep_set_block_jacobi(self.h, num_subdomains as u32, std::ptr::null(), std::ptr::null()) };
         if rc != 0 { return Err(last_error(std::ptr::null())); }
         Ok(())
     }
