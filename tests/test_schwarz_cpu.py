@@ -119,3 +119,32 @@ def test_partition_helpers():
     adj = [[j for j in (i - 1, i + 1) if 0 <= j < 12] for i in range(12)]
     for part, ov in [([0, 1, 2], 1), ([5, 6], 2), ([11], 3), ([3, 4], 0)]:
         assert np.array_equal(bem.extend_partition(part, adj, ov, 12).astype(np.int64), so.extend_partition(part, adj, ov, 12))
+
+
+def test_geometric_subdomains_are_rank_aligned_partitions():
+    """bem.spatial_subdomains / bem.voronoi_subdomains (host logic of the config-3 / config-4 block-Jacobi legs): every DOF in
+    exactly one cluster, no cluster across two ranks' row blocks, sizes bounded, deterministic, indices ascending."""
+    from math_audio_b200.mesh import generate_box_mesh_quad, generate_geodesic_sphere_mesh
+
+    for mesh, nranks, bs in [(generate_geodesic_sphere_mesh(1.0, 9), 4, 40), (generate_box_mesh_quad(0.32, 0.44, 0.64, 8, 11, 16), 2, 64),
+                             (generate_geodesic_sphere_mesh(0.1, 5), 8, 16)]:
+        n = mesh.num_dofs
+        chunk = (n + nranks - 1) // nranks
+        for fn in (bem.spatial_subdomains, bem.voronoi_subdomains):
+            parts = fn(mesh.center[:n], nranks, bs)
+            again = fn(mesh.center[:n], nranks, bs)
+            assert len(parts) == len(again) and all(np.array_equal(a, b) for a, b in zip(parts, again))
+            allidx = np.concatenate(parts).astype(np.int64)
+            assert np.array_equal(np.sort(allidx), np.arange(n))
+            for q in parts:
+                q = q.astype(np.int64)
+                assert len(q) >= 1 and np.all(np.diff(q) > 0)
+                assert q[0] // chunk == q[-1] // chunk
+            sizes = np.array([len(q) for q in parts])
+            assert sizes.max() <= (bs if fn is bem.spatial_subdomains else 3 * bs)
+            # compact: the mean cluster radius is a small multiple of the radius of a disc of the cluster's share of the surface
+            c = mesh.center[:n]
+            rad = np.mean([np.linalg.norm(c[q.astype(np.int64)] - c[q.astype(np.int64)].mean(axis=0), axis=1).max() for q in parts])
+            area = float(np.sum(mesh.area[:n])) if hasattr(mesh, "area") else None
+            if area:
+                assert rad < 3.0 * np.sqrt(area * sizes.mean() / n / np.pi)
