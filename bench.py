@@ -249,7 +249,7 @@ def run_reference(args):
     """Reference arm: the CPU restatement of the reference's path (`oracle/`, kind "port": the Rust
     reference cannot be built in this image) on all host threads.  Every timed step is a COMPLETE
     frequency of the workload (full assembly + GMRES to 1e-10), run back to back until --steps is
-    reached or the time budget (BENCH_REF_BUDGET_S, default 600 s) would be exceeded -- at least two.
+    reached or the time budget (BENCH_REF_BUDGET_S, default 300 s) would be exceeded -- at least two.
     `steps` of the line is the number of frequencies actually run; `value` is their mean wall time."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -258,7 +258,7 @@ def run_reference(args):
     n = wl["mesh"].num_dofs
     if 16.0 * n * n > 0.6 * (os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_PHYS_PAGES")):
         raise SystemExit(f"reference arm: the {16.0 * n * n / 1e9:.0f} GB matrix of {wl['name']} does not fit the host memory")
-    budget = float(os.environ.get("BENCH_REF_BUDGET_S", "600"))
+    budget = float(os.environ.get("BENCH_REF_BUDGET_S", "300"))
     t_begin = time.perf_counter()
     for s in range(args.warmup):  # warm-up: thread pool, page cache, libm -- a few rows only
         cpu_sample(wl, s, 0.5)
