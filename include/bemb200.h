@@ -194,7 +194,8 @@ int bemb200_matrix_diagonal(const bemb200_matrix* m, double* out);
  *   local numbering (the reference keeps them ascending, schwarz.rs:199-202); sets may overlap (weights 1 / multiplicity).
  * A subdomain holds at most 4096 unknowns.  On a row-sharded operator every rank passes the same subdomains and each must
  * lie inside one rank's row block (BEMB200_EINVAL otherwise): M^-1 then acts on a rank's slab without communication.
- * The handle is independent of the matrix after creation (it stores the inverse blocks). */
+ * The handle is independent of the matrix after creation (it stores the inverse blocks) but, like a matrix handle, belongs to
+ * the matrix's context: free it before bemb200_ctx_destroy (its device memory returns to the context's stream-ordered pool). */
 typedef struct bemb200_precond bemb200_precond;
 typedef struct bemb200_precond_stats {
     uint32_t num_subdomains;   /* stats() of schwarz.rs:135-158: count, min / max / average size */
