@@ -296,6 +296,39 @@ def run_reference(args):
     return 0
 
 
+def ride_along(name, fn, world, dev, wait_s=90.0):
+    """Run one side block (row-sharded parity, config 3 / 4 / 5) after the headline measurement: its failure must not take the
+    headline JSON line with it.  An exception becomes {"error": ...}.  With several ranks the outcome is agreed on with one
+    all-reduce; a rank that failed ALONE cannot be joined by the others (they sit in a collective of the block), so it waits
+    `wait_s` for them and then ends the job with a non-zero exit instead of leaving it hanging until the driver's limit."""
+    err = None
+    try:
+        out = fn()
+    except Exception as e:
+        import traceback
+
+        traceback.print_exc(file=sys.stderr)
+        err = f"{type(e).__name__}: {e}"
+        out = {"error": err}
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        flag = torch.tensor([1.0 if err else 0.0], device=dev)
+        work = dist.all_reduce(flag, op=dist.ReduceOp.MAX, async_op=True)
+        deadline = time.monotonic() + wait_s
+        while not work.is_completed():
+            if err and time.monotonic() > deadline:
+                print(f"bench.py: {name} failed on this rank only ({err}); the other ranks did not arrive within {wait_s:.0f} s",
+                      file=sys.stderr, flush=True)
+                os._exit(1)
+            time.sleep(0.005)
+        work.wait()
+        if float(flag.item()) > 0 and not err:
+            out = {"error": f"{name} failed on another rank", "this_rank": out}
+    return out
+
+
 def run_sharded_parity(ctx, rank, world, dev):
     """Row-sharded parity inside the bench job (the driver's scaling lease is the only place with several GPUs): the committed
     golden fixtures tests/golden/ico2_ka0p2.npz and ico2_ka6.npz (oracle matrix, right-hand side, GMRES solution and iteration
@@ -1000,7 +1033,7 @@ def run_native(args):
         print(f"isolated zgemv measurement failed: {e}", file=sys.stderr)
 
     # ---- row-sharded parity against the committed golden fixtures (several GPUs exist only in the driver's scaling lease)
-    sharded_parity = run_sharded_parity(ctx, rank, world, dev) if world > 1 else None
+    sharded_parity = ride_along("sharded_parity", lambda: run_sharded_parity(ctx, rank, world, dev), world, dev) if world > 1 else None
     # ---- 32 right-hand sides on the tensor-core block matvec (config 5) ride along on one GPU
     config5 = None
     if world == 1 and not os.environ.get("BENCH_NO_CONFIG5"):
@@ -1025,7 +1058,7 @@ def run_native(args):
             driver.buffers = [None, None]
         except Exception:
             pass
-        config3 = run_config3(ctx, rank, world, dev)
+        config3 = ride_along("config3", lambda: run_config3(ctx, rank, world, dev), world, dev)
     # ---- the north-star target (config 4) rides along whenever all 8 GPUs of the box are in the job
     config4 = None
     if (world >= 8 or os.environ.get("BENCH_CONFIG4")) and not os.environ.get("BENCH_NO_CONFIG4"):
@@ -1034,7 +1067,7 @@ def run_native(args):
             driver.buffers = [None, None]
         except Exception:
             pass
-        config4 = run_config4(ctx, rank, world, dev)
+        config4 = ride_along("config4", lambda: run_config4(ctx, rank, world, dev), world, dev)
 
     if rank != 0:
         if world > 1:

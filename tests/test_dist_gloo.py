@@ -84,3 +84,54 @@ def test_sharded_matvec_replicated_arnoldi_gloo(tmp_path, orc):
     j0, j1, js = (np.load(tmp_path / f) for f in ("infop_0.npy", "infop_1.npy", "infop_single.npy"))
     assert (p0 == p1).all() and (p0 == ps).all(), "row-sharded block-Jacobi differs from the global preconditioner"
     assert (j0 == j1).all() and (j0 == js).all() and j0[2] == 1 and j0[0] < i0[0]  # and it does precondition
+
+
+RIDE_ALONG_WORKER = r'''
+import json, os, sys
+sys.path.insert(0, os.environ["REPO_ROOT"])
+import torch
+from math_audio_b200 import dist as bdist
+import bench
+
+rank, world = bdist.init_process_group("gloo")
+dev = torch.device("cpu")
+def boom():
+    raise RuntimeError("golden file mismatch")
+res = {}
+# 1. nobody fails: the block comes back untouched
+res["ok"] = bench.ride_along("blk", lambda: {"v": rank}, world, dev)
+# 2. every rank fails the same way: every rank carries the error and goes on to print its line
+res["all"] = bench.ride_along("blk", boom, world, dev)
+# 3. rank 1 fails alone but rank 0 still arrives: rank 0 learns about it, its own block is kept beside the error
+res["one"] = bench.ride_along("blk", (boom if rank == 1 else (lambda: {"v": 0})), world, dev)
+json.dump(res, open(os.path.join(os.environ["OUT_DIR"], f"ride_{rank}.json"), "w"))
+# 4. rank 1 fails alone and rank 0 never arrives (it sits in a collective of the block): rank 1 ends the job after wait_s
+if rank == 1:
+    bench.ride_along("blk", boom, world, dev, wait_s=1.0)
+    sys.exit(0)  # not reached
+else:
+    import time
+    time.sleep(20)
+'''
+
+
+def test_bench_side_blocks_cannot_take_the_headline_line_with_them(tmp_path):
+    """bench.ride_along on 2 gloo ranks: errors become {"error": ...} on every rank (agreed with one all-reduce); a rank that
+    failed alone and is not joined within its time limit exits non-zero instead of hanging the job."""
+    worker = tmp_path / "ride.py"
+    worker.write_text(RIDE_ALONG_WORKER)
+    env = dict(os.environ, REPO_ROOT=str(ROOT), OUT_DIR=str(tmp_path), MASTER_ADDR="127.0.0.1", MASTER_PORT="29537",
+               WORLD_SIZE="2", OMP_NUM_THREADS="1")
+    procs = [subprocess.Popen([sys.executable, str(worker)], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)), stderr=subprocess.PIPE, text=True)
+             for r in range(2)]
+    err1 = procs[1].communicate(timeout=120)[1]
+    assert procs[1].returncode == 1 and "failed on this rank only" in err1
+    procs[0].kill()
+    procs[0].communicate()
+    import json
+
+    r0, r1 = (json.load(open(tmp_path / f"ride_{r}.json")) for r in range(2))
+    assert r0["ok"] == {"v": 0} and r1["ok"] == {"v": 1}
+    assert r0["all"] == r1["all"] == {"error": "RuntimeError: golden file mismatch"}
+    assert r1["one"] == {"error": "RuntimeError: golden file mismatch"}
+    assert r0["one"] == {"error": "blk failed on another rank", "this_rank": {"v": 0}}
