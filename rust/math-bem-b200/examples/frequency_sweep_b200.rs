@@ -10,7 +10,7 @@ use math_audio_bem::core::solver::fmm_interface::{solve_gmres, DenseOperator};
 use math_audio_bem::core::types::PhysicsParams;
 use math_audio_solvers::iterative::GmresConfig;
 use math_bem_b200::{build_tbem_system_gpu, GpuContext, GpuSweep};
-use ndarray::Array1;
+use ndarray::{Array1, Array2};
 use num_complex::Complex64;
 
 fn main() -> Result<(), String> {
@@ -19,8 +19,13 @@ fn main() -> Result<(), String> {
     let mesh = generate_icosphere_mesh(radius, 5);                       // 20 480 Tri3
     let config = GmresConfig { max_iterations: 1000, restart: 50, tolerance: 1e-10, print_interval: 0 };
     let frequencies: Vec<f64> = (0..64).map(|i| 136.5 * (32.0f64).powf(i as f64 / 63.0)).collect();
-    let centers: Vec<Array1<f64>> = mesh.elements.iter().map(|e| e.center.clone()).collect();
-    let normals: Vec<Array1<f64>> = mesh.elements.iter().map(|e| e.normal.clone()).collect();
+    // centers / normals as (n, 3) arrays, as in audio_frequency_sweep.rs:102-110
+    let n = mesh.elements.len();
+    let mut centers = Array2::<f64>::zeros((n, 3));
+    let mut normals = Array2::<f64>::zeros((n, 3));
+    for (i, e) in mesh.elements.iter().enumerate() {
+        for j in 0..3 { centers[[i, j]] = e.center[j]; normals[[i, j]] = e.normal[j]; }
+    }
     let case = |f: f64| {
         let physics = PhysicsParams::new(f, 343.0, 1.21, false);
         let (beta, _) = physics.burton_miller_beta_adaptive(radius);

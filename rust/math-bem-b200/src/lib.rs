@@ -20,7 +20,7 @@ use num_complex::Complex64;
 struct CtxInner(*mut bemb200_ctx);
 unsafe impl Send for CtxInner {}
 unsafe impl Sync for CtxInner {}
-impl Drop for CtxInner { fn drop(&mut self) { unsafe { bemb200_ctx_destroy(self.m) } } }
+impl Drop for CtxInner { fn drop(&mut self) { unsafe { bemb200_ctx_destroy(self.0) } } }
 #[derive(Clone)]
 pub struct GpuContext(Arc<CtxInner>);
 impl GpuContext {
@@ -30,7 +30,7 @@ impl GpuContext {
         if rc != 0 { return Err(last_error(std::ptr::null())); }
         Ok(Self(Arc::new(CtxInner(h))))
     }
-    fn raw(&self) -> *mut bemb200_ctx { (self.m).0 }
+    fn raw(&self) -> *mut bemb200_ctx { (self.0).0 }
     fn error(&self) -> String { last_error(self.raw()) }
 }
 

@@ -243,3 +243,43 @@ def test_binding_arities_match_the_header():
     lib_rs = (root / "rust" / "bem-b200-sys" / "src" / "lib.rs").read_text()
     for m in re.finditer(r"pub fn (bemb200_\w+)\(([^)]*)\)", lib_rs, flags=re.S):
         assert nargs(m.group(2)) == decl[m.group(1)], m.group(1)
+
+
+def test_rust_imports_resolve_to_public_items_of_the_reference():
+    """Every `use math_audio_{bem,solvers}::path::{Items}` of the safe crate and its example names a public item of the reference
+    source tree (this container only: /root/reference is absent on the GPU box).  No Rust compiler exists in this image, so this
+    is the nearest thing to name resolution the crates get."""
+    import re
+
+    ref = Path("/root/reference")
+    if not ref.exists():
+        pytest.skip("/root/reference is only present in the build container")
+    root = Path(__file__).resolve().parent.parent
+    src = (root / "rust" / "math-bem-b200" / "src" / "lib.rs").read_text() + (root / "rust" / "math-bem-b200" / "examples" / "frequency_sweep_b200.rs").read_text()
+    crates = {"math_audio_bem": ref / "math-bem" / "src", "math_audio_solvers": ref / "math-solvers" / "src"}
+    seen = 0
+    for m in re.finditer(r"\buse (math_audio_\w+)((?:::\w+)+)::(\{[^}]*\}|\w+);", src):
+        base = crates[m.group(1)]
+        mods = m.group(2).strip(":").split("::")
+        items = [i.strip() for i in m.group(3).strip("{}").split(",") if i.strip()]
+        cand = [base.joinpath(*mods).with_suffix(".rs"), base.joinpath(*mods) / "mod.rs"]
+        files = [c for c in cand if c.exists()]
+        assert files, (m.group(0), "no such module in the reference")
+        text = files[0].read_text()
+        for it in items:
+            public = re.search(rf"pub (?:fn|struct|enum|trait|type|const) {it}\b", text) or re.search(rf"pub use [^;]*\b{it}\b", text, flags=re.S)
+            assert public, (m.group(0), it)
+            seen += 1
+    assert seen >= 12
+    # the two reference calls the example makes with non-trivial argument types
+    inc = (ref / "math-bem" / "src" / "core" / "incident.rs").read_text()
+    sig = re.search(r"pub fn compute_rhs_with_beta\(\s*&self,\s*element_centers: &(\w+)<f64>,\s*element_normals: &(\w+)<f64>", inc)
+    assert sig and sig.group(1) == sig.group(2) == "Array2"
+    ex = (root / "rust" / "math-bem-b200" / "examples" / "frequency_sweep_b200.rs").read_text()
+    assert "Array2::<f64>::zeros((n, 3))" in ex and "Vec<Array1<f64>>" not in ex
+    # tuple structs are addressed by position
+    safe = (root / "rust" / "math-bem-b200" / "src" / "lib.rs").read_text()
+    for name in re.findall(r"struct (\w+)\([^)]*\);", safe):
+        body = re.findall(rf"impl(?: \w+ for)? {name} \{{.*?\n\}}|impl Drop for {name} \{{[^\n]*\}}", safe, flags=re.S)
+        for b in body:
+            assert not re.search(r"self\.[a-z_]+\b(?!\()", re.sub(r"self\.\d", "", b)) or name not in ("CtxInner", "GpuContext"), (name, b[:120])
