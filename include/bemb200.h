@@ -30,6 +30,7 @@ extern "C" {
 #define BEMB200_ENCCL (-5)      /* NCCL error / NCCL not loadable */
 #define BEMB200_EUNSUPPORTED (-6)
 #define BEMB200_ESINGULAR (-7)   /* LuError::SingularMatrix (math-solvers/src/direct/lu.rs:15-21) */
+#define BEMB200_ECALLBACK (-8)   /* a caller-supplied function (bemb200_precond_fn) reported failure */
 
 typedef struct bemb200_ctx bemb200_ctx;
 typedef struct bemb200_staged_mesh bemb200_staged_mesh;
@@ -217,6 +218,19 @@ int bemb200_precond_apply(const bemb200_precond* p, const double* r, double* z);
  * solve on the rank's slab, the exchange, one Gram-Schmidt kernel.  Arguments as bemb200_gmres_preconditioned. */
 int bemb200_gmres_schwarz(const bemb200_matrix* m, const bemb200_precond* precond, const double* b, const double* x0,
                           uint32_t max_iterations, uint32_t restart, double tolerance, double* x_out, bemb200_gmres_info* info);
+/* gmres_preconditioned_with_guess (gmres.rs:434-585) with ANY implementation of the reference's `Preconditioner` trait
+ * (math-solvers/src/traits.rs:366-371: `fn apply(&self, r: &Array1<T>) -> Array1<T>`) -- ILU, AMG, hierarchical, a caller's own.
+ * `apply(user, r, z, n)` must write z = M^-1 r (n complex128, interleaved, HOST memory owned by the library for the duration
+ * of the call) and return 0; any other value ends the solve with BEMB200_ECALLBACK.  The Arnoldi process (ZGEMV, Gram-Schmidt,
+ * update) stays on the device; one vector goes down and one comes up per application.  `apply` is called exactly where the
+ * reference calls `precond.apply`: once for M^-1 b, once per restart cycle for M^-1 (b - A x), once per Arnoldi step for
+ * M^-1 (A v_j) (`*precond_calls`, may be NULL, returns the count).  It runs on the calling thread with the context's lock
+ * held: it must not call into the same context.  Single-rank operators only (BEMB200_EUNSUPPORTED otherwise): the trait acts
+ * on whole vectors.  Other arguments as bemb200_gmres_preconditioned. */
+typedef int (*bemb200_precond_fn)(void* user, const double* r, double* z, uint64_t n);
+int bemb200_gmres_callback(const bemb200_matrix* m, bemb200_precond_fn apply, void* user, const double* b, const double* x0,
+                           uint32_t max_iterations, uint32_t restart, double tolerance, double* x_out, bemb200_gmres_info* info,
+                           uint64_t* precond_calls);
 /* same with DEVICE pointers (b_dev, x0_dev or NULL, x_dev) */
 int bemb200_gmres_device(const bemb200_matrix* m, const double* b_dev, const double* x0_dev, uint32_t max_iterations,
                          uint32_t restart, double tolerance, double* x_dev, bemb200_gmres_info* info);

@@ -22,9 +22,11 @@
 // Shape mismatches throw std::invalid_argument (the reference panics); library failures throw
 // bemb200::Error carrying the BEMB200_E* code and bemb200_last_error().
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <complex>
 #include <cstdint>
+#include <exception>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -454,6 +456,54 @@ inline GmresSolution gmres_preconditioned_with_guess(const DenseOperator& op, co
     return s;
 }
 inline GmresSolution gmres_preconditioned(const DenseOperator& op, const AdditiveSchwarzPreconditioner& p, const std::vector<Complex64>& b,
+                                          const GmresConfig& config) {  // gmres.rs:282
+    return gmres_preconditioned_with_guess(op, p, b, nullptr, config);
+}
+
+// Any other preconditioner: the reference's `Preconditioner` trait (traits.rs:366-371) as an abstract class.  `apply` runs on
+// the host (once for M^-1 b, once per restart cycle, once per Arnoldi step) while the Arnoldi process stays on the device
+// (bemb200_gmres_callback); an exception thrown by `apply` ends the solve and is rethrown to the caller.
+struct Preconditioner {
+    virtual ~Preconditioner() = default;
+    virtual std::vector<Complex64> apply(const std::vector<Complex64>& r) const = 0;
+};
+namespace detail {
+struct PrecondCall {
+    const Preconditioner* p;
+    std::exception_ptr error;
+};
+inline int precond_trampoline(void* user, const double* r, double* z, uint64_t n) noexcept {
+    auto* call = static_cast<PrecondCall*>(user);
+    try {
+        const auto* rc = reinterpret_cast<const Complex64*>(r);
+        std::vector<Complex64> out = call->p->apply(std::vector<Complex64>(rc, rc + n));
+        if (out.size() != n) throw std::invalid_argument("Preconditioner::apply: result has the wrong length");
+        std::copy(out.begin(), out.end(), reinterpret_cast<Complex64*>(z));
+        return 0;
+    } catch (...) {
+        call->error = std::current_exception();
+        return 1;
+    }
+}
+}  // namespace detail
+inline GmresSolution gmres_preconditioned_with_guess(const DenseOperator& op, const Preconditioner& p, const std::vector<Complex64>& b,
+                                                     const std::vector<Complex64>* x0, const GmresConfig& config) {  // gmres.rs:434
+    if (b.size() != op.num_rows() || (x0 && x0->size() != b.size()))
+        throw std::invalid_argument("gmres_preconditioned: vector lengths must match");
+    GmresSolution s;
+    s.x.resize(b.size());
+    bemb200_gmres_info info{};
+    detail::PrecondCall call{&p, nullptr};
+    const int rc = bemb200_gmres_callback(op.handle(), &detail::precond_trampoline, &call, reinterpret_cast<const double*>(b.data()),
+                                          x0 ? reinterpret_cast<const double*>(x0->data()) : nullptr,
+                                          static_cast<uint32_t>(config.max_iterations), static_cast<uint32_t>(config.restart),
+                                          config.tolerance, reinterpret_cast<double*>(s.x.data()), &info, nullptr);
+    if (call.error) std::rethrow_exception(call.error);
+    check(rc, op.context().handle());
+    s.iterations = info.iterations; s.restarts = info.restarts; s.residual = info.residual; s.converged = info.converged != 0;
+    return s;
+}
+inline GmresSolution gmres_preconditioned(const DenseOperator& op, const Preconditioner& p, const std::vector<Complex64>& b,
                                           const GmresConfig& config) {  // gmres.rs:282
     return gmres_preconditioned_with_guess(op, p, b, nullptr, config);
 }

@@ -14,7 +14,7 @@ _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "lib" / "libbemb200.so"
 
 OK = 0
-ERRORS = {-1: "EINVAL", -2: "ENODEVICE", -3: "ECUDA", -4: "ENOMEM", -5: "ENCCL", -6: "EUNSUPPORTED", -7: "ESINGULAR"}
+ERRORS = {-1: "EINVAL", -2: "ENODEVICE", -3: "ECUDA", -4: "ENOMEM", -5: "ENCCL", -6: "EUNSUPPORTED", -7: "ESINGULAR", -8: "ECALLBACK"}
 
 
 class Bemb200Error(RuntimeError):
@@ -59,6 +59,9 @@ class CRoomSource(C.Structure):
 # every symbol include/bemb200.h declares: (restype, argtypes)
 _VP = C.c_void_p
 _PP = C.POINTER(C.c_void_p)
+# bemb200_precond_fn: int apply(void* user, const double* r, double* z, uint64_t n)  (Preconditioner::apply, traits.rs:366-371)
+PRECOND_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_uint64)
+
 SYMBOLS = {
     "bemb200_device_count": (C.c_int, []),
     "bemb200_ctx_create": (C.c_int, [C.c_int, _PP]),
@@ -101,6 +104,8 @@ SYMBOLS = {
     "bemb200_precond_stats_get": (C.c_int, [_VP, C.POINTER(CPrecondStats)]),
     "bemb200_precond_apply": (C.c_int, [_VP, _VP, _VP]),
     "bemb200_gmres_schwarz": (C.c_int, [_VP, _VP, _VP, _VP, C.c_uint32, C.c_uint32, C.c_double, _VP, C.POINTER(CGmresInfo)]),
+    "bemb200_gmres_callback": (C.c_int, [_VP, PRECOND_FN, _VP, _VP, _VP, C.c_uint32, C.c_uint32, C.c_double, _VP, C.POINTER(CGmresInfo),
+                                         C.POINTER(C.c_uint64)]),
     "bemb200_gmres_device": (C.c_int, [_VP, _VP, _VP, C.c_uint32, C.c_uint32, C.c_double, _VP, C.POINTER(CGmresInfo)]),
     "bemb200_gmres_batched": (C.c_int, [_VP, _VP, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, _VP, C.POINTER(CGmresInfo),
                                         C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),

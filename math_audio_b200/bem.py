@@ -707,18 +707,57 @@ class AdditiveSchwarzPreconditioner:
             pass
 
 
+def _gmres_user_preconditioner(operator: "DenseOperator", precond, b: np.ndarray, x0a: Optional[np.ndarray],
+                               config: "GmresConfig") -> "GmresSolution":
+    """bemb200_gmres_callback: the caller's ``precond.apply`` behind a C function pointer.  An exception raised by
+    ``apply`` (or a result of the wrong shape) ends the solve (BEMB200_ECALLBACK) and is re-raised here."""
+    n = operator.num_rows()
+    failure = []
+
+    def trampoline(_user, r_ptr, z_ptr, nn):
+        try:
+            r = np.ctypeslib.as_array(r_ptr, shape=(2 * nn,)).view(np.complex128)
+            z = np.asarray(precond.apply(r.copy()), dtype=np.complex128)
+            if z.shape != (nn,):
+                raise ValueError(f"Preconditioner.apply returned shape {z.shape}, expected ({nn},)")
+            np.ctypeslib.as_array(z_ptr, shape=(2 * nn,)).view(np.complex128)[:] = z
+            return 0
+        except BaseException as e:  # never let an exception cross the C frames
+            failure.append(e)
+            return 1
+
+    cb = _capi.PRECOND_FN(trampoline)  # kept alive until the call has returned
+    x = np.empty(n, dtype=np.complex128)
+    info = _capi.CGmresInfo()
+    calls = C.c_uint64(0)
+    rc = _capi.lib().bemb200_gmres_callback(operator.matrix._h, cb, None, _capi.ptr(b), _capi.ptr(x0a) if x0a is not None else None,
+                                            config.max_iterations, config.restart, config.tolerance, _capi.ptr(x), C.byref(info),
+                                            C.byref(calls))
+    if failure:
+        raise failure[0]
+    _capi.check(rc, operator.matrix.ctx._h)
+    sol = GmresSolution(x=x, iterations=int(info.iterations), restarts=int(info.restarts), residual=float(info.residual),
+                        converged=bool(info.converged))
+    sol.preconditioner_calls = int(calls.value)
+    return sol
+
+
 def gmres_preconditioned_with_guess(operator: DenseOperator, precond, b: np.ndarray, x0: Optional[np.ndarray],
                                     config: GmresConfig) -> GmresSolution:
     """gmres.rs:434-585: left-preconditioned restarted GMRES on the device.  ``precond`` is an
     IdentityPreconditioner, a DiagonalPreconditioner or an AdditiveSchwarzPreconditioner (block-Jacobi) -- the
-    preconditioners of the reference that apply to a dense operator without an O(N^3) factorisation."""
-    if not isinstance(precond, (IdentityPreconditioner, DiagonalPreconditioner, AdditiveSchwarzPreconditioner)):
-        raise TypeError("the device solver supports IdentityPreconditioner, DiagonalPreconditioner and AdditiveSchwarzPreconditioner")
+    preconditioners of the reference that apply to a dense operator without an O(N^3) factorisation, applied on the
+    device -- or ANY other object with the trait's method ``apply(r) -> z`` (traits.rs:366-371), which is called on the
+    host once per application while the Arnoldi process stays on the device (bemb200_gmres_callback)."""
     b = np.ascontiguousarray(b, dtype=np.complex128)
     n = operator.num_rows()
     if b.shape != (n,):
         raise ValueError(f"gmres: b has shape {b.shape}, operator has {n} rows")
     x0a = np.ascontiguousarray(x0, dtype=np.complex128) if x0 is not None else None
+    if not isinstance(precond, (IdentityPreconditioner, DiagonalPreconditioner, AdditiveSchwarzPreconditioner)):
+        if not callable(getattr(precond, "apply", None)):
+            raise TypeError("precond must be one of the built-in preconditioners or implement apply(r) -> z (Preconditioner, traits.rs:366)")
+        return _gmres_user_preconditioner(operator, precond, b, x0a, config)
     if isinstance(precond, AdditiveSchwarzPreconditioner):
         x = np.empty(n, dtype=np.complex128)
         info = _capi.CGmresInfo()

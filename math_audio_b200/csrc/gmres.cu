@@ -335,6 +335,39 @@ static int schwarz_residual(bemb200_matrix* m, const bemb200_precond* sp, const 
     return norm_of(m, ws->w, nullptr, ws->r, out);  // r = M^-1 (b - A x), its norm
 }
 
+// ---- user preconditioner (bemb200_gmres_callback): Preconditioner::apply (traits.rs:366-371) supplied by the caller as a host
+// function.  The Arnoldi process stays on the device; only M^-1 makes the round trip through two pinned host vectors.
+struct UserPrecond {
+    bemb200_precond_fn fn = nullptr;
+    void* user = nullptr;
+    cplx* r_h = nullptr;  // pinned, n
+    cplx* z_h = nullptr;  // pinned, n
+    uint64_t calls = 0;
+};
+// dst (device, n) = M^-1 src (device, n); src == dst allowed.  Single rank only (checked by the entry point).
+static int user_full(bemb200_matrix* m, UserPrecond* up, const cplx* src, cplx* dst) {
+    bemb200_ctx* ctx = m->ctx;
+    const size_t nb = m->n_rows * sizeof(cplx);
+    BEMB_CUDA(ctx, cudaMemcpyAsync(up->r_h, src, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    BEMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    up->calls += 1;
+    const int urc = up->fn(up->user, reinterpret_cast<const double*>(up->r_h), reinterpret_cast<double*>(up->z_h), m->n_rows);
+    if (urc != 0) return set_error(ctx, BEMB200_ECALLBACK, "the preconditioner callback returned a non-zero code");
+    // z_h is not touched again before the next user_full has synchronised the stream, i.e. after this copy has completed
+    BEMB_CUDA(ctx, cudaMemcpyAsync(dst, up->z_h, nb, cudaMemcpyHostToDevice, ctx->stream));
+    return BEMB200_OK;
+}
+// r = M^-1 (b - A x) with A x in ws->w; *out = ||r||  (gmres.rs:473-476)
+static int user_residual(bemb200_matrix* m, UserPrecond* up, const cplx* b, double* out) {
+    bemb200_ctx* ctx = m->ctx;
+    GmresWorkspace* ws = m->ws;
+    BEMB_CUDA(ctx, launch_residual(b, ws->w, ws->r, m->n_rows, ws->scal_d, nullptr, ctx->stream));  // r = b - A x
+    m->last_launches += 1;
+    int rc = user_full(m, up, ws->r, ws->w);
+    if (rc != BEMB200_OK) return rc;
+    return norm_of(m, ws->w, nullptr, ws->r, out);  // r = M^-1 (b - A x), its norm
+}
+
 static int update_x(bemb200_matrix* m, cplx* x, const std::vector<cplx>& y) {
     bemb200_ctx* ctx = m->ctx;
     GmresWorkspace* ws = m->ws;
@@ -677,13 +710,14 @@ extern "C" void bemb200_debug_fused_times(double* total_ms, double* matvec_ms, d
 // `sp`: additive Schwarz / block-Jacobi preconditioner (schwarz.cu) instead of a diagonal one: M^-1 acts on the rank's slab of
 // A v between the ZGEMV and the exchange; the Gram-Schmidt kernel then sees an already preconditioned vector.
 static int gmres_core(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t max_iterations, uint32_t restart, double tol,
-                      bemb200_gmres_info* info, bool precond = false, const cplx* pinv = nullptr, const bemb200_precond* sp = nullptr) {
+                      bemb200_gmres_info* info, bool precond = false, const cplx* pinv = nullptr, const bemb200_precond* sp = nullptr,
+                      UserPrecond* up = nullptr) {
     bemb200_ctx* ctx = m->ctx;
     GmresWorkspace* ws = m->ws;
     const uint64_t n = m->n_rows;
     const int mm = (int)restart;
     cudaStream_t s = ctx->stream;
-    if (!sp) {
+    if (!sp && !up) {
         bool used = false;
         int frc = gmres_fused_solve(m, b, x, max_iterations, restart, tol, info, precond, pinv, &used);
         if (frc != BEMB200_OK || used) return frc;
@@ -692,6 +726,9 @@ static int gmres_core(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t max_it
     int rc = BEMB200_OK;
     if (sp) {
         rc = schwarz_full(m, sp, b, ws->w);  // M^-1 b
+        if (rc == BEMB200_OK) rc = norm_of(m, ws->w, nullptr, nullptr, &b_norm);
+    } else if (up) {
+        rc = user_full(m, up, b, ws->w);  // M^-1 b
         if (rc == BEMB200_OK) rc = norm_of(m, ws->w, nullptr, nullptr, &b_norm);
     } else {
         rc = norm_of(m, b, nullptr, nullptr, &b_norm, pinv);  // ||b|| resp. ||M^-1 b|| (gmres.rs:455-457)
@@ -728,7 +765,7 @@ static int gmres_core(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t max_it
         if (!every) ctx->px.ok = false;
         if (ctx->px.err_h) *ctx->px.err_h = 0;
     }
-    const bool peer_fused = !sp && allow_grid && ctx->nranks > 1 && ctx->px.ok && ctx->px.npad >= ws->npad && ws->npad == ws->chunk * (uint64_t)ctx->nranks &&
+    const bool peer_fused = !sp && !up && allow_grid && ctx->nranks > 1 && ctx->px.ok && ctx->px.npad >= ws->npad && ws->npad == ws->chunk * (uint64_t)ctx->nranks &&
                             mgs_peer_wait_capable(n, restart, allow_grid);
     static const unsigned long long peer_timeout_ns = []() {
         const char* v = std::getenv("BEMB200_PEER_TIMEOUT_MS");
@@ -743,7 +780,7 @@ static int gmres_core(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t max_it
         rc = matvec(m, x, ws->w, true);
         if (rc != BEMB200_OK) return rc;
         double beta = 0.0;
-        rc = sp ? schwarz_residual(m, sp, b, &beta) : norm_of(m, b, ws->w, ws->r, &beta, pinv);
+        rc = sp ? schwarz_residual(m, sp, b, &beta) : (up ? user_residual(m, up, b, &beta) : norm_of(m, b, ws->w, ws->r, &beta, pinv));
         if (rc != BEMB200_OK) return rc;
         accumulate_matvec_time(m);
         double rel = beta / b_norm;
@@ -791,6 +828,10 @@ static int gmres_core(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t max_it
                     BEMB_CUDA(ctx, schwarz_apply_local(sp, sp->tmp, yloc, s));
                     m->last_launches += schwarz_apply_launches(sp);
                 }
+                if (up) {  // w = M^-1 (A v_j) through the caller's function (host round trip of one vector)
+                    int rc3 = user_full(m, up, yloc, yloc);
+                    if (rc3 != BEMB200_OK) return rc3;
+                }
                 if (ctx->nranks > 1) {
                     int rc2 = nccl_allgather_bytes(ctx, yloc, ws->w, ws->chunk * sizeof(cplx));
                     if (rc2 != BEMB200_OK) return rc2;
@@ -818,7 +859,7 @@ static int gmres_core(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t max_it
                 rc = enqueue_iteration(j);
                 if (rc != BEMB200_OK) return rc;
             }
-            if (g_speculate && j + 1 < mm && !ws->launched[j + 1]) {
+            if (g_speculate && !up && j + 1 < mm && !ws->launched[j + 1]) {
                 rc = enqueue_iteration(j + 1);
                 if (rc != BEMB200_OK) return rc;
             }
@@ -885,7 +926,7 @@ static int gmres_core(bemb200_matrix* m, const cplx* b, cplx* x, uint32_t max_it
     rc = matvec(m, x, ws->w, true);
     if (rc != BEMB200_OK) return rc;
     double rn = 0.0;
-    rc = sp ? schwarz_residual(m, sp, b, &rn) : norm_of(m, b, ws->w, ws->r, &rn, pinv);
+    rc = sp ? schwarz_residual(m, sp, b, &rn) : (up ? user_residual(m, up, b, &rn) : norm_of(m, b, ws->w, ws->r, &rn, pinv));
     if (rc != BEMB200_OK) return rc;
     accumulate_matvec_time(m);
     *info = bemb200_gmres_info{total_iterations, restarts, rn / b_norm, 0};
@@ -1273,6 +1314,52 @@ int bemb200_gmres_schwarz(const bemb200_matrix* cm, const bemb200_precond* preco
     else BEMB_CUDA(ctx, cudaMemsetAsync(ws->xout, 0, nb, ctx->stream));
     rc = gmres_core(m, ws->bin, ws->xout, max_iterations, restart, tolerance, info, true, nullptr, precond);
     if (rc != BEMB200_OK) return rc;
+    BEMB_CUDA(ctx, cudaMemcpyAsync(x_out, ws->xout, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    BEMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BEMB200_OK;
+}
+
+int bemb200_gmres_callback(const bemb200_matrix* cm, bemb200_precond_fn apply, void* user, const double* b, const double* x0,
+                           uint32_t max_iterations, uint32_t restart, double tolerance, double* x_out, bemb200_gmres_info* info,
+                           uint64_t* precond_calls) {
+    bemb200_matrix* m = const_cast<bemb200_matrix*>(cm);
+    if (!m || !apply || !b || !x_out || !info) return set_error(nullptr, BEMB200_EINVAL, "NULL argument");
+    bemb200_ctx* ctx = m->ctx;
+    if (m->n_rows != m->n_cols) return set_error(ctx, BEMB200_EINVAL, "gmres needs a square operator");
+    if (restart == 0) return set_error(ctx, BEMB200_EINVAL, "restart must be >= 1");
+    if (ctx->nranks != 1 || m->r0 != 0 || m->r1 != m->n_rows)
+        return set_error(ctx, BEMB200_EUNSUPPORTED, "bemb200_gmres_callback: a host preconditioner acts on whole vectors -- single-rank operators only");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    BEMB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = check_partition(m);
+    if (rc != BEMB200_OK) return rc;
+    rc = ensure_workspace(m, restart);
+    if (rc != BEMB200_OK) return rc;
+    reset_stats(m);
+    GmresWorkspace* ws = m->ws;
+    const size_t nb = m->n_rows * sizeof(cplx);
+    struct Pinned {  // the two host vectors of the round trip
+        cplx* p = nullptr;
+        ~Pinned() { if (p) cudaFreeHost(p); }
+    } rbuf, zbuf;
+    if (cudaMallocHost((void**)&rbuf.p, nb ? nb : sizeof(cplx)) != cudaSuccess || cudaMallocHost((void**)&zbuf.p, nb ? nb : sizeof(cplx)) != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(ctx, BEMB200_ENOMEM, "pinned host vectors for the preconditioner callback");
+    }
+    UserPrecond up;
+    up.fn = apply;
+    up.user = user;
+    up.r_h = rbuf.p;
+    up.z_h = zbuf.p;
+    BEMB_CUDA(ctx, cudaMemcpyAsync(ws->bin, b, nb, cudaMemcpyHostToDevice, ctx->stream));
+    if (x0) BEMB_CUDA(ctx, cudaMemcpyAsync(ws->xout, x0, nb, cudaMemcpyHostToDevice, ctx->stream));
+    else BEMB_CUDA(ctx, cudaMemsetAsync(ws->xout, 0, nb, ctx->stream));
+    rc = gmres_core(m, ws->bin, ws->xout, max_iterations, restart, tolerance, info, true, nullptr, nullptr, &up);
+    if (precond_calls) *precond_calls = up.calls;
+    if (rc != BEMB200_OK) {
+        cudaStreamSynchronize(ctx->stream);  // nothing of this solve may still be reading the pinned vectors when they go
+        return rc;
+    }
     BEMB_CUDA(ctx, cudaMemcpyAsync(x_out, ws->xout, nb, cudaMemcpyDeviceToHost, ctx->stream));
     BEMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return BEMB200_OK;

@@ -30,6 +30,8 @@ pub struct bemb200_mesh {
 }
 #[repr(C)] #[derive(Clone, Copy)]
 pub struct bemb200_physics { pub wave_number: f64, pub harmonic_factor: f64, pub tau: f64, pub gamma: f64 }
+/// `int apply(void* user, const double* r, double* z, uint64_t n)`: z = M^-1 r on host memory, 0 = success (`Preconditioner::apply`).
+pub type bemb200_precond_fn = Option<unsafe extern "C" fn(user: *mut c_void, r: *const f64, z: *mut f64, n: u64) -> c_int>;
 #[repr(C)] #[derive(Clone, Copy, Default)]
 pub struct bemb200_gmres_info { pub iterations: u64, pub restarts: u64, pub residual: f64, pub converged: i32 }
 
@@ -83,6 +85,10 @@ extern "C" {
     pub fn bemb200_gmres_schwarz(m: *const bemb200_matrix, precond: *const bemb200_precond, b: *const f64, x0: *const f64,
                                  max_iterations: u32, restart: u32, tolerance: f64, x_out: *mut f64,
                                  info: *mut bemb200_gmres_info) -> c_int;
+    // gmres_preconditioned with a caller-supplied Preconditioner (host function), Arnoldi process on the device
+    pub fn bemb200_gmres_callback(m: *const bemb200_matrix, apply: bemb200_precond_fn, user: *mut c_void, b: *const f64, x0: *const f64,
+                                  max_iterations: u32, restart: u32, tolerance: f64, x_out: *mut f64, info: *mut bemb200_gmres_info,
+                                  precond_calls: *mut u64) -> c_int;
     pub fn bemb200_gmres_batched(m: *const bemb200_matrix, b_all: *const f64, nrhs: u32, max_iterations: u32, restart: u32,
                                  tolerance: f64, x_all: *mut f64, infos: *mut bemb200_gmres_info, block_matvec_ms: *mut f64,
                                  block_matvecs: *mut u64) -> c_int;

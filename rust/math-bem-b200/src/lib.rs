@@ -11,7 +11,7 @@ use std::sync::Arc;
 use bem_b200_sys::*;
 use math_audio_bem::core::types::{BoundaryCondition, Element, ElementType, PhysicsParams};
 use math_audio_solvers::iterative::{BiCgstabConfig, BiCgstabSolution, CgsConfig, CgsSolution, GmresConfig, GmresSolution};
-use math_audio_solvers::traits::LinearOperator;
+use math_audio_solvers::traits::{LinearOperator, Preconditioner};
 use ndarray::{Array1, Array2};
 use num_complex::Complex64;
 
@@ -131,6 +131,38 @@ impl GpuDenseOperator {
                                                 config.max_iterations as u32, config.restart as u32, config.tolerance,
                                                 x.as_mut_ptr() as *mut f64, &mut info) };
         unsafe { bemb200_precond_free(p) };
+        if rc != 0 { return Err(self.ctx.error()); }
+        Ok(GmresSolution { x, iterations: info.iterations as usize, restarts: info.restarts as usize,
+                           residual: info.residual, converged: info.converged != 0 })
+    }
+    /// `gmres_preconditioned(operator, precond, b, config)` (gmres.rs:282) with ANY implementation of the reference's
+    /// `Preconditioner` trait (traits.rs:366-371) -- ILU, AMG, hierarchical, the caller's own: `precond.apply` runs on the host
+    /// exactly where the reference calls it while the Arnoldi process stays on the device (`bemb200_gmres_callback`).  A panic
+    /// inside `apply` (or a result of the wrong length) ends the solve with `Err`.  Single-GPU operators only.
+    pub fn gmres_preconditioned_with<P: Preconditioner<Complex64>>(&self, precond: &P, b: &Array1<Complex64>,
+                                                                   config: &GmresConfig<f64>) -> Result<GmresSolution<Complex64>, String> {
+        unsafe extern "C" fn trampoline<P: Preconditioner<Complex64>>(user: *mut std::os::raw::c_void, r: *const f64, z: *mut f64,
+                                                                      n: u64) -> std::os::raw::c_int {
+            let n = n as usize;
+            let precond = &*(user as *const P);
+            let r = Array1::from(std::slice::from_raw_parts(r as *const Complex64, n).to_vec());
+            // unwinding must not cross the C frames
+            match std::panic::catch_unwind(std::panic::AssertUnwindSafe(|| precond.apply(&r))) {
+                Ok(out) if out.len() == n => {
+                    let dst = std::slice::from_raw_parts_mut(z as *mut Complex64, n);
+                    for (d, s) in dst.iter_mut().zip(out.iter()) { *d = *s; }
+                    0
+                }
+                _ => 1,
+            }
+        }
+        assert_eq!(b.len(), self.num_rows(), "Vector lengths must match");
+        let mut x = Array1::<Complex64>::zeros(b.len());
+        let mut info = bemb200_gmres_info::default();
+        let rc = unsafe { bemb200_gmres_callback(self.m, Some(trampoline::<P>), precond as *const P as *mut std::os::raw::c_void,
+                                                 contiguous(b).as_ptr() as *const f64, std::ptr::null(), config.max_iterations as u32,
+                                                 config.restart as u32, config.tolerance, x.as_mut_ptr() as *mut f64, &mut info,
+                                                 std::ptr::null_mut()) };
         if rc != 0 { return Err(self.ctx.error()); }
         Ok(GmresSolution { x, iterations: info.iterations as usize, restarts: info.restarts as usize,
                            residual: info.residual, converged: info.converged != 0 })
