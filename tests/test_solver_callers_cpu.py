@@ -146,3 +146,95 @@ def test_field_point_and_eval_point_generators():
     assert plane.shape == (25, 3) and np.all(np.abs(plane[:, 2]) < 1e-10)
     tilted = pp.generate_plane_eval_points([1.0, 1.0, 1.0], [2.0, 0.0, 0.0], 0.5, 3)          # |n.x| >= 0.9 branch
     assert np.allclose(tilted[:, 0], 1.0) and np.allclose(tilted.mean(axis=0), [1.0, 1.0, 1.0])
+
+
+# ---- user Preconditioner behind bemb200_precond_fn: the Python trampoline, driven by a stand-in for the C side -------------------
+def test_user_preconditioner_trampoline_marshals_vectors_and_exceptions(monkeypatch, orc):
+    """`gmres_preconditioned(op, any_object_with_apply, ...)` hands `apply` to the library as a C function pointer.  Here the
+    library call is replaced by a host stand-in with the same signature that runs the oracle's preconditioned GMRES and calls the
+    function pointer exactly as csrc/gmres.cu does (pointers to interleaved doubles, n, return code): the trampoline must
+    marshal r and z correctly, count calls, and carry exceptions out of the C frames."""
+    import ctypes as C
+
+    from math_audio_b200 import _capi, bem
+
+    rng = np.random.default_rng(5)
+    n = 40
+    A = np.eye(n) * 4.0 + 0.3 * (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)))
+    b = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+
+    class FakeLib:
+        def bemb200_gmres_callback(self, mh, cb, user, b_ptr, x0_ptr, max_iterations, restart, tol, x_ptr, info_ref, calls_ref):
+            bb = np.ctypeslib.as_array(C.cast(b_ptr, C.POINTER(C.c_double)), shape=(2 * n,)).view(np.complex128)
+            rbuf, zbuf = (C.c_double * (2 * n))(), (C.c_double * (2 * n))()
+            state = {"calls": 0, "rc": 0}
+
+            def precond(r):
+                if state["rc"]:  # the real library stops at the first failure; the oracle's loop cannot be left from a callback
+                    return np.zeros_like(r)
+                np.frombuffer(rbuf, dtype=np.complex128)[:] = r
+                state["calls"] += 1
+                rc = cb(user, C.cast(rbuf, C.POINTER(C.c_double)), C.cast(zbuf, C.POINTER(C.c_double)), n)
+                if rc != 0:
+                    state["rc"] = rc
+                    return np.zeros_like(r)
+                return np.frombuffer(zbuf, dtype=np.complex128).copy()
+
+            x, info = orc.gmres_preconditioned_cb(lambda v: A @ v, precond, n, bb.copy(), max_iterations=max_iterations,
+                                                  restart=restart, tolerance=tol)
+            if state["rc"]:
+                C.cast(calls_ref, C.POINTER(C.c_uint64))[0] = state["calls"]
+                return -8
+            np.ctypeslib.as_array(C.cast(x_ptr, C.POINTER(C.c_double)), shape=(2 * n,)).view(np.complex128)[:] = x
+            inf = C.cast(info_ref, C.POINTER(_capi.CGmresInfo))[0]
+            inf.iterations, inf.restarts, inf.residual, inf.converged = info["iterations"], info["restarts"], info["residual"], int(info["converged"])
+            C.cast(calls_ref, C.POINTER(C.c_uint64))[0] = state["calls"]
+            return 0
+
+        def bemb200_last_error(self, ctx):
+            return b"the preconditioner callback returned a non-zero code"
+
+    class FakeMatrix:
+        _h = None
+        shape = (n, n)
+
+        class ctx:
+            _h = None
+
+    op = bem.DenseOperator.__new__(bem.DenseOperator)
+    op.matrix = FakeMatrix()
+    monkeypatch.setattr(_capi, "lib", lambda: FakeLib())
+
+    class Jacobi:
+        def __init__(self):
+            self.seen = 0
+
+        def apply(self, r):
+            assert r.dtype == np.complex128 and r.shape == (n,)
+            self.seen += 1
+            return r / np.diag(A)
+
+    jac = Jacobi()
+    cfg = bem.GmresConfig(max_iterations=50, restart=7, tolerance=1e-12)
+    sol = bem.gmres_preconditioned(op, jac, b, cfg)
+    xo, io = orc.gmres_preconditioned_cb(lambda v: A @ v, lambda r: r / np.diag(A), n, b, max_iterations=50, restart=7, tolerance=1e-12)
+    assert sol.converged and sol.iterations == io["iterations"] and sol.restarts == io["restarts"]
+    assert np.array_equal(sol.x, xo)
+    assert jac.seen == sol.preconditioner_calls == sol.iterations + sol.restarts + 2
+    assert np.linalg.norm(A @ sol.x - b) / np.linalg.norm(b) < 1e-10
+
+    class Boom:
+        def apply(self, r):
+            raise KeyError("user preconditioner failed")
+
+    with pytest.raises(KeyError):
+        bem.gmres_preconditioned(op, Boom(), b, cfg)
+
+    class Short:
+        def apply(self, r):
+            return r[:-1]
+
+    with pytest.raises(ValueError):
+        bem.gmres_preconditioned(op, Short(), b, cfg)
+    with pytest.raises(TypeError):
+        bem.gmres_preconditioned(op, object(), b, cfg)
