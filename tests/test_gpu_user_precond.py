@@ -1,8 +1,6 @@
 """gmres_preconditioned with a caller-supplied `Preconditioner` (math-solvers/src/traits.rs:366-371) behind the C ABI:
-bemb200_gmres_callback.  The check runs in its own process (tests/drivers/user_precond.py).
-
-Written after this round's GPU minutes were spent: the first execution on hardware is the driver's, hence the non-strict
-xfail marker -- drop it once a green run is on record."""
+bemb200_gmres_callback.  The check runs in its own process (tests/drivers/user_precond.py: a caller's Python code runs inside a
+library call there); first green run on a B200: profiles/r02zz_user_precond.json."""
 import json
 import subprocess
 import sys
@@ -14,7 +12,6 @@ ROOT = Path(__file__).resolve().parent.parent
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="first hardware run of bemb200_gmres_callback (added without GPU access)")
 def test_gmres_with_user_preconditioner_callback():
     p = subprocess.run([sys.executable, str(ROOT / "tests" / "drivers" / "user_precond.py")], capture_output=True, text=True, timeout=240)
     assert p.returncode == 0, p.stderr[-3000:]
