@@ -30,3 +30,27 @@ def test_gmres_with_user_preconditioner_callback():
     assert out["exception"] == "KeyError: user preconditioner failed" and out["wrong_shape"] == "ValueError"
     assert out["after_failure"]["converged"] and out["after_failure"]["true_residual"] < 1e-8
     assert out["rc_on_nonzero_return"] == -8                          # BEMB200_ECALLBACK
+
+
+def _build_cpp(tmp_path):
+    from math_audio_b200 import _capi
+
+    exe = tmp_path / "test_user_precond"
+    libdir = _capi.LIB_PATH.parent
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-I", str(ROOT / "include"), str(ROOT / "tests" / "cpp" / "test_user_precond.cpp"), "-o", str(exe),
+           f"-L{libdir}", "-lbemb200", f"-Wl,-rpath,{libdir}", "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"]
+    subprocess.run(cmd, check=True)
+    return exe
+
+
+def test_cpp_user_preconditioner_compiles(tmp_path):
+    assert _build_cpp(tmp_path).exists()
+
+
+@pytest.mark.gpu
+def test_cpp_user_preconditioner_on_gpu(tmp_path):
+    """bemb200::Preconditioner (include/bemb200.hpp) on the device solver.  The Python wrapper of the same C entry is green on a
+    B200 (profiles/r02zz_user_precond.json); this C++ twin was added after the round's GPU minutes were spent, so its first
+    hardware run is the driver's."""
+    out = subprocess.run([str(_build_cpp(tmp_path))], capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0 and "PASS" in out.stdout, out.stdout + out.stderr
