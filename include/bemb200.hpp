@@ -273,6 +273,27 @@ public:
         const bemb200_mesh mesh = soa.view(nodes);
         check(bemb200_mesh_stage(ctx.handle(), &mesh, &h_), ctx.handle());
         num_dofs_ = soa.ndof;
+        // DOF address of the j-th non-evaluation element; left empty for the sequential map of every generator
+        bool sequential = true;
+        std::vector<uint32_t> map;
+        std::vector<uint8_t> seen(soa.ndof, 0);
+        bool permutation = true;
+        for (std::size_t i = 0; i < soa.n_elem; ++i) {
+            if (soa.is_eval[i]) continue;
+            const uint32_t d = soa.dof[i];
+            sequential = sequential && d == map.size();
+            if (d >= soa.ndof || seen[d]) permutation = false; else seen[d] = 1;
+            map.push_back(d);
+        }
+        if (!sequential && permutation) enum_to_dof_ = std::move(map);
+    }
+    // A surface vector as the reference takes it (entry j belongs to the j-th non-evaluation element, pressure.rs:96-113,
+    // 452-458) re-addressed to the DOF order of the C ABI; the identity for sequential DOF maps.
+    std::vector<Complex64> in_dof_order(const std::vector<Complex64>& values) const {
+        if (enum_to_dof_.empty()) return values;
+        std::vector<Complex64> out(values.size());
+        for (std::size_t j = 0; j < values.size(); ++j) out[enum_to_dof_[j]] = values[j];
+        return out;
     }
     ~StagedMesh() { bemb200_staged_mesh_free(h_); }
     StagedMesh(const StagedMesh&) = delete;
@@ -286,6 +307,7 @@ private:
     const Context* ctx_;
     bemb200_staged_mesh* h_ = nullptr;
     std::size_t num_dofs_ = 0;
+    std::vector<uint32_t> enum_to_dof_;
 };
 // build_tbem_system_with_beta on a staged mesh (all rows)
 inline TbemSystem build_tbem_system_with_beta(const StagedMesh& mesh, const PhysicsParams& physics, Complex64 beta) {
@@ -638,8 +660,9 @@ inline std::vector<Complex64> compute_scattered_field(const StagedMesh& mesh, co
         throw std::invalid_argument("compute_scattered_field: surface vectors must have num_dofs entries");
     const bemb200_physics phys = physics_abi(physics);
     std::vector<Complex64> out(eval_points.size() / 3);
-    check(bemb200_scattered_field(mesh.handle(), &phys, out.size(), eval_points.data(), reinterpret_cast<const double*>(surface_pressure.data()),
-                                  surface_velocity.empty() ? nullptr : reinterpret_cast<const double*>(surface_velocity.data()),
+    const std::vector<Complex64> ps = mesh.in_dof_order(surface_pressure), vs = mesh.in_dof_order(surface_velocity);
+    check(bemb200_scattered_field(mesh.handle(), &phys, out.size(), eval_points.data(), reinterpret_cast<const double*>(ps.data()),
+                                  vs.empty() ? nullptr : reinterpret_cast<const double*>(vs.data()),
                                   reinterpret_cast<double*>(out.data())),
           mesh.context().handle());
     return out;
@@ -651,8 +674,9 @@ inline std::vector<double> compute_rcs(const StagedMesh& mesh, const std::vector
     if (surface_pressure.size() != mesh.num_dofs()) throw std::invalid_argument("compute_rcs: surface_pressure must have num_dofs entries");
     const bemb200_physics phys = physics_abi(physics);
     std::vector<double> out(directions.size() / 3);
+    const std::vector<Complex64> ps = mesh.in_dof_order(surface_pressure);  // entry j <-> j-th non-evaluation element
     check(bemb200_compute_rcs(mesh.handle(), &phys, static_cast<uint32_t>(out.size()), directions.data(),
-                              reinterpret_cast<const double*>(surface_pressure.data()), out.data()),
+                              reinterpret_cast<const double*>(ps.data()), out.data()),
           mesh.context().handle());
     return out;
 }

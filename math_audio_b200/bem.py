@@ -183,6 +183,29 @@ def default_context() -> Context:
     return _default_ctx
 
 
+def enumeration_to_dof(mesh: Mesh) -> Optional[np.ndarray]:
+    """DOF address of the j-th non-evaluation element, or None when that is j itself (every generator's sequential map).
+    The reference pairs entry j of a surface vector with the j-th non-evaluation element (postprocess/pressure.rs:96-113,
+    452-458); the device kernels pair an element with the entry at its DOF address (the C ABI's contract, include/bemb200.h)."""
+    dof = np.asarray(mesh.dof, dtype=np.int64)[np.asarray(mesh.is_eval) == 0]
+    if np.array_equal(dof, np.arange(dof.size)):
+        return None
+    if not np.array_equal(np.sort(dof), np.arange(dof.size)):
+        return None  # not a permutation of 0..num_dofs-1: bemb200_mesh_stage has the say on such a mesh
+    return dof
+
+
+def surface_values_in_dof_order(enum_to_dof: Optional[np.ndarray], values: np.ndarray) -> np.ndarray:
+    """Re-address a surface vector given as the reference takes it (entry j belongs to the j-th non-evaluation element) to the
+    DOF order of the C ABI.  The pairing of values and elements -- including what it does to a solution vector of a mesh with
+    a permuted DOF map -- is then the reference's."""
+    if enum_to_dof is None:
+        return values
+    out = np.empty_like(values)
+    out[enum_to_dof] = values
+    return out
+
+
 class StagedMesh:
     """Frequency-independent device copy of a mesh (reused across a sweep)."""
 
@@ -194,6 +217,7 @@ class StagedMesh:
         _capi.check(self._lib.bemb200_mesh_stage(self.ctx._h, C.byref(cm), C.byref(self._h)), self.ctx._h)
         self.num_dofs = int(self._lib.bemb200_staged_num_dofs(self._h))
         self.nbytes_host = _capi.mesh_nbytes(mesh)
+        self.enum_to_dof = enumeration_to_dof(mesh)
 
     def dg_dn_sign(self, wave_number: float) -> float:
         return float(self._lib.bemb200_dg_dn_sign(self._h, wave_number))
@@ -473,16 +497,19 @@ def incident_rhs_device(staged: StagedMesh, physics: PhysicsParams, beta: comple
 
 def compute_scattered_field(eval_points: np.ndarray, staged: StagedMesh, surface_pressure: np.ndarray,
                             surface_velocity: Optional[np.ndarray], physics: PhysicsParams) -> np.ndarray:
-    """postprocess/pressure.rs:81-137 on the device (surface values in DOF order)."""
+    """postprocess/pressure.rs:81-137 on the device.  Surface values as the reference takes them: entry j belongs to the j-th
+    non-evaluation element (re-addressed to the ABI's DOF order here when the mesh has a permuted DOF map)."""
     pts = np.ascontiguousarray(eval_points, dtype=np.float64).reshape(-1, 3)
     ps = np.ascontiguousarray(surface_pressure, dtype=np.complex128)
     if ps.shape != (staged.num_dofs,):
         raise ValueError("surface_pressure must have num_dofs entries")
+    ps = surface_values_in_dof_order(staged.enum_to_dof, ps)
     vs = None
     if surface_velocity is not None:
         vs = np.ascontiguousarray(surface_velocity, dtype=np.complex128)
         if vs.shape != (staged.num_dofs,):
             raise ValueError("surface_velocity must have num_dofs entries")
+        vs = surface_values_in_dof_order(staged.enum_to_dof, vs)
     out = np.empty(pts.shape[0], dtype=np.complex128)
     ph = _cphys(physics)
     _capi.check(_capi.lib().bemb200_scattered_field(staged._h, C.byref(ph), pts.shape[0], _capi.ptr(pts), _capi.ptr(ps),
@@ -496,6 +523,7 @@ def compute_rcs(surface_pressure: np.ndarray, staged: StagedMesh, direction, phy
     ps = np.ascontiguousarray(surface_pressure, dtype=np.complex128)
     if ps.shape != (staged.num_dofs,):
         raise ValueError("surface_pressure must have num_dofs entries")
+    ps = surface_values_in_dof_order(staged.enum_to_dof, ps)  # entry j belongs to the j-th non-evaluation element (pressure.rs:452-458)
     d = np.ascontiguousarray(direction, dtype=np.float64)
     single = d.ndim == 1
     d = d.reshape(-1, 3)

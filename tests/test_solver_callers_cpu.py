@@ -238,3 +238,50 @@ def test_user_preconditioner_trampoline_marshals_vectors_and_exceptions(monkeypa
         bem.gmres_preconditioned(op, Short(), b, cfg)
     with pytest.raises(TypeError):
         bem.gmres_preconditioned(op, object(), b, cfg)
+
+
+# ---- surface vectors of a mesh with a permuted DOF map: enumeration order (reference) -> DOF order (C ABI) ------------------------
+def test_surface_values_are_paired_with_elements_as_the_reference_pairs_them(orc):
+    """postprocess/pressure.rs:96-113, 452-458 pair entry j of a surface vector with the j-th non-evaluation element; the device
+    kernels walk the staged mesh in DOF order and pair an element with the entry at its DOF address.  The host wrappers
+    re-address the vector (bem.surface_values_in_dof_order).  Checked with the oracle alone: evaluating the permuted mesh with
+    the caller's vector == evaluating the DOF-sorted, sequentially numbered mesh (what the device walks) with the re-addressed
+    vector -- field and RCS, with evaluation-only elements in between."""
+    import dataclasses
+
+    from math_audio_b200 import bem
+    from math_audio_b200.mesh import generate_icosphere_mesh
+
+    mesh = generate_icosphere_mesh(0.1, 1)  # 80 Tri3
+    assert bem.enumeration_to_dof(mesh) is None  # generators number sequentially: nothing to do
+    rng = np.random.default_rng(11)
+    mesh.is_eval[::9] = 1
+    nd = mesh.num_dofs
+    bnd = np.flatnonzero(mesh.is_eval == 0)
+    mesh.dof[bnd] = rng.permutation(nd).astype(np.uint32)
+    e2d = bem.enumeration_to_dof(mesh)
+    assert e2d is not None and np.array_equal(e2d, mesh.dof[bnd])
+    p = rng.standard_normal(nd) + 1j * rng.standard_normal(nd)
+    v = rng.standard_normal(nd) + 1j * rng.standard_normal(nd)
+    p_dof, v_dof = bem.surface_values_in_dof_order(e2d, p), bem.surface_values_in_dof_order(e2d, v)
+    for j, e in enumerate(bnd):
+        assert p_dof[mesh.dof[e]] == p[j] and v_dof[mesh.dof[e]] == v[j]
+    # the mesh the device walks: boundary elements sorted by DOF address, numbered 0..nd-1, no evaluation elements
+    order = bnd[np.argsort(mesh.dof[bnd])]
+    fields = {f.name: getattr(mesh, f.name) for f in dataclasses.fields(mesh)}
+    for name in ("conn", "etype", "center", "normal", "area", "bc_type", "bc_len", "bc_val", "dof", "is_eval"):
+        fields[name] = np.ascontiguousarray(fields[name][order])
+    staged_view = type(mesh)(**fields)
+    staged_view.dof[:] = np.arange(nd, dtype=np.uint32)
+    k = 12.0
+    pts = 0.3 * rng.standard_normal((9, 3)) + np.array([0.0, 0.0, 0.5])
+    a = orc.scattered_field(mesh, pts, p, k, surface_velocity=v)
+    b = orc.scattered_field(staged_view, pts, p_dof, k, surface_velocity=v_dof)
+    assert np.max(np.abs(a - b)) <= 1e-13 * np.max(np.abs(a))
+    dirs = rng.standard_normal((5, 3))
+    dirs /= np.linalg.norm(dirs, axis=1)[:, None]
+    ra, rb = orc.compute_rcs(mesh, p, dirs, k), orc.compute_rcs(staged_view, p_dof, dirs, k)
+    assert np.max(np.abs(ra - rb)) <= 1e-12 * np.max(np.abs(ra))
+    # a map that is not a permutation is left to bemb200_mesh_stage to refuse
+    mesh.dof[bnd[0]] = mesh.dof[bnd[1]]
+    assert bem.enumeration_to_dof(mesh) is None
