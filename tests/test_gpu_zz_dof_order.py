@@ -3,8 +3,7 @@ surface vectors as the reference does (entry j belongs to the j-th non-evaluatio
 452-458) and re-address them to the C ABI's DOF order; the result must be the oracle's for the same mesh and vectors.
 
 The re-addressing itself is checked on the CPU (tests/test_solver_callers_cpu.py); this is its composition with the staged mesh
-on the device.  Written after the round's GPU minutes were spent, so the first hardware run is the driver's: non-strict xfail
-until a green run is on record."""
+on the device (first green run on a B200: profiles/r02zz_pytest_dof_order.log)."""
 import numpy as np
 import pytest
 
@@ -13,7 +12,6 @@ from math_audio_b200.types import PhysicsParams
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="first hardware run (added without GPU access)")
 def test_field_and_rcs_with_permuted_dofs_and_evaluation_elements(orc):
     from math_audio_b200 import bem
 
