@@ -48,6 +48,7 @@ def test_cpp_user_preconditioner_compiles(tmp_path):
 
 
 @pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="first hardware run of the C++ twin (the Python wrapper of the same C entry is green on a B200)")
 def test_cpp_user_preconditioner_on_gpu(tmp_path):
     """bemb200::Preconditioner (include/bemb200.hpp) on the device solver.  The Python wrapper of the same C entry is green on a
     B200 (profiles/r02zz_user_precond.json); this C++ twin was added after the round's GPU minutes were spent, so its first
