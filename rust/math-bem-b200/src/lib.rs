@@ -1,6 +1,6 @@
 //! Safe wrappers over `bem-b200-sys` with the reference's signatures: `build_tbem_system_gpu`
 //! (<- `build_tbem_system_with_beta`, math-bem/src/core/assembly/tbem.rs:96), `GpuDenseOperator: LinearOperator<Complex64>`
-//! (<- `DenseOperator`, math-bem/src/core/solver/fmm_interface.rs:25-52), `GpuSweep` (the per-frequency loop of
+//! (<- `DenseOperator`, math-bem/src/core/solver/fmm_interface.rs:25-52), `GpuStagedMesh` (staged assembly, field evaluation, RCS), `GpuSweep` (the per-frequency loop of
 //! math-bem/examples/audio_frequency_sweep.rs with the assembly of f + 1 underneath the solve of f) and `GpuGroup`
 //! (one process, several devices).  This crate depends on math-bem and math-solvers; neither depends on it: the switch
 //! to the GPU is made by the CALLER (see examples/frequency_sweep_b200.rs), so there is no dependency cycle.
@@ -278,6 +278,77 @@ fn flatten(elements: &[Element], nodes: &Array2<f64>) -> Result<FlatMesh, String
 }
 fn physics_of(p: &PhysicsParams) -> bemb200_physics {
     bemb200_physics { wave_number: p.wave_number, harmonic_factor: p.harmonic_factor, tau: p.tau, gamma: p.gamma() }
+}
+
+/// Frequency-independent device copy of a mesh (`bemb200_mesh_stage`): staged once, reused by the assembly of every frequency
+/// and by the field evaluation after the solve (`compute_scattered_field` postprocess/pressure.rs:81-137, `compute_rcs` :438-478).
+pub struct GpuStagedMesh { h: *mut bemb200_staged_mesh, ctx: GpuContext, num_dofs: usize, enum_to_dof: Option<Vec<usize>> }
+unsafe impl Send for GpuStagedMesh {}
+unsafe impl Sync for GpuStagedMesh {}
+impl Drop for GpuStagedMesh { fn drop(&mut self) { unsafe { bemb200_staged_mesh_free(self.h) } } }
+impl GpuStagedMesh {
+    pub fn new(ctx: &GpuContext, elements: &[Element], nodes: &Array2<f64>) -> Result<Self, String> {
+        let flat = flatten(elements, nodes)?;
+        let mesh = flat.view();
+        let mut h = std::ptr::null_mut();
+        let rc = unsafe { bemb200_mesh_stage(ctx.raw(), &mesh, &mut h) };
+        if rc != 0 { return Err(ctx.error()); }
+        // DOF address of the j-th non-evaluation element; `None` for the sequential map every generator produces
+        let map: Vec<usize> = elements.iter().filter(|e| !e.property.is_evaluation()).map(|e| e.dof_addresses[0]).collect();
+        let sequential = map.iter().enumerate().all(|(j, &d)| d == j);
+        let num_dofs = map.len();
+        Ok(Self { h, ctx: ctx.clone(), num_dofs, enum_to_dof: if sequential { None } else { Some(map) } })
+    }
+    pub fn num_dofs(&self) -> usize { self.num_dofs }
+    /// `build_tbem_system_with_beta` on the staged mesh (tbem.rs:96): only the frequency-dependent work is repeated.
+    pub fn build_tbem_system(&self, physics: &PhysicsParams, beta: Complex64) -> Result<GpuTbemSystem, String> {
+        let phys = physics_of(physics);
+        let mut m = std::ptr::null_mut();
+        let rc = unsafe { bemb200_assemble_staged(self.ctx.raw(), self.h, &phys, beta.re, beta.im, 0, self.num_dofs as u64, &mut m) };
+        if rc != 0 { return Err(self.ctx.error()); }
+        let mut rhs = Array1::<Complex64>::zeros(self.num_dofs);
+        let rc = unsafe { bemb200_rhs_download_full(m, rhs.as_mut_ptr() as *mut f64) };
+        if rc != 0 { unsafe { bemb200_matrix_free(m) }; return Err(self.ctx.error()); }
+        Ok(GpuTbemSystem { operator: GpuDenseOperator { m, ctx: self.ctx.clone() }, rhs, num_dofs: self.num_dofs })
+    }
+    /// The reference pairs entry j of a surface vector with the j-th non-evaluation element (pressure.rs:96-113); the ABI wants
+    /// the entry at the element's DOF address.  Identity for sequential DOF maps.
+    fn in_dof_order(&self, values: &Array1<Complex64>) -> Vec<Complex64> {
+        match &self.enum_to_dof {
+            None => values.iter().cloned().collect(),
+            Some(map) => {
+                let mut out = vec![Complex64::new(0.0, 0.0); values.len()];
+                for (j, v) in values.iter().enumerate() { out[map[j]] = *v; }
+                out
+            }
+        }
+    }
+    /// `compute_scattered_field(eval_points, elements, nodes, surface_pressure, surface_velocity, physics)` (pressure.rs:81).
+    pub fn compute_scattered_field(&self, eval_points: &Array2<f64>, surface_pressure: &Array1<Complex64>,
+                                   surface_velocity: Option<&Array1<Complex64>>, physics: &PhysicsParams) -> Result<Array1<Complex64>, String> {
+        assert_eq!(eval_points.ncols(), 3, "eval_points must be n x 3");
+        assert_eq!(surface_pressure.len(), self.num_dofs, "Vector lengths must match");
+        let pts = eval_points.as_standard_layout();
+        let ps = self.in_dof_order(surface_pressure);
+        let vs = surface_velocity.map(|v| { assert_eq!(v.len(), self.num_dofs, "Vector lengths must match"); self.in_dof_order(v) });
+        let phys = physics_of(physics);
+        let mut out = Array1::<Complex64>::zeros(eval_points.nrows());
+        let rc = unsafe { bemb200_scattered_field(self.h, &phys, eval_points.nrows() as u64, pts.as_ptr(), ps.as_ptr() as *const f64,
+                                                  vs.as_ref().map_or(std::ptr::null(), |v| v.as_ptr() as *const f64),
+                                                  out.as_mut_ptr() as *mut f64) };
+        if rc != 0 { return Err(self.ctx.error()); }
+        Ok(out)
+    }
+    /// `compute_rcs(surface_pressure, elements, direction, physics)` (pressure.rs:438).
+    pub fn compute_rcs(&self, surface_pressure: &Array1<Complex64>, direction: [f64; 3], physics: &PhysicsParams) -> Result<f64, String> {
+        assert_eq!(surface_pressure.len(), self.num_dofs, "Vector lengths must match");
+        let ps = self.in_dof_order(surface_pressure);
+        let phys = physics_of(physics);
+        let mut out = 0.0f64;
+        let rc = unsafe { bemb200_compute_rcs(self.h, &phys, 1, direction.as_ptr(), ps.as_ptr() as *const f64, &mut out) };
+        if rc != 0 { return Err(self.ctx.error()); }
+        Ok(out)
+    }
 }
 
 /// Frequency sweep with the assembly of frequency f + 1 underneath the solve of f (`bemb200_sweep_*`): `submit` a
