@@ -283,3 +283,46 @@ def test_rust_imports_resolve_to_public_items_of_the_reference():
         body = re.findall(rf"impl(?: \w+ for)? {name} \{{.*?\n\}}|impl Drop for {name} \{{[^\n]*\}}", safe, flags=re.S)
         for b in body:
             assert not re.search(r"self\.[a-z_]+\b(?!\()", re.sub(r"self\.\d", "", b)) or name not in ("CtxInner", "GpuContext"), (name, b[:120])
+
+
+def test_oracle_is_test_infrastructure_only():
+    """oracle/ is the checker, never the product: nothing under math_audio_b200/ or include/ imports, links or names it; the
+    library's dynamic dependencies do not include it; bench.py imports it only inside the two functions of the CPU legs
+    (cpu_baseline sample, --impl reference) and __graft_entry__ only in build() (compiling the checker) and smoke()."""
+    import ast
+    import re
+    import subprocess
+
+    from math_audio_b200 import _capi
+
+    root = Path(__file__).resolve().parent.parent
+
+    def oracle_imports(path):
+        tree = ast.parse(path.read_text())
+        parents = {}
+        for node in ast.walk(tree):
+            for child in ast.iter_child_nodes(node):
+                parents[child] = node
+        found = []
+        for node in ast.walk(tree):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                names = [node.module or ""]
+            if any(n == "oracle" or n.startswith("oracle.") for n in names):
+                fn = node
+                while fn in parents and not isinstance(fn, (ast.FunctionDef, ast.AsyncFunctionDef)):
+                    fn = parents[fn]
+                found.append(fn.name if isinstance(fn, ast.FunctionDef) else "<module>")
+        return found
+
+    for py in (root / "math_audio_b200").rglob("*.py"):
+        assert oracle_imports(py) == [], py
+    for src in list((root / "math_audio_b200" / "csrc").iterdir()) + list((root / "include").iterdir()):
+        if src.is_file():
+            assert not re.search(r"\boracle\b|bem_oracle", src.read_text(errors="replace")), src
+    needed = subprocess.run(["readelf", "-d", str(_capi.LIB_PATH)], capture_output=True, text=True, check=True).stdout
+    assert "NEEDED" in needed and "oracle" not in needed
+    assert set(oracle_imports(root / "bench.py")) == {"cpu_sample", "cpu_full_frequency"}
+    assert set(oracle_imports(root / "__graft_entry__.py")) == {"build", "smoke"}
