@@ -132,3 +132,15 @@ def test_side_blocks_are_wired_into_the_native_line():
         body = src[src.index(f"def {fn}("):]
         body = body[: body.index("\ndef ", 10)]
         assert not re.search(r"^\s*(from\s+oracle|import\s+oracle)", body, re.M), fn
+
+
+def test_reference_arm_under_torchrun_only_rank0_works():
+    """Launched like the repo's own arm for N > 1 (one process per GPU): rank 0 alone runs and prints the line, the other
+    ranks exit 0 at once without output and without touching a process group."""
+    e = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29541")
+    p = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2", "--workload", "sphere1k",
+                        "--steps", "2", "--warmup", "1"], capture_output=True, text=True, env=e, timeout=120)
+    assert p.returncode == 0 and p.stdout.strip() == ""
+    line = _run_bench("--impl", "reference", "--gpus", "2", "--workload", "sphere1k", "--steps", "2", "--warmup", "1",
+                      env={"RANK": "0", "LOCAL_RANK": "0", "WORLD_SIZE": "2", "MASTER_ADDR": "127.0.0.1", "MASTER_PORT": "29541"})
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["steps"] == 2 and line["gpu_launches"] == 0
