@@ -3,7 +3,8 @@
 Written from the reference's Rust sources alone (math-bem/src/core/assembly/tbem.rs:96-345,
 core/integration/regular.rs:33-260, core/integration/singular.rs:48-82,123-465,497-745,
 core/integration/gauss.rs:15-105, core/types.rs:64-70, core/mesh/element.rs:124-131,
-math-solvers/src/iterative/gmres.rs:105-277,589-621, blas_helpers.rs:21-73) WITHOUT consulting
+math-solvers/src/iterative/gmres.rs:105-277,589-621, blas_helpers.rs:21-73; for the neighbours of the path also
+core/incident.rs:93-342 and core/postprocess/pressure.rs:81-259,438-478) WITHOUT consulting
 oracle/bem_oracle.cpp: its purpose is to pin the C++ oracle (the reference cannot be compiled in this
 image and holds no numeric golden vectors for this path -- SURVEY.md 8c).  Two restatements written
 separately from the same source that agree to 1e-13 on every matrix entry and on every GMRES iteration
@@ -432,3 +433,103 @@ def _back(h, g, k):
         if abs(h[i, i]) > 1e-30:
             y[i] = s / h[i, i]
     return y
+
+
+# ---- neighbours of the path, again from the Rust sources alone --------------------------------
+# core/incident.rs:93-342 and core/postprocess/pressure.rs:81-259, 438-478.  Vectorised over collocation / evaluation points,
+# so the summation order differs from the C++ oracle's loops on purpose (agreement is to rounding, not to the bit).
+def incident_pressure(kind: str, vec, amplitude: complex, points: np.ndarray, k: float) -> np.ndarray:
+    """incident.rs:93-166.  kind 'plane': p = A exp(i k d.x) (direction used as given, incident.rs:106-116);
+    kind 'point': p = S exp(ikr)/(4 pi r) for r > 1e-10, else 0 (:119-132)."""
+    pts = np.asarray(points, dtype=float)
+    v = np.asarray(vec, dtype=float)
+    if kind == "plane":
+        kdotx = k * (pts @ v)
+        return amplitude * (np.cos(kdotx) + 1j * np.sin(kdotx))
+    d = pts - v
+    r = np.sqrt(np.sum(d * d, axis=1))
+    out = np.zeros(len(pts), dtype=complex)
+    ok = r > 1e-10
+    kr = k * r[ok]
+    out[ok] = amplitude * ((np.cos(kr) + 1j * np.sin(kr)) / (4.0 * math.pi * r[ok]))
+    return out
+
+
+def incident_normal_derivative(kind: str, vec, amplitude: complex, points: np.ndarray, normals: np.ndarray, k: float) -> np.ndarray:
+    """incident.rs:177-280.  plane: dp/dn = i k (d.n) p (:196-208); point: S (ik - 1/r) G (x - x0).n / r (:210-233)."""
+    pts, nrm = np.asarray(points, dtype=float), np.asarray(normals, dtype=float)
+    v = np.asarray(vec, dtype=float)
+    if kind == "plane":
+        return 1j * (k * (nrm @ v)) * incident_pressure(kind, v, amplitude, pts, k)
+    d = pts - v
+    r = np.sqrt(np.sum(d * d, axis=1))
+    out = np.zeros(len(pts), dtype=complex)
+    ok = r > 1e-10
+    ro = r[ok]
+    kr = k * ro
+    g = (np.cos(kr) + 1j * np.sin(kr)) / (4.0 * math.pi * ro)
+    dgdr = (1j * k - 1.0 / ro) * g
+    drdn = np.sum(d[ok] * nrm[ok], axis=1) / ro
+    out[ok] = amplitude * dgdr * drdn
+    return out
+
+
+def incident_rhs(sources, points, normals, k: float, beta: complex, tau: float = 1.0, gamma: float = 1.0) -> np.ndarray:
+    """compute_rhs_with_beta (incident.rs:317-342): rhs = -(gamma p_inc + beta tau dp_inc/dn); `sources` is a list of
+    (kind, vector, amplitude) -- one entry for PlaneWave / PointSource, several for the Multiple* variants (:136-165, :235-276)."""
+    p = sum(incident_pressure(kd, v, a, points, k) for kd, v, a in sources)
+    dp = sum(incident_normal_derivative(kd, v, a, points, normals, k) for kd, v, a in sources)
+    return -(gamma * p + beta * tau * dp)
+
+
+def scattered_field(nodes, conn, is_eval, eval_points, surface_pressure, surface_velocity, k: float, harmonic: float = 1.0) -> np.ndarray:
+    """compute_scattered_field + integrate_element_field (pressure.rs:81-259): entry j of the surface vectors belongs to the
+    j-th NON-EVALUATION element (:96-113); every element -- Quad4 too -- is integrated over the triangle of its first three
+    nodes with the 7-point rule (order 3, :162-198); G = exp(i w r)/(4 pi r) with w = k * harmonic_factor (:92, :236-238);
+    result += p dG/dn_y J w_q - [ |v| > 1e-15 ] v G J w_q (:248-256); quadrature points with J < 1e-15 or r < 1e-15 are skipped."""
+    nodes = np.asarray(nodes, dtype=float)
+    bnd = [e for e in range(len(conn)) if not is_eval[e]]
+    tri = triangle_quadrature(3)
+    xi, eta, wq = tri[:, 0], tri[:, 1], tri[:, 2]
+    N = np.stack([1.0 - xi - eta, xi, eta], axis=1)                 # (7, 3)
+    c = np.stack([nodes[np.asarray(conn)[bnd][:, v].astype(np.int64)] for v in range(3)], axis=1)   # (nb, 3 nodes, 3)
+    y = np.einsum("qn,bnd->bqd", N, c)                              # quadrature points (nb, 7, 3)
+    dxds = c[:, 1] - c[:, 0]
+    dxdt = c[:, 2] - c[:, 0]
+    nv = np.cross(dxds, dxdt)
+    jac = np.sqrt(np.sum(nv * nv, axis=1))
+    good = jac >= 1e-15
+    en = np.zeros_like(nv)
+    en[good] = nv[good] / jac[good][:, None]
+    w = k * harmonic
+    ps = np.asarray(surface_pressure, dtype=complex)
+    vs = None if surface_velocity is None else np.asarray(surface_velocity, dtype=complex)
+    out = np.zeros(len(eval_points), dtype=complex)
+    for i, x in enumerate(np.asarray(eval_points, dtype=float)):
+        rv = y - x                                                   # (nb, 7, 3)
+        r = np.sqrt(np.sum(rv * rv, axis=2))
+        use = good[:, None] & (r >= 1e-15)
+        rs = np.where(use, r, 1.0)
+        g = (np.cos(w * rs) + 1j * np.sin(w * rs)) / (4.0 * math.pi * rs)
+        dgdn = g * (-1.0 / rs + 1j * w) * (np.einsum("bqd,bd->bq", rv, en) / rs)
+        vjacwe = jac[:, None] * wq[None, :]
+        contrib = ps[:, None] * dgdn * vjacwe
+        if vs is not None:
+            has_v = np.abs(vs) > 1e-15
+            contrib = contrib - np.where(has_v[:, None], vs[:, None] * g * vjacwe, 0.0)
+        out[i] = np.sum(np.where(use, contrib, 0.0))
+    return out
+
+
+def rcs(centers, normals, areas, is_eval, surface_pressure, directions, k: float) -> np.ndarray:
+    """compute_rcs (pressure.rs:438-478): F(d) = sum_j p_j exp(-i k c_j.d) A_j (i k)(n_j.d) over the non-evaluation elements in
+    enumeration order, RCS = 4 pi |F|^2."""
+    keep = np.asarray(is_eval) == 0
+    c, n, a = np.asarray(centers, dtype=float)[keep], np.asarray(normals, dtype=float)[keep], np.asarray(areas, dtype=float)[keep]
+    ps = np.asarray(surface_pressure, dtype=complex)
+    out = []
+    for d in np.asarray(directions, dtype=float).reshape(-1, 3):
+        phase = -k * (c @ d)
+        far = np.sum(ps * (np.cos(phase) + 1j * np.sin(phase)) * a * (1j * k) * (n @ d))
+        out.append(4.0 * math.pi * (far.real ** 2 + far.imag ** 2))
+    return np.array(out)

@@ -104,3 +104,43 @@ def test_quad4_box_rows():
     Ai = _rows(mesh, ph, beta, conn, rows)
     scale = np.max(np.abs(Ao[rows]), axis=1, keepdims=True)
     assert np.max(np.abs(Ai - Ao[rows]) / scale) < TOL
+
+
+def test_incident_rhs_field_and_rcs_of_the_two_restatements_agree():
+    """SURVEY 8f ranks 1-2 (incident.rs:93-342, pressure.rs:81-259, 438-478): the C++ oracle against the independent numpy
+    restatement on a Tri3 sphere with evaluation-only elements and on a Quad4 box (first-triangle rule), plane waves and point
+    sources, interior tau, exp(-ikr) convention, a surface velocity with zero entries, points close to the surface."""
+    rng = np.random.default_rng(17)
+    for mesh in (generate_icosphere_mesh(A_RADIUS, 2), generate_box_mesh_quad(0.3, 0.4, 0.5, 3, 4, 5)):
+        k = 21.0
+        beta = 0.2 + 1j / k
+        for tau in (1.0, -1.0):
+            for kind, name, vec, amp in ((0, "plane", [0.0, 0.0, 1.0], 1.0), (0, "plane", [0.6, 0.0, 0.8], 0.5 + 0.25j),
+                                         (1, "point", [0.7, -0.2, 0.4], 2.0)):
+                ref, pinc = orc.incident_rhs(kind, vec, amp, mesh.center, mesh.normal, k, beta, tau=tau)
+                got = ind.incident_rhs([(name, vec, amp)], mesh.center, mesh.normal, k, beta, tau=tau)
+                assert np.max(np.abs(got - ref)) <= 1e-13 * np.max(np.abs(ref))
+                assert np.max(np.abs(ind.incident_pressure(name, vec, amp, mesh.center, k) - pinc)) <= 1e-13 * np.max(np.abs(pinc))
+        two = ind.incident_rhs([("plane", [0.0, 0.0, 1.0], 1.0), ("plane", [1.0, 0.0, 0.0], 0.5)], mesh.center, mesh.normal, k, beta)
+        ref = sum(orc.incident_rhs(0, v, a, mesh.center, mesh.normal, k, beta)[0] for v, a in (([0.0, 0.0, 1.0], 1.0), ([1.0, 0.0, 0.0], 0.5)))
+        assert np.max(np.abs(two - ref)) <= 1e-13 * np.max(np.abs(ref))    # MultiplePlaneWaves (incident.rs:136-147)
+        # field evaluation and RCS, with evaluation-only elements in between (they are skipped and do not consume an entry)
+        mesh.is_eval[::7] = 1
+        nd = mesh.num_dofs
+        mesh.dof[mesh.is_eval == 0] = np.arange(nd, dtype=np.uint32)
+        conn = [list(map(int, c[: mesh.etype[i]])) for i, c in enumerate(mesh.conn)]
+        p = rng.standard_normal(nd) + 1j * rng.standard_normal(nd)
+        v = rng.standard_normal(nd) + 1j * rng.standard_normal(nd)
+        v[::3] = 0.0
+        pts = rng.standard_normal((23, 3))
+        pts *= (np.array([0.15, 0.6, 3.0])[rng.integers(0, 3, 23)] / np.linalg.norm(pts, axis=1))[:, None] + 0.3
+        for vel in (None, v):
+            for harmonic in (1.0, -1.0):
+                ref = orc.scattered_field(mesh, pts, p, k, surface_velocity=vel, harmonic=harmonic)
+                got = ind.scattered_field(mesh.nodes, conn, mesh.is_eval, pts, p, vel, k, harmonic=harmonic)
+                assert np.max(np.abs(got - ref)) <= 1e-12 * np.max(np.abs(ref))
+        dirs = rng.standard_normal((6, 3))
+        dirs /= np.linalg.norm(dirs, axis=1)[:, None]
+        ref = orc.compute_rcs(mesh, p, dirs, k)
+        got = ind.rcs(mesh.center, mesh.normal, mesh.area, mesh.is_eval, p, dirs, k)
+        assert np.max(np.abs(got - ref)) <= 1e-12 * np.max(np.abs(ref))
