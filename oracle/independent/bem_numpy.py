@@ -10,6 +10,9 @@ image and holds no numeric golden vectors for this path -- SURVEY.md 8c).  Two r
 separately from the same source that agree to 1e-13 on every matrix entry and on every GMRES iteration
 count are the strongest pin available without a Rust toolchain.
 
+`assemble_rows_general` walks tbem.rs:126-345 for every boundary-condition class (free terms, matrix entry per field BC, the
+integrators' right-hand-side terms with the unscaled beta).
+
 Different structure on purpose: the un-subdivided pairs of a row are evaluated as one vectorised numpy
 expression over (field element, quadrature point); only subdivided pairs and the self term walk the
 reference's loops.  Tables come from oracle/independent/tables.json (extract_tables.py parses gauss.rs).
@@ -175,9 +178,18 @@ def generate_subelements(x: np.ndarray, coords: np.ndarray, etype: int, area: fl
     return out
 
 
-def regular_pair(x, nx, coords, etype, area, k, harmonic=1.0):
-    """regular_integration for one (source, field element) pair -> (G, H, Ht, E)."""
-    acc = np.zeros(4, dtype=complex)
+def unscaled_beta(k: float, harmonic: float, tau: float) -> complex:
+    """PhysicsParams::burton_miller_beta (types.rs:64-70): i * harmonic_factor / k outside, 0 inside -- what the integrators
+    use for their right-hand-side terms whatever beta the assembly was called with (regular.rs:166-168)."""
+    return complex(0.0, harmonic / k) if tau > 0.0 else 0j
+
+
+def regular_pair(x, nx, coords, etype, area, k, harmonic=1.0, bc=None, bc_type=0, tau=1.0, gamma=1.0):
+    """regular_integration for one (source, field element) pair -> (G, H, Ht, E) and, when per-node boundary values `bc` are
+    given (compute_rhs), a fifth entry: the right-hand-side contribution of regular.rs:157-177 (the values are interpolated
+    with the first len(bc) shape functions only; velocity: (zg gamma tau + zht beta0) v, pressure: -(zhh gamma tau + ze beta0) p)."""
+    acc = np.zeros(5 if bc is not None else 4, dtype=complex)
+    b0 = unscaled_beta(k, harmonic, tau)
     for xc, ec, fac, order, tv in generate_subelements(x, coords, etype, area):
         q = element_quadrature(etype, order)
         cs, et, w = q[:, 0], q[:, 1], q[:, 2]
@@ -191,10 +203,17 @@ def regular_pair(x, nx, coords, etype, area, k, harmonic=1.0):
             w2 = w * det
         else:
             s, t, w2 = xc + cs * fac, ec + et * fac, w * (fac * fac)
-        _, jac, ny, y = geometry_at(coords, etype, s, t)
+        nsh, jac, ny, y = geometry_at(coords, etype, s, t)
         zg, zhh, zht, ze = kernels(x, nx, y, ny, w2 * jac, k, harmonic)
+        terms = [(zg, 0), (zhh, 1), (zht, 2), (ze, 3)]
+        if bc is not None:
+            zb = sum(bc[i] * nsh[i] for i in range(min(len(bc), nsh.shape[0])))
+            if bc_type == 0:
+                terms.append(((zg * gamma * tau + zht * b0) * zb, 4))
+            elif bc_type == 1:
+                terms.append((-((zhh * gamma * tau + ze * b0) * zb), 4))
         # the reference accumulates point by point: a left-to-right running sum, not numpy's pairwise sum
-        for z, i in ((zg, 0), (zhh, 1), (zht, 2), (ze, 3)):
+        for z, i in terms:
             a = acc[i]
             for v in z:
                 a = a + v
@@ -221,8 +240,12 @@ def element_size(coords: np.ndarray, etype: int) -> float:
     return tot / etype
 
 
-def singular_self(x, nx, coords, etype, k, harmonic=1.0):
+def singular_self(x, nx, coords, etype, k, harmonic=1.0, bc=None, bc_type=0, tau=1.0, gamma=1.0):
+    """-> (G, H, Ht, E) and with `bc` a fifth entry, the right-hand-side contribution: velocity values are interpolated at every
+    Duffy point (singular.rs:359-375), pressure values enter as their mean times -(H gamma tau + E beta0) at the end (:381-391)."""
     wav = harmonic * k
+    b0 = unscaled_beta(k, harmonic, tau)
+    R = 0j
     ngpo1, ngausin, nsec1, nsec2 = for_ka(k * element_size(coords, etype))
     gx, gw = gauss_legendre(ngpo1)
     sx, sw = gauss_legendre(ngausin)
@@ -268,7 +291,7 @@ def singular_self(x, nx, coords, etype, k, harmonic=1.0):
                     wg = sw[i] * sw[j]
                     sgg = 0.5 * (1.0 - sga) * s0 + 0.25 * (1.0 + sga) * ((1.0 - tga) * s1 + (1.0 + tga) * s2)
                     tgg = 0.5 * (1.0 - sga) * t0 + 0.25 * (1.0 + sga) * ((1.0 - tga) * t1 + (1.0 + tga) * t2)
-                    _, jac, ny, y = geometry_at(coords, etype, sgg, tgg)
+                    nsh, jac, ny, y = geometry_at(coords, etype, sgg, tgg)
                     w = wg * (1.0 + sga) * aresub * float(jac)
                     d = y - x
                     r = math.sqrt(float(d @ d))
@@ -278,11 +301,19 @@ def singular_self(x, nx, coords, etype, k, harmonic=1.0):
                     re2 = w / (4.0 * math.pi * r)
                     zg = complex(math.cos(wav * r) * re2, math.sin(wav * r) * re2)
                     base = zg * complex(-1.0 / r, wav)
+                    zht = base * float(-(u @ nx))
                     G += zg
                     H += base * float(u @ ny)
-                    HT += base * float(-(u @ nx))
+                    HT += zht
                     E += zg * (k * k) * float(nx @ ny)
-    return np.array([G, H, HT, E])
+                    if bc is not None and bc_type == 0:
+                        zb = sum(bc[i] * float(nsh[i]) for i in range(min(len(bc), nsh.shape[0])))
+                        R += (zg * gamma * tau + zht * b0) * zb
+    if bc is None:
+        return np.array([G, H, HT, E])
+    if bc_type == 1:
+        R = -(H * gamma * tau + E * b0) * (sum(bc) / len(bc))
+    return np.array([G, H, HT, E, R])
 
 
 # ---- tbem.rs: rigid (zero-velocity) elements only -----------------------------------------------------------
@@ -340,6 +371,52 @@ def assemble_rows(nodes, conn, etype, centers, normals, areas, k, beta, rows, ha
             out[oi, j] = (h * sign) * gamma * tau + e * beta
         out[oi, i] += -gamma * 0.5
     return out
+
+
+def assemble_rows_general(nodes, conn, etype, centers, normals, areas, bc_type, bc_values, dof, is_eval, k, beta, rows,
+                          harmonic=1.0, tau=1.0, gamma=1.0):
+    """Rows (by DOF address) of build_tbem_system_with_beta for ANY boundary conditions, element by element as tbem.rs:126-218
+    walks them -> (A[rows, :], rhs[rows]).  bc_type 0 velocity / 1 pressure / 2 transfer (contributes nothing, :239-242);
+    bc_values[e]: the per-node values of element e (length 1..4).  Free terms: add_free_terms (:273-304) with the MEAN of the
+    values; matrix entry: assemble_tbem (:311-345); right-hand side: the integrators' own term with the unscaled beta."""
+    n_el = len(conn)
+    bnd = [e for e in range(n_el) if not is_eval[e]]
+    ndof = len(bnd)
+    sign = dg_dn_sign(centers, k)
+    A = np.zeros((len(rows), ndof), dtype=complex)
+    rhs = np.zeros(len(rows), dtype=complex)
+    by_dof = {int(dof[e]): e for e in bnd}
+    for oi, d in enumerate(rows):
+        i = by_dof[int(d)]
+        x, nx = centers[i], normals[i]
+        vals = [complex(v) for v in bc_values[i]]
+        avg = sum(vals) / len(vals)
+        if bc_type[i] == 0:
+            A[oi, int(dof[i])] -= gamma * 0.5
+            rhs[oi] += avg * beta * tau * 0.5
+        elif bc_type[i] == 1:
+            A[oi, int(dof[i])] -= beta * tau * 0.5
+            rhs[oi] += avg * tau * 0.5
+        for j in bnd:
+            c = nodes[conn[j][: etype[j]]]
+            fv = [complex(v) for v in bc_values[j]]
+            compute_rhs = any(abs(v) > 1e-15 for v in fv)
+            kw = dict(bc=fv, bc_type=int(bc_type[j]), tau=tau, gamma=gamma) if compute_rhs else {}
+            if j == i:
+                res = singular_self(x, nx, c, int(etype[j]), k, harmonic, **kw)
+            else:
+                res = regular_pair(x, nx, c, int(etype[j]), float(areas[j]), k, harmonic, **kw)
+            g, h, ht, e = res[0], res[1] * sign, res[2], res[3]
+            if bc_type[j] == 0:
+                coeff = h * gamma * tau + e * beta
+            elif bc_type[j] == 1:
+                coeff = -(g * gamma * tau + ht * beta)
+            else:
+                coeff = 0j
+            A[oi, int(dof[j])] += coeff
+            if compute_rhs:
+                rhs[oi] += res[4]
+    return A, rhs
 
 
 # ---- gmres.rs:105-277 ------------------------------------------------------------------------------------------

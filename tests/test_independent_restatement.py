@@ -144,3 +144,82 @@ def test_incident_rhs_field_and_rcs_of_the_two_restatements_agree():
         ref = orc.compute_rcs(mesh, p, dirs, k)
         got = ind.rcs(mesh.center, mesh.normal, mesh.area, mesh.is_eval, p, dirs, k)
         assert np.max(np.abs(got - ref)) <= 1e-12 * np.max(np.abs(ref))
+
+
+def _general(mesh, ph, beta, rows, tau=1.0):
+    conn = [list(map(int, c[: mesh.etype[i]])) for i, c in enumerate(mesh.conn)]
+    bcv = [list(mesh.bc_val[e, : mesh.bc_len[e]]) for e in range(mesh.n_elem)]
+    return ind.assemble_rows_general(mesh.nodes, conn, mesh.etype, mesh.center, mesh.normal, mesh.area, mesh.bc_type, bcv, mesh.dof,
+                                     mesh.is_eval, ph.wave_number, complex(beta), rows, tau=tau)
+
+
+def test_general_boundary_conditions_of_the_two_restatements_agree():
+    """tbem.rs:126-345 with every boundary-condition class: pressure and transfer elements, 1-entry non-zero
+    velocities (only N0 is used: regular.rs:159-164), full-length per-node velocities, Tri3 + Quad4 in one mesh with warped quads,
+    evaluation-only elements and a permuted DOF map; both frequencies straddle the dG/dn sign switch.  Matrix rows row-normwise
+    and right-hand sides (free terms, integrator terms with the unscaled beta) must agree between the C++ oracle and the
+    independent numpy restatement."""
+    from math_audio_b200.mesh import BC_PRESSURE, BC_TRANSFER, mesh_from_data
+
+    box = generate_box_mesh_quad(0.3, 0.4, 0.5, 3, 4, 5)
+    nodes = box.nodes.copy()
+    conn = []
+    for q in box.conn[:, :4]:
+        if abs(nodes[q, 2].mean() + 0.25) < 1e-12:
+            conn += [[q[0], q[1], q[2]], [q[0], q[2], q[3]]]
+        else:
+            conn.append(list(q))
+    warped = np.abs(nodes[:, 0] - 0.15) < 1e-12
+    nodes[warped, 0] += 0.01 * np.sin(17.0 * nodes[warped, 1]) * np.cos(11.0 * nodes[warped, 2])
+    mesh = mesh_from_data(nodes, conn)
+    n = mesh.n_elem
+    rng = np.random.default_rng(5)
+    pick = rng.permutation(n)
+    mesh.bc_type[pick[:9]] = BC_PRESSURE
+    mesh.bc_val[pick[:5], 0] = 0.7 - 0.2j
+    mesh.bc_type[pick[9:12]] = BC_TRANSFER
+    mesh.bc_val[pick[12:20], 0] = 1.0 + 0.5j
+    full = pick[20:26]
+    mesh.bc_len[full] = mesh.etype[full]
+    for e in full:
+        mesh.bc_val[e, : mesh.etype[e]] = rng.standard_normal(mesh.etype[e]) + 1j * rng.standard_normal(mesh.etype[e])
+    two = pick[26:29]                                   # two values on a 3/4-node element: the remaining shape functions are dropped
+    mesh.bc_len[two] = 2
+    mesh.bc_val[two, 0], mesh.bc_val[two, 1] = 0.3, -0.4j
+    mesh.bc_type[pick[29]] = BC_PRESSURE                # a pressure element with a full-length vector (mean in the self term)
+    mesh.bc_len[pick[29]] = mesh.etype[pick[29]]
+    mesh.bc_val[pick[29], : mesh.etype[pick[29]]] = [1.0, 2.0j, -1.0, 0.5][: mesh.etype[pick[29]]]
+    mesh.is_eval[pick[30:34]] = 1
+    nd = mesh.num_dofs
+    mesh.dof[mesh.is_eval == 0] = rng.permutation(nd).astype(np.uint32)
+    # rows whose own element is of every class, by DOF address
+    rows = sorted({int(mesh.dof[e]) for e in (pick[0], pick[6], pick[9], pick[12], pick[20], pick[26], pick[29], pick[40], pick[41])})
+    for freq, tau in ((200.0, 1.0), (2500.0, 1.0), (900.0, -1.0)):
+        ph = PhysicsParams.new(freq, 343.0, 1.21, tau < 0)
+        beta = ph.burton_miller_beta_scaled(2.0) if tau > 0 else 0.05 + 0.02j
+        Ao, rhso, _ = orc.assemble(mesh, ph.wave_number, beta, tau=tau)
+        A, rhs = _general(mesh, ph, beta, rows, tau=tau)
+        scale = np.max(np.abs(Ao[rows]), axis=1, keepdims=True)
+        assert np.max(np.abs(A - Ao[rows]) / scale) < TOL, (freq, tau)
+        assert np.max(np.abs(rhs - rhso[rows])) <= TOL * np.max(np.abs(rhso)), (freq, tau)
+        assert np.abs(A[:, mesh.dof[pick[9:12]]]).max() == 0.0 and np.abs(rhso).max() > 0
+
+
+def test_box_with_piston_rhs_of_the_two_restatements_agree():
+    """The config-3 shape in small (tests/golden/box_4x6x8_piston.npz is its oracle record): Quad4 cabinet, full-length velocity
+    vectors on the piston elements, beta = i/k.  Rows facing, next to and on the piston."""
+    mesh = generate_box_mesh_quad(0.32, 0.44, 0.64, 4, 6, 8)
+    ph = PhysicsParams.new(500.0, 343.0, 1.21, False)
+    front = (np.abs(mesh.center[:, 1] + 0.22) < 1e-9) & (np.hypot(mesh.center[:, 0], mesh.center[:, 2]) < 0.12)
+    v = np.zeros((mesh.n_elem, 4), dtype=np.complex128)
+    v[front] = 1.0
+    mesh.set_velocity_bc(v)
+    mesh.bc_len[~front] = 1
+    beta = ph.burton_miller_beta()
+    Ao, rhso, _ = orc.assemble(mesh, ph.wave_number, beta)
+    piston = np.flatnonzero(front)
+    rows = sorted({0, int(piston[0]), int(piston[-1]), int(piston[0]) - 1, mesh.n_elem - 1})
+    A, rhs = _general(mesh, ph, beta, rows)
+    scale = np.max(np.abs(Ao[rows]), axis=1, keepdims=True)
+    assert np.max(np.abs(A - Ao[rows]) / scale) < TOL
+    assert np.max(np.abs(rhs - rhso[rows])) <= TOL * np.max(np.abs(rhso))
