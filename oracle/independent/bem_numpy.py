@@ -434,20 +434,28 @@ def _norm(x):
     return math.sqrt(s)
 
 
-def gmres(apply, b, restart, tol, max_cycles, x0=None, sequential_blas=False):
-    """gmres_with_guess.  `sequential_blas` = the reference's element-by-element inner products (slow in Python);
-    otherwise numpy's vdot / norm (different summation order: same counts unless a decision sits on a rounding edge)."""
+def gmres(apply, b, restart, tol, max_cycles, x0=None, sequential_blas=False, precond=None):
+    """gmres_with_guess (gmres.rs:105-277) and, with `precond` (a function r -> M^-1 r), gmres_preconditioned_with_guess
+    (gmres.rs:434-585): left preconditioning -- M^-1 b for the reference norm, M^-1 (b - A x) at the start of every cycle,
+    M^-1 (A v_j) in every Arnoldi step, residuals relative to ||M^-1 b||.  `sequential_blas` = the reference's
+    element-by-element inner products (slow in Python); otherwise numpy's vdot / norm (different summation order: same counts
+    unless a decision sits on a rounding edge)."""
     inner = _inner if sequential_blas else (lambda x, y: complex(np.vdot(x, y)))
     norm = _norm if sequential_blas else (lambda x: float(np.linalg.norm(x)))
+    plain_apply = apply
+    if precond is not None:
+        apply = lambda v: precond(plain_apply(v))  # noqa: E731  (w = M^-1 (A v_j), gmres.rs:513-514)
     n = len(b)
     m = restart
     x = np.zeros(n, dtype=complex) if x0 is None else np.array(x0, dtype=complex)
-    b_norm = norm(b)
+    b_norm = norm(b if precond is None else precond(np.array(b, dtype=complex)))
     if b_norm < 1e-15:
         return x, dict(iterations=0, restarts=0, residual=0.0, converged=True)
     its = restarts = 0
     for _ in range(max_cycles):
-        r = b - apply(x)
+        r = b - plain_apply(x)
+        if precond is not None:
+            r = precond(r)
         beta = norm(r)
         rel = beta / b_norm
         if rel < tol:
@@ -497,8 +505,23 @@ def gmres(apply, b, restart, tol, max_cycles, x0=None, sequential_blas=False):
         for i, yi in enumerate(y):
             x = x + yi * v[i]
         restarts += 1
-    rel = norm(b - apply(x)) / b_norm
+    r = b - plain_apply(x)
+    rel = norm(r if precond is None else precond(r)) / b_norm
     return x, dict(iterations=its, restarts=restarts, residual=rel, converged=False)
+
+
+def row_sum_correction(A: np.ndarray) -> float:
+    """apply_row_sum_correction (tbem.rs:500-520), in place: A[i, i] -= sum_j A[i, j], row by row with a running sum;
+    returns |sum of all row sums| / n."""
+    n = A.shape[0]
+    total = 0j
+    for i in range(n):
+        rs = 0j
+        for v in A[i]:
+            rs += v
+        total += rs
+        A[i, i] -= rs
+    return abs(total) / n
 
 
 def _back(h, g, k):

@@ -223,3 +223,40 @@ def test_box_with_piston_rhs_of_the_two_restatements_agree():
     scale = np.max(np.abs(Ao[rows]), axis=1, keepdims=True)
     assert np.max(np.abs(A - Ao[rows]) / scale) < TOL
     assert np.max(np.abs(rhs - rhso[rows])) <= TOL * np.max(np.abs(rhso))
+
+
+def test_preconditioned_gmres_and_row_sum_correction_of_the_two_restatements_agree():
+    """gmres_preconditioned_with_guess (gmres.rs:434-585) with the diagonal preconditioner (diagonal.rs:20-58) and with a dense
+    block preconditioner through the callback form, several restart lengths, an initial guess, the zero right-hand side and an
+    exhausted cycle budget; apply_row_sum_correction (tbem.rs:500-520).  On the assembled icosphere(2) system at ka = 6."""
+    mesh, ph, beta, conn = _case(2, 6.0)
+    A, rhs0, _ = orc.assemble(mesh, ph.wave_number, beta)
+    n = A.shape[0]
+    b = rhs0 + orc.incident_rhs(0, [0.0, 0.0, 1.0], 1.0, mesh.center, mesh.normal, ph.wave_number, beta)[0]
+    inv = orc.inverse_diagonal(np.diag(A))
+    for restart, tol, cycles in ((50, 1e-10, 100), (7, 1e-10, 100), (5, 1e-12, 3)):
+        xo, io = orc.gmres_preconditioned(A, b, inv_diag=inv, max_iterations=cycles, restart=restart, tolerance=tol)
+        xi, ii = ind.gmres(lambda v: A @ v, b, restart, tol, cycles, precond=lambda r: r * inv)
+        assert (ii["iterations"], ii["restarts"], ii["converged"]) == (io["iterations"], io["restarts"], io["converged"]), (restart, tol)
+        assert np.linalg.norm(xi - xo) <= 1e-10 * np.linalg.norm(xo)
+        assert abs(ii["residual"] - io["residual"]) <= 1e-6 * io["residual"] + 1e-16
+    assert not io["converged"] and io["restarts"] == 3                      # the last case runs out of cycles
+    # a block preconditioner through the callback form, with an initial guess
+    edges = np.linspace(0, n, 9).astype(int)
+    blocks = [np.linalg.inv(A[s:e, s:e]) for s, e in zip(edges[:-1], edges[1:])]
+
+    def block(r):
+        return np.concatenate([m @ r[s:e] for (s, e), m in zip(zip(edges[:-1], edges[1:]), blocks)])
+
+    x0 = 0.1 * b
+    xo, io = orc.gmres_preconditioned_cb(lambda v: A @ v, block, n, b, x0=x0, max_iterations=100, restart=40, tolerance=1e-10)
+    xi, ii = ind.gmres(lambda v: A @ v, b, 40, 1e-10, 100, x0=x0, precond=block)
+    assert (ii["iterations"], ii["restarts"], ii["converged"]) == (io["iterations"], io["restarts"], io["converged"]) and io["converged"] and io["restarts"] >= 2
+    assert np.linalg.norm(xi - xo) <= 1e-10 * np.linalg.norm(xo)
+    xz, iz = ind.gmres(lambda v: A @ v, np.zeros(n, dtype=complex), 10, 1e-10, 5, x0=x0, precond=block)
+    assert iz == dict(iterations=0, restarts=0, residual=0.0, converged=True) and np.array_equal(xz, x0)   # ||M^-1 b|| < 1e-15: x0 back
+    # row-sum correction
+    Ac, Ai = A.copy(), A.copy()
+    co, ci = orc.row_sum_correction(Ac), ind.row_sum_correction(Ai)
+    assert abs(co - ci) <= 1e-13 * max(co, 1e-300) and np.max(np.abs(Ac - Ai)) <= 1e-13 * np.max(np.abs(Ac))
+    assert np.max(np.abs(Ai.sum(axis=1))) < 1e-12
