@@ -413,3 +413,41 @@ def test_beta_helpers_and_neg_z_wave():
     w = IncidentField.plane_wave_neg_z()
     p = w.evaluate_pressure(np.array([[0.0, 0.0, 0.3]]), ph)
     assert abs(p[0] - np.exp(-1j * 3.0)) < 1e-15
+
+
+def test_mie_series_against_scipy_including_the_reference_monopole_quirk(orc):
+    """math-wave/src/analytical/solutions_3d.rs:56-184 against a series built from scipy's spherical Bessel functions and Legendre
+    polynomials (library code, no restatement): the oracle's Mie field equals it to rounding IF the n = 0 coefficient is formed as
+    the reference forms it -- with y_{-1}(x) = -sin(x)/x (solutions_3d.rs:167-172; the recurrence gives +sin(x)/x).  With the
+    textbook coefficient the two differ visibly around ka = 1, which is part of why the reference's own BEM-vs-Mie figures sit at
+    20-30 %: the quirk is replicated, not repaired (the check of config 1 is 'equal to the reference's figure')."""
+    from scipy.special import eval_legendre, spherical_jn, spherical_yn
+
+    a = 0.1
+
+    def series(k, r, th, quirk):
+        ka = k * a
+        out = np.zeros(len(r), dtype=complex)
+        for n in range(50):
+            jp = spherical_jn(n, ka, derivative=True)
+            yp = spherical_yn(n, ka, derivative=True)
+            if quirk and n == 0:
+                yp = -math.sin(ka) / ka - (1.0 / ka) * spherical_yn(0, ka)
+            an = jp / (jp + 1j * yp)
+            kr = k * r
+            hn = spherical_jn(n, kr) + 1j * spherical_yn(n, kr)
+            out += (2 * n + 1) * (1j ** n) * (spherical_jn(n, kr) - an * hn) * eval_legendre(n, np.cos(th))
+        return out
+
+    th = np.linspace(0.0, math.pi, 19)
+    for ka in (0.2, 1.0, 3.0, 8.0):
+        k = ka / a
+        for rr in (a, 2.0 * a, 10.0 * a):
+            r = np.full_like(th, rr)
+            got = orc.mie_rigid_sphere(k, a, 50, r, th)
+            want = series(k, r, th, quirk=True)
+            assert np.max(np.abs(got - want)) <= 1e-11 * np.max(np.abs(want)), (ka, rr)
+    r = np.full_like(th, a)
+    textbook = series(1.0 / a, r, th, quirk=False)
+    ref = orc.mie_rigid_sphere(1.0 / a, a, 50, r, th)
+    assert np.linalg.norm(ref - textbook) / np.linalg.norm(textbook) > 0.5
