@@ -451,3 +451,46 @@ def test_mie_series_against_scipy_including_the_reference_monopole_quirk(orc):
     textbook = series(1.0 / a, r, th, quirk=False)
     ref = orc.mie_rigid_sphere(1.0 / a, a, 50, r, th)
     assert np.linalg.norm(ref - textbook) / np.linalg.norm(textbook) > 0.5
+
+
+def test_quadrature_tables_against_numpy_and_exactness(orc):
+    """gauss.rs:134-400 as mathematics, not as a transcription: every tabulated Gauss-Legendre order equals numpy's leggauss nodes
+    and weights to the table's 15 digits, and the triangle rules integrate every monomial up to their degree exactly over the
+    reference triangle (TR1: 1, TR4: 3, TR7: 5, TR13: 7; int x^a y^b = a! b! / (a + b + 2)!).  Orders without a table round UP to
+    the next one (gauss.rs:15-60)."""
+    for order in (1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 16, 20):
+        x, w = orc.gauss_legendre(order)
+        xr, wr = np.polynomial.legendre.leggauss(order)
+        assert len(x) == order
+        o = np.argsort(x)
+        assert np.max(np.abs(x[o] - xr)) < 5e-15 and np.max(np.abs(w[o] - wr)) < 5e-15, order
+    for order, table in ((9, 12), (11, 12), (13, 16), (15, 16), (17, 20), (19, 20)):   # 9 skips the 10-point table
+        assert len(orc.gauss_legendre(order)[0]) == table
+    for order, npts, degree in ((1, 1, 1), (2, 4, 3), (3, 7, 5), (4, 13, 7)):
+        t = orc.triangle_quadrature(order)
+        assert len(t) == npts and abs(t[:, 2].sum() - 0.5) < 1e-14
+        for a in range(degree + 1):
+            for b in range(degree + 1 - a):
+                exact = math.factorial(a) * math.factorial(b) / math.factorial(a + b + 2)
+                got = float(np.sum(t[:, 2] * t[:, 0] ** a * t[:, 1] ** b))
+                assert abs(got - exact) < 2e-15 + 1e-13 * exact, (order, a, b)
+    q = orc.quad_quadrature(4)
+    assert len(q) == 16 and abs(q[:, 2].sum() - 4.0) < 1e-14
+    assert abs(np.sum(q[:, 2] * q[:, 0] ** 6 * q[:, 1] ** 4) - (2.0 / 7.0) * (2.0 / 5.0)) < 1e-14   # 4 x 4 GL: exact to degree 7 per axis
+
+
+def test_device_tables_are_the_pinned_tables():
+    """The CUDA kernels read math_audio_b200/csrc/quad_tables.h, the oracle reads oracle/quad_tables.h; both are written by
+    tools/gen_quad_tables.py from gauss.rs:134-400.  Same numbers, digit for digit -- so the mathematical pin above (numpy's
+    leggauss, monomial exactness) holds for what the GPU integrates with."""
+    import re
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+
+    def numbers(path):
+        text = re.sub(r"//[^\n]*", "", path.read_text())
+        return re.findall(r"[-+]?\d+\.\d+(?:[eE][-+]?\d+)?", text)
+
+    dev, orc_t = numbers(root / "math_audio_b200" / "csrc" / "quad_tables.h"), numbers(root / "oracle" / "quad_tables.h")
+    assert len(dev) > 200 and dev == orc_t
