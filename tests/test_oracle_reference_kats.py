@@ -494,3 +494,40 @@ def test_device_tables_are_the_pinned_tables():
 
     dev, orc_t = numbers(root / "math_audio_b200" / "csrc" / "quad_tables.h"), numbers(root / "oracle" / "quad_tables.h")
     assert len(dev) > 200 and dev == orc_t
+
+
+def test_kernels_are_the_derivatives_their_names_claim(orc):
+    """regular.rs:112-154 as mathematics.  For an un-subdivided pair the quadrature points do not depend on the source point, so
+    differentiating the quadrature sum of one kernel w.r.t. the source position gives the quadrature sum of the differentiated
+    kernel: with G = exp(ikr)/(4 pi r),
+        int dG/dn_x  ("dg_dnx", zht)          = d/dn_x  [ int G ]          (central difference along n_x)
+        int d2G/dn_x dn_y  ("d2g_dnxdny", ze)  = d/dn_x  [ int dG/dn_y ]
+    and dG/dn_y itself against a difference of int G under a rigid shift of the element along its own normal.  Tri3 and Quad4,
+    both time conventions.  (The reference's formulas could in principle differ from the mathematics; this shows that what the
+    restatement took from regular.rs is the object each name claims, signs included.)"""
+    rng = np.random.default_rng(2)
+    tri = np.array([[0.0, 0.0, 0.0], [0.11, 0.01, 0.0], [0.02, 0.09, 0.01]])
+    quad = np.array([[0.0, 0.0, 0.0], [0.1, 0.0, 0.01], [0.11, 0.1, 0.0], [0.0, 0.09, 0.0]])
+    for coords, etype, area in ((tri, 3, 0.005), (quad, 4, 0.01)):
+        for harmonic in (1.0, -1.0):
+            k = 23.0
+            src = np.array([0.35, -0.2, 0.45])          # ratio >> 3: never subdivided
+            nx = rng.standard_normal(3)
+            nx /= np.linalg.norm(nx)
+            base = orc.regular_integration(src, nx, coords, etype, area, k, harmonic=harmonic)
+            assert base["nqp"] in (13, 16)
+            h = 2e-6
+            up = orc.regular_integration(src + h * nx, nx, coords, etype, area, k, harmonic=harmonic)
+            dn = orc.regular_integration(src - h * nx, nx, coords, etype, area, k, harmonic=harmonic)
+            keys = list(base.keys())
+            g, hh, ht, e = keys[0], keys[1], keys[2], keys[3]
+            d_g = (up[g] - dn[g]) / (2 * h)
+            d_h = (up[hh] - dn[hh]) / (2 * h)
+            assert abs(d_g - base[ht]) <= 2e-7 * abs(base[ht]), (etype, harmonic, "dG/dn_x")
+            assert abs(d_h - base[e]) <= 2e-7 * abs(base[e]), (etype, harmonic, "d2G/dn_x dn_y")
+            if etype == 3:  # flat element: its normal is one vector, a rigid shift along it differentiates G w.r.t. n_y
+                ny = np.cross(coords[1] - coords[0], coords[2] - coords[0])
+                ny /= np.linalg.norm(ny)
+                gp = orc.regular_integration(src, nx, coords + h * ny, etype, area, k, harmonic=harmonic)[g]
+                gm = orc.regular_integration(src, nx, coords - h * ny, etype, area, k, harmonic=harmonic)[g]
+                assert abs((gp - gm) / (2 * h) - base[hh]) <= 2e-7 * abs(base[hh]), (harmonic, "dG/dn_y")
