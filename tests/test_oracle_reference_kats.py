@@ -531,3 +531,59 @@ def test_kernels_are_the_derivatives_their_names_claim(orc):
                 gp = orc.regular_integration(src, nx, coords + h * ny, etype, area, k, harmonic=harmonic)[g]
                 gm = orc.regular_integration(src, nx, coords - h * ny, etype, area, k, harmonic=harmonic)[g]
                 assert abs((gp - gm) / (2 * h) - base[hh]) <= 2e-7 * abs(base[hh]), (harmonic, "dG/dn_y")
+
+
+def test_self_term_against_exact_polar_integration(orc):
+    """singular.rs:123-394 as mathematics.  For a flat element and the source at its centre the two non-trivial self integrals
+    have one-dimensional closed forms in polar coordinates about the source (R(theta) = distance to the boundary):
+        int G dS                         = int_0^2pi (exp(ikR) - 1) / (4 pi i k) dtheta
+        f.p. int d2G/dn_x dn_y dS        = i k / 2 - (1 / 4 pi) int_0^2pi exp(ikR) / R dtheta     (Hadamard finite part)
+    evaluated here with scipy's adaptive quad.  The reference's edge-integral regularisation + Duffy quadrature must reproduce
+    them to its quadrature accuracy (1e-6 ... 1e-4 for k h <= 0.2, degrading towards k h = 4), and its double-layer self terms
+    vanish on a flat element.  Tri3 and Quad4, including the k h >= 1 branch with the repeated sub-triangle (nsec2 = 3, 4)."""
+    from scipy.integrate import quad
+
+    def exact(coords, x, k):
+        G = E = 0j
+        n = len(coords)
+        for i in range(n):
+            a, b = coords[i] - x, coords[(i + 1) % n] - x
+            e1 = a / np.linalg.norm(a)
+            nrm = np.cross(a, b)
+            e2 = np.cross(nrm / np.linalg.norm(nrm), e1)
+            a2, b2 = np.array([a @ e1, a @ e2]), np.array([b @ e1, b @ e2])
+            t0, t1 = math.atan2(a2[1], a2[0]), math.atan2(b2[1], b2[0])
+            if t1 < t0:
+                t1 += 2.0 * math.pi
+            d = b2 - a2
+            c = a2[0] * d[1] - a2[1] * d[0]
+
+            def R(t):
+                return c / (math.cos(t) * d[1] - math.sin(t) * d[0])
+
+            def fg(t):
+                return (np.exp(1j * k * R(t)) - 1.0) / (4.0 * math.pi * 1j * k)
+
+            def fe(t):
+                return -np.exp(1j * k * R(t)) / (4.0 * math.pi * R(t)) + 1j * k / (4.0 * math.pi)
+
+            for f, which in ((fg, "g"), (fe, "e")):
+                v = complex(quad(lambda t: f(t).real, t0, t1, epsabs=1e-14, epsrel=1e-12)[0],
+                            quad(lambda t: f(t).imag, t0, t1, epsabs=1e-14, epsrel=1e-12)[0])
+                if which == "g":
+                    G += v
+                else:
+                    E += v
+        return G, E
+
+    tri = np.array([[0.0, 0.0, 0.0], [0.011, 0.001, 0.0], [0.002, 0.009, 0.0]])
+    quad4 = np.array([[0.0, 0.0, 0.0], [0.01, 0.0, 0.0], [0.011, 0.01, 0.0], [0.0, 0.009, 0.0]])
+    nx = np.array([0.0, 0.0, 1.0])
+    for coords, etype in ((tri, 3), (quad4, 4)):
+        x = coords.mean(axis=0)   # Tri3 centroid; for the bilinear Quad4 the image of (0, 0) is the mean of the nodes
+        for k, bar in ((1.0, 2e-4), (20.0, 2e-4), (100.0, 2e-3), (400.0, 1e-2)):   # k h = 0.01, 0.2, 1, 4
+            r = orc.singular_integration(x, nx, coords, etype, k)
+            G, E = exact(coords, x, k)
+            assert abs(r["g"] - G) <= bar * abs(G), (etype, k, "G")
+            assert abs(r["d2g"] - E) <= bar * abs(E), (etype, k, "E")
+            assert abs(r["dg_dn"]) < 1e-12 * abs(G) * k + 1e-18 and abs(r["dg_dnx"]) < 1e-12 * abs(G) * k + 1e-18
