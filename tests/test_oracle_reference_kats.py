@@ -587,3 +587,56 @@ def test_self_term_against_exact_polar_integration(orc):
             assert abs(r["g"] - G) <= bar * abs(G), (etype, k, "G")
             assert abs(r["d2g"] - E) <= bar * abs(E), (etype, k, "E")
             assert abs(r["dg_dn"]) < 1e-12 * abs(G) * k + 1e-18 and abs(r["dg_dnx"]) < 1e-12 * abs(G) * k + 1e-18
+
+
+def test_adaptive_subdivision_against_adaptive_cubature(orc):
+    """generate_subelements + regular_integration (singular.rs:497-660, regular.rs:33-182) as mathematics: the four integrals of a
+    near pair against scipy's adaptive dblquad of the same kernels over the triangle.  Where the ratio test subdivides (91 and 247
+    quadrature points here) the reference's scheme is accurate to 1e-7 or better, as is the un-subdivided 13-point rule at
+    ratio >= 3 -- a wrong sub-element map, Jacobian or weight would show at the 1e-2 level.  A source 0.15 element sizes above
+    the centroid runs into the caps of the scheme (110 sub-elements, levels cut after 15 splits: singular.rs:558-562, 648-650):
+    1339 points and a truncated integral -- the quirk the CUDA near kernel reproduces decision for decision."""
+    from scipy.integrate import dblquad
+
+    def kern(x, nx, y, ny, k):
+        d = y - x
+        r = np.linalg.norm(d)
+        u = d / r
+        g = np.exp(1j * k * r) / (4.0 * math.pi * r)
+        base = g * (1j * k - 1.0 / r)
+        h1, h2, nn = u @ ny, -(u @ nx), nx @ ny
+        rq = h1 * h2
+        e = g * (((3.0 / r ** 2 - k * k) * rq + nn / r ** 2) + 1j * (-k / r * (3.0 * rq + nn)))
+        return g, base * h1, base * h2, e
+
+    tri = np.array([[0.0, 0.0, 0.0], [0.011, 0.001, 0.0], [0.002, 0.009, 0.0]])
+    nyv = np.cross(tri[1] - tri[0], tri[2] - tri[0])
+    jac = np.linalg.norm(nyv)
+    nyv = nyv / jac
+    area = 0.5 * jac
+    nx = np.array([0.3, -0.2, 0.93])
+    nx /= np.linalg.norm(nx)
+    k = 20.0
+
+    def exact(x, comps):
+        out = []
+        for comp in comps:
+            vals = []
+            for part in (np.real, np.imag):
+                def f(t, s):
+                    return float(part(kern(x, nx, tri[0] + (tri[1] - tri[0]) * s + (tri[2] - tri[0]) * t, nyv, k)[comp])) * jac
+                vals.append(dblquad(f, 0, 1, lambda s: 0.0, lambda s: 1.0 - s, epsabs=1e-13, epsrel=1e-10)[0])
+            out.append(complex(vals[0], vals[1]))
+        return out
+
+    cen = tri.mean(axis=0)
+    for off, nqp in (([0.004, 0.003, 0.004], 247), ([0.012, 0.0, 0.002], 91), ([0.03, 0.02, 0.01], 13)):
+        x = cen + np.array(off)
+        r = orc.regular_integration(x, nx, tri, 3, area, k)
+        assert r["nqp"] == nqp
+        for got, want in zip((r["g"], r["dg_dn"], r["dg_dnx"], r["d2g"]), exact(x, (0, 1, 2, 3))):
+            assert abs(got - want) <= 2e-7 * abs(want), (off, got, want)
+    x = cen + np.array([0.0, 0.0, 0.0015])
+    r = orc.regular_integration(x, nx, tri, 3, area, k)
+    (want,) = exact(x, (0,))
+    assert r["nqp"] == 1339 and 0.03 < abs(r["g"] - want) / abs(want) < 0.2
