@@ -640,3 +640,36 @@ def test_adaptive_subdivision_against_adaptive_cubature(orc):
     r = orc.regular_integration(x, nx, tri, 3, area, k)
     (want,) = exact(x, (0,))
     assert r["nqp"] == 1339 and 0.03 < abs(r["g"] - want) / abs(want) < 0.2
+
+
+def test_incident_field_and_field_evaluation_as_physics(orc):
+    """incident.rs:93-342 and pressure.rs:81-259 as physics rather than transcription.
+    (1) dp_inc/dn of a plane wave and of a point source (recovered from compute_rhs_with_beta = -(gamma p + beta tau dp/dn)) equals a
+        central difference of p_inc along the normal.
+    (2) Kirchhoff-Helmholtz: the field of a point source INSIDE a closed surface, evaluated outside from its own surface pressure
+        and normal derivative through compute_scattered_field (p dG/dn_y - dp/dn G, outward normals), is the source's field:
+        0.8 % with 320 constant elements, 0.2 % with 1 280 (second order) -- signs, normal orientation and the 7-point rule."""
+    from math_audio_b200.mesh import generate_icosphere_mesh
+
+    a, k = 0.1, 15.0
+    beta = 1j / k
+    mesh = generate_icosphere_mesh(a, 2)
+    h = 1e-6
+    for kind, vec in ((0, [0.6, 0.0, 0.8]), (1, [0.02, -0.01, 0.03]), (1, [0.4, 0.3, -0.2])):
+        rhs, p = orc.incident_rhs(kind, vec, 1.0, mesh.center, mesh.normal, k, beta)
+        dpdn = -(rhs + p) / beta
+        _, pp = orc.incident_rhs(kind, vec, 1.0, mesh.center + h * mesh.normal, mesh.normal, k, beta)
+        _, pm = orc.incident_rhs(kind, vec, 1.0, mesh.center - h * mesh.normal, mesh.normal, k, beta)
+        assert np.max(np.abs((pp - pm) / (2 * h) - dpdn)) <= 1e-7 * np.max(np.abs(dpdn)), (kind, vec)
+    x0 = np.array([0.02, -0.01, 0.03])
+    pts = np.array([[0.3, 0.1, -0.2], [0.0, 0.0, 0.25], [-0.5, 0.4, 0.1]])
+    r = np.linalg.norm(pts - x0, axis=1)
+    exact = np.exp(1j * k * r) / (4.0 * math.pi * r)
+    errs = []
+    for sub in (2, 3):
+        mesh = generate_icosphere_mesh(a, sub)
+        rhs, p = orc.incident_rhs(1, x0, 1.0, mesh.center, mesh.normal, k, beta)
+        dpdn = -(rhs + p) / beta
+        got = orc.scattered_field(mesh, pts, p, k, surface_velocity=dpdn)
+        errs.append(float(np.max(np.abs(got - exact) / np.abs(exact))))
+    assert errs[0] < 0.012 and errs[1] < 0.003 and errs[1] < errs[0] / 3.0
