@@ -19,3 +19,14 @@ def orc():
 
     oracle.build()
     return oracle
+
+
+@pytest.fixture(scope="session", autouse=True)
+def built_library():
+    """A fresh checkout has no libbemb200.so (built artefacts are not tracked): build it once, in-tree, with nvcc for sm_100a
+    (cross-compiles without a GPU).  An existing library is left alone -- on the GPU box it is the one that travelled."""
+    from math_audio_b200 import build as _b
+
+    if not _b.LIB.exists():
+        _b.build()
+    return _b.LIB
