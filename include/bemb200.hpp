@@ -530,6 +530,114 @@ inline GmresSolution gmres_preconditioned(const DenseOperator& op, const Precond
     return gmres_preconditioned_with_guess(op, p, b, nullptr, config);
 }
 
+// ---- pipelined frequency sweep and the single-process multi-GPU group (bemb200_sweep_*, bemb200_multi_*) -------------------------
+// Sweep: the per-frequency loop of math-bem/examples/audio_frequency_sweep.rs with the assembly of frequency f + 1 underneath the
+// solve of f.  submit() a frequency, next() returns the oldest one solved; keep two in flight.
+class Sweep {
+public:
+    Sweep(int device, const std::vector<Element>& elements, const std::vector<double>& nodes, bool overlap = true,
+          int background_blocks_per_sm = 2) {
+        const MeshSoA soa(elements);
+        const bemb200_mesh mesh = soa.view(nodes);
+        check(bemb200_sweep_create(device, 0, 1, nullptr, &mesh, overlap ? 1 : 0, background_blocks_per_sm, &h_));
+        n_ = static_cast<std::size_t>(bemb200_sweep_num_dofs(h_));
+    }
+    ~Sweep() { bemb200_sweep_destroy(h_); }
+    Sweep(const Sweep&) = delete;
+    Sweep& operator=(const Sweep&) = delete;
+    std::size_t num_dofs() const { return n_; }
+    // rhs_extra = IncidentField::compute_rhs_with_beta(...) (added to TbemSystem.rhs); empty = none
+    void submit(const PhysicsParams& physics, Complex64 beta, const std::vector<Complex64>& rhs_extra, const GmresConfig& config) {
+        if (!rhs_extra.empty() && rhs_extra.size() != n_) throw std::invalid_argument("Sweep::submit: vector lengths must match");
+        const bemb200_physics phys = physics_abi(physics);
+        check(bemb200_sweep_submit(h_, &phys, beta.real(), beta.imag(),
+                                   rhs_extra.empty() ? nullptr : reinterpret_cast<const double*>(rhs_extra.data()),
+                                   static_cast<uint32_t>(config.max_iterations), static_cast<uint32_t>(config.restart), config.tolerance));
+    }
+    // solve every following frequency with gmres_preconditioned + block-Jacobi (AdditiveSchwarzPreconditioner::from_csr(.., S, 0));
+    // 0 switches back to plain gmres
+    void set_block_jacobi(std::size_t num_subdomains) {
+        check(bemb200_sweep_set_block_jacobi(h_, static_cast<uint32_t>(num_subdomains), nullptr, nullptr));
+    }
+    GmresSolution next() {
+        GmresSolution s;
+        s.x.resize(n_);
+        bemb200_gmres_info info{};
+        check(bemb200_sweep_next(h_, reinterpret_cast<double*>(s.x.data()), &info, nullptr, nullptr));
+        s.iterations = info.iterations; s.restarts = info.restarts; s.residual = info.residual; s.converged = info.converged != 0;
+        return s;
+    }
+
+private:
+    bemb200_sweep* h_ = nullptr;
+    std::size_t n_ = 0;
+};
+
+// MultiGpu: ONE process, several devices (the shape of BemSolver::solve, bem_solver.rs:273-322): rows block-partitioned over the
+// devices, persistent fused GMRES kernel per device, Krylov vectors and reduction partials through peer-mapped memory.
+class MultiGpu {
+public:
+    explicit MultiGpu(const std::vector<int>& devices) {
+        check(bemb200_multi_create(devices.data(), static_cast<int>(devices.size()), &h_));
+    }
+    ~MultiGpu() { bemb200_multi_destroy(h_); }
+    MultiGpu(const MultiGpu&) = delete;
+    MultiGpu& operator=(const MultiGpu&) = delete;
+    int num_ranks() const { return bemb200_multi_num_ranks(h_); }
+
+    class System {  // the row-sharded TbemSystem; must not outlive its group
+    public:
+        ~System() { bemb200_multi_matrix_free(m_); }
+        System(System&& o) noexcept : g_(o.g_), m_(o.m_), rhs(std::move(o.rhs)), num_dofs(o.num_dofs) { o.m_ = nullptr; }
+        System(const System&) = delete;
+        System& operator=(const System&) = delete;
+        GmresSolution gmres(const std::vector<Complex64>& b, const GmresConfig& config) const {  // gmres.rs:96 on the sharded operator
+            if (b.size() != num_dofs) throw std::invalid_argument("gmres: vector lengths must match");
+            GmresSolution s;
+            s.x.resize(b.size());
+            bemb200_gmres_info info{};
+            g_->check_group(bemb200_multi_gmres(m_, reinterpret_cast<const double*>(b.data()), nullptr, static_cast<uint32_t>(config.max_iterations),
+                                                static_cast<uint32_t>(config.restart), config.tolerance, reinterpret_cast<double*>(s.x.data()), &info));
+            s.iterations = info.iterations; s.restarts = info.restarts; s.residual = info.residual; s.converged = info.converged != 0;
+            return s;
+        }
+
+    private:
+        friend class MultiGpu;
+        System(const MultiGpu* g, bemb200_multi_matrix* m) : g_(g), m_(m) {}
+        const MultiGpu* g_;
+        bemb200_multi_matrix* m_;
+
+    public:
+        std::vector<Complex64> rhs;
+        std::size_t num_dofs = 0;
+    };
+
+    // build_tbem_system_with_beta on the group: every device assembles its bemb200_partition row block
+    System build_tbem_system_with_beta(const std::vector<Element>& elements, const std::vector<double>& nodes, const PhysicsParams& physics,
+                                       Complex64 beta) const {
+        const MeshSoA soa(elements);
+        const bemb200_mesh mesh = soa.view(nodes);
+        const bemb200_physics phys = physics_abi(physics);
+        bemb200_multi_matrix* m = nullptr;
+        check_group(bemb200_multi_assemble(h_, &mesh, &phys, beta.real(), beta.imag(), &m));
+        System sys(this, m);
+        sys.num_dofs = static_cast<std::size_t>(bemb200_multi_num_rows(m));
+        sys.rhs.resize(sys.num_dofs);
+        check_group(bemb200_multi_rhs_download(m, reinterpret_cast<double*>(sys.rhs.data())));
+        return sys;
+    }
+
+private:
+    void check_group(int rc) const {
+        if (rc != BEMB200_OK) {
+            const char* msg = bemb200_multi_last_error(h_);
+            throw Error(rc, msg ? msg : "");
+        }
+    }
+    bemb200_multi* h_ = nullptr;
+};
+
 // ---- BiCGSTAB / LU (the solvers of BemSolver::solve_dense_system, bem_solver.rs:435-463) ---------------------
 struct BiCgstabConfig {  // bicgstab.rs:19-37
     std::size_t max_iterations = 1000;

@@ -34,3 +34,15 @@ def test_cpp_host_api_on_gpu(tmp_path, orc):
     exe = _build(tmp_path, orc)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True, timeout=300)
     assert "PASS" in out.stdout, out.stdout + out.stderr
+
+
+def test_cpp_sweep_and_multi_gpu_wrappers_compile_and_link(tmp_path):
+    """bemb200::Sweep / bemb200::MultiGpu (include/bemb200.hpp) against the library's exported symbols, warnings as errors."""
+    from math_audio_b200 import _capi
+
+    exe = tmp_path / "instantiate_sweep_multi"
+    libdir = _capi.LIB_PATH.parent
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I", str(ROOT / "include"), str(ROOT / "tests" / "cpp" / "instantiate_sweep_multi.cpp"),
+           "-o", str(exe), f"-L{libdir}", "-lbemb200", f"-Wl,-rpath,{libdir}"]
+    subprocess.run(cmd, check=True)
+    assert subprocess.run([str(exe)]).returncode == 0  # nothing is executed: main returns before touching the GPU
