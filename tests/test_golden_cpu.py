@@ -326,3 +326,36 @@ def test_oracle_is_test_infrastructure_only():
     assert "NEEDED" in needed and "oracle" not in needed
     assert set(oracle_imports(root / "bench.py")) == {"cpu_sample", "cpu_full_frequency"}
     assert set(oracle_imports(root / "__graft_entry__.py")) == {"build", "smoke"}
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/bemb200.h must compile as C99 with pedantic warnings as errors (no C++ in the
+    signatures, no torch types), and a C program using it must link against libbemb200.so and get a clean error -- not a crash --
+    for a NULL mesh without ever touching a GPU."""
+    import subprocess
+
+    from math_audio_b200 import _capi
+
+    root = Path(__file__).resolve().parent.parent
+    src = tmp_path / "use_from_c.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "bemb200.h"
+static int jacobi(void* user, const double* r, double* z, uint64_t n) { (void)user; memcpy(z, r, 16 * n); return 0; }
+int main(void) {
+    uint64_t b = 7, e = 7;
+    bemb200_partition(10, 4, 1, &b, &e);                 /* [3, 6) */
+    bemb200_precond_fn fn = jacobi;                      /* the callback type is a plain C function pointer */
+    bemb200_sweep* sw = NULL;
+    int rc = bemb200_sweep_create(0, 0, 1, NULL, NULL, 1, 2, &sw);   /* NULL mesh: EINVAL before any device work */
+    printf("%llu %llu %d %d\n", (unsigned long long)b, (unsigned long long)e, rc, fn != NULL);
+    return (b == 3 && e == 6 && rc == BEMB200_EINVAL && sw == NULL) ? 0 : 1;
+}
+''')
+    exe = tmp_path / "use_from_c"
+    libdir = _capi.LIB_PATH.parent
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Wpedantic", "-Werror", "-I", str(root / "include"), str(src), "-o", str(exe),
+                    f"-L{libdir}", "-lbemb200", f"-Wl,-rpath,{libdir}"], check=True)
+    p = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
