@@ -673,3 +673,57 @@ def test_incident_field_and_field_evaluation_as_physics(orc):
         got = orc.scattered_field(mesh, pts, p, k, surface_velocity=dpdn)
         errs.append(float(np.max(np.abs(got - exact) / np.abs(exact))))
     assert errs[0] < 0.012 and errs[1] < 0.003 and errs[1] < errs[0] / 3.0
+
+
+def test_gmres_counts_are_the_mathematically_determined_ones(orc):
+    """gmres.rs:105-277 / 434-585 as mathematics.  Restarted GMRES(m) is determined by its definition -- in every cycle x_j
+    minimises ||M (b - A x)|| over x_0 + K_j(M A, M r_0) -- not by how Arnoldi, Gram-Schmidt and the Givens rotations are coded.
+    Re-computing it with LAPACK (QR for the Krylov basis, least squares for the minimiser) must give the oracle's iteration and
+    restart counts, residuals and solutions: plain, with short restarts, and left-preconditioned, on assembled BEM systems."""
+    from math_audio_b200.mesh import generate_icosphere_mesh
+    from math_audio_b200.types import PhysicsParams
+
+    def by_definition(A, b, restart, tol, max_cycles, M=None):
+        n = len(b)
+        x = np.zeros(n, dtype=complex)
+        Mf = (lambda v: v) if M is None else M
+        bn = np.linalg.norm(Mf(b))
+        its = restarts = 0
+        for _ in range(max_cycles):
+            r0 = Mf(b - A @ x)
+            beta = np.linalg.norm(r0)
+            if beta / bn < tol:
+                return x, its, restarts, beta / bn, True
+            Q = (r0 / beta)[:, None]
+            for j in range(restart):
+                its += 1
+                if j > 0:
+                    Q, _ = np.linalg.qr(np.column_stack([Q, Mf(A @ Q[:, -1])]))
+                B = np.column_stack([Mf(A @ Q[:, i]) for i in range(Q.shape[1])])
+                y = np.linalg.lstsq(B, r0, rcond=None)[0]
+                res = np.linalg.norm(r0 - B @ y) / bn
+                if res < tol:
+                    return x + Q @ y, its, restarts, res, True
+            x = x + Q @ y
+            restarts += 1
+        return x, its, restarts, np.linalg.norm(Mf(b - A @ x)) / bn, False
+
+    a = 0.1
+    for sub, ka in ((1, 0.5), (2, 3.0)):
+        mesh = generate_icosphere_mesh(a, sub)
+        ph = PhysicsParams.from_wave_number(ka / a)
+        beta, _ = ph.burton_miller_beta_adaptive(a)
+        A, rhs0, _ = orc.assemble(mesh, ph.wave_number, beta)
+        b = rhs0 + orc.incident_rhs(0, [0.0, 0.0, 1.0], 1.0, mesh.center, mesh.normal, ph.wave_number, beta)[0]
+        inv = orc.inverse_diagonal(np.diag(A))
+        cases = [(50, None), (6, None), (8, inv)]
+        for restart, pinv in cases:
+            if pinv is None:
+                xo, io = orc.gmres(A, b, max_iterations=200, restart=restart, tolerance=1e-10)
+                x, its, rs, res, conv = by_definition(A, b, restart, 1e-10, 200)
+            else:
+                xo, io = orc.gmres_preconditioned(A, b, inv_diag=pinv, max_iterations=200, restart=restart, tolerance=1e-10)
+                x, its, rs, res, conv = by_definition(A, b, restart, 1e-10, 200, M=lambda v: v * pinv)
+            assert (its, rs, conv) == (io["iterations"], io["restarts"], io["converged"]) and conv, (sub, restart)
+            assert abs(res - io["residual"]) <= 1e-3 * io["residual"]
+            assert np.linalg.norm(x - xo) <= 1e-10 * np.linalg.norm(xo)
