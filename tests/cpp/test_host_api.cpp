@@ -4,7 +4,7 @@
 //   math-solvers/src/iterative/gmres.rs:631-705          test_gmres_simple / test_gmres_identity
 //   math-bem/tests/test_fmm_validation.rs:537-700        test_gmres_with_operator / _restart_behavior
 //   math-solvers/src/iterative/bicgstab.rs:196-219       test_bicgstab_simple
-//   math-solvers/src/iterative/cgs.rs:164-185            test_cgs_simple
+//   math-solvers/src/iterative/cgs.rs:158-181            test_cgs_simple
 //   math-solvers/src/direct/lu.rs:178-219                test_lu_solve_complex / _identity / _singular
 //   math-bem/src/room_acoustics/solver.rs:1155-1170      test_greens_function / test_pressure_to_spl (room path smoke)
 // plus entry / solution parity against the CPU oracle (linked: oracle/_build/libbem_oracle.so) on a
@@ -318,7 +318,7 @@ int main() {
         CHECK(sb.converged && info.converged && sb.iterations == info.iterations);
         CHECK(std::sqrt(e1 / den) < 1e-8 && std::sqrt(e2 / den) < 1e-10);
         std::printf("bicgstab it=%zu dx=%.2e  lu dx=%.2e\n", sb.iterations, std::sqrt(e1 / den), std::sqrt(e2 / den));
-        // cgs.rs:164-185 test_cgs_simple, then the same 300 x 300 system against the oracle's cgs
+        // cgs.rs:158-181 test_cgs_simple, then the same 300 x 300 system against the oracle's cgs
         CgsSolution sc0 = cgs(op, b, CgsConfig{100, 1e-10, 0});
         CHECK(sc0.converged);
         std::vector<Complex64> axc = op.apply(sc0.x);

@@ -47,7 +47,7 @@ def test_cgs_kats_and_dense(bem, orc):
     (solve_cgs :360, solve_with_ilu :389 -- which runs unpreconditioned CGS -- solve_tbem_with_ilu :441)."""
     A = np.array([[4, 1], [1, 3]], dtype=np.complex128)
     b = np.array([1, 2], dtype=np.complex128)
-    sol = bem.cgs(bem.DenseOperator(A), b, bem.CgsConfig(100, 1e-10, 0))                 # cgs.rs:164-185
+    sol = bem.cgs(bem.DenseOperator(A), b, bem.CgsConfig(100, 1e-10, 0))                 # cgs.rs:158-181
     assert sol.converged and np.linalg.norm(A @ sol.x - b) < 1e-8
     z = bem.cgs(bem.DenseOperator(A), np.zeros(2, dtype=complex), bem.CgsConfig())
     assert z.converged and z.iterations == 0 and z.residual == 0.0 and not z.x.any()

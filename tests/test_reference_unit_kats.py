@@ -5,7 +5,7 @@ oracle and on the host-side mirror (CPU only):
     math-bem/src/core/types.rs:741-767               PhysicsParams::new, BoundaryCondition indices
     math-bem/src/core/mesh/element.rs:252-318        Tri3 shape functions, local_to_global, normal, area
     math-solvers/src/blas_helpers.rs:146-256         inner_product (conjugates x), vector_norm, axpy family
-    math-solvers/src/traits.rs:428-436               IdentityPreconditioner
+    math-solvers/src/traits.rs:428-435               IdentityPreconditioner
     math-solvers/src/preconditioners/diagonal.rs:105-145   DiagonalPreconditioner
 """
 import math
@@ -127,7 +127,7 @@ def test_inner_product_and_norms(orc):
     assert abs(orc.vector_norm(x) - np.linalg.norm(x)) < 1e-11
 
 
-# ---- traits.rs:428-436, diagonal.rs:105-145 --------------------------------------------------------
+# ---- traits.rs:428-435, diagonal.rs:105-145 --------------------------------------------------------
 def test_identity_and_diagonal_preconditioner(orc):
     r = np.array([1.0, 2.0, 3.0], dtype=np.complex128)
     z = bem.IdentityPreconditioner().apply(r)

@@ -32,7 +32,7 @@ def test_bicgstab_zero_rhs_and_budget(orc):
     assert abs(info["residual"] - np.linalg.norm(A @ x - b) / np.linalg.norm(b)) < 1e-12
 
 
-# ---- math-solvers/src/iterative/cgs.rs:157-186 -------------------------------------------------
+# ---- math-solvers/src/iterative/cgs.rs:151-182 -------------------------------------------------
 def test_cgs_simple(orc):
     A = np.array([[4, 1], [1, 3]], dtype=np.complex128)
     b = np.array([1, 2], dtype=np.complex128)
