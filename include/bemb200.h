@@ -241,7 +241,7 @@ int bemb200_gmres_device(const bemb200_matrix* m, const double* b_dev, const dou
  * borrows `a`), 1 factors in place (the handle then holds L\U).  factor_ms (may be NULL): device
  * time of the factorisation.  BEMB200_ESINGULAR = LuError::SingularMatrix. */
 int bemb200_lu_solve(const bemb200_matrix* m, const double* b, double* x_out, int overwrite_matrix, double* factor_ms);
-/* bicgstab (math-solvers/src/iterative/bicgstab.rs:53-215), the iterative solver of
+/* bicgstab (math-solvers/src/iterative/bicgstab.rs:46-187), the iterative solver of
  * BemSolver::solve_dense_system (bem_solver.rs:435-463): x0 = 0, two operator applications per
  * iteration, breakdown thresholds 1e-30, early exit on ||s||/||b|| < tol.  info->restarts = 0;
  * `converged` false on breakdown / stagnation / exhausted budget (the reference never errors). */

@@ -650,7 +650,7 @@ struct BiCgstabSolution {  // bicgstab.rs:40-50
     double residual = 0.0;
     bool converged = false;
 };
-inline BiCgstabSolution bicgstab(const DenseOperator& op, const std::vector<Complex64>& b, const BiCgstabConfig& config) {  // bicgstab.rs:53
+inline BiCgstabSolution bicgstab(const DenseOperator& op, const std::vector<Complex64>& b, const BiCgstabConfig& config) {  // bicgstab.rs:46
     if (b.size() != op.num_rows()) throw std::invalid_argument("bicgstab: vector length must match the operator");
     BiCgstabSolution s;
     s.x.resize(b.size());
@@ -793,7 +793,7 @@ struct LuError : std::runtime_error {  // lu.rs:15-21
     enum Kind { SingularMatrix, DimensionMismatch } kind;
     LuError(Kind k, const std::string& m) : std::runtime_error(m), kind(k) {}
 };
-// lu_solve(&a, &b) (lu.rs:136-161): `a` is left intact
+// lu_solve(&a, &b) (lu.rs:139-161): `a` is left intact
 inline std::vector<Complex64> lu_solve(const DenseOperator& a, const std::vector<Complex64>& b) {
     if (a.num_rows() != a.num_cols() || b.size() != a.num_rows())
         throw LuError(LuError::DimensionMismatch, "Matrix dimensions mismatch: expected " + std::to_string(a.num_rows()) + ", got " + std::to_string(b.size()));

@@ -836,7 +836,7 @@ class BiCgstabSolution:
 
 
 def bicgstab(operator: DenseOperator, b: np.ndarray, config: BiCgstabConfig) -> BiCgstabSolution:
-    """bicgstab.rs:53-215 on the device (x0 = 0; two ZGEMVs per iteration, fused vector kernels)."""
+    """bicgstab.rs:46-187 on the device (x0 = 0; two ZGEMVs per iteration, fused vector kernels)."""
     b = np.ascontiguousarray(b, dtype=np.complex128)
     if b.shape != (operator.num_rows(),):
         raise ValueError("b does not match the operator")
@@ -883,7 +883,7 @@ class LuError(RuntimeError):
 
 
 def lu_solve(a, b: np.ndarray, ctx: Optional[Context] = None, overwrite: bool = False, stats: Optional[dict] = None) -> np.ndarray:
-    """lu.rs:136-161 (LAPACK zgesv in the reference's native build) through cuSOLVER on the device.
+    """lu.rs:139-161 (LAPACK zgesv in the reference's native build) through cuSOLVER on the device.
     ``a``: host matrix, DeviceMatrix, TbemSystem or DenseOperator.  Raises LuError for a singular matrix /
     dimension mismatch."""
     if isinstance(a, DenseOperator):

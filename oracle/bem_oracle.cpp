@@ -1076,7 +1076,7 @@ void orc_inner_product(const double* x, const double* y, uint64_t n, double* out
 }
 double orc_vector_norm(const double* x, uint64_t n) { return vector_norm((const cplx*)x, n); }
 
-// ---- bicgstab: math-solvers/src/iterative/bicgstab.rs:53-215 on a dense row-major matrix ----
+// ---- bicgstab: math-solvers/src/iterative/bicgstab.rs:46-187 on a dense row-major matrix ----
 void orc_bicgstab(const double* A, uint64_t n, const double* b_in, uint32_t max_iterations, double tolerance, double* x_out,
                   orc_gmres_info* info, int nthreads) {
     const cplx* b = (const cplx*)b_in;
@@ -1148,7 +1148,7 @@ void orc_cgs(const double* A, uint64_t n, const double* b_in, uint32_t max_itera
     *info = {max_iterations, 0, vector_norm(r.data(), n) / b_norm, 0};
 }
 
-// ---- lu_solve: math-solvers/src/direct/lu.rs:136-161.  The default build (feature "native" =>
+// ---- lu_solve: math-solvers/src/direct/lu.rs:139-161.  The default build (feature "native" =>
 // `ndarray-linalg`, math-solvers/Cargo.toml:48-57) calls LAPACK zgesv (ndarray-linalg 0.18 / lax 0.18 /
 // OpenBLAS, not vendored): partial-pivoting LU + two triangular solves, restated here with the elimination
 // loop of the portable path (lu.rs:81-133).  returns 0, or 1 = LuError::SingularMatrix.

@@ -257,7 +257,7 @@ def vector_norm(x) -> float:
 
 
 def bicgstab(A, b, max_iterations=1000, tolerance=1e-6, nthreads=0):
-    """math-solvers/src/iterative/bicgstab.rs:53-215 on a dense row-major matrix -> (x, info dict)."""
+    """math-solvers/src/iterative/bicgstab.rs:46-187 on a dense row-major matrix -> (x, info dict)."""
     A = np.ascontiguousarray(A, dtype=np.complex128)
     b = np.ascontiguousarray(b, dtype=np.complex128)
     n = b.shape[0]
@@ -281,7 +281,7 @@ def cgs(A, b, max_iterations=1000, tolerance=1e-6, nthreads=0):
 
 
 def lu_solve(A, b):
-    """math-solvers/src/direct/lu.rs:136-161 -> x; raises np.linalg.LinAlgError for LuError::SingularMatrix."""
+    """math-solvers/src/direct/lu.rs:139-161 -> x; raises np.linalg.LinAlgError for LuError::SingularMatrix."""
     A = np.ascontiguousarray(A, dtype=np.complex128)
     b = np.ascontiguousarray(b, dtype=np.complex128)
     n = b.shape[0]

@@ -185,7 +185,7 @@ impl GpuDenseOperator {
             restarts: infos[s].restarts as usize, residual: infos[s].residual, converged: infos[s].converged != 0,
         }).collect()
     }
-    /// `bicgstab(operator, b, config)` (bicgstab.rs:53), the solver of `BemSolver::solve_dense_system`.
+    /// `bicgstab(operator, b, config)` (bicgstab.rs:46), the solver of `BemSolver::solve_dense_system`.
     pub fn bicgstab(&self, b: &Array1<Complex64>, config: &BiCgstabConfig<f64>) -> BiCgstabSolution<Complex64> {
         assert_eq!(b.len(), self.num_rows(), "Vector lengths must match");
         let mut x = Array1::<Complex64>::zeros(b.len());
@@ -206,7 +206,7 @@ impl GpuDenseOperator {
         assert_eq!(rc, 0, "libbemb200: {}", self.ctx.error());
         CgsSolution { x, iterations: info.iterations as usize, residual: info.residual, converged: info.converged != 0 }
     }
-    /// `lu_solve(&a, &b)` (direct/lu.rs:136): cuSOLVER zgetrf + zgetrs on a copy; `Err` = `LuError::SingularMatrix`.
+    /// `lu_solve(&a, &b)` (direct/lu.rs:142): cuSOLVER zgetrf + zgetrs on a copy; `Err` = `LuError::SingularMatrix`.
     pub fn lu_solve(&self, b: &Array1<Complex64>) -> Result<Array1<Complex64>, String> {
         if b.len() != self.num_rows() { return Err("Matrix dimensions mismatch".into()); }
         let mut x = Array1::<Complex64>::zeros(b.len());
